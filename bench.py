@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- ELBO forward+backward throughput of the gridded variational GP hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on; it fits one GPU): 2-D
+B1-spline ASVGP (GriddedMatern12ASVGP / Matern12B1SplineASVGP feature family), 512 x 512 grid of inducing
+variables, N = 2^26 synthetic along-track observations in acquisition order, float32 observations, float64
+grid side, full batch.  The observation axis is sharded over the ranks (total N fixed -> "strong" scaling); one
+step = grid forward + fused per-observation forward/backward + one all-reduce + grid backward, i.e. the ELBO and
+every gradient.  One JSON line is printed by rank 0.
+
+`--impl reference` times the reference's CPU algorithm (the structured torch restatement in oracle/, the only
+form of the reference's maths that can run at this size: SURVEY.md section 0 fact 5) on the host cores, on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "elbo_fwd_bwd_observations_per_sec"
+UNIT = "obs/s"
+N_TOTAL = 1 << 26
+KNOTS = (512, 512)
+PASSES = 1024          # ascending passes; as many descending ones (SURVEY.md section 8d, config 3 geometry)
+TRACK_GRADIENT = 2.0
+
+
+def workload_config(n_total, world, extra=None):
+    cfg = {
+        "workload": "configs[4]: 2-D B1-spline ASVGP, 512x512 inducing grid, N=2^26 synthetic along-track "
+                    "observations (acquisition order), fp32 observations / fp64 grid side, full batch",
+        "n_obs_total": n_total, "grid": list(KNOTS), "family": "B1_ASVGP", "obs_dtype": "float32",
+        "sharding": f"observation axis, {world} contiguous shard(s), one all-reduce(sum) of the gradient buffer",
+        "l2_policy": "inputs larger than L2 (805 MB of observations per step vs 126 MB L2); no explicit flush",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic satellite-track-shaped data (geometry of src/utils/dataloaders.py:290-377 generate_track)
+# ---------------------------------------------------------------------------------------------------------
+def field(x1, x2):
+    return (torch.sin(5 * x1) + torch.cos(7 * x2) + 0.5 * torch.sin(15 * x1) + 0.5 * torch.cos(12 * x2))
+
+
+def make_tracks(lo, hi, n_total, device, dtype, seed=0):
+    """Observations lo..hi-1 (global acquisition order) of the synthetic track data set."""
+    n = hi - lo
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 7919 + lo % 104729)
+    idx = torch.arange(lo, hi, device=device, dtype=torch.int64)
+    per_pass = max(1, n_total // (2 * PASSES))
+    j = torch.clamp(idx // per_pass, max=2 * PASSES - 1)
+    k = idx - j * per_pass
+    jitter = torch.rand(n, generator=g, device=device, dtype=torch.float64)
+    t = ((k.to(torch.float64) + jitter) / float(per_pass)).clamp_(0.0, 1.0)       # monotone along a pass
+    asc = j < PASSES
+    off = (j % PASSES).to(torch.float64) / PASSES
+    x1 = off + t / TRACK_GRADIENT
+    x1 = x1 - torch.floor(x1)
+    x2 = torch.where(asc, t, 1.0 - t)
+    y = field(x1, x2) + 0.05 * torch.randn(n, generator=g, device=device, dtype=torch.float64)
+    return [x1.to(dtype).contiguous(), x2.to(dtype).contiguous()], y.to(dtype).contiguous()
+
+
+def make_params(meshes, device, seed=1):
+    """theta (non_informative_initialise(lmbda=5, kappa=10)-style), m ~ 0.1 N(0,1), L_d = I + 0.1 tril N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    D = len(meshes)
+    Ms = [int(m.numel()) for m in meshes]
+    M = 1
+    for n in Ms:
+        M *= n
+    l = torch.full((D,), 0.2887 / 5.0, dtype=torch.float64)
+    s2 = torch.full((D,), 1.2, dtype=torch.float64)
+    noise = torch.tensor([1.2 / 100.0], dtype=torch.float64)
+    theta = torch.cat([l, s2, noise])
+    m = 0.1 * torch.randn(M, generator=g, dtype=torch.float64)
+    Ls = [torch.eye(n, dtype=torch.float64) + 0.1 * torch.tril(torch.randn(n, n, generator=g, dtype=torch.float64)) / math.sqrt(n)
+          for n in Ms]
+    return theta, m, Ls
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm, mx = [], []
+            reasons = set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for r in rows:
+                r = [c.strip() for c in r]
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                except Exception:
+                    continue
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                sm.sort()
+                out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's structured ELBO (float32 per-observation arithmetic) + autograd on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(n_sample, seed=0):
+    from oracle import vggp_oracle as O
+    meshes = [torch.linspace(0, 1, k) for k in KNOTS]
+    xs, y = make_tracks(0, n_sample, n_sample, torch.device("cpu"), torch.float32, seed)
+    X = torch.stack(xs, dim=1).to(torch.float64)
+    y = y.to(torch.float64)
+    theta, m, Ls = make_params(meshes, "cpu")
+    D = len(meshes)
+
+    def step():
+        l = theta[:D].clone().requires_grad_(True)
+        s2 = theta[D:2 * D].clone().requires_grad_(True)
+        nz = theta[2 * D].clone().requires_grad_(True)
+        mm = m.clone().requires_grad_(True)
+        LL = [L.clone().requires_grad_(True) for L in Ls]
+        elbo = O.elbo_structured(O.B1_ASVGP, meshes, X, y, l, s2, nz, mm, LL, ref_quirks=False,
+                                 work_dtype=torch.float32)
+        torch.autograd.grad(elbo, [l, s2, nz, mm] + LL)
+        return float(elbo.detach())
+
+    return step
+
+
+def time_cpu_baseline(budget_s=20.0, steps=3, warmup=1, n_cap=1 << 22):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 1 << 17
+    step = cpu_oracle_step_fn(n)
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    # grid-side cost is constant; scale the sample so that (steps + warmup) runs fit the budget
+    scale = max(1.0, budget_s / max(dt * (steps + warmup), 1e-3))
+    n_sample = int(min(n_cap, max(n, (1 << int(math.log2(n * scale))))))
+    if n_sample != n:
+        step = cpu_oracle_step_fn(n_sample)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n_sample / dt, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": f"{n_sample} observations of the same track workload on the full 512x512 grid, fp32 "
+                      f"per-observation arithmetic, {steps} timed fwd+bwd steps after {warmup} warm-up "
+                      f"({dt * 1e3:.1f} ms/step), torch CPU + autograd",
+            "ms_per_step": dt * 1e3, "n_sample": n_sample}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: calibrate on 2^17 observations, then size the sample so the whole run ends in ~2 minutes
+    n = 1 << 17
+    step = cpu_oracle_step_fn(n)
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    total = args.steps + args.warmup
+    scale = max(1.0, 120.0 / max(dt * total, 1e-3))
+    n_sample = int(min(1 << 22, max(n, 1 << int(math.log2(n * scale)))))
+    if n_sample != n:
+        step = cpu_oracle_step_fn(n_sample)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = n_sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(N_TOTAL, world, {"cpu_sample_obs": n_sample}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
+                         "sample": f"{n_sample} observations per step (bounded sample of the 2^26 workload), full "
+                                   f"512x512 grid, structured torch-CPU restatement of the reference maths + autograd"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import vggp_b200 as vg
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    lib = vg._lib.load()
+
+    n_total = int(args.n_obs)
+    lo, hi = vg.shard_bounds(n_total, rank, world)
+    n_local = hi - lo
+    dtype = torch.float32
+    meshes = [torch.linspace(0, 1, k) for k in KNOTS]
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, device)
+    xs, y = make_tracks(lo, hi, n_total, device, dtype)
+    theta, m, Ls = make_params(meshes, device)
+    theta_d = theta.to(device)
+    m_d = m.to(device)
+    L_d = torch.cat([L.reshape(-1) for L in Ls]).to(device).contiguous()
+    group = "world" if world > 1 else None
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        plan.grid_forward(theta_d, m_d, L_d)
+        if i is not None:
+            ev_a[i].record()
+        plan.obs_fwd_bwd(xs, y)
+        if i is not None:
+            ev_b[i].record()
+        if group is not None:
+            plan.allreduce_gbuf(None)
+        return plan.grid_backward(theta_d, m_d, L_d, 1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    if plan.read_info() != 0:
+        raise SystemExit("factorisation failed in the bench configuration")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.vggp_launch_count()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        out = step(i)
+    t_end.record()
+    barrier()
+    launches = lib.vggp_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    k1_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps
+    tt = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = tt[0].item() / args.steps
+    k1_ms = tt[1].item()
+    value = n_total / (ms_step * 1e-3)
+
+    # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        xs_h = [x.cpu().pin_memory() for x in xs]
+        y_h = y.cpu().pin_memory()
+        th_h, m_h, L_h = theta.pin_memory(), m.pin_memory(), torch.cat([L.reshape(-1) for L in Ls]).pin_memory()
+        D = len(meshes)
+        out_h = torch.empty(4, dtype=torch.float64).pin_memory()
+        dth_h = torch.empty(2 * D + 1, dtype=torch.float64).pin_memory()
+        dm_h = torch.empty(plan.M, dtype=torch.float64).pin_memory()
+        dL_h = torch.empty(plan.L_total, dtype=torch.float64).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in xs_h + [y_h, th_h, m_h, L_h])
+        d2h = sum(t.numel() * t.element_size() for t in (out_h, dth_h, dm_h, dL_h))
+        import ctypes as C
+        stream = torch.cuda.current_stream(device).cuda_stream
+
+        def e2e_step():
+            if world == 1:
+                ptrs = (C.c_void_p * D)(*[t.data_ptr() for t in xs_h])
+                vg._lib.check(lib.vggp_elbo_host(plan.handle, ptrs, y_h.data_ptr(), n_local, th_h.data_ptr(),
+                                                 m_h.data_ptr(), L_h.data_ptr(), 1.0, out_h.data_ptr(),
+                                                 dth_h.data_ptr(), dm_h.data_ptr(), dL_h.data_ptr(), stream))
+            else:
+                for dst, src in zip(xs + [y], xs_h + [y_h]):
+                    dst.copy_(src, non_blocking=True)
+                theta_d.copy_(th_h, non_blocking=True)
+                m_d.copy_(m_h, non_blocking=True)
+                L_d.copy_(L_h, non_blocking=True)
+                o, dth, dm, dL = step()
+                out_h.copy_(o, non_blocking=True)
+                dth_h.copy_(dth, non_blocking=True)
+                dm_h.copy_(dm, non_blocking=True)
+                dL_h.copy_(dL, non_blocking=True)
+                torch.cuda.synchronize()
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
+               "path": "vggp_elbo_host (C ABI, pinned host buffers)" if world == 1 else
+                       "pinned host -> device copies + plan.step + device -> host of ELBO and gradients"}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg_bytes = n_local * (len(KNOTS) + 1) * 4 + 2 * plan.M * 4
+        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n_total, world, {"n_obs_per_gpu": n_local}),
+            "elbo": out[0].item(),
+            "roofline": {"bound": "hbm", "kernel": "k_obs_b1 (fused per-observation ELBO forward+backward)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": k1_ms,
+                         "algorithmic_bytes": alg_bytes,
+                         "share_of_step": k1_ms / ms_step},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = time_cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/*
+ * vggp.h -- C ABI of libvggp.so: the sm_100a ELBO forward/backward hot path for variational Gaussian
+ * processes with gridded (Kronecker-structured) inducing variables.
+ *
+ * This is the drop-in boundary.  The reference (maxnorman569/Variational-Gridded-Gaussian-Processes) is pure
+ * Python and has no FFI; the entry points below are what a ctypes binding placed inside the reference's
+ * model classes would call instead of the dense torch code:
+ *
+ *   reference code replaced                                            entry point
+ *   ------------------------------------------------------------------ ---------------------------------
+ *   src/basis/bspline.py:92-94   SplineBasis.__call__ (B1 hats)         vggp_b1_stencil / vggp_b1_features_dense
+ *   src/models/sparse/gridded_kronecker_structure.py:1325-1374          vggp_b0_features_dense
+ *        _Kuf_along_dim (cell-integrated Matern-1/2 features)
+ *   gridded_kronecker_structure.py:731-780, 1286-1323 _Kuu_along_dim    vggp_grid_forward (factor build)
+ *   gridded_kronecker_structure.py:796-811, 1376-1390 _Kuu (torch.kron) vggp_grid_forward (never formed:
+ *        + kronecker_structure.py:265-269 lazify(Kuu).inv_matmul         per-dimension Cholesky, inverse and
+ *                                                                        Kronecker mode-n products instead)
+ *   gridded_kronecker_structure.py:813-828, 1392-1407 _Kuf (Khatri-Rao) vggp_obs_fwd_bwd (never formed:
+ *        + kronecker_structure.py:249-278 _elbo (N x N algebra)          per-observation fused kernel)
+ *   elbow.backward()  (5_gridded_kronecker_structure_models.ipynb:445)  vggp_obs_fwd_bwd + vggp_grid_backward
+ *   whole step with host buffers                                        vggp_elbo_host
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = invalid argument (VGGP_E_*), > 0 = a cudaError_t value;
+ *     vggp_last_error() returns a static/thread-local message for the last non-zero status.
+ *   - all work is asynchronous and ordered on the `stream` argument (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream).  No entry point except vggp_plan_create/destroy, vggp_read_info and
+ *     vggp_elbo_host synchronises the host.
+ *   - the caller owns every buffer passed in; the library allocates only inside vggp_plan_create (its
+ *     grid-side workspace) and frees it in vggp_plan_destroy.
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - grid-side quantities (theta, m, L_d, their gradients, the ELBO) are always float64.  Observations,
+ *     alpha as seen by the per-observation kernel and the per-observation gradient buffer use the plan's
+ *     `obs_dtype` (VGGP_F32 or VGGP_F64).
+ *   - index convention: flat inducing index u = ((i_1*M_2 + i_2)*M_3 + i_3), matching torch.kron(K_1, K_2)
+ *     (gridded_kronecker_structure.py:1389) and the Khatri-Rao loop order (:1406).
+ */
+#ifndef VGGP_H
+#define VGGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGGP_MAX_D 3
+
+/* feature family */
+#define VGGP_B1_ASVGP   0   /* B1-spline (hat) features, tridiagonal RKHS Kuu: GriddedMatern12ASVGP, Matern12B1SplineASVGP */
+#define VGGP_B0_GRIDDED 1   /* cell-integrated Matern-1/2 features, Toeplitz Kuu: Matern12GriddedGP, Matern12B0SplineGriddedGP */
+
+/* observation dtype */
+#define VGGP_F32 0
+#define VGGP_F64 1
+
+/* status codes (< 0) */
+#define VGGP_E_ARG        -1
+#define VGGP_E_FAMILY     -2
+#define VGGP_E_DTYPE      -3
+#define VGGP_E_DIM        -4
+#define VGGP_E_NOMEM      -5
+#define VGGP_E_UNSUPPORTED -6
+
+typedef struct vggp_plan vggp_plan;
+
+/* ABI version of this header; vggp_abi_version() must return the same value. */
+#define VGGP_ABI_VERSION 1
+int vggp_abi_version(void);
+const char* vggp_last_error(void);
+/* Number of CUDA kernels this library has launched so far in this process (host-side counter). */
+uint64_t vggp_launch_count(void);
+
+/*
+ * Plan = grid descriptor + workspace, one per (model, device).
+ *   family      VGGP_B1_ASVGP | VGGP_B0_GRIDDED
+ *   D           number of input dimensions, 1..VGGP_MAX_D
+ *   n_knots     [D] number of knots of each per-dimension mesh (B1: M_d = n_knots, B0: M_d = n_knots-1)
+ *   knots_host  [D] host pointers to the float32 knot arrays, exactly as the reference builds them
+ *               (torch.linspace without dtype, gridded_kronecker_structure.py:707-720, 1278-1279).  Knots are
+ *               never regenerated on the device.
+ *   obs_dtype   VGGP_F32 | VGGP_F64
+ *   device      CUDA device ordinal
+ */
+int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots,
+                     const float* const* knots_host, int obs_dtype, int device);
+int vggp_plan_destroy(vggp_plan* plan);
+
+/* M_d (inducing variables per dimension) and M = prod M_d. */
+int vggp_plan_dims(const vggp_plan* plan, int* D, int* m_per_dim /*[D]*/, int64_t* M);
+
+/*
+ * Layout of the per-observation gradient buffer (`gbuf`) written by vggp_obs_fwd_bwd and all-reduced (sum)
+ * across ranks before vggp_grid_backward:
+ *     [ n_obs_elems values of obs_dtype | pad to 8 bytes | n_scalars float64 ]
+ *   n_obs_elems = M (d alpha) + per-dimension band / factor-gradient blocks
+ *   scalars     = { sum_n (r_n^2 - prod p + prod q), n_local, n_inside, reserved... }
+ * `scalar_offset_bytes` is the byte offset of the float64 block, `total_bytes` the size to allocate.
+ */
+int vggp_gbuf_layout(const vggp_plan* plan, int64_t* n_obs_elems, int64_t* scalar_offset_bytes,
+                     int64_t* n_scalars, int64_t* total_bytes);
+
+/*
+ * Grid-side forward: build K_d(theta), Cholesky, P_d = K_d^-1, R_d = P_d tril(L_d), Q_d = R_d R_d^T, S_d,
+ * alpha = (kron_d P_d) m through mode-n products, the band tables the per-observation kernel reads, and the
+ * KL ingredients (log-dets, traces, <m, alpha>).  Everything stays in the plan workspace.
+ *   theta  [2D+1] float64: lengthscale_1..D, outputscale_1..D, noise   (constrained values)
+ *   m      [M]    float64 variational mean (u-space, unwhitened; prior N(0, Kuu))
+ *   L      [sum_d M_d^2] float64, the D row-major M_d x M_d factors back to back; lower triangle is used,
+ *          S = kron_d L_d L_d^T
+ */
+int vggp_grid_forward(vggp_plan* plan, const double* theta, const double* m, const double* L, void* stream);
+
+/*
+ * Per-observation fused forward+backward over one shard of the minibatch.
+ *   x      [D] HOST array of device pointers, x[d] -> n values of obs_dtype (structure of arrays)
+ *   y      n values of obs_dtype
+ *   n      number of observations in this shard (may be 0)
+ *   gbuf   output, layout above; zeroed by this call, then accumulated.
+ * Reads alpha / band tables produced by the last vggp_grid_forward on the same plan.
+ */
+int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream);
+
+/*
+ * Grid-side backward + ELBO assembly from the (all-reduced) gbuf.
+ *   ell_scale   N / B minibatch scaling of the expected log-likelihood (1 for full batch)
+ *   out    [4]    float64: ELBO, ell_scale * ELL, KL, n_obs(all ranks)
+ *   dtheta [2D+1] float64 d ELBO / d theta (constrained values)
+ *   dm     [M]    float64
+ *   dL     [sum_d M_d^2] float64 (strictly-upper triangles are zero)
+ */
+int vggp_grid_backward(vggp_plan* plan, const double* theta, const double* m, const double* L,
+                       const void* gbuf, double ell_scale,
+                       double* out, double* dtheta, double* dm, double* dL, void* stream);
+
+/* Failed-factorisation flag of the last forward (0 = ok, d+1 = factor d not positive definite).
+ * Synchronises `stream`. */
+int vggp_read_info(vggp_plan* plan, int* info_host, void* stream);
+
+/*
+ * Whole step through HOST buffers (the call a ctypes binding inside the reference's `_elbo` would make):
+ * copies x/y/theta/m/L host->device into plan-owned staging buffers (grown on demand, the only call that
+ * may allocate after plan creation), runs forward + per-observation + backward on `stream`, copies
+ * out/dtheta/dm/dL back and synchronises.
+ */
+int vggp_elbo_host(vggp_plan* plan, const void* const* x_host, const void* y_host, int64_t n,
+                   const double* theta_host, const double* m_host, const double* L_host, double ell_scale,
+                   double* out_host, double* dtheta_host, double* dm_host, double* dL_host, void* stream);
+
+/* ---- feature evaluation (bit-exact restatement of the reference's basis calls) ------------------------- */
+
+/* B1 stencil of dimension `dim`: for each x[n], c[n] (int32; -1 = outside the mesh), w_lo[n], w_hi[n] such
+ * that column n of B1SplineBasis(mesh)(x) (bspline.py:92-94) has w_lo at row c, w_hi at row c+1. */
+int vggp_b1_stencil(const vggp_plan* plan, int dim, const void* x, int64_t n,
+                    int32_t* c, void* w_lo, void* w_hi, void* stream);
+
+/* Dense (M_d, n) row-major feature matrix of dimension `dim`, numerically equal to the reference's
+ * `_Kuf_along_dim` for the plan's family (B0 family needs theta for lengthscale/outputscale). */
+int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n, const double* theta,
+                        void* phi, void* stream);
+
+/* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
+
+/* Device pointer to a float64 workspace array of the last forward.  which: */
+#define VGGP_WS_K      0   /* Cholesky factor C_d of K_d (lower; upper triangle undefined) */
+#define VGGP_WS_P      1   /* P_d = K_d^-1 */
+#define VGGP_WS_R      2   /* R_d = P_d tril(L_d) */
+#define VGGP_WS_Q      3   /* Q_d = R_d R_d^T */
+#define VGGP_WS_S      4   /* S_d = tril(L_d) tril(L_d)^T */
+#define VGGP_WS_ALPHA  5   /* alpha (M), dim ignored */
+#define VGGP_WS_SCAL   6   /* scalars: logdet K_d [3], logdet S_d [3], tr(P_d S_d) [3], <m,alpha> */
+#define VGGP_WS_KRAW   7   /* K_d as built (before factorisation) */
+int vggp_workspace_ptr(const vggp_plan* plan, int which, int dim, double** ptr, int64_t* n_elems);
+
+/* Batched strided float64 GEMM on the tensor cores (DMMA m8n8k4) or the SIMT fallback used to cross-check it:
+ *   C[b] = alpha * A[b] * B[b] + beta * C[b],  A: m x k, B: k x n, element (i,j) of X at X + b*bsX + i*rsX + j*csX */
+int vggp_gemm_f64(int use_mma, int batch, int m, int n, int k, double alpha,
+                  const double* A, int64_t rsA, int64_t csA, int64_t bsA,
+                  const double* B, int64_t rsB, int64_t csB, int64_t bsB,
+                  double beta, double* C, int64_t rsC, int64_t csC, int64_t bsC, int splitk, void* stream);
+
+/* Apply a dense (M_d x M_d, row-major) matrix along mode `dim` of the M-tensor `src` -> `dst` (float64). */
+int vggp_mode_product(vggp_plan* plan, int dim, const double* A, const double* src, double* dst, void* stream);
+
+/* Select the GEMM inner loop used by the grid-side path: 1 = DMMA tensor cores (default), 0 = SIMT. */
+int vggp_set_gemm_mode(int use_mma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGGP_H */

@@ -1,0 +1,233 @@
+"""GPU parity of the fused ELBO forward/backward against the structured CPU oracle (oracle/vggp_oracle.py,
+itself pinned to the reference by tests/test_oracle_golden.py and tests/test_oracle_identities.py).
+
+Tolerances (BASELINE.json north_star): float64 observations 1e-5 relative (we assert much tighter), float32
+observations 1e-3 relative; gradients are compared in the norm of each parameter block."""
+import importlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vggp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vg():
+    import vggp_b200
+    vggp_b200._lib.load()
+    return vggp_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def make_problem(knots, N, seed, family=O.B1_ASVGP, x_lo=-0.05, x_hi=1.05):
+    D = len(knots)
+    g = torch.Generator().manual_seed(seed)
+    meshes = [torch.linspace(0, 1, k) for k in knots]
+    X = torch.rand(N, D, generator=g, dtype=torch.float64) * (x_hi - x_lo) + x_lo
+    # a few observations exactly on knots / boundaries
+    for d in range(D):
+        X[d::97, d] = meshes[d][(torch.arange(len(X[d::97, d])) * 3) % knots[d]].to(torch.float64)
+    y = torch.sin(3 * X[:, 0]) + (torch.cos(5 * X[:, -1]) if D > 1 else 0) + 0.1 * torch.randn(N, generator=g, dtype=torch.float64)
+    l = torch.rand(D, generator=g, dtype=torch.float64) * 0.4 + 0.2
+    s2 = torch.rand(D, generator=g, dtype=torch.float64) * 0.8 + 0.6
+    noise = torch.tensor(0.07, dtype=torch.float64)
+    Ms = [O.n_inducing(family, m) for m in meshes]
+    M = int(np.prod(Ms))
+    m = torch.randn(M, generator=g, dtype=torch.float64) * 0.2
+    Ls = [torch.eye(n, dtype=torch.float64) * 0.6 + 0.05 * torch.randn(n, n, generator=g, dtype=torch.float64) for n in Ms]
+    return meshes, X, y, l, s2, noise, m, Ls
+
+
+def oracle_value_and_grads(family, meshes, X, y, l, s2, noise, m, Ls, scale=1.0):
+    l = l.clone().requires_grad_(True)
+    s2 = s2.clone().requires_grad_(True)
+    noise = noise.clone().requires_grad_(True)
+    m = m.clone().requires_grad_(True)
+    Ls = [L.clone().requires_grad_(True) for L in Ls]
+    elbo = O.elbo_structured(family, meshes, X, y, l, s2, noise, m, Ls, ref_quirks=False, scale=scale)
+    grads = torch.autograd.grad(elbo, [l, s2, noise, m] + Ls)
+    return elbo.detach(), grads
+
+
+def relerr(a, b):
+    a = a.detach().cpu().to(torch.float64).reshape(-1)
+    b = b.detach().cpu().to(torch.float64).reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+CASES = [
+    # knots, N
+    ((12,), 700),
+    ((9, 7), 900),
+    ((70, 13), 5000),
+    ((6, 66, 5), 4000),
+    ((130, 9), 3000),
+]
+
+
+@pytest.mark.parametrize("knots,N", CASES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
+def test_elbo_and_grads_match_oracle_b1(vg, dev, knots, N, dtype, tol):
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=42 + D)
+    Xq = X.to(dtype)          # quantise the observations once so oracle and kernel see identical inputs
+    yq = y.to(dtype)
+    scale = 1.7
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=scale)
+    assert plan.read_info() == 0
+    assert out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (out.cpu(), elbo_ref)
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10, ("dl", dtheta[:D].cpu(), g_ref[0])
+    assert relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10, ("ds2", dtheta[D:2 * D].cpu(), g_ref[1])
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10, ("dnoise", dtheta[2 * D].cpu(), g_ref[2])
+    assert relerr(dm, g_ref[3]) < tol * 10, "dm"
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n).cpu()
+        off += n * n
+        assert torch.count_nonzero(torch.triu(dLd, 1)) == 0
+        assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
+
+
+def test_simt_and_dmma_paths_agree(vg, dev):
+    knots, N = (40, 33), 2000
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [X[:, d].contiguous().to(dev) for d in range(2)]
+    res = []
+    try:
+        for mode in (1, 0):
+            vg._lib.load().vggp_set_gemm_mode(mode)
+            out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, y.to(dev))
+            res.append((out.clone(), dtheta.clone(), dm.clone(), dL.clone()))
+    finally:
+        vg._lib.load().vggp_set_gemm_mode(1)
+    for a, b in zip(res[0], res[1]):
+        assert relerr(a, b) < 1e-10
+
+
+def test_all_observations_outside_the_mesh(vg, dev):
+    meshes = [torch.linspace(0, 1, 8), torch.linspace(0, 1, 6)]
+    N = 300
+    X = torch.rand(N, 2, dtype=torch.float64) + 2.0
+    y = torch.randn(N, dtype=torch.float64)
+    _, _, _, l, s2, noise, m, Ls = make_problem((8, 6), 10, seed=1)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, [X[:, 0].contiguous().to(dev), X[:, 1].contiguous().to(dev)], y.to(dev))
+    assert abs(out[0].item() - elbo_ref.item()) < 1e-9 * abs(elbo_ref.item())
+    assert relerr(dm, g_ref[3]) < 1e-8
+
+
+def test_empty_shard(vg, dev):
+    # n = 0 observations: ELBO = -KL, gradients finite
+    meshes, X, y, l, s2, noise, m, Ls = make_problem((9, 7), 10, seed=2)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, X[:0], y[:0], l, s2, noise, m, Ls)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    e = torch.empty(0, dtype=torch.float64, device=dev)
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, [e, e], e)
+    assert abs(out[0].item() - elbo_ref.item()) < 1e-9 * abs(elbo_ref.item())
+    assert abs(out[0].item() + out[2].item()) < 1e-9 * abs(out[2].item())
+    assert relerr(dm, g_ref[3]) < 1e-8
+
+
+def test_linearity_in_shards(vg, dev):
+    """Size-independent property: the gradient buffer of a data set is the sum of the buffers of its shards
+    (this is what the all-reduce relies on)."""
+    meshes, X, y, l, s2, noise, m, Ls = make_problem((33, 21), 20000, seed=9)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    plan.grid_forward(theta, m.to(dev), Lcat)
+    xs = [X[:, d].contiguous().to(dev) for d in range(2)]
+    yd = y.to(dev)
+    plan.obs_fwd_bwd(xs, yd)
+    full = plan.gbuf.clone().view(torch.float64)
+    acc = torch.zeros_like(full)
+    for lo, hi in ((0, 7000), (7000, 7001), (7001, 20000)):
+        plan.obs_fwd_bwd([x[lo:hi].contiguous() for x in xs], yd[lo:hi].contiguous())
+        acc += plan.gbuf.view(torch.float64)
+    assert relerr(acc, full) < 1e-12
+
+
+def _model_module(name):
+    return importlib.import_module(f"variational-gridded-gaussian-processes_b200.models.sparse.{name}")
+
+
+def test_model_class_training_loop_api(vg, dev):
+    """Drop-in API: constructor signature, .to(float64), parameters(), -_elbo().backward(), Adam step; ELBO and raw
+    parameter gradients against the oracle with the same softplus parameterisation."""
+    gks = _model_module("gridded_kronecker_structure")
+    g = torch.Generator().manual_seed(0)
+    N = 625
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(5 * X[:, 0]) + torch.cos(7 * X[:, 1]) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    model = gks.GriddedMatern12ASVGP(X, y, 10, 1, (0, 1), (0, 1)).to(torch.float64).to(dev)
+    names = [n for n, _ in model.named_parameters()]
+    for want in ("likelihood.noise_covar.raw_noise", "kernel_1.raw_outputscale", "kernel_1.base_kernel.raw_lengthscale",
+                 "kernel_2.raw_outputscale", "kernel_2.base_kernel.raw_lengthscale", "variational_mean",
+                 "variational_chol_1", "variational_chol_2"):
+        assert want in names
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.1, generator=None)
+        model.kernel_1.base_kernel.lengthscale = 0.4
+        model.likelihood.noise = 0.05
+    assert abs(model.kernel_1.base_kernel.lengthscale.item() - 0.4) < 1e-12
+    elbo = model._elbo()
+    assert elbo.dim() == 0 and elbo.requires_grad
+    (-elbo).backward()
+    # oracle with raw parameters
+    raw_l = torch.stack([model.kernel_1.base_kernel.raw_lengthscale.detach().cpu().reshape(()),
+                         model.kernel_2.base_kernel.raw_lengthscale.detach().cpu().reshape(())]).requires_grad_(True)
+    raw_s = torch.stack([model.kernel_1.raw_outputscale.detach().cpu(), model.kernel_2.raw_outputscale.detach().cpu()]).requires_grad_(True)
+    raw_n = model.likelihood.noise_covar.raw_noise.detach().cpu().reshape(()).requires_grad_(True)
+    l, s2, noise = O.constrain(raw_l, raw_s, raw_n)
+    meshes = [O.make_padded_mesh(0, 1, 10, 1)] * 2
+    m = model.variational_mean.detach().cpu()
+    Ls = [model.variational_chol_1.detach().cpu(), model.variational_chol_2.detach().cpu()]
+    ref = O.elbo_structured(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls, ref_quirks=False)
+    gl, gs, gn = torch.autograd.grad(-ref, [raw_l, raw_s, raw_n])
+    assert abs(elbo.item() - ref.item()) < 1e-9 * abs(ref.item())
+    assert abs(model.kernel_1.base_kernel.raw_lengthscale.grad.item() - gl[0].item()) < 1e-7 * abs(gl[0].item())
+    assert abs(model.kernel_2.raw_outputscale.grad.item() - gs[1].item()) < 1e-7 * abs(gs[1].item())
+    assert abs(model.likelihood.noise_covar.raw_noise.grad.item() - gn.item()) < 1e-7 * abs(gn.item())
+    # a few Adam steps must increase the bound
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    first = None
+    for it in range(15):
+        opt.zero_grad()
+        loss = -model._elbo()
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    assert (-model._elbo()).item() < first
+
+
+def test_model_refuses_cpu(vg):
+    ks = _model_module("kronecker_structure")
+    X = torch.rand(10, 2, dtype=torch.float64)
+    y = torch.rand(10, dtype=torch.float64)
+    model = ks.Matern12B1SplineASVGP(X, y, 5, (0, 1), (0, 1))
+    with pytest.raises(RuntimeError):
+        model._elbo()

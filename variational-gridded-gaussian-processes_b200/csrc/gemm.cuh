@@ -1,0 +1,220 @@
+// Grouped / batched / strided float64 GEMM for the grid-side algebra (Kronecker mode-n products, factor
+// products, Cholesky trailing updates, triangular-inverse recursion).
+//
+// One launch = a group of independent problems described by GemmDesc records in device memory; blockIdx.z
+// walks (problem, batch entry, k-split).  The inner loop is the FP64 tensor-core instruction
+// mma.sync.aligned.m8n8k4.f64 (tcgen05 has no f64 kind); a SIMT inner loop is kept only to cross-check it
+// in the tests.
+#pragma once
+#include "common.cuh"
+
+namespace vggp {
+
+struct GemmDesc {
+    const double* A;
+    const double* B;
+    double* C;
+    int m, n, k;
+    i64 rsA, csA, rsB, csB, rsC, csC;
+    int kinner;          // 0: plain k addressing; else k = ko*kinner + ki with ko using koA/koB
+    i64 koA, koB;
+    double alpha, beta;
+    int batch;
+    i64 bsA, bsB, bsC;
+    int splitk;          // > 1: partial sums are atomically added into C (C must already hold beta*C)
+    int lower_only;      // skip output tiles strictly above the diagonal
+    int a_mfast, b_kfast;  // which index is contiguous in memory (coalescing of the tile loads)
+    int zstart;          // first blockIdx.z of this problem (filled by gemm_finalize_group)
+    int tiles_m, tiles_n;
+};
+
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+constexpr int GEMM_THREADS_MMA = 128, GEMM_THREADS_SIMT = 256;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void gemm_store(const GemmDesc& d, double* __restrict__ Cb, int row, int col, double v) {
+    if (row >= d.m || col >= d.n) return;
+    double* p = Cb + (i64)row * d.rsC + (i64)col * d.csC;
+    if (d.splitk > 1) {
+        atomicAdd(p, d.alpha * v);
+    } else {
+        double r = d.alpha * v;
+        if (d.beta != 0.0) r += d.beta * (*p);
+        *p = r;
+    }
+}
+
+template <bool MMA>
+__device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As)[GBK + 4], double (*Bs)[GBN + 4]) {
+    const int tid = threadIdx.x;
+    constexpr int nthreads = MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT;
+    const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+    if (tile_m >= d.tiles_m || tile_n >= d.tiles_n) return;
+    const int m0 = tile_m * GBM, n0 = tile_n * GBN;
+    if (d.lower_only && n0 >= m0 + GBM) return;
+    const int split = zz % d.splitk;
+    const int b = zz / d.splitk;
+    int kbeg = 0, kend = d.k;
+    if (d.splitk > 1) {
+        const int kchunk = ((d.k + d.splitk - 1) / d.splitk + GBK - 1) / GBK * GBK;
+        kbeg = split * kchunk;
+        kend = min(d.k, kbeg + kchunk);
+        if (kbeg >= kend) return;
+    }
+    const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
+    const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
+    double* __restrict__ Cb = d.C + (i64)b * d.bsC;
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // MMA: 4 warps as 2 x 2, 32 x 32 each
+    const int ty = tid >> 4, tx = tid & 15;                  // SIMT: 16 x 16 threads, 4 x 4 each
+
+    double acc[4][4][MMA ? 2 : 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < (MMA ? 2 : 1); ++c) acc[i][j][c] = 0.0;
+
+    for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+        // ---- stage the A (GBM x GBK) and B (GBK x GBN) tiles (zero-filled at the edges) ----
+        for (int e = tid; e < GBM * GBK; e += nthreads) {
+            int mm, kk;
+            if (d.a_mfast) { mm = e % GBM; kk = e / GBM; } else { kk = e % GBK; mm = e / GBK; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            double v = 0.0;
+            if (gm < d.m && gk < kend) {
+                i64 off = (i64)gm * d.rsA;
+                off += d.kinner ? (i64)(gk / d.kinner) * d.koA + (i64)(gk % d.kinner) * d.csA : (i64)gk * d.csA;
+                v = __ldg(Ab + off);
+            }
+            As[mm][kk] = v;
+        }
+        for (int e = tid; e < GBK * GBN; e += nthreads) {
+            int nn, kk;
+            if (d.b_kfast) { kk = e % GBK; nn = e / GBK; } else { nn = e % GBN; kk = e / GBN; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            double v = 0.0;
+            if (gn < d.n && gk < kend) {
+                i64 off = (i64)gn * d.csB;
+                off += d.kinner ? (i64)(gk / d.kinner) * d.koB + (i64)(gk % d.kinner) * d.rsB : (i64)gk * d.rsB;
+                v = __ldg(Bb + off);
+            }
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+        if constexpr (MMA) {
+#pragma unroll
+            for (int ks = 0; ks < GBK / 4; ++ks) {
+                double a[4], bb[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = As[wm + mi * 8 + g][ks * 4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) bb[ni] = Bs[ks * 4 + t][wn + ni * 8 + g];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < GBK; ++kk) {
+                double a[4], bb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][kk];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][0] = fma(a[i], bb[j], acc[i][j][0]);
+            }
+        }
+        __syncthreads();
+    }
+
+    if constexpr (MMA) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int row = m0 + wm + mi * 8 + g;
+                const int col = n0 + wn + ni * 8 + t * 2;
+                gemm_store(d, Cb, row, col, acc[mi][ni][0]);
+                gemm_store(d, Cb, row, col + 1, acc[mi][ni][1]);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gemm_store(d, Cb, m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j][0]);
+    }
+}
+
+// Group launch: descriptors live in device memory (built once at plan creation).
+template <bool MMA>
+__global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
+k_gemm_group(const GemmDesc* __restrict__ descs, int ndesc) {
+    __shared__ double As[GBM][GBK + 4];
+    __shared__ double Bs[GBK][GBN + 4];
+    __shared__ GemmDesc sd;
+    const int z = blockIdx.z;
+    int p = 0;
+    for (int i = 1; i < ndesc; ++i)
+        if (z >= descs[i].zstart) p = i;
+    if (threadIdx.x == 0) sd = descs[p];
+    __syncthreads();
+    gemm_body<MMA>(sd, z - sd.zstart, As, Bs);
+}
+
+// Single ad-hoc problem passed by value (tests, vggp_gemm_f64, vggp_mode_product).
+template <bool MMA>
+__global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
+k_gemm_one(const __grid_constant__ GemmDesc d) {
+    __shared__ double As[GBM][GBK + 4];
+    __shared__ double Bs[GBK][GBN + 4];
+    gemm_body<MMA>(d, blockIdx.z, As, Bs);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+struct GemmGroupDims {
+    int gx, gy, gz;
+};
+
+inline void gemm_desc_defaults(GemmDesc& d) {
+    memset(&d, 0, sizeof(d));
+    d.alpha = 1.0;
+    d.beta = 0.0;
+    d.batch = 1;
+    d.splitk = 1;
+}
+
+// Fill the derived fields of a group of descriptors (zstart, tile counts, coalescing hints).
+inline GemmGroupDims gemm_finalize_group(GemmDesc* descs, int ndesc) {
+    GemmGroupDims g = {0, 0, 0};
+    int z = 0;
+    for (int i = 0; i < ndesc; ++i) {
+        GemmDesc& d = descs[i];
+        d.tiles_m = (d.m + GBM - 1) / GBM;
+        d.tiles_n = (d.n + GBN - 1) / GBN;
+        d.a_mfast = (d.rsA == 1 && d.csA != 1) ? 1 : 0;
+        d.b_kfast = (d.rsB == 1 && d.csB != 1) ? 1 : 0;
+        if (d.splitk < 1) d.splitk = 1;
+        if (d.batch < 1) d.batch = 1;
+        d.zstart = z;
+        z += d.batch * d.splitk;
+        if (d.tiles_n > g.gx) g.gx = d.tiles_n;
+        if (d.tiles_m > g.gy) g.gy = d.tiles_m;
+    }
+    g.gz = z;
+    return g;
+}
+
+}  // namespace vggp

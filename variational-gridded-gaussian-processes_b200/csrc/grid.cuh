@@ -1,0 +1,435 @@
+// Grid-side kernels: per-dimension factor build, blocked Cholesky, triangular inverse leaves, band / trace /
+// log-det reductions, and the elementwise + reduction pieces of the reverse pass.  All float64.
+// Maths: SURVEY.md appendix A.  Reference formulas: gridded_kronecker_structure.py:731-780 (B1/ASVGP Kuu),
+// :1286-1323 (B0 Toeplitz Kuu).
+#pragma once
+#include "common.cuh"
+
+namespace vggp {
+
+constexpr int NB = 64;            // Cholesky / triangular-inverse block size
+constexpr int MAX_LEAVES = 40;    // supports M_d <= 2560
+
+// scalar slots in the plan's float64 scalar block
+enum {
+    SC_LOGDETK = 0,   // [3]
+    SC_LOGDETS = 3,   // [3]
+    SC_TR = 6,        // [3] tr(P_d S_d)
+    SC_MALPHA = 9,    // <m, alpha>
+    SC_COUNT = 16
+};
+
+struct GridDims {
+    int D, family, obs_dtype;
+    int n[VGGP_MAX_D];            // M_d
+    int K[VGGP_MAX_D];            // knots
+    float delta32[VGGP_MAX_D];    // mesh[1] - mesh[0] in float32 (reference: SplineBasis.delta, bspline.py:89)
+    i64 M;
+    i64 Loff[VGGP_MAX_D];         // offset of L_d inside the concatenated L / dL arrays
+    int band_off[VGGP_MAX_D];     // offset (elements) of dim d's block inside the band tables / gbuf band part
+    double* Kraw[VGGP_MAX_D];
+    double* Kc[VGGP_MAX_D];       // factored in place -> Cholesky factor (lower)
+    double* W[VGGP_MAX_D];        // C^-1
+    double* P[VGGP_MAX_D];
+    double* Lt[VGGP_MAX_D];       // tril(L_d)
+    double* R[VGGP_MAX_D];
+    double* S[VGGP_MAX_D];
+    double* Q[VGGP_MAX_D];
+    double* dP[VGGP_MAX_D];
+    double* dR[VGGP_MAX_D];
+    double* X[VGGP_MAX_D];
+    double* Y[VGGP_MAX_D];
+    double* dK[VGGP_MAX_D];
+    double* dLraw[VGGP_MAX_D];
+    double* tmp[VGGP_MAX_D];
+    double* sc;                   // SC_COUNT scalars
+    int* info;
+    void* bandT;                  // band tables in obs dtype: per dim [pd | po | qd | qo], each n[d] long
+    int leaf_cnt[VGGP_MAX_D];
+    int leaf_lo[VGGP_MAX_D][MAX_LEAVES + 1];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K_d(theta) entry.  theta = [l_1..l_D, s2_1..s2_D, noise].
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double b1_A(int i, int j, int n, double dl) {
+    if (i == j) return (2.0 / 3.0 * dl) + ((i == 0 || i == n - 1) ? -(1.0 / 3.0 * dl) : 0.0);
+    if (i - j == 1 || j - i == 1) return 1.0 / 6.0 * dl;
+    return 0.0;
+}
+__device__ __forceinline__ double b1_B(int i, int j, int n, double dl) {
+    if (i == j) return (2.0 / dl) + ((i == 0 || i == n - 1) ? -(1.0 / dl) : 0.0);
+    if (i - j == 1 || j - i == 1) return -1.0 / dl;
+    return 0.0;
+}
+__device__ __forceinline__ double b1_BC(int i, int j, int n) { return (i == j && (i == 0 || i == n - 1)) ? 1.0 : 0.0; }
+
+// (k * delta) rounded to float32 first, as the reference's int64-tensor * 0-dim float32 does
+__device__ __forceinline__ double b0_kdelta(int k, float delta32) { return (double)((float)k * delta32); }
+
+// r(k) and d r(k) / d l of the B0 Toeplitz first row (without the l^2 s2 factor)
+__device__ __forceinline__ void b0_row(int k, float delta32, double l, double& r, double& dr) {
+    if (k == 0) {
+        const double dl = (double)delta32;
+        const double e = exp(-dl / l);
+        r = 2.0 * (e + dl / l - 1.0);
+        dr = 2.0 * (e * dl / (l * l) - dl / (l * l));
+    } else {
+        const double a0 = b0_kdelta(k - 1, delta32), a1 = b0_kdelta(k + 1, delta32), a2 = b0_kdelta(k, delta32);
+        const double e0 = exp(-a0 / l), e1 = exp(-a1 / l), e2 = exp(-a2 / l);
+        r = e0 + e1 - 2.0 * e2;
+        const double il2 = 1.0 / (l * l);
+        dr = (e0 * a0 + e1 * a1 - 2.0 * e2 * a2) * il2;
+    }
+}
+
+__device__ __forceinline__ double factor_entry(const GridDims& g, const double* theta, int d, int i, int j) {
+    const double l = theta[d], s2 = theta[g.D + d];
+    const int n = g.n[d];
+    if (g.family == VGGP_B1_ASVGP) {
+        const double dl = (double)g.delta32[d];
+        const int dist = i > j ? i - j : j - i;
+        if (dist > 1) return 0.0;
+        return (b1_A(i, j, n, dl) * l + b1_B(i, j, n, dl) * (1.0 / l) + b1_BC(i, j, n)) * (1.0 / (2.0 * s2));
+    } else {
+        double r, dr;
+        b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
+        return r * (l * l * s2);
+    }
+}
+
+// d K_d[i][j] / d l and / d s2
+__device__ __forceinline__ void factor_entry_grad(const GridDims& g, const double* theta, int d, int i, int j,
+                                                  double& dKdl, double& dKds2) {
+    const double l = theta[d], s2 = theta[g.D + d];
+    const int n = g.n[d];
+    if (g.family == VGGP_B1_ASVGP) {
+        const double dl = (double)g.delta32[d];
+        const int dist = i > j ? i - j : j - i;
+        if (dist > 1) { dKdl = 0.0; dKds2 = 0.0; return; }
+        const double A = b1_A(i, j, n, dl), B = b1_B(i, j, n, dl), BC = b1_BC(i, j, n);
+        dKdl = (A - B / (l * l)) / (2.0 * s2);
+        dKds2 = -(A * l + B / l + BC) / (2.0 * s2 * s2);
+    } else {
+        double r, dr;
+        b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
+        dKdl = s2 * (2.0 * l * r + l * l * dr);
+        dKds2 = l * l * r;
+    }
+}
+
+// grid (ceil(nmax^2 / 256), D)
+__global__ void k_build_factors(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+                                const double* __restrict__ L) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && d == 0 && threadIdx.x < SC_COUNT) g.sc[threadIdx.x] = 0.0;
+    if (blockIdx.x == 0 && d == 0 && threadIdx.x == 0) *g.info = 0;
+    if (e >= (i64)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    const double k = factor_entry(g, theta, d, i, j);
+    g.Kraw[d][e] = k;
+    g.Kc[d][e] = k;
+    g.W[d][e] = 0.0;
+    g.Lt[d][e] = (j <= i) ? L[g.Loff[d] + e] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky, one panel per launch: every CTA factors the NB x NB diagonal block in
+// shared memory (redundantly -- it is tiny), CTA 0 writes it back and accumulates the log-det, CTA c >= 1
+// solves its NB rows of the panel against it.  The trailing update is a grouped GEMM launch.
+// grid (row chunks, D), 256 threads, dynamic smem 2 * NB * (NB+1) doubles.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ GridDims g, int j0) {
+    extern __shared__ double sm[];
+    double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    if (j0 >= n) return;
+    const int w = min(NB, n - j0);
+    const int r0 = j0 + (int)blockIdx.x * NB;
+    if (r0 >= n) return;
+    double* __restrict__ A = g.Kc[d];
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int e = tid; e < w * w; e += nt) {
+        const int i = e / w, j = e % w;
+        s[i][j] = A[(i64)(j0 + i) * n + (j0 + j)];
+    }
+    __syncthreads();
+    for (int c = 0; c < w; ++c) {
+        if (tid == 0) {
+            const double piv = s[c][c];
+            if (!(piv > 0.0)) atomicMax(g.info, d + 1);
+            s[c][c] = sqrt(piv);
+        }
+        __syncthreads();
+        const double dcc = s[c][c];
+        for (int r = c + 1 + tid; r < w; r += nt) s[r][c] /= dcc;
+        __syncthreads();
+        const int rem = w - c - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int r = c + 1 + e / rem, cc = c + 1 + e % rem;
+            if (cc <= r) s[r][cc] -= s[r][c] * s[cc][c];
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        for (int e = tid; e < w * w; e += nt) {
+            const int i = e / w, j = e % w;
+            if (j <= i) A[(i64)(j0 + i) * n + (j0 + j)] = s[i][j];
+        }
+        if (tid == 0) {
+            double ld = 0.0;
+            for (int c = 0; c < w; ++c) ld += log(s[c][c]);
+            g.sc[SC_LOGDETK + d] += 2.0 * ld;     // single writer per launch; launches are stream-ordered
+        }
+        return;
+    }
+    const int rows = min(NB, n - r0);
+    for (int e = tid; e < rows * w; e += nt) {
+        const int i = e / w, j = e % w;
+        a[i][j] = A[(i64)(r0 + i) * n + (j0 + j)];
+    }
+    __syncthreads();
+    if (tid < rows) {
+        for (int c = 0; c < w; ++c) {
+            double v = a[tid][c];
+            for (int k = 0; k < c; ++k) v -= a[tid][k] * s[c][k];
+            a[tid][c] = v / s[c][c];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < rows * w; e += nt) {
+        const int i = e / w, j = e % w;
+        A[(i64)(r0 + i) * n + (j0 + j)] = a[i][j];
+    }
+}
+
+// Inverse of the diagonal (leaf) blocks of the lower-triangular factor: W[lo:hi, lo:hi] = C[lo:hi, lo:hi]^-1.
+// grid (max leaves, D), NB threads, dynamic smem 2 * NB * (NB+1) doubles.
+__global__ void __launch_bounds__(NB) k_triinv_leaf(const __grid_constant__ GridDims g) {
+    extern __shared__ double sm[];
+    double (*c)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
+    double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    const int d = blockIdx.y;
+    if ((int)blockIdx.x >= g.leaf_cnt[d]) return;
+    const int n = g.n[d];
+    const int lo = g.leaf_lo[d][blockIdx.x], hi = g.leaf_lo[d][blockIdx.x + 1];
+    const int w = hi - lo;
+    const double* __restrict__ C = g.Kc[d];
+    double* __restrict__ W = g.W[d];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < w * w; e += NB) {
+        const int i = e / w, j = e % w;
+        c[i][j] = (j <= i) ? C[(i64)(lo + i) * n + (lo + j)] : 0.0;
+    }
+    __syncthreads();
+    if (tid < w) {
+        const int j = tid;
+        x[j][j] = 1.0 / c[j][j];
+        for (int i = j + 1; i < w; ++i) {
+            double v = 0.0;
+            for (int k = j; k < i; ++k) v -= c[i][k] * x[k][j];
+            x[i][j] = v / c[i][i];
+        }
+        for (int i = j; i < w; ++i) W[(i64)(lo + i) * n + (lo + j)] = x[i][j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward reductions per dimension: band tables of P_d and Q_d (in the observation dtype), tr(P_d S_d) =
+// <R_d, tril L_d>, log det S_d = 2 sum log |L_ii|.   grid (D), 1024 threads.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) k_fwd_reduce(const __grid_constant__ GridDims g) {
+    __shared__ double red[32];
+    const int d = blockIdx.x;
+    const int n = g.n[d];
+    const double* __restrict__ P = g.P[d];
+    const double* __restrict__ Q = g.Q[d];
+    const double* __restrict__ R = g.R[d];
+    const double* __restrict__ Lt = g.Lt[d];
+    T* band = reinterpret_cast<T*>(g.bandT) + g.band_off[d];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        band[i] = (T)P[(i64)i * n + i];
+        band[n + i] = (i + 1 < n) ? (T)P[(i64)i * n + i + 1] : (T)0;
+        band[2 * n + i] = (T)Q[(i64)i * n + i];
+        band[3 * n + i] = (i + 1 < n) ? (T)Q[(i64)i * n + i + 1] : (T)0;
+    }
+    double tr = 0.0, ld = 0.0;
+    for (i64 e = threadIdx.x; e < (i64)n * n; e += blockDim.x) tr += R[e] * Lt[e];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ld += log(fabs(Lt[(i64)i * n + i]));
+    tr = block_sum(tr, red);
+    ld = block_sum(ld, red);
+    if (threadIdx.x == 0) {
+        g.sc[SC_TR + d] = tr;
+        g.sc[SC_LOGDETS + d] = 2.0 * ld;
+    }
+}
+
+// alpha (float64) -> observation dtype, and <m, alpha>.
+template <typename T>
+__global__ void __launch_bounds__(256) k_cast_alpha(const double* __restrict__ alpha, const double* __restrict__ m,
+                                                    T* __restrict__ alphaT, i64 M, double* __restrict__ sc) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (i64)gridDim.x * blockDim.x) {
+        const double a = alpha[i];
+        alphaT[i] = (T)a;
+        acc += a * m[i];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(sc + SC_MALPHA, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Reverse pass pieces
+// ---------------------------------------------------------------------------------------------------------
+struct GbufView {
+    const void* obs;       // n_obs_elems values of the observation dtype: [g_alpha (M) | band blocks]
+    const double* scal;    // float64 scalars
+};
+
+// g = (ell_scale / noise) * g_alpha_raw, ghat = g - m/2
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_prep(const T* __restrict__ ga, const double* __restrict__ m,
+                                                  const double* __restrict__ theta, int D, double ell_scale,
+                                                  double* __restrict__ gout, double* __restrict__ ghat, i64 M) {
+    const double c = ell_scale / theta[2 * D];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (i64)gridDim.x * blockDim.x) {
+        const double v = c * (double)ga[i];
+        gout[i] = v;
+        ghat[i] = v - 0.5 * m[i];
+    }
+}
+
+__device__ __forceinline__ double tr_others(const GridDims& g, int d) {
+    double c = 1.0;
+    for (int e = 0; e < g.D; ++e)
+        if (e != d) c *= g.sc[SC_TR + e];
+    return c;
+}
+
+// dP_d (holding the mode-d Gram contraction) += band scatter - c_d/2 S_d ;  dR_d = 2 sym(dQ band) R_d.
+// grid (ceil(nmax^2/256), D)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_dP_dR(const __grid_constant__ GridDims g, const T* __restrict__ gband,
+                                                   const double* __restrict__ theta, double ell_scale) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (i64)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    const double noise = theta[2 * g.D];
+    const double cP = ell_scale / (2.0 * noise), cQ = -ell_scale / (2.0 * noise);
+    const T* __restrict__ b = gband + g.band_off[d];   // [bp_diag | bp_off | bq_diag | bq_off]
+    double v = g.dP[d][e] - 0.5 * tr_others(g, d) * g.S[d][e];
+    if (i == j) v += cP * (double)b[i];
+    else if (i - j == 1) v += cP * (double)b[n + j];
+    else if (j - i == 1) v += cP * (double)b[n + i];
+    g.dP[d][e] = v;
+    const double* __restrict__ R = g.R[d];
+    double r = (double)b[2 * n + i] * R[e];
+    if (i > 0) r += (double)b[3 * n + i - 1] * R[e - n];
+    if (i + 1 < n) r += (double)b[3 * n + i] * R[e + n];
+    g.dR[d][e] = 2.0 * cQ * r;
+}
+
+// X = (dP + dP^T) / 2.   grid (ceil(nmax^2/256), D)
+__global__ void __launch_bounds__(256) k_sym(const __grid_constant__ GridDims g) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (i64)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    g.X[d][e] = 0.5 * (g.dP[d][e] + g.dP[d][(i64)j * n + i]);
+}
+
+// dL_out = tril(dLraw - c_d R_d + (M/M_d) diag(1/L_ii)).   grid (ceil(nmax^2/256), D)
+__global__ void __launch_bounds__(256) k_bwd_dL(const __grid_constant__ GridDims g, double* __restrict__ dL) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (i64)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    double v = 0.0;
+    if (j <= i) {
+        v = g.dLraw[d][e] - tr_others(g, d) * g.R[d][e];
+        if (i == j) v += ((double)g.M / (double)n) / g.Lt[d][e];
+    }
+    dL[g.Loff[d] + e] = v;
+}
+
+// dm = (kron P) g - alpha
+__global__ void __launch_bounds__(256) k_bwd_dm(const double* __restrict__ pg, const double* __restrict__ alpha,
+                                                double* __restrict__ dm, i64 M) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (i64)gridDim.x * blockDim.x)
+        dm[i] = pg[i] - alpha[i];
+}
+
+// d theta and the ELBO scalars.  grid (D), 1024 threads.
+//   dK_d(total) = dKraw_d - (M / (2 M_d)) P_d ;  dl_d = <dK, dK/dl>, ds2_d = <dK, dK/ds2> + dkff * kff / s2_d
+//   block 0 additionally writes dnoise and out[0..3].
+__global__ void __launch_bounds__(1024) k_bwd_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+                                                    const double* __restrict__ gscal, double ell_scale,
+                                                    double* __restrict__ out, double* __restrict__ dtheta) {
+    __shared__ double red[32];
+    const int d = blockIdx.x;
+    const int n = g.n[d];
+    const int D = g.D;
+    const double* __restrict__ dK = g.dK[d];
+    const double* __restrict__ P = g.P[d];
+    const double half_ratio = 0.5 * (double)g.M / (double)n;
+    double sl = 0.0, ss = 0.0;
+    if (g.family == VGGP_B1_ASVGP) {
+        for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) {
+            const int i = e / 3, j = i + (e % 3) - 1;
+            if (j < 0 || j >= n) continue;
+            double a, b;
+            factor_entry_grad(g, theta, d, i, j, a, b);
+            const double v = dK[(i64)i * n + j] - half_ratio * P[(i64)i * n + j];
+            sl += v * a;
+            ss += v * b;
+        }
+    } else {
+        for (i64 e = threadIdx.x; e < (i64)n * n; e += blockDim.x) {
+            const int i = (int)(e / n), j = (int)(e % n);
+            double a, b;
+            factor_entry_grad(g, theta, d, i, j, a, b);
+            const double v = dK[e] - half_ratio * P[e];
+            sl += v * a;
+            ss += v * b;
+        }
+    }
+    sl = block_sum(sl, red);
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+        const double noise = theta[2 * D];
+        double kff = 1.0;
+        for (int e = 0; e < D; ++e) kff *= theta[D + e];
+        const double E = gscal[0], nobs = gscal[1];
+        const double dkff = -ell_scale * nobs / (2.0 * noise);
+        dtheta[d] = sl;
+        dtheta[D + d] = ss + dkff * kff / theta[D + d];
+        if (d == 0) {
+            const double tot = E + nobs * kff;
+            const double ell = -0.5 * nobs * log(2.0 * 3.14159265358979323846 * noise) - tot / (2.0 * noise);
+            dtheta[2 * D] = ell_scale * (-nobs / (2.0 * noise) + tot / (2.0 * noise * noise));
+            double trp = 1.0, lds = 0.0;
+            for (int e = 0; e < D; ++e) {
+                trp *= g.sc[SC_TR + e];
+                lds += ((double)g.M / (double)g.n[e]) * (g.sc[SC_LOGDETK + e] - g.sc[SC_LOGDETS + e]);
+            }
+            const double kl = 0.5 * (trp + g.sc[SC_MALPHA] - (double)g.M + lds);
+            out[0] = ell_scale * ell - kl;
+            out[1] = ell_scale * ell;
+            out[2] = kl;
+            out[3] = nobs;
+        }
+    }
+}
+
+}  // namespace vggp

@@ -1,0 +1,736 @@
+// libvggp.so -- plan, static launch schedules and the extern "C" entry points declared in include/vggp.h.
+// sm_100a only; there is no CPU path in this library.
+#include <vector>
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "grid.cuh"
+#include "obs.cuh"
+
+namespace vggp {
+thread_local char g_err[512] = {0};
+unsigned long long g_launches = 0;
+static int g_use_mma = 1;
+
+struct Phase {
+    GemmDesc* d_descs = nullptr;
+    int ndesc = 0;
+    GemmGroupDims dims = {0, 0, 0};
+};
+}  // namespace vggp
+
+using namespace vggp;
+
+struct vggp_plan {
+    int family, D, obs_dtype, device;
+    int K[VGGP_MAX_D], n[VGGP_MAX_D];
+    i64 M, Lsize;
+    i64 stride[VGGP_MAX_D];
+    float* d_knots[VGGP_MAX_D];
+    MeshView mesh[VGGP_MAX_D];
+    GridDims g;
+    int nmax;
+    // M-sized float64 work tensors
+    double *mws, *alpha, *Tm[VGGP_MAX_D], *tmpM[VGGP_MAX_D], *gM, *ghat, *pgA, *pgB;
+    void* alphaT;
+    int band_off[VGGP_MAX_D], band_total, knot_off[VGGP_MAX_D], knot_total;
+    // schedules
+    std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
+    int n_panels;
+    std::vector<Phase> triinv;             // two launches per recursion depth, deepest first
+    Phase pinv, rs, qq, alpha_phase, gram, dPdL, Yp, dKp;
+    std::vector<Phase> chains;             // D-1 launches building T_d = m x_{e != d} P_e
+    std::vector<Phase> dm_chain;           // D launches: (kron P) g
+    double* dm_result;
+    std::vector<void*> allocs;
+    // staging for vggp_elbo_host
+    void* st_x = nullptr; void* st_y = nullptr; i64 st_n = 0;
+    double *st_theta = nullptr, *st_m = nullptr, *st_L = nullptr, *st_out = nullptr, *st_dtheta = nullptr,
+           *st_dm = nullptr, *st_dL = nullptr;
+    void* st_gbuf = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(vggp_plan* p, T** out, i64 count) {
+    void* ptr = nullptr;
+    if (count <= 0) count = 1;
+    VGGP_CUDA(cudaMalloc(&ptr, (size_t)count * sizeof(T)));
+    VGGP_CUDA(cudaMemset(ptr, 0, (size_t)count * sizeof(T)));
+    p->allocs.push_back(ptr);
+    *out = reinterpret_cast<T*>(ptr);
+    return 0;
+}
+
+int make_phase(vggp_plan* p, std::vector<GemmDesc>& descs, Phase& ph) {
+    ph.ndesc = (int)descs.size();
+    if (ph.ndesc == 0) return 0;
+    ph.dims = gemm_finalize_group(descs.data(), ph.ndesc);
+    int rc = dev_alloc(p, &ph.d_descs, ph.ndesc);
+    if (rc) return rc;
+    VGGP_CUDA(cudaMemcpy(ph.d_descs, descs.data(), sizeof(GemmDesc) * ph.ndesc, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int launch_phase(const Phase& ph, cudaStream_t st) {
+    if (ph.ndesc == 0) return 0;
+    dim3 grid(ph.dims.gx, ph.dims.gy, ph.dims.gz);
+    if (g_use_mma) k_gemm_group<true><<<grid, GEMM_THREADS_MMA, 0, st>>>(ph.d_descs, ph.ndesc);
+    else k_gemm_group<false><<<grid, GEMM_THREADS_SIMT, 0, st>>>(ph.d_descs, ph.ndesc);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_one(GemmDesc d, int use_mma, cudaStream_t st) {
+    GemmGroupDims dims = gemm_finalize_group(&d, 1);
+    if (d.m <= 0 || d.n <= 0) return 0;
+    dim3 grid(dims.gx, dims.gy, dims.gz);
+    if (use_mma) k_gemm_one<true><<<grid, GEMM_THREADS_MMA, 0, st>>>(d);
+    else k_gemm_one<false><<<grid, GEMM_THREADS_SIMT, 0, st>>>(d);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+// plain row-major square matrix product helper: C (n x n) = alpha * op(A) * op(B) + beta * C
+GemmDesc square_desc(int n, const double* A, bool tA, const double* B, bool tB, double* C, double alpha, double beta) {
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    d.A = A; d.B = B; d.C = C;
+    d.m = d.n = d.k = n;
+    d.rsA = tA ? 1 : n; d.csA = tA ? n : 1;
+    d.rsB = tB ? 1 : n; d.csB = tB ? n : 1;
+    d.rsC = n; d.csC = 1;
+    d.alpha = alpha; d.beta = beta;
+    return d;
+}
+
+// dst = src x_e A   (apply the M_e x M_e matrix A along mode e of the M-tensor)
+GemmDesc mode_desc(const vggp_plan* p, int e, const double* A, const double* src, double* dst) {
+    i64 outer = 1, inner = 1;
+    for (int f = 0; f < e; ++f) outer *= p->n[f];
+    for (int f = e + 1; f < p->D; ++f) inner *= p->n[f];
+    const int ne = p->n[e];
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    if (inner > 1) {
+        d.A = A; d.B = src; d.C = dst;
+        d.m = ne; d.n = (int)inner; d.k = ne;
+        d.rsA = ne; d.csA = 1;
+        d.rsB = inner; d.csB = 1;
+        d.rsC = inner; d.csC = 1;
+        d.batch = (int)outer;
+        d.bsA = 0; d.bsB = (i64)ne * inner; d.bsC = (i64)ne * inner;
+    } else {
+        // dst (outer x ne) = src (outer x ne) * A^T
+        d.A = src; d.B = A; d.C = dst;
+        d.m = (int)outer; d.n = ne; d.k = ne;
+        d.rsA = ne; d.csA = 1;
+        d.rsB = 1; d.csB = ne;
+        d.rsC = ne; d.csC = 1;
+    }
+    return d;
+}
+
+// dP_d[i][j] = sum_{o,r} ghat[o,i,r] * T_d[o,j,r]
+GemmDesc gram_desc(const vggp_plan* p, int e, const double* ghat, const double* Td, double* dP, int n_descs_in_group) {
+    i64 outer = 1, inner = 1;
+    for (int f = 0; f < e; ++f) outer *= p->n[f];
+    for (int f = e + 1; f < p->D; ++f) inner *= p->n[f];
+    const int ne = p->n[e];
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    d.A = ghat; d.B = Td; d.C = dP;
+    d.m = ne; d.n = ne; d.k = (int)(outer * inner);
+    d.kinner = (int)inner;
+    d.rsA = inner; d.csA = 1; d.koA = (i64)ne * inner;
+    d.csB = inner; d.rsB = 1; d.koB = (i64)ne * inner;
+    if (inner == 1) { d.rsA = 1; d.csA = 0; d.csB = 1; d.rsB = 0; }
+    d.rsC = ne; d.csC = 1;
+    d.alpha = 1.0; d.beta = 0.0;
+    const int tiles = ((ne + GBM - 1) / GBM) * ((ne + GBN - 1) / GBN) * n_descs_in_group;
+    int sk = (2 * 148 + tiles - 1) / tiles;
+    const int max_sk = std::max(1, d.k / (GBK * 8));
+    sk = std::max(1, std::min(sk, max_sk));
+    d.splitk = sk;
+    return d;
+}
+
+void build_leaves(int lo, int hi, std::vector<int>& bounds) {
+    if (hi - lo <= NB) { bounds.push_back(lo); return; }
+    const int half = (hi - lo + 1) / 2;
+    const int mid = lo + (half + NB - 1) / NB * NB;
+    build_leaves(lo, mid, bounds);
+    build_leaves(mid, hi, bounds);
+}
+
+struct Node { int lo, mid, hi, depth; };
+void build_nodes(int lo, int hi, int depth, std::vector<Node>& nodes) {
+    if (hi - lo <= NB) return;
+    const int half = (hi - lo + 1) / 2;
+    const int mid = lo + (half + NB - 1) / NB * NB;
+    nodes.push_back({lo, mid, hi, depth});
+    build_nodes(lo, mid, depth + 1, nodes);
+    build_nodes(mid, hi, depth + 1, nodes);
+}
+
+GemmDesc sub_desc(int n, const double* A, int ar, int ac, const double* B, int br, int bc, double* C, int cr, int cc,
+                  int m, int nn, int k, double alpha, double beta) {
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    d.A = A + (i64)ar * n + ac; d.B = B + (i64)br * n + bc; d.C = C + (i64)cr * n + cc;
+    d.m = m; d.n = nn; d.k = k;
+    d.rsA = n; d.csA = 1; d.rsB = n; d.csB = 1; d.rsC = n; d.csC = 1;
+    d.alpha = alpha; d.beta = beta;
+    return d;
+}
+
+int build_schedules(vggp_plan* p) {
+    const int D = p->D;
+    GridDims& g = p->g;
+    int rc;
+    // ---- Cholesky trailing updates, one phase per panel ----
+    p->n_panels = (p->nmax + NB - 1) / NB;
+    p->chol_trailing.resize(p->n_panels);
+    for (int j = 0; j < p->n_panels; ++j) {
+        std::vector<GemmDesc> ds;
+        const int j0 = j * NB;
+        for (int d = 0; d < D; ++d) {
+            const int n = p->n[d];
+            const int r0 = j0 + NB;
+            if (r0 >= n) continue;
+            GemmDesc x;
+            gemm_desc_defaults(x);
+            x.A = g.Kc[d] + (i64)r0 * n + j0;                  // panel (n - r0) x NB
+            x.B = x.A;                                         // panel^T: B(k, j) = panel[j][k]
+            x.C = g.Kc[d] + (i64)r0 * n + r0;
+            x.m = n - r0; x.n = n - r0; x.k = NB;
+            x.rsA = n; x.csA = 1; x.rsB = 1; x.csB = n; x.rsC = n; x.csC = 1;
+            x.alpha = -1.0; x.beta = 1.0; x.lower_only = 1;
+            ds.push_back(x);
+        }
+        if ((rc = make_phase(p, ds, p->chol_trailing[j]))) return rc;
+    }
+    // ---- triangular inverse recursion ----
+    int max_depth = -1;
+    std::vector<std::vector<Node>> nodes(D);
+    for (int d = 0; d < D; ++d) {
+        build_nodes(0, p->n[d], 0, nodes[d]);
+        for (auto& nd : nodes[d]) max_depth = std::max(max_depth, nd.depth);
+    }
+    for (int depth = max_depth; depth >= 0; --depth) {
+        std::vector<GemmDesc> s1, s2;
+        for (int d = 0; d < D; ++d) {
+            const int n = p->n[d];
+            for (auto& nd : nodes[d]) {
+                if (nd.depth != depth) continue;
+                const int m1 = nd.mid - nd.lo, m2 = nd.hi - nd.mid;
+                // tmp21 = C21 * W11 ; W21 = -W22 * tmp21
+                s1.push_back(sub_desc(n, g.Kc[d], nd.mid, nd.lo, g.W[d], nd.lo, nd.lo, g.tmp[d], nd.mid, nd.lo, m2, m1, m1, 1.0, 0.0));
+                s2.push_back(sub_desc(n, g.W[d], nd.mid, nd.mid, g.tmp[d], nd.mid, nd.lo, g.W[d], nd.mid, nd.lo, m2, m1, m2, -1.0, 0.0));
+            }
+        }
+        Phase a, b;
+        if ((rc = make_phase(p, s1, a))) return rc;
+        if ((rc = make_phase(p, s2, b))) return rc;
+        p->triinv.push_back(a);
+        p->triinv.push_back(b);
+    }
+    // ---- P = W^T W ; R = P Lt, S = Lt Lt^T ; Q = R R^T ----
+    {
+        std::vector<GemmDesc> a, b, c;
+        for (int d = 0; d < D; ++d) {
+            const int n = p->n[d];
+            a.push_back(square_desc(n, g.W[d], true, g.W[d], false, g.P[d], 1.0, 0.0));
+            b.push_back(square_desc(n, g.P[d], false, g.Lt[d], false, g.R[d], 1.0, 0.0));
+            b.push_back(square_desc(n, g.Lt[d], false, g.Lt[d], true, g.S[d], 1.0, 0.0));
+            c.push_back(square_desc(n, g.R[d], false, g.R[d], true, g.Q[d], 1.0, 0.0));
+        }
+        if ((rc = make_phase(p, a, p->pinv))) return rc;
+        if ((rc = make_phase(p, b, p->rs))) return rc;
+        if ((rc = make_phase(p, c, p->qq))) return rc;
+    }
+    // ---- chains T_d = m x_{e != d} P_e, then alpha = T_{D-1} x_{D-1} P_{D-1} ----
+    if (D == 1) {
+        p->Tm[0] = p->mws;
+    }
+    for (int s = 0; s + 1 < D; ++s) {
+        std::vector<GemmDesc> ds;
+        for (int d = 0; d < D; ++d) {
+            // modes e != d in increasing order; step s uses the s-th of them
+            int e = s;
+            if (e >= d) e += 1;
+            const bool first = (s == 0), last = (s == D - 2);
+            const double* src = first ? p->mws : p->tmpM[d];
+            double* dst = last ? p->Tm[d] : p->tmpM[d];
+            ds.push_back(mode_desc(p, e, g.P[e], src, dst));
+        }
+        Phase ph;
+        if ((rc = make_phase(p, ds, ph))) return rc;
+        p->chains.push_back(ph);
+    }
+    {
+        std::vector<GemmDesc> ds;
+        ds.push_back(mode_desc(p, D - 1, g.P[D - 1], p->Tm[D - 1], p->alpha));
+        if ((rc = make_phase(p, ds, p->alpha_phase))) return rc;
+    }
+    // ---- reverse: (kron P) g ----
+    {
+        const double* src = p->gM;
+        for (int e = 0; e < D; ++e) {
+            double* dst = (e % 2 == 0) ? p->pgA : p->pgB;
+            std::vector<GemmDesc> ds;
+            ds.push_back(mode_desc(p, e, g.P[e], src, dst));
+            Phase ph;
+            if ((rc = make_phase(p, ds, ph))) return rc;
+            p->dm_chain.push_back(ph);
+            src = dst;
+            p->dm_result = dst;
+        }
+    }
+    // ---- reverse: Gram contractions, dP += dR Lt^T, dLraw = P dR, Y = P X, dK = -Y P ----
+    {
+        std::vector<GemmDesc> gr, a, y, k;
+        for (int d = 0; d < D; ++d) {
+            const int n = p->n[d];
+            gr.push_back(gram_desc(p, d, p->ghat, p->Tm[d], g.dP[d], D));
+            a.push_back(square_desc(n, g.dR[d], false, g.Lt[d], true, g.dP[d], 1.0, 1.0));
+            a.push_back(square_desc(n, g.P[d], false, g.dR[d], false, g.dLraw[d], 1.0, 0.0));
+            y.push_back(square_desc(n, g.P[d], false, g.X[d], false, g.Y[d], 1.0, 0.0));
+            k.push_back(square_desc(n, g.Y[d], false, g.P[d], false, g.dK[d], -1.0, 0.0));
+        }
+        if ((rc = make_phase(p, gr, p->gram))) return rc;
+        if ((rc = make_phase(p, a, p->dPdL))) return rc;
+        if ((rc = make_phase(p, y, p->Yp))) return rc;
+        if ((rc = make_phase(p, k, p->dKp))) return rc;
+    }
+    return 0;
+}
+
+template <typename T, int D>
+int launch_obs_b1(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
+    ObsArgs<T, D> a;
+    for (int d = 0; d < D; ++d) {
+        a.x[d] = reinterpret_cast<const T*>(x[d]);
+        a.mesh[d] = p->mesh[d];
+        a.stride[d] = p->stride[d];
+        a.band_off[d] = p->band_off[d];
+        a.knot_off[d] = p->knot_off[d];
+    }
+    a.y = reinterpret_cast<const T*>(y);
+    a.n = n;
+    a.band_total = p->band_total;
+    a.knot_total = p->knot_total;
+    a.alpha = reinterpret_cast<const T*>(p->alphaT);
+    a.band = reinterpret_cast<const T*>(p->g.bandT);
+    T* gb = reinterpret_cast<T*>(gbuf);
+    a.galpha = gb;
+    a.gband = gb + p->M;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    const size_t smem = (size_t)2 * p->band_total * sizeof(T) + (size_t)p->knot_total * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_v1<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_obs_b1_v1<T, D><<<(unsigned)blocks, 256, smem, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+int obs_dispatch_D(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
+    switch (p->D) {
+        case 1: return launch_obs_b1<T, 1>(p, x, y, n, gbuf, st);
+        case 2: return launch_obs_b1<T, 2>(p, x, y, n, gbuf, st);
+        case 3: return launch_obs_b1<T, 3>(p, x, y, n, gbuf, st);
+    }
+    return fail(VGGP_E_DIM, "D must be 1..3");
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int vggp_abi_version(void) { return VGGP_ABI_VERSION; }
+const char* vggp_last_error(void) { return g_err; }
+uint64_t vggp_launch_count(void) { return (uint64_t)g_launches; }
+
+int vggp_set_gemm_mode(int use_mma) {
+    g_use_mma = use_mma ? 1 : 0;
+    return 0;
+}
+
+int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, const float* const* knots_host,
+                     int obs_dtype, int device) {
+    if (!out || !n_knots || !knots_host) return fail(VGGP_E_ARG, "null argument");
+    if (family != VGGP_B1_ASVGP && family != VGGP_B0_GRIDDED) return fail(VGGP_E_FAMILY, "unknown feature family");
+    if (D < 1 || D > VGGP_MAX_D) return fail(VGGP_E_DIM, "D must be 1..3");
+    if (obs_dtype != VGGP_F32 && obs_dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "obs_dtype must be VGGP_F32 or VGGP_F64");
+    for (int d = 0; d < D; ++d) {
+        if (n_knots[d] < 3) return fail(VGGP_E_ARG, "each mesh needs at least 3 knots");
+        if (n_knots[d] > NB * MAX_LEAVES) return fail(VGGP_E_ARG, "mesh too large");
+        for (int k = 1; k < n_knots[d]; ++k)
+            if (!(knots_host[d][k] > knots_host[d][k - 1])) return fail(VGGP_E_ARG, "knots must be strictly increasing");
+    }
+    VGGP_CUDA(cudaSetDevice(device));
+    vggp_plan* p = new (std::nothrow) vggp_plan();
+    if (!p) return fail(VGGP_E_NOMEM, "out of host memory");
+    p->family = family; p->D = D; p->obs_dtype = obs_dtype; p->device = device;
+    p->M = 1; p->Lsize = 0; p->nmax = 0;
+    int rc = 0;
+    GridDims& g = p->g;
+    memset(&g, 0, sizeof(g));
+    g.D = D; g.family = family; g.obs_dtype = obs_dtype;
+    int boff = 0, koff = 0;
+    for (int d = 0; d < D; ++d) {
+        p->K[d] = n_knots[d];
+        p->n[d] = (family == VGGP_B1_ASVGP) ? n_knots[d] : n_knots[d] - 1;
+        p->M *= p->n[d];
+        g.n[d] = p->n[d]; g.K[d] = p->K[d];
+        g.delta32[d] = knots_host[d][1] - knots_host[d][0];
+        g.Loff[d] = p->Lsize;
+        p->Lsize += (i64)p->n[d] * p->n[d];
+        p->nmax = std::max(p->nmax, p->n[d]);
+        p->band_off[d] = boff; g.band_off[d] = boff;
+        boff += 4 * p->n[d];
+        p->knot_off[d] = koff;
+        koff += p->K[d];
+    }
+    p->band_total = boff;
+    p->knot_total = koff;
+    g.M = p->M;
+    for (int d = 0; d < D; ++d) {
+        i64 s = 1;
+        for (int f = d + 1; f < D; ++f) s *= p->n[f];
+        p->stride[d] = s;
+    }
+#define TRY(expr) do { rc = (expr); if (rc) { vggp_plan_destroy(p); return rc; } } while (0)
+    for (int d = 0; d < D; ++d) {
+        const int K = p->K[d];
+        TRY(dev_alloc(p, &p->d_knots[d], K));
+        rc = (int)cudaMemcpy(p->d_knots[d], knots_host[d], sizeof(float) * K, cudaMemcpyHostToDevice);
+        if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaMemcpy(knots) failed"); }
+        MeshView& mv = p->mesh[d];
+        mv.t = p->d_knots[d]; mv.K = K; mv.t0 = knots_host[d][0];
+        mv.inv_h = (float)((double)(K - 1) / ((double)knots_host[d][K - 1] - (double)knots_host[d][0]));
+        mv.nearly_uniform = 1;
+        for (int k = 0; k < K; ++k) {
+            const float gf = (knots_host[d][k] - mv.t0) * mv.inv_h;
+            if (fabsf(gf - (float)k) > 1.25f) mv.nearly_uniform = 0;
+        }
+        const i64 nn = (i64)p->n[d] * p->n[d];
+        TRY(dev_alloc(p, &g.Kraw[d], nn)); TRY(dev_alloc(p, &g.Kc[d], nn)); TRY(dev_alloc(p, &g.W[d], nn));
+        TRY(dev_alloc(p, &g.P[d], nn)); TRY(dev_alloc(p, &g.Lt[d], nn)); TRY(dev_alloc(p, &g.R[d], nn));
+        TRY(dev_alloc(p, &g.S[d], nn)); TRY(dev_alloc(p, &g.Q[d], nn)); TRY(dev_alloc(p, &g.dP[d], nn));
+        TRY(dev_alloc(p, &g.dR[d], nn)); TRY(dev_alloc(p, &g.X[d], nn)); TRY(dev_alloc(p, &g.Y[d], nn));
+        TRY(dev_alloc(p, &g.dK[d], nn)); TRY(dev_alloc(p, &g.dLraw[d], nn)); TRY(dev_alloc(p, &g.tmp[d], nn));
+        std::vector<int> bounds;
+        build_leaves(0, p->n[d], bounds);
+        bounds.push_back(p->n[d]);
+        g.leaf_cnt[d] = (int)bounds.size() - 1;
+        for (size_t i = 0; i < bounds.size(); ++i) g.leaf_lo[d][i] = bounds[i];
+    }
+    TRY(dev_alloc(p, &g.sc, SC_COUNT));
+    TRY(dev_alloc(p, &g.info, 1));
+    const size_t tsz = obs_dtype == VGGP_F32 ? 4 : 8;
+    {
+        unsigned char* b = nullptr;
+        TRY(dev_alloc(p, &b, (i64)p->band_total * tsz));
+        g.bandT = b;
+        unsigned char* a = nullptr;
+        TRY(dev_alloc(p, &a, p->M * (i64)tsz));
+        p->alphaT = a;
+    }
+    TRY(dev_alloc(p, &p->mws, p->M)); TRY(dev_alloc(p, &p->alpha, p->M));
+    TRY(dev_alloc(p, &p->gM, p->M)); TRY(dev_alloc(p, &p->ghat, p->M));
+    TRY(dev_alloc(p, &p->pgA, p->M)); TRY(dev_alloc(p, &p->pgB, p->M));
+    for (int d = 0; d < D; ++d) {
+        if (D > 1) TRY(dev_alloc(p, &p->Tm[d], p->M));
+        if (D > 2) TRY(dev_alloc(p, &p->tmpM[d], p->M)); else p->tmpM[d] = nullptr;
+    }
+    TRY(build_schedules(p));
+    rc = (int)cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(2 * NB * (NB + 1) * sizeof(double)));
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_triinv_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(2 * NB * (NB + 1) * sizeof(double)));
+    if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
+#undef TRY
+    *out = p;
+    return 0;
+}
+
+int vggp_plan_destroy(vggp_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    for (void* ptr : p->allocs) cudaFree(ptr);
+    void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
+    for (void* ptr : st)
+        if (ptr) cudaFree(ptr);
+    delete p;
+    return 0;
+}
+
+int vggp_plan_dims(const vggp_plan* p, int* D, int* m_per_dim, int64_t* M) {
+    if (!p) return fail(VGGP_E_ARG, "null plan");
+    if (D) *D = p->D;
+    if (m_per_dim) for (int d = 0; d < p->D; ++d) m_per_dim[d] = p->n[d];
+    if (M) *M = p->M;
+    return 0;
+}
+
+int vggp_gbuf_layout(const vggp_plan* p, int64_t* n_obs_elems, int64_t* scalar_offset_bytes, int64_t* n_scalars,
+                     int64_t* total_bytes) {
+    if (!p) return fail(VGGP_E_ARG, "null plan");
+    const i64 tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    const i64 ne = p->M + p->band_total;
+    const i64 soff = (ne * tsz + 7) / 8 * 8;
+    if (n_obs_elems) *n_obs_elems = ne;
+    if (scalar_offset_bytes) *scalar_offset_bytes = soff;
+    if (n_scalars) *n_scalars = 8;
+    if (total_bytes) *total_bytes = soff + 8 * 8;
+    return 0;
+}
+
+int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const double* L, void* stream) {
+    if (!p || !theta || !m || !L) return fail(VGGP_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->D;
+    int rc;
+    VGGP_CUDA(cudaMemcpyAsync(p->mws, m, sizeof(double) * p->M, cudaMemcpyDeviceToDevice, st));
+    const i64 nn = (i64)p->nmax * p->nmax;
+    dim3 egrid(ceil_div(nn, 256), D);
+    k_build_factors<<<egrid, 256, 0, st>>>(p->g, theta, L);
+    VGGP_LAUNCH_CHECK();
+    const size_t csm = 2 * NB * (NB + 1) * sizeof(double);
+    for (int j = 0; j < p->n_panels; ++j) {
+        const int j0 = j * NB;
+        dim3 grid(ceil_div(p->nmax - j0, NB), D);
+        k_chol_panel<<<grid, 256, csm, st>>>(p->g, j0);
+        VGGP_LAUNCH_CHECK();
+        if ((rc = launch_phase(p->chol_trailing[j], st))) return rc;
+    }
+    int max_leaves = 0;
+    for (int d = 0; d < D; ++d) max_leaves = std::max(max_leaves, p->g.leaf_cnt[d]);
+    k_triinv_leaf<<<dim3(max_leaves, D), NB, csm, st>>>(p->g);
+    VGGP_LAUNCH_CHECK();
+    for (auto& ph : p->triinv) if ((rc = launch_phase(ph, st))) return rc;
+    if ((rc = launch_phase(p->pinv, st))) return rc;
+    if ((rc = launch_phase(p->rs, st))) return rc;
+    if ((rc = launch_phase(p->qq, st))) return rc;
+    if (p->obs_dtype == VGGP_F32) k_fwd_reduce<float><<<D, 1024, 0, st>>>(p->g);
+    else k_fwd_reduce<double><<<D, 1024, 0, st>>>(p->g);
+    VGGP_LAUNCH_CHECK();
+    for (auto& ph : p->chains) if ((rc = launch_phase(ph, st))) return rc;
+    if ((rc = launch_phase(p->alpha_phase, st))) return rc;
+    const int cblocks = (int)std::min<i64>((p->M + 255) / 256, 148 * 4);
+    if (p->obs_dtype == VGGP_F32)
+        k_cast_alpha<float><<<cblocks, 256, 0, st>>>(p->alpha, p->mws, reinterpret_cast<float*>(p->alphaT), p->M, p->g.sc);
+    else
+        k_cast_alpha<double><<<cblocks, 256, 0, st>>>(p->alpha, p->mws, reinterpret_cast<double*>(p->alphaT), p->M, p->g.sc);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
+    if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
+    cudaStream_t st = (cudaStream_t)stream;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
+    if (n == 0) return 0;
+    for (int d = 0; d < p->D; ++d)
+        if (!x[d]) return fail(VGGP_E_ARG, "null observation pointer");
+    if (p->family != VGGP_B1_ASVGP)
+        return fail(VGGP_E_UNSUPPORTED, "per-observation kernel for the B0 (cell-integrated) family is not built yet");
+    if (p->obs_dtype == VGGP_F32) return obs_dispatch_D<float>(p, x, y, n, gbuf, st);
+    return obs_dispatch_D<double>(p, x, y, n, gbuf, st);
+}
+
+int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,
+                       double ell_scale, double* out, double* dtheta, double* dm, double* dL, void* stream) {
+    if (!p || !theta || !m || !L || !gbuf || !out || !dtheta || !dm || !dL) return fail(VGGP_E_ARG, "null argument");
+    (void)L;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->D;
+    int rc;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    const double* gscal = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(gbuf) + soff);
+    const int mblocks = (int)std::min<i64>((p->M + 255) / 256, 148 * 4);
+    if (p->obs_dtype == VGGP_F32)
+        k_bwd_prep<float><<<mblocks, 256, 0, st>>>(reinterpret_cast<const float*>(gbuf), p->mws, theta, D, ell_scale, p->gM, p->ghat, p->M);
+    else
+        k_bwd_prep<double><<<mblocks, 256, 0, st>>>(reinterpret_cast<const double*>(gbuf), p->mws, theta, D, ell_scale, p->gM, p->ghat, p->M);
+    VGGP_LAUNCH_CHECK();
+    for (auto& ph : p->dm_chain) if ((rc = launch_phase(ph, st))) return rc;
+    k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
+    VGGP_LAUNCH_CHECK();
+    for (int d = 0; d < D; ++d)
+        VGGP_CUDA(cudaMemsetAsync(p->g.dP[d], 0, sizeof(double) * (size_t)p->n[d] * p->n[d], st));
+    if ((rc = launch_phase(p->gram, st))) return rc;
+    const i64 nn = (i64)p->nmax * p->nmax;
+    dim3 egrid(ceil_div(nn, 256), D);
+    if (p->obs_dtype == VGGP_F32)
+        k_bwd_dP_dR<float><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const float*>(gbuf) + p->M, theta, ell_scale);
+    else
+        k_bwd_dP_dR<double><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const double*>(gbuf) + p->M, theta, ell_scale);
+    VGGP_LAUNCH_CHECK();
+    if ((rc = launch_phase(p->dPdL, st))) return rc;
+    k_sym<<<egrid, 256, 0, st>>>(p->g);
+    VGGP_LAUNCH_CHECK();
+    if ((rc = launch_phase(p->Yp, st))) return rc;
+    if ((rc = launch_phase(p->dKp, st))) return rc;
+    k_bwd_dL<<<egrid, 256, 0, st>>>(p->g, dL);
+    VGGP_LAUNCH_CHECK();
+    k_bwd_theta<<<D, 1024, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
+    if (!p || !info_host) return fail(VGGP_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGGP_CUDA(cudaMemcpyAsync(info_host, p->g.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VGGP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vggp_elbo_host(vggp_plan* p, const void* const* x_host, const void* y_host, int64_t n, const double* theta_host,
+                   const double* m_host, const double* L_host, double ell_scale, double* out_host,
+                   double* dtheta_host, double* dm_host, double* dL_host, void* stream) {
+    if (!p || !theta_host || !m_host || !L_host || !out_host || !dtheta_host || !dm_host || !dL_host || n < 0)
+        return fail(VGGP_E_ARG, "bad argument");
+    if (n > 0 && (!x_host || !y_host)) return fail(VGGP_E_ARG, "null observation pointers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->D;
+    const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    if (!p->st_theta) {
+        VGGP_CUDA(cudaMalloc(&p->st_theta, sizeof(double) * (2 * D + 1)));
+        VGGP_CUDA(cudaMalloc(&p->st_dtheta, sizeof(double) * (2 * D + 1)));
+        VGGP_CUDA(cudaMalloc(&p->st_out, sizeof(double) * 4));
+        VGGP_CUDA(cudaMalloc(&p->st_m, sizeof(double) * p->M));
+        VGGP_CUDA(cudaMalloc(&p->st_dm, sizeof(double) * p->M));
+        VGGP_CUDA(cudaMalloc(&p->st_L, sizeof(double) * p->Lsize));
+        VGGP_CUDA(cudaMalloc(&p->st_dL, sizeof(double) * p->Lsize));
+        VGGP_CUDA(cudaMalloc(&p->st_gbuf, (size_t)total));
+    }
+    if (n > p->st_n) {
+        if (p->st_x) cudaFree(p->st_x);
+        if (p->st_y) cudaFree(p->st_y);
+        p->st_x = p->st_y = nullptr; p->st_n = 0;
+        VGGP_CUDA(cudaMalloc(&p->st_x, tsz * (size_t)n * D));
+        VGGP_CUDA(cudaMalloc(&p->st_y, tsz * (size_t)n));
+        p->st_n = n;
+    }
+    const void* xdev[VGGP_MAX_D] = {nullptr, nullptr, nullptr};
+    for (int d = 0; d < D && n > 0; ++d) {
+        unsigned char* dst = reinterpret_cast<unsigned char*>(p->st_x) + (size_t)d * n * tsz;
+        VGGP_CUDA(cudaMemcpyAsync(dst, x_host[d], tsz * (size_t)n, cudaMemcpyHostToDevice, st));
+        xdev[d] = dst;
+    }
+    if (n > 0) VGGP_CUDA(cudaMemcpyAsync(p->st_y, y_host, tsz * (size_t)n, cudaMemcpyHostToDevice, st));
+    VGGP_CUDA(cudaMemcpyAsync(p->st_theta, theta_host, sizeof(double) * (2 * D + 1), cudaMemcpyHostToDevice, st));
+    VGGP_CUDA(cudaMemcpyAsync(p->st_m, m_host, sizeof(double) * p->M, cudaMemcpyHostToDevice, st));
+    VGGP_CUDA(cudaMemcpyAsync(p->st_L, L_host, sizeof(double) * p->Lsize, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = vggp_grid_forward(p, p->st_theta, p->st_m, p->st_L, stream))) return rc;
+    if ((rc = vggp_obs_fwd_bwd(p, xdev, p->st_y, n, p->st_gbuf, stream))) return rc;
+    if ((rc = vggp_grid_backward(p, p->st_theta, p->st_m, p->st_L, p->st_gbuf, ell_scale, p->st_out, p->st_dtheta,
+                                 p->st_dm, p->st_dL, stream))) return rc;
+    VGGP_CUDA(cudaMemcpyAsync(out_host, p->st_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    VGGP_CUDA(cudaMemcpyAsync(dtheta_host, p->st_dtheta, sizeof(double) * (2 * D + 1), cudaMemcpyDeviceToHost, st));
+    VGGP_CUDA(cudaMemcpyAsync(dm_host, p->st_dm, sizeof(double) * p->M, cudaMemcpyDeviceToHost, st));
+    VGGP_CUDA(cudaMemcpyAsync(dL_host, p->st_dL, sizeof(double) * p->Lsize, cudaMemcpyDeviceToHost, st));
+    VGGP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vggp_b1_stencil(const vggp_plan* p, int dim, const void* x, int64_t n, int32_t* c, void* w_lo, void* w_hi,
+                    void* stream) {
+    if (!p || dim < 0 || dim >= p->D || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!x || !c || !w_lo || !w_hi) return fail(VGGP_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 8);
+    if (p->obs_dtype == VGGP_F32)
+        k_b1_stencil<float><<<blocks, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, c, (float*)w_lo, (float*)w_hi);
+    else
+        k_b1_stencil<double><<<blocks, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, c, (double*)w_lo, (double*)w_hi);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, const double* theta, void* phi,
+                        void* stream) {
+    if (!p || dim < 0 || dim >= p->D || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!x || !phi) return fail(VGGP_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    if (p->family == VGGP_B1_ASVGP) {
+        VGGP_CUDA(cudaMemsetAsync(phi, 0, tsz * (size_t)n * p->n[dim], st));
+        const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 8);
+        if (p->obs_dtype == VGGP_F32) k_b1_dense<float><<<blocks, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, (float*)phi);
+        else k_b1_dense<double><<<blocks, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, (double*)phi);
+    } else {
+        if (!theta) return fail(VGGP_E_ARG, "theta required for the B0 family");
+        double th[2 * VGGP_MAX_D + 1];
+        VGGP_CUDA(cudaMemcpyAsync(th, theta, sizeof(double) * (2 * p->D + 1), cudaMemcpyDeviceToHost, st));
+        VGGP_CUDA(cudaStreamSynchronize(st));
+        dim3 grid(ceil_div(n, 256), p->n[dim]);
+        if (p->obs_dtype == VGGP_F32)
+            k_b0_dense<float><<<grid, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, th[dim], th[p->D + dim], (float*)phi);
+        else
+            k_b0_dense<double><<<grid, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, th[dim], th[p->D + dim], (double*)phi);
+    }
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {
+    if (!p || !ptr) return fail(VGGP_E_ARG, "null argument");
+    if (which != VGGP_WS_ALPHA && which != VGGP_WS_SCAL && (dim < 0 || dim >= p->D)) return fail(VGGP_E_ARG, "bad dim");
+    const i64 nn = (which == VGGP_WS_ALPHA || which == VGGP_WS_SCAL) ? 0 : (i64)p->n[dim] * p->n[dim];
+    switch (which) {
+        case VGGP_WS_K: *ptr = p->g.Kc[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_P: *ptr = p->g.P[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_R: *ptr = p->g.R[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_Q: *ptr = p->g.Q[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_S: *ptr = p->g.S[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_KRAW: *ptr = p->g.Kraw[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_ALPHA: *ptr = p->alpha; if (n_elems) *n_elems = p->M; return 0;
+        case VGGP_WS_SCAL: *ptr = p->g.sc; if (n_elems) *n_elems = SC_COUNT; return 0;
+    }
+    return fail(VGGP_E_ARG, "unknown workspace id");
+}
+
+int vggp_gemm_f64(int use_mma, int batch, int m, int n, int k, double alpha, const double* A, int64_t rsA, int64_t csA,
+                  int64_t bsA, const double* B, int64_t rsB, int64_t csB, int64_t bsB, double beta, double* C,
+                  int64_t rsC, int64_t csC, int64_t bsC, int splitk, void* stream) {
+    if (!A || !B || !C || m < 0 || n < 0 || k < 0 || batch < 1) return fail(VGGP_E_ARG, "bad argument");
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    d.A = A; d.B = B; d.C = C; d.m = m; d.n = n; d.k = k;
+    d.rsA = rsA; d.csA = csA; d.bsA = bsA; d.rsB = rsB; d.csB = csB; d.bsB = bsB; d.rsC = rsC; d.csC = csC; d.bsC = bsC;
+    d.alpha = alpha; d.beta = beta; d.batch = batch; d.splitk = splitk < 1 ? 1 : splitk;
+    return launch_one(d, use_mma, (cudaStream_t)stream);
+}
+
+int vggp_mode_product(vggp_plan* p, int dim, const double* A, const double* src, double* dst, void* stream) {
+    if (!p || !A || !src || !dst || dim < 0 || dim >= p->D) return fail(VGGP_E_ARG, "bad argument");
+    return launch_one(mode_desc(p, dim, A, src, dst), g_use_mma, (cudaStream_t)stream);
+}
+
+}  // extern "C"

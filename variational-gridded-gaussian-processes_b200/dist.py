@@ -1,0 +1,47 @@
+"""Observation-axis data parallelism: contiguous equal shards of the observation arrays,
+replicated grid-side parameters, ONE sum-all-reduce of the per-observation gradient buffer per step.
+Device-agnostic torch.distributed plumbing (NCCL on the GPUs, gloo in the CPU tests)."""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of rank's contiguous slice; sizes differ by at most one, every observation belongs to one rank."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    base, rem = divmod(int(n), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_gbuf_views(raw: torch.Tensor, obs: torch.Tensor, scal: torch.Tensor, group=None) -> None:
+    """Sum the gradient buffer over ranks.  float64 observations: the whole allocation is one float64 vector and
+    one collective; float32 observations: the float32 block and the float64 scalar block are two typed views of
+    the same allocation and go out as two collectives issued back to back."""
+    if obs.dtype == torch.float64 and raw.numel() % 8 == 0:
+        dist.all_reduce(raw.view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the default group when world > 1."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local_rank, world

@@ -1,0 +1,206 @@
+"""Shared implementation of the gridded sparse variational GP models (D = 1, 2, 3).
+
+What the reference does in `_elbo()` (kronecker_structure.py:249-278): builds dense Kuu = torch.kron(K_1, K_2),
+dense Kuf (Khatri-Rao) and N x N evidence matrices for the *collapsed* bound.  Here `_elbo()` is the uncollapsed
+bound with explicit variational parameters q(u) = N(m, kron_d L_d L_d^T) evaluated by
+libvggp: per-dimension Cholesky / inverse / Kronecker mode-n products on the grid side and one fused
+per-observation kernel; at the optimal q(u) the two bounds coincide (tests/test_oracle_identities.py).
+
+Training-loop API kept from the notebooks (5_gridded_kronecker_structure_models.ipynb:438-446):
+    opt = torch.optim.Adam(model.parameters()); loss = -model._elbo(); loss.backward(); opt.step()
+"""
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .. import _lib
+from ..params import GaussianLikelihood, GriddedNormal, MaternKernel, ScaleKernel
+from ..plan import GridPlan, gridded_elbo
+from ..dist import shard_bounds
+
+
+class GriddedVariationalGP(nn.Module):
+    family: int = _lib.B1_ASVGP
+
+    def __init__(self, X: torch.Tensor, y: torch.Tensor, meshes: Sequence[torch.Tensor]):
+        super().__init__()
+        self.train_inputs = (X,)
+        self.train_targets = y
+        self.likelihood = GaussianLikelihood()
+        self.D = len(meshes)
+        self._meshes = [m.detach().to(torch.float32).cpu() for m in meshes]
+        if self.D == 1:
+            # univariate_structure.py:563-571: a single `kernel`
+            self.kernel = ScaleKernel(MaternKernel(nu=0.5))
+            self._kernels = [self.kernel]
+        else:
+            # kronecker_structure.py:30-32: kernel_1, kernel_2 (kernel_3 for the 3-D generalisation)
+            self._kernels = []
+            for d in range(self.D):
+                k = ScaleKernel(MaternKernel(nu=0.5, active_dims=[d]))
+                setattr(self, f"kernel_{d + 1}", k)
+                self._kernels.append(k)
+        self.m_per_dim = [m.numel() if self.family == _lib.B1_ASVGP else m.numel() - 1 for m in self._meshes]
+        M = 1
+        for n in self.m_per_dim:
+            M *= n
+        self.M = M
+        # variational parameters: q(u) = N(m, kron_d L_d L_d^T)
+        self.variational_mean = nn.Parameter(torch.zeros(M))
+        self._chol_names = []
+        for d, n in enumerate(self.m_per_dim):
+            name = f"variational_chol_{d + 1}"
+            setattr(self, name, nn.Parameter(torch.eye(n)))
+            self._chol_names.append(name)
+        self._plan: Optional[GridPlan] = None
+        self._obs = None
+        self._group = None
+        self._n_total = int(y.numel())
+
+    # ---- parameters as the kernels see them -----------------------------------------------------------------
+    def _chols(self) -> List[torch.Tensor]:
+        return [getattr(self, n) for n in self._chol_names]
+
+    def _hyper(self):
+        ls = torch.cat([k.base_kernel.lengthscale.reshape(-1) for k in self._kernels])
+        os_ = torch.cat([k.outputscale.reshape(-1) for k in self._kernels])
+        return ls, os_, self.likelihood.noise.reshape(-1)
+
+    # ---- data placement -------------------------------------------------------------------------------------
+    def set_train_data(self, X: torch.Tensor, y: torch.Tensor):
+        self.train_inputs = (X,)
+        self.train_targets = y
+        self._n_total = int(y.numel())
+        self._obs = None
+
+    def shard_observations(self, rank: int, world: int, group="world"):
+        """Keep this rank's contiguous slice of the observations; `_elbo()` then all-reduces the per-observation
+        gradient buffer over `group`.  Call on every rank with the same full data set."""
+        X, y = self.train_inputs[0], self.train_targets
+        lo, hi = shard_bounds(y.numel(), rank, world)
+        self._n_total = int(y.numel())
+        self.train_inputs = (X[lo:hi],)
+        self.train_targets = y[lo:hi]
+        self._group = group if world > 1 else None
+        self._obs = None
+
+    def _device_dtype(self):
+        p = self.variational_mean
+        if p.device.type != "cuda":
+            raise RuntimeError("the ELBO path runs only on CUDA (sm_100a): move the model with .to('cuda'); "
+                               "there is no CPU fallback")
+        return p.device, p.dtype
+
+    def _ensure_plan(self):
+        device, dtype = self._device_dtype()
+        if self._plan is None or self._plan.device != device or self._plan.obs_dtype != dtype:
+            self._plan = GridPlan(self.family, self._meshes, dtype, device)
+            self._obs = None
+        if self._obs is None:
+            X = self.train_inputs[0]
+            X = X.reshape(X.shape[0], -1) if X.dim() > 1 else X.reshape(-1, 1)
+            if X.shape[1] != self.D:
+                raise ValueError(f"X must have {self.D} columns")
+            Xd = X.to(device=device, dtype=dtype)
+            xs = [Xd[:, d].contiguous() for d in range(self.D)]       # structure of arrays, made once
+            y = self.train_targets.reshape(-1).to(device=device, dtype=dtype).contiguous()
+            self._obs = (xs, y)
+        return self._plan
+
+    # ---- the hot path ---------------------------------------------------------------------------------------
+    def _elbo(self, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Evidence lower bound (0-dim tensor with grad_fn).  `batch`: optional index tensor / slice selecting a
+        minibatch of this rank's observations; the expected log-likelihood is rescaled by N / B."""
+        plan = self._ensure_plan()
+        xs, y = self._obs
+        scale = 1.0
+        if batch is not None:
+            xs = [x[batch].contiguous() for x in xs]
+            y = y[batch].contiguous()
+            n_local = self._obs[1].numel()
+            scale = float(n_local) / float(max(1, y.numel()))
+        ls, os_, noise = self._hyper()
+        return gridded_elbo(plan, xs, y, ls, os_, noise, self.variational_mean, self._chols(),
+                            ell_scale=scale, group=self._group)
+
+    def elbo_terms(self) -> torch.Tensor:
+        """[ELBO, scaled ELL, KL, n_obs] of the last `_elbo()` call (device tensor, no sync)."""
+        raise NotImplementedError
+
+    # ---- variational distribution ---------------------------------------------------------------------------
+    def q_u(self) -> GriddedNormal:
+        """q(u) = N(m, kron_d L_d L_d^T): the *learned* variational distribution.  (The reference's q_u() returns
+        the analytically optimal one, gridded_kronecker_structure.py:903-916; the two agree at the optimum.)"""
+        Ss = []
+        for L in self._chols():
+            Lt = torch.tril(L.detach())
+            Ss.append(Lt @ Lt.T)
+        return GriddedNormal(self.variational_mean.detach(), Ss)
+
+    # ---- reference plug-in points (dense, small problems only) -------------------------------------------------
+    def _theta(self) -> torch.Tensor:
+        ls, os_, noise = self._hyper()
+        return torch.cat([ls, os_, noise]).detach().to(torch.float64).contiguous()
+
+    def _Kuu_along_dim(self, dim: int) -> torch.Tensor:
+        plan = self._ensure_plan()
+        theta = self._theta()
+        m = self.variational_mean.detach().to(torch.float64).contiguous()
+        L = torch.cat([c.detach().to(torch.float64).reshape(-1) for c in self._chols()]).contiguous()
+        plan.grid_forward(theta, m, L)
+        return plan.workspace(_lib.WS_KRAW, dim)
+
+    def _Kuf_along_dim(self, dim: int, x: torch.Tensor) -> torch.Tensor:
+        plan = self._ensure_plan()
+        return plan.features_dense(dim, x, self._theta())
+
+    def _Kuu(self) -> torch.Tensor:
+        out = self._Kuu_along_dim(0)
+        for d in range(1, self.D):
+            out = torch.kron(out, self._Kuu_along_dim(d))
+        return out
+
+    def _Kuf(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.reshape(x.shape[0], -1) if x.dim() > 1 else x.reshape(-1, 1)
+        feats = [self._Kuf_along_dim(d, x[:, d].contiguous()) for d in range(self.D)]
+        out = feats[0]
+        for f in feats[1:]:
+            out = (out[:, None, :] * f[None, :, :]).reshape(-1, f.shape[-1])
+        return out
+
+    # ---- initialisers (kronecker_structure.py:34-88; evident intent) ----------------
+    def non_informative_initialise(self, lmbda: float, kappa: float) -> None:
+        X = self.train_inputs[0]
+        X = X.reshape(X.shape[0], -1) if X.dim() > 1 else X.reshape(-1, 1)
+        y = self.train_targets
+        for d, k in enumerate(self._kernels):
+            k.outputscale = y.var()
+            k.base_kernel.lengthscale = X[:, d].std() / lmbda
+        mean_os = sum(k.outputscale for k in self._kernels) / len(self._kernels)
+        self.likelihood.noise = mean_os / (kappa ** 2)
+
+    def informative_initialise(self, prior_amplitude: float, lmbda: float) -> None:
+        X = self.train_inputs[0]
+        X = X.reshape(X.shape[0], -1) if X.dim() > 1 else X.reshape(-1, 1)
+        y = self.train_targets
+        for d, k in enumerate(self._kernels):
+            k.outputscale = (torch.tensor(prior_amplitude) / 2) ** 2
+            k.base_kernel.lengthscale = X[:, d].std() / lmbda
+        mean_os = sum(k.outputscale for k in self._kernels) / len(self._kernels)
+        self.likelihood.noise = y.var() - mean_os
+
+
+def linspace_mesh(lims, n_knots: int) -> torch.Tensor:
+    """float32 torch.linspace without dtype, exactly as the reference builds its meshes."""
+    return torch.linspace(lims[0], lims[1], n_knots)
+
+
+def padded_b0_mesh(lims, n_b0_splines: int, padding_factor: int):
+    """gridded_kronecker_structure.py:707-720: B0 mesh plus `padding_factor` extra knots each side, built from
+    Python floats of float32 values."""
+    b0 = torch.linspace(lims[0], lims[1], n_b0_splines + 1)
+    d = b0[1] - b0[0]
+    left = torch.tensor([(b0[0] - (i * d)).item() for i in range(padding_factor, 0, -1)])
+    right = torch.tensor([(b0[-1] + (i * d)).item() for i in range(1, padding_factor + 1)])
+    return b0, d, torch.cat((left, b0, right))

@@ -1,0 +1,234 @@
+"""Host-side wrapper of one libvggp plan + the autograd bridge used by the model classes.
+
+The three C-ABI calls of a step (grid forward -> per-observation forward+backward -> grid backward) run
+asynchronously on torch's current CUDA stream; with a process group, the single all-reduce(sum) of the
+per-observation gradient buffer sits between the second and third call."""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_TORCH_DTYPE = {_lib.F32: torch.float32, _lib.F64: torch.float64}
+_OBS_CODE = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class GridPlan:
+    """Grid descriptor (family, per-dimension float32 meshes) + device workspace."""
+
+    def __init__(self, family: int, meshes: Sequence[torch.Tensor], obs_dtype: torch.dtype, device):
+        lib = _lib.load()
+        self.lib = lib
+        self.family = int(family)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GridPlan needs a CUDA device: this package has no CPU path")
+        self.obs_dtype = obs_dtype
+        self.D = len(meshes)
+        self.meshes = [m.detach().to("cpu", torch.float32).contiguous() for m in meshes]
+        n_knots = (C.c_int * self.D)(*[int(m.numel()) for m in self.meshes])
+        ptrs = (C.POINTER(C.c_float) * self.D)(
+            *[C.cast(m.data_ptr(), C.POINTER(C.c_float)) for m in self.meshes])
+        handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        _lib.check(lib.vggp_plan_create(C.byref(handle), self.family, self.D, n_knots, ptrs,
+                                        _OBS_CODE[obs_dtype], dev_index))
+        self.handle = handle
+        dims = (C.c_int * 3)()
+        M = C.c_int64()
+        Dd = C.c_int()
+        _lib.check(lib.vggp_plan_dims(handle, C.byref(Dd), dims, C.byref(M)))
+        self.m_per_dim = [int(dims[d]) for d in range(self.D)]
+        self.M = int(M.value)
+        self.L_sizes = [n * n for n in self.m_per_dim]
+        self.L_total = sum(self.L_sizes)
+        ne, so, ns, tot = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.vggp_gbuf_layout(handle, C.byref(ne), C.byref(so), C.byref(ns), C.byref(tot)))
+        self.gbuf_obs_elems, self.gbuf_scalar_offset = int(ne.value), int(so.value)
+        self.gbuf_scalars, self.gbuf_bytes = int(ns.value), int(tot.value)
+        self.gbuf = torch.zeros(self.gbuf_bytes, dtype=torch.uint8, device=self.device)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.vggp_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- views of the gradient buffer (what gets all-reduced) ------------------------------------------------
+    def gbuf_views(self, gbuf: Optional[torch.Tensor] = None):
+        g = self.gbuf if gbuf is None else gbuf
+        esz = 4 if self.obs_dtype == torch.float32 else 8
+        obs = g[: self.gbuf_obs_elems * esz].view(self.obs_dtype)
+        scal = g[self.gbuf_scalar_offset: self.gbuf_scalar_offset + 8 * self.gbuf_scalars].view(torch.float64)
+        return obs, scal
+
+    # -- the three calls -------------------------------------------------------------------------------------
+    def grid_forward(self, theta: torch.Tensor, m: torch.Tensor, L: torch.Tensor):
+        self._check_f64(theta, 2 * self.D + 1, "theta")
+        self._check_f64(m, self.M, "m")
+        self._check_f64(L, self.L_total, "L")
+        _lib.check(self.lib.vggp_grid_forward(self.handle, theta.data_ptr(), m.data_ptr(), L.data_ptr(),
+                                              _stream_ptr(self.device)))
+
+    def obs_fwd_bwd(self, xs: Sequence[torch.Tensor], y: torch.Tensor, gbuf: Optional[torch.Tensor] = None):
+        g = self.gbuf if gbuf is None else gbuf
+        n = int(y.numel())
+        for t in list(xs) + [y]:
+            if t.dtype != self.obs_dtype or t.device != self.device or not t.is_contiguous() or t.numel() != n:
+                raise ValueError("observations must be contiguous 1-D tensors of the plan's dtype on the plan's device")
+        ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
+        _lib.check(self.lib.vggp_obs_fwd_bwd(self.handle, ptrs, y.data_ptr(), n, g.data_ptr(),
+                                             _stream_ptr(self.device)))
+
+    def grid_backward(self, theta, m, L, ell_scale: float, gbuf: Optional[torch.Tensor] = None):
+        g = self.gbuf if gbuf is None else gbuf
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        dtheta = torch.empty(2 * self.D + 1, dtype=torch.float64, device=self.device)
+        dm = torch.empty(self.M, dtype=torch.float64, device=self.device)
+        dL = torch.empty(self.L_total, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.vggp_grid_backward(self.handle, theta.data_ptr(), m.data_ptr(), L.data_ptr(),
+                                               g.data_ptr(), float(ell_scale), out.data_ptr(), dtheta.data_ptr(),
+                                               dm.data_ptr(), dL.data_ptr(), _stream_ptr(self.device)))
+        return out, dtheta, dm, dL
+
+    def allreduce_gbuf(self, group=None, gbuf: Optional[torch.Tensor] = None):
+        """One sum-all-reduce of the per-observation gradient buffer (two typed views of one allocation when the
+        observation dtype is float32, a single float64 view otherwise)."""
+        from .dist import allreduce_gbuf_views
+        g = self.gbuf if gbuf is None else gbuf
+        obs, scal = self.gbuf_views(g)
+        allreduce_gbuf_views(g, obs, scal, group)
+
+    def step(self, theta, m, L, xs, y, ell_scale: float = 1.0, group=None):
+        """ELBO and all gradients for one (sharded) minibatch.  Returns (out[4], dtheta, dm, dL).
+        `group`: None = single process; "world" or a ProcessGroup = all-reduce the gradient buffer over it."""
+        self.grid_forward(theta, m, L)
+        self.obs_fwd_bwd(xs, y)
+        if group is not None:
+            self.allreduce_gbuf(None if isinstance(group, str) else group)
+        return self.grid_backward(theta, m, L, ell_scale)
+
+    def read_info(self) -> int:
+        info = C.c_int(0)
+        _lib.check(self.lib.vggp_read_info(self.handle, C.byref(info), _stream_ptr(self.device)))
+        return int(info.value)
+
+    # -- feature evaluation ----------------------------------------------------------------------------------
+    def b1_stencil(self, dim: int, x: torch.Tensor):
+        x = x.to(self.device, self.obs_dtype).contiguous()
+        n = x.numel()
+        c = torch.empty(n, dtype=torch.int32, device=self.device)
+        wl = torch.empty_like(x)
+        wh = torch.empty_like(x)
+        _lib.check(self.lib.vggp_b1_stencil(self.handle, dim, x.data_ptr(), n, c.data_ptr(), wl.data_ptr(),
+                                            wh.data_ptr(), _stream_ptr(self.device)))
+        return c, wl, wh
+
+    def features_dense(self, dim: int, x: torch.Tensor, theta: Optional[torch.Tensor] = None):
+        x = x.to(self.device, self.obs_dtype).contiguous()
+        n = x.numel()
+        phi = torch.empty(self.m_per_dim[dim], n, dtype=self.obs_dtype, device=self.device)
+        tp = theta.data_ptr() if theta is not None else None
+        _lib.check(self.lib.vggp_features_dense(self.handle, dim, x.data_ptr(), n, tp, phi.data_ptr(),
+                                                _stream_ptr(self.device)))
+        return phi
+
+    # -- workspace views -------------------------------------------------------------------------------------
+    def workspace(self, which: int, dim: int = 0) -> torch.Tensor:
+        """Copy of a float64 workspace array of the last forward (tests / predictions)."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.vggp_workspace_ptr(self.handle, which, dim, C.byref(ptr), C.byref(n)))
+        out = torch.as_tensor(_DevArray(ptr.value, int(n.value)), device=self.device).clone()
+        if which in (_lib.WS_ALPHA, _lib.WS_SCAL):
+            return out
+        nd = self.m_per_dim[dim]
+        return out.view(nd, nd)
+
+    def mode_product(self, dim: int, A: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+        dst = torch.empty_like(src)
+        _lib.check(self.lib.vggp_mode_product(self.handle, dim, A.data_ptr(), src.data_ptr(), dst.data_ptr(),
+                                              _stream_ptr(self.device)))
+        return dst
+
+    def _check_f64(self, t: torch.Tensor, numel: int, name: str):
+        if t.dtype != torch.float64 or t.device != self.device or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"{name} must be a contiguous float64 tensor with {numel} elements on {self.device}")
+
+
+class _DevArray:
+    """float64 device array seen through __cuda_array_interface__ (zero-copy view of plan workspace)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def gemm_f64(A: torch.Tensor, B: torch.Tensor, use_mma: bool = True, splitk: int = 1,
+             alpha: float = 1.0, beta: float = 0.0, C_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = alpha * A @ B + beta * C through vggp_gemm_f64 (arbitrary strides; optional leading batch dim)."""
+    lib = _lib.load()
+    if A.dim() == 2:
+        A = A.unsqueeze(0)
+        B = B.unsqueeze(0)
+        squeeze = True
+    else:
+        squeeze = False
+    batch, m, k = A.shape
+    n = B.shape[2]
+    Cm = torch.zeros(batch, m, n, dtype=torch.float64, device=A.device) if C_in is None else C_in.reshape(batch, m, n)
+    _lib.check(lib.vggp_gemm_f64(1 if use_mma else 0, batch, m, n, k, float(alpha),
+                                 A.data_ptr(), A.stride(1), A.stride(2), A.stride(0) if batch > 1 else 0,
+                                 B.data_ptr(), B.stride(1), B.stride(2), B.stride(0) if batch > 1 else 0,
+                                 float(beta), Cm.data_ptr(), Cm.stride(1), Cm.stride(2), Cm.stride(0),
+                                 int(splitk), _stream_ptr(A.device)))
+    return Cm[0] if squeeze else Cm
+
+
+class _GriddedELBO(torch.autograd.Function):
+    """ELBO(theta, m, L_1..L_D) with the reverse pass computed in the same fused step."""
+
+    @staticmethod
+    def forward(ctx, plan: GridPlan, xs, y, ell_scale, group, lengthscale, outputscale, noise, m, *Ls):
+        theta = torch.cat([lengthscale.reshape(-1), outputscale.reshape(-1), noise.reshape(-1)]).to(torch.float64).contiguous()
+        m64 = m.detach().to(torch.float64).contiguous()
+        L64 = torch.cat([L.detach().to(torch.float64).reshape(-1) for L in Ls]).contiguous()
+        out, dtheta, dm, dL = plan.step(theta.detach(), m64, L64, xs, y, ell_scale, group)
+        D = plan.D
+        ctx.D = D
+        ctx.shapes = (lengthscale.shape, outputscale.shape, noise.shape, m.shape, [L.shape for L in Ls])
+        ctx.dtypes = (lengthscale.dtype, outputscale.dtype, noise.dtype, m.dtype, [L.dtype for L in Ls])
+        ctx.L_sizes = plan.L_sizes
+        ctx.save_for_backward(dtheta, dm, dL)
+        ctx.aux = out
+        return out[0].to(m.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dtheta, dm, dL = ctx.saved_tensors
+        D = ctx.D
+        go = grad_out.to(torch.float64)
+        sl, ss, sn, sm, sL = ctx.shapes
+        tl, ts, tn, tm, tL = ctx.dtypes
+        g_l = (go * dtheta[:D]).reshape(sl).to(tl)
+        g_s = (go * dtheta[D:2 * D]).reshape(ss).to(ts)
+        g_n = (go * dtheta[2 * D]).reshape(sn).to(tn)
+        g_m = (go * dm).reshape(sm).to(tm)
+        gLs = []
+        off = 0
+        for shp, dt, sz in zip(sL, tL, ctx.L_sizes):
+            gLs.append((go * dL[off:off + sz]).reshape(shp).to(dt))
+            off += sz
+        return (None, None, None, None, None, g_l, g_s, g_n, g_m, *gLs)
+
+
+def gridded_elbo(plan: GridPlan, xs: List[torch.Tensor], y: torch.Tensor, lengthscale, outputscale, noise, m,
+                 Ls: Sequence[torch.Tensor], ell_scale: float = 1.0, group=None) -> torch.Tensor:
+    return _GriddedELBO.apply(plan, xs, y, ell_scale, group, lengthscale, outputscale, noise, m, *Ls)
