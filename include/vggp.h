@@ -113,13 +113,32 @@ int vggp_gbuf_layout(const vggp_plan* plan, int64_t* n_obs_elems, int64_t* scala
 int vggp_grid_forward(vggp_plan* plan, const double* theta, const double* m, const double* L, void* stream);
 
 /*
- * Per-observation fused forward+backward over one shard of the minibatch.
- *   x      [D] HOST array of device pointers, x[d] -> n values of obs_dtype (structure of arrays)
- *   y      n values of obs_dtype
- *   n      number of observations in this shard (may be 0)
- *   gbuf   output, layout above; zeroed by this call, then accumulated.
- * Reads alpha / band tables produced by the last vggp_grid_forward on the same plan.
+ * Packed observation layout (setup, once per data set / minibatch partition; X is constant over optimisation
+ * steps).  The fused kernel gives every lane one contiguous run of `run_len` observations and reads them
+ * "warp-transposed" so that the loads stay coalesced; padding slots hold NaN.  With sort_by_cell != 0 the
+ * observations are first ordered by flat grid-cell id (stable radix sort), so that a lane's run stays inside one
+ * cell for as long as possible; this changes only the order of the summation, not the result.
+ *   vggp_obs_pack_geometry  n -> padded length of every packed array and the run length (depends on the device)
+ *   vggp_obs_pack           x[D], y (n values each) -> xp[D], yp (n_packed values each, caller-allocated).
+ *                           May allocate temporary sort buffers (freed before returning, synchronises `stream`
+ *                           in that case); with sort_by_cell == 0 it is allocation-free and asynchronous.
  */
+int vggp_obs_pack_geometry(const vggp_plan* plan, int64_t n, int64_t* n_packed, int* run_len);
+int vggp_obs_pack(vggp_plan* plan, const void* const* x, const void* y, int64_t n, int sort_by_cell,
+                  void* const* xp, void* yp, void* stream);
+
+/*
+ * Per-observation fused forward+backward over one shard of the minibatch.
+ *   x / xp [D] HOST array of device pointers to structure-of-arrays observations of obs_dtype
+ *   y / yp     targets
+ *   n          number of (real) observations in this shard (may be 0)
+ *   gbuf       output, layout above; zeroed by this call, then accumulated.
+ * Reads alpha / band tables produced by the last vggp_grid_forward on the same plan.
+ * vggp_obs_fwd_bwd_packed consumes arrays produced by vggp_obs_pack (the hot-path form: nothing but the fused
+ * kernel runs).  vggp_obs_fwd_bwd takes plain arrays in any order: it first transposes them into plan-owned
+ * scratch (grown on demand -- the one allocation this call may make), then runs the same kernel.
+ */
+int vggp_obs_fwd_bwd_packed(vggp_plan* plan, const void* const* xp, const void* yp, int64_t n, void* gbuf, void* stream);
 int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream);
 
 /*

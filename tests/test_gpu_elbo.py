@@ -74,9 +74,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("layout", ["raw", "packed_sorted", "packed_unsorted"])
 @pytest.mark.parametrize("knots,N", CASES)
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
-def test_elbo_and_grads_match_oracle_b1(vg, dev, knots, N, dtype, tol):
+def test_elbo_and_grads_match_oracle_b1(vg, dev, knots, N, dtype, tol, layout):
     D = len(knots)
     meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=42 + D)
     Xq = X.to(dtype)          # quantise the observations once so oracle and kernel see identical inputs
@@ -88,7 +89,12 @@ def test_elbo_and_grads_match_oracle_b1(vg, dev, knots, N, dtype, tol):
     theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
     Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
     xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
-    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=scale)
+    if layout == "raw":
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=scale)
+    else:
+        packed = plan.pack(xs, yq.to(dev), sort_by_cell=(layout == "packed_sorted"))
+        assert packed.n == N and packed.run_len % 4 == 0
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, packed, None, ell_scale=scale)
     assert plan.read_info() == 0
     assert out[3].item() == N
     assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (out.cpu(), elbo_ref)
@@ -222,6 +228,41 @@ def test_model_class_training_loop_api(vg, dev):
         opt.step()
         first = loss.item() if first is None else first
     assert (-model._elbo()).item() < first
+
+
+def test_packing_is_a_permutation(vg, dev):
+    """vggp_obs_pack keeps every observation exactly once (multiset equality), pads with NaN / 0, and with
+    sort_by_cell orders each lane's run by flat cell id."""
+    meshes = [torch.linspace(0, 1, 40), torch.linspace(0, 1, 23)]
+    g = torch.Generator().manual_seed(3)
+    N = 10007
+    X = (torch.rand(N, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1).to(torch.float32)
+    y = torch.randn(N, generator=g, dtype=torch.float64).to(torch.float32)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    xs = [X[:, d].contiguous().to(dev) for d in range(2)]
+    for sort in (False, True):
+        pk = plan.pack(xs, y.to(dev), sort_by_cell=sort)
+        R = pk.run_len
+        yp = pk.yp.cpu()
+        x1p, x2p = pk.xp[0].cpu(), pk.xp[1].cpu()
+        real = ~torch.isnan(x1p)
+        assert int(real.sum()) == N
+        assert torch.all(yp[~real] == 0) and torch.all(torch.isnan(x2p[~real]))
+        key_in = torch.sort(X[:, 0].to(torch.float64) * 7.0 + X[:, 1].to(torch.float64) * 13.0 + y.to(torch.float64))[0]
+        key_pk = torch.sort(x1p[real].to(torch.float64) * 7.0 + x2p[real].to(torch.float64) * 13.0 + yp[real].to(torch.float64))[0]
+        assert torch.equal(key_in, key_pk)
+        # un-transpose: stream position s = (32 w + l) R + j  lives at  w*32R + (j//4)*128 + l*4 + j%4
+        nw = x1p.numel() // (32 * R)
+        st = x1p.reshape(nw, R // 4, 32, 4).permute(0, 2, 1, 3).reshape(-1)[:N]
+        st2 = x2p.reshape(nw, R // 4, 32, 4).permute(0, 2, 1, 3).reshape(-1)[:N]
+        if not sort:
+            assert torch.equal(st, X[:, 0]) and torch.equal(st2, X[:, 1])
+        else:
+            c1, _, _ = O.b1_stencil(meshes[0], st.to(torch.float32))
+            c2, _, _ = O.b1_stencil(meshes[1], st2.to(torch.float32))
+            ncell = 39 * 22
+            key = torch.where((c1 >= 0) & (c2 >= 0), c1 * 22 + c2, torch.full_like(c1, ncell))
+            assert torch.all(key[1:] >= key[:-1])
 
 
 def test_model_refuses_cpu(vg):

@@ -156,7 +156,10 @@ def test_grid_forward_pieces(vg, dev, family, knots):
     meshes = [torch.linspace(0, 1 + 0.5 * d, k) for d, k in enumerate(knots)]
     plan = vg.GridPlan(family, meshes, torch.float64, dev)
     g = torch.Generator().manual_seed(100 + D)
-    l = torch.rand(D, generator=g, dtype=torch.float64) * 0.5 + 0.2
+    # B0 family: the reference's float32 rounding of (k +- 1) * delta (gridded_kronecker_structure.py:1312-1316)
+    # makes the Toeplitz factor numerically indefinite once l / delta is large (min eigenvalue -8e-7 at 130 cells,
+    # l = 0.68); keep the lengthscales where the reference's own factor is positive definite
+    l = torch.rand(D, generator=g, dtype=torch.float64) * (0.5 if family == 0 else 0.1) + (0.2 if family == 0 else 0.05)
     s2 = torch.rand(D, generator=g, dtype=torch.float64) + 0.5
     noise = torch.tensor([0.05], dtype=torch.float64)
     theta = torch.cat([l, s2, noise])
@@ -201,6 +204,20 @@ def test_grid_forward_pieces(vg, dev, family, knots):
         assert abs(sc[6 + d] - trs[d]) < 1e-8 * abs(trs[d])
     ma = (m * alpha_ref.reshape(-1)).sum()
     assert abs(sc[9] - ma) < 1e-8 * max(1.0, abs(ma))
+
+
+def test_reference_b0_factor_indefinite_is_reported(vg, dev):
+    """The reference's own B0 Toeplitz factor is indefinite here (float32-rounded exponents); the reference would
+    raise LinAlgError / add jitter (6_gulf_stream_experiement.ipynb cell 13 warning).  The library must flag it."""
+    mesh = torch.linspace(0, 1, 131)
+    K = O.kuu_b0(mesh, torch.tensor(0.6819, dtype=torch.float64), torch.tensor(1.4908, dtype=torch.float64))
+    assert torch.linalg.eigvalsh(K).min() < 0
+    plan = vg.GridPlan(vg.B0_GRIDDED, [mesh], torch.float64, dev)
+    theta = torch.tensor([0.6819, 1.4908, 0.1], dtype=torch.float64, device=dev)
+    m = torch.zeros(130, dtype=torch.float64, device=dev)
+    L = torch.eye(130, dtype=torch.float64, device=dev).reshape(-1).contiguous()
+    plan.grid_forward(theta, m, L)
+    assert plan.read_info() == 1
 
 
 def test_not_positive_definite_is_reported(vg, dev):

@@ -27,6 +27,9 @@ SIGNATURES = {
     "vggp_plan_dims": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
     "vggp_gbuf_layout": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "vggp_grid_forward": (C.c_int, [_vp, _dp, _dp, _dp, _vp]),
+    "vggp_obs_pack_geometry": (C.c_int, [_vp, _i64, C.POINTER(_i64), C.POINTER(C.c_int)]),
+    "vggp_obs_pack": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, C.c_int, C.POINTER(_vp), _dp, _vp]),
+    "vggp_obs_fwd_bwd_packed": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),
     "vggp_obs_fwd_bwd": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),

@@ -1,5 +1,6 @@
 // Per-observation kernels: B1 interpolation stencil (bit-exact restatement of bspline.py:23-77, 92-94),
-// dense feature matrices (tests / small predictions) and the fused ELBO forward+backward over observations.
+// dense feature matrices (tests / small predictions), the observation packing pass and the fused ELBO
+// forward+backward over packed observations.
 #pragma once
 #include "common.cuh"
 
@@ -41,15 +42,29 @@ __device__ __forceinline__ int find_cell(const float* __restrict__ t, int K, flo
     return c;
 }
 
+// Correctly rounded u / h for float from the correctly rounded reciprocal rh = RN(1/h) (Markstein): one
+// multiply and two fused multiply-adds.  Valid for the operand ranges of the stencil (0 <= u <= h, h a normal
+// float32 knot spacing); bit-exactness against IEEE division is asserted by the stencil tests.
+__device__ __forceinline__ float div_by_cached_rcp(float u, float h, float rh) {
+    const float q0 = u * rh;
+    const float rem = fmaf(-q0, h, u);
+    return fmaf(rem, rh, q0);
+}
+__device__ __forceinline__ double div_by_cached_rcp(double u, double h, double rh) {
+    (void)rh;
+    return u / h;
+}
+
 // Interpolation weights of the two hats overlapping cell c.  The denominator is the float32 knot
 // difference promoted to T (0-dim float32 arithmetic in the reference), the numerators are computed in T;
-// true IEEE subtraction and division (no reciprocal, no fma contraction is possible here).
+// true IEEE subtraction and division (no fma contraction is possible here).
 template <typename T>
 __device__ __forceinline__ void b1_weights(const float* __restrict__ t, int c, T x, bool inside, T& w_lo, T& w_hi) {
     const float tl = t[c], th = t[c + 1];
     const T h = (T)(th - tl);
-    const T wh = (x - (T)tl) / h;
-    const T wl = ((T)th - x) / h;
+    const T rh = (T)1 / h;
+    const T wh = div_by_cached_rcp(x - (T)tl, h, rh);
+    const T wl = div_by_cached_rcp((T)th - x, h, rh);
     w_hi = inside ? wh : (T)0;
     w_lo = inside ? wl : (T)0;
 }
@@ -86,8 +101,8 @@ __global__ void __launch_bounds__(256) k_b1_dense(MeshView mv, const T* __restri
     }
 }
 
-// B0 cell-integrated Matern-1/2 feature of cell k at x (gridded_kronecker_structure.py:1325-1374), and its
-// derivative w.r.t. the lengthscale.  idx = searchsorted(mesh, x, right=False).
+// B0 cell-integrated Matern-1/2 feature of cell k at x (gridded_kronecker_structure.py:1325-1374).
+// idx = searchsorted(mesh, x, right=False).
 template <typename T>
 __device__ __forceinline__ T b0_feature(const float* __restrict__ t, int k, int idx, T x, T l, T s2) {
     const T a = (T)t[k], b = (T)t[k + 1];
@@ -124,139 +139,419 @@ __global__ void __launch_bounds__(256) k_b0_dense(MeshView mv, const T* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1: fused per-observation ELBO forward + backward, B1 (ASVGP) family.
+// Packed observation layout.
 //
-// Per observation: cell + weights per dimension, mu = <kron phi_d, alpha> (2^D-point gather), p_d, q_d from the
-// main/first off diagonals of P_d, Q_d, then in the same pass the reverse-mode contributions
-//   g_alpha[corner] += w_corner * r,  bp_d += (prod_{e!=d} p_e) w (x) w,  bq_d += (prod_{e!=d} q_e) w (x) w,
-//   E += r^2 - prod p + prod q,  n += 1.
-// All hyper-parameter dependent factors (1/noise, ell_scale, kff) are applied on the grid side.
+// The fused kernel gives every lane one contiguous RUN of R observations of the (optionally cell-sorted)
+// stream and walks it sequentially, so that per-cell state and gradient accumulators live in registers and are
+// flushed only when the run leaves a cell.  To keep the global loads coalesced the stream is stored
+// "warp-transposed": observation j of lane l of warp w (stream position (32 w + l) R + j) lives at
+//      w * 32 R + (j / 4) * 128 + l * 4 + (j % 4)
+// so one 16-byte (float4) load per lane fetches 4 consecutive observations of its run and a warp reads 512
+// contiguous bytes.  Padding slots hold x = NaN (outside every mesh), y = 0.
 // ---------------------------------------------------------------------------------------------------------
+struct PackGeom {
+    int R;          // run length per lane (multiple of 4)
+    i64 nwarps;     // number of warps of runs
+    i64 n_packed;   // nwarps * 32 * R
+};
+
+// key = flat cell id (row-major over cells) or `ncells` for observations outside the mesh
 template <typename T, int D>
-struct ObsArgs {
+struct KeyArgs {
     const T* x[D];
-    const T* y;
     i64 n;
     MeshView mesh[D];
-    i64 stride[D];
-    int band_off[D];     // offset of dim d inside band tables: [pd | po | qd | qo] each K[d] long
-    int band_total;      // 4 * sum K
-    int knot_off[D];
-    int knot_total;
-    const T* alpha;
-    const T* band;
-    T* galpha;
-    T* gband;
-    double* gs;
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256) k_obs_b1_v1(const __grid_constant__ ObsArgs<T, D> a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    T* s_band = reinterpret_cast<T*>(smraw);                 // band_total
-    T* s_gband = s_band + a.band_total;                       // band_total
-    float* s_knots = reinterpret_cast<float*>(s_gband + a.band_total);   // knot_total
-    __shared__ double red[32];
-
-    for (int i = threadIdx.x; i < a.band_total; i += blockDim.x) {
-        s_band[i] = a.band[i];
-        s_gband[i] = (T)0;
-    }
-#pragma unroll
-    for (int d = 0; d < D; ++d)
-        for (int i = threadIdx.x; i < a.mesh[d].K; i += blockDim.x) s_knots[a.knot_off[d] + i] = a.mesh[d].t[i];
-    __syncthreads();
-
-    T accE = (T)0;
-    i64 cnt = 0, cnt_in = 0;
+__global__ void __launch_bounds__(256) k_cell_keys(const __grid_constant__ KeyArgs<T, D> a, uint32_t ncells,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (i64)gridDim.x * blockDim.x) {
-        int c[D];
-        T wl[D], wh[D];
+        uint32_t key = 0;
         bool all_in = true;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const T xv = a.x[d][i];
             bool inside;
-            const float* t = s_knots + a.knot_off[d];
-            c[d] = find_cell<T>(t, a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h, a.mesh[d].nearly_uniform, xv, inside);
-            b1_weights<T>(t, c[d], xv, inside, wl[d], wh[d]);
+            const int c = find_cell<T>(a.mesh[d].t, a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h,
+                                       a.mesh[d].nearly_uniform, a.x[d][i], inside);
+            key = key * (uint32_t)(a.mesh[d].K - 1) + (uint32_t)c;
             all_in = all_in && inside;
         }
-        const T yv = a.y[i];
-        T p[D], q[D];
+        keys[i] = all_in ? key : ncells;
+        idx[i] = (uint32_t)i;
+    }
+}
+
+template <typename T, int D>
+struct GatherArgs {
+    const T* x[D];
+    const T* y;
+    T* xp[D];
+    T* yp;
+    i64 n;
+    const uint32_t* perm;   // nullptr: keep the input order
+    PackGeom geo;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_pack_gather(const __grid_constant__ GatherArgs<T, D> a) {
+    const i64 per_warp = (i64)32 * a.geo.R;
+    T nanv;
+    if (sizeof(T) == 4) nanv = (T)__int_as_float(0x7fc00000); else nanv = (T)__longlong_as_double(0x7ff8000000000000LL);
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < a.geo.n_packed; q += (i64)gridDim.x * blockDim.x) {
+        const i64 w = q / per_warp;
+        const int rem = (int)(q - w * per_warp);
+        const int g4 = rem >> 7, lane = (rem & 127) >> 2, jj = rem & 3;
+        const i64 s = (w * 32 + lane) * (i64)a.geo.R + (g4 * 4 + jj);
+        if (s < a.n) {
+            const i64 src = a.perm ? (i64)a.perm[s] : s;
+#pragma unroll
+            for (int d = 0; d < D; ++d) a.xp[d][q] = a.x[d][src];
+            a.yp[q] = a.y[src];
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) a.xp[d][q] = nanv;
+            a.yp[q] = (T)0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA (bulk async copy) helpers: the per-CTA tables (band tables of P_d, Q_d and the knots) are staged into
+// shared memory with one cp.async.bulk completing on an mbarrier.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(phase)
+                     : "memory");
+    } while (!ok);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: fused per-observation ELBO forward + backward, B1 (ASVGP) family, packed layout.
+//
+// Per observation (hat weight a_d = w_hi of dimension d, w_lo = 1 - a_d):
+//   mu   = sum_S am[S] prod_{d in S} a_d                 (alpha at the 2^D cell corners, monomial basis)
+//   p_d  = pe[d][0] + pe[d][1] a_d + pe[d][2] a_d^2      (main / first off diagonal of P_d at the cell)
+//   q_d  likewise from Q_d;   v = kff - prod p_d + prod q_d;   r = y - mu
+// and, in the same pass, the reverse-mode sums kept in registers while the run stays in one cell:
+//   gm[S]    += r prod_{d in S} a_d        -> d alpha at the corners
+//   bp[d][k] += (prod_{e != d} p_e) a_d^k  -> main / off-diagonal gradients of P_d   (bq likewise for Q_d)
+//   E        += r^2 - prod p + prod q
+// 1/noise, ell_scale and kff are applied on the grid side.  On leaving a cell the sums are converted back to
+// the corner / band bases and flushed: d alpha with global float atomics (L2-resident M-vector), band sums
+// into per-CTA shared accumulators that are added to the global buffer once at the end.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int D>
+struct PackedArgs {
+    const T* xp[D];
+    const T* yp;
+    PackGeom geo;
+    MeshView mesh[D];
+    i64 stride[D];
+    int band_off[D];       // offset of dim d inside band tables: [pd | po | qd | qo] each n_d long
+    int band_total;        // 4 * sum n_d
+    int knot_off[D];
+    int knot_total;
+    int table_bytes;       // bytes of [band (T) | pad16 | knots (float)] in `tables`
+    int knots_byte_off;
+    const unsigned char* tables;
+    const T* alpha;
+    T* galpha;
+    T* gband;
+    double* gs;
+    double n_real;
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, T (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<double>(const double* p, double (&v)[4]) {
+    const double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename T, int D>
+struct LaneState {
+    int c[D];
+    T tlo[D], thi[D], h[D], rh[D];
+    T am[1 << D];
+    T pe[D][3], qe[D][3];
+    // accumulators
+    T gm[1 << D];
+    T bp[D][3], bq[D][3];
+    T accE;
+    bool valid;
+};
+
+template <typename T, int D>
+__device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<T, D>& s, T* s_gband) {
+    if (!s.valid) return;
+    // monomial moments -> corner sums: per dimension (m0, m1) -> (m0 - m1, m1)
+    T g[1 << D];
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) g[i] = s.gm[i];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
+#pragma unroll
+        for (int i = 0; i < (1 << D); ++i)
+            if (!(i & bit)) g[i] -= g[i | bit];
+    }
+    i64 base = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) base += (i64)s.c[d] * a.stride[d];
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) {
+        i64 off = base;
+#pragma unroll
+        for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? a.stride[d] : 0;
+        atomicAdd(a.galpha + off, g[i]);
+        s.gm[i] = (T)0;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int n = a.mesh[d].K;
+        T* gb = s_gband + a.band_off[d];
+        // sums of w (1-a)^2, w (1-a) a, w a^2 from the moments s0, s1, s2
+        const T pll = s.bp[d][0] - (T)2 * s.bp[d][1] + s.bp[d][2], plh = s.bp[d][1] - s.bp[d][2], phh = s.bp[d][2];
+        const T qll = s.bq[d][0] - (T)2 * s.bq[d][1] + s.bq[d][2], qlh = s.bq[d][1] - s.bq[d][2], qhh = s.bq[d][2];
+        atomicAdd(gb + s.c[d], pll);
+        atomicAdd(gb + n + s.c[d], plh);
+        atomicAdd(gb + s.c[d] + 1, phh);
+        atomicAdd(gb + 2 * n + s.c[d], qll);
+        atomicAdd(gb + 3 * n + s.c[d], qlh);
+        atomicAdd(gb + 2 * n + s.c[d] + 1, qhh);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.bp[d][k] = (T)0; s.bq[d][k] = (T)0; }
+    }
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneState<T, D>& s, const int (&c)[D],
+                                               const T* s_band, const float* s_knots) {
+    i64 base = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        s.c[d] = c[d];
+        const float tl = s_knots[a.knot_off[d] + c[d]], th = s_knots[a.knot_off[d] + c[d] + 1];
+        s.tlo[d] = (T)tl;
+        s.thi[d] = (T)th;
+        s.h[d] = (T)(th - tl);                 // float32 subtraction, then promoted (reference semantics)
+        s.rh[d] = (T)1 / s.h[d];
+        base += (i64)c[d] * a.stride[d];
+        const int n = a.mesh[d].K;
+        const T* b = s_band + a.band_off[d];
+        const T A = b[c[d]], B2 = (T)2 * b[n + c[d]], C = b[c[d] + 1];
+        s.pe[d][0] = A; s.pe[d][1] = B2 - (T)2 * A; s.pe[d][2] = A - B2 + C;
+        const T Aq = b[2 * n + c[d]], B2q = (T)2 * b[3 * n + c[d]], Cq = b[2 * n + c[d] + 1];
+        s.qe[d][0] = Aq; s.qe[d][1] = B2q - (T)2 * Aq; s.qe[d][2] = Aq - B2q + Cq;
+    }
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) {
+        i64 off = base;
+#pragma unroll
+        for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? a.stride[d] : 0;
+        s.am[i] = __ldg(a.alpha + off);
+    }
+    // corner values -> monomial coefficients: per dimension (lo, hi) -> (lo, hi - lo)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
+#pragma unroll
+        for (int i = 0; i < (1 << D); ++i)
+            if (i & bit) s.am[i] -= s.am[i ^ bit];
+    }
+    s.valid = true;
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void lane_process(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&x)[D], T y,
+                                             const T* s_band, T* s_gband, const float* s_knots) {
+    bool same = s.valid;
+#pragma unroll
+    for (int d = 0; d < D; ++d) same = same && (x[d] > s.tlo[d]) && (x[d] <= s.thi[d]);
+    if (!same) {
+        int c[D];
+        bool all_in = true, moved = !s.valid;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const int K = a.mesh[d].K;
-            const T* b = s_band + a.band_off[d];
-            const T ll = wl[d] * wl[d], lh = wl[d] * wh[d], hh = wh[d] * wh[d];
-            p[d] = ll * b[c[d]] + (T)2 * lh * b[K + c[d]] + hh * b[c[d] + 1];
-            q[d] = ll * b[2 * K + c[d]] + (T)2 * lh * b[3 * K + c[d]] + hh * b[2 * K + c[d] + 1];
+            bool inside;
+            c[d] = find_cell<T>(s_knots + a.knot_off[d], a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h,
+                                a.mesh[d].nearly_uniform, x[d], inside);
+            all_in = all_in && inside;
+            moved = moved || (c[d] != s.c[d]);
         }
-        T pp = (T)1, qq = (T)1;
+        if (!all_in) {           // zero feature column: mu = 0, p = q = 0
+            s.accE += y * y;
+            return;
+        }
+        if (moved) {
+            lane_flush<T, D>(a, s, s_gband);
+            lane_load_cell<T, D>(a, s, c, s_band, s_knots);
+        }
+    }
+    T w[D], p[D], q[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { pp *= p[d]; qq *= q[d]; }
-        i64 base = 0;
+    for (int d = 0; d < D; ++d) {
+        w[d] = div_by_cached_rcp(x[d] - s.tlo[d], s.h[d], s.rh[d]);
+        p[d] = fma(fma(s.pe[d][2], w[d], s.pe[d][1]), w[d], s.pe[d][0]);
+        q[d] = fma(fma(s.qe[d][2], w[d], s.qe[d][1]), w[d], s.qe[d][0]);
+    }
+    // monomials prod_{d in S} a_d, S indexed by bits (dimension 0 = most significant bit)
+    T mono[1 << D];
+    mono[0] = (T)1;
 #pragma unroll
-        for (int d = 0; d < D; ++d) base += (i64)c[d] * a.stride[d];
-        T mu = (T)0;
-        T wc[1 << D];
-        if (all_in) {
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
 #pragma unroll
-            for (int corner = 0; corner < (1 << D); ++corner) {
-                T w = (T)1;
-                i64 off = base;
+        for (int i = 0; i < (1 << D); ++i)
+            if ((i & bit) && !(i & (bit - 1))) {
+                // i has `bit` as its lowest set bit: mono[i] = mono[i ^ bit] * a_d
+                mono[i] = mono[i ^ bit] * w[d];
+            }
+    }
+    T mu = s.am[0];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const int hi = (corner >> (D - 1 - d)) & 1;
-                    w *= hi ? wh[d] : wl[d];
-                    off += hi ? a.stride[d] : 0;
+    for (int i = 1; i < (1 << D); ++i) mu = fma(s.am[i], mono[i], mu);
+    const T r = y - mu;
+    s.gm[0] += r;
+#pragma unroll
+    for (int i = 1; i < (1 << D); ++i) s.gm[i] = fma(r, mono[i], s.gm[i]);
+    T pp = (T)1, qq = (T)1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { pp *= p[d]; qq *= q[d]; }
+    s.accE += fma(r, r, qq - pp);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        T op = (T)1, oq = (T)1;
+#pragma unroll
+        for (int e = 0; e < D; ++e)
+            if (e != d) { op *= p[e]; oq *= q[e]; }
+        const T t1 = op * w[d], u1 = oq * w[d];
+        s.bp[d][0] += op;
+        s.bp[d][1] += t1;
+        s.bp[d][2] = fma(t1, w[d], s.bp[d][2]);
+        s.bq[d][0] += oq;
+        s.bq[d][1] += u1;
+        s.bq[d][2] = fma(u1, w[d], s.bq[d][2]);
+    }
+}
+
+constexpr int OBS_THREADS = 256;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 2 : 3) : (D == 1 ? 2 : 1))) k_obs_b1(const __grid_constant__ PackedArgs<T, D> a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    // [tables: band (T) | knots (float)] [gband accumulators (T)] [mbarrier]
+    const T* s_band = reinterpret_cast<const T*>(smraw);
+    const float* s_knots = reinterpret_cast<const float*>(smraw + a.knots_byte_off);
+    T* s_gband = reinterpret_cast<T*>(smraw + a.table_bytes);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double red[32];
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < a.band_total; i += blockDim.x) s_gband[i] = (T)0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)a.table_bytes);
+        bulk_g2s(smraw, a.tables, (uint32_t)a.table_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const i64 warp = (i64)blockIdx.x * (OBS_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    LaneState<T, D> s;
+    s.valid = false;
+    s.accE = (T)0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        s.c[d] = -1;
+        s.tlo[d] = s.thi[d] = s.h[d] = s.rh[d] = (T)0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.bp[d][k] = (T)0; s.bq[d][k] = (T)0; s.pe[d][k] = (T)0; s.qe[d][k] = (T)0; }
+    }
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) { s.gm[i] = (T)0; s.am[i] = (T)0; }
+
+    if (warp < a.geo.nwarps) {
+        const i64 base = warp * (i64)32 * a.geo.R + lane * 4;
+        const int groups = a.geo.R >> 2;
+        T xa[D][4], ya[4], xb[D][4], yb[4];
+#pragma unroll
+        for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + base, xa[d]);
+        load4<T>(a.yp + base, ya);
+        // software double buffer: the loads of the next group of 4 observations are in flight while this one
+        // is processed (no register copies: the two buffers alternate)
+        for (int gi = 0; gi < groups; gi += 2) {
+            if (gi + 1 < groups) {
+                const i64 o = base + (i64)(gi + 1) * 128;
+#pragma unroll
+                for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xb[d]);
+                load4<T>(a.yp + o, yb);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                T xx[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xx[d] = xa[d][j];
+                lane_process<T, D>(a, s, xx, ya[j], s_band, s_gband, s_knots);
+            }
+            if (gi + 2 < groups) {
+                const i64 o = base + (i64)(gi + 2) * 128;
+#pragma unroll
+                for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xa[d]);
+                load4<T>(a.yp + o, ya);
+            }
+            if (gi + 1 < groups) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    T xx[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) xx[d] = xb[d][j];
+                    lane_process<T, D>(a, s, xx, yb[j], s_band, s_gband, s_knots);
                 }
-                wc[corner] = w;
-                mu += w * __ldg(a.alpha + off);
             }
         }
-        const T r = yv - mu;
-        accE += r * r - pp + qq;
-        cnt += 1;
-        if (all_in) {
-            cnt_in += 1;
-#pragma unroll
-            for (int corner = 0; corner < (1 << D); ++corner) {
-                i64 off = base;
-#pragma unroll
-                for (int d = 0; d < D; ++d) off += ((corner >> (D - 1 - d)) & 1) ? a.stride[d] : 0;
-                atomicAdd(a.galpha + off, wc[corner] * r);
-            }
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int K = a.mesh[d].K;
-                T op = (T)1, oq = (T)1;
-#pragma unroll
-                for (int e = 0; e < D; ++e)
-                    if (e != d) { op *= p[e]; oq *= q[e]; }
-                T* gb = s_gband + a.band_off[d];
-                const T ll = wl[d] * wl[d], lh = wl[d] * wh[d], hh = wh[d] * wh[d];
-                atomicAdd(gb + c[d], op * ll);
-                atomicAdd(gb + K + c[d], op * lh);
-                atomicAdd(gb + c[d] + 1, op * hh);
-                atomicAdd(gb + 2 * K + c[d], oq * ll);
-                atomicAdd(gb + 3 * K + c[d], oq * lh);
-                atomicAdd(gb + 2 * K + c[d] + 1, oq * hh);
-            }
-        }
+        lane_flush<T, D>(a, s, s_gband);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < a.band_total; i += blockDim.x) {
         const T v = s_gband[i];
         if (v != (T)0) atomicAdd(a.gband + i, v);
     }
-    double e = block_sum((double)accE, red);
-    double c1 = block_sum((double)cnt, red);
-    double c2 = block_sum((double)cnt_in, red);
+    const double e = block_sum((double)s.accE, red);
     if (threadIdx.x == 0) {
         atomicAdd(a.gs + 0, e);
-        atomicAdd(a.gs + 1, c1);
-        atomicAdd(a.gs + 2, c2);
+        if (blockIdx.x == 0) {
+            a.gs[1] = a.n_real;          // single writer; summed over ranks by the all-reduce
+        }
     }
 }
 

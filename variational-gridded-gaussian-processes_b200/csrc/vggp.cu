@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <new>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "grid.cuh"
@@ -36,6 +38,11 @@ struct vggp_plan {
     double *mws, *alpha, *Tm[VGGP_MAX_D], *tmpM[VGGP_MAX_D], *gM, *ghat, *pgA, *pgB;
     void* alphaT;
     int band_off[VGGP_MAX_D], band_total, knot_off[VGGP_MAX_D], knot_total;
+    unsigned char* tables;                 // [band tables (obs dtype) | pad16 | knots (float32) | pad16]
+    int table_bytes, knots_byte_off;
+    int sm_count, obs_blocks_per_sm;
+    // scratch for vggp_obs_fwd_bwd on unpacked observations (grown on demand)
+    void* pk_x[VGGP_MAX_D] = {nullptr, nullptr, nullptr}; void* pk_y = nullptr; i64 pk_cap = 0;
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
@@ -309,50 +316,143 @@ int build_schedules(vggp_plan* p) {
     return 0;
 }
 
+PackGeom pack_geometry(const vggp_plan* p, i64 n) {
+    PackGeom g;
+    const i64 target_lanes = (i64)p->sm_count * p->obs_blocks_per_sm * OBS_THREADS;
+    i64 R = (n + target_lanes - 1) / target_lanes;
+    R = (R + 3) / 4 * 4;
+    if (R < 16) R = 16;
+    const i64 lanes = (n + R - 1) / R;
+    g.R = (int)R;
+    g.nwarps = (lanes + 31) / 32;
+    g.n_packed = g.nwarps * 32 * R;
+    return g;
+}
+
 template <typename T, int D>
-int launch_obs_b1(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
-    ObsArgs<T, D> a;
+size_t obs_smem_bytes(const vggp_plan* p) {
+    return (size_t)p->table_bytes + (size_t)p->band_total * sizeof(T);
+}
+
+template <typename T, int D>
+int obs_prepare(vggp_plan* p) {
+    const size_t smem = obs_smem_bytes<T, D>(p);
+    if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
+    VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1<T, D>, OBS_THREADS, smem));
+    p->obs_blocks_per_sm = nb < 1 ? 1 : nb;
+    return 0;
+}
+
+template <typename T, int D>
+int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n, void* gbuf, cudaStream_t st) {
+    PackedArgs<T, D> a;
+    a.geo = pack_geometry(p, n);
     for (int d = 0; d < D; ++d) {
-        a.x[d] = reinterpret_cast<const T*>(x[d]);
+        a.xp[d] = reinterpret_cast<const T*>(xp[d]);
         a.mesh[d] = p->mesh[d];
         a.stride[d] = p->stride[d];
         a.band_off[d] = p->band_off[d];
         a.knot_off[d] = p->knot_off[d];
     }
-    a.y = reinterpret_cast<const T*>(y);
-    a.n = n;
+    a.yp = reinterpret_cast<const T*>(yp);
     a.band_total = p->band_total;
     a.knot_total = p->knot_total;
+    a.table_bytes = p->table_bytes;
+    a.knots_byte_off = p->knots_byte_off;
+    a.tables = p->tables;
     a.alpha = reinterpret_cast<const T*>(p->alphaT);
-    a.band = reinterpret_cast<const T*>(p->g.bandT);
     T* gb = reinterpret_cast<T*>(gbuf);
     a.galpha = gb;
     a.gband = gb + p->M;
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
-    const size_t smem = (size_t)2 * p->band_total * sizeof(T) + (size_t)p->knot_total * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_v1<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
-    i64 blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_obs_b1_v1<T, D><<<(unsigned)blocks, 256, smem, st>>>(a);
+    a.n_real = (double)n;
+    const i64 blocks = (a.geo.nwarps + (OBS_THREADS / 32) - 1) / (OBS_THREADS / 32);
+    k_obs_b1<T, D><<<(unsigned)blocks, OBS_THREADS, obs_smem_bytes<T, D>(p), st>>>(a);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
 
-template <typename T>
-int obs_dispatch_D(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
-    switch (p->D) {
-        case 1: return launch_obs_b1<T, 1>(p, x, y, n, gbuf, st);
-        case 2: return launch_obs_b1<T, 2>(p, x, y, n, gbuf, st);
-        case 3: return launch_obs_b1<T, 3>(p, x, y, n, gbuf, st);
+template <typename T, int D>
+int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort_by_cell, void* const* xp, void* yp,
+              cudaStream_t st) {
+    GatherArgs<T, D> ga;
+    ga.geo = pack_geometry(p, n);
+    ga.n = n;
+    ga.perm = nullptr;
+    for (int d = 0; d < D; ++d) {
+        ga.x[d] = reinterpret_cast<const T*>(x[d]);
+        ga.xp[d] = reinterpret_cast<T*>(xp[d]);
     }
-    return fail(VGGP_E_DIM, "D must be 1..3");
+    ga.y = reinterpret_cast<const T*>(y);
+    ga.yp = reinterpret_cast<T*>(yp);
+    uint32_t *keys_in = nullptr, *keys_out = nullptr, *idx_in = nullptr, *idx_out = nullptr;
+    void* temp = nullptr;
+    if (sort_by_cell && n > 0) {
+        if (n >= ((i64)1 << 32)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^32 observations per shard");
+        i64 ncells = 1;
+        KeyArgs<T, D> ka;
+        ka.n = n;
+        for (int d = 0; d < D; ++d) {
+            ka.x[d] = ga.x[d];
+            ka.mesh[d] = p->mesh[d];
+            ncells *= (p->K[d] - 1);
+        }
+        if (ncells >= ((i64)1 << 32) - 1) return fail(VGGP_E_UNSUPPORTED, "too many cells for 32-bit keys");
+        VGGP_CUDA(cudaMalloc(&keys_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&keys_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&idx_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&idx_out, sizeof(uint32_t) * n));
+        const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
+        k_cell_keys<T, D><<<blocks, 256, 0, st>>>(ka, (uint32_t)ncells, keys_in, idx_in);
+        VGGP_LAUNCH_CHECK();
+        int end_bit = 1;
+        while (((i64)1 << end_bit) <= ncells) ++end_bit;
+        size_t temp_bytes = 0;
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
+        VGGP_CUDA(cudaMalloc(&temp, temp_bytes));
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
+        ga.perm = idx_out;
+    }
+    if (ga.geo.n_packed > 0) {
+        const int blocks = (int)std::min<i64>((ga.geo.n_packed + 255) / 256, 148 * 16);
+        k_pack_gather<T, D><<<blocks, 256, 0, st>>>(ga);
+        VGGP_LAUNCH_CHECK();
+    }
+    if (keys_in) {
+        VGGP_CUDA(cudaStreamSynchronize(st));
+        cudaFree(keys_in); cudaFree(keys_out); cudaFree(idx_in); cudaFree(idx_out); cudaFree(temp);
+    }
+    return 0;
+}
+
+#define VGGP_DISPATCH_TD(p, FN, ...)                                                        \
+    do {                                                                                    \
+        if ((p)->obs_dtype == VGGP_F32) {                                                   \
+            switch ((p)->D) {                                                               \
+                case 1: return FN<float, 1>(__VA_ARGS__);                                   \
+                case 2: return FN<float, 2>(__VA_ARGS__);                                   \
+                case 3: return FN<float, 3>(__VA_ARGS__);                                   \
+            }                                                                               \
+        } else {                                                                            \
+            switch ((p)->D) {                                                               \
+                case 1: return FN<double, 1>(__VA_ARGS__);                                  \
+                case 2: return FN<double, 2>(__VA_ARGS__);                                  \
+                case 3: return FN<double, 3>(__VA_ARGS__);                                  \
+            }                                                                               \
+        }                                                                                   \
+        return fail(VGGP_E_DIM, "D must be 1..3");                                          \
+    } while (0)
+
+int obs_prepare_dispatch(vggp_plan* p) { VGGP_DISPATCH_TD(p, obs_prepare, p); }
+int obs_packed_dispatch(vggp_plan* p, const void* const* xp, const void* yp, i64 n, void* gbuf, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, launch_obs_packed, p, xp, yp, n, gbuf, st);
+}
+int pack_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort, void* const* xp, void* yp, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, pack_impl, p, x, y, n, sort, xp, yp, st);
 }
 
 }  // namespace
@@ -443,9 +543,17 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     TRY(dev_alloc(p, &g.info, 1));
     const size_t tsz = obs_dtype == VGGP_F32 ? 4 : 8;
     {
-        unsigned char* b = nullptr;
-        TRY(dev_alloc(p, &b, (i64)p->band_total * tsz));
-        g.bandT = b;
+        const int band_bytes = (int)(((size_t)p->band_total * tsz + 15) / 16 * 16);
+        const int knot_bytes = (int)(((size_t)p->knot_total * 4 + 15) / 16 * 16);
+        p->knots_byte_off = band_bytes;
+        p->table_bytes = band_bytes + knot_bytes;
+        TRY(dev_alloc(p, &p->tables, p->table_bytes));
+        g.bandT = p->tables;
+        for (int d = 0; d < D; ++d) {
+            rc = (int)cudaMemcpy(p->tables + band_bytes + 4 * (size_t)p->knot_off[d], knots_host[d],
+                                 sizeof(float) * p->K[d], cudaMemcpyHostToDevice);
+            if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaMemcpy(knot table) failed"); }
+        }
         unsigned char* a = nullptr;
         TRY(dev_alloc(p, &a, p->M * (i64)tsz));
         p->alphaT = a;
@@ -458,6 +566,14 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         if (D > 2) TRY(dev_alloc(p, &p->tmpM[d], p->M)); else p->tmpM[d] = nullptr;
     }
     TRY(build_schedules(p));
+    {
+        cudaDeviceProp prop;
+        rc = (int)cudaGetDeviceProperties(&prop, device);
+        if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaGetDeviceProperties failed"); }
+        p->sm_count = prop.multiProcessorCount;
+        p->obs_blocks_per_sm = 1;
+        if (family == VGGP_B1_ASVGP) TRY(obs_prepare_dispatch(p));
+    }
     rc = (int)cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(2 * NB * (NB + 1) * sizeof(double)));
     if (!rc) rc = (int)cudaFuncSetAttribute(k_triinv_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -472,6 +588,9 @@ int vggp_plan_destroy(vggp_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     for (void* ptr : p->allocs) cudaFree(ptr);
+    for (int d = 0; d < VGGP_MAX_D; ++d)
+        if (p->pk_x[d]) cudaFree(p->pk_x[d]);
+    if (p->pk_y) cudaFree(p->pk_y);
     void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
     for (void* ptr : st)
         if (ptr) cudaFree(ptr);
@@ -540,20 +659,64 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
     return 0;
 }
 
-int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
+int vggp_obs_pack_geometry(const vggp_plan* p, int64_t n, int64_t* n_packed, int* run_len) {
+    if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    const PackGeom g = pack_geometry(p, n);
+    if (n_packed) *n_packed = g.n_packed;
+    if (run_len) *run_len = g.R;
+    return 0;
+}
+
+int vggp_obs_pack(vggp_plan* p, const void* const* x, const void* y, int64_t n, int sort_by_cell, void* const* xp,
+                  void* yp, void* stream) {
+    if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!x || !y || !xp || !yp) return fail(VGGP_E_ARG, "null argument");
+    for (int d = 0; d < p->D; ++d)
+        if (!x[d] || !xp[d]) return fail(VGGP_E_ARG, "null observation pointer");
+    return pack_dispatch(p, x, y, n, sort_by_cell, xp, yp, (cudaStream_t)stream);
+}
+
+int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp, int64_t n, void* gbuf, void* stream) {
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
-    if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
+    if (n > 0 && (!xp || !yp)) return fail(VGGP_E_ARG, "null observation pointers");
     cudaStream_t st = (cudaStream_t)stream;
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
     if (n == 0) return 0;
     for (int d = 0; d < p->D; ++d)
-        if (!x[d]) return fail(VGGP_E_ARG, "null observation pointer");
+        if (!xp[d]) return fail(VGGP_E_ARG, "null observation pointer");
     if (p->family != VGGP_B1_ASVGP)
         return fail(VGGP_E_UNSUPPORTED, "per-observation kernel for the B0 (cell-integrated) family is not built yet");
-    if (p->obs_dtype == VGGP_F32) return obs_dispatch_D<float>(p, x, y, n, gbuf, st);
-    return obs_dispatch_D<double>(p, x, y, n, gbuf, st);
+    return obs_packed_dispatch(p, xp, yp, n, gbuf, st);
+}
+
+int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
+    if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
+    if (n == 0) return vggp_obs_fwd_bwd_packed(p, nullptr, nullptr, 0, gbuf, stream);
+    if (p->family != VGGP_B1_ASVGP)
+        return fail(VGGP_E_UNSUPPORTED, "per-observation kernel for the B0 (cell-integrated) family is not built yet");
+    // unpacked input: transpose into the packed layout (input order kept) in plan-owned scratch, grown on demand
+    const PackGeom g = pack_geometry(p, n);
+    const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    if (g.n_packed > p->pk_cap) {
+        VGGP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        for (int d = 0; d < p->D; ++d) {
+            if (p->pk_x[d]) cudaFree(p->pk_x[d]);
+            p->pk_x[d] = nullptr;
+        }
+        if (p->pk_y) cudaFree(p->pk_y);
+        p->pk_y = nullptr;
+        p->pk_cap = 0;
+        for (int d = 0; d < p->D; ++d) VGGP_CUDA(cudaMalloc(&p->pk_x[d], tsz * (size_t)g.n_packed));
+        VGGP_CUDA(cudaMalloc(&p->pk_y, tsz * (size_t)g.n_packed));
+        p->pk_cap = g.n_packed;
+    }
+    int rc = vggp_obs_pack(p, x, y, n, 0, p->pk_x, p->pk_y, stream);
+    if (rc) return rc;
+    return vggp_obs_fwd_bwd_packed(p, p->pk_x, p->pk_y, n, gbuf, stream);
 }
 
 int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,

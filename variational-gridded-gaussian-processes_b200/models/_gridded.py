@@ -55,6 +55,7 @@ class GriddedVariationalGP(nn.Module):
             self._chol_names.append(name)
         self._plan: Optional[GridPlan] = None
         self._obs = None
+        self._packed = None
         self._group = None
         self._n_total = int(y.numel())
 
@@ -106,6 +107,8 @@ class GriddedVariationalGP(nn.Module):
             xs = [Xd[:, d].contiguous() for d in range(self.D)]       # structure of arrays, made once
             y = self.train_targets.reshape(-1).to(device=device, dtype=dtype).contiguous()
             self._obs = (xs, y)
+            # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant)
+            self._packed = self._plan.pack(xs, y, sort_by_cell=True)
         return self._plan
 
     # ---- the hot path ---------------------------------------------------------------------------------------
@@ -113,11 +116,11 @@ class GriddedVariationalGP(nn.Module):
         """Evidence lower bound (0-dim tensor with grad_fn).  `batch`: optional index tensor / slice selecting a
         minibatch of this rank's observations; the expected log-likelihood is rescaled by N / B."""
         plan = self._ensure_plan()
-        xs, y = self._obs
+        xs, y = self._packed, None
         scale = 1.0
         if batch is not None:
-            xs = [x[batch].contiguous() for x in xs]
-            y = y[batch].contiguous()
+            xs = [x[batch].contiguous() for x in self._obs[0]]
+            y = self._obs[1][batch].contiguous()
             n_local = self._obs[1].numel()
             scale = float(n_local) / float(max(1, y.numel()))
         ls, os_, noise = self._hyper()

@@ -13,6 +13,13 @@ def inv_softplus(x: torch.Tensor) -> torch.Tensor:
     return x + torch.log(-torch.expm1(-x))
 
 
+def _as_like(value, ref: torch.Tensor) -> torch.Tensor:
+    """Python numbers are taken at the parameter's precision (not through a float32 temporary)."""
+    if torch.is_tensor(value):
+        return value.detach().to(device=ref.device, dtype=ref.dtype)
+    return torch.tensor(value, dtype=ref.dtype, device=ref.device)
+
+
 class MaternKernel(nn.Module):
     def __init__(self, nu: float = 0.5, active_dims=None):
         super().__init__()
@@ -28,7 +35,7 @@ class MaternKernel(nn.Module):
 
     @lengthscale.setter
     def lengthscale(self, value):
-        value = torch.as_tensor(value).to(self.raw_lengthscale)
+        value = _as_like(value, self.raw_lengthscale)
         with torch.no_grad():
             self.raw_lengthscale.copy_(inv_softplus(value).expand_as(self.raw_lengthscale))
 
@@ -45,7 +52,7 @@ class ScaleKernel(nn.Module):
 
     @outputscale.setter
     def outputscale(self, value):
-        value = torch.as_tensor(value).to(self.raw_outputscale)
+        value = _as_like(value, self.raw_outputscale)
         with torch.no_grad():
             self.raw_outputscale.copy_(inv_softplus(value).reshape(()))
 
@@ -61,7 +68,7 @@ class HomoskedasticNoise(nn.Module):
 
     @noise.setter
     def noise(self, value):
-        value = torch.as_tensor(value).to(self.raw_noise)
+        value = _as_like(value, self.raw_noise)
         with torch.no_grad():
             self.raw_noise.copy_(inv_softplus(value - NOISE_LOWER_BOUND).expand_as(self.raw_noise))
 

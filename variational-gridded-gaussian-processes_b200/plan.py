@@ -79,12 +79,40 @@ class GridPlan:
         _lib.check(self.lib.vggp_grid_forward(self.handle, theta.data_ptr(), m.data_ptr(), L.data_ptr(),
                                               _stream_ptr(self.device)))
 
-    def obs_fwd_bwd(self, xs: Sequence[torch.Tensor], y: torch.Tensor, gbuf: Optional[torch.Tensor] = None):
-        g = self.gbuf if gbuf is None else gbuf
-        n = int(y.numel())
+    def _check_obs(self, xs, y, n):
+        if len(xs) != self.D:
+            raise ValueError(f"expected {self.D} coordinate arrays")
         for t in list(xs) + [y]:
             if t.dtype != self.obs_dtype or t.device != self.device or not t.is_contiguous() or t.numel() != n:
                 raise ValueError("observations must be contiguous 1-D tensors of the plan's dtype on the plan's device")
+
+    def pack(self, xs: Sequence[torch.Tensor], y: torch.Tensor, sort_by_cell: bool = True) -> "PackedObs":
+        """One-time layout pass (X is constant over optimisation steps): optional ordering by grid cell + the
+        warp-transposed layout the fused kernel streams (include/vggp.h, vggp_obs_pack)."""
+        n = int(y.numel())
+        self._check_obs(xs, y, n)
+        npk, run = C.c_int64(), C.c_int()
+        _lib.check(self.lib.vggp_obs_pack_geometry(self.handle, n, C.byref(npk), C.byref(run)))
+        xp = [torch.empty(int(npk.value), dtype=self.obs_dtype, device=self.device) for _ in range(self.D)]
+        yp = torch.empty(int(npk.value), dtype=self.obs_dtype, device=self.device)
+        if n > 0:
+            src = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
+            dst = (C.c_void_p * self.D)(*[t.data_ptr() for t in xp])
+            _lib.check(self.lib.vggp_obs_pack(self.handle, src, y.data_ptr(), n, 1 if sort_by_cell else 0, dst,
+                                              yp.data_ptr(), _stream_ptr(self.device)))
+        return PackedObs(xp, yp, n, int(run.value), bool(sort_by_cell))
+
+    def obs_fwd_bwd(self, xs, y: Optional[torch.Tensor] = None, gbuf: Optional[torch.Tensor] = None):
+        """Fused per-observation forward+backward.  `xs` is either a PackedObs (hot path) or a list of plain
+        coordinate arrays with targets `y` (any order; transposed into plan scratch first)."""
+        g = self.gbuf if gbuf is None else gbuf
+        if isinstance(xs, PackedObs):
+            ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs.xp])
+            _lib.check(self.lib.vggp_obs_fwd_bwd_packed(self.handle, ptrs, xs.yp.data_ptr(), xs.n, g.data_ptr(),
+                                                        _stream_ptr(self.device)))
+            return
+        n = int(y.numel())
+        self._check_obs(xs, y, n)
         ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
         _lib.check(self.lib.vggp_obs_fwd_bwd(self.handle, ptrs, y.data_ptr(), n, g.data_ptr(),
                                              _stream_ptr(self.device)))
@@ -162,6 +190,16 @@ class GridPlan:
     def _check_f64(self, t: torch.Tensor, numel: int, name: str):
         if t.dtype != torch.float64 or t.device != self.device or not t.is_contiguous() or t.numel() != numel:
             raise ValueError(f"{name} must be a contiguous float64 tensor with {numel} elements on {self.device}")
+
+
+class PackedObs:
+    """Observations in the packed (optionally cell-sorted, warp-transposed) layout of vggp_obs_pack."""
+
+    def __init__(self, xp, yp, n: int, run_len: int, sorted_by_cell: bool):
+        self.xp, self.yp, self.n, self.run_len, self.sorted_by_cell = xp, yp, n, run_len, sorted_by_cell
+
+    def numel(self) -> int:
+        return self.n
 
 
 class _DevArray:
