@@ -182,11 +182,11 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
 /* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
 
 /* Device pointer to a float64 workspace array of the last forward.  which: */
-#define VGGP_WS_K      0   /* Cholesky factor C_d of K_d (lower; upper triangle undefined) */
+#define VGGP_WS_K      0   /* Cholesky factor C_d of K_d (lower; upper triangle undefined); dense factor path only */
 #define VGGP_WS_P      1   /* P_d = K_d^-1 */
 #define VGGP_WS_R      2   /* R_d = P_d tril(L_d) */
-#define VGGP_WS_Q      3   /* Q_d = R_d R_d^T */
-#define VGGP_WS_S      4   /* S_d = tril(L_d) tril(L_d)^T */
+#define VGGP_WS_Q      3   /* Q_d = R_d R_d^T (dense factor path only; the structured path keeps just its band) */
+#define VGGP_WS_S      4   /* (retired: S_d is not materialised) */
 #define VGGP_WS_ALPHA  5   /* alpha (M), dim ignored */
 #define VGGP_WS_SCAL   6   /* scalars: logdet K_d [3], logdet S_d [3], tr(P_d S_d) [3], <m,alpha> */
 #define VGGP_WS_KRAW   7   /* K_d as built (before factorisation) */
@@ -204,6 +204,10 @@ int vggp_mode_product(vggp_plan* plan, int dim, const double* A, const double* s
 
 /* Select the GEMM inner loop used by the grid-side path: 1 = DMMA tensor cores (default), 0 = SIMT. */
 int vggp_set_gemm_mode(int use_mma);
+
+/* Plans created afterwards for the B1 family use (1, default) the O(M_d^2) twisted-factorisation inverse of the
+ * tridiagonal factor, or (0) the same dense blocked Cholesky + triangular inverse the B0 family uses (cross-check). */
+int vggp_set_b1_structured(int on);
 
 #ifdef __cplusplus
 }

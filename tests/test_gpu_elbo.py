@@ -129,6 +129,27 @@ def test_simt_and_dmma_paths_agree(vg, dev):
         assert relerr(a, b) < 1e-10
 
 
+def test_structured_and_dense_factor_paths_agree(vg, dev):
+    """B1 family: twisted-factorisation inverse (default) vs dense Cholesky path, whole step."""
+    knots, N = (150, 70), 3000
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=6)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [X[:, d].contiguous().to(dev) for d in range(2)]
+    res = []
+    try:
+        for mode in (1, 0):
+            vg._lib.load().vggp_set_b1_structured(mode)
+            plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+            out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, y.to(dev))
+            assert plan.read_info() == 0
+            res.append((out.clone(), dtheta.clone(), dm.clone(), dL.clone()))
+    finally:
+        vg._lib.load().vggp_set_b1_structured(1)
+    for a, b in zip(res[0], res[1]):
+        assert relerr(a, b) < 1e-8
+
+
 def test_all_observations_outside_the_mesh(vg, dev):
     meshes = [torch.linspace(0, 1, 8), torch.linspace(0, 1, 6)]
     N = 300

@@ -42,6 +42,7 @@ SIGNATURES = {
                                 _dp, _i64, _i64, _i64, C.c_int, _vp]),
     "vggp_mode_product": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _vp]),
     "vggp_set_gemm_mode": (C.c_int, [C.c_int]),
+    "vggp_set_b1_structured": (C.c_int, [C.c_int]),
 }
 
 _lib = None

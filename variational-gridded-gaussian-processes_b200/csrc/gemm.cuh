@@ -24,6 +24,8 @@ struct GemmDesc {
     int splitk;          // > 1: partial sums are atomically added into C (C must already hold beta*C)
     int lower_only;      // skip output tiles strictly above the diagonal
     int a_mfast, b_kfast;  // which index is contiguous in memory (coalescing of the tile loads)
+    int fast;              // eligible for the pipelined cp.async kernel (unit stride along one index of A, B and C rows)
+    int a_kcontig, b_ncontig, a_vec2, b_vec2;
     int zstart;          // first blockIdx.z of this problem (filled by gemm_finalize_group)
     int tiles_m, tiles_n;
 };
@@ -158,12 +160,133 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined path: 64 x 64 x 16 tiles, two cp.async stages, 4 warps of 32 x 32 (4 x 4 DMMA m8n8k4 tiles each).
+// Operand tiles keep their memory orientation in shared memory (rows along the contiguous index) with row
+// pitches chosen so that the DMMA fragment reads are bank-conflict free:
+//   k-contiguous operand : [64][20]  (element (mn, k) at mn * 20 + k)
+//   mn-contiguous operand: [16][68]  (element (mn, k) at k * 68 + mn)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GF_STAGE = 2560;     // doubles per stage: A 1280 + B 1280
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage one operand tile.  `kc`: the k index is the contiguous one.  Rows of the tile run along the other index.
+//   kc  : 64 rows (mn) x 16 (k),  global (mn, k) at base + mn * ld + k
+//   !kc : 16 rows (k)  x 64 (mn), global (mn, k) at base + k * ld + mn
+__device__ __forceinline__ void gemm_stage_tile(double* sm, const double* __restrict__ base, i64 ld, bool kc, bool vec2,
+                                                int mn0, int k0, int mn_lim, int k_lim, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = tid + it * 128;
+        int row, col, grow, gcol, row_lim, col_lim;
+        double* dst;
+        if (kc) { row = c >> 3; col = (c & 7) << 1; grow = mn0 + row; gcol = k0 + col; row_lim = mn_lim; col_lim = k_lim; dst = sm + row * 20 + col; }
+        else    { row = c >> 5; col = (c & 31) << 1; grow = k0 + row; gcol = mn0 + col; row_lim = k_lim; col_lim = mn_lim; dst = sm + row * 68 + col; }
+        int valid = (grow < row_lim) ? (col_lim - gcol) : 0;
+        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
+        const double* src = valid ? base + (i64)grow * ld + gcol : base;
+        if (vec2) {
+            cp_async16(dst, src, valid * 8);
+        } else {
+            cp_async8(dst, src, valid > 0 ? 8 : 0);
+            cp_async8(dst + 1, valid > 1 ? src + 1 : base, valid > 1 ? 8 : 0);
+        }
+    }
+}
+
+__device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double* sm) {
+    const int tid = threadIdx.x;
+    const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+    if (tile_m >= d.tiles_m || tile_n >= d.tiles_n) return;
+    const int m0 = tile_m * GBM, n0 = tile_n * GBN;
+    if (d.lower_only && n0 >= m0 + GBM) return;
+    const int split = zz % d.splitk;
+    const int b = zz / d.splitk;
+    int kbeg = 0, kend = d.k;
+    if (d.splitk > 1) {
+        const int kchunk = ((d.k + d.splitk - 1) / d.splitk + GBK - 1) / GBK * GBK;
+        kbeg = split * kchunk;
+        kend = min(d.k, kbeg + kchunk);
+        if (kbeg >= kend) return;
+    }
+    const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
+    const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
+    double* __restrict__ Cb = d.C + (i64)b * d.bsC;
+    const bool akc = d.a_kcontig != 0, bnc = d.b_ncontig != 0;
+    const i64 lda = akc ? d.rsA : d.csA;
+    const i64 ldb = bnc ? d.rsB : d.csB;
+    const int sAm = akc ? 20 : 1, sAk = akc ? 1 : 68;
+    const int sBk = bnc ? 68 : 1, sBn = bnc ? 1 : 20;
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int aoff = (wm + g) * sAm + t * sAk;
+    const int boff = t * sBk + (wn + g) * sBn;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int nk = (kend - kbeg + GBK - 1) / GBK;
+    gemm_stage_tile(sm, Ab, lda, akc, d.a_vec2 != 0, m0, kbeg, d.m, kend, tid);
+    gemm_stage_tile(sm + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, kbeg, d.n, kend, tid);
+    cp_async_commit();
+    for (int it = 0; it < nk; ++it) {
+        if (it + 1 < nk) {
+            double* nx = sm + ((it + 1) & 1) * GF_STAGE;
+            const int k0 = kbeg + (it + 1) * GBK;
+            gemm_stage_tile(nx, Ab, lda, akc, d.a_vec2 != 0, m0, k0, d.m, kend, tid);
+            gemm_stage_tile(nx + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, k0, d.n, kend, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* As = sm + (it & 1) * GF_STAGE;
+        const double* Bs = As + 1280;
+#pragma unroll
+        for (int ks = 0; ks < GBK / 4; ++ks) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[aoff + mi * 8 * sAm + ks * 4 * sAk];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bb[ni] = Bs[boff + ks * 4 * sBk + ni * 8 * sBn];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int row = m0 + wm + mi * 8 + g;
+            const int col = n0 + wn + ni * 8 + t * 2;
+            gemm_store(d, Cb, row, col, acc[mi][ni][0]);
+            gemm_store(d, Cb, row, col + 1, acc[mi][ni][1]);
+        }
+}
+
 // Group launch: descriptors live in device memory (built once at plan creation).
 template <bool MMA>
 __global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
 k_gemm_group(const GemmDesc* __restrict__ descs, int ndesc) {
-    __shared__ double As[GBM][GBK + 4];
-    __shared__ double Bs[GBK][GBN + 4];
+    __shared__ __align__(16) double smem[2 * GF_STAGE];
     __shared__ GemmDesc sd;
     const int z = blockIdx.z;
     int p = 0;
@@ -171,16 +294,27 @@ k_gemm_group(const GemmDesc* __restrict__ descs, int ndesc) {
         if (z >= descs[i].zstart) p = i;
     if (threadIdx.x == 0) sd = descs[p];
     __syncthreads();
-    gemm_body<MMA>(sd, z - sd.zstart, As, Bs);
+    if (MMA && sd.fast) {
+        gemm_fast_body(sd, z - sd.zstart, smem);
+    } else {
+        double (*As)[GBK + 4] = reinterpret_cast<double (*)[GBK + 4]>(smem);
+        double (*Bs)[GBN + 4] = reinterpret_cast<double (*)[GBN + 4]>(smem + GBM * (GBK + 4));
+        gemm_body<MMA>(sd, z - sd.zstart, As, Bs);
+    }
 }
 
 // Single ad-hoc problem passed by value (tests, vggp_gemm_f64, vggp_mode_product).
 template <bool MMA>
 __global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
 k_gemm_one(const __grid_constant__ GemmDesc d) {
-    __shared__ double As[GBM][GBK + 4];
-    __shared__ double Bs[GBK][GBN + 4];
-    gemm_body<MMA>(d, blockIdx.z, As, Bs);
+    __shared__ __align__(16) double smem[2 * GF_STAGE];
+    if (MMA && d.fast) {
+        gemm_fast_body(d, blockIdx.z, smem);
+    } else {
+        double (*As)[GBK + 4] = reinterpret_cast<double (*)[GBK + 4]>(smem);
+        double (*Bs)[GBN + 4] = reinterpret_cast<double (*)[GBN + 4]>(smem + GBM * (GBK + 4));
+        gemm_body<MMA>(d, blockIdx.z, As, Bs);
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -208,6 +342,14 @@ inline GemmGroupDims gemm_finalize_group(GemmDesc* descs, int ndesc) {
         d.b_kfast = (d.rsB == 1 && d.csB != 1) ? 1 : 0;
         if (d.splitk < 1) d.splitk = 1;
         if (d.batch < 1) d.batch = 1;
+        // pipelined kernel: A and B have unit stride along one index, plain k addressing, k >= one tile
+        const bool a_unit = (d.csA == 1) || (d.rsA == 1), b_unit = (d.csB == 1) || (d.rsB == 1);
+        d.a_kcontig = (d.csA == 1) ? 1 : 0;
+        d.b_ncontig = (d.csB == 1) ? 1 : 0;
+        d.fast = (a_unit && b_unit && d.kinner == 0 && d.k >= 1) ? 1 : 0;
+        const i64 lda = d.a_kcontig ? d.rsA : d.csA, ldb = d.b_ncontig ? d.rsB : d.csB;
+        d.a_vec2 = (lda % 2 == 0 && d.bsA % 2 == 0 && ((uintptr_t)d.A % 16) == 0) ? 1 : 0;
+        d.b_vec2 = (ldb % 2 == 0 && d.bsB % 2 == 0 && ((uintptr_t)d.B % 16) == 0) ? 1 : 0;
         d.zstart = z;
         z += d.batch * d.splitk;
         if (d.tiles_n > g.gx) g.gx = d.tiles_n;

@@ -26,14 +26,14 @@ struct GridDims {
     float delta32[VGGP_MAX_D];    // mesh[1] - mesh[0] in float32 (reference: SplineBasis.delta, bspline.py:89)
     i64 M;
     i64 Loff[VGGP_MAX_D];         // offset of L_d inside the concatenated L / dL arrays
-    int band_off[VGGP_MAX_D];     // offset (elements) of dim d's block inside the band tables / gbuf band part
+    int band_off[VGGP_MAX_D];     // offset (elements) of dim d's block inside the gbuf band part [bp_d|bp_o|bq_d|bq_o]
+    int tab_off[VGGP_MAX_D];      // offset (elements) of dim d's block inside the per-cell tables (8 n_d each)
     double* Kraw[VGGP_MAX_D];
     double* Kc[VGGP_MAX_D];       // factored in place -> Cholesky factor (lower)
     double* W[VGGP_MAX_D];        // C^-1
     double* P[VGGP_MAX_D];
     double* Lt[VGGP_MAX_D];       // tril(L_d)
     double* R[VGGP_MAX_D];
-    double* S[VGGP_MAX_D];
     double* Q[VGGP_MAX_D];
     double* dP[VGGP_MAX_D];
     double* dR[VGGP_MAX_D];
@@ -42,9 +42,11 @@ struct GridDims {
     double* dK[VGGP_MAX_D];
     double* dLraw[VGGP_MAX_D];
     double* tmp[VGGP_MAX_D];
+    double* Qb[VGGP_MAX_D];       // float64 main / first off diagonal of Q_d: [diag (n) | off (n)]
+    int structured;               // 1: B1 family with the tridiagonal factor path (no dense Cholesky / Q / dK)
     double* sc;                   // SC_COUNT scalars
     int* info;
-    void* bandT;                  // band tables in obs dtype: per dim [pd | po | qd | qo], each n[d] long
+    void* bandT;                  // per-cell tables in obs dtype: per dim [pe0 pe1 pe2 qe0 qe1 qe2 h rh], each n[d] long
     int leaf_cnt[VGGP_MAX_D];
     int leaf_lo[VGGP_MAX_D][MAX_LEAVES + 1];
 };
@@ -130,8 +132,10 @@ __global__ void k_build_factors(const __grid_constant__ GridDims g, const double
     const int i = (int)(e / n), j = (int)(e % n);
     const double k = factor_entry(g, theta, d, i, j);
     g.Kraw[d][e] = k;
-    g.Kc[d][e] = k;
-    g.W[d][e] = 0.0;
+    if (!g.structured) {
+        g.Kc[d][e] = k;
+        g.W[d][e] = 0.0;
+    }
     g.Lt[d][e] = (j <= i) ? L[g.Loff[d] + e] : 0.0;
 }
 
@@ -240,34 +244,137 @@ __global__ void __launch_bounds__(NB) k_triinv_leaf(const __grid_constant__ Grid
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Forward reductions per dimension: band tables of P_d and Q_d (in the observation dtype), tr(P_d S_d) =
-// <R_d, tril L_d>, log det S_d = 2 sum log |L_ii|.   grid (D), 1024 threads.
+// Structured inverse of the tridiagonal B1/ASVGP factor K_d (diag a_i, off-diagonal b_i): twisted factorisation
+//   d_0 = a_0, d_k = a_k - b_{k-1}^2 / d_{k-1}   (top-down pivots; log det K = sum log d_k)
+//   e_{n-1} = a_{n-1}, e_k = a_k - b_k^2 / e_{k+1} (bottom-up pivots)
+//   P[j][j] = 1 / (d_j + e_j - a_j)
+//   P[i][j] = P[j][j] prod_{k=i}^{j-1} (-b_k / d_k)  (i < j),   P[i][j] = P[j][j] prod_{k=j+1}^{i} (-b_{k-1} / e_k)  (i > j)
+// O(n^2) work, two O(n) sequential recurrences (run redundantly by every CTA, in two different warps).
+// grid (ceil(n / 256), D), 256 threads, dynamic smem 7 n doubles.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ GridDims g, const double* __restrict__ theta) {
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    if ((int)blockIdx.x * 256 >= n) return;
+    double* a = sm;
+    double* b = a + n;
+    double* dd = b + n;
+    double* ee = dd + n;
+    double* ru = ee + n;
+    double* rl = ru + n;
+    double* pd = rl + n;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 256) {
+        a[i] = factor_entry(g, theta, d, i, i);
+        b[i] = (i + 1 < n) ? factor_entry(g, theta, d, i, i + 1) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double prev = a[0];
+        dd[0] = prev;
+        bool bad = !(prev > 0.0);
+        for (int k = 1; k < n; ++k) {
+            const double bk = b[k - 1];
+            prev = a[k] - bk * bk / prev;
+            dd[k] = prev;
+            bad = bad || !(prev > 0.0);
+        }
+        if (bad) atomicMax(g.info, d + 1);
+    } else if (tid == 32) {
+        double nxt = a[n - 1];
+        ee[n - 1] = nxt;
+        for (int k = n - 2; k >= 0; --k) {
+            const double bk = b[k];
+            nxt = a[k] - bk * bk / nxt;
+            ee[k] = nxt;
+        }
+    }
+    __syncthreads();
+    double ld = 0.0;
+    for (int i = tid; i < n; i += 256) {
+        pd[i] = 1.0 / (dd[i] + ee[i] - a[i]);
+        ru[i] = (i + 1 < n) ? -b[i] / dd[i] : 0.0;
+        rl[i] = (i + 1 < n) ? -b[i] / ee[i + 1] : 0.0;
+        ld += log(dd[i]);
+    }
+    ld = block_sum(ld, red);
+    if (blockIdx.x == 0 && tid == 0) g.sc[SC_LOGDETK + d] = ld;
+    __syncthreads();
+    const int j = (int)blockIdx.x * 256 + tid;
+    if (j >= n) return;
+    double* __restrict__ P = g.P[d];
+    double p = pd[j];
+    P[(i64)j * n + j] = p;
+    for (int i = j - 1; i >= 0; --i) {
+        p *= ru[i];
+        P[(i64)i * n + j] = p;
+    }
+    p = pd[j];
+    for (int i = j + 1; i < n; ++i) {
+        p *= rl[i - 1];
+        P[(i64)i * n + j] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward reductions, one warp per row i of dimension d: per-cell tables of P_d and Q_d (observation dtype,
+// monomial basis), the float64 band of Q_d, tr(P_d S_d) = <R_d, tril L_d>, log det S_d = 2 sum log |L_ii|.
+// The band of Q_d = R_d R_d^T is formed from row dot products (structured path: the full Q_d is never built).
+// grid (ceil(nmax / 8), D), 256 threads.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(1024) k_fwd_reduce(const __grid_constant__ GridDims g) {
-    __shared__ double red[32];
-    const int d = blockIdx.x;
+__global__ void __launch_bounds__(256) k_fwd_reduce(const __grid_constant__ GridDims g) {
+    const int d = blockIdx.y;
     const int n = g.n[d];
+    const int lane = threadIdx.x & 31;
+    const int i = (int)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
     const double* __restrict__ P = g.P[d];
-    const double* __restrict__ Q = g.Q[d];
     const double* __restrict__ R = g.R[d];
     const double* __restrict__ Lt = g.Lt[d];
-    T* band = reinterpret_cast<T*>(g.bandT) + g.band_off[d];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        band[i] = (T)P[(i64)i * n + i];
-        band[n + i] = (i + 1 < n) ? (T)P[(i64)i * n + i + 1] : (T)0;
-        band[2 * n + i] = (T)Q[(i64)i * n + i];
-        band[3 * n + i] = (i + 1 < n) ? (T)Q[(i64)i * n + i + 1] : (T)0;
+    const bool last = (i + 1 >= n);
+    double qd = 0.0, qo = 0.0, tr = 0.0;
+    const double* Ri = R + (i64)i * n;
+    const double* Rn = R + (i64)(last ? i : i + 1) * n;
+    const double* Li = Lt + (i64)i * n;
+    for (int k = lane; k < n; k += 32) {
+        const double r = Ri[k];
+        qd = fma(r, r, qd);
+        qo = fma(r, Rn[k], qo);
+        tr = fma(r, Li[k], tr);
     }
-    double tr = 0.0, ld = 0.0;
-    for (i64 e = threadIdx.x; e < (i64)n * n; e += blockDim.x) tr += R[e] * Lt[e];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ld += log(fabs(Lt[(i64)i * n + i]));
-    tr = block_sum(tr, red);
-    ld = block_sum(ld, red);
-    if (threadIdx.x == 0) {
-        g.sc[SC_TR + d] = tr;
-        g.sc[SC_LOGDETS + d] = 2.0 * ld;
+    qd = warp_sum(qd);
+    qo = warp_sum(qo);
+    tr = warp_sum(tr);
+    if (lane == 0) {
+        if (last) qo = 0.0;
+        g.Qb[d][i] = qd;
+        g.Qb[d][n + i] = qo;
+        // per-cell tables, monomial basis in the hat weight a (w_lo = 1 - a):
+        //   p(a) = A (1-a)^2 + 2 B (1-a) a + C a^2 = pe0 + pe1 a + pe2 a^2, A = P[c][c], B = P[c][c+1], C = P[c+1][c+1]
+        T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];       // [pe0 | pe1 | pe2 | qe0 | qe1 | qe2 | h | rh]
+        const double A = P[(i64)i * n + i], B2 = last ? 0.0 : 2.0 * P[(i64)i * n + i + 1],
+                     C = last ? 0.0 : P[(i64)(i + 1) * n + i + 1];
+        tab[i] = (T)A; tab[n + i] = (T)(B2 - 2.0 * A); tab[2 * n + i] = (T)(A - B2 + C);
+        atomicAdd(g.sc + SC_TR + d, tr);
+        atomicAdd(g.sc + SC_LOGDETS + d, 2.0 * log(fabs(Li[i])));
     }
+}
+
+// Second half of the per-cell tables: needs Q[c+1][c+1] of the next row, so it runs after k_fwd_reduce.
+// grid (ceil(nmax / 256), D)
+template <typename T>
+__global__ void __launch_bounds__(256) k_fwd_qtable(const __grid_constant__ GridDims g) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const int i = (int)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const bool last = (i + 1 >= n);
+    T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];
+    const double Aq = g.Qb[d][i], B2q = last ? 0.0 : 2.0 * g.Qb[d][n + i], Cq = last ? 0.0 : g.Qb[d][i + 1];
+    tab[3 * n + i] = (T)Aq; tab[4 * n + i] = (T)(B2q - 2.0 * Aq); tab[5 * n + i] = (T)(Aq - B2q + Cq);
 }
 
 // alpha (float64) -> observation dtype, and <m, alpha>.
@@ -313,7 +420,8 @@ __device__ __forceinline__ double tr_others(const GridDims& g, int d) {
     return c;
 }
 
-// dP_d (holding the mode-d Gram contraction) += band scatter - c_d/2 S_d ;  dR_d = 2 sym(dQ band) R_d.
+// dP_d (holding the mode-d Gram contraction) += band scatter ;  dR_d = 2 sym(dQ band) R_d.
+// (the -c_d/2 S_d term of dP_d is routed straight to dK_d as +c_d/2 Q_d in k_bwd_theta: P S P = Q)
 // grid (ceil(nmax^2/256), D)
 template <typename T>
 __global__ void __launch_bounds__(256) k_bwd_dP_dR(const __grid_constant__ GridDims g, const T* __restrict__ gband,
@@ -326,7 +434,7 @@ __global__ void __launch_bounds__(256) k_bwd_dP_dR(const __grid_constant__ GridD
     const double noise = theta[2 * g.D];
     const double cP = ell_scale / (2.0 * noise), cQ = -ell_scale / (2.0 * noise);
     const T* __restrict__ b = gband + g.band_off[d];   // [bp_diag | bp_off | bq_diag | bq_off]
-    double v = g.dP[d][e] - 0.5 * tr_others(g, d) * g.S[d][e];
+    double v = g.dP[d][e];
     if (i == j) v += cP * (double)b[i];
     else if (i - j == 1) v += cP * (double)b[n + j];
     else if (j - i == 1) v += cP * (double)b[n + i];
@@ -370,36 +478,53 @@ __global__ void __launch_bounds__(256) k_bwd_dm(const double* __restrict__ pg, c
         dm[i] = pg[i] - alpha[i];
 }
 
-// d theta and the ELBO scalars.  grid (D), 1024 threads.
-//   dK_d(total) = dKraw_d - (M / (2 M_d)) P_d ;  dl_d = <dK, dK/dl>, ds2_d = <dK, dK/ds2> + dkff * kff / s2_d
-//   block 0 additionally writes dnoise and out[0..3].
-__global__ void __launch_bounds__(1024) k_bwd_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
-                                                    const double* __restrict__ gscal, double ell_scale,
-                                                    double* __restrict__ out, double* __restrict__ dtheta) {
+// d theta and the ELBO scalars.
+//   dK_d(total) = -Y_d P_d + (c_d / 2) Q_d - (M / (2 M_d)) P_d,  Y_d = P_d sym(dP_d),  c_d = prod_{e != d} tr(P_e S_e)
+//   dl_d = <dK, dK/dl>, ds2_d = <dK, dK/ds2> + dkff * kff / s2_d        (accumulated atomically into dtheta)
+// Structured (B1) path: dK/dtheta is tridiagonal, so only the band of Y P is formed, one warp per band entry;
+// dense path: dK_d = -Y_d P_d comes from a GEMM and the full Q_d is used.
+// grid (chunks, D), 256 threads; dtheta must be zero on entry.  Block (0, 0) also writes dnoise and out[0..3].
+__global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+                                                   const double* __restrict__ gscal, double ell_scale,
+                                                   double* __restrict__ out, double* __restrict__ dtheta) {
     __shared__ double red[32];
-    const int d = blockIdx.x;
+    const int d = blockIdx.y;
     const int n = g.n[d];
     const int D = g.D;
-    const double* __restrict__ dK = g.dK[d];
     const double* __restrict__ P = g.P[d];
     const double half_ratio = 0.5 * (double)g.M / (double)n;
+    const double half_c = 0.5 * tr_others(g, d);
     double sl = 0.0, ss = 0.0;
-    if (g.family == VGGP_B1_ASVGP) {
-        for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) {
+    if (g.structured) {
+        const double* __restrict__ Y = g.Y[d];
+        const int lane = threadIdx.x & 31;
+        const int wglobal = (int)blockIdx.x * 8 + (threadIdx.x >> 5);
+        const int wtotal = (int)gridDim.x * 8;
+        for (int e = wglobal; e < 3 * n; e += wtotal) {
             const int i = e / 3, j = i + (e % 3) - 1;
             if (j < 0 || j >= n) continue;
-            double a, b;
-            factor_entry_grad(g, theta, d, i, j, a, b);
-            const double v = dK[(i64)i * n + j] - half_ratio * P[(i64)i * n + j];
-            sl += v * a;
-            ss += v * b;
+            const double* Yi = Y + (i64)i * n;
+            const double* Pj = P + (i64)j * n;          // P symmetric: column j = row j
+            double acc = 0.0;
+            for (int k = lane; k < n; k += 32) acc = fma(Yi[k], Pj[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const double q = (i == j) ? g.Qb[d][i] : g.Qb[d][n + (i < j ? i : j)];
+                const double v = -acc + half_c * q - half_ratio * P[(i64)i * n + j];
+                double a, b;
+                factor_entry_grad(g, theta, d, i, j, a, b);
+                sl += v * a;
+                ss += v * b;
+            }
         }
     } else {
-        for (i64 e = threadIdx.x; e < (i64)n * n; e += blockDim.x) {
+        const double* __restrict__ dK = g.dK[d];
+        const double* __restrict__ Q = g.Q[d];
+        for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < (i64)n * n; e += (i64)gridDim.x * blockDim.x) {
             const int i = (int)(e / n), j = (int)(e % n);
             double a, b;
             factor_entry_grad(g, theta, d, i, j, a, b);
-            const double v = dK[e] - half_ratio * P[e];
+            const double v = dK[e] + half_c * Q[e] - half_ratio * P[e];
             sl += v * a;
             ss += v * b;
         }
@@ -407,27 +532,30 @@ __global__ void __launch_bounds__(1024) k_bwd_theta(const __grid_constant__ Grid
     sl = block_sum(sl, red);
     ss = block_sum(ss, red);
     if (threadIdx.x == 0) {
-        const double noise = theta[2 * D];
-        double kff = 1.0;
-        for (int e = 0; e < D; ++e) kff *= theta[D + e];
-        const double E = gscal[0], nobs = gscal[1];
-        const double dkff = -ell_scale * nobs / (2.0 * noise);
-        dtheta[d] = sl;
-        dtheta[D + d] = ss + dkff * kff / theta[D + d];
-        if (d == 0) {
-            const double tot = E + nobs * kff;
-            const double ell = -0.5 * nobs * log(2.0 * 3.14159265358979323846 * noise) - tot / (2.0 * noise);
-            dtheta[2 * D] = ell_scale * (-nobs / (2.0 * noise) + tot / (2.0 * noise * noise));
-            double trp = 1.0, lds = 0.0;
-            for (int e = 0; e < D; ++e) {
-                trp *= g.sc[SC_TR + e];
-                lds += ((double)g.M / (double)g.n[e]) * (g.sc[SC_LOGDETK + e] - g.sc[SC_LOGDETS + e]);
+        atomicAdd(dtheta + d, sl);
+        atomicAdd(dtheta + D + d, ss);
+        if (blockIdx.x == 0) {
+            const double noise = theta[2 * D];
+            double kff = 1.0;
+            for (int e = 0; e < D; ++e) kff *= theta[D + e];
+            const double E = gscal[0], nobs = gscal[1];
+            const double dkff = -ell_scale * nobs / (2.0 * noise);
+            atomicAdd(dtheta + D + d, dkff * kff / theta[D + d]);
+            if (d == 0) {
+                const double tot = E + nobs * kff;
+                const double ell = -0.5 * nobs * log(2.0 * 3.14159265358979323846 * noise) - tot / (2.0 * noise);
+                atomicAdd(dtheta + 2 * D, ell_scale * (-nobs / (2.0 * noise) + tot / (2.0 * noise * noise)));
+                double trp = 1.0, lds = 0.0;
+                for (int e = 0; e < D; ++e) {
+                    trp *= g.sc[SC_TR + e];
+                    lds += ((double)g.M / (double)g.n[e]) * (g.sc[SC_LOGDETK + e] - g.sc[SC_LOGDETS + e]);
+                }
+                const double kl = 0.5 * (trp + g.sc[SC_MALPHA] - (double)g.M + lds);
+                out[0] = ell_scale * ell - kl;
+                out[1] = ell_scale * ell;
+                out[2] = kl;
+                out[3] = nobs;
             }
-            const double kl = 0.5 * (trp + g.sc[SC_MALPHA] - (double)g.M + lds);
-            out[0] = ell_scale * ell - kl;
-            out[1] = ell_scale * ell;
-            out[2] = kl;
-            out[3] = nobs;
         }
     }
 }

@@ -266,11 +266,10 @@ struct PackedArgs {
     PackGeom geo;
     MeshView mesh[D];
     i64 stride[D];
-    int band_off[D];       // offset of dim d inside band tables: [pd | po | qd | qo] each n_d long
-    int band_total;        // 4 * sum n_d
+    int band_off[D];       // offset of dim d inside the gradient band block: [bp_d | bp_o | bq_d | bq_o] each n_d long
+    int tab_off[D];        // offset (elements of T) of dim d inside the cell tables: [pe0 pe1 pe2 qe0 qe1 qe2 h rh] each n_d long
     int knot_off[D];
-    int knot_total;
-    int table_bytes;       // bytes of [band (T) | pad16 | knots (float)] in `tables`
+    int table_bytes;       // bytes of [cell tables (T) | pad16 | knots (float) | pad16] in `tables`
     int knots_byte_off;
     const unsigned char* tables;
     const T* alpha;
@@ -297,7 +296,7 @@ __device__ __forceinline__ void load4<double>(const double* p, double (&v)[4]) {
 template <typename T, int D>
 struct LaneState {
     int c[D];
-    T tlo[D], thi[D], h[D], rh[D];
+    T tlo[D], tlo_chk[D], thi[D], h[D], rh[D];
     T am[1 << D];
     T pe[D][3], qe[D][3];
     // accumulators
@@ -307,19 +306,18 @@ struct LaneState {
     bool valid;
 };
 
+// Leave the cached cell: convert the monomial moments back to corner / band sums and add them to the global
+// gradient buffer with fire-and-forget float atomics (RED; the buffer is L2-resident).
 template <typename T, int D>
-__device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<T, D>& s, T* s_gband) {
+__device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<T, D>& s) {
     if (!s.valid) return;
-    // monomial moments -> corner sums: per dimension (m0, m1) -> (m0 - m1, m1)
-    T g[1 << D];
-#pragma unroll
-    for (int i = 0; i < (1 << D); ++i) g[i] = s.gm[i];
+    // per dimension (m0, m1) -> (m0 - m1, m1)
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int bit = 1 << (D - 1 - d);
 #pragma unroll
         for (int i = 0; i < (1 << D); ++i)
-            if (!(i & bit)) g[i] -= g[i | bit];
+            if (!(i & bit)) s.gm[i] -= s.gm[i | bit];
     }
     i64 base = 0;
 #pragma unroll
@@ -329,46 +327,43 @@ __device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<
         i64 off = base;
 #pragma unroll
         for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? a.stride[d] : 0;
-        atomicAdd(a.galpha + off, g[i]);
+        atomicAdd(a.galpha + off, s.gm[i]);
         s.gm[i] = (T)0;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int n = a.mesh[d].K;
-        T* gb = s_gband + a.band_off[d];
+        T* gb = a.gband + a.band_off[d] + s.c[d];
         // sums of w (1-a)^2, w (1-a) a, w a^2 from the moments s0, s1, s2
-        const T pll = s.bp[d][0] - (T)2 * s.bp[d][1] + s.bp[d][2], plh = s.bp[d][1] - s.bp[d][2], phh = s.bp[d][2];
-        const T qll = s.bq[d][0] - (T)2 * s.bq[d][1] + s.bq[d][2], qlh = s.bq[d][1] - s.bq[d][2], qhh = s.bq[d][2];
-        atomicAdd(gb + s.c[d], pll);
-        atomicAdd(gb + n + s.c[d], plh);
-        atomicAdd(gb + s.c[d] + 1, phh);
-        atomicAdd(gb + 2 * n + s.c[d], qll);
-        atomicAdd(gb + 3 * n + s.c[d], qlh);
-        atomicAdd(gb + 2 * n + s.c[d] + 1, qhh);
+        atomicAdd(gb, s.bp[d][0] - (T)2 * s.bp[d][1] + s.bp[d][2]);
+        atomicAdd(gb + n, s.bp[d][1] - s.bp[d][2]);
+        atomicAdd(gb + 1, s.bp[d][2]);
+        atomicAdd(gb + 2 * n, s.bq[d][0] - (T)2 * s.bq[d][1] + s.bq[d][2]);
+        atomicAdd(gb + 3 * n, s.bq[d][1] - s.bq[d][2]);
+        atomicAdd(gb + 2 * n + 1, s.bq[d][2]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { s.bp[d][k] = (T)0; s.bq[d][k] = (T)0; }
     }
 }
 
+// Enter cell c: knots and per-cell tables from shared memory, alpha corners from L2.
 template <typename T, int D>
 __device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneState<T, D>& s, const int (&c)[D],
-                                               const T* s_band, const float* s_knots) {
+                                               const T (&tl)[D], const T (&th)[D], const T* s_tab) {
     i64 base = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        s.c[d] = c[d];
-        const float tl = s_knots[a.knot_off[d] + c[d]], th = s_knots[a.knot_off[d] + c[d] + 1];
-        s.tlo[d] = (T)tl;
-        s.thi[d] = (T)th;
-        s.h[d] = (T)(th - tl);                 // float32 subtraction, then promoted (reference semantics)
-        s.rh[d] = (T)1 / s.h[d];
-        base += (i64)c[d] * a.stride[d];
         const int n = a.mesh[d].K;
-        const T* b = s_band + a.band_off[d];
-        const T A = b[c[d]], B2 = (T)2 * b[n + c[d]], C = b[c[d] + 1];
-        s.pe[d][0] = A; s.pe[d][1] = B2 - (T)2 * A; s.pe[d][2] = A - B2 + C;
-        const T Aq = b[2 * n + c[d]], B2q = (T)2 * b[3 * n + c[d]], Cq = b[2 * n + c[d] + 1];
-        s.qe[d][0] = Aq; s.qe[d][1] = B2q - (T)2 * Aq; s.qe[d][2] = Aq - B2q + Cq;
+        const T* tb = s_tab + a.tab_off[d] + c[d];
+        s.c[d] = c[d];
+        s.tlo[d] = tl[d];
+        s.tlo_chk[d] = tl[d];
+        s.thi[d] = th[d];
+        s.pe[d][0] = tb[0]; s.pe[d][1] = tb[n]; s.pe[d][2] = tb[2 * n];
+        s.qe[d][0] = tb[3 * n]; s.qe[d][1] = tb[4 * n]; s.qe[d][2] = tb[5 * n];
+        s.h[d] = tb[6 * n];          // (T)(float32 knot difference), reference semantics
+        s.rh[d] = tb[7 * n];         // correctly rounded 1 / h
+        base += (i64)c[d] * a.stride[d];
     }
 #pragma unroll
     for (int i = 0; i < (1 << D); ++i) {
@@ -389,31 +384,61 @@ __device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneSt
 }
 
 template <typename T, int D>
-__device__ __forceinline__ void lane_process(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&x)[D], T y,
-                                             const T* s_band, T* s_gband, const float* s_knots) {
-    bool same = s.valid;
+__device__ __forceinline__ bool lane_in_cell(const LaneState<T, D>& s, const T (&x)[D]) {
+    bool same = true;
 #pragma unroll
-    for (int d = 0; d < D; ++d) same = same && (x[d] > s.tlo[d]) && (x[d] <= s.thi[d]);
-    if (!same) {
-        int c[D];
-        bool all_in = true, moved = !s.valid;
+    for (int d = 0; d < D; ++d) same = same && (x[d] > s.tlo_chk[d]) && (x[d] <= s.thi[d]);
+    return same;
+}
+
+// Slow path (one copy per kernel): the observation is not inside the cached cell.  Returns true when the
+// observation has been consumed here (outside the mesh: zero feature column, mu = 0, p = q = 0).
+// Cell search = arithmetic guess, then walk until t[c] < x <= t[c+1] (exact comparisons against the float32 knots,
+// same result as searchsorted(mesh, x, right=False) - 1 clamped to [0, K-2]).
+template <typename T, int D>
+__device__ __forceinline__ bool lane_switch(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&x)[D], T y,
+                                            const T* s_tab, const float* s_knots) {
+    int c[D];
+    T tl[D], th[D];
+    bool all_in = true, moved = !s.valid;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            bool inside;
-            c[d] = find_cell<T>(s_knots + a.knot_off[d], a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h,
-                                a.mesh[d].nearly_uniform, x[d], inside);
-            all_in = all_in && inside;
-            moved = moved || (c[d] != s.c[d]);
+    for (int d = 0; d < D; ++d) {
+        const float* t = s_knots + a.knot_off[d];
+        const int K = a.mesh[d].K;
+        float gf = ((float)x[d] - a.mesh[d].t0) * a.mesh[d].inv_h;
+        gf = fminf(fmaxf(gf, 0.0f), (float)(K - 2));          // NaN -> 0
+        int cc = (int)gf;
+        T lo = (T)t[cc], hi = (T)t[cc + 1];
+#pragma unroll 1
+        while (true) {
+            if (cc > 0 && x[d] <= lo) { --cc; hi = lo; lo = (T)t[cc]; continue; }
+            if (cc < K - 2 && x[d] > hi) { ++cc; lo = hi; hi = (T)t[cc + 1]; continue; }
+            break;
         }
-        if (!all_in) {           // zero feature column: mu = 0, p = q = 0
-            s.accE += y * y;
-            return;
-        }
-        if (moved) {
-            lane_flush<T, D>(a, s, s_gband);
-            lane_load_cell<T, D>(a, s, c, s_band, s_knots);
-        }
+        c[d] = cc; tl[d] = lo; th[d] = hi;
+        all_in = all_in && (x[d] >= (T)t[0]) && (x[d] <= (T)t[K - 1]);
+        moved = moved || (cc != s.c[d]);
     }
+    if (!all_in) {
+        s.accE += y * y;
+        return true;
+    }
+    if (moved) {
+        lane_flush<T, D>(a, s);
+        lane_load_cell<T, D>(a, s, c, tl, th, s_tab);
+    } else {
+        // x == first knot of the mesh: it belongs to cell 0 although x > t_lo fails; widen the cached lower bound
+        // so that the fast check accepts it (the weight formula is unchanged: a = (x - t_0) / h = 0)
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (c[d] == 0 && x[d] == s.tlo[d]) s.tlo_chk[d] = -INFINITY;
+    }
+    return false;
+}
+
+// Fast path: straight-line arithmetic for an observation inside the cached cell.
+template <typename T, int D>
+__device__ __forceinline__ void lane_math(LaneState<T, D>& s, const T (&x)[D], T y) {
     T w[D], p[D], q[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -429,10 +454,7 @@ __device__ __forceinline__ void lane_process(const PackedArgs<T, D>& a, LaneStat
         const int bit = 1 << (D - 1 - d);
 #pragma unroll
         for (int i = 0; i < (1 << D); ++i)
-            if ((i & bit) && !(i & (bit - 1))) {
-                // i has `bit` as its lowest set bit: mono[i] = mono[i ^ bit] * a_d
-                mono[i] = mono[i ^ bit] * w[d];
-            }
+            if ((i & bit) && !(i & (bit - 1))) mono[i] = (i ^ bit) ? mono[i ^ bit] * w[d] : w[d];
     }
     T mu = s.am[0];
 #pragma unroll
@@ -441,16 +463,21 @@ __device__ __forceinline__ void lane_process(const PackedArgs<T, D>& a, LaneStat
     s.gm[0] += r;
 #pragma unroll
     for (int i = 1; i < (1 << D); ++i) s.gm[i] = fma(r, mono[i], s.gm[i]);
-    T pp = (T)1, qq = (T)1;
+    T pp = p[0], qq = q[0];
 #pragma unroll
-    for (int d = 0; d < D; ++d) { pp *= p[d]; qq *= q[d]; }
+    for (int d = 1; d < D; ++d) { pp *= p[d]; qq *= q[d]; }
     s.accE += fma(r, r, qq - pp);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         T op = (T)1, oq = (T)1;
+        bool first = true;
 #pragma unroll
         for (int e = 0; e < D; ++e)
-            if (e != d) { op *= p[e]; oq *= q[e]; }
+            if (e != d) {
+                op = first ? p[e] : op * p[e];
+                oq = first ? q[e] : oq * q[e];
+                first = false;
+            }
         const T t1 = op * w[d], u1 = oq * w[d];
         s.bp[d][0] += op;
         s.bp[d][1] += t1;
@@ -461,15 +488,45 @@ __device__ __forceinline__ void lane_process(const PackedArgs<T, D>& a, LaneStat
     }
 }
 
+// One group of 4 consecutive observations of this lane's run.  The 4 fast-path copies are straight-line code; the
+// single slow-path copy is entered by breaking out of the switch and re-entering it at the same position.
+template <typename T, int D>
+__device__ __forceinline__ void lane_group(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&xg)[D][4],
+                                           const T (&yg)[4], const T* s_tab, const float* s_knots) {
+    int j = 0;
+    for (;;) {
+        switch (j) {
+#define VGGP_OBS_CASE(J)                                                     \
+    case J: {                                                                \
+        T xx[D];                                                             \
+        _Pragma("unroll") for (int d = 0; d < D; ++d) xx[d] = xg[d][J];      \
+        if (!lane_in_cell<T, D>(s, xx)) { j = J; break; }                    \
+        lane_math<T, D>(s, xx, yg[J]);                                       \
+    }
+            VGGP_OBS_CASE(0)
+            VGGP_OBS_CASE(1)
+            VGGP_OBS_CASE(2)
+            VGGP_OBS_CASE(3)
+#undef VGGP_OBS_CASE
+            j = 4;
+        }
+        if (j >= 4) break;
+        T xx[D];
+        T yy = (j == 0) ? yg[0] : (j == 1) ? yg[1] : (j == 2) ? yg[2] : yg[3];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xx[d] = (j == 0) ? xg[d][0] : (j == 1) ? xg[d][1] : (j == 2) ? xg[d][2] : xg[d][3];
+        if (lane_switch<T, D>(a, s, xx, yy, s_tab, s_knots)) ++j;
+    }
+}
+
 constexpr int OBS_THREADS = 256;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 2 : 3) : (D == 1 ? 2 : 1))) k_obs_b1(const __grid_constant__ PackedArgs<T, D> a) {
+__global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b1(const __grid_constant__ PackedArgs<T, D> a) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    // [tables: band (T) | knots (float)] [gband accumulators (T)] [mbarrier]
-    const T* s_band = reinterpret_cast<const T*>(smraw);
+    // [cell tables (T) | knots (float)], staged by one TMA bulk copy
+    const T* s_tab = reinterpret_cast<const T*>(smraw);
     const float* s_knots = reinterpret_cast<const float*>(smraw + a.knots_byte_off);
-    T* s_gband = reinterpret_cast<T*>(smraw + a.table_bytes);
     __shared__ __align__(8) uint64_t bar;
     __shared__ double red[32];
 
@@ -477,7 +534,6 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 2 : 3
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < a.band_total; i += blockDim.x) s_gband[i] = (T)0;
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, (uint32_t)a.table_bytes);
@@ -493,7 +549,9 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 2 : 3
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         s.c[d] = -1;
-        s.tlo[d] = s.thi[d] = s.h[d] = s.rh[d] = (T)0;
+        s.tlo[d] = s.h[d] = s.rh[d] = (T)0;
+        s.tlo_chk[d] = (T)INFINITY;      // nothing is inside the (empty) initial cell
+        s.thi[d] = -(T)INFINITY;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { s.bp[d][k] = (T)0; s.bq[d][k] = (T)0; s.pe[d][k] = (T)0; s.qe[d][k] = (T)0; }
     }
@@ -507,51 +565,31 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 2 : 3
 #pragma unroll
         for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + base, xa[d]);
         load4<T>(a.yp + base, ya);
-        // software double buffer: the loads of the next group of 4 observations are in flight while this one
-        // is processed (no register copies: the two buffers alternate)
-        for (int gi = 0; gi < groups; gi += 2) {
+        // software pipeline: the loads of the next group of 4 observations are in flight while this one is
+        // processed.  One copy of the group code (rotating the buffers costs 3 register moves per observation but
+        // keeps the loop inside the instruction cache).
+#pragma unroll 1
+        for (int gi = 0; gi < groups; ++gi) {
             if (gi + 1 < groups) {
                 const i64 o = base + (i64)(gi + 1) * 128;
 #pragma unroll
                 for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xb[d]);
                 load4<T>(a.yp + o, yb);
             }
+            lane_group<T, D>(a, s, xa, ya, s_tab, s_knots);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                T xx[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) xx[d] = xa[d][j];
-                lane_process<T, D>(a, s, xx, ya[j], s_band, s_gband, s_knots);
-            }
-            if (gi + 2 < groups) {
-                const i64 o = base + (i64)(gi + 2) * 128;
-#pragma unroll
-                for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xa[d]);
-                load4<T>(a.yp + o, ya);
-            }
-            if (gi + 1 < groups) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    T xx[D];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) xx[d] = xb[d][j];
-                    lane_process<T, D>(a, s, xx, yb[j], s_band, s_gband, s_knots);
-                }
+                for (int d = 0; d < D; ++d) xa[d][j] = xb[d][j];
+                ya[j] = yb[j];
             }
         }
-        lane_flush<T, D>(a, s, s_gband);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < a.band_total; i += blockDim.x) {
-        const T v = s_gband[i];
-        if (v != (T)0) atomicAdd(a.gband + i, v);
+        lane_flush<T, D>(a, s);
     }
     const double e = block_sum((double)s.accE, red);
     if (threadIdx.x == 0) {
         atomicAdd(a.gs + 0, e);
-        if (blockIdx.x == 0) {
-            a.gs[1] = a.n_real;          // single writer; summed over ranks by the all-reduce
-        }
+        if (blockIdx.x == 0) a.gs[1] = a.n_real;      // single writer; summed over ranks by the all-reduce
     }
 }
 

@@ -15,6 +15,7 @@ namespace vggp {
 thread_local char g_err[512] = {0};
 unsigned long long g_launches = 0;
 static int g_use_mma = 1;
+static int g_b1_structured = 1;    // tridiagonal (twisted factorisation) inverse for the B1 family
 
 struct Phase {
     GemmDesc* d_descs = nullptr;
@@ -38,6 +39,7 @@ struct vggp_plan {
     double *mws, *alpha, *Tm[VGGP_MAX_D], *tmpM[VGGP_MAX_D], *gM, *ghat, *pgA, *pgB;
     void* alphaT;
     int band_off[VGGP_MAX_D], band_total, knot_off[VGGP_MAX_D], knot_total;
+    int tab_off[VGGP_MAX_D], tab_total;
     unsigned char* tables;                 // [band tables (obs dtype) | pad16 | knots (float32) | pad16]
     int table_bytes, knots_byte_off;
     int sm_count, obs_blocks_per_sm;
@@ -245,14 +247,13 @@ int build_schedules(vggp_plan* p) {
         p->triinv.push_back(a);
         p->triinv.push_back(b);
     }
-    // ---- P = W^T W ; R = P Lt, S = Lt Lt^T ; Q = R R^T ----
+    // ---- P = W^T W ; R = P Lt ; Q = R R^T (dense path only) ----
     {
         std::vector<GemmDesc> a, b, c;
         for (int d = 0; d < D; ++d) {
             const int n = p->n[d];
             a.push_back(square_desc(n, g.W[d], true, g.W[d], false, g.P[d], 1.0, 0.0));
             b.push_back(square_desc(n, g.P[d], false, g.Lt[d], false, g.R[d], 1.0, 0.0));
-            b.push_back(square_desc(n, g.Lt[d], false, g.Lt[d], true, g.S[d], 1.0, 0.0));
             c.push_back(square_desc(n, g.R[d], false, g.R[d], true, g.Q[d], 1.0, 0.0));
         }
         if ((rc = make_phase(p, a, p->pinv))) return rc;
@@ -331,7 +332,7 @@ PackGeom pack_geometry(const vggp_plan* p, i64 n) {
 
 template <typename T, int D>
 size_t obs_smem_bytes(const vggp_plan* p) {
-    return (size_t)p->table_bytes + (size_t)p->band_total * sizeof(T);
+    return (size_t)p->table_bytes;
 }
 
 template <typename T, int D>
@@ -354,11 +355,10 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
         a.mesh[d] = p->mesh[d];
         a.stride[d] = p->stride[d];
         a.band_off[d] = p->band_off[d];
+        a.tab_off[d] = p->tab_off[d];
         a.knot_off[d] = p->knot_off[d];
     }
     a.yp = reinterpret_cast<const T*>(yp);
-    a.band_total = p->band_total;
-    a.knot_total = p->knot_total;
     a.table_bytes = p->table_bytes;
     a.knots_byte_off = p->knots_byte_off;
     a.tables = p->tables;
@@ -469,6 +469,11 @@ int vggp_set_gemm_mode(int use_mma) {
     return 0;
 }
 
+int vggp_set_b1_structured(int on) {
+    g_b1_structured = on ? 1 : 0;
+    return 0;
+}
+
 int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, const float* const* knots_host,
                      int obs_dtype, int device) {
     if (!out || !n_knots || !knots_host) return fail(VGGP_E_ARG, "null argument");
@@ -490,7 +495,8 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     GridDims& g = p->g;
     memset(&g, 0, sizeof(g));
     g.D = D; g.family = family; g.obs_dtype = obs_dtype;
-    int boff = 0, koff = 0;
+    g.structured = (family == VGGP_B1_ASVGP && g_b1_structured) ? 1 : 0;
+    int boff = 0, koff = 0, toff = 0;
     for (int d = 0; d < D; ++d) {
         p->K[d] = n_knots[d];
         p->n[d] = (family == VGGP_B1_ASVGP) ? n_knots[d] : n_knots[d] - 1;
@@ -502,10 +508,13 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->nmax = std::max(p->nmax, p->n[d]);
         p->band_off[d] = boff; g.band_off[d] = boff;
         boff += 4 * p->n[d];
+        p->tab_off[d] = toff; g.tab_off[d] = toff;
+        toff += 8 * p->n[d];
         p->knot_off[d] = koff;
         koff += p->K[d];
     }
     p->band_total = boff;
+    p->tab_total = toff;
     p->knot_total = koff;
     g.M = p->M;
     for (int d = 0; d < D; ++d) {
@@ -530,9 +539,10 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         const i64 nn = (i64)p->n[d] * p->n[d];
         TRY(dev_alloc(p, &g.Kraw[d], nn)); TRY(dev_alloc(p, &g.Kc[d], nn)); TRY(dev_alloc(p, &g.W[d], nn));
         TRY(dev_alloc(p, &g.P[d], nn)); TRY(dev_alloc(p, &g.Lt[d], nn)); TRY(dev_alloc(p, &g.R[d], nn));
-        TRY(dev_alloc(p, &g.S[d], nn)); TRY(dev_alloc(p, &g.Q[d], nn)); TRY(dev_alloc(p, &g.dP[d], nn));
+        TRY(dev_alloc(p, &g.Q[d], nn)); TRY(dev_alloc(p, &g.dP[d], nn));
         TRY(dev_alloc(p, &g.dR[d], nn)); TRY(dev_alloc(p, &g.X[d], nn)); TRY(dev_alloc(p, &g.Y[d], nn));
         TRY(dev_alloc(p, &g.dK[d], nn)); TRY(dev_alloc(p, &g.dLraw[d], nn)); TRY(dev_alloc(p, &g.tmp[d], nn));
+        TRY(dev_alloc(p, &g.Qb[d], 2 * (i64)p->n[d]));
         std::vector<int> bounds;
         build_leaves(0, p->n[d], bounds);
         bounds.push_back(p->n[d]);
@@ -543,7 +553,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     TRY(dev_alloc(p, &g.info, 1));
     const size_t tsz = obs_dtype == VGGP_F32 ? 4 : 8;
     {
-        const int band_bytes = (int)(((size_t)p->band_total * tsz + 15) / 16 * 16);
+        const int band_bytes = (int)(((size_t)p->tab_total * tsz + 15) / 16 * 16);
         const int knot_bytes = (int)(((size_t)p->knot_total * 4 + 15) / 16 * 16);
         p->knots_byte_off = band_bytes;
         p->table_bytes = band_bytes + knot_bytes;
@@ -553,6 +563,22 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
             rc = (int)cudaMemcpy(p->tables + band_bytes + 4 * (size_t)p->knot_off[d], knots_host[d],
                                  sizeof(float) * p->K[d], cudaMemcpyHostToDevice);
             if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaMemcpy(knot table) failed"); }
+            // static per-cell tables: h = (T)(float32 knot difference), rh = correctly rounded 1 / h
+            const int n = p->n[d];
+            std::vector<unsigned char> hb(2 * (size_t)n * tsz, 0);
+            for (int c = 0; c + 1 < p->K[d] && c < n; ++c) {
+                const float hf = knots_host[d][c + 1] - knots_host[d][c];
+                if (obs_dtype == VGGP_F32) {
+                    reinterpret_cast<float*>(hb.data())[c] = hf;
+                    reinterpret_cast<float*>(hb.data())[n + c] = 1.0f / hf;
+                } else {
+                    reinterpret_cast<double*>(hb.data())[c] = (double)hf;
+                    reinterpret_cast<double*>(hb.data())[n + c] = 1.0 / (double)hf;
+                }
+            }
+            rc = (int)cudaMemcpy(p->tables + ((size_t)p->tab_off[d] + 6 * (size_t)n) * tsz, hb.data(), hb.size(),
+                                 cudaMemcpyHostToDevice);
+            if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaMemcpy(cell table) failed"); }
         }
         unsigned char* a = nullptr;
         TRY(dev_alloc(p, &a, p->M * (i64)tsz));
@@ -574,6 +600,9 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->obs_blocks_per_sm = 1;
         if (family == VGGP_B1_ASVGP) TRY(obs_prepare_dispatch(p));
     }
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_b1_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(7 * (size_t)p->nmax * sizeof(double)));
+    if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_inverse) failed"); }
     rc = (int)cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(2 * NB * (NB + 1) * sizeof(double)));
     if (!rc) rc = (int)cudaFuncSetAttribute(k_triinv_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -629,25 +658,43 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
     dim3 egrid(ceil_div(nn, 256), D);
     k_build_factors<<<egrid, 256, 0, st>>>(p->g, theta, L);
     VGGP_LAUNCH_CHECK();
-    const size_t csm = 2 * NB * (NB + 1) * sizeof(double);
-    for (int j = 0; j < p->n_panels; ++j) {
-        const int j0 = j * NB;
-        dim3 grid(ceil_div(p->nmax - j0, NB), D);
-        k_chol_panel<<<grid, 256, csm, st>>>(p->g, j0);
+    if (p->g.structured) {
+        // B1 family: tridiagonal factor -> twisted-factorisation inverse, O(n^2)
+        k_b1_inverse<<<dim3(ceil_div(p->nmax, 256), D), 256, 7 * (size_t)p->nmax * sizeof(double), st>>>(p->g, theta);
         VGGP_LAUNCH_CHECK();
-        if ((rc = launch_phase(p->chol_trailing[j], st))) return rc;
+    } else {
+        const size_t csm = 2 * NB * (NB + 1) * sizeof(double);
+        for (int j = 0; j < p->n_panels; ++j) {
+            const int j0 = j * NB;
+            dim3 grid(ceil_div(p->nmax - j0, NB), D);
+            k_chol_panel<<<grid, 256, csm, st>>>(p->g, j0);
+            VGGP_LAUNCH_CHECK();
+            if ((rc = launch_phase(p->chol_trailing[j], st))) return rc;
+        }
+        int max_leaves = 0;
+        for (int d = 0; d < D; ++d) max_leaves = std::max(max_leaves, p->g.leaf_cnt[d]);
+        k_triinv_leaf<<<dim3(max_leaves, D), NB, csm, st>>>(p->g);
+        VGGP_LAUNCH_CHECK();
+        for (auto& ph : p->triinv) if ((rc = launch_phase(ph, st))) return rc;
+        if ((rc = launch_phase(p->pinv, st))) return rc;
     }
-    int max_leaves = 0;
-    for (int d = 0; d < D; ++d) max_leaves = std::max(max_leaves, p->g.leaf_cnt[d]);
-    k_triinv_leaf<<<dim3(max_leaves, D), NB, csm, st>>>(p->g);
-    VGGP_LAUNCH_CHECK();
-    for (auto& ph : p->triinv) if ((rc = launch_phase(ph, st))) return rc;
-    if ((rc = launch_phase(p->pinv, st))) return rc;
     if ((rc = launch_phase(p->rs, st))) return rc;
-    if ((rc = launch_phase(p->qq, st))) return rc;
-    if (p->obs_dtype == VGGP_F32) k_fwd_reduce<float><<<D, 1024, 0, st>>>(p->g);
-    else k_fwd_reduce<double><<<D, 1024, 0, st>>>(p->g);
-    VGGP_LAUNCH_CHECK();
+    if (!p->g.structured) {
+        if ((rc = launch_phase(p->qq, st))) return rc;
+    }
+    {
+        dim3 rgrid(ceil_div(p->nmax, 8), D), tgrid(ceil_div(p->nmax, 256), D);
+        if (p->obs_dtype == VGGP_F32) {
+            k_fwd_reduce<float><<<rgrid, 256, 0, st>>>(p->g);
+            VGGP_LAUNCH_CHECK();
+            k_fwd_qtable<float><<<tgrid, 256, 0, st>>>(p->g);
+        } else {
+            k_fwd_reduce<double><<<rgrid, 256, 0, st>>>(p->g);
+            VGGP_LAUNCH_CHECK();
+            k_fwd_qtable<double><<<tgrid, 256, 0, st>>>(p->g);
+        }
+        VGGP_LAUNCH_CHECK();
+    }
     for (auto& ph : p->chains) if ((rc = launch_phase(ph, st))) return rc;
     if ((rc = launch_phase(p->alpha_phase, st))) return rc;
     const int cblocks = (int)std::min<i64>((p->M + 255) / 256, 148 * 4);
@@ -752,10 +799,13 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     k_sym<<<egrid, 256, 0, st>>>(p->g);
     VGGP_LAUNCH_CHECK();
     if ((rc = launch_phase(p->Yp, st))) return rc;
-    if ((rc = launch_phase(p->dKp, st))) return rc;
+    if (!p->g.structured) {
+        if ((rc = launch_phase(p->dKp, st))) return rc;
+    }
     k_bwd_dL<<<egrid, 256, 0, st>>>(p->g, dL);
     VGGP_LAUNCH_CHECK();
-    k_bwd_theta<<<D, 1024, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
+    VGGP_CUDA(cudaMemsetAsync(dtheta, 0, sizeof(double) * (2 * D + 1), st));
+    k_bwd_theta<<<dim3(p->g.structured ? 24 : 64, D), 256, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -871,7 +921,7 @@ int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int
         case VGGP_WS_P: *ptr = p->g.P[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_R: *ptr = p->g.R[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_Q: *ptr = p->g.Q[dim]; if (n_elems) *n_elems = nn; return 0;
-        case VGGP_WS_S: *ptr = p->g.S[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_S: return fail(VGGP_E_UNSUPPORTED, "S_d is no longer materialised");
         case VGGP_WS_KRAW: *ptr = p->g.Kraw[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_ALPHA: *ptr = p->alpha; if (n_elems) *n_elems = p->M; return 0;
         case VGGP_WS_SCAL: *ptr = p->g.sc; if (n_elems) *n_elems = SC_COUNT; return 0;
