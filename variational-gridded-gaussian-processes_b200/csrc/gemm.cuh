@@ -23,6 +23,7 @@ struct GemmDesc {
     i64 bsA, bsB, bsC;
     int splitk;          // > 1: partial sums are atomically added into C (C must already hold beta*C)
     int lower_only;      // skip output tiles strictly above the diagonal
+    int tri_b;           // 1: B(k,n) = 0 for k < n (lower-triangular B); 2: B(k,n) = 0 for k > n (its transpose)
     int a_mfast, b_kfast;  // which index is contiguous in memory (coalescing of the tile loads)
     int fast;              // eligible for the pipelined cp.async kernel (unit stride along one index of A, B and C rows)
     int a_kcontig, b_ncontig, a_vec2, b_vec2;
@@ -31,7 +32,8 @@ struct GemmDesc {
 };
 
 constexpr int GBM = 64, GBN = 64, GBK = 16;
-constexpr int GEMM_THREADS_MMA = 128, GEMM_THREADS_SIMT = 256;
+constexpr int GEMM_THREADS_MMA = 256, GEMM_THREADS_SIMT = 256;
+constexpr int GEMM_NI = 2;      // DMMA path: 8 warps as 2 (m) x 4 (n), each 32 x 16 = 4 x 2 tiles of m8n8
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -68,16 +70,19 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
         kend = min(d.k, kbeg + kchunk);
         if (kbeg >= kend) return;
     }
+    if (d.tri_b == 1) kbeg = max(kbeg, n0 / GBK * GBK);          // triangular operand: skip the all-zero k range
+    if (d.tri_b == 2) kend = min(kend, n0 + GBN);
+    if (kbeg >= kend && d.splitk > 1) return;
     const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
     const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
     double* __restrict__ Cb = d.C + (i64)b * d.bsC;
 
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // MMA: 4 warps as 2 x 2, 32 x 32 each
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;   // MMA: 8 warps as 2 x 4, 32 x 16 each
     const int ty = tid >> 4, tx = tid & 15;                  // SIMT: 16 x 16 threads, 4 x 4 each
 
-    double acc[4][4][MMA ? 2 : 1];
+    double acc[4][4][MMA ? 2 : 1];      // MMA path uses [4][GEMM_NI][2]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -115,15 +120,15 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
         if constexpr (MMA) {
 #pragma unroll
             for (int ks = 0; ks < GBK / 4; ++ks) {
-                double a[4], bb[4];
+                double a[4], bb[GEMM_NI];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi) a[mi] = As[wm + mi * 8 + g][ks * 4 + t];
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) bb[ni] = Bs[ks * 4 + t][wn + ni * 8 + g];
+                for (int ni = 0; ni < GEMM_NI; ++ni) bb[ni] = Bs[ks * 4 + t][wn + ni * 8 + g];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                    for (int ni = 0; ni < GEMM_NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
             }
         } else {
 #pragma unroll
@@ -146,7 +151,7 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
+            for (int ni = 0; ni < GEMM_NI; ++ni) {
                 const int row = m0 + wm + mi * 8 + g;
                 const int col = n0 + wn + ni * 8 + t * 2;
                 gemm_store(d, Cb, row, col, acc[mi][ni][0]);
@@ -161,7 +166,8 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pipelined path: 64 x 64 x 16 tiles, two cp.async stages, 4 warps of 32 x 32 (4 x 4 DMMA m8n8k4 tiles each).
+// Pipelined path: 64 x 64 x 16 tiles, two cp.async stages, 8 warps of 32 x 16 (4 x 2 DMMA m8n8k4 tiles each);
+// two warps per scheduler are needed to keep the DMMA pipe busy (ncu: 40 % with one warp per scheduler).
 // Operand tiles keep their memory orientation in shared memory (rows along the contiguous index) with row
 // pitches chosen so that the DMMA fragment reads are bank-conflict free:
 //   k-contiguous operand : [64][20]  (element (mn, k) at mn * 20 + k)
@@ -185,8 +191,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void gemm_stage_tile(double* sm, const double* __restrict__ base, i64 ld, bool kc, bool vec2,
                                                 int mn0, int k0, int mn_lim, int k_lim, int tid) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int c = tid + it * 128;
+    for (int it = 0; it < 2; ++it) {
+        const int c = tid + it * 256;
         int row, col, grow, gcol, row_lim, col_lim;
         double* dst;
         if (kc) { row = c >> 3; col = (c & 7) << 1; grow = mn0 + row; gcol = k0 + col; row_lim = mn_lim; col_lim = k_lim; dst = sm + row * 20 + col; }
@@ -218,6 +224,9 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         kend = min(d.k, kbeg + kchunk);
         if (kbeg >= kend) return;
     }
+    if (d.tri_b == 1) kbeg = max(kbeg, n0 / GBK * GBK);          // triangular operand: skip the all-zero k range
+    if (d.tri_b == 2) kend = min(kend, n0 + GBN);
+    if (kbeg >= kend && d.splitk > 1) return;
     const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
     const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
     double* __restrict__ Cb = d.C + (i64)b * d.bsC;
@@ -229,15 +238,15 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
 
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
     const int aoff = (wm + g) * sAm + t * sAk;
     const int boff = t * sBk + (wn + g) * sBn;
 
-    double acc[4][4][2];
+    double acc[4][GEMM_NI][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < GEMM_NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nk = (kend - kbeg + GBK - 1) / GBK;
     gemm_stage_tile(sm, Ab, lda, akc, d.a_vec2 != 0, m0, kbeg, d.m, kend, tid);
@@ -259,22 +268,22 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         const double* Bs = As + 1280;
 #pragma unroll
         for (int ks = 0; ks < GBK / 4; ++ks) {
-            double a[4], bb[4];
+            double a[4], bb[GEMM_NI];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) a[mi] = As[aoff + mi * 8 * sAm + ks * 4 * sAk];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bb[ni] = Bs[boff + ks * 4 * sBk + ni * 8 * sBn];
+            for (int ni = 0; ni < GEMM_NI; ++ni) bb[ni] = Bs[boff + ks * 4 * sBk + ni * 8 * sBn];
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                for (int ni = 0; ni < GEMM_NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < GEMM_NI; ++ni) {
             const int row = m0 + wm + mi * 8 + g;
             const int col = n0 + wn + ni * 8 + t * 2;
             gemm_store(d, Cb, row, col, acc[mi][ni][0]);

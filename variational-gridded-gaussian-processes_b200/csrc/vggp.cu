@@ -49,9 +49,8 @@ struct vggp_plan {
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
     std::vector<Phase> triinv;             // two launches per recursion depth, deepest first
-    Phase pinv, rs, qq, alpha_phase, gram, dPdL, Yp, dKp;
+    Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp;
     std::vector<Phase> chains;             // D-1 launches building T_d = m x_{e != d} P_e
-    std::vector<Phase> dm_chain;           // D launches: (kron P) g
     double* dm_result;
     std::vector<void*> allocs;
     // staging for vggp_elbo_host
@@ -153,10 +152,17 @@ GemmDesc gram_desc(const vggp_plan* p, int e, const double* ghat, const double* 
     gemm_desc_defaults(d);
     d.A = ghat; d.B = Td; d.C = dP;
     d.m = ne; d.n = ne; d.k = (int)(outer * inner);
-    d.kinner = (int)inner;
-    d.rsA = inner; d.csA = 1; d.koA = (i64)ne * inner;
-    d.csB = inner; d.rsB = 1; d.koB = (i64)ne * inner;
-    if (inner == 1) { d.rsA = 1; d.csA = 0; d.csB = 1; d.rsB = 0; }
+    if (outer == 1) {
+        // first mode: A(i, k=r) = ghat[i][r], B(k=r, j) = T[j][r]
+        d.rsA = inner; d.csA = 1; d.rsB = 1; d.csB = inner;
+    } else if (inner == 1) {
+        // last mode: A(i, k=o) = ghat[o][i], B(k=o, j) = T[o][j]
+        d.rsA = 1; d.csA = ne; d.rsB = ne; d.csB = 1;
+    } else {
+        d.kinner = (int)inner;
+        d.rsA = inner; d.csA = 1; d.koA = (i64)ne * inner;
+        d.csB = inner; d.rsB = 1; d.koB = (i64)ne * inner;
+    }
     d.rsC = ne; d.csC = 1;
     d.alpha = 1.0; d.beta = 0.0;
     const int tiles = ((ne + GBM - 1) / GBM) * ((ne + GBN - 1) / GBN) * n_descs_in_group;
@@ -253,7 +259,11 @@ int build_schedules(vggp_plan* p) {
         for (int d = 0; d < D; ++d) {
             const int n = p->n[d];
             a.push_back(square_desc(n, g.W[d], true, g.W[d], false, g.P[d], 1.0, 0.0));
-            b.push_back(square_desc(n, g.P[d], false, g.Lt[d], false, g.R[d], 1.0, 0.0));
+            {
+                GemmDesc r = square_desc(n, g.P[d], false, g.Lt[d], false, g.R[d], 1.0, 0.0);
+                r.tri_b = 1;                            // B = Lt is lower-triangular
+                b.push_back(r);
+            }
             c.push_back(square_desc(n, g.R[d], false, g.R[d], true, g.Q[d], 1.0, 0.0));
         }
         if ((rc = make_phase(p, a, p->pinv))) return rc;
@@ -284,33 +294,38 @@ int build_schedules(vggp_plan* p) {
         ds.push_back(mode_desc(p, D - 1, g.P[D - 1], p->Tm[D - 1], p->alpha));
         if ((rc = make_phase(p, ds, p->alpha_phase))) return rc;
     }
-    // ---- reverse: (kron P) g ----
+    // ---- reverse pass, three grouped launches:
+    //   bwdA = { first mode of (kron P) g,  Gram contractions dP_d }
+    //   bwdB = { remaining modes of (kron P) g (D = 2: the last one),  dP_d += dR_d Lt_d^T,  dLraw_d = P_d dR_d }
+    //   Yp   = { Y_d = P_d sym(dP_d) }     (+ dKp = { dK_d = -Y_d P_d } on the dense factor path)
+    // For D = 3 the middle mode of (kron P) g gets its own launch between bwdA and bwdB.
     {
+        std::vector<GemmDesc> A, B, mid, y, k;
         const double* src = p->gM;
         for (int e = 0; e < D; ++e) {
             double* dst = (e % 2 == 0) ? p->pgA : p->pgB;
-            std::vector<GemmDesc> ds;
-            ds.push_back(mode_desc(p, e, g.P[e], src, dst));
-            Phase ph;
-            if ((rc = make_phase(p, ds, ph))) return rc;
-            p->dm_chain.push_back(ph);
+            GemmDesc md = mode_desc(p, e, g.P[e], src, dst);
+            if (e == 0) A.push_back(md);
+            else if (e == D - 1) B.push_back(md);
+            else mid.push_back(md);
             src = dst;
             p->dm_result = dst;
         }
-    }
-    // ---- reverse: Gram contractions, dP += dR Lt^T, dLraw = P dR, Y = P X, dK = -Y P ----
-    {
-        std::vector<GemmDesc> gr, a, y, k;
         for (int d = 0; d < D; ++d) {
             const int n = p->n[d];
-            gr.push_back(gram_desc(p, d, p->ghat, p->Tm[d], g.dP[d], D));
-            a.push_back(square_desc(n, g.dR[d], false, g.Lt[d], true, g.dP[d], 1.0, 1.0));
-            a.push_back(square_desc(n, g.P[d], false, g.dR[d], false, g.dLraw[d], 1.0, 0.0));
+            A.push_back(gram_desc(p, d, p->ghat, p->Tm[d], g.dP[d], D));
+            GemmDesc x1 = square_desc(n, g.dR[d], false, g.Lt[d], true, g.dP[d], 1.0, 1.0);
+            x1.tri_b = 2;                                   // B = Lt^T
+            B.push_back(x1);
+            GemmDesc x2 = square_desc(n, g.P[d], false, g.dR[d], false, g.dLraw[d], 1.0, 0.0);
+            x2.lower_only = 1;                              // only tril(dL) is used
+            B.push_back(x2);
             y.push_back(square_desc(n, g.P[d], false, g.X[d], false, g.Y[d], 1.0, 0.0));
             k.push_back(square_desc(n, g.Y[d], false, g.P[d], false, g.dK[d], -1.0, 0.0));
         }
-        if ((rc = make_phase(p, gr, p->gram))) return rc;
-        if ((rc = make_phase(p, a, p->dPdL))) return rc;
+        if ((rc = make_phase(p, A, p->bwdA))) return rc;
+        if ((rc = make_phase(p, mid, p->bwdMid))) return rc;
+        if ((rc = make_phase(p, B, p->bwdB))) return rc;
         if ((rc = make_phase(p, y, p->Yp))) return rc;
         if ((rc = make_phase(p, k, p->dKp))) return rc;
     }
@@ -782,12 +797,10 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     else
         k_bwd_prep<double><<<mblocks, 256, 0, st>>>(reinterpret_cast<const double*>(gbuf), p->mws, theta, D, ell_scale, p->gM, p->ghat, p->M);
     VGGP_LAUNCH_CHECK();
-    for (auto& ph : p->dm_chain) if ((rc = launch_phase(ph, st))) return rc;
-    k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
-    VGGP_LAUNCH_CHECK();
     for (int d = 0; d < D; ++d)
         VGGP_CUDA(cudaMemsetAsync(p->g.dP[d], 0, sizeof(double) * (size_t)p->n[d] * p->n[d], st));
-    if ((rc = launch_phase(p->gram, st))) return rc;
+    if ((rc = launch_phase(p->bwdA, st))) return rc;
+    if ((rc = launch_phase(p->bwdMid, st))) return rc;
     const i64 nn = (i64)p->nmax * p->nmax;
     dim3 egrid(ceil_div(nn, 256), D);
     if (p->obs_dtype == VGGP_F32)
@@ -795,7 +808,9 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     else
         k_bwd_dP_dR<double><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const double*>(gbuf) + p->M, theta, ell_scale);
     VGGP_LAUNCH_CHECK();
-    if ((rc = launch_phase(p->dPdL, st))) return rc;
+    if ((rc = launch_phase(p->bwdB, st))) return rc;
+    k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
+    VGGP_LAUNCH_CHECK();
     k_sym<<<egrid, 256, 0, st>>>(p->g);
     VGGP_LAUNCH_CHECK();
     if ((rc = launch_phase(p->Yp, st))) return rc;
