@@ -110,6 +110,71 @@ def test_elbo_and_grads_match_oracle_b1(vg, dev, knots, N, dtype, tol, layout):
         assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
 
 
+B0_CASES = [((14,), 600), ((10, 8), 700), ((71, 14), 1500)]
+
+
+@pytest.mark.parametrize("knots,N", B0_CASES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-3)])
+def test_elbo_and_grads_match_oracle_b0(vg, dev, knots, N, dtype, tol):
+    """B0 (cell-integrated Matern-1/2) family: dense, hyper-parameter dependent features; observations partly outside
+    the mesh (the features are non-zero there)."""
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=77 + D, family=O.B0_GRIDDED)
+    l = l * 0.3 + 0.03            # keep l / delta where the reference's float32-rounded Toeplitz factor is PD
+    Xq, yq = X.to(dtype), y.to(dtype)
+    scale = 1.3
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = vg.GridPlan(vg.B0_GRIDDED, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=scale)
+    assert plan.read_info() == 0
+    assert out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (out.cpu(), elbo_ref)
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10, ("dl", dtheta[:D].cpu(), g_ref[0])
+    assert relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10, ("ds2", dtheta[D:2 * D].cpu(), g_ref[1])
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10, ("dnoise", dtheta[2 * D].cpu(), g_ref[2])
+    assert relerr(dm, g_ref[3]) < tol * 10, "dm"
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n).cpu()
+        off += n * n
+        assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
+
+
+@pytest.mark.parametrize("pset", ["raw0", "raw1"])
+def test_b0_1d_matches_reference_collapsed_bound_at_optimal_q(vg, dev, golden_dir, pset):
+    """Direct pin to numbers produced by the reference's own code (oracle/make_golden.py, case G3:
+    gridded_univariate_structure.Matern12GriddedGP): in 1-D every covariance is a 'Kronecker product of one factor', so
+    the CUDA uncollapsed bound evaluated at the reference's optimal q(v) = N(m*, S*) must equal the reference's
+    collapsed `_elbo()`."""
+    import os
+    ref = np.load(os.path.join(golden_dir, "reference_models.npz"))
+    key = f"G3_griddedgp1d.{pset}"
+    x = torch.from_numpy(ref["g3.x"])
+    y = torch.from_numpy(ref["g3.y"])
+    m_star = torch.from_numpy(ref[key + ".q_mean"])
+    S_star = torch.from_numpy(ref[key + ".q_cov"])
+    elbo_ref = float(ref[key + ".elbo"])
+    raw = {"raw0": (0.0, 0.0, 0.0), "raw1": (-0.3, 0.5, -3.0)}[pset]       # (raw_l, raw_s, raw_noise), make_golden.py
+    l, s2, noise = O.constrain(torch.tensor([raw[0]], dtype=torch.float64), torch.tensor([raw[1]], dtype=torch.float64),
+                               torch.tensor(raw[2], dtype=torch.float64))
+    mesh = torch.linspace(0.0, 2.0, 33)
+    S_sym = 0.5 * (S_star + S_star.T)
+    Lc = torch.linalg.cholesky(S_sym)
+    plan = vg.GridPlan(vg.B0_GRIDDED, [mesh], torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    out, dtheta, dm, dL = plan.step(theta, m_star.to(dev).contiguous(), Lc.reshape(-1).to(dev).contiguous(),
+                                    [x.to(dev).contiguous()], y.to(dev).contiguous())
+    assert plan.read_info() == 0
+    assert abs(out[0].item() - elbo_ref) < 1e-6 * abs(elbo_ref), (out[0].item(), elbo_ref)
+    # (m*, S*) is the maximiser of the uncollapsed bound: its gradient w.r.t. m vanishes there
+    alpha = plan.workspace(vg._lib.WS_ALPHA)
+    assert dm.abs().max().item() < 1e-6 * alpha.abs().max().item()
+
+
 def test_simt_and_dmma_paths_agree(vg, dev):
     knots, N = (40, 33), 2000
     meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5)

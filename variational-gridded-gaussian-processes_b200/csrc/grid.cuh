@@ -28,6 +28,7 @@ struct GridDims {
     i64 Loff[VGGP_MAX_D];         // offset of L_d inside the concatenated L / dL arrays
     int band_off[VGGP_MAX_D];     // offset (elements) of dim d's block inside the gbuf band part [bp_d|bp_o|bq_d|bq_o]
     int tab_off[VGGP_MAX_D];      // offset (elements) of dim d's block inside the per-cell tables (8 n_d each)
+    i64 gfac_off[VGGP_MAX_D];     // B0 family: offset of dim d's [bP | bQ] block inside the gbuf factor part
     double* Kraw[VGGP_MAX_D];
     double* Kc[VGGP_MAX_D];       // factored in place -> Cholesky factor (lower)
     double* W[VGGP_MAX_D];        // C^-1
@@ -446,6 +447,25 @@ __global__ void __launch_bounds__(256) k_bwd_dP_dR(const __grid_constant__ GridD
     g.dR[d][e] = 2.0 * cQ * r;
 }
 
+// Dense-feature (B0) family: the per-observation kernel returns FULL factor-gradient sums bP_d, bQ_d.
+//   dP_d += cP bP_d ;  X_d = cQ (bQ_d + bQ_d^T) = 2 cQ sym(bQ_d)   (then dR_d = X_d R_d by a GEMM)
+// grid (ceil(nmax^2/256), D)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_dense_prep(const __grid_constant__ GridDims g, const T* __restrict__ gfac,
+                                                        const double* __restrict__ theta, double ell_scale) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (i64)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    const double noise = theta[2 * g.D];
+    const double cP = ell_scale / (2.0 * noise), cQ = -ell_scale / (2.0 * noise);
+    const T* __restrict__ bP = gfac + g.gfac_off[d];
+    const T* __restrict__ bQ = bP + (i64)n * n;
+    g.dP[d][e] += cP * (double)bP[e];
+    g.X[d][e] = cQ * ((double)bQ[e] + (double)bQ[(i64)j * n + i]);
+}
+
 // X = (dP + dP^T) / 2.   grid (ceil(nmax^2/256), D)
 __global__ void __launch_bounds__(256) k_sym(const __grid_constant__ GridDims g) {
     const int d = blockIdx.y;
@@ -541,6 +561,11 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
             const double E = gscal[0], nobs = gscal[1];
             const double dkff = -ell_scale * nobs / (2.0 * noise);
             atomicAdd(dtheta + D + d, dkff * kff / theta[D + d]);
+            if (g.family == VGGP_B0_GRIDDED) {
+                // the features themselves depend on (l_d, s2_d): sums accumulated by the per-observation kernel
+                atomicAdd(dtheta + d, (ell_scale / noise) * gscal[3 + d]);
+                atomicAdd(dtheta + D + d, (ell_scale / noise) * gscal[5 + d] / theta[D + d]);
+            }
             if (d == 0) {
                 const double tot = E + nobs * kff;
                 const double ell = -0.5 * nobs * log(2.0 * 3.14159265358979323846 * noise) - tot / (2.0 * noise);

@@ -593,4 +593,246 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1 for the B0 (cell-integrated Matern-1/2) family: dense features phi_d(x) in R^{M_d} that depend on
+// (l_d, s2_d).  This is the reference's own O(N (M + sum M_d^2)) dense algorithm (gridded_kronecker_structure.py:
+// 1392-1407 + kronecker_structure.py:265-275) restated per tile of observations -- features live in shared memory and
+// never reach HBM -- with the reverse pass fused in.  D <= 2 (as the reference).  It is the correctness baseline for
+// this family; the tensor-core / semiseparable-scan forms replace it later.
+//
+// Per observation n:  mu = phi_1^T A phi_2,  p_d = phi_d^T P_d phi_d,  q_d = phi_d^T Q_d phi_d,  r = y - mu.
+// Outputs (raw sums; 1/noise, ell_scale applied on the grid side):
+//   g_alpha[i][j] += r phi_1[i] phi_2[j]
+//   bP_d[i][j]    += (prod_{e!=d} p_e) phi_d[i] phi_d[j]        bQ_d likewise with q
+//   E             += r^2 - prod p + prod q
+//   G_l[d]        += sum_i gphi_d[i] dphi_d[i]/dl,   G_s[d] += sum_i gphi_d[i] phi_d[i]      (features depend on theta)
+//        with gphi_d = r V_d + (prod_{e!=d} p_e) P_d phi_d - (prod_{e!=d} q_e) Q_d phi_d,  V_1 = A phi_2, V_2 = A^T phi_1
+// ---------------------------------------------------------------------------------------------------------
+constexpr int B0_TN = 4;        // observations per tile
+
+template <typename T, int D>
+struct B0Args {
+    const T* x[D];
+    const T* y;
+    i64 n;
+    MeshView mesh[D];
+    int nd[D];               // M_d = K_d - 1
+    const double* theta;     // l[D], s2[D], noise
+    const T* alpha;          // (M_1, M_2) row-major, obs dtype
+    const double* P[D];
+    const double* Q[D];
+    T* galpha;
+    T* gfac;                 // per dim [bP (n_d^2) | bQ (n_d^2)]
+    i64 gfac_off[D];
+    double* gs;              // [E, n, -, G_l[0..1], G_s[0..1]]
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_obs_b0(const __grid_constant__ B0Args<T, D> a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[32];
+    __shared__ T s_r[B0_TN], s_op[D][B0_TN], s_oq[D][B0_TN];
+    // shared arrays, each [sum_d n_d][B0_TN]
+    int off[D], ntot = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { off[d] = ntot; ntot += a.nd[d]; }
+    T* phi = reinterpret_cast<T*>(smraw);
+    T* dphi = phi + (size_t)ntot * B0_TN;
+    T* V = dphi + (size_t)ntot * B0_TN;
+    T* Zp = V + (size_t)ntot * B0_TN;
+    T* Zq = Zp + (size_t)ntot * B0_TN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const i64 ntiles = (a.n + B0_TN - 1) / B0_TN;
+    double accE = 0.0, accGl[D], accGs[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { accGl[d] = 0.0; accGs[d] = 0.0; }
+
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 n0 = tile * B0_TN;
+        // ---- 1. features and their lengthscale derivative ----
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const T l = (T)a.theta[d], s2 = (T)a.theta[D + d];
+            for (int e = tid; e < a.nd[d] * B0_TN; e += blockDim.x) {
+                const int k = e / B0_TN, t = e % B0_TN;
+                T f = (T)0, df = (T)0;
+                if (n0 + t < a.n) {
+                    const T xv = a.x[d][n0 + t];
+                    const int idx = lower_bound_knots<T>(a.mesh[d].t, a.mesh[d].K, xv);
+                    const T A1 = fabs(xv - (T)a.mesh[d].t[k]), A2 = fabs(xv - (T)a.mesh[d].t[k + 1]);
+                    const T e1 = exp(-A1 / l), e2 = exp(-A2 / l);
+                    const T g1 = e1 * ((T)1 + A1 / l), g2 = e2 * ((T)1 + A2 / l);     // d/dl of l exp(-A/l)
+                    const int sgn = idx - k - 1;
+                    if (sgn == 0) { f = (T)2 * l - (l * e1 + l * e2); df = (T)2 - (g1 + g2); }
+                    else if (sgn > 0) { f = -(l * e1 - l * e2); df = -(g1 - g2); }
+                    else { f = l * e1 - l * e2; df = g1 - g2; }
+                    f *= s2;
+                    df *= s2;
+                }
+                phi[(size_t)(off[d] + k) * B0_TN + t] = f;
+                dphi[(size_t)(off[d] + k) * B0_TN + t] = df;
+            }
+        }
+        __syncthreads();
+        // ---- 2. V_d: contraction of alpha with the other dimension's features; Zp, Zq ----
+        if (D == 1) {
+            for (int e = tid; e < a.nd[0] * B0_TN; e += blockDim.x) V[e] = a.alpha[e / B0_TN];
+        } else {
+            const int n1 = a.nd[0], n2 = a.nd[D - 1];
+            for (int i = warp; i < n1; i += nwarps) {            // V_1[i][t] = sum_j A[i][j] phi_2[j][t]
+                T acc[B0_TN];
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) acc[t] = (T)0;
+                for (int j = lane; j < n2; j += 32) {
+                    const T av = a.alpha[(i64)i * n2 + j];
+#pragma unroll
+                    for (int t = 0; t < B0_TN; ++t) acc[t] += av * phi[(size_t)(off[D - 1] + j) * B0_TN + t];
+                }
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) {
+                    const T v = warp_sum(acc[t]);
+                    if (lane == 0) V[(size_t)(off[0] + i) * B0_TN + t] = v;
+                }
+            }
+            for (int j = tid; j < n2; j += blockDim.x) {         // V_2[j][t] = sum_i A[i][j] phi_1[i][t]
+                T acc[B0_TN];
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) acc[t] = (T)0;
+                for (int i = 0; i < n1; ++i) {
+                    const T av = a.alpha[(i64)i * n2 + j];
+#pragma unroll
+                    for (int t = 0; t < B0_TN; ++t) acc[t] += av * phi[(size_t)(off[0] + i) * B0_TN + t];
+                }
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) V[(size_t)(off[D - 1] + j) * B0_TN + t] = acc[t];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int nn = a.nd[d];
+            for (int i = warp; i < nn; i += nwarps) {
+                T ap[B0_TN], aq[B0_TN];
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) { ap[t] = (T)0; aq[t] = (T)0; }
+                for (int j = lane; j < nn; j += 32) {
+                    const T pv = (T)a.P[d][(i64)i * nn + j], qv = (T)a.Q[d][(i64)i * nn + j];
+#pragma unroll
+                    for (int t = 0; t < B0_TN; ++t) {
+                        const T f = phi[(size_t)(off[d] + j) * B0_TN + t];
+                        ap[t] += pv * f;
+                        aq[t] += qv * f;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) {
+                    const T vp = warp_sum(ap[t]), vq = warp_sum(aq[t]);
+                    if (lane == 0) {
+                        Zp[(size_t)(off[d] + i) * B0_TN + t] = vp;
+                        Zq[(size_t)(off[d] + i) * B0_TN + t] = vq;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. per-observation scalars: one warp per observation of the tile ----
+        if (warp < B0_TN) {
+            const int t = warp;
+            T mu = (T)0, p[D], q[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { p[d] = (T)0; q[d] = (T)0; }
+            for (int i = lane; i < a.nd[0]; i += 32) mu += phi[(size_t)(off[0] + i) * B0_TN + t] * V[(size_t)(off[0] + i) * B0_TN + t];
+            mu = warp_sum(mu);
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                for (int i = lane; i < a.nd[d]; i += 32) {
+                    const T f = phi[(size_t)(off[d] + i) * B0_TN + t];
+                    p[d] += f * Zp[(size_t)(off[d] + i) * B0_TN + t];
+                    q[d] += f * Zq[(size_t)(off[d] + i) * B0_TN + t];
+                }
+                p[d] = warp_sum(p[d]);
+                q[d] = warp_sum(q[d]);
+            }
+            if (lane == 0) {
+                const bool live = (n0 + t < a.n);
+                const T r = live ? a.y[n0 + t] - mu : (T)0;
+                T pp = (T)1, qq = (T)1;
+#pragma unroll
+                for (int d = 0; d < D; ++d) { pp *= p[d]; qq *= q[d]; }
+                if (live) accE += (double)(r * r - pp + qq);
+                s_r[t] = r;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    T op = (T)1, oq = (T)1;
+#pragma unroll
+                    for (int e = 0; e < D; ++e)
+                        if (e != d) { op *= p[e]; oq *= q[e]; }
+                    s_op[d][t] = live ? op : (T)0;
+                    s_oq[d][t] = live ? oq : (T)0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. reverse pass ----
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double gl = 0.0, gsv = 0.0;
+            for (int e = tid; e < a.nd[d] * B0_TN; e += blockDim.x) {
+                const int t = e % B0_TN;
+                const size_t o = (size_t)off[d] * B0_TN + e;
+                const T gphi = s_r[t] * V[o] + s_op[d][t] * Zp[o] - s_oq[d][t] * Zq[o];
+                gl += (double)(gphi * dphi[o]);
+                gsv += (double)(gphi * phi[o]);
+            }
+            accGl[d] += gl;
+            accGs[d] += gsv;
+            const int nn = a.nd[d];
+            T* gP = a.gfac + a.gfac_off[d];
+            T* gQ = gP + (i64)nn * nn;
+            for (int e = tid; e < nn * nn; e += blockDim.x) {
+                const int i = e / nn, j = e % nn;
+                T vp = (T)0, vq = (T)0;
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) {
+                    const T ff = phi[(size_t)(off[d] + i) * B0_TN + t] * phi[(size_t)(off[d] + j) * B0_TN + t];
+                    vp += s_op[d][t] * ff;
+                    vq += s_oq[d][t] * ff;
+                }
+                atomicAdd(gP + e, vp);
+                atomicAdd(gQ + e, vq);
+            }
+        }
+        if (D == 1) {
+            for (int i = tid; i < a.nd[0]; i += blockDim.x) {
+                T v = (T)0;
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t) v += s_r[t] * phi[(size_t)i * B0_TN + t];
+                atomicAdd(a.galpha + i, v);
+            }
+        } else {
+            const int n1 = a.nd[0], n2 = a.nd[D - 1];
+            for (int e = tid; e < n1 * n2; e += blockDim.x) {
+                const int i = e / n2, j = e % n2;
+                T v = (T)0;
+#pragma unroll
+                for (int t = 0; t < B0_TN; ++t)
+                    v += s_r[t] * phi[(size_t)(off[0] + i) * B0_TN + t] * phi[(size_t)(off[D - 1] + j) * B0_TN + t];
+                atomicAdd(a.galpha + e, v);
+            }
+        }
+        __syncthreads();
+    }
+    double e = block_sum(accE, red);
+    if (tid == 0) atomicAdd(a.gs + 0, e);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double gl = block_sum(accGl[d], red);
+        const double gsv = block_sum(accGs[d], red);
+        if (tid == 0) {
+            atomicAdd(a.gs + 3 + d, gl);
+            atomicAdd(a.gs + 5 + d, gsv);
+        }
+    }
+    if (tid == 0 && blockIdx.x == 0) a.gs[1] = (double)a.n;
+}
+
 }  // namespace vggp

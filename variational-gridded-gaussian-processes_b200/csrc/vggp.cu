@@ -38,8 +38,10 @@ struct vggp_plan {
     // M-sized float64 work tensors
     double *mws, *alpha, *Tm[VGGP_MAX_D], *tmpM[VGGP_MAX_D], *gM, *ghat, *pgA, *pgB;
     void* alphaT;
+    double* theta_dev;                     // copy of theta of the last forward (the B0 features depend on it)
     int band_off[VGGP_MAX_D], band_total, knot_off[VGGP_MAX_D], knot_total;
     int tab_off[VGGP_MAX_D], tab_total;
+    i64 gfac_off[VGGP_MAX_D], gfac_total;   // B0 family: full factor-gradient blocks [bP | bQ] per dim
     unsigned char* tables;                 // [band tables (obs dtype) | pad16 | knots (float32) | pad16]
     int table_bytes, knots_byte_off;
     int sm_count, obs_blocks_per_sm;
@@ -49,7 +51,7 @@ struct vggp_plan {
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
     std::vector<Phase> triinv;             // two launches per recursion depth, deepest first
-    Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp;
+    Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp, dRp;
     std::vector<Phase> chains;             // D-1 launches building T_d = m x_{e != d} P_e
     double* dm_result;
     std::vector<void*> allocs;
@@ -300,7 +302,7 @@ int build_schedules(vggp_plan* p) {
     //   Yp   = { Y_d = P_d sym(dP_d) }     (+ dKp = { dK_d = -Y_d P_d } on the dense factor path)
     // For D = 3 the middle mode of (kron P) g gets its own launch between bwdA and bwdB.
     {
-        std::vector<GemmDesc> A, B, mid, y, k;
+        std::vector<GemmDesc> A, B, mid, y, k, dr;
         const double* src = p->gM;
         for (int e = 0; e < D; ++e) {
             double* dst = (e % 2 == 0) ? p->pgA : p->pgB;
@@ -322,7 +324,9 @@ int build_schedules(vggp_plan* p) {
             B.push_back(x2);
             y.push_back(square_desc(n, g.P[d], false, g.X[d], false, g.Y[d], 1.0, 0.0));
             k.push_back(square_desc(n, g.Y[d], false, g.P[d], false, g.dK[d], -1.0, 0.0));
+            dr.push_back(square_desc(n, g.X[d], false, g.R[d], false, g.dR[d], 1.0, 0.0));   // dense family: dR = 2 cQ sym(bQ) R
         }
+        if ((rc = make_phase(p, dr, p->dRp))) return rc;
         if ((rc = make_phase(p, A, p->bwdA))) return rc;
         if ((rc = make_phase(p, mid, p->bwdMid))) return rc;
         if ((rc = make_phase(p, B, p->bwdB))) return rc;
@@ -444,6 +448,45 @@ int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort
     return 0;
 }
 
+template <typename T, int D>
+int launch_obs_b0(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
+    B0Args<T, D> a;
+    int ntot = 0;
+    for (int d = 0; d < D; ++d) {
+        a.x[d] = reinterpret_cast<const T*>(x[d]);
+        a.mesh[d] = p->mesh[d];
+        a.nd[d] = p->n[d];
+        a.P[d] = p->g.P[d];
+        a.Q[d] = p->g.Q[d];
+        a.gfac_off[d] = p->gfac_off[d];
+        ntot += p->n[d];
+    }
+    a.y = reinterpret_cast<const T*>(y);
+    a.n = n;
+    a.theta = p->theta_dev;
+    a.alpha = reinterpret_cast<const T*>(p->alphaT);
+    T* gb = reinterpret_cast<T*>(gbuf);
+    a.galpha = gb;
+    a.gfac = gb + p->M;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    const size_t smem = (size_t)5 * ntot * B0_TN * sizeof(T);
+    if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "B0 feature tiles do not fit in shared memory");
+    VGGP_CUDA(cudaFuncSetAttribute(k_obs_b0<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 tiles = (n + B0_TN - 1) / B0_TN;
+    const int blocks = (int)std::min<i64>(tiles, (i64)p->sm_count * 2);
+    k_obs_b0<T, D><<<blocks, 256, smem, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int obs_b0_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
+    if (p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
+    if (p->obs_dtype == VGGP_F32) return p->D == 1 ? launch_obs_b0<float, 1>(p, x, y, n, gbuf, st) : launch_obs_b0<float, 2>(p, x, y, n, gbuf, st);
+    return p->D == 1 ? launch_obs_b0<double, 1>(p, x, y, n, gbuf, st) : launch_obs_b0<double, 2>(p, x, y, n, gbuf, st);
+}
+
 #define VGGP_DISPATCH_TD(p, FN, ...)                                                        \
     do {                                                                                    \
         if ((p)->obs_dtype == VGGP_F32) {                                                   \
@@ -512,6 +555,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     g.D = D; g.family = family; g.obs_dtype = obs_dtype;
     g.structured = (family == VGGP_B1_ASVGP && g_b1_structured) ? 1 : 0;
     int boff = 0, koff = 0, toff = 0;
+    i64 foff = 0;
     for (int d = 0; d < D; ++d) {
         p->K[d] = n_knots[d];
         p->n[d] = (family == VGGP_B1_ASVGP) ? n_knots[d] : n_knots[d] - 1;
@@ -525,11 +569,14 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         boff += 4 * p->n[d];
         p->tab_off[d] = toff; g.tab_off[d] = toff;
         toff += 8 * p->n[d];
+        p->gfac_off[d] = foff; g.gfac_off[d] = foff;
+        foff += 2 * (i64)p->n[d] * p->n[d];
         p->knot_off[d] = koff;
         koff += p->K[d];
     }
     p->band_total = boff;
     p->tab_total = toff;
+    p->gfac_total = foff;
     p->knot_total = koff;
     g.M = p->M;
     for (int d = 0; d < D; ++d) {
@@ -599,6 +646,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         TRY(dev_alloc(p, &a, p->M * (i64)tsz));
         p->alphaT = a;
     }
+    TRY(dev_alloc(p, &p->theta_dev, 2 * VGGP_MAX_D + 1));
     TRY(dev_alloc(p, &p->mws, p->M)); TRY(dev_alloc(p, &p->alpha, p->M));
     TRY(dev_alloc(p, &p->gM, p->M)); TRY(dev_alloc(p, &p->ghat, p->M));
     TRY(dev_alloc(p, &p->pgA, p->M)); TRY(dev_alloc(p, &p->pgB, p->M));
@@ -654,7 +702,7 @@ int vggp_gbuf_layout(const vggp_plan* p, int64_t* n_obs_elems, int64_t* scalar_o
                      int64_t* total_bytes) {
     if (!p) return fail(VGGP_E_ARG, "null plan");
     const i64 tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
-    const i64 ne = p->M + p->band_total;
+    const i64 ne = p->M + (p->family == VGGP_B0_GRIDDED ? p->gfac_total : (i64)p->band_total);
     const i64 soff = (ne * tsz + 7) / 8 * 8;
     if (n_obs_elems) *n_obs_elems = ne;
     if (scalar_offset_bytes) *scalar_offset_bytes = soff;
@@ -669,6 +717,7 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
     const int D = p->D;
     int rc;
     VGGP_CUDA(cudaMemcpyAsync(p->mws, m, sizeof(double) * p->M, cudaMemcpyDeviceToDevice, st));
+    VGGP_CUDA(cudaMemcpyAsync(p->theta_dev, theta, sizeof(double) * (2 * D + 1), cudaMemcpyDeviceToDevice, st));
     const i64 nn = (i64)p->nmax * p->nmax;
     dim3 egrid(ceil_div(nn, 256), D);
     k_build_factors<<<egrid, 256, 0, st>>>(p->g, theta, L);
@@ -733,6 +782,7 @@ int vggp_obs_pack(vggp_plan* p, const void* const* x, const void* y, int64_t n, 
                   void* yp, void* stream) {
     if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n == 0) return 0;
+    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the packed layout is used by the B1 family only");
     if (!x || !y || !xp || !yp) return fail(VGGP_E_ARG, "null argument");
     for (int d = 0; d < p->D; ++d)
         if (!x[d] || !xp[d]) return fail(VGGP_E_ARG, "null observation pointer");
@@ -750,16 +800,23 @@ int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp,
     for (int d = 0; d < p->D; ++d)
         if (!xp[d]) return fail(VGGP_E_ARG, "null observation pointer");
     if (p->family != VGGP_B1_ASVGP)
-        return fail(VGGP_E_UNSUPPORTED, "per-observation kernel for the B0 (cell-integrated) family is not built yet");
+        return fail(VGGP_E_UNSUPPORTED, "the packed layout is used by the B1 family only; call vggp_obs_fwd_bwd");
     return obs_packed_dispatch(p, xp, yp, n, gbuf, st);
 }
 
 int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
-    if (n == 0) return vggp_obs_fwd_bwd_packed(p, nullptr, nullptr, 0, gbuf, stream);
-    if (p->family != VGGP_B1_ASVGP)
-        return fail(VGGP_E_UNSUPPORTED, "per-observation kernel for the B0 (cell-integrated) family is not built yet");
+    if (n == 0 || p->family != VGGP_B1_ASVGP) {
+        cudaStream_t st0 = (cudaStream_t)stream;
+        i64 ne0, so0, ns0, tot0;
+        vggp_gbuf_layout(p, &ne0, &so0, &ns0, &tot0);
+        VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)tot0, st0));
+        if (n == 0) return 0;
+        for (int d = 0; d < p->D; ++d)
+            if (!x[d]) return fail(VGGP_E_ARG, "null observation pointer");
+        return obs_b0_dispatch(p, x, y, n, gbuf, st0);
+    }
     // unpacked input: transpose into the packed layout (input order kept) in plan-owned scratch, grown on demand
     const PackGeom g = pack_geometry(p, n);
     const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
@@ -803,11 +860,20 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     if ((rc = launch_phase(p->bwdMid, st))) return rc;
     const i64 nn = (i64)p->nmax * p->nmax;
     dim3 egrid(ceil_div(nn, 256), D);
-    if (p->obs_dtype == VGGP_F32)
-        k_bwd_dP_dR<float><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const float*>(gbuf) + p->M, theta, ell_scale);
-    else
-        k_bwd_dP_dR<double><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const double*>(gbuf) + p->M, theta, ell_scale);
-    VGGP_LAUNCH_CHECK();
+    if (p->family == VGGP_B1_ASVGP) {
+        if (p->obs_dtype == VGGP_F32)
+            k_bwd_dP_dR<float><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const float*>(gbuf) + p->M, theta, ell_scale);
+        else
+            k_bwd_dP_dR<double><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const double*>(gbuf) + p->M, theta, ell_scale);
+        VGGP_LAUNCH_CHECK();
+    } else {
+        if (p->obs_dtype == VGGP_F32)
+            k_bwd_dense_prep<float><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const float*>(gbuf) + p->M, theta, ell_scale);
+        else
+            k_bwd_dense_prep<double><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const double*>(gbuf) + p->M, theta, ell_scale);
+        VGGP_LAUNCH_CHECK();
+        if ((rc = launch_phase(p->dRp, st))) return rc;
+    }
     if ((rc = launch_phase(p->bwdB, st))) return rc;
     k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
     VGGP_LAUNCH_CHECK();

@@ -107,8 +107,9 @@ class GriddedVariationalGP(nn.Module):
             xs = [Xd[:, d].contiguous() for d in range(self.D)]       # structure of arrays, made once
             y = self.train_targets.reshape(-1).to(device=device, dtype=dtype).contiguous()
             self._obs = (xs, y)
-            # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant)
-            self._packed = self._plan.pack(xs, y, sort_by_cell=True)
+            # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant); the packed
+            # layout belongs to the compact-stencil (B1) kernel, the dense-feature (B0) kernel streams plain arrays
+            self._packed = self._plan.pack(xs, y, sort_by_cell=True) if self.family == _lib.B1_ASVGP else None
         return self._plan
 
     # ---- the hot path ---------------------------------------------------------------------------------------
@@ -116,7 +117,10 @@ class GriddedVariationalGP(nn.Module):
         """Evidence lower bound (0-dim tensor with grad_fn).  `batch`: optional index tensor / slice selecting a
         minibatch of this rank's observations; the expected log-likelihood is rescaled by N / B."""
         plan = self._ensure_plan()
-        xs, y = self._packed, None
+        if self._packed is not None:
+            xs, y = self._packed, None
+        else:
+            xs, y = self._obs
         scale = 1.0
         if batch is not None:
             xs = [x[batch].contiguous() for x in self._obs[0]]
