@@ -59,23 +59,35 @@ def field(x1, x2):
     return (torch.sin(5 * x1) + torch.cos(7 * x2) + 0.5 * torch.sin(15 * x1) + 0.5 * torch.cos(12 * x2))
 
 
+def _hash_uniform(idx, salt):
+    """Counter-based uniform(0,1) from the global observation index (int64 LCG + xorshift mix, wrap-around
+    arithmetic): the data set does not depend on how it is sharded over ranks."""
+    def wrap(v):                              # Python int -> two's-complement int64
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+    h = idx * wrap(6364136223846793005) + wrap(1442695040888963407 + salt * 7046029254386353131)
+    h = h ^ ((h >> 29) & ((1 << 35) - 1))     # logical shift
+    h = h * wrap(0xBF58476D1CE4E5B9)
+    h = h ^ ((h >> 32) & ((1 << 32) - 1))
+    return ((h >> 11) & ((1 << 40) - 1)).to(torch.float64) / float(1 << 40)
+
+
 def make_tracks(lo, hi, n_total, device, dtype, seed=0):
     """Observations lo..hi-1 (global acquisition order) of the synthetic track data set."""
-    n = hi - lo
-    g = torch.Generator(device=device)
-    g.manual_seed(seed * 7919 + lo % 104729)
     idx = torch.arange(lo, hi, device=device, dtype=torch.int64)
     per_pass = max(1, n_total // (2 * PASSES))
     j = torch.clamp(idx // per_pass, max=2 * PASSES - 1)
     k = idx - j * per_pass
-    jitter = torch.rand(n, generator=g, device=device, dtype=torch.float64)
+    jitter = _hash_uniform(idx, 2 * seed + 1)
     t = ((k.to(torch.float64) + jitter) / float(per_pass)).clamp_(0.0, 1.0)       # monotone along a pass
     asc = j < PASSES
     off = (j % PASSES).to(torch.float64) / PASSES
     x1 = off + t / TRACK_GRADIENT
     x1 = x1 - torch.floor(x1)
     x2 = torch.where(asc, t, 1.0 - t)
-    y = field(x1, x2) + 0.05 * torch.randn(n, generator=g, device=device, dtype=torch.float64)
+    # noise: sum of 4 uniforms (Irwin-Hall), variance 4/12 -> scaled to sigma = 0.05
+    u = sum(_hash_uniform(idx, 2 * seed + 10 + q) for q in range(4)) - 2.0
+    y = field(x1, x2) + 0.05 * math.sqrt(3.0) * u
     return [x1.to(dtype).contiguous(), x2.to(dtype).contiguous()], y.to(dtype).contiguous()
 
 

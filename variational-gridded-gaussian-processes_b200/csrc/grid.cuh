@@ -9,6 +9,7 @@ namespace vggp {
 
 constexpr int NB = 64;            // Cholesky / triangular-inverse block size
 constexpr int MAX_LEAVES = 40;    // supports M_d <= 2560
+constexpr int SS_SEG = 32;        // segment length of the semiseparable product kernel
 
 // scalar slots in the plan's float64 scalar block
 enum {
@@ -44,7 +45,9 @@ struct GridDims {
     double* dLraw[VGGP_MAX_D];
     double* tmp[VGGP_MAX_D];
     double* Qb[VGGP_MAX_D];       // float64 main / first off diagonal of Q_d: [diag (n) | off (n)]
-    int structured;               // 1: B1 family with the tridiagonal factor path (no dense Cholesky / Q / dK)
+    int structured;               // B1 family: 0 dense Cholesky path, 1 twisted-factorisation inverse + GEMM products,
+                                  // 2 (default) twisted factorisation + semiseparable O(n^2) products with P_d
+    double* gen[VGGP_MAX_D];      // semiseparable generators of P_d: [pd | ru | rl | gl | gu] each n, then [glend | guend] each nseg
     double* sc;                   // SC_COUNT scalars
     int* info;
     void* bandT;                  // per-cell tables in obs dtype: per dim [pe0 pe1 pe2 qe0 qe1 qe2 h rh], each n[d] long
@@ -303,6 +306,23 @@ __global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ Grid
     ld = block_sum(ld, red);
     if (blockIdx.x == 0 && tid == 0) g.sc[SC_LOGDETK + d] = ld;
     __syncthreads();
+    if (blockIdx.x == 0) {
+        // generators for the semiseparable products (k_ss_apply): segment-local decay products
+        //   gl[i] = prod_{k=a}^{i-1} rl[k],  gu[i] = prod_{k=i}^{b-2} ru[k]   for i in segment [a, b)
+        //   glend[s] = prod_{k=a}^{b-1} rl[k],  guend[s] = ru[a-1] * gu[a]
+        double* gen = g.gen[d];
+        const int nseg = (n + SS_SEG - 1) / SS_SEG;
+        for (int i = tid; i < n; i += 256) { gen[i] = pd[i]; gen[n + i] = ru[i]; gen[2 * n + i] = rl[i]; }
+        for (int sgi = tid; sgi < nseg; sgi += 256) {
+            const int a0 = sgi * SS_SEG, b0 = min(n, a0 + SS_SEG);
+            double pl = 1.0;
+            for (int i = a0; i < b0; ++i) { gen[3 * n + i] = pl; pl *= rl[i]; }
+            gen[5 * n + sgi] = pl;
+            double pu = 1.0;
+            for (int i = b0 - 1; i >= a0; --i) { gen[4 * n + i] = pu; if (i > a0) pu *= ru[i - 1]; }
+            gen[5 * n + nseg + sgi] = (a0 > 0) ? ru[a0 - 1] * pu : 0.0;
+        }
+    }
     const int j = (int)blockIdx.x * 256 + tid;
     if (j >= n) return;
     double* __restrict__ P = g.P[d];
@@ -316,6 +336,98 @@ __global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ Grid
     for (int i = j + 1; i < n; ++i) {
         p *= rl[i - 1];
         P[(i64)i * n + j] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Semiseparable product: dst = src x_mode P_d for the B1 family, O(M) per mode instead of a GEMM.
+//   P[i][j] = pd[j] prod_{k=i}^{j-1} ru[k] (i < j),  pd[i] (i == j),  pd[j] prod_{k=j}^{i-1} rl[k] (i > j)
+//   y_i = s_i + l_i + u_i,  s_i = pd_i x_i,  l_{i+1} = rl_i (s_i + l_i),  u_{i-1} = ru_{i-1} (s_i + u_i)
+// Every fibre is cut into segments of SS_SEG elements handled by one thread each (local recurrences with zero
+// carry-in, in registers); the carries are chained through shared memory by one thread per fibre and applied with
+// the precomputed segment-local decay products gl / gu.
+// One launch = a group of tasks (blockIdx.y); grid.x covers the fibres of the largest task.
+// ---------------------------------------------------------------------------------------------------------
+struct SsTask {
+    const double* src;
+    double* dst;
+    const double* gen;        // generators of the dimension being applied
+    int n;                    // M_d
+    int nseg;                 // ceil(n / SS_SEG)
+    int nseg_pad;             // power of two >= nseg, <= 256
+    i64 inner;                // element stride along the mode
+    i64 nfibres;              // outer * inner
+};
+
+constexpr int SS_MAX_TASKS = 8;
+struct SsGroup {
+    SsTask t[SS_MAX_TASKS];
+    int ntasks;
+};
+
+__global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGroup grp) {
+    __shared__ double sL[256], sU[256], sLin[256], sUin[256];
+    const SsTask& tk = grp.t[blockIdx.y];
+    const int fpb = 256 / tk.nseg_pad;                      // fibres per block
+    const int tid = threadIdx.x;
+    const int fl = tid % fpb, sg = tid / fpb;
+    const i64 f = (i64)blockIdx.x * fpb + fl;
+    if ((i64)blockIdx.x * fpb >= tk.nfibres) return;
+    const bool live = (f < tk.nfibres) && (sg < tk.nseg);
+    const int n = tk.n;
+    const int a0 = sg * SS_SEG;
+    const double* __restrict__ gen = tk.gen;
+    double sv[SS_SEG], yv[SS_SEG];
+    i64 base = 0;
+    if (live) {
+        const i64 o = f / tk.inner, r = f - o * tk.inner;
+        base = o * (i64)n * tk.inner + r;
+#pragma unroll
+        for (int j = 0; j < SS_SEG; ++j) {
+            const int i = a0 + j;
+            sv[j] = (i < n) ? gen[i] * tk.src[base + (i64)i * tk.inner] : 0.0;
+        }
+        double l = 0.0;
+#pragma unroll
+        for (int j = 0; j < SS_SEG; ++j) {
+            const int i = a0 + j;
+            yv[j] = sv[j] + l;
+            l = (i < n) ? gen[2 * n + i] * (sv[j] + l) : l;
+        }
+        double u = 0.0;
+#pragma unroll
+        for (int j = SS_SEG - 1; j >= 0; --j) {
+            const int i = a0 + j;
+            if (i < n) {
+                yv[j] += u;
+                u = (i > 0) ? gen[n + i - 1] * (sv[j] + u) : 0.0;
+            }
+        }
+        sL[tid] = l;
+        sU[tid] = u;
+    }
+    __syncthreads();
+    if (sg == 0 && f < tk.nfibres) {
+        // chain the carries of this fibre: Lin[s] = Lout[s-1], Lout[s] = Lloc[s] + Lin[s] * glend[s]
+        double c = 0.0;
+        for (int s2 = 0; s2 < tk.nseg; ++s2) {
+            sLin[s2 * fpb + fl] = c;
+            c = sL[s2 * fpb + fl] + c * gen[5 * n + s2];
+        }
+        c = 0.0;
+        for (int s2 = tk.nseg - 1; s2 >= 0; --s2) {
+            sUin[s2 * fpb + fl] = c;
+            c = sU[s2 * fpb + fl] + c * gen[5 * n + tk.nseg + s2];
+        }
+    }
+    __syncthreads();
+    if (live) {
+        const double lin = sLin[tid], uin = sUin[tid];
+#pragma unroll
+        for (int j = 0; j < SS_SEG; ++j) {
+            const int i = a0 + j;
+            if (i < n) tk.dst[base + (i64)i * tk.inner] = yv[j] + lin * gen[3 * n + i] + uin * gen[4 * n + i];
+        }
     }
 }
 
@@ -523,11 +635,15 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
         for (int e = wglobal; e < 3 * n; e += wtotal) {
             const int i = e / 3, j = i + (e % 3) - 1;
             if (j < 0 || j >= n) continue;
-            const double* Yi = Y + (i64)i * n;
-            const double* Pj = P + (i64)j * n;          // P symmetric: column j = row j
             double acc = 0.0;
-            for (int k = lane; k < n; k += 32) acc = fma(Yi[k], Pj[k], acc);
-            acc = warp_sum(acc);
+            if (g.structured == 2) {
+                acc = g.dK[d][(i64)i * n + j];          // Z = Y P from the semiseparable product (k_ss_apply)
+            } else {
+                const double* Yi = Y + (i64)i * n;
+                const double* Pj = P + (i64)j * n;      // P symmetric: column j = row j
+                for (int k = lane; k < n; k += 32) acc = fma(Yi[k], Pj[k], acc);
+                acc = warp_sum(acc);
+            }
             if (lane == 0) {
                 const double q = (i == j) ? g.Qb[d][i] : g.Qb[d][n + (i < j ? i : j)];
                 const double v = -acc + half_c * q - half_ratio * P[(i64)i * n + j];

@@ -11,6 +11,7 @@ struct MeshView {
     int K;
     float t0, inv_h;     // arithmetic guess of the cell: floor((x - t0) * inv_h)
     int nearly_uniform;  // guess is within +-2 cells of the truth (checked at plan creation)
+    float tfirst, tlast; // mesh[0], mesh[K-1]
 };
 
 // c = clamp(searchsorted(mesh, x, right=False) - 1, 0, K-2);  inside = mesh[0] <= x <= mesh[K-1].
@@ -265,7 +266,7 @@ struct PackedArgs {
     const T* yp;
     PackGeom geo;
     MeshView mesh[D];
-    i64 stride[D];
+    int stride[D];         // row-major strides of alpha (M < 2^31, checked at plan creation)
     int band_off[D];       // offset of dim d inside the gradient band block: [bp_d | bp_o | bq_d | bq_o] each n_d long
     int tab_off[D];        // offset (elements of T) of dim d inside the cell tables: [pe0 pe1 pe2 qe0 qe1 qe2 h rh] each n_d long
     int knot_off[D];
@@ -319,21 +320,22 @@ __device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<
         for (int i = 0; i < (1 << D); ++i)
             if (!(i & bit)) s.gm[i] -= s.gm[i | bit];
     }
-    i64 base = 0;
+    int base = 0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) base += (i64)s.c[d] * a.stride[d];
+    for (int d = 0; d < D; ++d) base += s.c[d] * a.stride[d];
+    T* ga = a.galpha + base;
 #pragma unroll
     for (int i = 0; i < (1 << D); ++i) {
-        i64 off = base;
+        int off = 0;
 #pragma unroll
         for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? a.stride[d] : 0;
-        atomicAdd(a.galpha + off, s.gm[i]);
+        atomicAdd(ga + off, s.gm[i]);
         s.gm[i] = (T)0;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int n = a.mesh[d].K;
-        T* gb = a.gband + a.band_off[d] + s.c[d];
+        T* gb = a.gband + (a.band_off[d] + s.c[d]);
         // sums of w (1-a)^2, w (1-a) a, w a^2 from the moments s0, s1, s2
         atomicAdd(gb, s.bp[d][0] - (T)2 * s.bp[d][1] + s.bp[d][2]);
         atomicAdd(gb + n, s.bp[d][1] - s.bp[d][2]);
@@ -350,11 +352,11 @@ __device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<
 template <typename T, int D>
 __device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneState<T, D>& s, const int (&c)[D],
                                                const T (&tl)[D], const T (&th)[D], const T* s_tab) {
-    i64 base = 0;
+    int base = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const int n = a.mesh[d].K;
-        const T* tb = s_tab + a.tab_off[d] + c[d];
+        const T* tb = s_tab + (a.tab_off[d] + c[d]);
         s.c[d] = c[d];
         s.tlo[d] = tl[d];
         s.tlo_chk[d] = tl[d];
@@ -363,14 +365,15 @@ __device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneSt
         s.qe[d][0] = tb[3 * n]; s.qe[d][1] = tb[4 * n]; s.qe[d][2] = tb[5 * n];
         s.h[d] = tb[6 * n];          // (T)(float32 knot difference), reference semantics
         s.rh[d] = tb[7 * n];         // correctly rounded 1 / h
-        base += (i64)c[d] * a.stride[d];
+        base += c[d] * a.stride[d];
     }
+    const T* al = a.alpha + base;
 #pragma unroll
     for (int i = 0; i < (1 << D); ++i) {
-        i64 off = base;
+        int off = 0;
 #pragma unroll
         for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? a.stride[d] : 0;
-        s.am[i] = __ldg(a.alpha + off);
+        s.am[i] = __ldg(al + off);
     }
     // corner values -> monomial coefficients: per dimension (lo, hi) -> (lo, hi - lo)
 #pragma unroll
@@ -391,37 +394,49 @@ __device__ __forceinline__ bool lane_in_cell(const LaneState<T, D>& s, const T (
     return same;
 }
 
-// Slow path (one copy per kernel): the observation is not inside the cached cell.  Returns true when the
-// observation has been consumed here (outside the mesh: zero feature column, mu = 0, p = q = 0).
-// Cell search = arithmetic guess, then walk until t[c] < x <= t[c+1] (exact comparisons against the float32 knots,
-// same result as searchsorted(mesh, x, right=False) - 1 clamped to [0, K-2]).
+// Slow path: the observation is not inside the cached cell.  Returns true when the observation has been consumed
+// here (outside the mesh: zero feature column, mu = 0, p = q = 0).
+// Cell search: walk from the cached cell (cell-sorted or along-track data move to a neighbouring cell), falling back
+// to the arithmetic guess after 4 steps; the loop ends when t[c] < x <= t[c+1] (exact comparisons against the float32
+// knots, same result as searchsorted(mesh, x, right=False) - 1 clamped to [0, K-2]).
 template <typename T, int D>
 __device__ __forceinline__ bool lane_switch(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&x)[D], T y,
                                             const T* s_tab, const float* s_knots) {
+    bool all_in = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) all_in = all_in && (x[d] >= (T)a.mesh[d].tfirst) && (x[d] <= (T)a.mesh[d].tlast);
+    if (!all_in) {               // also catches NaN padding
+        s.accE += y * y;
+        return true;
+    }
     int c[D];
     T tl[D], th[D];
-    bool all_in = true, moved = !s.valid;
+    bool moved = !s.valid;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const float* t = s_knots + a.knot_off[d];
         const int K = a.mesh[d].K;
-        float gf = ((float)x[d] - a.mesh[d].t0) * a.mesh[d].inv_h;
-        gf = fminf(fmaxf(gf, 0.0f), (float)(K - 2));          // NaN -> 0
-        int cc = (int)gf;
-        T lo = (T)t[cc], hi = (T)t[cc + 1];
+        int cc;
+        T lo, hi;
+        if (s.valid) {
+            cc = s.c[d]; lo = s.tlo[d]; hi = s.thi[d];
+        } else {
+            cc = 0; lo = (T)t[0]; hi = (T)t[1];
+        }
+        int steps = 0;
 #pragma unroll 1
         while (true) {
-            if (cc > 0 && x[d] <= lo) { --cc; hi = lo; lo = (T)t[cc]; continue; }
-            if (cc < K - 2 && x[d] > hi) { ++cc; lo = hi; hi = (T)t[cc + 1]; continue; }
-            break;
+            if (cc > 0 && x[d] <= lo) { --cc; hi = lo; lo = (T)t[cc]; }
+            else if (cc < K - 2 && x[d] > hi) { ++cc; lo = hi; hi = (T)t[cc + 1]; }
+            else break;
+            if (++steps == 4) {          // far jump: restart from the arithmetic guess
+                float gf = ((float)x[d] - a.mesh[d].t0) * a.mesh[d].inv_h;
+                gf = fminf(fmaxf(gf, 0.0f), (float)(K - 2));
+                cc = (int)gf; lo = (T)t[cc]; hi = (T)t[cc + 1];
+            }
         }
         c[d] = cc; tl[d] = lo; th[d] = hi;
-        all_in = all_in && (x[d] >= (T)t[0]) && (x[d] <= (T)t[K - 1]);
         moved = moved || (cc != s.c[d]);
-    }
-    if (!all_in) {
-        s.accE += y * y;
-        return true;
     }
     if (moved) {
         lane_flush<T, D>(a, s);
@@ -565,11 +580,10 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
 #pragma unroll
         for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + base, xa[d]);
         load4<T>(a.yp + base, ya);
-        // software pipeline: the loads of the next group of 4 observations are in flight while this one is
-        // processed.  One copy of the group code (rotating the buffers costs 3 register moves per observation but
-        // keeps the loop inside the instruction cache).
+        // software pipeline over groups of 4 observations: while one buffer is processed the loads of the next
+        // group are in flight (two alternating register buffers, no copies)
 #pragma unroll 1
-        for (int gi = 0; gi < groups; ++gi) {
+        for (int gi = 0; gi < groups; gi += 2) {
             if (gi + 1 < groups) {
                 const i64 o = base + (i64)(gi + 1) * 128;
 #pragma unroll
@@ -577,12 +591,13 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
                 load4<T>(a.yp + o, yb);
             }
             lane_group<T, D>(a, s, xa, ya, s_tab, s_knots);
+            if (gi + 2 < groups) {
+                const i64 o = base + (i64)(gi + 2) * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) xa[d][j] = xb[d][j];
-                ya[j] = yb[j];
+                for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xa[d]);
+                load4<T>(a.yp + o, ya);
             }
+            if (gi + 1 < groups) lane_group<T, D>(a, s, xb, yb, s_tab, s_knots);
         }
         lane_flush<T, D>(a, s);
     }

@@ -15,7 +15,7 @@ namespace vggp {
 thread_local char g_err[512] = {0};
 unsigned long long g_launches = 0;
 static int g_use_mma = 1;
-static int g_b1_structured = 1;    // tridiagonal (twisted factorisation) inverse for the B1 family
+static int g_b1_structured = 2;    // B1 family: 0 dense, 1 twisted inverse + GEMMs, 2 + semiseparable products
 
 struct Phase {
     GemmDesc* d_descs = nullptr;
@@ -51,7 +51,10 @@ struct vggp_plan {
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
     std::vector<Phase> triinv;             // two launches per recursion depth, deepest first
-    Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp, dRp;
+    Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp, dRp, gramOnly, dPOnly;
+    std::vector<SsGroup> ss_fwd;           // structured == 2: R_d, the T_d chains, alpha
+    std::vector<SsGroup> ss_dm;            // (kron P) g, one group per mode
+    SsGroup ss_dL, ss_Y, ss_Z;
     std::vector<Phase> chains;             // D-1 launches building T_d = m x_{e != d} P_e
     double* dm_result;
     std::vector<void*> allocs;
@@ -173,6 +176,39 @@ GemmDesc gram_desc(const vggp_plan* p, int e, const double* ghat, const double* 
     sk = std::max(1, std::min(sk, max_sk));
     d.splitk = sk;
     return d;
+}
+
+// dst = src x_e P_e through the semiseparable generators of dimension `gdim` applied along mode e of a tensor with
+// the given mode sizes (the M-tensor, or an n x n matrix when dims2 is used)
+SsTask ss_task(const double* gen, int n, i64 outer, i64 inner, const double* src, double* dst) {
+    SsTask t;
+    t.src = src; t.dst = dst; t.gen = gen; t.n = n;
+    t.nseg = (n + SS_SEG - 1) / SS_SEG;
+    int pad = 1;
+    while (pad < t.nseg) pad <<= 1;
+    t.nseg_pad = pad;
+    t.inner = inner;
+    t.nfibres = outer * inner;
+    return t;
+}
+
+SsTask ss_mode_task(const vggp_plan* p, int e, const double* src, double* dst) {
+    i64 outer = 1, inner = 1;
+    for (int f = 0; f < e; ++f) outer *= p->n[f];
+    for (int f = e + 1; f < p->D; ++f) inner *= p->n[f];
+    return ss_task(p->g.gen[e], p->n[e], outer, inner, src, dst);
+}
+
+int launch_ss(const SsGroup& grp, cudaStream_t st) {
+    if (grp.ntasks == 0) return 0;
+    i64 gx = 1;
+    for (int i = 0; i < grp.ntasks; ++i) {
+        const int fpb = 256 / grp.t[i].nseg_pad;
+        gx = std::max<i64>(gx, (grp.t[i].nfibres + fpb - 1) / fpb);
+    }
+    k_ss_apply<<<dim3((unsigned)gx, grp.ntasks), 256, 0, st>>>(grp);
+    VGGP_LAUNCH_CHECK();
+    return 0;
 }
 
 void build_leaves(int lo, int hi, std::vector<int>& bounds) {
@@ -327,11 +363,72 @@ int build_schedules(vggp_plan* p) {
             dr.push_back(square_desc(n, g.X[d], false, g.R[d], false, g.dR[d], 1.0, 0.0));   // dense family: dR = 2 cQ sym(bQ) R
         }
         if ((rc = make_phase(p, dr, p->dRp))) return rc;
+        // structured == 2: the only GEMMs left are the Gram contractions and dP += dR Lt^T
+        std::vector<GemmDesc> go, po;
+        for (int d = 0; d < D; ++d) {
+            const int n = p->n[d];
+            go.push_back(gram_desc(p, d, p->ghat, p->Tm[d], g.dP[d], D));
+            GemmDesc x1 = square_desc(n, g.dR[d], false, g.Lt[d], true, g.dP[d], 1.0, 1.0);
+            x1.tri_b = 2;
+            po.push_back(x1);
+        }
+        if ((rc = make_phase(p, go, p->gramOnly))) return rc;
+        if ((rc = make_phase(p, po, p->dPOnly))) return rc;
         if ((rc = make_phase(p, A, p->bwdA))) return rc;
         if ((rc = make_phase(p, mid, p->bwdMid))) return rc;
         if ((rc = make_phase(p, B, p->bwdB))) return rc;
         if ((rc = make_phase(p, y, p->Yp))) return rc;
         if ((rc = make_phase(p, k, p->dKp))) return rc;
+    }
+    // ---- semiseparable product groups (B1 family, structured == 2) ----
+    if (g.structured == 2) {
+        if (2 * D > SS_MAX_TASKS) return fail(VGGP_E_DIM, "too many tasks for one semiseparable group");
+        SsGroup g0;
+        g0.ntasks = 0;
+        for (int d = 0; d < D; ++d)          // R_d = P_d Lt_d : mode 0 of an n x n matrix
+            g0.t[g0.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.Lt[d], g.R[d]);
+        for (int s = 0; s + 1 < D; ++s) {
+            SsGroup gs;
+            gs.ntasks = 0;
+            for (int d = 0; d < D; ++d) {
+                int e = s;
+                if (e >= d) e += 1;
+                const bool first = (s == 0), last = (s == D - 2);
+                const double* src = first ? p->mws : p->tmpM[d];
+                double* dst = last ? p->Tm[d] : p->tmpM[d];
+                gs.t[gs.ntasks++] = ss_mode_task(p, e, src, dst);
+            }
+            if (s == 0) {                    // first chain step shares the launch with the R_d products
+                for (int i = 0; i < gs.ntasks; ++i) g0.t[g0.ntasks++] = gs.t[i];
+            } else {
+                if (p->ss_fwd.empty()) p->ss_fwd.push_back(g0);
+                p->ss_fwd.push_back(gs);
+            }
+        }
+        if (p->ss_fwd.empty()) p->ss_fwd.push_back(g0);
+        SsGroup ga;
+        ga.ntasks = 1;
+        ga.t[0] = ss_mode_task(p, D - 1, p->Tm[D - 1], p->alpha);
+        p->ss_fwd.push_back(ga);
+        // reverse: (kron P) g mode by mode; the last mode shares its launch with dLraw_d = P_d dR_d
+        const double* src = p->gM;
+        for (int e = 0; e < D; ++e) {
+            double* dst = (e % 2 == 0) ? p->pgA : p->pgB;
+            SsGroup gd;
+            gd.ntasks = 1;
+            gd.t[0] = ss_mode_task(p, e, src, dst);
+            if (e == D - 1)
+                for (int d = 0; d < D; ++d) gd.t[gd.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.dR[d], g.dLraw[d]);
+            p->ss_dm.push_back(gd);
+            src = dst;
+            p->dm_result = dst;
+        }
+        p->ss_Y.ntasks = 0;
+        p->ss_Z.ntasks = 0;
+        for (int d = 0; d < D; ++d) {
+            p->ss_Y.t[p->ss_Y.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.X[d], g.Y[d]);      // Y = P X
+            p->ss_Z.t[p->ss_Z.ntasks++] = ss_task(g.gen[d], p->n[d], p->n[d], 1, g.Y[d], g.dK[d]);     // Z = Y P
+        }
     }
     return 0;
 }
@@ -372,7 +469,7 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
     for (int d = 0; d < D; ++d) {
         a.xp[d] = reinterpret_cast<const T*>(xp[d]);
         a.mesh[d] = p->mesh[d];
-        a.stride[d] = p->stride[d];
+        a.stride[d] = (int)p->stride[d];
         a.band_off[d] = p->band_off[d];
         a.tab_off[d] = p->tab_off[d];
         a.knot_off[d] = p->knot_off[d];
@@ -528,7 +625,7 @@ int vggp_set_gemm_mode(int use_mma) {
 }
 
 int vggp_set_b1_structured(int on) {
-    g_b1_structured = on ? 1 : 0;
+    g_b1_structured = on < 0 ? 0 : (on > 2 ? 2 : on);
     return 0;
 }
 
@@ -544,6 +641,11 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         for (int k = 1; k < n_knots[d]; ++k)
             if (!(knots_host[d][k] > knots_host[d][k - 1])) return fail(VGGP_E_ARG, "knots must be strictly increasing");
     }
+    {
+        double Mchk = 1.0;
+        for (int d = 0; d < D; ++d) Mchk *= (double)n_knots[d];
+        if (Mchk >= 2147483647.0) return fail(VGGP_E_ARG, "M = prod M_d must be below 2^31");
+    }
     VGGP_CUDA(cudaSetDevice(device));
     vggp_plan* p = new (std::nothrow) vggp_plan();
     if (!p) return fail(VGGP_E_NOMEM, "out of host memory");
@@ -553,7 +655,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     GridDims& g = p->g;
     memset(&g, 0, sizeof(g));
     g.D = D; g.family = family; g.obs_dtype = obs_dtype;
-    g.structured = (family == VGGP_B1_ASVGP && g_b1_structured) ? 1 : 0;
+    g.structured = (family == VGGP_B1_ASVGP) ? g_b1_structured : 0;
     int boff = 0, koff = 0, toff = 0;
     i64 foff = 0;
     for (int d = 0; d < D; ++d) {
@@ -594,6 +696,8 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         mv.t = p->d_knots[d]; mv.K = K; mv.t0 = knots_host[d][0];
         mv.inv_h = (float)((double)(K - 1) / ((double)knots_host[d][K - 1] - (double)knots_host[d][0]));
         mv.nearly_uniform = 1;
+        mv.tfirst = knots_host[d][0];
+        mv.tlast = knots_host[d][K - 1];
         for (int k = 0; k < K; ++k) {
             const float gf = (knots_host[d][k] - mv.t0) * mv.inv_h;
             if (fabsf(gf - (float)k) > 1.25f) mv.nearly_uniform = 0;
@@ -605,6 +709,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         TRY(dev_alloc(p, &g.dR[d], nn)); TRY(dev_alloc(p, &g.X[d], nn)); TRY(dev_alloc(p, &g.Y[d], nn));
         TRY(dev_alloc(p, &g.dK[d], nn)); TRY(dev_alloc(p, &g.dLraw[d], nn)); TRY(dev_alloc(p, &g.tmp[d], nn));
         TRY(dev_alloc(p, &g.Qb[d], 2 * (i64)p->n[d]));
+        TRY(dev_alloc(p, &g.gen[d], 5 * (i64)p->n[d] + 2 * (((i64)p->n[d] + SS_SEG - 1) / SS_SEG) + 8));
         std::vector<int> bounds;
         build_leaves(0, p->n[d], bounds);
         bounds.push_back(p->n[d]);
@@ -742,7 +847,11 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
         for (auto& ph : p->triinv) if ((rc = launch_phase(ph, st))) return rc;
         if ((rc = launch_phase(p->pinv, st))) return rc;
     }
-    if ((rc = launch_phase(p->rs, st))) return rc;
+    if (p->g.structured == 2) {
+        if ((rc = launch_ss(p->ss_fwd[0], st))) return rc;      // R_d (and the first step of the T_d chains)
+    } else {
+        if ((rc = launch_phase(p->rs, st))) return rc;
+    }
     if (!p->g.structured) {
         if ((rc = launch_phase(p->qq, st))) return rc;
     }
@@ -759,8 +868,12 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
         }
         VGGP_LAUNCH_CHECK();
     }
-    for (auto& ph : p->chains) if ((rc = launch_phase(ph, st))) return rc;
-    if ((rc = launch_phase(p->alpha_phase, st))) return rc;
+    if (p->g.structured == 2) {
+        for (size_t i = 1; i < p->ss_fwd.size(); ++i) if ((rc = launch_ss(p->ss_fwd[i], st))) return rc;
+    } else {
+        for (auto& ph : p->chains) if ((rc = launch_phase(ph, st))) return rc;
+        if ((rc = launch_phase(p->alpha_phase, st))) return rc;
+    }
     const int cblocks = (int)std::min<i64>((p->M + 255) / 256, 148 * 4);
     if (p->obs_dtype == VGGP_F32)
         k_cast_alpha<float><<<cblocks, 256, 0, st>>>(p->alpha, p->mws, reinterpret_cast<float*>(p->alphaT), p->M, p->g.sc);
@@ -856,10 +969,17 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     VGGP_LAUNCH_CHECK();
     for (int d = 0; d < D; ++d)
         VGGP_CUDA(cudaMemsetAsync(p->g.dP[d], 0, sizeof(double) * (size_t)p->n[d] * p->n[d], st));
-    if ((rc = launch_phase(p->bwdA, st))) return rc;
-    if ((rc = launch_phase(p->bwdMid, st))) return rc;
+    const bool ss = (p->g.structured == 2);
     const i64 nn = (i64)p->nmax * p->nmax;
     dim3 egrid(ceil_div(nn, 256), D);
+    if (ss) {
+        // B1 family, semiseparable products: (kron P) g mode by mode, Gram contractions on the tensor cores
+        for (int e = 0; e + 1 < D; ++e) if ((rc = launch_ss(p->ss_dm[e], st))) return rc;
+        if ((rc = launch_phase(p->gramOnly, st))) return rc;
+    } else {
+        if ((rc = launch_phase(p->bwdA, st))) return rc;
+        if ((rc = launch_phase(p->bwdMid, st))) return rc;
+    }
     if (p->family == VGGP_B1_ASVGP) {
         if (p->obs_dtype == VGGP_F32)
             k_bwd_dP_dR<float><<<egrid, 256, 0, st>>>(p->g, reinterpret_cast<const float*>(gbuf) + p->M, theta, ell_scale);
@@ -874,14 +994,24 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
         VGGP_LAUNCH_CHECK();
         if ((rc = launch_phase(p->dRp, st))) return rc;
     }
-    if ((rc = launch_phase(p->bwdB, st))) return rc;
+    if (ss) {
+        if ((rc = launch_ss(p->ss_dm[D - 1], st))) return rc;       // last mode of (kron P) g  +  dLraw_d = P_d dR_d
+        if ((rc = launch_phase(p->dPOnly, st))) return rc;          // dP_d += dR_d Lt_d^T
+    } else {
+        if ((rc = launch_phase(p->bwdB, st))) return rc;
+    }
     k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
     VGGP_LAUNCH_CHECK();
     k_sym<<<egrid, 256, 0, st>>>(p->g);
     VGGP_LAUNCH_CHECK();
-    if ((rc = launch_phase(p->Yp, st))) return rc;
-    if (!p->g.structured) {
-        if ((rc = launch_phase(p->dKp, st))) return rc;
+    if (ss) {
+        if ((rc = launch_ss(p->ss_Y, st))) return rc;               // Y_d = P_d sym(dP_d)
+        if ((rc = launch_ss(p->ss_Z, st))) return rc;               // Z_d = Y_d P_d (its band is -dK_d's GEMM part)
+    } else {
+        if ((rc = launch_phase(p->Yp, st))) return rc;
+        if (!p->g.structured) {
+            if ((rc = launch_phase(p->dKp, st))) return rc;
+        }
     }
     k_bwd_dL<<<egrid, 256, 0, st>>>(p->g, dL);
     VGGP_LAUNCH_CHECK();
