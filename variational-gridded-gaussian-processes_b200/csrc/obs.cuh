@@ -278,6 +278,7 @@ struct PackedArgs {
     T* gband;
     double* gs;
     double n_real;
+    unsigned int* counter;   // work-stealing counter over warp chunks (zeroed before the launch)
 };
 
 template <typename T>
@@ -503,34 +504,19 @@ __device__ __forceinline__ void lane_math(LaneState<T, D>& s, const T (&x)[D], T
     }
 }
 
-// One group of 4 consecutive observations of this lane's run.  The 4 fast-path copies are straight-line code; the
-// single slow-path copy is entered by breaking out of the switch and re-entering it at the same position.
+// One group of 4 consecutive observations of this lane's run: per observation an exact cell-membership check, the
+// (rare, divergent) cell switch, then the straight-line arithmetic with all lanes reconverged.
 template <typename T, int D>
 __device__ __forceinline__ void lane_group(const PackedArgs<T, D>& a, LaneState<T, D>& s, const T (&xg)[D][4],
                                            const T (&yg)[4], const T* s_tab, const float* s_knots) {
-    int j = 0;
-    for (;;) {
-        switch (j) {
-#define VGGP_OBS_CASE(J)                                                     \
-    case J: {                                                                \
-        T xx[D];                                                             \
-        _Pragma("unroll") for (int d = 0; d < D; ++d) xx[d] = xg[d][J];      \
-        if (!lane_in_cell<T, D>(s, xx)) { j = J; break; }                    \
-        lane_math<T, D>(s, xx, yg[J]);                                       \
-    }
-            VGGP_OBS_CASE(0)
-            VGGP_OBS_CASE(1)
-            VGGP_OBS_CASE(2)
-            VGGP_OBS_CASE(3)
-#undef VGGP_OBS_CASE
-            j = 4;
-        }
-        if (j >= 4) break;
-        T xx[D];
-        T yy = (j == 0) ? yg[0] : (j == 1) ? yg[1] : (j == 2) ? yg[2] : yg[3];
 #pragma unroll
-        for (int d = 0; d < D; ++d) xx[d] = (j == 0) ? xg[d][0] : (j == 1) ? xg[d][1] : (j == 2) ? xg[d][2] : xg[d][3];
-        if (lane_switch<T, D>(a, s, xx, yy, s_tab, s_knots)) ++j;
+    for (int j = 0; j < 4; ++j) {
+        T xx[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xx[d] = xg[d][j];
+        bool consumed = false;
+        if (!lane_in_cell<T, D>(s, xx)) consumed = lane_switch<T, D>(a, s, xx, yg[j], s_tab, s_knots);
+        if (!consumed) lane_math<T, D>(s, xx, yg[j]);
     }
 }
 
@@ -556,7 +542,6 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
     }
     mbar_wait(&bar, 0);
 
-    const i64 warp = (i64)blockIdx.x * (OBS_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     LaneState<T, D> s;
     s.valid = false;
@@ -573,17 +558,23 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
 #pragma unroll
     for (int i = 0; i < (1 << D); ++i) { s.gm[i] = (T)0; s.am[i] = (T)0; }
 
-    if (warp < a.geo.nwarps) {
-        const i64 base = warp * (i64)32 * a.geo.R + lane * 4;
-        const int groups = a.geo.R >> 2;
+    // persistent warps: every warp takes the next chunk (32 lanes x R observations) from a global counter, so the
+    // data-dependent cost of the cell switches balances over the SMs
+    const int groups = a.geo.R >> 2;
+    for (;;) {
+        unsigned int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(a.counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((i64)chunk >= a.geo.nwarps) break;
+        const i64 base = (i64)chunk * 32 * a.geo.R + lane * 4;
         T xa[D][4], ya[4], xb[D][4], yb[4];
 #pragma unroll
         for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + base, xa[d]);
         load4<T>(a.yp + base, ya);
-        // software pipeline over groups of 4 observations: while one buffer is processed the loads of the next
-        // group are in flight (two alternating register buffers, no copies)
+        // software pipeline over groups of 4 observations: the loads of the next group are in flight while this one
+        // is processed (one copy of the group code; rotating the buffers costs 3 register moves per observation)
 #pragma unroll 1
-        for (int gi = 0; gi < groups; gi += 2) {
+        for (int gi = 0; gi < groups; ++gi) {
             if (gi + 1 < groups) {
                 const i64 o = base + (i64)(gi + 1) * 128;
 #pragma unroll
@@ -591,15 +582,17 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b
                 load4<T>(a.yp + o, yb);
             }
             lane_group<T, D>(a, s, xa, ya, s_tab, s_knots);
-            if (gi + 2 < groups) {
-                const i64 o = base + (i64)(gi + 2) * 128;
 #pragma unroll
-                for (int d = 0; d < D; ++d) load4<T>(a.xp[d] + o, xa[d]);
-                load4<T>(a.yp + o, ya);
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) xa[d][j] = xb[d][j];
+                ya[j] = yb[j];
             }
-            if (gi + 1 < groups) lane_group<T, D>(a, s, xb, yb, s_tab, s_knots);
         }
         lane_flush<T, D>(a, s);
+        s.valid = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { s.tlo_chk[d] = (T)INFINITY; s.thi[d] = -(T)INFINITY; s.c[d] = -1; }
     }
     const double e = block_sum((double)s.accE, red);
     if (threadIdx.x == 0) {

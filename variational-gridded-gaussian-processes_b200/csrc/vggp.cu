@@ -39,6 +39,7 @@ struct vggp_plan {
     double *mws, *alpha, *Tm[VGGP_MAX_D], *tmpM[VGGP_MAX_D], *gM, *ghat, *pgA, *pgB;
     void* alphaT;
     double* theta_dev;                     // copy of theta of the last forward (the B0 features depend on it)
+    unsigned int* obs_counter;             // work-stealing counter of the per-observation kernel
     int band_off[VGGP_MAX_D], band_total, knot_off[VGGP_MAX_D], knot_total;
     int tab_off[VGGP_MAX_D], tab_total;
     i64 gfac_off[VGGP_MAX_D], gfac_total;   // B0 family: full factor-gradient blocks [bP | bQ] per dim
@@ -439,6 +440,7 @@ PackGeom pack_geometry(const vggp_plan* p, i64 n) {
     i64 R = (n + target_lanes - 1) / target_lanes;
     R = (R + 3) / 4 * 4;
     if (R < 16) R = 16;
+    if (R > 512) R = 512;        // chunks of 32 x 512 observations are handed out dynamically to persistent warps
     const i64 lanes = (n + R - 1) / R;
     g.R = (int)R;
     g.nwarps = (lanes + 31) / 32;
@@ -486,7 +488,10 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
     a.n_real = (double)n;
-    const i64 blocks = (a.geo.nwarps + (OBS_THREADS / 32) - 1) / (OBS_THREADS / 32);
+    a.counter = p->obs_counter;
+    VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
+    i64 blocks = (a.geo.nwarps + (OBS_THREADS / 32) - 1) / (OBS_THREADS / 32);
+    blocks = std::min<i64>(blocks, (i64)p->sm_count * p->obs_blocks_per_sm);
     k_obs_b1<T, D><<<(unsigned)blocks, OBS_THREADS, obs_smem_bytes<T, D>(p), st>>>(a);
     VGGP_LAUNCH_CHECK();
     return 0;
@@ -752,6 +757,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->alphaT = a;
     }
     TRY(dev_alloc(p, &p->theta_dev, 2 * VGGP_MAX_D + 1));
+    TRY(dev_alloc(p, &p->obs_counter, 4));
     TRY(dev_alloc(p, &p->mws, p->M)); TRY(dev_alloc(p, &p->alpha, p->M));
     TRY(dev_alloc(p, &p->gM, p->M)); TRY(dev_alloc(p, &p->ghat, p->M));
     TRY(dev_alloc(p, &p->pgA, p->M)); TRY(dev_alloc(p, &p->pgB, p->M));
