@@ -251,17 +251,17 @@ __global__ void __launch_bounds__(NB) k_triinv_leaf(const __grid_constant__ Grid
 // Structured inverse of the tridiagonal B1/ASVGP factor K_d (diag a_i, off-diagonal b_i): twisted factorisation
 //   d_0 = a_0, d_k = a_k - b_{k-1}^2 / d_{k-1}   (top-down pivots; log det K = sum log d_k)
 //   e_{n-1} = a_{n-1}, e_k = a_k - b_k^2 / e_{k+1} (bottom-up pivots)
-//   P[j][j] = 1 / (d_j + e_j - a_j)
-//   P[i][j] = P[j][j] prod_{k=i}^{j-1} (-b_k / d_k)  (i < j),   P[i][j] = P[j][j] prod_{k=j+1}^{i} (-b_{k-1} / e_k)  (i > j)
-// O(n^2) work, two O(n) sequential recurrences (run redundantly by every CTA, in two different warps).
-// grid (ceil(n / 256), D), 256 threads, dynamic smem 7 n doubles.
+//   P[j][j] = pd_j = 1 / (d_j + e_j - a_j)
+//   P[i][j] = pd_j prod_{k=i}^{j-1} ru_k (i < j), ru_k = -b_k / d_k ;  P[i][j] = pd_j prod_{k=j}^{i-1} rl_k (i > j), rl_k = -b_k / e_{k+1}
+// k_b1_factor: the two O(n) recurrences (two warps of one CTA per dimension) and the generator tables used by the
+// semiseparable products.
+// grid (D), 256 threads, dynamic smem 7 n doubles.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ GridDims g, const double* __restrict__ theta) {
+__global__ void __launch_bounds__(256) k_b1_factor(const __grid_constant__ GridDims g, const double* __restrict__ theta) {
     extern __shared__ double sm[];
     __shared__ double red[32];
-    const int d = blockIdx.y;
+    const int d = blockIdx.x;
     const int n = g.n[d];
-    if ((int)blockIdx.x * 256 >= n) return;
     double* a = sm;
     double* b = a + n;
     double* dd = b + n;
@@ -275,24 +275,40 @@ __global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ Grid
         b[i] = (i + 1 < n) ? factor_entry(g, theta, d, i, i + 1) : 0.0;
     }
     __syncthreads();
+    // The pivots change very slowly along the Toeplitz interior (contraction factor close to 1), so the reciprocal
+    // of the previous pivot is an excellent Newton seed: 1/d_k costs one Newton step (two dependent FMAs) plus a
+    // residual check, instead of a ~100-cycle float64 division on the serial critical path; whenever the residual
+    // is not at rounding level (first rows, last row) the exact division is used.
     if (tid == 0) {
         double prev = a[0];
         dd[0] = prev;
+        double r = 1.0 / prev;
         bool bad = !(prev > 0.0);
         for (int k = 1; k < n; ++k) {
             const double bk = b[k - 1];
-            prev = a[k] - bk * bk / prev;
-            dd[k] = prev;
-            bad = bad || !(prev > 0.0);
+            const double nxt = fma(-bk * bk, r, a[k]);
+            dd[k] = nxt;
+            bad = bad || !(nxt > 0.0);
+            double e = fma(-nxt, r, 1.0);
+            double rn = fma(r, e, r);
+            e = fma(-nxt, rn, 1.0);
+            if (!(fabs(e) < 3e-16)) rn = 1.0 / nxt;
+            r = rn;
         }
         if (bad) atomicMax(g.info, d + 1);
     } else if (tid == 32) {
         double nxt = a[n - 1];
         ee[n - 1] = nxt;
+        double r = 1.0 / nxt;
         for (int k = n - 2; k >= 0; --k) {
             const double bk = b[k];
-            nxt = a[k] - bk * bk / nxt;
-            ee[k] = nxt;
+            const double cur = fma(-bk * bk, r, a[k]);
+            ee[k] = cur;
+            double e = fma(-cur, r, 1.0);
+            double rn = fma(r, e, r);
+            e = fma(-cur, rn, 1.0);
+            if (!(fabs(e) < 3e-16)) rn = 1.0 / cur;
+            r = rn;
         }
     }
     __syncthreads();
@@ -304,39 +320,54 @@ __global__ void __launch_bounds__(256) k_b1_inverse(const __grid_constant__ Grid
         ld += log(dd[i]);
     }
     ld = block_sum(ld, red);
-    if (blockIdx.x == 0 && tid == 0) g.sc[SC_LOGDETK + d] = ld;
+    if (tid == 0) g.sc[SC_LOGDETK + d] = ld;
     __syncthreads();
-    if (blockIdx.x == 0) {
-        // generators for the semiseparable products (k_ss_apply): segment-local decay products
-        //   gl[i] = prod_{k=a}^{i-1} rl[k],  gu[i] = prod_{k=i}^{b-2} ru[k]   for i in segment [a, b)
-        //   glend[s] = prod_{k=a}^{b-1} rl[k],  guend[s] = ru[a-1] * gu[a]
-        double* gen = g.gen[d];
-        const int nseg = (n + SS_SEG - 1) / SS_SEG;
-        for (int i = tid; i < n; i += 256) { gen[i] = pd[i]; gen[n + i] = ru[i]; gen[2 * n + i] = rl[i]; }
-        for (int sgi = tid; sgi < nseg; sgi += 256) {
-            const int a0 = sgi * SS_SEG, b0 = min(n, a0 + SS_SEG);
-            double pl = 1.0;
-            for (int i = a0; i < b0; ++i) { gen[3 * n + i] = pl; pl *= rl[i]; }
-            gen[5 * n + sgi] = pl;
-            double pu = 1.0;
-            for (int i = b0 - 1; i >= a0; --i) { gen[4 * n + i] = pu; if (i > a0) pu *= ru[i - 1]; }
-            gen[5 * n + nseg + sgi] = (a0 > 0) ? ru[a0 - 1] * pu : 0.0;
-        }
+    // generators for the semiseparable products (k_ss_apply): segment-local decay products
+    //   gl[i] = prod_{k=a}^{i-1} rl[k],  gu[i] = prod_{k=i}^{b-2} ru[k]   for i in segment [a, b)
+    //   glend[s] = prod_{k=a}^{b-1} rl[k],  guend[s] = ru[a-1] * gu[a]
+    double* gen = g.gen[d];
+    const int nseg = (n + SS_SEG - 1) / SS_SEG;
+    for (int i = tid; i < n; i += 256) { gen[i] = pd[i]; gen[n + i] = ru[i]; gen[2 * n + i] = rl[i]; }
+    for (int sgi = tid; sgi < nseg; sgi += 256) {
+        const int a0 = sgi * SS_SEG, b0 = min(n, a0 + SS_SEG);
+        double pl = 1.0;
+        for (int i = a0; i < b0; ++i) { gen[3 * n + i] = pl; pl *= rl[i]; }
+        gen[5 * n + sgi] = pl;
+        double pu = 1.0;
+        for (int i = b0 - 1; i >= a0; --i) { gen[4 * n + i] = pu; if (i > a0) pu *= ru[i - 1]; }
+        gen[5 * n + nseg + sgi] = (a0 > 0) ? ru[a0 - 1] * pu : 0.0;
     }
-    const int j = (int)blockIdx.x * 256 + tid;
+}
+
+// Explicit P_d from the generators (O(n^2)): needed by the GEMM product path (structured == 1) and by
+// vggp_workspace_ptr; the semiseparable path (structured == 2) never materialises P_d in a step.
+// grid (ceil(nmax / 256), D), 256 threads
+__global__ void __launch_bounds__(256) k_b1_fill_P(const __grid_constant__ GridDims g) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const int j = (int)blockIdx.x * 256 + threadIdx.x;
     if (j >= n) return;
+    const double* __restrict__ gen = g.gen[d];
     double* __restrict__ P = g.P[d];
-    double p = pd[j];
+    const double pj = gen[j];
+    double p = pj;
     P[(i64)j * n + j] = p;
     for (int i = j - 1; i >= 0; --i) {
-        p *= ru[i];
+        p *= gen[n + i];
         P[(i64)i * n + j] = p;
     }
-    p = pd[j];
+    p = pj;
     for (int i = j + 1; i < n; ++i) {
-        p *= rl[i - 1];
+        p *= gen[2 * n + i - 1];
         P[(i64)i * n + j] = p;
     }
+}
+
+// P_d[i][j] for |i - j| <= 1 from the generators
+__device__ __forceinline__ double b1_P_band(const double* __restrict__ gen, int n, int i, int j) {
+    if (i == j) return gen[i];
+    if (j == i + 1) return gen[j] * gen[n + i];
+    return gen[j] * gen[2 * n + j];          // j == i - 1
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -366,7 +397,8 @@ struct SsGroup {
 };
 
 __global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGroup grp) {
-    __shared__ double sL[256], sU[256], sLin[256], sUin[256];
+    extern __shared__ double sgen[];          // generators of this task's dimension: [pd | ru | rl | gl | gu], 5 n
+    __shared__ double sL[256], sU[256], sLin[256], sUin[256], sGl[256], sGu[256];
     const SsTask& tk = grp.t[blockIdx.y];
     const int fpb = 256 / tk.nseg_pad;                      // fibres per block
     const int tid = threadIdx.x;
@@ -377,6 +409,11 @@ __global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGrou
     const int n = tk.n;
     const int a0 = sg * SS_SEG;
     const double* __restrict__ gen = tk.gen;
+    for (int i = tid; i < 5 * n; i += 256) sgen[i] = gen[i];
+    if (tid < tk.nseg) {                 // segment carry factors, read by the serial chain below
+        sGl[tid] = gen[5 * n + tid];
+        sGu[tid] = gen[5 * n + tk.nseg + tid];
+    }
     double sv[SS_SEG], yv[SS_SEG];
     i64 base = 0;
     if (live) {
@@ -385,14 +422,25 @@ __global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGrou
 #pragma unroll
         for (int j = 0; j < SS_SEG; ++j) {
             const int i = a0 + j;
-            sv[j] = (i < n) ? gen[i] * tk.src[base + (i64)i * tk.inner] : 0.0;
+            sv[j] = (i < n) ? tk.src[base + (i64)i * tk.inner] : 0.0;
         }
+    }
+    __syncthreads();
+    if (live) {
+        const double* pd = sgen;
+        const double* ru = sgen + n;
+        const double* rl = sgen + 2 * n;
         double l = 0.0;
 #pragma unroll
         for (int j = 0; j < SS_SEG; ++j) {
             const int i = a0 + j;
-            yv[j] = sv[j] + l;
-            l = (i < n) ? gen[2 * n + i] * (sv[j] + l) : l;
+            if (i < n) {
+                sv[j] *= pd[i];
+                yv[j] = sv[j] + l;
+                l = rl[i] * (sv[j] + l);
+            } else {
+                yv[j] = 0.0;
+            }
         }
         double u = 0.0;
 #pragma unroll
@@ -400,7 +448,7 @@ __global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGrou
             const int i = a0 + j;
             if (i < n) {
                 yv[j] += u;
-                u = (i > 0) ? gen[n + i - 1] * (sv[j] + u) : 0.0;
+                u = (i > 0) ? ru[i - 1] * (sv[j] + u) : 0.0;
             }
         }
         sL[tid] = l;
@@ -412,21 +460,23 @@ __global__ void __launch_bounds__(256) k_ss_apply(const __grid_constant__ SsGrou
         double c = 0.0;
         for (int s2 = 0; s2 < tk.nseg; ++s2) {
             sLin[s2 * fpb + fl] = c;
-            c = sL[s2 * fpb + fl] + c * gen[5 * n + s2];
+            c = sL[s2 * fpb + fl] + c * sGl[s2];
         }
         c = 0.0;
         for (int s2 = tk.nseg - 1; s2 >= 0; --s2) {
             sUin[s2 * fpb + fl] = c;
-            c = sU[s2 * fpb + fl] + c * gen[5 * n + tk.nseg + s2];
+            c = sU[s2 * fpb + fl] + c * sGu[s2];
         }
     }
     __syncthreads();
     if (live) {
         const double lin = sLin[tid], uin = sUin[tid];
+        const double* gl = sgen + 3 * n;
+        const double* gu = sgen + 4 * n;
 #pragma unroll
         for (int j = 0; j < SS_SEG; ++j) {
             const int i = a0 + j;
-            if (i < n) tk.dst[base + (i64)i * tk.inner] = yv[j] + lin * gen[3 * n + i] + uin * gen[4 * n + i];
+            if (i < n) tk.dst[base + (i64)i * tk.inner] = yv[j] + lin * gl[i] + uin * gu[i];
         }
     }
 }
@@ -468,8 +518,17 @@ __global__ void __launch_bounds__(256) k_fwd_reduce(const __grid_constant__ Grid
         // per-cell tables, monomial basis in the hat weight a (w_lo = 1 - a):
         //   p(a) = A (1-a)^2 + 2 B (1-a) a + C a^2 = pe0 + pe1 a + pe2 a^2, A = P[c][c], B = P[c][c+1], C = P[c+1][c+1]
         T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];       // [pe0 | pe1 | pe2 | qe0 | qe1 | qe2 | h | rh]
-        const double A = P[(i64)i * n + i], B2 = last ? 0.0 : 2.0 * P[(i64)i * n + i + 1],
-                     C = last ? 0.0 : P[(i64)(i + 1) * n + i + 1];
+        double A, B2, C;
+        if (g.structured == 2) {
+            const double* gen = g.gen[d];
+            A = b1_P_band(gen, n, i, i);
+            B2 = last ? 0.0 : 2.0 * b1_P_band(gen, n, i, i + 1);
+            C = last ? 0.0 : b1_P_band(gen, n, i + 1, i + 1);
+        } else {
+            A = P[(i64)i * n + i];
+            B2 = last ? 0.0 : 2.0 * P[(i64)i * n + i + 1];
+            C = last ? 0.0 : P[(i64)(i + 1) * n + i + 1];
+        }
         tab[i] = (T)A; tab[n + i] = (T)(B2 - 2.0 * A); tab[2 * n + i] = (T)(A - B2 + C);
         atomicAdd(g.sc + SC_TR + d, tr);
         atomicAdd(g.sc + SC_LOGDETS + d, 2.0 * log(fabs(Li[i])));
@@ -646,7 +705,8 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
             }
             if (lane == 0) {
                 const double q = (i == j) ? g.Qb[d][i] : g.Qb[d][n + (i < j ? i : j)];
-                const double v = -acc + half_c * q - half_ratio * P[(i64)i * n + j];
+                const double pij = (g.structured == 2) ? b1_P_band(g.gen[d], n, i, j) : P[(i64)i * n + j];
+                const double v = -acc + half_c * q - half_ratio * pij;
                 double a, b;
                 factor_entry_grad(g, theta, d, i, j, a, b);
                 sl += v * a;

@@ -520,10 +520,10 @@ __device__ __forceinline__ void lane_group(const PackedArgs<T, D>& a, LaneState<
     }
 }
 
-constexpr int OBS_THREADS = 256;
+constexpr int OBS_THREADS = 128;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? 2 : 1)) k_obs_b1(const __grid_constant__ PackedArgs<T, D> a) {
+__global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 5) : (D == 1 ? 4 : 2))) k_obs_b1(const __grid_constant__ PackedArgs<T, D> a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     // [cell tables (T) | knots (float)], staged by one TMA bulk copy
     const T* s_tab = reinterpret_cast<const T*>(smraw);

@@ -203,11 +203,13 @@ SsTask ss_mode_task(const vggp_plan* p, int e, const double* src, double* dst) {
 int launch_ss(const SsGroup& grp, cudaStream_t st) {
     if (grp.ntasks == 0) return 0;
     i64 gx = 1;
+    int nmax = 1;
     for (int i = 0; i < grp.ntasks; ++i) {
         const int fpb = 256 / grp.t[i].nseg_pad;
         gx = std::max<i64>(gx, (grp.t[i].nfibres + fpb - 1) / fpb);
+        nmax = std::max(nmax, grp.t[i].n);
     }
-    k_ss_apply<<<dim3((unsigned)gx, grp.ntasks), 256, 0, st>>>(grp);
+    k_ss_apply<<<dim3((unsigned)gx, grp.ntasks), 256, 5 * (size_t)nmax * sizeof(double), st>>>(grp);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -774,9 +776,11 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->obs_blocks_per_sm = 1;
         if (family == VGGP_B1_ASVGP) TRY(obs_prepare_dispatch(p));
     }
-    if (!rc) rc = (int)cudaFuncSetAttribute(k_b1_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_b1_factor, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(7 * (size_t)p->nmax * sizeof(double)));
-    if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_inverse) failed"); }
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_ss_apply, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(5 * (size_t)p->nmax * sizeof(double)));
+    if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_factor / k_ss_apply) failed"); }
     rc = (int)cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(2 * NB * (NB + 1) * sizeof(double)));
     if (!rc) rc = (int)cudaFuncSetAttribute(k_triinv_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -835,8 +839,12 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
     VGGP_LAUNCH_CHECK();
     if (p->g.structured) {
         // B1 family: tridiagonal factor -> twisted-factorisation inverse, O(n^2)
-        k_b1_inverse<<<dim3(ceil_div(p->nmax, 256), D), 256, 7 * (size_t)p->nmax * sizeof(double), st>>>(p->g, theta);
+        k_b1_factor<<<D, 256, 7 * (size_t)p->nmax * sizeof(double), st>>>(p->g, theta);
         VGGP_LAUNCH_CHECK();
+        if (p->g.structured == 1) {       // GEMM product path needs the explicit inverse
+            k_b1_fill_P<<<dim3(ceil_div(p->nmax, 256), D), 256, 0, st>>>(p->g);
+            VGGP_LAUNCH_CHECK();
+        }
     } else {
         const size_t csm = 2 * NB * (NB + 1) * sizeof(double);
         for (int j = 0; j < p->n_panels; ++j) {
@@ -1135,7 +1143,13 @@ int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int
     const i64 nn = (which == VGGP_WS_ALPHA || which == VGGP_WS_SCAL) ? 0 : (i64)p->n[dim] * p->n[dim];
     switch (which) {
         case VGGP_WS_K: *ptr = p->g.Kc[dim]; if (n_elems) *n_elems = nn; return 0;
-        case VGGP_WS_P: *ptr = p->g.P[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_P:
+            if (p->g.structured == 2) {      // not materialised in a step: fill it now (synchronous, debugging / tests only)
+                k_b1_fill_P<<<dim3(ceil_div(p->nmax, 256), p->D), 256>>>(p->g);
+                VGGP_LAUNCH_CHECK();
+                VGGP_CUDA(cudaDeviceSynchronize());
+            }
+            *ptr = p->g.P[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_R: *ptr = p->g.R[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_Q: *ptr = p->g.Q[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_S: return fail(VGGP_E_UNSUPPORTED, "S_d is no longer materialised");
