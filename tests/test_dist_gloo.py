@@ -164,3 +164,44 @@ def test_shard_bounds_partition(n, world):
     assert prev == n and max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         vdist.shard_bounds(n, world, world)
+
+
+def _reshard_worker(rank, world, port, out_dir):
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    vdist = importlib.import_module("variational-gridded-gaussian-processes_b200.dist")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        n = 500 + 37 * rank
+        n_keys = 48
+        keys = torch.randint(0, n_keys + 1, (n,), generator=g)          # n_keys = "outside the mesh"
+        x1 = torch.rand(n, generator=g, dtype=torch.float64)
+        x2 = keys.to(torch.float64) + 0.25                               # lets the test recover the key afterwards
+        y = torch.rand(n, generator=g, dtype=torch.float64) + rank
+        xs, yy = vdist.spatial_reshard([x1, x2], y, keys, n_keys, None)
+        torch.save({"x1": xs[0], "x2": xs[1], "y": yy, "in_x1": x1, "in_y": y}, os.path.join(out_dir, f"reshard{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_spatial_reshard_two_ranks(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_reshard_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), f"reshard{r}.pt")) for r in range(world)]
+    n_keys = 48
+    # every observation is on exactly one rank afterwards (multiset equality of (x1, y) pairs)
+    before = torch.sort(torch.cat([r["in_x1"] * 3.0 + r["in_y"] for r in res]))[0]
+    after = torch.sort(torch.cat([r["x1"] * 3.0 + r["y"] for r in res]))[0]
+    assert torch.equal(before, after)
+    # rank r owns the keys k with k * world // (n_keys + 1) == r
+    for r, d in enumerate(res):
+        keys = (d["x2"] - 0.25).round().to(torch.int64)
+        assert torch.all((keys * world) // (n_keys + 1) == r)
+        assert d["x1"].numel() == d["y"].numel() == d["x2"].numel()

@@ -10,7 +10,7 @@ Module layout mirrors the reference's `src/` for the classes on the hot path:
 """
 from . import _lib  # noqa: F401
 from .plan import GridPlan, gridded_elbo, gemm_f64  # noqa: F401
-from .dist import shard_bounds, init_from_env  # noqa: F401
+from .dist import shard_bounds, init_from_env, spatial_reshard  # noqa: F401
 from .models._gridded import GriddedVariationalGP  # noqa: F401
 
 B1_ASVGP = _lib.B1_ASVGP

@@ -45,3 +45,29 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, local_rank, world
+
+
+def spatial_reshard(xs, y, keys: torch.Tensor, n_keys: int, group=None):
+    """One-time exchange (setup): give every rank a contiguous range of grid cells instead of a contiguous range of
+    acquisition order, so that each rank's observations stay dense per cell (the fused kernel flushes gradients per
+    cell, its cost per observation grows when a rank sees only a few observations of each cell).
+
+    xs, y   this rank's observations (any order); keys = flat cell id of each observation in [0, n_keys]
+            (n_keys = outside the mesh).  Observation k goes to rank  keys[k] * world // (n_keys + 1).
+    Returns the observations this rank owns afterwards.  Pure torch.distributed plumbing (all_to_all_single)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return xs, y
+    dest = (keys.to(torch.int64) * world) // (n_keys + 1)
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    ss, rs = send_counts.tolist(), recv_counts.tolist()
+    out = []
+    for t in list(xs) + [y]:
+        src = t[order].contiguous()
+        dst = torch.empty(int(sum(rs)), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(dst, src, output_split_sizes=rs, input_split_sizes=ss, group=group)
+        out.append(dst)
+    return out[:-1], out[-1]

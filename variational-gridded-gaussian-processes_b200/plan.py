@@ -102,6 +102,26 @@ class GridPlan:
                                               yp.data_ptr(), _stream_ptr(self.device)))
         return PackedObs(xp, yp, n, int(run.value), bool(sort_by_cell))
 
+    def cell_keys(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Flat (row-major) cell id of every observation, n_cells for observations outside the mesh (B1 stencil)."""
+        key = None
+        inside = None
+        for d in range(self.D):
+            c, _, _ = self.b1_stencil(d, xs[d])
+            ok = c >= 0
+            c = c.clamp(min=0).to(torch.int64)
+            cells = int(self.meshes[d].numel()) - 1
+            key = c if key is None else key * cells + c
+            inside = ok if inside is None else (inside & ok)
+        return torch.where(inside, key, torch.full_like(key, self.n_cells))
+
+    @property
+    def n_cells(self) -> int:
+        n = 1
+        for m in self.meshes:
+            n *= int(m.numel()) - 1
+        return n
+
     def obs_fwd_bwd(self, xs, y: Optional[torch.Tensor] = None, gbuf: Optional[torch.Tensor] = None):
         """Fused per-observation forward+backward.  `xs` is either a PackedObs (hot path) or a list of plain
         coordinate arrays with targets `y` (any order; transposed into plan scratch first)."""
