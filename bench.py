@@ -306,8 +306,9 @@ def main():
     ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-spatial-reshard", action="store_true",
-                    help="multi-GPU: keep the acquisition-order shards instead of exchanging them by cell range at setup")
+    ap.add_argument("--spatial-reshard", action="store_true",
+                    help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
+                         "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -338,7 +339,7 @@ def main():
     plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, device)
     xs, y = make_tracks(lo, hi, n_total, device, dtype)
     sharding = "contiguous in acquisition order"
-    if world > 1 and not args.no_spatial_reshard:
+    if world > 1 and args.spatial_reshard:
         # one-time setup exchange: every rank ends up owning a contiguous range of grid cells (dist.spatial_reshard)
         keys = plan.cell_keys(xs)
         xs, y = vg.spatial_reshard(xs, y, keys, plan.n_cells)

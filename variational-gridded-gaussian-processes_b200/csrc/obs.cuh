@@ -309,9 +309,11 @@ struct LaneState {
 };
 
 // Leave the cached cell: convert the monomial moments back to corner / band sums and add them to the global
-// gradient buffer with fire-and-forget float atomics (RED; the buffer is L2-resident).
+// gradient buffer with fire-and-forget float atomics (RED; the buffer is L2-resident).  The band sums of dimension
+// d are indexed by c_d alone, so they are flushed only when c_d itself changes (`newc`; nullptr = flush everything):
+// in cell-sorted order the slow dimensions change rarely, which removes most of the same-address RED traffic.
 template <typename T, int D>
-__device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<T, D>& s) {
+__device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<T, D>& s, const int* newc) {
     if (!s.valid) return;
     // per dimension (m0, m1) -> (m0 - m1, m1)
 #pragma unroll
@@ -335,6 +337,7 @@ __device__ __forceinline__ void lane_flush(const PackedArgs<T, D>& a, LaneState<
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
+        if (newc != nullptr && newc[d] == s.c[d]) continue;
         const int n = a.mesh[d].K;
         T* gb = a.gband + (a.band_off[d] + s.c[d]);
         // sums of w (1-a)^2, w (1-a) a, w a^2 from the moments s0, s1, s2
@@ -440,7 +443,7 @@ __device__ __forceinline__ bool lane_switch(const PackedArgs<T, D>& a, LaneState
         moved = moved || (cc != s.c[d]);
     }
     if (moved) {
-        lane_flush<T, D>(a, s);
+        lane_flush<T, D>(a, s, c);
         lane_load_cell<T, D>(a, s, c, tl, th, s_tab);
     } else {
         // x == first knot of the mesh: it belongs to cell 0 although x > t_lo fails; widen the cached lower bound
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 5
                 ya[j] = yb[j];
             }
         }
-        lane_flush<T, D>(a, s);
+        lane_flush<T, D>(a, s, nullptr);
         s.valid = false;
 #pragma unroll
         for (int d = 0; d < D; ++d) { s.tlo_chk[d] = (T)INFINITY; s.thi[d] = -(T)INFINITY; s.c[d] = -1; }
