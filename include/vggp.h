@@ -179,6 +179,15 @@ int vggp_b1_stencil(const vggp_plan* plan, int dim, const void* x, int64_t n,
 int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n, const double* theta,
                         void* phi, void* stream);
 
+/*
+ * Point prediction at test points from the state of the last vggp_grid_forward (B1 family): the marginal mean and
+ * variance of q(f(x*)) -- kronecker_structure.py:199-230 `posterior` restricted to its diagonal --
+ *   mean = <kron_d phi_d(x*), alpha>,   var = prod_d s2_d - prod_d phi_d^T P_d phi_d + prod_d phi_d^T Q_d phi_d.
+ *   x [D] HOST array of device pointers (n values of obs_dtype each); mean, var: n values of obs_dtype.
+ * Test points outside the mesh get mean 0 and the prior variance.
+ */
+int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, void* var, void* stream);
+
 /* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
 
 /* Device pointer to a float64 workspace array of the last forward.  which: */
@@ -190,6 +199,7 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
 #define VGGP_WS_ALPHA  5   /* alpha (M), dim ignored */
 #define VGGP_WS_SCAL   6   /* scalars: logdet K_d [3], logdet S_d [3], tr(P_d S_d) [3], <m,alpha> */
 #define VGGP_WS_KRAW   7   /* K_d as built (before factorisation) */
+#define VGGP_WS_QBAND  8   /* main / first off diagonal of Q_d: [diag (M_d) | off (M_d)] */
 int vggp_workspace_ptr(const vggp_plan* plan, int which, int dim, double** ptr, int64_t* n_elems);
 
 /* Batched strided float64 GEMM on the tensor cores (DMMA m8n8k4) or the SIMT fallback used to cross-check it:

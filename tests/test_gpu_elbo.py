@@ -373,6 +373,76 @@ def test_packing_is_a_permutation(vg, dev):
             assert torch.all(key[1:] >= key[:-1])
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_point_prediction_matches_dense_formulas(vg, dev, dtype, tol):
+    """posterior(x*) marginals against the dense formulas of kronecker_structure.py:199-230 written with (m, S):
+    mean = Kuf*^T Kuu^-1 m,  var = k** - diag(Kuf*^T Kuu^-1 Kuf*) + diag(Kuf*^T Kuu^-1 S Kuu^-1 Kuf*)."""
+    knots = (11, 8)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, 50, seed=21)
+    g = torch.Generator().manual_seed(4)
+    Xs = (torch.rand(400, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1).to(dtype)
+    Kuu, Kuf, _, _ = O.dense_Kuu_Kuf(O.B1_ASVGP, meshes, Xs.to(torch.float64), l, s2, ref_quirks=False)
+    S = O.kron_cov_from_factors(Ls)
+    A = torch.linalg.solve(Kuu, Kuf)
+    mean_ref = A.T @ m
+    var_ref = torch.prod(s2) - (Kuf * A).sum(0) + (A * (S @ A)).sum(0)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    plan.grid_forward(theta, m.to(dev), Lcat)
+    mean, var = plan.predict([Xs[:, 0].contiguous().to(dev), Xs[:, 1].contiguous().to(dev)])
+    scale = max(1.0, mean_ref.abs().max().item())
+    assert (mean.cpu().to(torch.float64) - mean_ref).abs().max().item() < tol * scale
+    assert (var.cpu().to(torch.float64) - var_ref).abs().max().item() < tol * max(1.0, var_ref.abs().max().item())
+    # model-level API
+    gks = _model_module("kronecker_structure")
+    model = gks.Matern12B1SplineASVGP(X, y, 9, (0, 1), (0, 1)).to(dtype).to(dev)
+    post = model.posterior(Xs.to(dev))
+    pred = model.posterior_predictive(Xs.to(dev))
+    assert post.mean.shape == (400,) and torch.all(pred.variance > post.variance)
+    lo, hi = post.confidence_region()
+    assert torch.all(hi >= lo)
+
+
+def test_q_v_cell_integrals_match_dense_formulas(vg, dev):
+    """GriddedMatern12ASVGP.q_v() marginals against the dense matrices the reference builds (_Kvu :831-845,
+    _Kvv :847-901) with the intended covariance  Kvv - Kvu Kuu^-1 Kuv + Kvu Kuu^-1 S Kuu^-1 Kuv."""
+    gks = _model_module("gridded_kronecker_structure")
+    g = torch.Generator().manual_seed(12)
+    nb, pad = 6, 1
+    X = torch.rand(200, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(4 * X[:, 0]) + 0.1 * torch.randn(200, generator=g, dtype=torch.float64)
+    model = gks.GriddedMatern12ASVGP(X, y, nb, pad, (0, 1), (0, 1)).to(torch.float64).to(dev)
+    with torch.no_grad():
+        model.variational_mean.copy_(torch.randn(model.M, generator=g, dtype=torch.float64).to(dev))
+        for c in model._chols():
+            c.add_(0.1 * torch.randn(c.shape, generator=g, dtype=torch.float64).to(dev))
+        model.kernel_1.base_kernel.lengthscale = 0.3
+        model.kernel_2.outputscale = 1.4
+    qv = model.q_v()
+    # dense reference construction on the CPU
+    meshes = [O.make_padded_mesh(0, 1, nb, pad)] * 2
+    l = torch.stack([model.kernel_1.base_kernel.lengthscale.detach().cpu().reshape(()),
+                     model.kernel_2.base_kernel.lengthscale.detach().cpu().reshape(())])
+    s2 = torch.stack([model.kernel_1.outputscale.detach().cpu(), model.kernel_2.outputscale.detach().cpu()])
+    Ks = [O.kuu_b1(meshes[d], l[d], s2[d], ref_quirks=False) for d in range(2)]
+    Kuu = torch.kron(Ks[0], Ks[1])
+    Kd = meshes[0].numel()
+    delta = (meshes[0][1] - meshes[0][0]).to(torch.float64)
+    first_row = torch.nn.functional.pad(torch.stack([delta, delta]), (pad, Kd - (pad + 2)))
+    Kvu_d = torch.vstack([torch.roll(first_row, i) for i in range(nb)])
+    Kvu = torch.kron(Kvu_d, Kvu_d)
+    b0mesh = torch.linspace(0, 1, nb + 1)
+    Kvv = torch.kron(O.kuu_b0(b0mesh, l[0], s2[0]), O.kuu_b0(b0mesh, l[1], s2[1]))
+    m = model.variational_mean.detach().cpu()
+    S = O.kron_cov_from_factors([c.detach().cpu() for c in model._chols()])
+    A = torch.linalg.solve(Kuu, Kvu.T)
+    mean_ref = A.T @ m
+    cov_ref = Kvv - Kvu @ A + A.T @ S @ A
+    assert relerr(qv.mean, mean_ref) < 1e-9
+    assert relerr(qv.variance, torch.diagonal(cov_ref)) < 1e-9
+
+
 def test_model_refuses_cpu(vg):
     ks = _model_module("kronecker_structure")
     X = torch.rand(10, 2, dtype=torch.float64)

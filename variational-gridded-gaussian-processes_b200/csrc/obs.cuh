@@ -605,6 +605,71 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 5
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Point prediction (the forward half of K1 at arbitrary test points, kronecker_structure.py:199-230 restricted to the
+// marginals): mean = <kron phi_d(x*), alpha>,  var = kff - prod_d phi_d^T P_d phi_d + prod_d phi_d^T Q_d phi_d.
+// Plain structure-of-arrays input in any order; one thread per test point.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int D>
+struct PredictArgs {
+    const T* x[D];
+    i64 n;
+    MeshView mesh[D];
+    int stride[D];
+    int tab_off[D];
+    const T* tab;            // per-cell tables (global memory)
+    const T* alpha;
+    const double* theta;     // l[D], s2[D], noise
+    T* mean;
+    T* var;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_predict_b1(const __grid_constant__ PredictArgs<T, D> a) {
+    T kff = (T)1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) kff *= (T)a.theta[D + d];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (i64)gridDim.x * blockDim.x) {
+        int c[D];
+        T w[D];
+        bool all_in = true;
+        T pp = (T)1, qq = (T)1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const T xv = a.x[d][i];
+            bool inside;
+            c[d] = find_cell<T>(a.mesh[d].t, a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h, a.mesh[d].nearly_uniform, xv, inside);
+            all_in = all_in && inside;
+            const int n = a.mesh[d].K;
+            const T* tb = a.tab + (a.tab_off[d] + c[d]);
+            w[d] = div_by_cached_rcp(xv - (T)a.mesh[d].t[c[d]], tb[6 * n], tb[7 * n]);
+            pp *= fma(fma(tb[2 * n], w[d], tb[n]), w[d], tb[0]);
+            qq *= fma(fma(tb[5 * n], w[d], tb[4 * n]), w[d], tb[3 * n]);
+        }
+        T mu = (T)0, v = kff;
+        if (all_in) {
+            int base = 0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) base += c[d] * a.stride[d];
+#pragma unroll
+            for (int corner = 0; corner < (1 << D); ++corner) {
+                T wt = (T)1;
+                int off = base;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const bool hi = (corner >> (D - 1 - d)) & 1;
+                    wt *= hi ? w[d] : ((T)1 - w[d]);
+                    off += hi ? a.stride[d] : 0;
+                }
+                mu += wt * a.alpha[off];
+            }
+            v = kff - pp + qq;
+        }
+        a.mean[i] = mu;
+        a.var[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K1 for the B0 (cell-integrated Matern-1/2) family: dense features phi_d(x) in R^{M_d} that depend on
 // (l_d, s2_d).  This is the reference's own O(N (M + sum M_d^2)) dense algorithm (gridded_kronecker_structure.py:
 // 1392-1407 + kronecker_structure.py:265-275) restated per tile of observations -- features live in shared memory and

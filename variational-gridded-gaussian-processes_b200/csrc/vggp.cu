@@ -585,6 +585,28 @@ int launch_obs_b0(vggp_plan* p, const void* const* x, const void* y, i64 n, void
     return 0;
 }
 
+template <typename T, int D>
+int launch_predict(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
+    PredictArgs<T, D> a;
+    for (int d = 0; d < D; ++d) {
+        a.x[d] = reinterpret_cast<const T*>(x[d]);
+        a.mesh[d] = p->mesh[d];
+        a.stride[d] = (int)p->stride[d];
+        a.tab_off[d] = p->tab_off[d];
+    }
+    a.n = n;
+    a.tab = reinterpret_cast<const T*>(p->tables);
+    a.alpha = reinterpret_cast<const T*>(p->alphaT);
+    a.theta = p->theta_dev;
+    a.mean = reinterpret_cast<T*>(mean);
+    a.var = reinterpret_cast<T*>(var);
+    const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 8);
+    k_predict_b1<T, D><<<blocks, 256, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+int predict_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st);
+
 int obs_b0_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
     if (p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (p->obs_dtype == VGGP_F32) return p->D == 1 ? launch_obs_b0<float, 1>(p, x, y, n, gbuf, st) : launch_obs_b0<float, 2>(p, x, y, n, gbuf, st);
@@ -610,6 +632,9 @@ int obs_b0_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, vo
     } while (0)
 
 int obs_prepare_dispatch(vggp_plan* p) { VGGP_DISPATCH_TD(p, obs_prepare, p); }
+int predict_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, launch_predict, p, x, n, mean, var, st);
+}
 int obs_packed_dispatch(vggp_plan* p, const void* const* xp, const void* yp, i64 n, void* gbuf, cudaStream_t st) {
     VGGP_DISPATCH_TD(p, launch_obs_packed, p, xp, yp, n, gbuf, st);
 }
@@ -1137,6 +1162,17 @@ int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, c
     return 0;
 }
 
+int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void* var, void* stream) {
+    if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    if (!x || !mean || !var) return fail(VGGP_E_ARG, "null argument");
+    for (int d = 0; d < p->D; ++d)
+        if (!x[d]) return fail(VGGP_E_ARG, "null test-point pointer");
+    if (p->family != VGGP_B1_ASVGP)
+        return fail(VGGP_E_UNSUPPORTED, "point prediction is built for the B1 family");
+    return predict_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
+}
+
 int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {
     if (!p || !ptr) return fail(VGGP_E_ARG, "null argument");
     if (which != VGGP_WS_ALPHA && which != VGGP_WS_SCAL && (dim < 0 || dim >= p->D)) return fail(VGGP_E_ARG, "bad dim");
@@ -1154,6 +1190,7 @@ int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int
         case VGGP_WS_Q: *ptr = p->g.Q[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_S: return fail(VGGP_E_UNSUPPORTED, "S_d is no longer materialised");
         case VGGP_WS_KRAW: *ptr = p->g.Kraw[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_QBAND: *ptr = p->g.Qb[dim]; if (n_elems) *n_elems = 2 * (i64)p->n[dim]; return 0;
         case VGGP_WS_ALPHA: *ptr = p->alpha; if (n_elems) *n_elems = p->M; return 0;
         case VGGP_WS_SCAL: *ptr = p->g.sc; if (n_elems) *n_elems = SC_COUNT; return 0;
     }

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from ..params import GaussianLikelihood, GriddedNormal, MaternKernel, ScaleKernel
+from ..params import GaussianLikelihood, GriddedMarginals, GriddedNormal, MaternKernel, ScaleKernel
 from ..plan import GridPlan, gridded_elbo
 from ..dist import shard_bounds
 
@@ -144,6 +144,25 @@ class GriddedVariationalGP(nn.Module):
             Lt = torch.tril(L.detach())
             Ss.append(Lt @ Lt.T)
         return GriddedNormal(self.variational_mean.detach(), Ss)
+
+    # ---- predictions (kronecker_structure.py:199-247, marginals only) --------------------------------------------
+    def posterior(self, x: torch.Tensor) -> GriddedMarginals:
+        """q(f(x*)): marginal mean and variance at the test points x (N*, D) under the current q(u) and
+        hyper-parameters.  B1 family."""
+        plan = self._ensure_plan()
+        theta = self._theta()
+        m = self.variational_mean.detach().to(torch.float64).contiguous()
+        L = torch.cat([c.detach().to(torch.float64).reshape(-1) for c in self._chols()]).contiguous()
+        plan.grid_forward(theta, m, L)
+        x = x.reshape(x.shape[0], -1) if x.dim() > 1 else x.reshape(-1, 1)
+        xs = [x[:, d].contiguous() for d in range(self.D)]
+        mean, var = plan.predict(xs)
+        return GriddedMarginals(mean, var)
+
+    def posterior_predictive(self, x: torch.Tensor) -> GriddedMarginals:
+        """p(y* | y): the posterior marginals pushed through the Gaussian likelihood (variance + noise)."""
+        post = self.posterior(x)
+        return GriddedMarginals(post.mean, post.variance + self.likelihood.noise.detach().to(post.variance.dtype).reshape(()))
 
     # ---- reference plug-in points (dense, small problems only) -------------------------------------------------
     def _theta(self) -> torch.Tensor:

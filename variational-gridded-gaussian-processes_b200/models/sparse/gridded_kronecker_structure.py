@@ -29,6 +29,45 @@ class GriddedMatern12ASVGP(KroneckerStructure):
         self.b1_basis_1, self.b1_basis_2 = B1SplineBasis(pad_1), B1SplineBasis(pad_2)
 
 
+    def q_v(self):
+        """q(v) for the B0 cell integrals v_c = int_cell f (gridded_kronecker_structure.py:831-947), marginals only:
+            mean = Kvu Kuu^-1 m = Kvu alpha,      Kvu = kron_d Kvu_d, rows of Kvu_d = [delta, delta] on the two knots of a cell
+            var  = diag(Kvv) - diag(Kvu Kuu^-1 Kuv) + diag(Kvu Kuu^-1 S Kuu^-1 Kuv)
+        Every term is a Kronecker product of per-dimension pieces that need only the main / first off diagonals of
+        P_d and Q_d.  Deviations from the reference, on purpose: the last term uses Kuu^-1 S Kuu^-1 (the reference
+        writes S^-1 at :942, its 1-D twin Sigma^-1 at gridded_univariate_structure.py:699 -- SURVEY.md appendix B); the
+        reference's `[delta, delta]` row (:836) is kept as is.  Returns cells in row-major (n_b0 x n_b0) order."""
+        from ... import _lib as L
+        from ...params import GriddedMarginals
+        plan = self._ensure_plan()
+        theta = self._theta()
+        m = self.variational_mean.detach().to(torch.float64).contiguous()
+        Lc = torch.cat([c.detach().to(torch.float64).reshape(-1) for c in self._chols()]).contiguous()
+        plan.grid_forward(theta, m, Lc)
+        nb, pad = self.n_b0_splines, self.padding_factor
+        alpha = plan.workspace(L.WS_ALPHA).reshape(plan.m_per_dim)
+        deltas = [self.b1_basis_1.delta.to(torch.float64).item(), self.b1_basis_2.delta.to(torch.float64).item()]
+        sl = lambda a: slice(pad + a, pad + a + nb)
+        mean = deltas[0] * deltas[1] * (alpha[sl(0), sl(0)] + alpha[sl(0), sl(1)] + alpha[sl(1), sl(0)] + alpha[sl(1), sl(1)])
+        kvv, kpk, kqk = [], [], []
+        for d in range(2):
+            n = plan.m_per_dim[d]
+            P = plan.workspace(L.WS_P, d)
+            qb = plan.workspace(L.WS_QBAND, d)
+            pd_, po = torch.diagonal(P), torch.diagonal(P, 1)
+            qd, qo = qb[:n], qb[n:2 * n - 1]
+            i = torch.arange(pad, pad + nb, device=P.device)
+            d2 = deltas[d] ** 2
+            kpk.append(d2 * (pd_[i] + 2 * po[i] + pd_[i + 1]))
+            kqk.append(d2 * (qd[i] + 2 * qo[i] + qd[i + 1]))
+            l, s2 = theta[d], theta[2 + d]
+            b0d = [self.b0_delta_1, self.b0_delta_2][d].to(torch.float64).to(P.device)
+            kvv.append((l ** 2 * s2 * 2 * (torch.exp(-b0d / l) + b0d / l - 1)).expand(nb))
+        outer = lambda a, b: (a[:, None] * b[None, :])
+        var = outer(kvv[0], kvv[1]) - outer(kpk[0], kpk[1]) + outer(kqk[0], kqk[1])
+        return GriddedMarginals(mean.reshape(-1), var.reshape(-1))
+
+
 class Matern12GriddedGP(KroneckerStructure):
     """gridded_kronecker_structure.py:1255-1433: the inducing variables are the B0 cell integrals."""
     family = _lib.B0_GRIDDED

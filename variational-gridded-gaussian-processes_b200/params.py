@@ -117,3 +117,26 @@ class GriddedNormal:
     def confidence_region(self):
         s2 = 2 * self.stddev
         return self.mean - s2, self.mean + s2
+
+
+class GriddedMarginals:
+    """Result of posterior(x*) / posterior_predictive(x*): marginal mean and variance at the test points.  The
+    reference returns a dense N* x N* MultivariateNormal (kronecker_structure.py:199-247); only its marginals --
+    what the notebooks plot and score -- are computed here."""
+
+    def __init__(self, mean: torch.Tensor, variance: torch.Tensor):
+        self.mean = mean
+        self.loc = mean
+        self.variance = variance
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.variance.clamp_min(0).sqrt()
+
+    def confidence_region(self):
+        s2 = 2 * self.stddev
+        return self.mean - s2, self.mean + s2
+
+    @property
+    def covariance_matrix(self):
+        raise NotImplementedError("only the marginal variances are computed; use .variance")

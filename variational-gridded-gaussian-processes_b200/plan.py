@@ -102,6 +102,19 @@ class GridPlan:
                                               yp.data_ptr(), _stream_ptr(self.device)))
         return PackedObs(xp, yp, n, int(run.value), bool(sort_by_cell))
 
+    def predict(self, xs: Sequence[torch.Tensor]):
+        """Marginal mean and variance of q(f(x*)) at test points, from the state of the last grid_forward."""
+        n = int(xs[0].numel())
+        xs = [t.to(self.device, self.obs_dtype).contiguous() for t in xs]
+        if len(xs) != self.D or any(t.numel() != n for t in xs):
+            raise ValueError(f"expected {self.D} coordinate arrays of equal length")
+        mean = torch.empty(n, dtype=self.obs_dtype, device=self.device)
+        var = torch.empty(n, dtype=self.obs_dtype, device=self.device)
+        ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
+        _lib.check(self.lib.vggp_predict(self.handle, ptrs, n, mean.data_ptr(), var.data_ptr(),
+                                         _stream_ptr(self.device)))
+        return mean, var
+
     def cell_keys(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
         """Flat (row-major) cell id of every observation, n_cells for observations outside the mesh (B1 stencil)."""
         key = None
@@ -196,7 +209,7 @@ class GridPlan:
         ptr, n = C.c_void_p(), C.c_int64()
         _lib.check(self.lib.vggp_workspace_ptr(self.handle, which, dim, C.byref(ptr), C.byref(n)))
         out = torch.as_tensor(_DevArray(ptr.value, int(n.value)), device=self.device).clone()
-        if which in (_lib.WS_ALPHA, _lib.WS_SCAL):
+        if which in (_lib.WS_ALPHA, _lib.WS_SCAL, _lib.WS_QBAND):
             return out
         nd = self.m_per_dim[dim]
         return out.view(nd, nd)
