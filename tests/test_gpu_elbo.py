@@ -443,6 +443,50 @@ def test_q_v_cell_integrals_match_dense_formulas(vg, dev):
     assert relerr(qv.variance, torch.diagonal(cov_ref)) < 1e-9
 
 
+def test_full_size_properties_bench_config(vg, dev):
+    """BASELINE.json configs[2] / [4] shape (2-D along-track observations, 512 x 512 grid, float32), N = 2^24, where
+    the oracle cannot run: size-independent properties instead.
+      (1) the cell-sorted packed layout, the acquisition-order packed layout and the plain-array entry point give the
+          same ELBO and gradients (different summation orders only);
+      (2) linearity: the gradient buffer of the data set equals the sum of the buffers of two shards;
+      (3) every observation is counted once (out[3] == N) and the ELBO is finite and negative."""
+    import bench
+    N = 1 << 24
+    meshes = [torch.linspace(0, 1, k) for k in bench.KNOTS]
+    xs, y = bench.make_tracks(0, N, N, dev, torch.float32)
+    theta, m, Ls = bench.make_params(meshes, dev)
+    theta, m = theta.to(dev), m.to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    pk_sorted = plan.pack(xs, y, sort_by_cell=True)
+    pk_acq = plan.pack(xs, y, sort_by_cell=False)
+    res = []
+    for obs, yy in ((pk_sorted, None), (pk_acq, None), (xs, y)):
+        out, dtheta, dm, dL = plan.step(theta, m, Lcat, obs, yy)
+        res.append((out.clone(), dtheta.clone(), dm.clone(), dL.clone()))
+    assert plan.read_info() == 0
+    assert res[0][0][3].item() == N and torch.isfinite(res[0][0]).all() and res[0][0][0].item() < 0
+    for k in (1, 2):
+        assert abs(res[k][0][0].item() - res[0][0][0].item()) < 1e-5 * abs(res[0][0][0].item())
+        for a, b in zip(res[k][1:], res[0][1:]):
+            assert relerr(a, b) < 1e-3
+    # linearity in shards on the sorted layout
+    plan.grid_forward(theta, m, Lcat)
+    plan.obs_fwd_bwd(pk_sorted)
+    obs_full, scal_full = [t.clone() for t in plan.gbuf_views()]
+    half = N // 2 + 12345
+    acc_obs = torch.zeros_like(obs_full, dtype=torch.float64)
+    acc_scal = torch.zeros_like(scal_full)
+    for lo, hi in ((0, half), (half, N)):
+        pk = plan.pack([x[lo:hi].contiguous() for x in xs], y[lo:hi].contiguous(), sort_by_cell=True)
+        plan.obs_fwd_bwd(pk)
+        o, sc = plan.gbuf_views()
+        acc_obs += o.to(torch.float64)
+        acc_scal += sc
+    assert relerr(acc_obs, obs_full) < 1e-4
+    assert abs(acc_scal[1].item() - N) == 0 and abs(acc_scal[0].item() - scal_full[0].item()) < 1e-5 * abs(scal_full[0].item())
+
+
 def test_model_refuses_cpu(vg):
     ks = _model_module("kronecker_structure")
     X = torch.rand(10, 2, dtype=torch.float64)

@@ -47,6 +47,9 @@ struct GridDims {
     double* Qb[VGGP_MAX_D];       // float64 main / first off diagonal of Q_d: [diag (n) | off (n)]
     int structured;               // B1 family: 0 dense Cholesky path, 1 twisted-factorisation inverse + GEMM products,
                                   // 2 (default) twisted factorisation + semiseparable O(n^2) products with P_d
+    double* Ad[VGGP_MAX_D];       // structured == 2: A_d = ghat x_d P_d (M-tensors)
+    const double* alpha;          // alpha (M-tensor)
+    i64 inner[VGGP_MAX_D];        // row-major stride of mode d in the M-tensor
     double* gen[VGGP_MAX_D];      // semiseparable generators of P_d: [pd | ru | rl | gl | gu] each n, then [glend | guend] each nseg
     double* sc;                   // SC_COUNT scalars
     int* info;
@@ -390,7 +393,7 @@ struct SsTask {
     i64 nfibres;              // outer * inner
 };
 
-constexpr int SS_MAX_TASKS = 8;
+constexpr int SS_MAX_TASKS = 12;
 struct SsGroup {
     SsTask t[SS_MAX_TASKS];
     int ntasks;
@@ -606,11 +609,13 @@ __global__ void __launch_bounds__(256) k_bwd_dP_dR(const __grid_constant__ GridD
     const double noise = theta[2 * g.D];
     const double cP = ell_scale / (2.0 * noise), cQ = -ell_scale / (2.0 * noise);
     const T* __restrict__ b = gband + g.band_off[d];   // [bp_diag | bp_off | bq_diag | bq_off]
-    double v = g.dP[d][e];
+    // structured == 2: only the band scatter goes through P . P (X_d); the Gram and dR L^T parts of dP_d enter dK_d's
+    // band as row dot products in k_bwd_theta, so dP_d itself is never formed
+    double v = (g.structured == 2) ? 0.0 : g.dP[d][e];
     if (i == j) v += cP * (double)b[i];
     else if (i - j == 1) v += cP * (double)b[n + j];
     else if (j - i == 1) v += cP * (double)b[n + i];
-    g.dP[d][e] = v;
+    if (g.structured == 2) g.X[d][e] = v; else g.dP[d][e] = v;
     const double* __restrict__ R = g.R[d];
     double r = (double)b[2 * n + i] * R[e];
     if (i > 0) r += (double)b[3 * n + i - 1] * R[e - n];
@@ -696,7 +701,24 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
             if (j < 0 || j >= n) continue;
             double acc = 0.0;
             if (g.structured == 2) {
-                acc = g.dK[d][(i64)i * n + j];          // Z = Y P from the semiseparable product (k_ss_apply)
+                // W = P dP P restricted to the band, dP = Gram + band scatter + dR L^T:
+                //   P (band scatter) P           -> Z (two semiseparable products, k_ss_apply), read at (i, j)
+                //   P unfold(ghat) unfold(T)^T P -> <A_d fibre i, alpha fibre j>,  A_d = ghat x_d P_d, alpha = T_d x_d P_d
+                //   P dR L^T P                   -> <(P dR) row i, (P L) row j> = <dLraw row i, R row j>
+                const double* __restrict__ A = g.Ad[d];
+                const double* __restrict__ al = g.alpha;
+                const i64 inner = g.inner[d];
+                const i64 rest = g.M / n;
+                for (i64 q = lane; q < rest; q += 32) {
+                    const i64 o = q / inner, r = q - o * inner;
+                    const i64 base = o * (i64)n * inner + r;
+                    acc = fma(A[base + (i64)i * inner], al[base + (i64)j * inner], acc);
+                }
+                const double* __restrict__ Li = g.dLraw[d] + (i64)i * n;
+                const double* __restrict__ Rj = g.R[d] + (i64)j * n;
+                for (int k = lane; k < n; k += 32) acc = fma(Li[k], Rj[k], acc);
+                acc = warp_sum(acc);
+                acc += g.dK[d][(i64)i * n + j];
             } else {
                 const double* Yi = Y + (i64)i * n;
                 const double* Pj = P + (i64)j * n;      // P symmetric: column j = row j

@@ -55,7 +55,7 @@ struct vggp_plan {
     Phase pinv, rs, qq, alpha_phase, bwdA, bwdMid, bwdB, Yp, dKp, dRp, gramOnly, dPOnly;
     std::vector<SsGroup> ss_fwd;           // structured == 2: R_d, the T_d chains, alpha
     std::vector<SsGroup> ss_dm;            // (kron P) g, one group per mode
-    SsGroup ss_dL, ss_Y, ss_Z;
+    SsGroup ss_Z;                          // D = 1 only: Z_0 = Y_0 P_0 needs its own launch
     std::vector<Phase> chains;             // D-1 launches building T_d = m x_{e != d} P_e
     double* dm_result;
     std::vector<void*> allocs;
@@ -385,7 +385,7 @@ int build_schedules(vggp_plan* p) {
     }
     // ---- semiseparable product groups (B1 family, structured == 2) ----
     if (g.structured == 2) {
-        if (2 * D > SS_MAX_TASKS) return fail(VGGP_E_DIM, "too many tasks for one semiseparable group");
+        if (3 * D + 1 > SS_MAX_TASKS) return fail(VGGP_E_DIM, "too many tasks for one semiseparable group");
         SsGroup g0;
         g0.ntasks = 0;
         for (int d = 0; d < D; ++d)          // R_d = P_d Lt_d : mode 0 of an n x n matrix
@@ -413,25 +413,30 @@ int build_schedules(vggp_plan* p) {
         ga.ntasks = 1;
         ga.t[0] = ss_mode_task(p, D - 1, p->Tm[D - 1], p->alpha);
         p->ss_fwd.push_back(ga);
-        // reverse: (kron P) g mode by mode; the last mode shares its launch with dLraw_d = P_d dR_d
+        // reverse pass without GEMMs: launch e applies mode e of (kron P) g; launch 0 also carries A_d = ghat x_d P_d,
+        // dLraw_d = P_d dR_d and Y_d = P_d X_d (X_d = band scatter), launch 1 (or a launch of its own for D = 1)
+        // Z_d = Y_d P_d
         const double* src = p->gM;
         for (int e = 0; e < D; ++e) {
             double* dst = (e % 2 == 0) ? p->pgA : p->pgB;
             SsGroup gd;
             gd.ntasks = 1;
             gd.t[0] = ss_mode_task(p, e, src, dst);
-            if (e == D - 1)
-                for (int d = 0; d < D; ++d) gd.t[gd.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.dR[d], g.dLraw[d]);
+            if (e == 0) {
+                for (int d = 0; d < D; ++d) {
+                    gd.t[gd.ntasks++] = ss_mode_task(p, d, p->ghat, g.Ad[d]);
+                    gd.t[gd.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.dR[d], g.dLraw[d]);
+                    gd.t[gd.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.X[d], g.Y[d]);
+                }
+            }
+            if (e == 1)
+                for (int d = 0; d < D; ++d) gd.t[gd.ntasks++] = ss_task(g.gen[d], p->n[d], p->n[d], 1, g.Y[d], g.dK[d]);
             p->ss_dm.push_back(gd);
             src = dst;
             p->dm_result = dst;
         }
-        p->ss_Y.ntasks = 0;
         p->ss_Z.ntasks = 0;
-        for (int d = 0; d < D; ++d) {
-            p->ss_Y.t[p->ss_Y.ntasks++] = ss_task(g.gen[d], p->n[d], 1, p->n[d], g.X[d], g.Y[d]);      // Y = P X
-            p->ss_Z.t[p->ss_Z.ntasks++] = ss_task(g.gen[d], p->n[d], p->n[d], 1, g.Y[d], g.dK[d]);     // Z = Y P
-        }
+        if (D == 1) p->ss_Z.t[p->ss_Z.ntasks++] = ss_task(g.gen[0], p->n[0], p->n[0], 1, g.Y[0], g.dK[0]);
     }
     return 0;
 }
@@ -788,6 +793,9 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     TRY(dev_alloc(p, &p->mws, p->M)); TRY(dev_alloc(p, &p->alpha, p->M));
     TRY(dev_alloc(p, &p->gM, p->M)); TRY(dev_alloc(p, &p->ghat, p->M));
     TRY(dev_alloc(p, &p->pgA, p->M)); TRY(dev_alloc(p, &p->pgB, p->M));
+    for (int d = 0; d < D; ++d) TRY(dev_alloc(p, &g.Ad[d], p->M));
+    g.alpha = p->alpha;
+    for (int d = 0; d < D; ++d) g.inner[d] = p->stride[d];
     for (int d = 0; d < D; ++d) {
         if (D > 1) TRY(dev_alloc(p, &p->Tm[d], p->M));
         if (D > 2) TRY(dev_alloc(p, &p->tmpM[d], p->M)); else p->tmpM[d] = nullptr;
@@ -1006,16 +1014,12 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     else
         k_bwd_prep<double><<<mblocks, 256, 0, st>>>(reinterpret_cast<const double*>(gbuf), p->mws, theta, D, ell_scale, p->gM, p->ghat, p->M);
     VGGP_LAUNCH_CHECK();
-    for (int d = 0; d < D; ++d)
-        VGGP_CUDA(cudaMemsetAsync(p->g.dP[d], 0, sizeof(double) * (size_t)p->n[d] * p->n[d], st));
     const bool ss = (p->g.structured == 2);
     const i64 nn = (i64)p->nmax * p->nmax;
     dim3 egrid(ceil_div(nn, 256), D);
-    if (ss) {
-        // B1 family, semiseparable products: (kron P) g mode by mode, Gram contractions on the tensor cores
-        for (int e = 0; e + 1 < D; ++e) if ((rc = launch_ss(p->ss_dm[e], st))) return rc;
-        if ((rc = launch_phase(p->gramOnly, st))) return rc;
-    } else {
+    if (!ss) {
+        for (int d = 0; d < D; ++d)
+            VGGP_CUDA(cudaMemsetAsync(p->g.dP[d], 0, sizeof(double) * (size_t)p->n[d] * p->n[d], st));
         if ((rc = launch_phase(p->bwdA, st))) return rc;
         if ((rc = launch_phase(p->bwdMid, st))) return rc;
     }
@@ -1034,19 +1038,18 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
         if ((rc = launch_phase(p->dRp, st))) return rc;
     }
     if (ss) {
-        if ((rc = launch_ss(p->ss_dm[D - 1], st))) return rc;       // last mode of (kron P) g  +  dLraw_d = P_d dR_d
-        if ((rc = launch_phase(p->dPOnly, st))) return rc;          // dP_d += dR_d Lt_d^T
+        // B1 family, no GEMM in the reverse pass: everything that multiplies P_d is a semiseparable product and dK_d is
+        // needed on its band only (k_bwd_theta)
+        for (auto& grp : p->ss_dm) if ((rc = launch_ss(grp, st))) return rc;
+        if ((rc = launch_ss(p->ss_Z, st))) return rc;
+        k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
+        VGGP_LAUNCH_CHECK();
     } else {
         if ((rc = launch_phase(p->bwdB, st))) return rc;
-    }
-    k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
-    VGGP_LAUNCH_CHECK();
-    k_sym<<<egrid, 256, 0, st>>>(p->g);
-    VGGP_LAUNCH_CHECK();
-    if (ss) {
-        if ((rc = launch_ss(p->ss_Y, st))) return rc;               // Y_d = P_d sym(dP_d)
-        if ((rc = launch_ss(p->ss_Z, st))) return rc;               // Z_d = Y_d P_d (its band is -dK_d's GEMM part)
-    } else {
+        k_bwd_dm<<<mblocks, 256, 0, st>>>(p->dm_result, p->alpha, dm, p->M);
+        VGGP_LAUNCH_CHECK();
+        k_sym<<<egrid, 256, 0, st>>>(p->g);
+        VGGP_LAUNCH_CHECK();
         if ((rc = launch_phase(p->Yp, st))) return rc;
         if (!p->g.structured) {
             if ((rc = launch_phase(p->dKp, st))) return rc;
@@ -1055,7 +1058,7 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     k_bwd_dL<<<egrid, 256, 0, st>>>(p->g, dL);
     VGGP_LAUNCH_CHECK();
     VGGP_CUDA(cudaMemsetAsync(dtheta, 0, sizeof(double) * (2 * D + 1), st));
-    k_bwd_theta<<<dim3(p->g.structured ? 24 : 64, D), 256, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
+    k_bwd_theta<<<dim3(p->g.structured == 2 ? 96 : (p->g.structured ? 24 : 64), D), 256, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
