@@ -330,8 +330,6 @@ def main():
     ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the whole step (kernels + all-reduce) from one CUDA graph")
     ap.add_argument("--spatial-reshard", action="store_true",
                     help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
                          "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
@@ -403,21 +401,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph = None
-    launches_per_step = None
-    if args.cuda_graph:
-        c0 = lib.vggp_launch_count()
-        step()
-        launches_per_step = lib.vggp_launch_count() - c0      # kernels of this library in one step (replayed by the graph)
-        graph, graph_out = plan.graphed_step(theta_d, m_d, L_d, packed, None, 1.0, group)
-        plain_step = step
-
-        def step(i=None, obs=None):          # noqa: F811  (the graph holds the packed, cell-sorted observations)
-            if obs is not None:
-                return plain_step(i, obs)
-            graph.replay()
-            return graph_out
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -452,18 +435,8 @@ def main():
     t_end.record()
     barrier()
     launches = lib.vggp_launch_count() - launches0
-    if graph is not None:
-        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
-    if graph is not None:
-        # events cannot be recorded inside a replayed graph: time the per-observation kernel in a separate loop
-        torch.cuda.synchronize()
-        for i in range(args.steps):
-            ev_a[i].record()
-            plan.obs_fwd_bwd(packed)
-            ev_b[i].record()
-        torch.cuda.synchronize()
     k1_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps
     tt = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -554,7 +527,7 @@ def main():
                 "n_obs_per_gpu": n_local, "run_len": packed.run_len, "observation_sharding": sharding,
                 "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
                           "(X is constant over optimisation steps); setup is outside the timed region",
-                "setup_ms": setup_ms, "cuda_graph": bool(args.cuda_graph),
+                "setup_ms": setup_ms,
                 "acquisition_order": {"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
                                       "note": "same step without the cell binning (along-track order kept)"}}),
             "elbo": out[0][0].item(),

@@ -178,22 +178,6 @@ class GridPlan:
             self.allreduce_gbuf(None if isinstance(group, str) else group)
         return self.grid_backward(theta, m, L, ell_scale)
 
-    def graphed_step(self, theta, m, L, xs, y=None, ell_scale: float = 1.0, group=None, warmup: int = 3):
-        """Capture one step (all C-ABI launches and the all-reduce) into a CUDA graph.  `theta`, `m`, `L` are STATIC
-        device buffers: write new parameter values into them (copy_) and call `.replay()`.  Returns
-        (graph, (out, dtheta, dm, dL)) -- the output tensors are overwritten by every replay."""
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self.step(theta, m, L, xs, y, ell_scale, group)
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            outs = self.step(theta, m, L, xs, y, ell_scale, group)
-        return graph, outs
-
     def read_info(self) -> int:
         info = C.c_int(0)
         _lib.check(self.lib.vggp_read_info(self.handle, C.byref(info), _stream_ptr(self.device)))
