@@ -330,6 +330,10 @@ def main():
     ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--obs-layout", default="packed", choices=["packed", "binned"],
+                    help="layout the fused per-observation kernel streams: 'packed' = k_obs_b1 (default, the kernel "
+                         "verified on B200 in round 1); 'binned' = k_obs_b1_binned (per-cell runs, opt-in)")
+    ap.add_argument("--run-cap", type=int, default=256, help="binned layout: longest run of one cell")
     ap.add_argument("--spatial-reshard", action="store_true",
                     help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
                          "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
@@ -374,7 +378,10 @@ def main():
     # in the packed layout the fused kernel streams; the acquisition-order packing is timed as a second leg
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    packed = plan.pack(xs, y, sort_by_cell=True)
+    if args.obs_layout == "binned":
+        packed = plan.bin(xs, y, run_cap=args.run_cap)
+    else:
+        packed = plan.pack(xs, y, sort_by_cell=True)
     torch.cuda.synchronize()
     setup_ms = (time.perf_counter() - t0) * 1e3
     theta, m, Ls = make_params(meshes, device)
@@ -524,16 +531,24 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_total, world, {
-                "n_obs_per_gpu": n_local, "run_len": packed.run_len, "observation_sharding": sharding,
-                "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
-                          "(X is constant over optimisation steps); setup is outside the timed region",
+                "n_obs_per_gpu": n_local, "observation_sharding": sharding,
+                **({"run_len": packed.run_len,
+                    "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
+                              "(X is constant over optimisation steps); setup is outside the timed region"}
+                   if args.obs_layout == "packed" else
+                   {"run_cap": packed.run_cap, "n_runs": packed.n_runs, "n_tasks": packed.n_tasks,
+                    "streamed_bytes": packed.streamed_bytes,
+                    "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
+                              "setup; setup is outside the timed region"}),
                 "setup_ms": setup_ms,
                 "acquisition_order": {"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
                                       "note": "same step without the cell binning (along-track order kept)"}}),
             "elbo": out[0][0].item(),
-            "roofline": {"bound": "hbm", "kernel": "k_obs_b1 (fused per-observation ELBO forward+backward)",
+            "roofline": {"bound": "hbm", "kernel": ("k_obs_b1" if args.obs_layout == "packed" else "k_obs_b1_binned")
+                         + " (fused per-observation ELBO forward+backward)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (k1_traffic() if (world == 1 and n_total == N_TOTAL) else None),
+                         "traffic": (k1_traffic() if (world == 1 and n_total == N_TOTAL
+                                                      and args.obs_layout == "packed") else None),
                          "peak_source": peak_src, "kernel_ms": k1_ms,
                          "algorithmic_bytes": alg_bytes,
                          "share_of_step": k1_ms / ms_step},

@@ -142,6 +142,39 @@ int vggp_obs_fwd_bwd_packed(vggp_plan* plan, const void* const* xp, const void* 
 int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream);
 
 /*
+ * Binned observation layout (B1 family; second form of the one-time setup, same gbuf as the packed form).
+ * The observations are ordered by grid cell and cut into RUNS -- all observations of one cell, or an equal share of
+ * them when the cell holds more than `run_cap` -- and 32 runs of (almost) equal length form one warp task, so that
+ * the fused kernel enters and leaves cells with all lanes active and needs no per-observation cell test.  Padding
+ * slots contribute nothing; observations outside the mesh are not streamed (their sum of y^2 is stored once).
+ *   vggp_obs_bin_prepare   x[D] (n values each) -> desc: the layout of this data set and the size of the buffer the
+ *                          caller must allocate (256-byte aligned).  Sorts by cell, reads the per-cell counts back
+ *                          and plans the runs on the host: synchronises `stream`, allocates temporaries that live
+ *                          until the matching vggp_obs_bin_pack (one pending layout per plan).
+ *   vggp_obs_bin_pack      fills `binned` (desc->bytes) from x[D], y; synchronises, frees the temporaries.
+ *   vggp_obs_fwd_bwd_binned  the fused forward+backward over a binned buffer (asynchronous, allocation-free);
+ *                          gbuf is zeroed by the call, exactly as vggp_obs_fwd_bwd_packed.
+ * Status of this form: the host planner and the per-lane arithmetic are exercised on the CPU by tests/host_emul;
+ * the device path is opt-in until it has been run on a B200.
+ */
+typedef struct vggp_binned_desc {
+    int64_t bytes;          /* size of the device buffer `binned` */
+    int64_t n;              /* observations given */
+    int64_t n_inside;       /* of which inside the mesh (streamed) */
+    int64_t n_tasks;        /* warp tasks of 32 runs */
+    int64_t n_runs;         /* non-empty runs */
+    int64_t data_elems;     /* streamed values of obs dtype, padding included: sum over tasks of 32 R_t (D + 1) */
+    int64_t off_task_off, off_task_R, off_run_cell, off_run_n, off_run_start, off_data;   /* byte offsets */
+    int32_t run_cap, D;
+} vggp_binned_desc;
+int vggp_obs_bin_prepare(vggp_plan* plan, const void* const* x, int64_t n, int run_cap, vggp_binned_desc* desc,
+                         void* stream);
+int vggp_obs_bin_pack(vggp_plan* plan, const vggp_binned_desc* desc, const void* const* x, const void* y,
+                      void* binned, void* stream);
+int vggp_obs_fwd_bwd_binned(vggp_plan* plan, const vggp_binned_desc* desc, const void* binned, void* gbuf,
+                            void* stream);
+
+/*
  * Grid-side backward + ELBO assembly from the (all-reduced) gbuf.
  *   ell_scale   N / B minibatch scaling of the expected log-likelihood (1 for full batch)
  *   out    [4]    float64: ELBO, ell_scale * ELL, KL, n_obs(all ranks)

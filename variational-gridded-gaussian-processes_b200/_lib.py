@@ -16,6 +16,15 @@ _vp = C.c_void_p
 _i64 = C.c_int64
 _dp = C.c_void_p   # device pointers travel as integers
 
+
+class BinnedDesc(C.Structure):
+    """vggp_binned_desc (include/vggp.h): layout of one binned data set."""
+    _fields_ = [("bytes", _i64), ("n", _i64), ("n_inside", _i64), ("n_tasks", _i64), ("n_runs", _i64),
+                ("data_elems", _i64), ("off_task_off", _i64), ("off_task_R", _i64), ("off_run_cell", _i64),
+                ("off_run_n", _i64), ("off_run_start", _i64), ("off_data", _i64),
+                ("run_cap", C.c_int32), ("D", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/vggp.h
 SIGNATURES = {
     "vggp_abi_version": (C.c_int, []),
@@ -31,6 +40,9 @@ SIGNATURES = {
     "vggp_obs_pack": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, C.c_int, C.POINTER(_vp), _dp, _vp]),
     "vggp_obs_fwd_bwd_packed": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),
     "vggp_obs_fwd_bwd": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),
+    "vggp_obs_bin_prepare": (C.c_int, [_vp, C.POINTER(_vp), _i64, C.c_int, C.POINTER(BinnedDesc), _vp]),
+    "vggp_obs_bin_pack": (C.c_int, [_vp, C.POINTER(BinnedDesc), C.POINTER(_vp), _dp, _dp, _vp]),
+    "vggp_obs_fwd_bwd_binned": (C.c_int, [_vp, C.POINTER(BinnedDesc), _dp, _dp, _vp]),
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
     "vggp_predict": (C.c_int, [_vp, C.POINTER(_vp), _i64, _dp, _dp, _vp]),

@@ -1,0 +1,457 @@
+// K1 "binned": fused per-observation ELBO forward + backward for the B1 (ASVGP) family over the binned layout of
+// binplan.hpp.  Same outputs as k_obs_b1 (obs.cuh) into the same gbuf; what changes is who owns a cell:
+//
+//   * one lane walks one RUN = (a share of) the observations of ONE grid cell, and the 32 runs of a warp task have
+//     the same padded length, so the warp enters its cells, streams, and flushes in lock step -- no per-observation
+//     cell test, no divergent cell switch;
+//   * the variance terms are accumulated as MOMENTS of the hat weights, sum_n prod_d a_{n,d}^{k_d} (k_d = 0..2),
+//     instead of evaluating p_d, q_d per observation: every band sum of P_d and Q_d and sum_n (prod q - prod p) is a
+//     fixed linear combination of these 3^D numbers with the per-cell band polynomials as coefficients, applied once
+//     per run at the flush.  Straight-line cost per observation in 2-D: 28 FP32 instructions (8 weights, 4 mean,
+//     5 residual sums, 1 r^2, 10 moments) against ~50 in k_obs_b1;
+//   * padding slots hold x_d = lower knot of the run's cell (weight a_d = 0 exactly: no moment is touched) and the
+//     residual of slots past the run's length is forced to 0, so padding contributes nothing;
+//   * observations outside every mesh are not streamed at all: their only contribution, sum y^2, is a constant of the
+//     data set computed at packing time.
+//
+// The per-lane arithmetic is __host__ __device__ so that tests/host_emul can execute exactly this code on the CPU
+// (test infrastructure only: libvggp.so exports no host path).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "binplan.hpp"
+
+#if defined(__CUDACC__)
+#define VGGP_HD __host__ __device__ __forceinline__
+#else
+#define VGGP_HD inline
+#endif
+
+namespace vggp {
+
+template <int D> struct Pow3 { static constexpr int v = 3 * Pow3<D - 1>::v; };
+template <> struct Pow3<0> { static constexpr int v = 1; };
+
+VGGP_HD float bin_fma(float a, float b, float c) { return fmaf(a, b, c); }
+VGGP_HD double bin_fma(double a, double b, double c) { return fma(a, b, c); }
+
+// correctly rounded u / h from the correctly rounded reciprocal (same scheme as div_by_cached_rcp in obs.cuh)
+VGGP_HD float bin_div(float u, float h, float rh) {
+    const float q0 = u * rh;
+    const float rem = fmaf(-q0, h, u);
+    return fmaf(rem, rh, q0);
+}
+VGGP_HD double bin_div(double u, double h, double rh) { (void)rh; return u / h; }
+
+template <typename T>
+VGGP_HD T bin_ldg(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// Addressing of the per-cell tables, the knots and the gradient buffer (a subset of PackedArgs in obs.cuh).
+template <int D>
+struct BinGeom {
+    int K[D];            // knots per dimension (cells: K - 1)
+    int stride[D];       // row-major strides of alpha
+    int band_off[D];     // offset of dim d inside the gradient band block: [bp_d | bp_o | bq_d | bq_o] each K long
+    int tab_off[D];      // offset of dim d inside the cell tables: [pe0 pe1 pe2 qe0 qe1 qe2 h rh] each K long
+    int knot_off[D];     // offset of dim d inside the knot block
+};
+
+template <typename T, int D>
+struct BinLane {
+    int c[D];
+    T tlo[D], h[D], rh[D];
+    T am[1 << D];                // alpha at the cell corners, monomial basis
+    T gm[1 << D];                // sum r prod_{d in S} a_d
+    T mom[Pow3<D>::v];           // sum prod_d a_d^{k_d}, index sum_d k_d 3^(D-1-d); entry 0 (the count) is not accumulated
+    T e;                         // sum r^2
+};
+
+// flat cell id (row-major over cells, dimension 0 slowest) -> per-dimension cell index
+template <int D>
+VGGP_HD void bin_decode_cell(uint32_t cell, const int (&K)[D], int (&c)[D]) {
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) {
+        const uint32_t nc = (uint32_t)(K[d] - 1);
+        c[d] = (int)(cell % nc);
+        cell /= nc;
+    }
+}
+
+// Enter cell c: knots and knot spacing from the staged tables, alpha corners from L2; clear the sums.
+template <typename T, int D>
+VGGP_HD void bin_lane_enter(const BinGeom<D>& g, BinLane<T, D>& s, const int (&c)[D], const T* tab,
+                            const float* knots, const T* alpha) {
+    int base = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int n = g.K[d];
+        const T* tb = tab + (g.tab_off[d] + c[d]);
+        s.c[d] = c[d];
+        s.tlo[d] = (T)knots[g.knot_off[d] + c[d]];
+        s.h[d] = tb[6 * n];          // (T)(float32 knot difference), reference semantics
+        s.rh[d] = tb[7 * n];         // correctly rounded 1 / h
+        base += c[d] * g.stride[d];
+    }
+    const T* al = alpha + base;
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) {
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? g.stride[d] : 0;
+        s.am[i] = bin_ldg(al + off);
+        s.gm[i] = (T)0;
+    }
+    // corner values -> monomial coefficients: per dimension (lo, hi) -> (lo, hi - lo)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
+#pragma unroll
+        for (int i = 0; i < (1 << D); ++i)
+            if (i & bit) s.am[i] -= s.am[i ^ bit];
+    }
+#pragma unroll
+    for (int i = 0; i < Pow3<D>::v; ++i) s.mom[i] = (T)0;
+    s.e = (T)0;
+}
+
+// One observation of the run.  `live` is false for the padding slots past the run's length (their x is the cell's
+// lower knot, so a_d = 0 and only the forced-zero residual needs the flag).
+template <typename T, int D>
+VGGP_HD void bin_lane_obs(BinLane<T, D>& s, const T (&x)[D], T y, bool live) {
+    T w[D], w2[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        w[d] = bin_div(x[d] - s.tlo[d], s.h[d], s.rh[d]);
+        w2[d] = w[d] * w[d];
+    }
+    // monomials prod_{d in S} a_d, S indexed by bits (dimension 0 = most significant bit)
+    T mono[1 << D];
+    mono[0] = (T)1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
+#pragma unroll
+        for (int i = 0; i < (1 << D); ++i)
+            if ((i & bit) && !(i & (bit - 1))) mono[i] = (i ^ bit) ? mono[i ^ bit] * w[d] : w[d];
+    }
+    T mu = s.am[0];
+#pragma unroll
+    for (int i = 1; i < (1 << D); ++i) mu = bin_fma(s.am[i], mono[i], mu);
+    const T r = live ? y - mu : (T)0;
+    s.gm[0] += r;
+#pragma unroll
+    for (int i = 1; i < (1 << D); ++i) s.gm[i] = bin_fma(r, mono[i], s.gm[i]);
+    s.e = bin_fma(r, r, s.e);
+    // moments: products over the trailing dimensions 1..D-1 are materialised (tp), dimension 0 is fused into the sums
+    constexpr int LEN = Pow3<D - 1>::v;
+    T tp[LEN];
+    tp[0] = (T)1;
+    {
+        int len = 1;
+#pragma unroll
+        for (int d = D - 1; d >= 1; --d) {
+#pragma unroll
+            for (int j = 0; j < LEN; ++j)
+                if (j < len) {
+                    tp[len + j] = (j == 0) ? w[d] : w[d] * tp[j];
+                    tp[2 * len + j] = (j == 0) ? w2[d] : w2[d] * tp[j];
+                }
+            len *= 3;
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < LEN; ++j) s.mom[j] += tp[j];
+    s.mom[LEN] += w[0];
+    s.mom[2 * LEN] += w2[0];
+#pragma unroll
+    for (int j = 1; j < LEN; ++j) {
+        s.mom[LEN + j] = bin_fma(w[0], tp[j], s.mom[LEN + j]);
+        s.mom[2 * LEN + j] = bin_fma(w2[0], tp[j], s.mom[2 * LEN + j]);
+    }
+}
+
+// Leave the cell: moments -> band sums of P_d, Q_d (monomial -> (diag, off, next diag) form), residual sums -> corner
+// form, all added to the gradient buffer through `add` (RED atomics on the device).  Returns the run's contribution to
+// sum_n (r^2 - prod p + prod q).
+template <typename T, int D, typename Adder>
+VGGP_HD T bin_lane_flush(const BinGeom<D>& g, BinLane<T, D>& s, int nrun, const T* tab, T* galpha, T* gband,
+                         const Adder& add) {
+    // per dimension (m0, m1) -> (m0 - m1, m1)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int bit = 1 << (D - 1 - d);
+#pragma unroll
+        for (int i = 0; i < (1 << D); ++i)
+            if (!(i & bit)) s.gm[i] -= s.gm[i | bit];
+    }
+    int base = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) base += s.c[d] * g.stride[d];
+    T* ga = galpha + base;
+#pragma unroll
+    for (int i = 0; i < (1 << D); ++i) {
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) off += (i & (1 << (D - 1 - d))) ? g.stride[d] : 0;
+        add(ga + off, s.gm[i]);
+    }
+    T pe[D][3], qe[D][3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int n = g.K[d];
+        const T* tb = tab + (g.tab_off[d] + s.c[d]);
+        pe[d][0] = tb[0]; pe[d][1] = tb[n]; pe[d][2] = tb[2 * n];
+        qe[d][0] = tb[3 * n]; qe[d][1] = tb[4 * n]; qe[d][2] = tb[5 * n];
+    }
+    s.mom[0] = (T)nrun;
+    T accV = (T)0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        T bp[3] = {(T)0, (T)0, (T)0}, bq[3] = {(T)0, (T)0, (T)0};
+#pragma unroll
+        for (int idx = 0; idx < Pow3<D>::v; ++idx) {
+            T cp = (T)1, cq = (T)1;
+            int kd = 0, rem = idx;
+#pragma unroll
+            for (int e = D - 1; e >= 0; --e) {
+                const int k = rem % 3;
+                rem /= 3;
+                if (e == d) kd = k;
+                else { cp *= pe[e][k]; cq *= qe[e][k]; }
+            }
+            bp[kd] = bin_fma(cp, s.mom[idx], bp[kd]);
+            bq[kd] = bin_fma(cq, s.mom[idx], bq[kd]);
+        }
+        if (d == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) accV += qe[0][k] * bq[k] - pe[0][k] * bp[k];
+        }
+        const int n = g.K[d];
+        T* gb = gband + (g.band_off[d] + s.c[d]);
+        // sums of w (1-a)^2, w (1-a) a, w a^2 from the moments s0, s1, s2
+        add(gb, bp[0] - (T)2 * bp[1] + bp[2]);
+        add(gb + n, bp[1] - bp[2]);
+        add(gb + 1, bp[2]);
+        add(gb + 2 * n, bq[0] - (T)2 * bq[1] + bq[2]);
+        add(gb + 3 * n, bq[1] - bq[2]);
+        add(gb + 2 * n + 1, bq[2]);
+    }
+    return s.e + accV;
+}
+
+// Where element `e` of a task's data block comes from.  A task stores R / 4 groups; group g holds, for each of the
+// D + 1 streamed arrays, 128 values: 4 consecutive observations of each of the 32 lanes (lane-major), so that one
+// 16-byte load per lane and array fetches observations 4 g .. 4 g + 3 of its run and a warp reads (D + 1) x 512
+// contiguous bytes per group.
+struct BinSlot { int arr, lane, j; };
+VGGP_HD BinSlot bin_slot_of(int64_t e, int D) {
+    const int per_group = (D + 1) * 128;
+    const int64_t g = e / per_group;
+    const int rem = (int)(e - g * per_group);
+    BinSlot s;
+    s.arr = rem >> 7;
+    s.lane = (rem & 127) >> 2;
+    s.j = (int)(g * 4) + (rem & 3);
+    return s;
+}
+VGGP_HD int64_t bin_elem_of(int arr, int lane, int j, int D) {
+    return (int64_t)(j >> 2) * ((D + 1) * 128) + arr * 128 + lane * 4 + (j & 3);
+}
+
+}  // namespace vggp
+
+// ---------------------------------------------------------------------------------------------------------
+// Device side
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__) && !defined(VGGP_HOST_EMUL)
+#include "obs.cuh"
+
+namespace vggp {
+
+struct AtomicAdder {
+    template <typename T>
+    __device__ __forceinline__ void operator()(T* p, T v) const { atomicAdd(p, v); }
+};
+
+template <typename T, int D>
+struct BinnedArgs {
+    BinGeom<D> geo;
+    const unsigned char* buf;        // binned buffer (binplan.hpp: bin_offsets)
+    i64 off_task_off, off_task_R, off_run_cell, off_run_n, off_data;
+    int n_tasks;
+    int table_bytes, knots_byte_off;
+    const unsigned char* tables;     // [cell tables (T) | pad16 | knots (float) | pad16], staged by one TMA bulk copy
+    const T* alpha;
+    T* galpha;
+    T* gband;
+    double* gs;
+    double n_real;
+    unsigned int* counter;           // work-stealing counter over tasks (zeroed before the launch)
+};
+
+constexpr int BIN_THREADS = 128;
+
+// one group = 4 consecutive observations of this lane's run: (D + 1) 16-byte loads, 128 values apart
+template <typename T, int D>
+__device__ __forceinline__ void bin_load_group(const T* p, T (&x)[D][4], T (&y)[4]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) load4<T>(p + d * 128, x[d]);
+    load4<T>(p + D * 128, y);
+}
+
+// `left` = observations of the run not yet consumed (slots past it are padding)
+template <typename T, int D>
+__device__ __forceinline__ void bin_group(BinLane<T, D>& s, const T (&x)[D][4], const T (&y)[4], int left) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T xx[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xx[d] = x[d][j];
+        bin_lane_obs<T, D>(s, xx, y[j], j < left);
+    }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(BIN_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 6) : (D == 1 ? 4 : 2)))
+k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const T* s_tab = reinterpret_cast<const T*>(smraw);
+    const float* s_knots = reinterpret_cast<const float*>(smraw + a.knots_byte_off);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double red[32];
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)a.table_bytes);
+        bulk_g2s(smraw, a.tables, (uint32_t)a.table_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int lane = threadIdx.x & 31;
+    const i64* task_off = reinterpret_cast<const i64*>(a.buf + a.off_task_off);
+    const int* task_R = reinterpret_cast<const int*>(a.buf + a.off_task_R);
+    const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell);
+    const int* run_n = reinterpret_cast<const int*>(a.buf + a.off_run_n);
+    const T* data = reinterpret_cast<const T*>(a.buf + a.off_data);
+    const AtomicAdder add;
+    double etot = 0.0;
+    BinLane<T, D> s;
+
+    // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
+    for (;;) {
+        unsigned int task = 0;
+        if (lane == 0) task = atomicAdd(a.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= (unsigned int)a.n_tasks) break;
+        const i64 slot = (i64)task * 32 + lane;
+        const uint32_t cell = __ldg(run_cell + slot);
+        const int nrun = __ldg(run_n + slot);
+        const int groups = __ldg(task_R + task) >> 2;
+        const T* base = data + __ldg(task_off + task) + lane * 4;
+        const bool valid = cell != BIN_EMPTY;
+        int c[D];
+        bin_decode_cell<D>(valid ? cell : 0u, a.geo.K, c);
+        bin_lane_enter<T, D>(a.geo, s, c, s_tab, s_knots, a.alpha);
+
+        // two register buffers in ping-pong: the loads of the next group of 4 observations are in flight while the
+        // current one is processed (no buffer rotation: the loop body handles two groups)
+        T xa[D][4], ya[4], xb[D][4], yb[4];
+        bin_load_group<T, D>(base, xa, ya);
+#pragma unroll 1
+        for (int gi = 0; gi < groups; gi += 2) {
+            if (gi + 1 < groups) bin_load_group<T, D>(base + (i64)(gi + 1) * ((D + 1) * 128), xb, yb);
+            bin_group<T, D>(s, xa, ya, nrun - 4 * gi);
+            if (gi + 2 < groups) bin_load_group<T, D>(base + (i64)(gi + 2) * ((D + 1) * 128), xa, ya);
+            if (gi + 1 < groups) bin_group<T, D>(s, xb, yb, nrun - 4 * (gi + 1));
+        }
+        if (valid) etot += (double)bin_lane_flush<T, D>(a.geo, s, nrun, s_tab, a.galpha, a.gband, add);
+    }
+    const double e = block_sum(etot, red);
+    if (threadIdx.x == 0) {
+        double extra = 0.0;
+        if (blockIdx.x == 0) {
+            extra = *reinterpret_cast<const double*>(a.buf);     // sum y^2 of the observations outside the mesh
+            a.gs[1] = a.n_real;                                  // single writer; summed over ranks by the all-reduce
+        }
+        atomicAdd(a.gs + 0, e + extra);
+    }
+}
+
+// ---- packing (one-time setup) ---------------------------------------------------------------------------
+
+// observations per flat cell id (keys[i] = ncells for observations outside the mesh)
+__global__ void __launch_bounds__(256) k_bin_histogram(const uint32_t* __restrict__ keys, i64 n, uint32_t* __restrict__ count) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        atomicAdd(count + keys[i], 1u);
+}
+
+template <typename T, int D>
+struct BinGatherArgs {
+    const T* x[D];
+    const T* y;
+    const uint32_t* perm;            // cell-sorted order: stream position -> input index
+    const float* knots[D];           // device knot arrays
+    int K[D];
+    unsigned char* buf;
+    i64 off_task_off, off_task_R, off_run_cell, off_run_n, off_run_start, off_data;
+    int n_tasks;
+};
+
+// one CTA per task (grid-stride): fill the task's data block, coalesced writes, gathered reads
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_bin_gather(const __grid_constant__ BinGatherArgs<T, D> a) {
+    const i64* task_off = reinterpret_cast<const i64*>(a.buf + a.off_task_off);
+    const int* task_R = reinterpret_cast<const int*>(a.buf + a.off_task_R);
+    const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell);
+    const int* run_n = reinterpret_cast<const int*>(a.buf + a.off_run_n);
+    const uint32_t* run_start = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_start);
+    T* data = reinterpret_cast<T*>(a.buf + a.off_data);
+    for (int task = blockIdx.x; task < a.n_tasks; task += gridDim.x) {
+        const i64 elems = (i64)32 * task_R[task] * (D + 1);
+        T* dst = data + task_off[task];
+        for (i64 e = threadIdx.x; e < elems; e += blockDim.x) {
+            const BinSlot sl = bin_slot_of(e, D);
+            const i64 slot = (i64)task * 32 + sl.lane;
+            const uint32_t cell = run_cell[slot];
+            T v;
+            if (sl.j < run_n[slot]) {
+                const i64 src = (i64)a.perm[(i64)run_start[slot] + sl.j];
+                v = (sl.arr < D) ? a.x[sl.arr < D ? sl.arr : 0][src] : a.y[src];
+            } else if (sl.arr < D) {
+                int c[D];
+                bin_decode_cell<D>(cell != BIN_EMPTY ? cell : 0u, a.K, c);
+                v = (T)a.knots[sl.arr][c[sl.arr]];           // padding: weight 0 in every dimension
+            } else {
+                v = (T)0;
+            }
+            dst[e] = v;
+        }
+    }
+}
+
+// sum of y^2 over the observations outside the mesh: stream positions [first, n) of the cell-sorted order
+template <typename T>
+__global__ void __launch_bounds__(256) k_bin_sum_y2(const T* __restrict__ y, const uint32_t* __restrict__ perm, i64 first,
+                                                    i64 n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (i64 i = first + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double v = (double)y[perm[i]];
+        acc += v * v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+}  // namespace vggp
+#endif

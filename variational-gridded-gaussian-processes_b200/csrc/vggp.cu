@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "grid.cuh"
 #include "obs.cuh"
+#include "obs_binned.cuh"
 
 namespace vggp {
 thread_local char g_err[512] = {0};
@@ -48,6 +49,9 @@ struct vggp_plan {
     int sm_count, obs_blocks_per_sm;
     // scratch for vggp_obs_fwd_bwd on unpacked observations (grown on demand)
     void* pk_x[VGGP_MAX_D] = {nullptr, nullptr, nullptr}; void* pk_y = nullptr; i64 pk_cap = 0;
+    // binned layout: the layout planned by vggp_obs_bin_prepare and the cell-sorted order, until vggp_obs_bin_pack
+    BinLayout bin_pending; uint32_t* bin_perm = nullptr; bool bin_has_pending = false;
+    int bin_blocks_per_sm = 0;             // resident CTAs of k_obs_b1_binned (queried at first use)
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
@@ -647,6 +651,152 @@ int pack_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, int 
     VGGP_DISPATCH_TD(p, pack_impl, p, x, y, n, sort, xp, yp, st);
 }
 
+// ---- binned layout (obs_binned.cuh) ---------------------------------------------------------------------
+template <typename T, int D>
+int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vggp_binned_desc* desc, cudaStream_t st) {
+    i64 ncells = 1;
+    for (int d = 0; d < D; ++d) ncells *= (p->K[d] - 1);
+    if (ncells >= ((i64)1 << 32) - 1) return fail(VGGP_E_UNSUPPORTED, "too many cells for 32-bit keys");
+    std::vector<uint32_t> count((size_t)ncells + 1, 0u);
+    if (n > 0) {
+        KeyArgs<T, D> ka;
+        ka.n = n;
+        for (int d = 0; d < D; ++d) {
+            ka.x[d] = reinterpret_cast<const T*>(x[d]);
+            ka.mesh[d] = p->mesh[d];
+        }
+        uint32_t *keys_in = nullptr, *keys_out = nullptr, *idx_in = nullptr, *idx_out = nullptr, *d_count = nullptr;
+        void* temp = nullptr;
+        VGGP_CUDA(cudaMalloc(&keys_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&keys_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&idx_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&idx_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(cudaMalloc(&d_count, sizeof(uint32_t) * (ncells + 1)));
+        VGGP_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * (ncells + 1), st));
+        const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
+        k_cell_keys<T, D><<<blocks, 256, 0, st>>>(ka, (uint32_t)ncells, keys_in, idx_in);
+        VGGP_LAUNCH_CHECK();
+        k_bin_histogram<<<blocks, 256, 0, st>>>(keys_in, n, d_count);
+        VGGP_LAUNCH_CHECK();
+        int end_bit = 1;
+        while (((i64)1 << end_bit) <= ncells) ++end_bit;
+        size_t temp_bytes = 0;
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
+        VGGP_CUDA(cudaMalloc(&temp, temp_bytes));
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
+        VGGP_CUDA(cudaMemcpyAsync(count.data(), d_count, sizeof(uint32_t) * (ncells + 1), cudaMemcpyDeviceToHost, st));
+        VGGP_CUDA(cudaStreamSynchronize(st));
+        cudaFree(keys_in); cudaFree(keys_out); cudaFree(idx_in); cudaFree(temp); cudaFree(d_count);
+        p->bin_perm = idx_out;
+    }
+    if (plan_bins(count.data(), ncells, run_cap, D, p->bin_pending) != 0) return fail(VGGP_E_ARG, "run_cap must be >= 4");
+    if (p->bin_pending.n != n) return fail(VGGP_E_ARG, "internal: cell histogram does not add up to n");
+    p->bin_has_pending = true;
+    const BinLayout& L = p->bin_pending;
+    const BinOffsets o = bin_offsets(L.n_tasks, L.data_elems, (int)sizeof(T));
+    desc->bytes = o.bytes; desc->n = n; desc->n_inside = L.n_inside; desc->n_tasks = L.n_tasks; desc->n_runs = L.n_runs;
+    desc->data_elems = L.data_elems;
+    desc->off_task_off = o.task_off; desc->off_task_R = o.task_R; desc->off_run_cell = o.run_cell; desc->off_run_n = o.run_n;
+    desc->off_run_start = o.run_start; desc->off_data = o.data;
+    desc->run_cap = run_cap / 4 * 4; desc->D = D;
+    return 0;
+}
+
+template <typename T, int D>
+int bin_pack_impl(vggp_plan* p, const vggp_binned_desc* desc, const void* const* x, const void* y, void* binned,
+                  cudaStream_t st) {
+    const BinLayout& L = p->bin_pending;
+    unsigned char* buf = reinterpret_cast<unsigned char*>(binned);
+    VGGP_CUDA(cudaMemsetAsync(buf, 0, BIN_HEADER_BYTES, st));
+    if (L.n_tasks > 0) {
+        VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_task_off, L.task_off.data(), sizeof(int64_t) * L.n_tasks, cudaMemcpyHostToDevice, st));
+        VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_task_R, L.task_R.data(), sizeof(int32_t) * L.n_tasks, cudaMemcpyHostToDevice, st));
+        VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_cell, L.run_cell.data(), sizeof(uint32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
+        VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_n, L.run_n.data(), sizeof(int32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
+        VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_start, L.run_start.data(), sizeof(uint32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
+        BinGatherArgs<T, D> ga;
+        for (int d = 0; d < D; ++d) {
+            ga.x[d] = reinterpret_cast<const T*>(x[d]);
+            ga.knots[d] = p->d_knots[d];
+            ga.K[d] = p->K[d];
+        }
+        ga.y = reinterpret_cast<const T*>(y);
+        ga.perm = p->bin_perm;
+        ga.buf = buf;
+        ga.off_task_off = desc->off_task_off; ga.off_task_R = desc->off_task_R; ga.off_run_cell = desc->off_run_cell;
+        ga.off_run_n = desc->off_run_n; ga.off_run_start = desc->off_run_start; ga.off_data = desc->off_data;
+        ga.n_tasks = (int)L.n_tasks;
+        const int blocks = (int)std::min<i64>(L.n_tasks, (i64)p->sm_count * 8);
+        k_bin_gather<T, D><<<blocks, 256, 0, st>>>(ga);
+        VGGP_LAUNCH_CHECK();
+    }
+    if (L.n > L.n_inside) {
+        const i64 nout = L.n - L.n_inside;
+        const int blocks = (int)std::min<i64>((nout + 255) / 256, 148 * 4);
+        k_bin_sum_y2<T><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(y), p->bin_perm, L.n_inside, L.n,
+                                                reinterpret_cast<double*>(buf));
+        VGGP_LAUNCH_CHECK();
+    }
+    VGGP_CUDA(cudaStreamSynchronize(st));
+    if (p->bin_perm) cudaFree(p->bin_perm);
+    p->bin_perm = nullptr;
+    p->bin_pending = BinLayout();
+    p->bin_has_pending = false;
+    return 0;
+}
+
+template <typename T, int D>
+int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    const size_t smem = obs_smem_bytes<T, D>(p);
+    if (p->bin_blocks_per_sm == 0) {
+        if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
+        VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_binned<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, smem));
+        p->bin_blocks_per_sm = nb < 1 ? 1 : nb;
+    }
+    BinnedArgs<T, D> a;
+    for (int d = 0; d < D; ++d) {
+        a.geo.K[d] = p->K[d];
+        a.geo.stride[d] = (int)p->stride[d];
+        a.geo.band_off[d] = p->band_off[d];
+        a.geo.tab_off[d] = p->tab_off[d];
+        a.geo.knot_off[d] = p->knot_off[d];
+    }
+    a.buf = reinterpret_cast<const unsigned char*>(binned);
+    a.off_task_off = desc->off_task_off; a.off_task_R = desc->off_task_R; a.off_run_cell = desc->off_run_cell;
+    a.off_run_n = desc->off_run_n; a.off_data = desc->off_data;
+    a.n_tasks = (int)desc->n_tasks;
+    a.table_bytes = p->table_bytes;
+    a.knots_byte_off = p->knots_byte_off;
+    a.tables = p->tables;
+    a.alpha = reinterpret_cast<const T*>(p->alphaT);
+    T* gb = reinterpret_cast<T*>(gbuf);
+    a.galpha = gb;
+    a.gband = gb + p->M;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    a.n_real = (double)desc->n;
+    a.counter = p->obs_counter;
+    VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
+    i64 blocks = (desc->n_tasks + (BIN_THREADS / 32) - 1) / (BIN_THREADS / 32);
+    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm));
+    k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, smem, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int bin_prepare_dispatch(vggp_plan* p, const void* const* x, i64 n, int cap, vggp_binned_desc* desc, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, bin_prepare_impl, p, x, n, cap, desc, st);
+}
+int bin_pack_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* const* x, const void* y, void* binned, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, bin_pack_impl, p, desc, x, y, binned, st);
+}
+int obs_binned_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, launch_obs_binned, p, desc, binned, gbuf, st);
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -831,6 +981,7 @@ int vggp_plan_destroy(vggp_plan* p) {
     for (int d = 0; d < VGGP_MAX_D; ++d)
         if (p->pk_x[d]) cudaFree(p->pk_x[d]);
     if (p->pk_y) cudaFree(p->pk_y);
+    if (p->bin_perm) cudaFree(p->bin_perm);
     void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
     for (void* ptr : st)
         if (ptr) cudaFree(ptr);
@@ -996,6 +1147,50 @@ int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t 
     int rc = vggp_obs_pack(p, x, y, n, 0, p->pk_x, p->pk_y, stream);
     if (rc) return rc;
     return vggp_obs_fwd_bwd_packed(p, p->pk_x, p->pk_y, n, gbuf, stream);
+}
+
+int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_cap, vggp_binned_desc* desc, void* stream) {
+    if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the binned layout is used by the B1 family only");
+    if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4");
+    if (n >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^31 observations per shard");
+    if (n > 0) {
+        if (!x) return fail(VGGP_E_ARG, "null observation pointers");
+        for (int d = 0; d < p->D; ++d)
+            if (!x[d]) return fail(VGGP_E_ARG, "null observation pointer");
+    }
+    if (p->bin_perm) { cudaFree(p->bin_perm); p->bin_perm = nullptr; }
+    p->bin_has_pending = false;
+    memset(desc, 0, sizeof(*desc));
+    return bin_prepare_dispatch(p, x, n, run_cap, desc, (cudaStream_t)stream);
+}
+
+int vggp_obs_bin_pack(vggp_plan* p, const vggp_binned_desc* desc, const void* const* x, const void* y, void* binned,
+                      void* stream) {
+    if (!p || !desc || !binned) return fail(VGGP_E_ARG, "bad argument");
+    if (!p->bin_has_pending) return fail(VGGP_E_ARG, "vggp_obs_bin_pack without a pending vggp_obs_bin_prepare on this plan");
+    const BinLayout& L = p->bin_pending;
+    if (desc->n != L.n || desc->n_tasks != L.n_tasks || desc->data_elems != L.data_elems || desc->D != p->D)
+        return fail(VGGP_E_ARG, "descriptor does not match the pending layout");
+    if (L.n > 0) {
+        if (!x || !y) return fail(VGGP_E_ARG, "null observation pointers");
+        for (int d = 0; d < p->D; ++d)
+            if (!x[d]) return fail(VGGP_E_ARG, "null observation pointer");
+    }
+    return bin_pack_dispatch(p, desc, x, y, binned, (cudaStream_t)stream);
+}
+
+int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, void* stream) {
+    if (!p || !desc || !gbuf) return fail(VGGP_E_ARG, "bad argument");
+    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the binned layout is used by the B1 family only");
+    if (desc->D != p->D) return fail(VGGP_E_ARG, "descriptor belongs to a plan of another dimension");
+    cudaStream_t st = (cudaStream_t)stream;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
+    if (desc->n == 0) return 0;
+    if (!binned) return fail(VGGP_E_ARG, "null binned buffer");
+    return obs_binned_dispatch(p, desc, binned, gbuf, st);
 }
 
 int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,

@@ -102,6 +102,21 @@ class GridPlan:
                                               yp.data_ptr(), _stream_ptr(self.device)))
         return PackedObs(xp, yp, n, int(run.value), bool(sort_by_cell))
 
+    def bin(self, xs: Sequence[torch.Tensor], y: torch.Tensor, run_cap: int = 256) -> "BinnedObs":
+        """One-time layout pass, second form (include/vggp.h, vggp_obs_bin_*): observations ordered by grid cell, cut
+        into per-cell runs of at most `run_cap`, 32 equally long runs per warp task.  Opt-in until it has been run
+        on a B200; `pack` is the default hot-path layout."""
+        n = int(y.numel())
+        self._check_obs(xs, y, n)
+        desc = _lib.BinnedDesc()
+        src = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
+        _lib.check(self.lib.vggp_obs_bin_prepare(self.handle, src, n, int(run_cap), C.byref(desc),
+                                                 _stream_ptr(self.device)))
+        buf = torch.empty(int(desc.bytes), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.vggp_obs_bin_pack(self.handle, C.byref(desc), src, y.data_ptr(), buf.data_ptr(),
+                                              _stream_ptr(self.device)))
+        return BinnedObs(buf, desc, 4 if self.obs_dtype == torch.float32 else 8)
+
     def predict(self, xs: Sequence[torch.Tensor]):
         """Marginal mean and variance of q(f(x*)) at test points, from the state of the last grid_forward."""
         n = int(xs[0].numel())
@@ -139,6 +154,10 @@ class GridPlan:
         """Fused per-observation forward+backward.  `xs` is either a PackedObs (hot path) or a list of plain
         coordinate arrays with targets `y` (any order; transposed into plan scratch first)."""
         g = self.gbuf if gbuf is None else gbuf
+        if isinstance(xs, BinnedObs):
+            _lib.check(self.lib.vggp_obs_fwd_bwd_binned(self.handle, C.byref(xs.desc), xs.buf.data_ptr(), g.data_ptr(),
+                                                        _stream_ptr(self.device)))
+            return
         if isinstance(xs, PackedObs):
             ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs.xp])
             _lib.check(self.lib.vggp_obs_fwd_bwd_packed(self.handle, ptrs, xs.yp.data_ptr(), xs.n, g.data_ptr(),
@@ -233,6 +252,23 @@ class PackedObs:
 
     def numel(self) -> int:
         return self.n
+
+
+class BinnedObs:
+    """Observations in the binned layout of vggp_obs_bin_pack: one device buffer + its host descriptor."""
+
+    def __init__(self, buf: torch.Tensor, desc, elem_size: int = 4):
+        self.buf, self.desc, self.elem_size = buf, desc, elem_size
+        self.n, self.n_inside = int(desc.n), int(desc.n_inside)
+        self.n_tasks, self.n_runs, self.run_cap = int(desc.n_tasks), int(desc.n_runs), int(desc.run_cap)
+
+    def numel(self) -> int:
+        return self.n
+
+    @property
+    def streamed_bytes(self) -> int:
+        """Bytes of observation data the fused kernel reads per launch (padding included)."""
+        return int(self.desc.data_elems) * self.elem_size
 
 
 class _DevArray:
