@@ -334,6 +334,9 @@ def main():
                     help="layout the fused per-observation kernel streams: 'packed' = k_obs_b1 (default, the kernel "
                          "verified on B200 in round 1); 'binned' = k_obs_b1_binned (per-cell runs, opt-in)")
     ap.add_argument("--run-cap", type=int, default=256, help="binned layout: longest run of one cell")
+    ap.add_argument("--binned-stream", default="ldg", choices=["ldg", "tma"],
+                    help="binned layout: 16-byte global loads into registers, or a per-warp shared-memory ring "
+                         "filled by TMA bulk copies (vggp_set_binned_stream)")
     ap.add_argument("--spatial-reshard", action="store_true",
                     help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
                          "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
@@ -379,6 +382,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if args.obs_layout == "binned":
+        lib.vggp_set_binned_stream(1 if args.binned_stream == "tma" else 0)
         packed = plan.bin(xs, y, run_cap=args.run_cap)
     else:
         packed = plan.pack(xs, y, sort_by_cell=True)
@@ -536,7 +540,7 @@ def main():
                     "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
                               "(X is constant over optimisation steps); setup is outside the timed region"}
                    if args.obs_layout == "packed" else
-                   {"run_cap": packed.run_cap, "n_runs": packed.n_runs, "n_tasks": packed.n_tasks,
+                   {"binned_stream": args.binned_stream, "run_cap": packed.run_cap, "n_runs": packed.n_runs, "n_tasks": packed.n_tasks,
                     "streamed_bytes": packed.streamed_bytes,
                     "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
                               "setup; setup is outside the timed region"}),

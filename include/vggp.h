@@ -173,6 +173,9 @@ int vggp_obs_bin_pack(vggp_plan* plan, const vggp_binned_desc* desc, const void*
                       void* binned, void* stream);
 int vggp_obs_fwd_bwd_binned(vggp_plan* plan, const vggp_binned_desc* desc, const void* binned, void* gbuf,
                             void* stream);
+/* How vggp_obs_fwd_bwd_binned streams the observations: 0 (default) coalesced 16-byte global loads into two register
+ * buffers; 1 = a per-warp shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier), two stages ahead. */
+int vggp_set_binned_stream(int mode);
 
 /*
  * Grid-side backward + ELBO assembly from the (all-reduced) gbuf.

@@ -31,10 +31,19 @@ def dev():
     return torch.device("cuda", 0)
 
 
+@pytest.fixture(params=[0, 1], ids=["ldg", "tma"])
+def stream_mode(request, vg):
+    """Both ways the binned kernel streams the observations (vggp_set_binned_stream)."""
+    lib = vg._lib.load()
+    lib.vggp_set_binned_stream(request.param)
+    yield request.param
+    lib.vggp_set_binned_stream(0)
+
+
 @pytest.mark.parametrize("run_cap", [8, 256])
 @pytest.mark.parametrize("knots,N", CASES)
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
-def test_binned_elbo_and_grads_match_oracle(vg, dev, knots, N, dtype, tol, run_cap):
+def test_binned_elbo_and_grads_match_oracle(vg, dev, knots, N, dtype, tol, run_cap, stream_mode):
     D = len(knots)
     meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=42 + D)
     Xq, yq = X.to(dtype), y.to(dtype)
@@ -63,7 +72,7 @@ def test_binned_elbo_and_grads_match_oracle(vg, dev, knots, N, dtype, tol, run_c
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-4)])
-def test_binned_and_packed_gradient_buffers_agree(vg, dev, dtype, tol):
+def test_binned_and_packed_gradient_buffers_agree(vg, dev, dtype, tol, stream_mode):
     """Same gbuf from both layouts (sum order differs): d alpha, band sums and the float64 scalars."""
     meshes, X, y, l, s2, noise, m, Ls = make_problem((40, 23), 30011, seed=9)
     plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)

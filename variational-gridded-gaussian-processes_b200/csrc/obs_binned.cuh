@@ -285,8 +285,9 @@ struct BinnedArgs {
     const unsigned char* buf;        // binned buffer (binplan.hpp: bin_offsets)
     i64 off_task_off, off_task_R, off_run_cell, off_run_n, off_data;
     int n_tasks;
-    int table_bytes, knots_byte_off;
-    const unsigned char* tables;     // [cell tables (T) | pad16 | knots (float) | pad16], staged by one TMA bulk copy
+    int knots_byte_off;
+    const unsigned char* tables;     // [cell tables (T) | pad16 | knots (float) | pad16] in global memory: touched once
+                                     // per run (enter / flush), never in the per-observation loop, so they stay in L2
     const T* alpha;
     T* galpha;
     T* gband;
@@ -296,6 +297,12 @@ struct BinnedArgs {
 };
 
 constexpr int BIN_THREADS = 128;
+constexpr int BIN_WARPS = BIN_THREADS / 32;
+constexpr int BIN_STAGES = 3;        // TMA ring: stages per warp
+constexpr int BIN_GPS = 2;           // groups (of 4 observations per lane) per stage
+
+template <typename T, int D>
+constexpr int bin_min_blocks() { return sizeof(T) == 4 ? (D == 3 ? 4 : 6) : (D == 1 ? 4 : 2); }
 
 // one group = 4 consecutive observations of this lane's run: (D + 1) 16-byte loads, 128 values apart
 template <typename T, int D>
@@ -303,6 +310,24 @@ __device__ __forceinline__ void bin_load_group(const T* p, T (&x)[D][4], T (&y)[
 #pragma unroll
     for (int d = 0; d < D; ++d) load4<T>(p + d * 128, x[d]);
     load4<T>(p + D * 128, y);
+}
+
+// the same group out of a shared-memory stage filled by a bulk copy (16-byte LDS, conflict-free: lane l reads bytes
+// [16 l, 16 l + 16) of every 128-value row)
+__device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void lds4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T, int D>
+__device__ __forceinline__ void bin_read_stage(const T* p, T (&x)[D][4], T (&y)[4]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) lds4(p + d * 128, x[d]);
+    lds4(p + D * 128, y);
 }
 
 // `left` = observations of the run not yet consumed (slots past it are padding)
@@ -317,65 +342,35 @@ __device__ __forceinline__ void bin_group(BinLane<T, D>& s, const T (&x)[D][4], 
     }
 }
 
+// what a warp needs to know about its task
 template <typename T, int D>
-__global__ void __launch_bounds__(BIN_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 6) : (D == 1 ? 4 : 2)))
-k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    const T* s_tab = reinterpret_cast<const T*>(smraw);
-    const float* s_knots = reinterpret_cast<const float*>(smraw + a.knots_byte_off);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ double red[32];
+struct BinTask {
+    const T* base;      // first value of this lane's first group
+    int groups, nrun;
+    bool valid;
+};
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)a.table_bytes);
-        bulk_g2s(smraw, a.tables, (uint32_t)a.table_bytes, &bar);
-    }
-    mbar_wait(&bar, 0);
+template <typename T, int D>
+__device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lane, BinLane<T, D>& s, BinTask<T, D>& t) {
+    unsigned int task = 0;
+    if (lane == 0) task = atomicAdd(a.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= (unsigned int)a.n_tasks) return false;
+    const i64 slot = (i64)task * 32 + lane;
+    const uint32_t cell = __ldg(reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell) + slot);
+    t.nrun = __ldg(reinterpret_cast<const int*>(a.buf + a.off_run_n) + slot);
+    t.groups = __ldg(reinterpret_cast<const int*>(a.buf + a.off_task_R) + task) >> 2;
+    t.base = reinterpret_cast<const T*>(a.buf + a.off_data) + __ldg(reinterpret_cast<const i64*>(a.buf + a.off_task_off) + task) + lane * 4;
+    t.valid = cell != BIN_EMPTY;
+    int c[D];
+    bin_decode_cell<D>(t.valid ? cell : 0u, a.geo.K, c);
+    bin_lane_enter<T, D>(a.geo, s, c, reinterpret_cast<const T*>(a.tables),
+                         reinterpret_cast<const float*>(a.tables + a.knots_byte_off), a.alpha);
+    return true;
+}
 
-    const int lane = threadIdx.x & 31;
-    const i64* task_off = reinterpret_cast<const i64*>(a.buf + a.off_task_off);
-    const int* task_R = reinterpret_cast<const int*>(a.buf + a.off_task_R);
-    const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell);
-    const int* run_n = reinterpret_cast<const int*>(a.buf + a.off_run_n);
-    const T* data = reinterpret_cast<const T*>(a.buf + a.off_data);
-    const AtomicAdder add;
-    double etot = 0.0;
-    BinLane<T, D> s;
-
-    // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
-    for (;;) {
-        unsigned int task = 0;
-        if (lane == 0) task = atomicAdd(a.counter, 1u);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= (unsigned int)a.n_tasks) break;
-        const i64 slot = (i64)task * 32 + lane;
-        const uint32_t cell = __ldg(run_cell + slot);
-        const int nrun = __ldg(run_n + slot);
-        const int groups = __ldg(task_R + task) >> 2;
-        const T* base = data + __ldg(task_off + task) + lane * 4;
-        const bool valid = cell != BIN_EMPTY;
-        int c[D];
-        bin_decode_cell<D>(valid ? cell : 0u, a.geo.K, c);
-        bin_lane_enter<T, D>(a.geo, s, c, s_tab, s_knots, a.alpha);
-
-        // two register buffers in ping-pong: the loads of the next group of 4 observations are in flight while the
-        // current one is processed (no buffer rotation: the loop body handles two groups)
-        T xa[D][4], ya[4], xb[D][4], yb[4];
-        bin_load_group<T, D>(base, xa, ya);
-#pragma unroll 1
-        for (int gi = 0; gi < groups; gi += 2) {
-            if (gi + 1 < groups) bin_load_group<T, D>(base + (i64)(gi + 1) * ((D + 1) * 128), xb, yb);
-            bin_group<T, D>(s, xa, ya, nrun - 4 * gi);
-            if (gi + 2 < groups) bin_load_group<T, D>(base + (i64)(gi + 2) * ((D + 1) * 128), xa, ya);
-            if (gi + 1 < groups) bin_group<T, D>(s, xb, yb, nrun - 4 * (gi + 1));
-        }
-        if (valid) etot += (double)bin_lane_flush<T, D>(a.geo, s, nrun, s_tab, a.galpha, a.gband, add);
-    }
+template <typename T, int D>
+__device__ __forceinline__ void bin_finish(const BinnedArgs<T, D>& a, double etot, double* red) {
     const double e = block_sum(etot, red);
     if (threadIdx.x == 0) {
         double extra = 0.0;
@@ -386,6 +381,107 @@ k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
         atomicAdd(a.gs + 0, e + extra);
     }
 }
+
+// Variant 0: the stream is read with coalesced 16-byte LDG.128 (evict-first) into two register buffers in ping-pong.
+template <typename T, int D>
+__global__ void __launch_bounds__(BIN_THREADS, (bin_min_blocks<T, D>()))
+k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31;
+    const AtomicAdder add;
+    double etot = 0.0;
+    BinLane<T, D> s;
+    BinTask<T, D> t;
+    // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
+    while (bin_next_task<T, D>(a, lane, s, t)) {
+        // the loads of the next group of 4 observations are in flight while the current one is processed (no buffer
+        // rotation: the loop body handles two groups)
+        T xa[D][4], ya[4], xb[D][4], yb[4];
+        bin_load_group<T, D>(t.base, xa, ya);
+#pragma unroll 1
+        for (int gi = 0; gi < t.groups; gi += 2) {
+            if (gi + 1 < t.groups) bin_load_group<T, D>(t.base + (i64)(gi + 1) * ((D + 1) * 128), xb, yb);
+            bin_group<T, D>(s, xa, ya, t.nrun - 4 * gi);
+            if (gi + 2 < t.groups) bin_load_group<T, D>(t.base + (i64)(gi + 2) * ((D + 1) * 128), xa, ya);
+            if (gi + 1 < t.groups) bin_group<T, D>(s, xb, yb, t.nrun - 4 * (gi + 1));
+        }
+        if (t.valid)
+            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, a.gband, add);
+    }
+    bin_finish<T, D>(a, etot, red);
+}
+
+// Variant 1: the stream is staged through shared memory by TMA.  Every warp owns a ring of BIN_STAGES stages of
+// BIN_GPS groups ((D + 1) x 512 B per group for float32) each; lane 0 issues one cp.async.bulk per stage,
+// BIN_STAGES - 1 stages ahead, each completing on the stage's mbarrier; the lanes wait on the barrier's phase and read
+// their 16 bytes per array and group with LDS.128 into registers.  The __syncwarp after the last read of a stage hands
+// it back to the producer, which refills it at the top of the next iteration.  Nothing but the ring lives in shared
+// memory, so the bytes in flight per SM (warps x (BIN_STAGES - 1) x BIN_GPS x 1.5 KB) do not depend on registers.
+template <typename T, int D>
+__global__ void __launch_bounds__(BIN_THREADS, (bin_min_blocks<T, D>()))
+k_obs_b1_binned_tma(const __grid_constant__ BinnedArgs<T, D> a) {
+    constexpr int GROUP_ELEMS = (D + 1) * 128;
+    constexpr int STAGE_ELEMS = BIN_GPS * GROUP_ELEMS;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) uint64_t full[BIN_WARPS][BIN_STAGES];
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* ring = reinterpret_cast<T*>(smraw) + (size_t)warp * BIN_STAGES * STAGE_ELEMS;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < BIN_STAGES; ++i) mbar_init(&full[warp][i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const AtomicAdder add;
+    double etot = 0.0;
+    BinLane<T, D> s;
+    BinTask<T, D> t;
+    unsigned int k0 = 0;                 // stages this warp has consumed so far: slot = k % STAGES, phase = (k / STAGES) & 1
+    while (bin_next_task<T, D>(a, lane, s, t)) {
+        const T* src = t.base - lane * 4;                    // the task's first group
+        const int nst = (t.groups + BIN_GPS - 1) / BIN_GPS;  // stages of this task (the last one may be partial)
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < BIN_STAGES - 1; ++i)
+                if (i < nst) {
+                    const unsigned int st = (k0 + i) % BIN_STAGES;
+                    const uint32_t bytes = (uint32_t)(min(BIN_GPS, t.groups - i * BIN_GPS) * GROUP_ELEMS * (int)sizeof(T));
+                    mbar_expect_tx(&full[warp][st], bytes);
+                    bulk_g2s(ring + (size_t)st * STAGE_ELEMS, src + (i64)i * STAGE_ELEMS, bytes, &full[warp][st]);
+                }
+        }
+#pragma unroll 1
+        for (int si = 0; si < nst; ++si) {
+            const unsigned int k = k0 + si, st = k % BIN_STAGES;
+            const int nx = si + BIN_STAGES - 1;
+            if (lane == 0 && nx < nst) {
+                // refill the slot consumed in the previous iteration (all lanes passed its __syncwarp)
+                const unsigned int sn = (k + BIN_STAGES - 1) % BIN_STAGES;
+                const uint32_t bytes = (uint32_t)(min(BIN_GPS, t.groups - nx * BIN_GPS) * GROUP_ELEMS * (int)sizeof(T));
+                mbar_expect_tx(&full[warp][sn], bytes);
+                bulk_g2s(ring + (size_t)sn * STAGE_ELEMS, src + (i64)nx * STAGE_ELEMS, bytes, &full[warp][sn]);
+            }
+            mbar_wait(&full[warp][st], (k / BIN_STAGES) & 1u);
+            const T* sp = ring + (size_t)st * STAGE_ELEMS + lane * 4;
+#pragma unroll
+            for (int g = 0; g < BIN_GPS; ++g) {
+                const int gi = si * BIN_GPS + g;
+                T x[D][4], y[4];
+                if (gi < t.groups) bin_read_stage<T, D>(sp + g * GROUP_ELEMS, x, y);
+                if (g == BIN_GPS - 1) __syncwarp();
+                if (gi < t.groups) bin_group<T, D>(s, x, y, t.nrun - 4 * gi);
+            }
+        }
+        k0 += (unsigned int)nst;
+        if (t.valid)
+            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, a.gband, add);
+    }
+    bin_finish<T, D>(a, etot, red);
+}
+
+template <typename T, int D>
+constexpr size_t bin_tma_smem_bytes() { return (size_t)BIN_WARPS * BIN_STAGES * BIN_GPS * (D + 1) * 128 * sizeof(T); }
 
 // ---- packing (one-time setup) ---------------------------------------------------------------------------
 

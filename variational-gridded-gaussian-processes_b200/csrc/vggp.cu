@@ -16,6 +16,7 @@ namespace vggp {
 thread_local char g_err[512] = {0};
 unsigned long long g_launches = 0;
 static int g_use_mma = 1;
+static int g_bin_stream = 0;       // binned K1: 0 = LDG.128 register ping-pong, 1 = TMA ring through shared memory
 static int g_b1_structured = 2;    // B1 family: 0 dense, 1 twisted inverse + GEMMs, 2 + semiseparable products
 
 struct Phase {
@@ -51,7 +52,7 @@ struct vggp_plan {
     void* pk_x[VGGP_MAX_D] = {nullptr, nullptr, nullptr}; void* pk_y = nullptr; i64 pk_cap = 0;
     // binned layout: the layout planned by vggp_obs_bin_prepare and the cell-sorted order, until vggp_obs_bin_pack
     BinLayout bin_pending; uint32_t* bin_perm = nullptr; bool bin_has_pending = false;
-    int bin_blocks_per_sm = 0;             // resident CTAs of k_obs_b1_binned (queried at first use)
+    int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
@@ -747,13 +748,17 @@ int bin_pack_impl(vggp_plan* p, const vggp_binned_desc* desc, const void* const*
 
 template <typename T, int D>
 int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
-    const size_t smem = obs_smem_bytes<T, D>(p);
-    if (p->bin_blocks_per_sm == 0) {
-        if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
-        VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_binned<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int mode = g_bin_stream ? 1 : 0;
+    const size_t smem = mode ? bin_tma_smem_bytes<T, D>() : 0;
+    if (p->bin_blocks_per_sm[mode] == 0) {
         int nb = 0;
-        VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, smem));
-        p->bin_blocks_per_sm = nb < 1 ? 1 : nb;
+        if (mode) {
+            VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_binned_tma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned_tma<T, D>, BIN_THREADS, smem));
+        } else {
+            VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, smem));
+        }
+        p->bin_blocks_per_sm[mode] = nb < 1 ? 1 : nb;
     }
     BinnedArgs<T, D> a;
     for (int d = 0; d < D; ++d) {
@@ -767,7 +772,6 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     a.off_task_off = desc->off_task_off; a.off_task_R = desc->off_task_R; a.off_run_cell = desc->off_run_cell;
     a.off_run_n = desc->off_run_n; a.off_data = desc->off_data;
     a.n_tasks = (int)desc->n_tasks;
-    a.table_bytes = p->table_bytes;
     a.knots_byte_off = p->knots_byte_off;
     a.tables = p->tables;
     a.alpha = reinterpret_cast<const T*>(p->alphaT);
@@ -780,9 +784,10 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     a.n_real = (double)desc->n;
     a.counter = p->obs_counter;
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
-    i64 blocks = (desc->n_tasks + (BIN_THREADS / 32) - 1) / (BIN_THREADS / 32);
-    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm));
-    k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, smem, st>>>(a);
+    i64 blocks = (desc->n_tasks + BIN_WARPS - 1) / BIN_WARPS;
+    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[mode]));
+    if (mode) k_obs_b1_binned_tma<T, D><<<(unsigned)blocks, BIN_THREADS, smem, st>>>(a);
+    else k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -808,6 +813,11 @@ uint64_t vggp_launch_count(void) { return (uint64_t)g_launches; }
 
 int vggp_set_gemm_mode(int use_mma) {
     g_use_mma = use_mma ? 1 : 0;
+    return 0;
+}
+
+int vggp_set_binned_stream(int mode) {
+    g_bin_stream = mode ? 1 : 0;
     return 0;
 }
 
