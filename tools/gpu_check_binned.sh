@@ -1,0 +1,58 @@
+#!/usr/bin/env bash
+# One gpurun call (1 GPU, no ncu) that decides whether the binned K1 path can become the default:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_check_binned.sh'
+# Every step runs under its own `timeout` (a hung kernel must not eat the call) and writes into gpurun_out/.
+# Read gpurun_out/binned_summary.txt afterwards.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out
+mkdir -p "$OUT"
+SUM="$OUT/binned_summary.txt"
+: > "$SUM"
+note() { echo "$*" | tee -a "$SUM"; }
+
+note "== 1. default GPU suite (packed kernel, the verified path)"
+timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/pytest_default.log" 2>&1
+note "   rc=$? $(tail -n 1 "$OUT/pytest_default.log")"
+
+note "== 2. binned path, LDG stream first (tests are parametrised ldg/tma; -k ldg isolates a TMA hang)"
+VGGP_TEST_BINNED=1 timeout 600 python -m pytest tests/test_gpu_binned.py -m gpu -x -q -k "ldg or not tma" > "$OUT/pytest_binned_ldg.log" 2>&1
+RC_LDG=$?
+note "   rc=$RC_LDG $(tail -n 1 "$OUT/pytest_binned_ldg.log")"
+VGGP_TEST_BINNED=1 timeout 600 python -m pytest tests/test_gpu_binned.py -m gpu -x -q -k "tma" > "$OUT/pytest_binned_tma.log" 2>&1
+RC_TMA=$?
+note "   tma rc=$RC_TMA $(tail -n 1 "$OUT/pytest_binned_tma.log")"
+
+bench() {   # name, extra args...
+    local name=$1; shift
+    timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline "$@" > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
+    local rc=$?
+    python - "$OUT/bench_$name.json" "$name" "$rc" <<'PY' | tee -a "$SUM"
+import json, sys
+path, name, rc = sys.argv[1:4]
+line = None
+for l in open(path):
+    if l.startswith("{"):
+        line = json.loads(l)
+if line is None:
+    print(f"   {name:28s} rc={rc} no JSON line")
+else:
+    r = line["roofline"]
+    print(f"   {name:28s} rc={rc} ms/step {line['ms_per_step']:.4f}  K1 {r['kernel_ms']:.4f} ms  "
+          f"{r['achieved']:.0f} GB/s  frac {r['frac']:.3f}  elbo {line['elbo']:.6e}")
+PY
+}
+
+note "== 3. bench A/B at the headline config (N = 2^26, 512 x 512), kernels only"
+bench packed
+if [ "$RC_LDG" = 0 ]; then
+    for cap in 128 256 512; do bench "binned_ldg_cap$cap" --obs-layout binned --binned-stream ldg --run-cap $cap; done
+fi
+if [ "$RC_TMA" = 0 ]; then
+    for cap in 128 256 512; do bench "binned_tma_cap$cap" --obs-layout binned --binned-stream tma --run-cap $cap; done
+fi
+note "== 4. thin shard (what one of 8 GPUs sees): N = 2^23"
+bench packed_n8m --n-obs 8388608
+[ "$RC_LDG" = 0 ] && bench binned_ldg_n8m --n-obs 8388608 --obs-layout binned --binned-stream ldg
+[ "$RC_TMA" = 0 ] && bench binned_tma_n8m --n-obs 8388608 --obs-layout binned --binned-stream tma
+note "done"
