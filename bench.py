@@ -540,7 +540,8 @@ def main():
                     "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
                               "(X is constant over optimisation steps); setup is outside the timed region"}
                    if args.obs_layout == "packed" else
-                   {"binned_stream": args.binned_stream, "run_cap": packed.run_cap, "n_runs": packed.n_runs, "n_tasks": packed.n_tasks,
+                   {"binned_stream": args.binned_stream, "run_cap": packed.run_cap, "n_runs": packed.n_runs,
+                    "n_tasks": packed.n_tasks,
                     "streamed_bytes": packed.streamed_bytes,
                     "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
                               "setup; setup is outside the timed region"}),

@@ -9,6 +9,7 @@ per-observation kernel; at the optimal q(u) the two bounds coincide (tests/test_
 Training-loop API kept from the notebooks (5_gridded_kronecker_structure_models.ipynb:438-446):
     opt = torch.optim.Adam(model.parameters()); loss = -model._elbo(); loss.backward(); opt.step()
 """
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -109,7 +110,12 @@ class GriddedVariationalGP(nn.Module):
             self._obs = (xs, y)
             # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant); the packed
             # layout belongs to the compact-stencil (B1) kernel, the dense-feature (B0) kernel streams plain arrays
-            self._packed = self._plan.pack(xs, y, sort_by_cell=True) if self.family == _lib.B1_ASVGP else None
+            if self.family != _lib.B1_ASVGP:
+                self._packed = None
+            elif os.environ.get("VGGP_OBS_LAYOUT", "packed") == "binned":     # opt-in, DESIGN.md section 8
+                self._packed = self._plan.bin(xs, y)
+            else:
+                self._packed = self._plan.pack(xs, y, sort_by_cell=True)
         return self._plan
 
     # ---- the hot path ---------------------------------------------------------------------------------------
