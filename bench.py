@@ -337,6 +337,8 @@ def main():
     ap.add_argument("--binned-stream", default="ldg", choices=["ldg", "tma"],
                     help="binned layout: 16-byte global loads into registers, or a per-warp shared-memory ring "
                          "filled by TMA bulk copies (vggp_set_binned_stream)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the step from CUDA graphs (the all-reduce stays outside the graphs); opt-in")
     ap.add_argument("--spatial-reshard", action="store_true",
                     help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
                          "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
@@ -412,6 +414,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    launches_per_step = None
+    if args.cuda_graph:
+        c0 = lib.vggp_launch_count()
+        step()
+        launches_per_step = lib.vggp_launch_count() - c0      # kernels of this library in one step (replayed by the graphs)
+        graphed = plan.graphed_step(theta_d, m_d, L_d, packed, None, 1.0, group)
+        plain_step = step
+
+        def step(i=None, obs=None):          # noqa: F811  (the graphs hold the cell-sorted observations)
+            if obs is not None:
+                return plain_step(i, obs)
+            return graphed.replay()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -446,8 +462,18 @@ def main():
     t_end.record()
     barrier()
     launches = lib.vggp_launch_count() - launches0
+    if graphed is not None:
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
+    if graphed is not None:
+        # events cannot be recorded inside a replayed graph: time the per-observation kernel in a separate loop
+        torch.cuda.synchronize()
+        for i in range(args.steps):
+            ev_a[i].record()
+            plan.obs_fwd_bwd(packed)
+            ev_b[i].record()
+        torch.cuda.synchronize()
     k1_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps
     tt = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -545,7 +571,7 @@ def main():
                     "streamed_bytes": packed.streamed_bytes,
                     "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
                               "setup; setup is outside the timed region"}),
-                "setup_ms": setup_ms,
+                "setup_ms": setup_ms, "cuda_graph": bool(args.cuda_graph),
                 "acquisition_order": {"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
                                       "note": "same step without the cell binning (along-track order kept)"}}),
             "elbo": out[0][0].item(),

@@ -45,6 +45,7 @@ PY
 
 note "== 3. bench A/B at the headline config (N = 2^26, 512 x 512), kernels only"
 bench packed
+bench packed_graph --cuda-graph
 if [ "$RC_LDG" = 0 ]; then
     for cap in 128 256 512; do bench "binned_ldg_cap$cap" --obs-layout binned --binned-stream ldg --run-cap $cap; done
 fi

@@ -197,6 +197,31 @@ class GridPlan:
             self.allreduce_gbuf(None if isinstance(group, str) else group)
         return self.grid_backward(theta, m, L, ell_scale)
 
+    def graphed_step(self, theta, m, L, xs, y=None, ell_scale: float = 1.0, group=None, warmup: int = 3):
+        """Capture the C-ABI launches of one step into CUDA graphs (opt-in; removes the launch gaps between the ~15
+        small kernels).  `theta`, `m`, `L` and the observations are STATIC device buffers: write new parameter values
+        into them (copy_) and call `.replay()`.  The all-reduce is NOT captured -- a round-1 run with NCCL inside the
+        graph did not shut down cleanly -- so a sharded step is two graphs around one eager all-reduce."""
+        gs = GraphedStep(self, group)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(theta, m, L, xs, y, ell_scale, group)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        gs.front = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gs.front):
+            self.grid_forward(theta, m, L)
+            self.obs_fwd_bwd(xs, y)
+            if group is None:
+                gs.outs = self.grid_backward(theta, m, L, ell_scale)
+        if group is not None:
+            gs.back = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gs.back):
+                gs.outs = self.grid_backward(theta, m, L, ell_scale)
+        return gs
+
     def read_info(self) -> int:
         info = C.c_int(0)
         _lib.check(self.lib.vggp_read_info(self.handle, C.byref(info), _stream_ptr(self.device)))
@@ -252,6 +277,23 @@ class PackedObs:
 
     def numel(self) -> int:
         return self.n
+
+
+class GraphedStep:
+    """One step as CUDA graph replays (GridPlan.graphed_step).  `.replay()` returns (out, dtheta, dm, dL); the tensors
+    are overwritten by every replay."""
+
+    def __init__(self, plan: "GridPlan", group):
+        self.plan, self.group = plan, group
+        self.front = self.back = None
+        self.outs = None
+
+    def replay(self):
+        self.front.replay()
+        if self.group is not None:
+            self.plan.allreduce_gbuf(None if isinstance(self.group, str) else self.group)
+            self.back.replay()
+        return self.outs
 
 
 class BinnedObs:
