@@ -1,0 +1,118 @@
+// TEST INFRASTRUCTURE ONLY -- a minimal SIMT emulator that lets g++ compile and run the library's CUDA kernels on the
+// CPU (found as <cuda_runtime.h> through -I when tests/host_emul is built; nvcc never sees this file).
+//
+// One kernel launch = blocks run one after the other; the threads of a block are ucontext fibres on ONE OS thread,
+// switched cooperatively at every synchronising primitive (__syncthreads, __syncwarp, warp shuffles, mbarrier waits,
+// atomics).  `__shared__` is `thread_local` (= one copy, shared by all fibres; dynamic shared memory is a
+// thread_local array defined in emul_device.cpp).  Bulk async copies (TMA) are queued and completed LATE, at random
+// scheduling points, so that reading a stage before its barrier completed, or refilling it before it was consumed,
+// corrupts the result.  This checks indexing, protocols and arithmetic of device code; it says nothing about memory
+// ordering or performance.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#define VGGP_EMUL 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ thread_local
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+using std::min;
+using std::max;
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+
+struct uint3 { unsigned int x, y, z; };
+struct dim3 {
+    unsigned int x, y, z;
+    dim3(unsigned int a = 1, unsigned int b = 1, unsigned int c = 1) : x(a), y(b), z(c) {}
+};
+struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
+struct double2 { double x, y; } __attribute__((aligned(16)));
+
+namespace cuda_emul {
+extern uint3 threadIdx_, blockIdx_;
+extern dim3 blockDim_, gridDim_;
+void yield();                                       // give the other fibres of the block a turn
+void sync_block();                                  // __syncthreads
+void sync_warp();                                   // all live lanes of the calling warp
+uint64_t* warp_slots();                             // 32 exchange slots of the calling warp
+int lane_id();
+void launch(dim3 grid, dim3 block, const std::function<void()>& kernel_body);
+void bulk_copy_async(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
+unsigned long long yields();
+}  // namespace cuda_emul
+
+#define threadIdx (cuda_emul::threadIdx_)
+#define blockIdx (cuda_emul::blockIdx_)
+#define blockDim (cuda_emul::blockDim_)
+#define gridDim (cuda_emul::gridDim_)
+
+inline void __syncthreads() { cuda_emul::sync_block(); }
+inline void __syncwarp(unsigned int = 0xffffffffu) { cuda_emul::sync_warp(); }
+
+template <typename T>
+inline T __shfl_sync(unsigned int, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of <= 8 bytes");
+    uint64_t* s = cuda_emul::warp_slots();
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    s[cuda_emul::lane_id()] = raw;
+    cuda_emul::sync_warp();
+    raw = s[src & 31];
+    cuda_emul::sync_warp();
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned int m, T v, int mask) { return __shfl_sync(m, v, cuda_emul::lane_id() ^ mask); }
+
+// atomics: fibres are cooperative, so a plain read-modify-write is atomic; yield afterwards to shuffle the order
+template <typename T>
+inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; cuda_emul::yield(); return o; }
+template <typename T>
+inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; cuda_emul::yield(); return o; }
+
+template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
+inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+inline double __longlong_as_double(long long v) { double f; memcpy(&f, &v, 8); return f; }
+
+// CPU stand-ins for the PTX wrappers of csrc/obs.cuh (mbarrier + bulk async copy).  The barrier word keeps the parity
+// of the phase in progress in bit 0 and the transaction bytes announced by expect_tx above bit 8; a queued copy
+// completes (memcpy + parity flip) at a random later scheduling point and must match the announced byte count.
+namespace vggp {
+inline void mbar_init(uint64_t* bar, int) { *bar = 0; }
+inline void fence_mbar_init() {}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    if (*bar >> 8) { fprintf(stderr, "cuda_emul: mbarrier re-armed while a copy is pending\n"); abort(); }
+    *bar = (*bar & 1ull) | ((uint64_t)bytes << 8);
+}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if ((*bar >> 8) != bytes || (bytes & 15u) || ((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) {
+        fprintf(stderr, "cuda_emul: bulk copy of %u bytes: size / alignment / expect_tx mismatch\n", bytes);
+        abort();
+    }
+    cuda_emul::bulk_copy_async(dst, src, bytes, bar);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((*bar & 1ull) == (uint64_t)parity) cuda_emul::yield();
+}
+}  // namespace vggp

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(256) k_pack_gather(const __grid_constant__ Gat
 // TMA (bulk async copy) helpers: the per-CTA tables (band tables of P_d, Q_d and the knots) are staged into
 // shared memory with one cp.async.bulk completing on an mbarrier.
 // ---------------------------------------------------------------------------------------------------------
+#ifndef VGGP_EMUL   // tests/host_emul supplies CPU stand-ins for these six PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -244,6 +245,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "memory");
     } while (!ok);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: fused per-observation ELBO forward + backward, B1 (ASVGP) family, packed layout.

@@ -269,7 +269,7 @@ VGGP_HD int64_t bin_elem_of(int arr, int lane, int j, int D) {
 // ---------------------------------------------------------------------------------------------------------
 // Device side
 // ---------------------------------------------------------------------------------------------------------
-#if defined(__CUDACC__) && !defined(VGGP_HOST_EMUL)
+#if (defined(__CUDACC__) || defined(VGGP_EMUL)) && !defined(VGGP_HOST_EMUL)   // VGGP_EMUL: tests/host_emul SIMT emulator
 #include "obs.cuh"
 
 namespace vggp {
