@@ -38,6 +38,32 @@ enum { cudaSuccess = 0 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 
+// ---- host runtime API: "device" memory is host memory, streams are synchronous ----
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+struct cudaDeviceProp { int multiProcessorCount; };
+template <typename P>
+inline cudaError_t cudaMalloc(P** p, size_t bytes) {
+    void* q = nullptr;
+    if (posix_memalign(&q, 256, bytes ? bytes : 256)) return 2;
+    memset(q, 0xCD, bytes);                      // poison: reading memory the library never wrote shows up
+    *p = reinterpret_cast<P*>(q);
+    return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 3; return cudaSuccess; }
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int bytes) { return bytes <= 227 * 1024 ? cudaSuccess : 1; }
+template <typename F>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
+
 struct uint3 { unsigned int x, y, z; };
 struct dim3 {
     unsigned int x, y, z;
@@ -56,6 +82,9 @@ uint64_t* warp_slots();                             // 32 exchange slots of the 
 int lane_id();
 void launch(dim3 grid, dim3 block, const std::function<void()>& kernel_body);
 void bulk_copy_async(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
+void cp_async_enqueue(void* dst, const void* src, int bytes, int src_bytes);   // per-thread cp.async queue
+void cp_async_commit_group();
+void cp_async_wait_group(int newest_groups_left_pending);
 unsigned long long yields();
 }  // namespace cuda_emul
 
@@ -115,4 +144,33 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((*bar & 1ull) == (uint64_t)parity) cuda_emul::yield();
 }
+}  // namespace vggp
+
+// CPU stand-ins for the PTX wrappers of csrc/gemm.cuh.
+namespace vggp {
+// mma.sync.aligned.m8n8k4.row.col.f64: lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2 (l%4) + {0,1}]
+inline void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    uint64_t* s = cuda_emul::warp_slots();
+    const int lane = cuda_emul::lane_id();
+    double A[32], B[32];
+    memcpy(&s[lane], &a, 8);
+    cuda_emul::sync_warp();
+    memcpy(A, s, sizeof(A));
+    cuda_emul::sync_warp();
+    memcpy(&s[lane], &b, 8);
+    cuda_emul::sync_warp();
+    memcpy(B, s, sizeof(B));
+    cuda_emul::sync_warp();
+    const int row = lane >> 2, col = (lane & 3) * 2;
+    for (int k = 0; k < 4; ++k) {
+        c0 = fma(A[row * 4 + k], B[col * 4 + k], c0);
+        c1 = fma(A[row * 4 + k], B[(col + 1) * 4 + k], c1);
+    }
+}
+// cp.async: the copy is DEFERRED until the group it belongs to is waited for (a missing wait reads stale data)
+inline void cp_async16(void* dst, const void* src, int src_bytes) { cuda_emul::cp_async_enqueue(dst, src, 16, src_bytes); }
+inline void cp_async8(void* dst, const void* src, int src_bytes) { cuda_emul::cp_async_enqueue(dst, src, 8, src_bytes); }
+inline void cp_async_commit() { cuda_emul::cp_async_commit_group(); }
+template <int N>
+inline void cp_async_wait() { cuda_emul::cp_async_wait_group(N); }
 }  // namespace vggp

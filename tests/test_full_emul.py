@@ -1,0 +1,150 @@
+"""The whole C ABI on the CPU under the SIMT emulator (tests/emul_lib.py, tests/host_emul): csrc/vggp.cu with its 45
+kernel launches rewritten, every kernel of csrc/*.cuh compiled unchanged by g++.  The same oracle parity checks the GPU
+suite makes (tests/test_gpu_elbo.py) are made here at small sizes.  Two purposes:
+  * the emulator is validated on the paths that passed on B200 (raw / packed layouts, structured and dense factor paths,
+    DMMA and SIMT GEMMs, B0 family);
+  * the paths that have NOT run on a GPU yet -- the binned layout end to end through vggp_obs_bin_prepare / _pack /
+    vggp_obs_fwd_bwd_binned, both streaming variants -- get the same parity check before their first GPU run.
+Test infrastructure only; the product library has no CPU path."""
+import numpy as np
+import pytest
+import torch
+
+import emul_lib
+from oracle import vggp_oracle as O
+from test_gpu_elbo import make_problem, oracle_value_and_grads
+
+
+@pytest.fixture(scope="module")
+def emu():
+    got = emul_lib.load()
+    if got is None:
+        pytest.skip("g++ not available")
+    return got
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = b.detach().cpu().to(torch.float64).reshape(-1).numpy()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, tol):
+    D = plan.D
+    assert plan.read_info() == 0
+    assert out[3] == N
+    assert abs(out[0] - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (out, elbo_ref)
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10
+    assert relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10
+    assert relerr(dm, g_ref[3]) < tol * 10
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n)
+        off += n * n
+        assert np.count_nonzero(np.triu(dLd, 1)) == 0
+        assert relerr(np.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
+
+
+B1_CASES = [((12,), 500), ((9, 7), 700), ((6, 14, 5), 900)]
+LAYOUTS = ["raw", "packed_sorted", "packed_unsorted", "binned_ldg", "binned_tma"]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("knots,N", B1_CASES)
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-3)])
+def test_b1_step_matches_oracle_under_emulation(emu, knots, N, dtype, tol, layout):
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=42 + D)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq, yq = X.to(tdt), y.to(tdt)
+    scale = 1.7
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], dtype)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    mm = m.numpy().copy()
+    Lcat = torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    yy = np.ascontiguousarray(yq.numpy())
+    lib.vggp_set_binned_stream(1 if layout == "binned_tma" else 0)
+    try:
+        if layout == "raw":
+            out, dtheta, dm, dL = plan.step(theta, mm, Lcat, xs, yy, ell_scale=scale)
+        elif layout.startswith("packed"):
+            out, dtheta, dm, dL = plan.step(theta, mm, Lcat, plan.pack(xs, yy, layout == "packed_sorted"), None, scale)
+        else:
+            binned = plan.bin(xs, yy, run_cap=16)
+            assert binned[2].n == N and binned[2].n_tasks == (binned[2].n_runs + 31) // 32
+            out, dtheta, dm, dL = plan.step(theta, mm, Lcat, binned, None, scale)
+        check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, tol)
+    finally:
+        lib.vggp_set_binned_stream(0)
+        plan.close()
+
+
+@pytest.mark.parametrize("structured", [0, 1])
+def test_dense_factor_paths_under_emulation(emu, structured):
+    """B1 family through the dense Cholesky + GEMM path (0) and the twisted inverse + GEMM products (1): grouped DMMA
+    GEMMs (mma.m8n8k4 and cp.async stand-ins) on the CPU."""
+    lib, L = emu
+    knots, N = (10, 8), 600
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls, scale=1.0)
+    lib.vggp_set_b1_structured(structured)
+    try:
+        plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+    finally:
+        lib.vggp_set_b1_structured(2)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    xs, y.numpy().copy(), 1.0)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, 1e-9)
+    plan.close()
+
+
+@pytest.mark.parametrize("knots,N", [((11,), 300), ((8, 7), 300)])
+def test_b0_family_under_emulation(emu, knots, N):
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=3, family=O.B0_GRIDDED)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes, X, y, l, s2, noise, m, Ls, scale=1.0)
+    plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, [t.numpy() for t in meshes], np.float64)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    xs, y.numpy().copy(), 1.0)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, 1e-8)
+    plan.close()
+
+
+def test_binned_abi_edge_cases_under_emulation(emu):
+    lib, L = emu
+    meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, meshes, np.float64)
+    rng = np.random.default_rng(0)
+    theta = np.array([0.3, 0.4, 1.0, 0.9, 0.05])
+    m = 0.1 * rng.standard_normal(63)
+    Lcat = np.concatenate([np.eye(n).reshape(-1) for n in (9, 7)])
+    empty = [np.zeros(0), np.zeros(0)]
+    out_b, *_ = plan.step(theta, m, Lcat, plan.bin(empty, np.zeros(0)), None, 1.0)
+    out_r, *_ = plan.step(theta, m, Lcat, empty, np.zeros(0), 1.0)
+    assert out_b[3] == 0 and np.allclose(out_b, out_r, rtol=1e-12, atol=0)
+    xo = [np.full(50, 3.0), rng.random(50)]
+    yo = rng.standard_normal(50)
+    b1 = plan.bin(xo, yo)
+    assert b1[2].n_tasks == 0 and b1[2].n_inside == 0
+    out_b, dth_b, dm_b, _ = plan.step(theta, m, Lcat, b1, None, 1.0)
+    out_r, dth_r, dm_r, _ = plan.step(theta, m, Lcat, xo, yo, 1.0)
+    assert np.allclose(out_b, out_r, rtol=1e-12) and np.allclose(dth_b, dth_r, rtol=1e-10) and np.allclose(dm_b, dm_r)
+    # a descriptor from another prepare is refused
+    d1 = plan.bin([rng.random(40), rng.random(40)], rng.standard_normal(40))[2]
+    desc = L.BinnedDesc()
+    import ctypes as C
+    xs = [rng.random(30), rng.random(30)]
+    plan.check(lib.vggp_obs_bin_prepare(plan.h, plan._xptrs(xs), 30, 16, C.byref(desc), None))
+    buf = np.zeros(int(d1.bytes) + 512, dtype=np.uint8)
+    assert lib.vggp_obs_bin_pack(plan.h, C.byref(d1), plan._xptrs(xs), emul_lib.ptr(rng.standard_normal(30)), emul_lib.ptr(buf), None) == -1      # VGGP_E_ARG
+    plan.close()

@@ -35,11 +35,13 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 constexpr int GEMM_THREADS_MMA = 256, GEMM_THREADS_SIMT = 256;
 constexpr int GEMM_NI = 2;      // DMMA path: 8 warps as 2 (m) x 4 (n), each 32 x 16 = 4 x 2 tiles of m8n8
 
+#ifndef VGGP_EMUL   // tests/host_emul supplies a CPU stand-in
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+#endif
 
 __device__ __forceinline__ void gemm_store(const GemmDesc& d, double* __restrict__ Cb, int row, int col, double v) {
     if (row >= d.m || col >= d.n) return;
@@ -175,6 +177,7 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GF_STAGE = 2560;     // doubles per stage: A 1280 + B 1280
 
+#ifndef VGGP_EMUL   // tests/host_emul supplies CPU stand-ins
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes));
 }
@@ -184,6 +187,7 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_by
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
 
 // Stage one operand tile.  `kc`: the k index is the contiguous one.  Rows of the tile run along the other index.
 //   kc  : 64 rows (mn) x 16 (k),  global (mn, k) at base + mn * ld + k
