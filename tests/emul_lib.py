@@ -140,6 +140,25 @@ class EmuPlan:
         self.obs_fwd_bwd(obs, y)
         return self.grid_backward(theta, m, Lcat, ell_scale)
 
+    def b1_stencil(self, dim, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        c = np.zeros(x.size, dtype=np.int32)
+        wl, wh = np.zeros_like(x), np.zeros_like(x)
+        self.check(self.lib.vggp_b1_stencil(self.h, dim, ptr(x), x.size, ptr(c), ptr(wl), ptr(wh), None))
+        return c, wl, wh
+
+    def features_dense(self, dim, x, theta=None):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        phi = np.zeros((self.m_per_dim[dim], x.size), dtype=self.dtype)
+        self.check(self.lib.vggp_features_dense(self.h, dim, ptr(x), x.size, ptr(theta), ptr(phi), None))
+        return phi
+
+    def predict(self, xs):
+        xs = [np.ascontiguousarray(x, dtype=self.dtype) for x in xs]
+        mean, var = np.zeros_like(xs[0]), np.zeros_like(xs[0])
+        self.check(self.lib.vggp_predict(self.h, self._xptrs(xs), xs[0].size, ptr(mean), ptr(var), None))
+        return mean, var
+
     def read_info(self):
         info = C.c_int(0)
         self.check(self.lib.vggp_read_info(self.h, C.byref(info), None))

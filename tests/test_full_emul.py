@@ -120,6 +120,53 @@ def test_b0_family_under_emulation(emu, knots, N):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["lin11_01", "lin129_01", "lin16_02", "lin21_m3_7", "padded21_pad2"])
+@pytest.mark.parametrize("tag,dtype", [("f64", np.float64), ("f32", np.float32)])
+def test_b1_stencil_kernel_bit_exact_vs_reference_golden(emu, golden_dir, name, tag, dtype):
+    """k_b1_stencil / k_b1_dense (emulated with -ffp-contract=off, IEEE float arithmetic) against the fixtures produced by
+    the reference's own bspline.py: identical cell index and identical weight bits."""
+    import os
+    lib, L = emu
+    sten = np.load(os.path.join(golden_dir, "b1_stencil.npz"))
+    mesh, x, phi_ref = sten[f"{name}.{tag}.mesh"], sten[f"{name}.{tag}.x"], sten[f"{name}.{tag}.phi"]
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [mesh], dtype)
+    phi = plan.features_dense(0, x)
+    assert phi.dtype == phi_ref.dtype and np.array_equal(phi, phi_ref)
+    c, wl, wh = plan.b1_stencil(0, x)
+    co, wlo, who = O.b1_stencil(torch.from_numpy(mesh), torch.from_numpy(x))
+    assert np.array_equal(c.astype(np.int64), co.numpy())
+    assert np.array_equal(wl, wlo.numpy()) and np.array_equal(wh, who.numpy())
+    plan.close()
+
+
+def test_point_prediction_under_emulation(emu):
+    """k_predict_b1 against the dense formulas mean = phi^T alpha, var = kff - phi^T P phi + phi^T Q phi built from the
+    workspace-independent oracle pieces."""
+    lib, L = emu
+    knots, N = (9, 7), 400
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=8)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    plan.grid_forward(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy())
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
+    mean, var = plan.predict(xs)
+    Ks = [O.kuu_factor(O.B1_ASVGP, meshes[d], l[d], s2[d], ref_quirks=False) for d in range(2)]
+    Ps = [torch.linalg.inv(K) for K in Ks]
+    Ss = [torch.tril(Lx) @ torch.tril(Lx).T for Lx in Ls]
+    Qs = [P @ S @ P for P, S in zip(Ps, Ss)]
+    alpha = (Ps[0] @ m.reshape(9, 7) @ Ps[1].T)
+    phis = [O.b1_features_dense(meshes[d], X[:, d]) for d in range(2)]          # (M_d, N)
+    mu_ref = torch.einsum("in,ij,jn->n", phis[0], alpha, phis[1])
+    p = [torch.einsum("in,ij,jn->n", phis[d], Ps[d], phis[d]) for d in range(2)]
+    q = [torch.einsum("in,ij,jn->n", phis[d], Qs[d], phis[d]) for d in range(2)]
+    inside = (phis[0].sum(0) > 0) & (phis[1].sum(0) > 0)
+    var_ref = torch.where(inside, s2[0] * s2[1] - p[0] * p[1] + q[0] * q[1], s2[0] * s2[1])
+    mu_ref = torch.where(inside, mu_ref, torch.zeros_like(mu_ref))
+    assert np.allclose(mean, mu_ref.numpy(), rtol=1e-9, atol=1e-11)
+    assert np.allclose(var, var_ref.numpy(), rtol=1e-9, atol=1e-11)
+    plan.close()
+
+
 def test_binned_abi_edge_cases_under_emulation(emu):
     lib, L = emu
     meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]
