@@ -84,6 +84,31 @@ def test_b1_step_matches_oracle_under_emulation(emu, knots, N, dtype, tol, layou
         plan.close()
 
 
+@pytest.mark.parametrize("layout", ["packed_sorted", "binned_ldg"])
+def test_two_wave_run_length_under_emulation(emu, layout):
+    """Enough observations that the packed layout needs two waves of chunks per resident warp (the emulated device
+    has 24 resident warps): run length and chunk count come out balanced, and the step still matches the oracle."""
+    import ctypes as C
+    lib, L = emu
+    knots, N = (33,), 420000
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=17)
+    Xq, yq = X.to(torch.float32), y.to(torch.float32)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=1.0)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float32)
+    npk, run = C.c_int64(), C.c_int()
+    plan.check(lib.vggp_obs_pack_geometry(plan.h, N, C.byref(npk), C.byref(run)))
+    chunks = npk.value // (32 * run.value)
+    assert run.value % 4 == 0 and run.value < 512 and 44 <= chunks <= 48          # just below 2 x 24 warps
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, 0].numpy())]
+    yy = np.ascontiguousarray(yq.numpy())
+    obs = plan.pack(xs, yy, True) if layout == "packed_sorted" else plan.bin(xs, yy, run_cap=256)
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), Ls[0].reshape(-1).numpy().copy(), obs, None, 1.0)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, 1e-3)
+    plan.close()
+
+
 @pytest.mark.parametrize("structured", [0, 1])
 def test_dense_factor_paths_under_emulation(emu, structured):
     """B1 family through the dense Cholesky + GEMM path (0) and the twisted inverse + GEMM products (1): grouped DMMA
