@@ -224,6 +224,18 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
  */
 int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, void* var, void* stream);
 
+/*
+ * Evaluation metrics of the reference (src/utils/evaluationmetrics.py:6-54) as one fused reduction.  `out` (DEVICE,
+ * 4 float64, zeroed by the call) receives the raw sums
+ *     { sum (t - p)^2,  sum |t - p|,  sum (t - t_0),  sum (t - t_0)^2 }       t_0 = truth[0]
+ * from which MSE = out0/n, MAE = out1/n, RMSE = sqrt(MSE), R^2 = 1 - out0 / (out3 - out2^2/n).
+ *   vggp_metrics          truth, pred: n values of `dtype` (VGGP_F32 | VGGP_F64) each
+ *   vggp_predict_metrics  the same sums for pred = posterior mean at the test points x[D] (state of the last
+ *                         vggp_grid_forward, B1 family), without writing the predictions to memory
+ */
+int vggp_metrics(int dtype, const void* truth, const void* pred, int64_t n, double* out, void* stream);
+int vggp_predict_metrics(vggp_plan* plan, const void* const* x, const void* y, int64_t n, double* out, void* stream);
+
 /* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
 
 /* Device pointer to a float64 workspace array of the last forward.  which: */

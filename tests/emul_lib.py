@@ -159,6 +159,13 @@ class EmuPlan:
         self.check(self.lib.vggp_predict(self.h, self._xptrs(xs), xs[0].size, ptr(mean), ptr(var), None))
         return mean, var
 
+    def predict_metrics(self, xs, y):
+        xs = [np.ascontiguousarray(x, dtype=self.dtype) for x in xs]
+        y = np.ascontiguousarray(y, dtype=self.dtype)
+        out = np.full(4, np.nan)
+        self.check(self.lib.vggp_predict_metrics(self.h, self._xptrs(xs), ptr(y), y.size, ptr(out), None))
+        return out
+
     def read_info(self):
         info = C.c_int(0)
         self.check(self.lib.vggp_read_info(self.h, C.byref(info), None))

@@ -192,6 +192,40 @@ def test_point_prediction_under_emulation(emu):
     plan.close()
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_metrics_kernels_under_emulation(emu, dtype, tol):
+    """vggp_metrics / vggp_predict_metrics against the reference's formulas (src/utils/evaluationmetrics.py:6-54)."""
+    lib, L = emu
+    rng = np.random.default_rng(1)
+    n = 7001
+    t = (50.0 + rng.standard_normal(n)).astype(dtype)             # large mean: the pivoted one-pass TSS must not cancel
+    p = (t + 0.3 * rng.standard_normal(n)).astype(dtype)
+    out = np.full(4, np.nan)
+    assert lib.vggp_metrics(L.F32 if dtype == np.float32 else L.F64, emul_lib.ptr(t), emul_lib.ptr(p), n, emul_lib.ptr(out), None) == 0
+    t64, p64 = t.astype(np.float64), p.astype(np.float64)
+    mse = np.mean((t64 - p64) ** 2)
+    mae = np.mean(np.abs(t64 - p64))
+    r2 = 1 - np.sum((t64 - p64) ** 2) / np.sum((t64 - t64.mean()) ** 2)
+    assert abs(out[0] / n - mse) <= tol * mse and abs(out[1] / n - mae) <= tol * mae
+    assert abs((1 - out[0] / (out[3] - out[2] ** 2 / n)) - r2) <= 10 * tol
+    assert lib.vggp_metrics(L.F64, None, None, 0, emul_lib.ptr(out), None) == 0 and not out.any()
+    # fused with the prediction
+    knots, N = (9, 7), 500
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=8)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [tt.numpy() for tt in meshes], dtype)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    plan.grid_forward(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy())
+    xs = [np.ascontiguousarray(X[:, d].numpy().astype(dtype)) for d in range(2)]
+    yy = y.numpy().astype(dtype)
+    mean, _ = plan.predict(xs)
+    sums = plan.predict_metrics(xs, yy)
+    e = yy.astype(np.float64) - mean.astype(np.float64)
+    assert abs(sums[0] - np.sum(e ** 2)) <= 1e-12 * np.sum(e ** 2) and abs(sums[1] - np.sum(np.abs(e))) <= 1e-12 * np.sum(np.abs(e))
+    c = yy.astype(np.float64) - float(yy[0])
+    assert abs(sums[2] - c.sum()) <= 1e-9 * max(1.0, abs(c.sum())) and abs(sums[3] - np.sum(c ** 2)) <= 1e-12 * np.sum(c ** 2)
+    plan.close()
+
+
 def test_binned_abi_edge_cases_under_emulation(emu):
     lib, L = emu
     meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]

@@ -1,9 +1,11 @@
-"""GPU parity of the binned K1 path (vggp_obs_bin_prepare / _pack / vggp_obs_fwd_bwd_binned, csrc/obs_binned.cuh).
+"""GPU tests of the paths written after the round-1 GPU budget was spent: the binned K1 layout
+(vggp_obs_bin_prepare / _pack / vggp_obs_fwd_bwd_binned, csrc/obs_binned.cuh), the CUDA-graph replay of the step and
+the fused evaluation metrics (csrc/metrics.cuh).
 
-OPT-IN: this path was written after the round-1 GPU budget was spent.  Its planner, lane arithmetic and layout are
-verified on the CPU (tests/test_binned_host_emul.py); the device glue has not run on a B200 yet, so these tests only run
-with VGGP_TEST_BINNED=1 and the default hot path stays the packed kernel (k_obs_b1).  First thing to do with a GPU:
-    VGGP_TEST_BINNED=1 python -m pytest tests/test_gpu_binned.py -m gpu -x -q
+OPT-IN: everything here passes on the CPU under the SIMT emulator (tests/test_full_emul.py, tests/test_device_emul.py),
+but none of it has run on a B200 yet, so these tests only run with VGGP_TEST_UNVERIFIED=1 and no default path uses this
+code.  First thing to do with a GPU (tools/gpu_check_binned.sh does it):
+    VGGP_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_new_paths.py -m gpu -x -q
 """
 import os
 
@@ -14,8 +16,8 @@ from oracle import vggp_oracle as O
 from test_gpu_elbo import CASES, make_problem, oracle_value_and_grads, relerr
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VGGP_TEST_BINNED") != "1",
-                                 reason="binned K1 path is opt-in until verified on a B200 (set VGGP_TEST_BINNED=1)")]
+              pytest.mark.skipif(os.environ.get("VGGP_TEST_UNVERIFIED") != "1",
+                                 reason="paths not yet run on a B200 are opt-in (set VGGP_TEST_UNVERIFIED=1)")]
 
 
 @pytest.fixture(scope="module")
@@ -168,3 +170,36 @@ def test_graphed_step_replays_the_plain_step(vg, dev, layout):
         torch.cuda.synchronize()
         for a, b in zip(got, ref):
             assert torch.allclose(a, b, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 1e-5)])
+def test_fused_metrics_match_reference_formulas(vg, dev, dtype, tol):
+    """utils.evaluationmetrics (vggp_metrics) and GridPlan.predict_metrics (vggp_predict_metrics) against the reference's
+    torch formulas (src/utils/evaluationmetrics.py:6-54)."""
+    import importlib
+    em = importlib.import_module("variational-gridded-gaussian-processes_b200.utils.evaluationmetrics")
+    g = torch.Generator().manual_seed(2)
+    true = (50.0 + torch.randn(300, 211, generator=g, dtype=torch.float64)).to(dtype).to(dev)
+    pred = (true.double() + 0.3 * torch.randn(300, 211, generator=g, dtype=torch.float64).to(dev)).to(dtype)
+    t64, p64 = true.double(), pred.double()
+    mse = torch.mean((t64 - p64) ** 2)
+    assert abs(em.mean_squared_error(true, pred) - mse) <= tol * mse
+    assert abs(em.root_mean_squared_error(true, pred) - torch.sqrt(mse)) <= tol * torch.sqrt(mse)
+    mae = torch.mean(torch.abs(t64 - p64))
+    assert abs(em.mean_absolute_error(true, pred) - mae) <= tol * mae
+    r2 = 1 - torch.sum((t64 - p64) ** 2) / torch.sum((t64 - torch.mean(t64)) ** 2)
+    assert abs(em.r_squared(true, pred) - r2) <= 10 * tol
+    with pytest.raises(AssertionError):
+        em.mean_squared_error(true.reshape(-1), pred.reshape(-1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        em.mean_squared_error(true.cpu(), pred.cpu())
+    meshes, X, y, l, s2, noise, m, Ls = make_problem((33, 21), 20000, seed=4)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    plan.grid_forward(torch.cat([l, s2, noise.reshape(1)]).to(dev), m.to(dev), torch.cat([L.reshape(-1) for L in Ls]).to(dev))
+    xs = [X[:, d].to(dtype).contiguous().to(dev) for d in range(2)]
+    yd = y.to(dtype).to(dev)
+    mean, _ = plan.predict(xs)
+    fused = plan.predict_metrics(xs, yd)
+    sep = em.all_metrics(yd.reshape(-1, 1), mean.reshape(-1, 1))
+    for k in ("mse", "mae", "rmse", "r2"):
+        assert abs(fused[k] - sep[k]) <= 1e-9 * max(1.0, abs(sep[k]))

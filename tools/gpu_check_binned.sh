@@ -16,10 +16,10 @@ timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/pytest_default.log" 2>&1
 note "   rc=$? $(tail -n 1 "$OUT/pytest_default.log")"
 
 note "== 2. binned path, LDG stream first (tests are parametrised ldg/tma; -k ldg isolates a TMA hang)"
-VGGP_TEST_BINNED=1 timeout 600 python -m pytest tests/test_gpu_binned.py -m gpu -x -q -k "ldg or not tma" > "$OUT/pytest_binned_ldg.log" 2>&1
+VGGP_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -x -q -k "ldg or not tma" > "$OUT/pytest_binned_ldg.log" 2>&1
 RC_LDG=$?
 note "   rc=$RC_LDG $(tail -n 1 "$OUT/pytest_binned_ldg.log")"
-VGGP_TEST_BINNED=1 timeout 600 python -m pytest tests/test_gpu_binned.py -m gpu -x -q -k "tma" > "$OUT/pytest_binned_tma.log" 2>&1
+VGGP_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -x -q -k "tma" > "$OUT/pytest_binned_tma.log" 2>&1
 RC_TMA=$?
 note "   tma rc=$RC_TMA $(tail -n 1 "$OUT/pytest_binned_tma.log")"
 

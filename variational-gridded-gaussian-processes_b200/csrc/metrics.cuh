@@ -1,0 +1,104 @@
+// Evaluation metrics of the reference (src/utils/evaluationmetrics.py:6-54: MSE, MAE, RMSE, R^2) as one fused
+// reduction, and the same reduction fused with the point prediction so that the predictive mean never goes to HBM
+// (SURVEY.md section 8f row 2).  Both kernels emit four raw float64 sums; the host mirror finishes the formulas:
+//     out = { sum (t - p)^2,  sum |t - p|,  sum (t - t_0),  sum (t - t_0)^2 }          t_0 = the first target
+//     MSE = out0 / n, MAE = out1 / n, RMSE = sqrt(MSE), R^2 = 1 - out0 / (out3 - out2^2 / n)
+// (the total sum of squares is taken about the pivot t_0 so that a large mean does not cancel in the one-pass form).
+// HBM-bound: 2 (or D + 1) values read per element, warp-shuffle + shared-memory block reduction, one float64 atomic per
+// block and output.
+#pragma once
+#include "obs.cuh"
+
+namespace vggp {
+
+__device__ __forceinline__ void metrics_flush(double sse, double sae, double s1, double s2, double* red, double* out) {
+    sse = block_sum(sse, red);
+    sae = block_sum(sae, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(out + 0, sse);
+        atomicAdd(out + 1, sae);
+        atomicAdd(out + 2, s1);
+        atomicAdd(out + 3, s2);
+    }
+}
+
+// out[4] must be zero on entry
+template <typename T>
+__global__ void __launch_bounds__(256) k_metrics(const T* __restrict__ truth, const T* __restrict__ pred, i64 n,
+                                                 double* __restrict__ out) {
+    __shared__ double red[32];
+    double sse = 0.0, sae = 0.0, s1 = 0.0, s2 = 0.0;
+    const double pivot = (double)truth[0];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double t = (double)truth[i];
+        const double e = t - (double)pred[i];
+        sse = fma(e, e, sse);
+        sae += fabs(e);
+        const double c = t - pivot;
+        s1 += c;
+        s2 = fma(c, c, s2);
+    }
+    metrics_flush(sse, sae, s1, s2, red, out);
+}
+
+// Prediction of the posterior mean at the test points (same arithmetic as k_predict_b1) fused with the metrics of
+// (y, mean).  out[4] must be zero on entry.
+template <typename T, int D>
+struct PredictMetricsArgs {
+    PredictArgs<T, D> p;     // mean / var pointers unused
+    const T* y;
+    double* out;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_predict_metrics(const __grid_constant__ PredictMetricsArgs<T, D> m) {
+    __shared__ double red[32];
+    const PredictArgs<T, D>& a = m.p;
+    double sse = 0.0, sae = 0.0, s1 = 0.0, s2 = 0.0;
+    const double pivot = (double)m.y[0];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (i64)gridDim.x * blockDim.x) {
+        int c[D];
+        T w[D];
+        bool all_in = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const T xv = a.x[d][i];
+            bool inside;
+            c[d] = find_cell<T>(a.mesh[d].t, a.mesh[d].K, a.mesh[d].t0, a.mesh[d].inv_h, a.mesh[d].nearly_uniform, xv, inside);
+            all_in = all_in && inside;
+            const int n = a.mesh[d].K;
+            const T* tb = a.tab + (a.tab_off[d] + c[d]);
+            w[d] = div_by_cached_rcp(xv - (T)a.mesh[d].t[c[d]], tb[6 * n], tb[7 * n]);
+        }
+        T mu = (T)0;
+        if (all_in) {
+            int base = 0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) base += c[d] * a.stride[d];
+#pragma unroll
+            for (int corner = 0; corner < (1 << D); ++corner) {
+                T wt = (T)1;
+                int off = base;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const bool hi = (corner >> (D - 1 - d)) & 1;
+                    wt *= hi ? w[d] : ((T)1 - w[d]);
+                    off += hi ? a.stride[d] : 0;
+                }
+                mu += wt * a.alpha[off];
+            }
+        }
+        const double t = (double)m.y[i];
+        const double e = t - (double)mu;
+        sse = fma(e, e, sse);
+        sae += fabs(e);
+        const double cc = t - pivot;
+        s1 += cc;
+        s2 = fma(cc, cc, s2);
+    }
+    metrics_flush(sse, sae, s1, s2, red, m.out);
+}
+
+}  // namespace vggp

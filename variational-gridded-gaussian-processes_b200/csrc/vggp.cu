@@ -11,6 +11,7 @@
 #include "grid.cuh"
 #include "obs.cuh"
 #include "obs_binned.cuh"
+#include "metrics.cuh"
 
 namespace vggp {
 thread_local char g_err[512] = {0};
@@ -623,6 +624,30 @@ int launch_predict(vggp_plan* p, const void* const* x, i64 n, void* mean, void* 
 }
 int predict_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st);
 
+template <typename T, int D>
+int launch_predict_metrics(vggp_plan* p, const void* const* x, const void* y, i64 n, double* out, cudaStream_t st) {
+    PredictMetricsArgs<T, D> m;
+    for (int d = 0; d < D; ++d) {
+        m.p.x[d] = reinterpret_cast<const T*>(x[d]);
+        m.p.mesh[d] = p->mesh[d];
+        m.p.stride[d] = (int)p->stride[d];
+        m.p.tab_off[d] = p->tab_off[d];
+    }
+    m.p.n = n;
+    m.p.tab = reinterpret_cast<const T*>(p->tables);
+    m.p.alpha = reinterpret_cast<const T*>(p->alphaT);
+    m.p.theta = p->theta_dev;
+    m.p.mean = nullptr;
+    m.p.var = nullptr;
+    m.y = reinterpret_cast<const T*>(y);
+    m.out = out;
+    const int blocks = (int)std::min<i64>((n + 255) / 256, (i64)p->sm_count * 8);
+    k_predict_metrics<T, D><<<blocks, 256, 0, st>>>(m);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+int predict_metrics_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, double* out, cudaStream_t st);
+
 int obs_b0_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, void* gbuf, cudaStream_t st) {
     if (p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (p->obs_dtype == VGGP_F32) return p->D == 1 ? launch_obs_b0<float, 1>(p, x, y, n, gbuf, st) : launch_obs_b0<float, 2>(p, x, y, n, gbuf, st);
@@ -650,6 +675,9 @@ int obs_b0_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, vo
 int obs_prepare_dispatch(vggp_plan* p) { VGGP_DISPATCH_TD(p, obs_prepare, p); }
 int predict_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
     VGGP_DISPATCH_TD(p, launch_predict, p, x, n, mean, var, st);
+}
+int predict_metrics_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, double* out, cudaStream_t st) {
+    VGGP_DISPATCH_TD(p, launch_predict_metrics, p, x, y, n, out, st);
 }
 int obs_packed_dispatch(vggp_plan* p, const void* const* xp, const void* yp, i64 n, void* gbuf, cudaStream_t st) {
     VGGP_DISPATCH_TD(p, launch_obs_packed, p, xp, yp, n, gbuf, st);
@@ -1385,6 +1413,32 @@ int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void
     if (p->family != VGGP_B1_ASVGP)
         return fail(VGGP_E_UNSUPPORTED, "point prediction is built for the B1 family");
     return predict_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
+}
+
+int vggp_metrics(int dtype, const void* truth, const void* pred, int64_t n, double* out, void* stream) {
+    if (!out || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (dtype != VGGP_F32 && dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "dtype must be VGGP_F32 or VGGP_F64");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGGP_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
+    if (n == 0) return 0;
+    if (!truth || !pred) return fail(VGGP_E_ARG, "null argument");
+    const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 8);
+    if (dtype == VGGP_F32) k_metrics<float><<<blocks, 256, 0, st>>>((const float*)truth, (const float*)pred, n, out);
+    else k_metrics<double><<<blocks, 256, 0, st>>>((const double*)truth, (const double*)pred, n, out);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_predict_metrics(vggp_plan* p, const void* const* x, const void* y, int64_t n, double* out, void* stream) {
+    if (!p || !out || n < 0) return fail(VGGP_E_ARG, "bad argument");
+    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "point prediction is built for the B1 family");
+    cudaStream_t st = (cudaStream_t)stream;
+    VGGP_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
+    if (n == 0) return 0;
+    if (!x || !y) return fail(VGGP_E_ARG, "null argument");
+    for (int d = 0; d < p->D; ++d)
+        if (!x[d]) return fail(VGGP_E_ARG, "null test-point pointer");
+    return predict_metrics_dispatch(p, x, y, n, out, st);
 }
 
 int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {

@@ -130,6 +130,21 @@ class GridPlan:
                                          _stream_ptr(self.device)))
         return mean, var
 
+    def predict_metrics(self, xs: Sequence[torch.Tensor], y: torch.Tensor) -> dict:
+        """MSE, MAE, RMSE, R^2 (src/utils/evaluationmetrics.py:6-54) of the posterior mean at the test points against
+        `y`, in one fused pass: the predictions are never written to memory (vggp_predict_metrics)."""
+        from .utils.evaluationmetrics import finish
+        n = int(y.numel())
+        xs = [t.to(self.device, self.obs_dtype).contiguous() for t in xs]
+        y = y.to(self.device, self.obs_dtype).contiguous()
+        if len(xs) != self.D or any(t.numel() != n for t in xs):
+            raise ValueError(f"expected {self.D} coordinate arrays of the length of y")
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        ptrs = (C.c_void_p * self.D)(*[t.data_ptr() for t in xs])
+        _lib.check(self.lib.vggp_predict_metrics(self.handle, ptrs, y.data_ptr(), n, out.data_ptr(),
+                                                 _stream_ptr(self.device)))
+        return finish(out, n)
+
     def cell_keys(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
         """Flat (row-major) cell id of every observation, n_cells for observations outside the mesh (B1 stencil)."""
         key = None
