@@ -216,11 +216,14 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
                         void* phi, void* stream);
 
 /*
- * Point prediction at test points from the state of the last vggp_grid_forward (B1 family): the marginal mean and
- * variance of q(f(x*)) -- kronecker_structure.py:199-230 `posterior` restricted to its diagonal --
+ * Point prediction at test points from the state of the last vggp_grid_forward: the marginal mean and variance of
+ * q(f(x*)) -- kronecker_structure.py:199-230 `posterior` restricted to its diagonal --
  *   mean = <kron_d phi_d(x*), alpha>,   var = prod_d s2_d - prod_d phi_d^T P_d phi_d + prod_d phi_d^T Q_d phi_d.
  *   x [D] HOST array of device pointers (n values of obs_dtype each); mean, var: n values of obs_dtype.
- * Test points outside the mesh get mean 0 and the prior variance.
+ * B1 family: test points outside the mesh get mean 0 and the prior variance (their feature column is zero).
+ * B0 family (D <= 2): the cell-integrated features are non-zero everywhere; they are evaluated in their scan form
+ *   (three local features per dimension against per-cell tables built by dense products on the grid side, csrc/b0scan.cuh),
+ *   O(1) work per point.  The first call allocates the tables inside the plan.  Not yet run on a B200.
  */
 int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, void* var, void* stream);
 

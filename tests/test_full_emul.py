@@ -192,6 +192,43 @@ def test_point_prediction_under_emulation(emu):
     plan.close()
 
 
+@pytest.mark.parametrize("knots", [(11,), (8, 7)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
+def test_b0_point_prediction_scan_form_under_emulation(emu, knots, dtype, tol):
+    """vggp_predict for the B0 family = the scan form of csrc/b0scan.cuh (per-cell tables from dense products, O(1) work
+    per point) against the dense formulas with the reference's dense features; points outside the mesh and on knots
+    included."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, 300, seed=12, family=O.B0_GRIDDED, x_lo=-0.3, x_hi=1.3)
+    plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, [t.numpy() for t in meshes], dtype)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    plan.grid_forward(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy())
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq = X.to(tdt)
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    mean, var = plan.predict(xs)
+    Ms = [k - 1 for k in knots]
+    Ks = [O.kuu_factor(O.B0_GRIDDED, meshes[d], l[d], s2[d], ref_quirks=False).to(torch.float64) for d in range(D)]
+    Ps = [torch.linalg.inv(K) for K in Ks]
+    Qs = [P @ torch.tril(Lx) @ torch.tril(Lx).T @ P for P, Lx in zip(Ps, Ls)]
+    phis = [O.b0_features_dense(meshes[d], Xq[:, d].to(torch.float64), l[d], s2[d]) for d in range(D)]
+    A = m.reshape(Ms)
+    for d in range(D):
+        A = O.mode_product(A, Ps[d], d)
+    mu_ref = phis[0].T @ A if D == 1 else torch.einsum("in,ij,jn->n", phis[0], A, phis[1])
+    pp = torch.ones_like(mu_ref)
+    qq = torch.ones_like(mu_ref)
+    for d in range(D):
+        pp = pp * (phis[d] * (Ps[d] @ phis[d])).sum(0)
+        qq = qq * (phis[d] * (Qs[d] @ phis[d])).sum(0)
+    var_ref = torch.prod(s2) - pp + qq
+    scale_mu = float(mu_ref.abs().max())
+    assert np.max(np.abs(mean - mu_ref.numpy())) <= tol * scale_mu
+    assert np.max(np.abs(var - var_ref.numpy())) <= tol * float(var_ref.abs().max())
+    plan.close()
+
+
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
 def test_metrics_kernels_under_emulation(emu, dtype, tol):
     """vggp_metrics / vggp_predict_metrics against the reference's formulas (src/utils/evaluationmetrics.py:6-54)."""

@@ -203,3 +203,33 @@ def test_fused_metrics_match_reference_formulas(vg, dev, dtype, tol):
     sep = em.all_metrics(yd.reshape(-1, 1), mean.reshape(-1, 1))
     for k in ("mse", "mae", "rmse", "r2"):
         assert abs(fused[k] - sep[k]) <= 1e-9 * max(1.0, abs(sep[k]))
+
+
+@pytest.mark.parametrize("knots", [(14,), (10, 8), (71, 14)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_b0_point_prediction_scan_form(vg, dev, knots, dtype, tol):
+    """vggp_predict for the B0 family (scan form, csrc/b0scan.cuh) against the dense formulas with the reference's dense
+    features; points outside the mesh and on knots included."""
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, 3000, seed=12, family=O.B0_GRIDDED, x_lo=-0.3, x_hi=1.3)
+    plan = vg.GridPlan(vg.B0_GRIDDED, meshes, dtype, dev)
+    plan.grid_forward(torch.cat([l, s2, noise.reshape(1)]).to(dev), m.to(dev), torch.cat([L.reshape(-1) for L in Ls]).to(dev))
+    Xq = X.to(dtype)
+    mean, var = plan.predict([Xq[:, d].contiguous().to(dev) for d in range(D)])
+    Ms = [k - 1 for k in knots]
+    Ks = [O.kuu_factor(O.B0_GRIDDED, meshes[d], l[d], s2[d], ref_quirks=False).to(torch.float64) for d in range(D)]
+    Ps = [torch.linalg.inv(K) for K in Ks]
+    Qs = [P @ torch.tril(Lx) @ torch.tril(Lx).T @ P for P, Lx in zip(Ps, Ls)]
+    phis = [O.b0_features_dense(meshes[d], Xq[:, d].to(torch.float64), l[d], s2[d]) for d in range(D)]
+    A = m.reshape(Ms)
+    for d in range(D):
+        A = O.mode_product(A, Ps[d], d)
+    mu_ref = phis[0].T @ A if D == 1 else torch.einsum("in,ij,jn->n", phis[0], A, phis[1])
+    pp = torch.ones_like(mu_ref)
+    qq = torch.ones_like(mu_ref)
+    for d in range(D):
+        pp = pp * (phis[d] * (Ps[d] @ phis[d])).sum(0)
+        qq = qq * (phis[d] * (Qs[d] @ phis[d])).sum(0)
+    var_ref = torch.prod(s2) - pp + qq
+    assert (mean.cpu().double() - mu_ref).abs().max() <= tol * mu_ref.abs().max()
+    assert (var.cpu().double() - var_ref).abs().max() <= tol * var_ref.abs().max()

@@ -12,6 +12,7 @@
 #include "obs.cuh"
 #include "obs_binned.cuh"
 #include "metrics.cuh"
+#include "b0scan.cuh"
 
 namespace vggp {
 thread_local char g_err[512] = {0};
@@ -53,6 +54,15 @@ struct vggp_plan {
     void* pk_x[VGGP_MAX_D] = {nullptr, nullptr, nullptr}; void* pk_y = nullptr; i64 pk_cap = 0;
     // binned layout: the layout planned by vggp_obs_bin_prepare and the cell-sorted order, until vggp_obs_bin_pack
     BinLayout bin_pending; uint32_t* bin_perm = nullptr; bool bin_has_pending = false;
+    // B0 family, scan form (b0scan.cuh): per-dimension transform rows and products, per-cell tables; allocated at first use
+    bool b0s_ready = false;
+    double* b0s_G[VGGP_MAX_D][4] = {};     // GL, GR, dGL/dl, dGR/dl: (K+1) x (K-1)
+    double* b0s_V[VGGP_MAX_D][4] = {};     // GL P, GR P, GL Q, GR Q: (K+1) x (K-1)
+    double* b0s_U[2] = {};                 // A G2^y^T: M1 x E2
+    double* b0s_B[2] = {};                 // G1^x A:   E1 x M2
+    double* b0s_TT[4] = {};                // G1^x U^y: E1 x E2
+    void* b0s_W[VGGP_MAX_D] = {};          // [2][6][E_d] obs dtype
+    void* b0s_Tt = nullptr;                // D = 1: [3][E1], D = 2: [3][3][E1][E2] obs dtype
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
@@ -836,6 +846,146 @@ int obs_binned_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* 
     VGGP_DISPATCH_TD(p, launch_obs_binned, p, desc, binned, gbuf, st);
 }
 
+// ---- B0 family, scan form (b0scan.cuh) -------------------------------------------------------------------
+// C (m x n, row-major, leading dimension ldc) = alpha * A * B + beta * C with arbitrary operand strides
+int gemm_rm(cudaStream_t st, int m, int n, int k, const double* A, i64 rsA, i64 csA, const double* B, i64 rsB, i64 csB,
+            double* C, i64 ldc, double alpha = 1.0, double beta = 0.0) {
+    GemmDesc d;
+    gemm_desc_defaults(d);
+    d.A = A; d.B = B; d.C = C;
+    d.m = m; d.n = n; d.k = k;
+    d.rsA = rsA; d.csA = csA; d.rsB = rsB; d.csB = csB; d.rsC = ldc; d.csC = 1;
+    d.alpha = alpha; d.beta = beta;
+    return launch_one(d, g_use_mma, st);
+}
+
+int b0scan_alloc(vggp_plan* p) {
+    if (p->b0s_ready) return 0;
+    if (p->family != VGGP_B0_GRIDDED || p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the scan form is built for the B0 family, D <= 2");
+    const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    int rc;
+    for (int d = 0; d < p->D; ++d) {
+        const i64 em = (i64)(p->K[d] + 1) * (p->K[d] - 1);
+        for (int k = 0; k < 4; ++k) {
+            if ((rc = dev_alloc(p, &p->b0s_G[d][k], em))) return rc;
+            if ((rc = dev_alloc(p, &p->b0s_V[d][k], em))) return rc;
+        }
+        unsigned char* w = nullptr;
+        if ((rc = dev_alloc(p, &w, (i64)(12 * (p->K[d] + 1) * tsz)))) return rc;
+        p->b0s_W[d] = w;
+    }
+    const i64 E1 = p->K[0] + 1, M1 = p->K[0] - 1;
+    unsigned char* tt = nullptr;
+    if (p->D == 1) {
+        if ((rc = dev_alloc(p, &tt, (i64)(3 * E1 * tsz)))) return rc;
+    } else {
+        const i64 E2 = p->K[1] + 1, M2 = p->K[1] - 1;
+        for (int k = 0; k < 2; ++k) {
+            if ((rc = dev_alloc(p, &p->b0s_U[k], M1 * E2))) return rc;
+            if ((rc = dev_alloc(p, &p->b0s_B[k], E1 * M2))) return rc;
+        }
+        for (int k = 0; k < 4; ++k)
+            if ((rc = dev_alloc(p, &p->b0s_TT[k], E1 * E2))) return rc;
+        if ((rc = dev_alloc(p, &tt, (i64)(9 * E1 * E2 * tsz)))) return rc;
+    }
+    p->b0s_Tt = tt;
+    p->b0s_ready = true;
+    return 0;
+}
+
+// Per-cell tables from the state of the last grid forward (alpha, P_d, Q_d, theta).
+template <typename T>
+int b0scan_tables(vggp_plan* p, cudaStream_t st) {
+    int rc = b0scan_alloc(p);
+    if (rc) return rc;
+    const int D = p->D;
+    B0sGArgs ga;
+    int emax = 0;
+    for (int d = 0; d < D; ++d) {
+        ga.knots[d] = p->d_knots[d];
+        ga.K[d] = p->K[d];
+        ga.GL[d] = p->b0s_G[d][0]; ga.GR[d] = p->b0s_G[d][1]; ga.dGL[d] = p->b0s_G[d][2]; ga.dGR[d] = p->b0s_G[d][3];
+        emax = std::max(emax, (p->K[d] + 1) * (p->K[d] - 1));
+    }
+    ga.theta = p->theta_dev;
+    k_b0s_G<<<dim3(ceil_div(emax, 256), D), 256, 0, st>>>(ga);
+    VGGP_LAUNCH_CHECK();
+    B0sWArgs<T> wa;
+    int kmax = 0;
+    for (int d = 0; d < D; ++d) {
+        const int M = p->K[d] - 1, E = p->K[d] + 1;
+        const double* mats[2] = {p->g.P[d], p->g.Q[d]};
+        for (int mat = 0; mat < 2; ++mat)
+            for (int x = 0; x < 2; ++x)      // V = G^x Mat
+                if ((rc = gemm_rm(st, E, M, M, p->b0s_G[d][x], M, 1, mats[mat], M, 1, p->b0s_V[d][2 * mat + x], M))) return rc;
+        wa.K[d] = p->K[d];
+        wa.GL[d] = p->b0s_G[d][0]; wa.GR[d] = p->b0s_G[d][1];
+        for (int k = 0; k < 4; ++k) wa.V[d][k] = p->b0s_V[d][k];
+        wa.Mat[d][0] = p->g.P[d]; wa.Mat[d][1] = p->g.Q[d];
+        wa.W[d] = reinterpret_cast<T*>(p->b0s_W[d]);
+        kmax = std::max(kmax, E);
+    }
+    k_b0s_W<T><<<dim3(ceil_div(kmax, 8), D), 256, 0, st>>>(wa);
+    VGGP_LAUNCH_CHECK();
+    const int E1 = p->K[0] + 1, M1 = p->K[0] - 1;
+    if (D == 1) {
+        k_b0s_T1<T><<<ceil_div(E1, 8), 256, 0, st>>>(p->K[0], p->b0s_G[0][0], p->b0s_G[0][1], p->alpha, reinterpret_cast<T*>(p->b0s_Tt));
+        VGGP_LAUNCH_CHECK();
+        return 0;
+    }
+    const int E2 = p->K[1] + 1, M2 = p->K[1] - 1;
+    for (int y = 0; y < 2; ++y)              // U^y = A G2^y^T
+        if ((rc = gemm_rm(st, M1, E2, M2, p->alpha, M2, 1, p->b0s_G[1][y], 1, M2, p->b0s_U[y], E2))) return rc;
+    for (int x = 0; x < 2; ++x) {            // B^x = G1^x A,  TT[2x+y] = G1^x U^y
+        if ((rc = gemm_rm(st, E1, M2, M1, p->b0s_G[0][x], M1, 1, p->alpha, M2, 1, p->b0s_B[x], M2))) return rc;
+        for (int y = 0; y < 2; ++y)
+            if ((rc = gemm_rm(st, E1, E2, M1, p->b0s_G[0][x], M1, 1, p->b0s_U[y], E2, 1, p->b0s_TT[2 * x + y], E2))) return rc;
+    }
+    B0sT2Args<T> ta;
+    ta.E1 = E1; ta.E2 = E2; ta.M1 = M1; ta.M2 = M2;
+    for (int k = 0; k < 4; ++k) ta.TT[k] = p->b0s_TT[k];
+    for (int k = 0; k < 2; ++k) { ta.B[k] = p->b0s_B[k]; ta.U[k] = p->b0s_U[k]; }
+    ta.A = p->alpha;
+    ta.Tt = reinterpret_cast<T*>(p->b0s_Tt);
+    k_b0s_T2<T><<<ceil_div((i64)E1 * E2, 256), 256, 0, st>>>(ta);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T, int D>
+void b0scan_point_tables(const vggp_plan* p, B0sPointTables<T, D>& t) {
+    for (int d = 0; d < D; ++d) {
+        t.mesh[d] = p->mesh[d];
+        t.E[d] = p->K[d] + 1;
+        t.W[d] = reinterpret_cast<const T*>(p->b0s_W[d]);
+    }
+    t.Tt = reinterpret_cast<const T*>(p->b0s_Tt);
+    t.theta = p->theta_dev;
+}
+
+template <typename T, int D>
+int launch_predict_b0s(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
+    int rc = b0scan_tables<T>(p, st);
+    if (rc) return rc;
+    B0sPredictArgs<T, D> a;
+    b0scan_point_tables<T, D>(p, a.tab);
+    for (int d = 0; d < D; ++d) a.x[d] = reinterpret_cast<const T*>(x[d]);
+    a.n = n;
+    a.mean = reinterpret_cast<T*>(mean);
+    a.var = reinterpret_cast<T*>(var);
+    const int blocks = (int)std::min<i64>((n + 255) / 256, (i64)p->sm_count * 8);
+    k_predict_b0s<T, D><<<blocks, 256, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int predict_b0s_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
+    if (p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
+    if (p->obs_dtype == VGGP_F32)
+        return p->D == 1 ? launch_predict_b0s<float, 1>(p, x, n, mean, var, st) : launch_predict_b0s<float, 2>(p, x, n, mean, var, st);
+    return p->D == 1 ? launch_predict_b0s<double, 1>(p, x, n, mean, var, st) : launch_predict_b0s<double, 2>(p, x, n, mean, var, st);
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -1410,8 +1560,8 @@ int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void
     if (!x || !mean || !var) return fail(VGGP_E_ARG, "null argument");
     for (int d = 0; d < p->D; ++d)
         if (!x[d]) return fail(VGGP_E_ARG, "null test-point pointer");
-    if (p->family != VGGP_B1_ASVGP)
-        return fail(VGGP_E_UNSUPPORTED, "point prediction is built for the B1 family");
+    if (p->family != VGGP_B1_ASVGP)      // B0 family: scan form, O(1) per point (b0scan.cuh)
+        return predict_b0s_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
     return predict_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
 }
 

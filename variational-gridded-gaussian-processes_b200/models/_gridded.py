@@ -154,7 +154,8 @@ class GriddedVariationalGP(nn.Module):
     # ---- predictions (kronecker_structure.py:199-247, marginals only) --------------------------------------------
     def posterior(self, x: torch.Tensor) -> GriddedMarginals:
         """q(f(x*)): marginal mean and variance at the test points x (N*, D) under the current q(u) and
-        hyper-parameters.  B1 family."""
+        hyper-parameters.  B1 family: 2^D-point stencil; B0 family: scan form of the cell-integrated features
+        (csrc/b0scan.cuh), O(1) per point as well."""
         plan = self._ensure_plan()
         theta = self._theta()
         m = self.variational_mean.detach().to(torch.float64).contiguous()
