@@ -192,6 +192,31 @@ def test_point_prediction_under_emulation(emu):
     plan.close()
 
 
+@pytest.mark.parametrize("knots,N", [((11,), 400), ((8, 7), 500), ((5, 12), 300)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-3)])
+def test_b0_step_scan_form_matches_oracle_under_emulation(emu, knots, N, dtype, tol):
+    """The B0 family through the binned layout = scan form (k_obs_b0s + table construction + adjoint stage, b0scan.cuh):
+    ELBO and every gradient against the oracle's dense-feature evaluation, observations outside the mesh included."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=21 + D, family=O.B0_GRIDDED, x_lo=-0.2, x_hi=1.2)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq, yq = X.to(tdt), y.to(tdt)
+    scale = 1.3
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, [t.numpy() for t in meshes], dtype)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    yy = np.ascontiguousarray(yq.numpy())
+    binned = plan.bin(xs, yy, run_cap=16)
+    assert binned[2].n_inside == N                      # every observation has an extended cell
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    binned, None, scale)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, tol)
+    plan.close()
+
+
 @pytest.mark.parametrize("knots", [(11,), (8, 7)])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
 def test_b0_point_prediction_scan_form_under_emulation(emu, knots, dtype, tol):

@@ -12,6 +12,7 @@
 // The tables are dense float64 products on the grid side (k_gemm_one), the per-point work is O(1).
 #pragma once
 #include "obs.cuh"
+#include "obs_binned.cuh"
 
 namespace vggp {
 
@@ -276,6 +277,384 @@ __global__ void __launch_bounds__(256) k_predict_b0s(const __grid_constant__ B0s
         a.mean[i] = mu;
         a.var[i] = kff - pp + qq;
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 for the B0 family in scan form: fused per-observation forward + backward over the binned layout of binplan.hpp
+// with EXTENDED cells (e_d = 0..K_d: observations outside the mesh belong to the virtual end cells and do contribute).
+// Same task / run structure as k_obs_b1_binned: one lane walks one run = (a share of) the observations of one extended
+// cell, the 32 runs of a warp task have the same padded length, the per-cell tables are loaded once per run.
+// Raw sums per cell (1 / noise, ell_scale applied on the grid side, like k_obs_b0):
+//   GT[X][Y][e1][e2]  += r f1^X f2^Y                      (adjoint of the mean tables; D = 1: GT[X][e])
+//   GW[d][mat][s][e_d] += o_d f_d^X f_d^Y                 o = prod_{e != d} p_e (mat 0) or q_e (mat 1), s = LL, LC, LR, CC, CR, RR
+//   E += r^2 - prod p + prod q;   G_l[d] += sum_X gf_d^X df_d^X / dl;   G_s[d] += sum_X gf_d^X f_d^X
+//        gf_d^X = r dmu/df_d^X + o^p_d zP_d^X - o^q_d zQ_d^X           (the part of the theta gradient that goes through the
+//                                                                      local features; the table part is added by the adjoint stage)
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void b0s_decode_cell(uint32_t cell, const int (&E)[D], int (&e)[D]) {
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) {
+        e[d] = (int)(cell % (uint32_t)E[d]);
+        cell /= (uint32_t)E[d];
+    }
+}
+
+// flat extended-cell key of every observation (row-major over e_1..e_D); every observation has one
+template <typename T, int D>
+struct B0sKeyArgs {
+    const T* x[D];
+    i64 n;
+    MeshView mesh[D];
+};
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_b0s_keys(const __grid_constant__ B0sKeyArgs<T, D> a, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ idx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (i64)gridDim.x * blockDim.x) {
+        uint32_t key = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            key = key * (uint32_t)(a.mesh[d].K + 1) + (uint32_t)lower_bound_knots<T>(a.mesh[d].t, a.mesh[d].K, a.x[d][i]);
+        keys[i] = key;
+        idx[i] = (uint32_t)i;
+    }
+}
+
+// fill the binned data blocks (same layout as k_bin_gather); padding slots get a finite coordinate of the run's cell
+template <typename T, int D>
+struct B0sGatherArgs {
+    const T* x[D];
+    const T* y;
+    const uint32_t* perm;
+    const float* knots[D];
+    int K[D];
+    unsigned char* buf;
+    i64 off_task_off, off_task_R, off_run_cell, off_run_n, off_run_start, off_data;
+    int n_tasks;
+};
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_b0s_gather(const __grid_constant__ B0sGatherArgs<T, D> a) {
+    const i64* task_off = reinterpret_cast<const i64*>(a.buf + a.off_task_off);
+    const int* task_R = reinterpret_cast<const int*>(a.buf + a.off_task_R);
+    const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell);
+    const int* run_n = reinterpret_cast<const int*>(a.buf + a.off_run_n);
+    const uint32_t* run_start = reinterpret_cast<const uint32_t*>(a.buf + a.off_run_start);
+    T* data = reinterpret_cast<T*>(a.buf + a.off_data);
+    int E[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) E[d] = a.K[d] + 1;
+    for (int task = blockIdx.x; task < a.n_tasks; task += gridDim.x) {
+        const i64 elems = (i64)32 * task_R[task] * (D + 1);
+        T* dst = data + task_off[task];
+        for (i64 el = threadIdx.x; el < elems; el += blockDim.x) {
+            const BinSlot sl = bin_slot_of(el, D);
+            const i64 slot = (i64)task * 32 + sl.lane;
+            const uint32_t cell = run_cell[slot];
+            T v = (T)0;
+            if (sl.j < run_n[slot]) {
+                const i64 src = (i64)a.perm[(i64)run_start[slot] + sl.j];
+                v = (sl.arr < D) ? a.x[sl.arr < D ? sl.arr : 0][src] : a.y[src];
+            } else if (sl.arr < D) {
+                int e[D];
+                b0s_decode_cell<D>(cell != BIN_EMPTY ? cell : 0u, E, e);
+                const int c = e[sl.arr] - 1, K = a.K[sl.arr];
+                v = (T)a.knots[sl.arr][c > 0 ? (c < K - 1 ? c : K - 1) : 0];
+            }
+            dst[el] = v;
+        }
+    }
+}
+
+template <typename T, int D>
+struct B0sObsArgs {
+    B0sPointTables<T, D> tab;
+    const unsigned char* buf;        // binned buffer
+    i64 off_task_off, off_task_R, off_run_cell, off_run_n, off_data;
+    int n_tasks;
+    T* GT;                           // D = 1: [3][E1];  D = 2: [3][3][E1][E2]   (zero on entry)
+    T* GW[D];                        // [2][6][E_d]                               (zero on entry)
+    double* gs;                      // gbuf scalars: [E, n, -, G_l[0..1], G_s[0..1]]
+    double n_real;
+    unsigned int* counter;
+};
+
+constexpr int B0S_THREADS = 128;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(B0S_THREADS) k_obs_b0s(const __grid_constant__ B0sObsArgs<T, D> a) {
+    __shared__ double red[32];
+    constexpr int NT = D == 1 ? 3 : 9;
+    const int lane = threadIdx.x & 31;
+    double accE = 0.0, accGl[D], accGs[D];
+    T l[D], s2[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        accGl[d] = 0.0; accGs[d] = 0.0;
+        l[d] = (T)a.tab.theta[d];
+        s2[d] = (T)a.tab.theta[D + d];
+    }
+    const i64 EE = D == 1 ? (i64)a.tab.E[0] : (i64)a.tab.E[0] * a.tab.E[D - 1];
+    for (;;) {
+        unsigned int task = 0;
+        if (lane == 0) task = atomicAdd(a.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= (unsigned int)a.n_tasks) break;
+        const i64 slot = (i64)task * 32 + lane;
+        const uint32_t cell = __ldg(reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell) + slot);
+        const int nrun = __ldg(reinterpret_cast<const int*>(a.buf + a.off_run_n) + slot);
+        const int groups = __ldg(reinterpret_cast<const int*>(a.buf + a.off_task_R) + task) >> 2;
+        const T* base = reinterpret_cast<const T*>(a.buf + a.off_data)
+                        + __ldg(reinterpret_cast<const i64*>(a.buf + a.off_task_off) + task) + lane * 4;
+        const bool valid = cell != BIN_EMPTY;
+        int e[D];
+        b0s_decode_cell<D>(valid ? cell : 0u, a.tab.E, e);
+        const i64 at = D == 1 ? (i64)e[0] : (i64)e[0] * a.tab.E[D - 1] + e[D - 1];
+        // per-cell constants: mean tables, quadratic-form tables, the two knots the local features decay from
+        T Tc[NT], Wc[D][2][6], tc[D], tc1[D];
+        bool hasL[D], hasR[D];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) Tc[k] = a.tab.Tt[(i64)k * EE + at];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int E = a.tab.E[d], K = a.tab.mesh[d].K, c = e[d] - 1;
+#pragma unroll
+            for (int mat = 0; mat < 2; ++mat)
+#pragma unroll
+                for (int s = 0; s < 6; ++s) Wc[d][mat][s] = a.tab.W[d][(i64)(mat * 6 + s) * E + e[d]];
+            tc[d] = (T)a.tab.mesh[d].t[c > 0 ? (c < K - 1 ? c : K - 1) : 0];
+            tc1[d] = (T)a.tab.mesh[d].t[c + 1 < K - 1 ? c + 1 : K - 1];
+            hasL[d] = c >= 0;
+            hasR[d] = c <= K - 2;
+        }
+        T gT[NT], gW[D][2][6];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) gT[k] = (T)0;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int mat = 0; mat < 2; ++mat)
+#pragma unroll
+                for (int s = 0; s < 6; ++s) gW[d][mat][s] = (T)0;
+        T accEr = (T)0, gl[D], gsv[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { gl[d] = (T)0; gsv[d] = (T)0; }
+
+#pragma unroll 1
+        for (int gi = 0; gi < groups; ++gi) {
+            T xg[D][4], yg[4];
+            bin_load_group<T, D>(base + (i64)gi * ((D + 1) * 128), xg, yg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (4 * gi + j >= nrun) continue;                   // padding slots of this lane
+                T f[D][3], df[D][3];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const T zL = (xg[d][j] - tc[d]) / l[d], zR = (tc1[d] - xg[d][j]) / l[d];
+                    const T eL = hasL[d] ? exp(-zL) : (T)0, eR = hasR[d] ? exp(-zR) : (T)0;
+                    const bool real = hasL[d] && hasR[d];
+                    f[d][0] = s2[d] * l[d] * eL;
+                    f[d][2] = s2[d] * l[d] * eR;
+                    f[d][1] = real ? (T)2 * s2[d] * l[d] - f[d][0] - f[d][2] : (T)0;
+                    df[d][0] = hasL[d] ? s2[d] * eL * ((T)1 + zL) : (T)0;
+                    df[d][2] = hasR[d] ? s2[d] * eR * ((T)1 + zR) : (T)0;
+                    df[d][1] = real ? (T)2 * s2[d] - df[d][0] - df[d][2] : (T)0;
+                }
+                // mean and d mu / d f
+                T mu = (T)0, tm[D][3];
+                if (D == 1) {
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) { tm[0][X] = Tc[X]; mu = fma(f[0][X], Tc[X], mu); }
+                } else {
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) { tm[0][X] = (T)0; tm[D - 1][X] = (T)0; }
+#pragma unroll
+                    for (int X = 0; X < 3; ++X)
+#pragma unroll
+                        for (int Y = 0; Y < 3; ++Y) {
+                            tm[0][X] = fma(f[D - 1][Y], Tc[3 * X + Y], tm[0][X]);
+                            tm[D - 1][Y] = fma(f[0][X], Tc[3 * X + Y], tm[D - 1][Y]);
+                        }
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) mu = fma(f[0][X], tm[0][X], mu);
+                }
+                // quadratic forms and their half gradients
+                T pq[D][2], z[D][2][3];
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+#pragma unroll
+                    for (int mat = 0; mat < 2; ++mat) {
+                        const T* w = Wc[d][mat];
+                        z[d][mat][0] = w[0] * f[d][0] + w[1] * f[d][1] + w[2] * f[d][2];
+                        z[d][mat][1] = w[1] * f[d][0] + w[3] * f[d][1] + w[4] * f[d][2];
+                        z[d][mat][2] = w[2] * f[d][0] + w[4] * f[d][1] + w[5] * f[d][2];
+                        pq[d][mat] = f[d][0] * z[d][mat][0] + f[d][1] * z[d][mat][1] + f[d][2] * z[d][mat][2];
+                    }
+                const T r = yg[j] - mu;
+                T pp = pq[0][0], qq = pq[0][1];
+#pragma unroll
+                for (int d = 1; d < D; ++d) { pp *= pq[d][0]; qq *= pq[d][1]; }
+                accEr += fma(r, r, qq - pp);
+                if (D == 1) {
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) gT[X] = fma(r, f[0][X], gT[X]);
+                } else {
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) {
+                        const T rf = r * f[0][X];
+#pragma unroll
+                        for (int Y = 0; Y < 3; ++Y) gT[3 * X + Y] = fma(rf, f[D - 1][Y], gT[3 * X + Y]);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    T o[2] = {(T)1, (T)1};
+#pragma unroll
+                    for (int e2 = 0; e2 < D; ++e2)
+                        if (e2 != d) { o[0] *= pq[e2][0]; o[1] *= pq[e2][1]; }
+                    const T ff[6] = {f[d][0] * f[d][0], f[d][0] * f[d][1], f[d][0] * f[d][2],
+                                     f[d][1] * f[d][1], f[d][1] * f[d][2], f[d][2] * f[d][2]};
+#pragma unroll
+                    for (int mat = 0; mat < 2; ++mat)
+#pragma unroll
+                        for (int s = 0; s < 6; ++s) gW[d][mat][s] = fma(o[mat], ff[s], gW[d][mat][s]);
+#pragma unroll
+                    for (int X = 0; X < 3; ++X) {
+                        const T gf = r * tm[d][X] + o[0] * z[d][0][X] - o[1] * z[d][1][X];
+                        gl[d] = fma(gf, df[d][X], gl[d]);
+                        gsv[d] = fma(gf, f[d][X], gsv[d]);
+                    }
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < NT; ++k) atomicAdd(a.GT + (i64)k * EE + at, gT[k]);
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int mat = 0; mat < 2; ++mat)
+#pragma unroll
+                    for (int s = 0; s < 6; ++s) atomicAdd(a.GW[d] + (i64)(mat * 6 + s) * a.tab.E[d] + e[d], gW[d][mat][s]);
+            accE += (double)accEr;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { accGl[d] += (double)gl[d]; accGs[d] += (double)gsv[d]; }
+        }
+    }
+    double eb = block_sum(accE, red);
+    if (threadIdx.x == 0) atomicAdd(a.gs + 0, eb);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double g1 = block_sum(accGl[d], red);
+        const double g2 = block_sum(accGs[d], red);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.gs + 3 + d, g1);
+            atomicAdd(a.gs + 5 + d, g2);
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) a.gs[1] = a.n_real;
+}
+
+// ---- adjoint stage: raw per-cell sums -> the gbuf blocks the B0 grid backward consumes -----------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_to_double(const T* __restrict__ src, double* __restrict__ dst, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_from_double(const double* __restrict__ src, T* __restrict__ dst, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = (T)src[i];
+}
+// dst (rows x cols, leading dimension ldd) = src view (leading dimension lds)
+__global__ void __launch_bounds__(256) k_b0s_copy2d(double* __restrict__ dst, i64 ldd, const double* __restrict__ src, i64 lds,
+                                                    int rows, int cols) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < (i64)rows * cols; i += (i64)gridDim.x * blockDim.x) {
+        const i64 r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+
+__device__ __forceinline__ double b0s_gw(const double* gw6, int X, int Y) { return gw6[b0s_sym_index(X, Y)]; }
+
+// One dimension, one matrix (mat 0 = P, 1 = Q):  S^X[e][i] = sum_Y gw^{XY}[e] G^Y[e][i]   (X = L, C, R; G^C[e] = unit row e-1)
+// grid (ceil(E M / 256)), 256 threads
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_S(int K, const double* __restrict__ GL, const double* __restrict__ GR,
+                                               const T* __restrict__ GW /* [6][E] of this matrix */, double* __restrict__ SL,
+                                               double* __restrict__ SC, double* __restrict__ SR) {
+    const int M = K - 1, E = K + 1;
+    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (i64)E * M) return;
+    const int e = (int)(idx / M), i = (int)(idx % M);
+    double gw6[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) gw6[s] = (double)GW[(i64)s * E + e];
+    const double g[3] = {GL[idx], (i == e - 1) ? 1.0 : 0.0, GR[idx]};
+    double out[3];
+#pragma unroll
+    for (int X = 0; X < 3; ++X) out[X] = b0s_gw(gw6, X, 0) * g[0] + b0s_gw(gw6, X, 1) * g[1] + b0s_gw(gw6, X, 2) * g[2];
+    SL[idx] = out[0];
+    SC[idx] = out[1];
+    SR[idx] = out[2];
+}
+
+// Quadratic-form part of Gamma^X = d(objective) / d G^X for X = L, R (and, in 1-D, the mean part GT^X[e] A[i]):
+//   Gamma^X[e][i] = sum_Y gwP^{XY}[e] VP^Y[e][i] - gwQ^{XY}[e] VQ^Y[e][i],    V^C[e] = row e-1 of the matrix
+// grid (ceil(E M / 256)), 256 threads
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_gamma_init(int K, const T* __restrict__ GW /* [2][6][E] */,
+                                                        const double* __restrict__ VPL, const double* __restrict__ VPR,
+                                                        const double* __restrict__ VQL, const double* __restrict__ VQR,
+                                                        const double* __restrict__ P, const double* __restrict__ Q,
+                                                        const double* __restrict__ GT1 /* 1-D: [3][E] float64, else nullptr */,
+                                                        const double* __restrict__ A1 /* 1-D: alpha */,
+                                                        double* __restrict__ GamL, double* __restrict__ GamR) {
+    const int M = K - 1, E = K + 1;
+    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (i64)E * M) return;
+    const int e = (int)(idx / M), i = (int)(idx % M), c = e - 1;
+    const bool real = c >= 0 && c < M;
+    double gp[6], gq[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) { gp[s] = (double)GW[(i64)s * E + e]; gq[s] = (double)GW[(i64)(6 + s) * E + e]; }
+    const double vp[3] = {VPL[idx], real ? P[(i64)c * M + i] : 0.0, VPR[idx]};
+    const double vq[3] = {VQL[idx], real ? Q[(i64)c * M + i] : 0.0, VQR[idx]};
+    double out[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int X = k == 0 ? B0S_L : B0S_R;
+        double v = 0.0;
+#pragma unroll
+        for (int Y = 0; Y < 3; ++Y) v += b0s_gw(gp, X, Y) * vp[Y] - b0s_gw(gq, X, Y) * vq[Y];
+        if (GT1) v += GT1[(i64)X * E + e] * A1[i];
+        out[k] = v;
+    }
+    GamL[idx] = out[0];
+    GamR[idx] = out[1];
+}
+
+// out += <GamL, dGL> + <GamR, dGR>
+__global__ void __launch_bounds__(256) k_b0s_dot(const double* __restrict__ GamL, const double* __restrict__ GamR,
+                                                 const double* __restrict__ dGL, const double* __restrict__ dGR, i64 n,
+                                                 double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        acc += GamL[i] * dGL[i] + GamR[i] * dGR[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// 1-D d alpha: galpha[i] = sum_X sum_e G^X[e][i] GT^X[e]  (one thread per i)
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_galpha1(int K, const double* __restrict__ GL, const double* __restrict__ GR,
+                                                     const double* __restrict__ GT /* [3][E] */, T* __restrict__ galpha) {
+    const int M = K - 1, E = K + 1;
+    const int i = (int)blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    double acc = GT[(i64)B0S_C * E + i + 1];
+    for (int e = 0; e < E; ++e)
+        acc += GL[(i64)e * M + i] * GT[(i64)B0S_L * E + e] + GR[(i64)e * M + i] * GT[(i64)B0S_R * E + e];
+    galpha[i] = (T)acc;
 }
 
 }  // namespace vggp

@@ -63,6 +63,13 @@ struct vggp_plan {
     double* b0s_TT[4] = {};                // G1^x U^y: E1 x E2
     void* b0s_W[VGGP_MAX_D] = {};          // [2][6][E_d] obs dtype
     void* b0s_Tt = nullptr;                // D = 1: [3][E1], D = 2: [3][3][E1][E2] obs dtype
+    void* b0s_raw = nullptr; i64 b0s_raw_bytes = 0;   // raw per-cell sums of k_obs_b0s (obs dtype): [GT | GW_0 | GW_1]
+    double* b0s_GTd = nullptr;             // GT in float64
+    double* b0s_H[3] = {};                 // M1 x E2
+    double* b0s_dA = nullptr;              // M1 x M2
+    double* b0s_S[3] = {};                 // (K+1) x (K-1), largest dimension
+    double* b0s_bM = nullptr;              // (K-1) x (K-1), largest dimension
+    double* b0s_Gam[2] = {};               // (K+1) x (K-1), largest dimension
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
@@ -700,7 +707,7 @@ int pack_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, int 
 template <typename T, int D>
 int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vggp_binned_desc* desc, cudaStream_t st) {
     i64 ncells = 1;
-    for (int d = 0; d < D; ++d) ncells *= (p->K[d] - 1);
+    for (int d = 0; d < D; ++d) ncells *= (p->family == VGGP_B0_GRIDDED ? p->K[d] + 1 : p->K[d] - 1);
     if (ncells >= ((i64)1 << 32) - 1) return fail(VGGP_E_UNSUPPORTED, "too many cells for 32-bit keys");
     std::vector<uint32_t> count((size_t)ncells + 1, 0u);
     if (n > 0) {
@@ -719,7 +726,16 @@ int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vgg
         VGGP_CUDA(cudaMalloc(&d_count, sizeof(uint32_t) * (ncells + 1)));
         VGGP_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * (ncells + 1), st));
         const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
-        k_cell_keys<T, D><<<blocks, 256, 0, st>>>(ka, (uint32_t)ncells, keys_in, idx_in);
+        if (p->family == VGGP_B0_GRIDDED) {       // extended cells: every observation has one (b0scan.cuh)
+            if constexpr (D <= 2) {
+                B0sKeyArgs<T, D> kb;
+                kb.n = n;
+                for (int d = 0; d < D; ++d) { kb.x[d] = ka.x[d]; kb.mesh[d] = p->mesh[d]; }
+                k_b0s_keys<T, D><<<blocks, 256, 0, st>>>(kb, keys_in, idx_in);
+            }
+        } else {
+            k_cell_keys<T, D><<<blocks, 256, 0, st>>>(ka, (uint32_t)ncells, keys_in, idx_in);
+        }
         VGGP_LAUNCH_CHECK();
         k_bin_histogram<<<blocks, 256, 0, st>>>(keys_in, n, d_count);
         VGGP_LAUNCH_CHECK();
@@ -759,20 +775,38 @@ int bin_pack_impl(vggp_plan* p, const vggp_binned_desc* desc, const void* const*
         VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_cell, L.run_cell.data(), sizeof(uint32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
         VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_n, L.run_n.data(), sizeof(int32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
         VGGP_CUDA(cudaMemcpyAsync(buf + desc->off_run_start, L.run_start.data(), sizeof(uint32_t) * 32 * L.n_tasks, cudaMemcpyHostToDevice, st));
-        BinGatherArgs<T, D> ga;
-        for (int d = 0; d < D; ++d) {
-            ga.x[d] = reinterpret_cast<const T*>(x[d]);
-            ga.knots[d] = p->d_knots[d];
-            ga.K[d] = p->K[d];
-        }
-        ga.y = reinterpret_cast<const T*>(y);
-        ga.perm = p->bin_perm;
-        ga.buf = buf;
-        ga.off_task_off = desc->off_task_off; ga.off_task_R = desc->off_task_R; ga.off_run_cell = desc->off_run_cell;
-        ga.off_run_n = desc->off_run_n; ga.off_run_start = desc->off_run_start; ga.off_data = desc->off_data;
-        ga.n_tasks = (int)L.n_tasks;
         const int blocks = (int)std::min<i64>(L.n_tasks, (i64)p->sm_count * 8);
-        k_bin_gather<T, D><<<blocks, 256, 0, st>>>(ga);
+        if (p->family == VGGP_B0_GRIDDED) {
+            if constexpr (D <= 2) {
+                B0sGatherArgs<T, D> gb0;
+                for (int d = 0; d < D; ++d) {
+                    gb0.x[d] = reinterpret_cast<const T*>(x[d]);
+                    gb0.knots[d] = p->d_knots[d];
+                    gb0.K[d] = p->K[d];
+                }
+                gb0.y = reinterpret_cast<const T*>(y);
+                gb0.perm = p->bin_perm;
+                gb0.buf = buf;
+                gb0.off_task_off = desc->off_task_off; gb0.off_task_R = desc->off_task_R; gb0.off_run_cell = desc->off_run_cell;
+                gb0.off_run_n = desc->off_run_n; gb0.off_run_start = desc->off_run_start; gb0.off_data = desc->off_data;
+                gb0.n_tasks = (int)L.n_tasks;
+                k_b0s_gather<T, D><<<blocks, 256, 0, st>>>(gb0);
+            }
+        } else {
+            BinGatherArgs<T, D> ga;
+            for (int d = 0; d < D; ++d) {
+                ga.x[d] = reinterpret_cast<const T*>(x[d]);
+                ga.knots[d] = p->d_knots[d];
+                ga.K[d] = p->K[d];
+            }
+            ga.y = reinterpret_cast<const T*>(y);
+            ga.perm = p->bin_perm;
+            ga.buf = buf;
+            ga.off_task_off = desc->off_task_off; ga.off_task_R = desc->off_task_R; ga.off_run_cell = desc->off_run_cell;
+            ga.off_run_n = desc->off_run_n; ga.off_run_start = desc->off_run_start; ga.off_data = desc->off_data;
+            ga.n_tasks = (int)L.n_tasks;
+            k_bin_gather<T, D><<<blocks, 256, 0, st>>>(ga);
+        }
         VGGP_LAUNCH_CHECK();
     }
     if (L.n > L.n_inside) {
@@ -889,6 +923,31 @@ int b0scan_alloc(vggp_plan* p) {
         if ((rc = dev_alloc(p, &tt, (i64)(9 * E1 * E2 * tsz)))) return rc;
     }
     p->b0s_Tt = tt;
+    // reverse side
+    i64 EE = E1, emmax = 0, mmmax = 0, gw_elems = 0;
+    for (int d = 0; d < p->D; ++d) {
+        emmax = std::max<i64>(emmax, (i64)(p->K[d] + 1) * (p->K[d] - 1));
+        mmmax = std::max<i64>(mmmax, (i64)(p->K[d] - 1) * (p->K[d] - 1));
+        gw_elems += 12 * (p->K[d] + 1);
+    }
+    if (p->D == 2) EE = E1 * (p->K[1] + 1);
+    const i64 nt = p->D == 1 ? 3 : 9;
+    unsigned char* raw = nullptr;
+    p->b0s_raw_bytes = (nt * EE + gw_elems) * (i64)tsz;
+    if ((rc = dev_alloc(p, &raw, p->b0s_raw_bytes))) return rc;
+    p->b0s_raw = raw;
+    if ((rc = dev_alloc(p, &p->b0s_GTd, nt * EE))) return rc;
+    for (int k = 0; k < 3; ++k)
+        if ((rc = dev_alloc(p, &p->b0s_S[k], emmax))) return rc;
+    for (int k = 0; k < 2; ++k)
+        if ((rc = dev_alloc(p, &p->b0s_Gam[k], emmax))) return rc;
+    if ((rc = dev_alloc(p, &p->b0s_bM, mmmax))) return rc;
+    if (p->D == 2) {
+        const i64 E2 = p->K[1] + 1, M2 = p->K[1] - 1;
+        for (int k = 0; k < 3; ++k)
+            if ((rc = dev_alloc(p, &p->b0s_H[k], M1 * E2))) return rc;
+        if ((rc = dev_alloc(p, &p->b0s_dA, M1 * M2))) return rc;
+    }
     p->b0s_ready = true;
     return 0;
 }
@@ -977,6 +1036,131 @@ int launch_predict_b0s(vggp_plan* p, const void* const* x, i64 n, void* mean, vo
     k_predict_b0s<T, D><<<blocks, 256, 0, st>>>(a);
     VGGP_LAUNCH_CHECK();
     return 0;
+}
+
+// Adjoint of the table construction: raw per-cell sums of k_obs_b0s -> d alpha, [bP | bQ] and the table part of G_l, in
+// the gbuf layout of the B0 family (what k_obs_b0 would have written).
+template <typename T, int D>
+int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
+    int rc;
+    const i64 E1 = p->K[0] + 1, M1 = p->K[0] - 1;
+    const i64 E2 = D == 2 ? p->K[1] + 1 : 1, M2 = D == 2 ? p->K[1] - 1 : 1;
+    const i64 EE = E1 * E2, NT = D == 1 ? 3 : 9;
+    const T* rawT = reinterpret_cast<const T*>(p->b0s_raw);
+    const T* GW[2] = {rawT + NT * EE, rawT + NT * EE + 12 * E1};
+    double* GTd = p->b0s_GTd;
+    k_b0s_to_double<T><<<ceil_div(NT * EE, 256), 256, 0, st>>>(rawT, GTd, NT * EE);
+    VGGP_LAUNCH_CHECK();
+    T* gb = reinterpret_cast<T*>(gbuf);
+    T* galpha = gb;
+    T* gfac = gb + p->M;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    double* gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    // ---- d alpha = sum_XY G1^X^T GT^{XY} G2^Y ----
+    if (D == 1) {
+        k_b0s_galpha1<T><<<ceil_div(M1, 256), 256, 0, st>>>(p->K[0], p->b0s_G[0][0], p->b0s_G[0][1], GTd, galpha);
+        VGGP_LAUNCH_CHECK();
+    } else {
+        for (int Y = 0; Y < 3; ++Y) {        // H^Y = sum_X G1^X^T GT^{XY}   (M1 x E2); X = C is a row shift
+            k_b0s_copy2d<<<ceil_div(M1 * E2, 256), 256, 0, st>>>(p->b0s_H[Y], E2, GTd + (3 * B0S_C + Y) * EE + E2, E2, (int)M1, (int)E2);
+            VGGP_LAUNCH_CHECK();
+            for (int x = 0; x < 2; ++x) {
+                const int X = x == 0 ? B0S_L : B0S_R;
+                if ((rc = gemm_rm(st, (int)M1, (int)E2, (int)E1, p->b0s_G[0][x], 1, M1, GTd + (3 * X + Y) * EE, E2, 1, p->b0s_H[Y], E2, 1.0, 1.0))) return rc;
+            }
+        }
+        k_b0s_copy2d<<<ceil_div(M1 * M2, 256), 256, 0, st>>>(p->b0s_dA, M2, p->b0s_H[B0S_C] + 1, E2, (int)M1, (int)M2);
+        VGGP_LAUNCH_CHECK();
+        for (int y = 0; y < 2; ++y) {
+            const int Y = y == 0 ? B0S_L : B0S_R;
+            if ((rc = gemm_rm(st, (int)M1, (int)M2, (int)E2, p->b0s_H[Y], E2, 1, p->b0s_G[1][y], M2, 1, p->b0s_dA, M2, 1.0, 1.0))) return rc;
+        }
+        k_b0s_from_double<T><<<ceil_div(M1 * M2, 256), 256, 0, st>>>(p->b0s_dA, galpha, M1 * M2);
+        VGGP_LAUNCH_CHECK();
+    }
+    // ---- [bP | bQ]_d = sum_XY G^X^T diag(gw^{XY}) G^Y ----
+    for (int d = 0; d < D; ++d) {
+        const int K = p->K[d];
+        const i64 M = K - 1, E = K + 1;
+        for (int mat = 0; mat < 2; ++mat) {
+            k_b0s_S<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, p->b0s_G[d][0], p->b0s_G[d][1], GW[d] + (i64)mat * 6 * E,
+                                                             p->b0s_S[0], p->b0s_S[1], p->b0s_S[2]);
+            VGGP_LAUNCH_CHECK();
+            k_b0s_copy2d<<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bM, M, p->b0s_S[B0S_C] + M, M, (int)M, (int)M);
+            VGGP_LAUNCH_CHECK();
+            for (int x = 0; x < 2; ++x)
+                if ((rc = gemm_rm(st, (int)M, (int)M, (int)E, p->b0s_G[d][x], 1, M, p->b0s_S[x == 0 ? B0S_L : B0S_R], M, 1, p->b0s_bM, M, 1.0, 1.0))) return rc;
+            k_b0s_from_double<T><<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bM, gfac + p->gfac_off[d] + (i64)mat * M * M, M * M);
+            VGGP_LAUNCH_CHECK();
+        }
+    }
+    // ---- table part of G_l[d] = sum_{X in L,R} <Gamma_d^X, dG_d^X / dl> ----
+    for (int d = 0; d < D; ++d) {
+        const int K = p->K[d];
+        const i64 M = K - 1, E = K + 1;
+        k_b0s_gamma_init<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, GW[d], p->b0s_V[d][0], p->b0s_V[d][1], p->b0s_V[d][2], p->b0s_V[d][3],
+                                                                  p->g.P[d], p->g.Q[d], D == 1 ? GTd : nullptr, D == 1 ? p->alpha : nullptr,
+                                                                  p->b0s_Gam[0], p->b0s_Gam[1]);
+        VGGP_LAUNCH_CHECK();
+        if (D == 2) {
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int S = s2 == 0 ? B0S_L : B0S_R;          // the side of THIS dimension
+                double* Gam = p->b0s_Gam[s2];
+                if (d == 0) {                                      // Gamma1^X += sum_Y GT^{XY} U^Y^T
+                    for (int y = 0; y < 2; ++y) {
+                        const int Y = y == 0 ? B0S_L : B0S_R;
+                        if ((rc = gemm_rm(st, (int)E1, (int)M1, (int)E2, GTd + (3 * S + Y) * EE, E2, 1, p->b0s_U[y], 1, E2, Gam, M1, 1.0, 1.0))) return rc;
+                    }
+                    if ((rc = gemm_rm(st, (int)E1, (int)M1, (int)M2, GTd + (3 * S + B0S_C) * EE + 1, E2, 1, p->alpha, 1, M2, Gam, M1, 1.0, 1.0))) return rc;
+                } else {                                           // Gamma2^Y += sum_X GT^{XY}^T B^X
+                    for (int x = 0; x < 2; ++x) {
+                        const int X = x == 0 ? B0S_L : B0S_R;
+                        if ((rc = gemm_rm(st, (int)E2, (int)M2, (int)E1, GTd + (3 * X + S) * EE, 1, E2, p->b0s_B[x], M2, 1, Gam, M2, 1.0, 1.0))) return rc;
+                    }
+                    if ((rc = gemm_rm(st, (int)E2, (int)M2, (int)M1, GTd + (3 * B0S_C + S) * EE + E2, 1, E2, p->alpha, M2, 1, Gam, M2, 1.0, 1.0))) return rc;
+                }
+            }
+        }
+        k_b0s_dot<<<std::min<int>(ceil_div(E * M, 256), 64), 256, 0, st>>>(p->b0s_Gam[0], p->b0s_Gam[1], p->b0s_G[d][2], p->b0s_G[d][3], E * M, gs + 3 + d);
+        VGGP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <typename T, int D>
+int launch_obs_b0s(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    int rc = b0scan_tables<T>(p, st);
+    if (rc) return rc;
+    VGGP_CUDA(cudaMemsetAsync(p->b0s_raw, 0, (size_t)p->b0s_raw_bytes, st));
+    B0sObsArgs<T, D> a;
+    b0scan_point_tables<T, D>(p, a.tab);
+    a.buf = reinterpret_cast<const unsigned char*>(binned);
+    a.off_task_off = desc->off_task_off; a.off_task_R = desc->off_task_R; a.off_run_cell = desc->off_run_cell;
+    a.off_run_n = desc->off_run_n; a.off_data = desc->off_data;
+    a.n_tasks = (int)desc->n_tasks;
+    const i64 E1 = p->K[0] + 1, EE = D == 1 ? E1 : E1 * (p->K[D - 1] + 1), NT = D == 1 ? 3 : 9;
+    T* rawT = reinterpret_cast<T*>(p->b0s_raw);
+    a.GT = rawT;
+    a.GW[0] = rawT + NT * EE;
+    if (D == 2) a.GW[D - 1] = rawT + NT * EE + 12 * E1;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    a.n_real = (double)desc->n;
+    a.counter = p->obs_counter;
+    VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
+    i64 blocks = (desc->n_tasks + (B0S_THREADS / 32) - 1) / (B0S_THREADS / 32);
+    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * 2));
+    k_obs_b0s<T, D><<<(unsigned)blocks, B0S_THREADS, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return b0scan_adjoint<T, D>(p, gbuf, st);
+}
+
+int obs_b0s_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    if (p->obs_dtype == VGGP_F32)
+        return p->D == 1 ? launch_obs_b0s<float, 1>(p, desc, binned, gbuf, st) : launch_obs_b0s<float, 2>(p, desc, binned, gbuf, st);
+    return p->D == 1 ? launch_obs_b0s<double, 1>(p, desc, binned, gbuf, st) : launch_obs_b0s<double, 2>(p, desc, binned, gbuf, st);
 }
 
 int predict_b0s_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, void* var, cudaStream_t st) {
@@ -1345,7 +1529,7 @@ int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t 
 
 int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_cap, vggp_binned_desc* desc, void* stream) {
     if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
-    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the binned layout is used by the B1 family only");
+    if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4");
     if (n >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^31 observations per shard");
     if (n > 0) {
@@ -1376,7 +1560,7 @@ int vggp_obs_bin_pack(vggp_plan* p, const vggp_binned_desc* desc, const void* co
 
 int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, void* stream) {
     if (!p || !desc || !gbuf) return fail(VGGP_E_ARG, "bad argument");
-    if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the binned layout is used by the B1 family only");
+    if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (desc->D != p->D) return fail(VGGP_E_ARG, "descriptor belongs to a plan of another dimension");
     cudaStream_t st = (cudaStream_t)stream;
     i64 n_elems, soff, nsc, total;
@@ -1384,6 +1568,7 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
     VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
     if (desc->n == 0) return 0;
     if (!binned) return fail(VGGP_E_ARG, "null binned buffer");
+    if (p->family == VGGP_B0_GRIDDED) return obs_b0s_dispatch(p, desc, binned, gbuf, st);     // scan form (b0scan.cuh)
     return obs_binned_dispatch(p, desc, binned, gbuf, st);
 }
 
