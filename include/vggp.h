@@ -142,7 +142,7 @@ int vggp_obs_fwd_bwd_packed(vggp_plan* plan, const void* const* xp, const void* 
 int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream);
 
 /*
- * Binned observation layout (B1 family; second form of the one-time setup, same gbuf as the packed form).
+ * Binned observation layout (second form of the one-time setup, same gbuf as the other forms).
  * The observations are ordered by grid cell and cut into RUNS -- all observations of one cell, or an equal share of
  * them when the cell holds more than `run_cap` -- and 32 runs of (almost) equal length form one warp task, so that
  * the fused kernel enters and leaves cells with all lanes active and needs no per-observation cell test.  Padding
@@ -154,8 +154,13 @@ int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64
  *   vggp_obs_bin_pack      fills `binned` (desc->bytes) from x[D], y; synchronises, frees the temporaries.
  *   vggp_obs_fwd_bwd_binned  the fused forward+backward over a binned buffer (asynchronous, allocation-free);
  *                          gbuf is zeroed by the call, exactly as vggp_obs_fwd_bwd_packed.
- * Status of this form: the host planner and the per-lane arithmetic are exercised on the CPU by tests/host_emul;
- * the device path is opt-in until it has been run on a B200.
+ * B0 family (D <= 2): the same three calls select the SCAN form of the cell-integrated features (csrc/b0scan.cuh,
+ * DESIGN.md section 10): cells are extended by one virtual cell on each side (observations outside the mesh do
+ * contribute in this family, n_inside == n), the per-observation kernel does O(1) work against per-cell tables built by
+ * dense products on the grid side, and an adjoint stage writes the same gbuf blocks vggp_obs_fwd_bwd writes for this
+ * family.  The first vggp_obs_fwd_bwd_binned on a B0 plan allocates the tables inside the plan.
+ * Status of this form: everything runs on the CPU under the SIMT emulator of tests/host_emul with oracle parity;
+ * the device path is opt-in until it has been run on a B200 (DESIGN.md sections 8 - 10).
  */
 typedef struct vggp_binned_desc {
     int64_t bytes;          /* size of the device buffer `binned` */

@@ -233,3 +233,32 @@ def test_b0_point_prediction_scan_form(vg, dev, knots, dtype, tol):
     var_ref = torch.prod(s2) - pp + qq
     assert (mean.cpu().double() - mu_ref).abs().max() <= tol * mu_ref.abs().max()
     assert (var.cpu().double() - var_ref).abs().max() <= tol * var_ref.abs().max()
+
+
+@pytest.mark.parametrize("knots,N", [((14,), 600), ((10, 8), 700), ((71, 14), 1500)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-3)])
+def test_b0_step_scan_form_matches_oracle(vg, dev, knots, N, dtype, tol):
+    """The B0 family through the binned layout = scan form (k_obs_b0s, csrc/b0scan.cuh): ELBO and every gradient against
+    the oracle's dense-feature evaluation, and against the dense-feature kernel k_obs_b0 on the same plan."""
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=21 + D, family=O.B0_GRIDDED, x_lo=-0.2, x_hi=1.2)
+    Xq, yq = X.to(dtype), y.to(dtype)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=1.3)
+    plan = vg.GridPlan(vg.B0_GRIDDED, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
+    binned = plan.bin(xs, yq.to(dev), run_cap=64)
+    assert binned.n_inside == N
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, binned, None, ell_scale=1.3)
+    assert plan.read_info() == 0 and out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item())
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10 and relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10 and relerr(dm, g_ref[3]) < tol * 10
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        assert relerr(torch.tril(dL[off:off + n * n].reshape(n, n).cpu()), torch.tril(g_ref[4 + d])) < tol * 10
+        off += n * n
+    out_d, dth_d, dm_d, _ = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=1.3)      # dense-feature kernel
+    assert abs(out[0].item() - out_d[0].item()) <= tol * abs(out_d[0].item()) and relerr(dm, dm_d) < tol * 10

@@ -110,10 +110,10 @@ class GriddedVariationalGP(nn.Module):
             self._obs = (xs, y)
             # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant); the packed
             # layout belongs to the compact-stencil (B1) kernel, the dense-feature (B0) kernel streams plain arrays
-            if self.family != _lib.B1_ASVGP:
+            if os.environ.get("VGGP_OBS_LAYOUT", "packed") == "binned":       # opt-in, DESIGN.md sections 8 and 10:
+                self._packed = self._plan.bin(xs, y)                          # B1: k_obs_b1_binned, B0: scan form
+            elif self.family != _lib.B1_ASVGP:
                 self._packed = None
-            elif os.environ.get("VGGP_OBS_LAYOUT", "packed") == "binned":     # opt-in, DESIGN.md section 8
-                self._packed = self._plan.bin(xs, y)
             else:
                 self._packed = self._plan.pack(xs, y, sort_by_cell=True)
         return self._plan
