@@ -244,6 +244,16 @@ int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, v
 int vggp_metrics(int dtype, const void* truth, const void* pred, int64_t n, double* out, void* stream);
 int vggp_predict_metrics(vggp_plan* plan, const void* const* x, const void* y, int64_t n, double* out, void* stream);
 
+/*
+ * Min-max scaling of the reference's data preparation (src/utils/dataprocessors.py:3-44), in the tensor's own dtype
+ * with separately rounded operations (bit for bit what torch computes).
+ *   vggp_minmax        minmax (DEVICE, 2 values of `dtype`) <- { min(x), max(x) }, n > 0; synchronises `stream`
+ *   vggp_minmax_scale  inverse == 0: y = (x - min) / (max - min);  inverse != 0: y = x * (max - min) + min.
+ *                      minmax is read on the device; y may alias x.
+ */
+int vggp_minmax(int dtype, const void* x, int64_t n, void* minmax, void* stream);
+int vggp_minmax_scale(int dtype, const void* x, int64_t n, const void* minmax, int inverse, void* y, void* stream);
+
 /* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
 
 /* Device pointer to a float64 workspace array of the last forward.  which: */

@@ -121,6 +121,15 @@ inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; cuda_emul::yi
 
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+// round-to-nearest arithmetic intrinsics: plain operators (the emulator is compiled with -ffp-contract=off)
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 inline double __longlong_as_double(long long v) { double f; memcpy(&f, &v, 8); return f; }
 

@@ -288,6 +288,31 @@ def test_metrics_kernels_under_emulation(emu, dtype, tol):
     plan.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_minmax_scaling_bit_exact_under_emulation(emu, dtype):
+    """vggp_minmax / vggp_minmax_scale against the reference's torch expressions (src/utils/dataprocessors.py:3-44)."""
+    lib, L = emu
+    code = L.F32 if dtype == np.float32 else L.F64
+    rng = np.random.default_rng(4)
+    for n in (1, 255, 70001):
+        x = (rng.standard_normal(n) * 37.0 + 11.0).astype(dtype)
+        mm = np.zeros(2, dtype=dtype)
+        assert lib.vggp_minmax(code, emul_lib.ptr(x), n, emul_lib.ptr(mm), None) == 0
+        assert mm[0] == x.min() and mm[1] == x.max()
+        if n == 1:
+            continue
+        y = np.zeros_like(x)
+        assert lib.vggp_minmax_scale(code, emul_lib.ptr(x), n, emul_lib.ptr(mm), 0, emul_lib.ptr(y), None) == 0
+        t = torch.from_numpy(x)
+        ref = (t - torch.min(t)) / (torch.max(t) - torch.min(t))
+        assert np.array_equal(y, ref.numpy())
+        back = np.zeros_like(x)
+        assert lib.vggp_minmax_scale(code, emul_lib.ptr(y), n, emul_lib.ptr(mm), 1, emul_lib.ptr(back), None) == 0
+        ref_back = ref * (torch.max(t) - torch.min(t)) + torch.min(t)
+        assert np.array_equal(back, ref_back.numpy())
+    assert lib.vggp_minmax(code, None, 0, emul_lib.ptr(mm), None) == -1
+
+
 def test_binned_abi_edge_cases_under_emulation(emu):
     lib, L = emu
     meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]

@@ -262,3 +262,22 @@ def test_b0_step_scan_form_matches_oracle(vg, dev, knots, N, dtype, tol):
         off += n * n
     out_d, dth_d, dm_d, _ = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=1.3)      # dense-feature kernel
     assert abs(out[0].item() - out_d[0].item()) <= tol * abs(out_d[0].item()) and relerr(dm, dm_d) < tol * 10
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_min_max_scaling_bit_exact(vg, dev, dtype):
+    """utils.dataprocessors (vggp_minmax / vggp_minmax_scale) against the reference's torch expressions
+    (src/utils/dataprocessors.py:3-44): identical bits."""
+    import importlib
+    dp = importlib.import_module("variational-gridded-gaussian-processes_b200.utils.dataprocessors")
+    g = torch.Generator().manual_seed(6)
+    t = (torch.randn(1000, 301, generator=g, dtype=torch.float64) * 37.0 + 11.0).to(dtype).to(dev)
+    scaled, lo, hi = dp.min_max_scaling(t)
+    assert lo.item() == t.min().item() and hi.item() == t.max().item()
+    ref = (t - torch.min(t)) / (torch.max(t) - torch.min(t))
+    assert torch.equal(scaled, ref)
+    assert torch.equal(dp.min_max_inverse(scaled, lo, hi), ref * (hi - lo) + lo)
+    s2, lo2, hi2 = dp.min_max_scaling(t, min=-200.0, max=300.0)
+    assert torch.equal(s2, (t - lo2) / (hi2 - lo2)) and lo2.item() == -200.0
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dp.min_max_scaling(t.cpu())

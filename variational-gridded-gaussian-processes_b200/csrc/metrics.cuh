@@ -101,4 +101,82 @@ __global__ void __launch_bounds__(256) k_predict_metrics(const __grid_constant__
     metrics_flush(sse, sae, s1, s2, red, m.out);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Min-max scaling of the reference's data preparation (src/utils/dataprocessors.py:3-44), SURVEY.md section 8f row 4:
+//   min_max_scaling:  (x - min) / (max - min)        min_max_inverse:  x * (max - min) + min
+// evaluated in the tensor's own dtype with separately rounded operations (no fma contraction), i.e. bit for bit what
+// torch computes; min and max stay on the device (no host synchronisation between the reduction and the scaling).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+// partial[2 b], partial[2 b + 1] = min, max over the elements block b visits.  n > 0.
+template <typename T>
+__global__ void __launch_bounds__(256) k_minmax_partial(const T* __restrict__ x, i64 n, T* __restrict__ partial) {
+    __shared__ T smin[8], smax[8];
+    T lo = x[0], hi = x[0];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const T v = x[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = smin[w] < lo ? smin[w] : lo; hi = smax[w] > hi ? smax[w] : hi; }
+        partial[2 * blockIdx.x] = lo;
+        partial[2 * blockIdx.x + 1] = hi;
+    }
+}
+// out[0] = min, out[1] = max over `blocks` partial pairs (one block)
+template <typename T>
+__global__ void __launch_bounds__(256) k_minmax_final(const T* __restrict__ partial, int blocks, T* __restrict__ out) {
+    __shared__ T smin[8], smax[8];
+    T lo = partial[0], hi = partial[1];
+    for (int b = threadIdx.x; b < blocks; b += 256) {
+        lo = partial[2 * b] < lo ? partial[2 * b] : lo;
+        hi = partial[2 * b + 1] > hi ? partial[2 * b + 1] : hi;
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = smin[w] < lo ? smin[w] : lo; hi = smax[w] > hi ? smax[w] : hi; }
+        out[0] = lo;
+        out[1] = hi;
+    }
+}
+
+__device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double rn_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+
+// inverse == 0: y = (x - mm[0]) / (mm[1] - mm[0]);  inverse != 0: y = x * (mm[1] - mm[0]) + mm[0]
+template <typename T>
+__global__ void __launch_bounds__(256) k_minmax_scale(const T* __restrict__ x, i64 n, const T* __restrict__ mm, int inverse,
+                                                      T* __restrict__ y) {
+    const T lo = mm[0], span = rn_sub(mm[1], mm[0]);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        y[i] = inverse ? rn_add(rn_mul(x[i], span), lo) : rn_div(rn_sub(x[i], lo), span);
+}
+
 }  // namespace vggp

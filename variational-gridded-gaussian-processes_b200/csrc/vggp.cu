@@ -1776,6 +1776,42 @@ int vggp_predict_metrics(vggp_plan* p, const void* const* x, const void* y, int6
     return predict_metrics_dispatch(p, x, y, n, out, st);
 }
 
+int vggp_minmax(int dtype, const void* x, int64_t n, void* minmax, void* stream) {
+    if (!x || !minmax || n <= 0) return fail(VGGP_E_ARG, "bad argument (n must be > 0)");
+    if (dtype != VGGP_F32 && dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "dtype must be VGGP_F32 or VGGP_F64");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<i64>((n + 255) / 256, 1024);
+    const size_t tsz = dtype == VGGP_F32 ? 4 : 8;
+    void* partial = nullptr;                 // 2 values per block; setup-time call, freed after the stream has drained
+    VGGP_CUDA(cudaMalloc(&partial, 2 * (size_t)blocks * tsz));
+    if (dtype == VGGP_F32) {
+        k_minmax_partial<float><<<blocks, 256, 0, st>>>((const float*)x, n, (float*)partial);
+        VGGP_LAUNCH_CHECK();
+        k_minmax_final<float><<<1, 256, 0, st>>>((const float*)partial, blocks, (float*)minmax);
+    } else {
+        k_minmax_partial<double><<<blocks, 256, 0, st>>>((const double*)x, n, (double*)partial);
+        VGGP_LAUNCH_CHECK();
+        k_minmax_final<double><<<1, 256, 0, st>>>((const double*)partial, blocks, (double*)minmax);
+    }
+    VGGP_LAUNCH_CHECK();
+    VGGP_CUDA(cudaStreamSynchronize(st));
+    cudaFree(partial);
+    return 0;
+}
+
+int vggp_minmax_scale(int dtype, const void* x, int64_t n, const void* minmax, int inverse, void* y, void* stream) {
+    if (n < 0 || !minmax) return fail(VGGP_E_ARG, "bad argument");
+    if (dtype != VGGP_F32 && dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "dtype must be VGGP_F32 or VGGP_F64");
+    if (n == 0) return 0;
+    if (!x || !y) return fail(VGGP_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 8);
+    if (dtype == VGGP_F32) k_minmax_scale<float><<<blocks, 256, 0, st>>>((const float*)x, n, (const float*)minmax, inverse, (float*)y);
+    else k_minmax_scale<double><<<blocks, 256, 0, st>>>((const double*)x, n, (const double*)minmax, inverse, (double*)y);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
 int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {
     if (!p || !ptr) return fail(VGGP_E_ARG, "null argument");
     if (which != VGGP_WS_ALPHA && which != VGGP_WS_SCAL && (dim < 0 || dim >= p->D)) return fail(VGGP_E_ARG, "bad dim");
