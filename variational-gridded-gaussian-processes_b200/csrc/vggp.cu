@@ -704,6 +704,21 @@ int pack_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, int 
 }
 
 // ---- binned layout (obs_binned.cuh) ---------------------------------------------------------------------
+// device temporaries of a setup call: freed on every exit path unless released to a longer-lived owner
+struct DevTemps {
+    std::vector<void*> ptrs;
+    ~DevTemps() { for (void* q : ptrs) if (q) cudaFree(q); }
+    template <typename P>
+    cudaError_t alloc(P** out, size_t bytes) {
+        void* q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *out = reinterpret_cast<P*>(q);
+        return e;
+    }
+    void release(void* q) { for (void*& r : ptrs) if (r == q) r = nullptr; }
+};
+
 template <typename T, int D>
 int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vggp_binned_desc* desc, cudaStream_t st) {
     i64 ncells = 1;
@@ -717,13 +732,14 @@ int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vgg
             ka.x[d] = reinterpret_cast<const T*>(x[d]);
             ka.mesh[d] = p->mesh[d];
         }
+        DevTemps tmp;
         uint32_t *keys_in = nullptr, *keys_out = nullptr, *idx_in = nullptr, *idx_out = nullptr, *d_count = nullptr;
-        void* temp = nullptr;
-        VGGP_CUDA(cudaMalloc(&keys_in, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&keys_out, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&idx_in, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&idx_out, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&d_count, sizeof(uint32_t) * (ncells + 1)));
+        unsigned char* temp = nullptr;
+        VGGP_CUDA(tmp.alloc(&keys_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&keys_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&idx_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&idx_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&d_count, sizeof(uint32_t) * (ncells + 1)));
         VGGP_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t) * (ncells + 1), st));
         const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
         if (p->family == VGGP_B0_GRIDDED) {       // extended cells: every observation has one (b0scan.cuh)
@@ -743,11 +759,11 @@ int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vgg
         while (((i64)1 << end_bit) <= ncells) ++end_bit;
         size_t temp_bytes = 0;
         VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
-        VGGP_CUDA(cudaMalloc(&temp, temp_bytes));
+        VGGP_CUDA(tmp.alloc(&temp, temp_bytes));
         VGGP_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
         VGGP_CUDA(cudaMemcpyAsync(count.data(), d_count, sizeof(uint32_t) * (ncells + 1), cudaMemcpyDeviceToHost, st));
         VGGP_CUDA(cudaStreamSynchronize(st));
-        cudaFree(keys_in); cudaFree(keys_out); cudaFree(idx_in); cudaFree(temp); cudaFree(d_count);
+        tmp.release(idx_out);                    // the cell-sorted order lives on until vggp_obs_bin_pack
         p->bin_perm = idx_out;
     }
     if (plan_bins(count.data(), ncells, run_cap, D, p->bin_pending) != 0) return fail(VGGP_E_ARG, "run_cap must be >= 4");
@@ -1782,8 +1798,9 @@ int vggp_minmax(int dtype, const void* x, int64_t n, void* minmax, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = (int)std::min<i64>((n + 255) / 256, 1024);
     const size_t tsz = dtype == VGGP_F32 ? 4 : 8;
-    void* partial = nullptr;                 // 2 values per block; setup-time call, freed after the stream has drained
-    VGGP_CUDA(cudaMalloc(&partial, 2 * (size_t)blocks * tsz));
+    DevTemps tmp;                            // 2 values per block; setup-time call, freed after the stream has drained
+    unsigned char* partial = nullptr;
+    VGGP_CUDA(tmp.alloc(&partial, 2 * (size_t)blocks * tsz));
     if (dtype == VGGP_F32) {
         k_minmax_partial<float><<<blocks, 256, 0, st>>>((const float*)x, n, (float*)partial);
         VGGP_LAUNCH_CHECK();
@@ -1795,7 +1812,6 @@ int vggp_minmax(int dtype, const void* x, int64_t n, void* minmax, void* stream)
     }
     VGGP_LAUNCH_CHECK();
     VGGP_CUDA(cudaStreamSynchronize(st));
-    cudaFree(partial);
     return 0;
 }
 
