@@ -43,17 +43,15 @@ else:
 PY
 }
 
-note "== 3. bench A/B at the headline config (N = 2^26, 512 x 512), kernels only"
+note "== 3. one-process K1 sweep at the headline config (N = 2^26, 512 x 512): K1 ms, step ms, fraction of the HBM peak"
+VARIANTS="packed"
+[ "$RC_LDG" = 0 ] && VARIANTS="$VARIANTS,binned:ldg:128,binned:ldg:256,binned:ldg:512"
+[ "$RC_TMA" = 0 ] && VARIANTS="$VARIANTS,binned:tma:128,binned:tma:256,binned:tma:512"
+rm -f "$OUT/sweep_k1.jsonl" "$OUT/sweep_k1_thin.jsonl"
+timeout 600 python tools/sweep_k1.py --variants "$VARIANTS" --out "$OUT/sweep_k1.jsonl" 2> "$OUT/sweep_k1.err" | tee -a "$SUM"
+note "== 4. thin shard (what one of 8 GPUs sees): N = 2^23"
+timeout 300 python tools/sweep_k1.py --n-obs 8388608 --variants "$VARIANTS" --out "$OUT/sweep_k1_thin.jsonl" 2> "$OUT/sweep_k1_thin.err" | tee -a "$SUM"
+note "== 5. full bench lines of the default path, plain and graph-replayed"
 bench packed
 bench packed_graph --cuda-graph
-if [ "$RC_LDG" = 0 ]; then
-    for cap in 128 256 512; do bench "binned_ldg_cap$cap" --obs-layout binned --binned-stream ldg --run-cap $cap; done
-fi
-if [ "$RC_TMA" = 0 ]; then
-    for cap in 128 256 512; do bench "binned_tma_cap$cap" --obs-layout binned --binned-stream tma --run-cap $cap; done
-fi
-note "== 4. thin shard (what one of 8 GPUs sees): N = 2^23"
-bench packed_n8m --n-obs 8388608
-[ "$RC_LDG" = 0 ] && bench binned_ldg_n8m --n-obs 8388608 --obs-layout binned --binned-stream ldg
-[ "$RC_TMA" = 0 ] && bench binned_tma_n8m --n-obs 8388608 --obs-layout binned --binned-stream tma
 note "done"
