@@ -64,6 +64,68 @@ __global__ void __launch_bounds__(256) k_b0s_G(const __grid_constant__ B0sGArgs 
     a.dGR[d][idx] = dgr;
 }
 
+// Per-cell decay factors of dimension blockIdx.y: eps_c = exp(-h_c / l), gam_c = 1 - eps_c (via expm1), d eps_c / d l.
+// GL and GR are rank-one decay (semiseparable) matrices: moving the position by one cell multiplies everything
+// accumulated so far by eps_c and adds gam_c times the new cell, so a product G^X v is a first-order recurrence.
+// out[d] = [eps (M) | gam (M) | deps (M)].  grid (ceil(Mmax / 256), D)
+struct B0sEpsArgs {
+    const float* knots[VGGP_MAX_D];
+    int K[VGGP_MAX_D];
+    double* out[VGGP_MAX_D];
+    const double* theta;
+};
+__global__ void __launch_bounds__(256) k_b0s_eps(const __grid_constant__ B0sEpsArgs a) {
+    const int d = blockIdx.y, M = a.K[d] - 1;
+    const int c = (int)blockIdx.x * 256 + threadIdx.x;
+    if (c >= M) return;
+    const double l = a.theta[d];
+    const double h = (double)a.knots[d][c + 1] - (double)a.knots[d][c];
+    const double e = exp(-h / l);
+    a.out[d][c] = e;
+    a.out[d][M + c] = -expm1(-h / l);
+    a.out[d][2 * M + c] = e * h / (l * l);
+}
+
+// L- and R-transform of every fibre of a tensor along one mode, one thread per fibre, two sequential sweeps:
+//   L[e+1] = eps_{e-1} L[e] + gam_{e-1} v_{e-1}  (e = 1..M, L[0] = L[1] = 0),   R[e-1] = gam_{e-1} v_{e-1} + eps_{e-1} R[e]  (e = M..1, R[M] = R[M+1] = 0)
+// i.e. dstL = G^L v, dstR = G^R v with E = M + 2 entries per fibre.  Element i of fibre f of the source is at
+// src[f_hi * s_hi + f_lo * s_lo + i * s_mode] with f = f_hi * n_lo + f_lo (same decomposition for the destination).
+struct B0sScanArgs {
+    const double* src;
+    double* dstL;
+    double* dstR;
+    const double* eps;       // [eps | gam | deps] of the mode's dimension
+    int M;
+    i64 n_fibres, n_lo;
+    i64 s_hi, s_lo, s_mode;  // source strides
+    i64 d_hi, d_lo, d_mode;  // destination strides
+};
+__global__ void __launch_bounds__(128) k_b0s_scan(const __grid_constant__ B0sScanArgs a) {
+    const i64 f = (i64)blockIdx.x * 128 + threadIdx.x;
+    if (f >= a.n_fibres) return;
+    const i64 fh = f / a.n_lo, fl = f - fh * a.n_lo;
+    const double* __restrict__ v = a.src + fh * a.s_hi + fl * a.s_lo;
+    double* __restrict__ L = a.dstL + fh * a.d_hi + fl * a.d_lo;
+    double* __restrict__ R = a.dstR + fh * a.d_hi + fl * a.d_lo;
+    const double* __restrict__ eps = a.eps;
+    const double* __restrict__ gam = a.eps + a.M;
+    const int M = a.M;
+    double acc = 0.0;
+    L[0] = 0.0;
+    L[a.d_mode] = 0.0;
+    for (int e = 1; e <= M; ++e) {
+        acc = fma(eps[e - 1], acc, gam[e - 1] * v[(i64)(e - 1) * a.s_mode]);
+        L[(i64)(e + 1) * a.d_mode] = acc;
+    }
+    acc = 0.0;
+    R[(i64)(M + 1) * a.d_mode] = 0.0;
+    R[(i64)M * a.d_mode] = 0.0;
+    for (int e = M; e >= 1; --e) {
+        acc = fma(eps[e - 1], acc, gam[e - 1] * v[(i64)(e - 1) * a.s_mode]);
+        R[(i64)(e - 1) * a.d_mode] = acc;
+    }
+}
+
 // Per-cell quadratic-form tables of dimension blockIdx.y, one warp per extended cell e:
 //   W[mat][s][e], mat 0 = P, 1 = Q, s = LL, LC, LR, CC, CR, RR, from V^X = G^X Mat (E x M) and the rows of G^Y.
 // grid (ceil((K+1) / 8), D), 256 threads

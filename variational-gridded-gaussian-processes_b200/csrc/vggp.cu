@@ -58,6 +58,7 @@ struct vggp_plan {
     bool b0s_ready = false;
     double* b0s_G[VGGP_MAX_D][4] = {};     // GL, GR, dGL/dl, dGR/dl: (K+1) x (K-1)
     double* b0s_V[VGGP_MAX_D][4] = {};     // GL P, GR P, GL Q, GR Q: (K+1) x (K-1)
+    double* b0s_eps[VGGP_MAX_D] = {};      // [eps | gam | d eps / d l], K-1 each
     double* b0s_U[2] = {};                 // A G2^y^T: M1 x E2
     double* b0s_B[2] = {};                 // G1^x A:   E1 x M2
     double* b0s_TT[4] = {};                // G1^x U^y: E1 x E2
@@ -920,6 +921,7 @@ int b0scan_alloc(vggp_plan* p) {
             if ((rc = dev_alloc(p, &p->b0s_G[d][k], em))) return rc;
             if ((rc = dev_alloc(p, &p->b0s_V[d][k], em))) return rc;
         }
+        if ((rc = dev_alloc(p, &p->b0s_eps[d], (i64)3 * (p->K[d] - 1)))) return rc;
         unsigned char* w = nullptr;
         if ((rc = dev_alloc(p, &w, (i64)(12 * (p->K[d] + 1) * tsz)))) return rc;
         p->b0s_W[d] = w;
@@ -968,31 +970,53 @@ int b0scan_alloc(vggp_plan* p) {
     return 0;
 }
 
-// Per-cell tables from the state of the last grid forward (alpha, P_d, Q_d, theta).
+// dstL = G^L src, dstR = G^R src along one mode (k_b0s_scan): n_hi x n_lo fibres of M elements -> M + 2 entries
+int b0s_scan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
+             double* dstL, double* dstR, i64 d_hi, i64 d_lo, i64 d_mode) {
+    B0sScanArgs a;
+    a.src = src; a.dstL = dstL; a.dstR = dstR; a.eps = eps; a.M = M;
+    a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
+    a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
+    a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
+    k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+// Per-cell tables from the state of the last grid forward (alpha, P_d, Q_d, theta).  Every product with G^L / G^R is a
+// first-order recurrence along a mode (k_b0s_scan, O(M) per mode); the dense G matrices are still written because the
+// quadratic-form tables take row dots with them and the adjoint stage contracts with their lengthscale derivatives.
 template <typename T>
 int b0scan_tables(vggp_plan* p, cudaStream_t st) {
     int rc = b0scan_alloc(p);
     if (rc) return rc;
     const int D = p->D;
     B0sGArgs ga;
-    int emax = 0;
+    B0sEpsArgs ea;
+    int emax = 0, mmax = 0;
     for (int d = 0; d < D; ++d) {
         ga.knots[d] = p->d_knots[d];
         ga.K[d] = p->K[d];
         ga.GL[d] = p->b0s_G[d][0]; ga.GR[d] = p->b0s_G[d][1]; ga.dGL[d] = p->b0s_G[d][2]; ga.dGR[d] = p->b0s_G[d][3];
+        ea.knots[d] = p->d_knots[d];
+        ea.K[d] = p->K[d];
+        ea.out[d] = p->b0s_eps[d];
         emax = std::max(emax, (p->K[d] + 1) * (p->K[d] - 1));
+        mmax = std::max(mmax, p->K[d] - 1);
     }
     ga.theta = p->theta_dev;
+    ea.theta = p->theta_dev;
     k_b0s_G<<<dim3(ceil_div(emax, 256), D), 256, 0, st>>>(ga);
+    VGGP_LAUNCH_CHECK();
+    k_b0s_eps<<<dim3(ceil_div(mmax, 256), D), 256, 0, st>>>(ea);
     VGGP_LAUNCH_CHECK();
     B0sWArgs<T> wa;
     int kmax = 0;
     for (int d = 0; d < D; ++d) {
         const int M = p->K[d] - 1, E = p->K[d] + 1;
         const double* mats[2] = {p->g.P[d], p->g.Q[d]};
-        for (int mat = 0; mat < 2; ++mat)
-            for (int x = 0; x < 2; ++x)      // V = G^x Mat
-                if ((rc = gemm_rm(st, E, M, M, p->b0s_G[d][x], M, 1, mats[mat], M, 1, p->b0s_V[d][2 * mat + x], M))) return rc;
+        for (int mat = 0; mat < 2; ++mat)       // V^x = G^x Mat (E x M): transform along the row index, fibres = columns
+            if ((rc = b0s_scan(st, p->b0s_eps[d], M, 1, M, mats[mat], 0, 1, M, p->b0s_V[d][2 * mat], p->b0s_V[d][2 * mat + 1], 0, 1, M))) return rc;
         wa.K[d] = p->K[d];
         wa.GL[d] = p->b0s_G[d][0]; wa.GR[d] = p->b0s_G[d][1];
         for (int k = 0; k < 4; ++k) wa.V[d][k] = p->b0s_V[d][k];
@@ -1009,13 +1033,13 @@ int b0scan_tables(vggp_plan* p, cudaStream_t st) {
         return 0;
     }
     const int E2 = p->K[1] + 1, M2 = p->K[1] - 1;
-    for (int y = 0; y < 2; ++y)              // U^y = A G2^y^T
-        if ((rc = gemm_rm(st, M1, E2, M2, p->alpha, M2, 1, p->b0s_G[1][y], 1, M2, p->b0s_U[y], E2))) return rc;
-    for (int x = 0; x < 2; ++x) {            // B^x = G1^x A,  TT[2x+y] = G1^x U^y
-        if ((rc = gemm_rm(st, E1, M2, M1, p->b0s_G[0][x], M1, 1, p->alpha, M2, 1, p->b0s_B[x], M2))) return rc;
-        for (int y = 0; y < 2; ++y)
-            if ((rc = gemm_rm(st, E1, E2, M1, p->b0s_G[0][x], M1, 1, p->b0s_U[y], E2, 1, p->b0s_TT[2 * x + y], E2))) return rc;
-    }
+    // U^y = A G2^y^T (M1 x E2): transform along dimension 2, fibres = rows of A
+    if ((rc = b0s_scan(st, p->b0s_eps[1], M2, M1, 1, p->alpha, M2, 0, 1, p->b0s_U[0], p->b0s_U[1], E2, 0, 1))) return rc;
+    // B^x = G1^x A (E1 x M2): transform along dimension 1, fibres = columns of A
+    if ((rc = b0s_scan(st, p->b0s_eps[0], M1, 1, M2, p->alpha, 0, 1, M2, p->b0s_B[0], p->b0s_B[1], 0, 1, M2))) return rc;
+    // TT[2x+y] = G1^x U^y (E1 x E2): transform along dimension 1 of U^y, fibres = its columns
+    for (int y = 0; y < 2; ++y)
+        if ((rc = b0s_scan(st, p->b0s_eps[0], M1, 1, E2, p->b0s_U[y], 0, 1, E2, p->b0s_TT[y], p->b0s_TT[2 + y], 0, 1, E2))) return rc;
     B0sT2Args<T> ta;
     ta.E1 = E1; ta.E2 = E2; ta.M1 = M1; ta.M2 = M2;
     for (int k = 0; k < 4; ++k) ta.TT[k] = p->b0s_TT[k];
