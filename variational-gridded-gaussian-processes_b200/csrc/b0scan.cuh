@@ -99,6 +99,8 @@ struct B0sScanArgs {
     i64 n_fibres, n_lo;
     i64 s_hi, s_lo, s_mode;  // source strides
     i64 d_hi, d_lo, d_mode;  // destination strides
+    double* tanL;            // optional: d dstL / d l and d dstR / d l (same layout as the destination), else nullptr
+    double* tanR;
 };
 __global__ void __launch_bounds__(128) k_b0s_scan(const __grid_constant__ B0sScanArgs a) {
     const i64 f = (i64)blockIdx.x * 128 + threadIdx.x;
@@ -110,19 +112,71 @@ __global__ void __launch_bounds__(128) k_b0s_scan(const __grid_constant__ B0sSca
     const double* __restrict__ eps = a.eps;
     const double* __restrict__ gam = a.eps + a.M;
     const int M = a.M;
-    double acc = 0.0;
+    const double* __restrict__ deps = a.eps + 2 * a.M;
+    double* __restrict__ TL = a.tanL ? a.tanL + fh * a.d_hi + fl * a.d_lo : nullptr;
+    double* __restrict__ TR = a.tanR ? a.tanR + fh * a.d_hi + fl * a.d_lo : nullptr;
+    // tangent: d acc' = eps d acc + deps (acc - v)   (gam = 1 - eps)
+    double acc = 0.0, tan = 0.0;
     L[0] = 0.0;
     L[a.d_mode] = 0.0;
+    if (TL) { TL[0] = 0.0; TL[a.d_mode] = 0.0; }
     for (int e = 1; e <= M; ++e) {
-        acc = fma(eps[e - 1], acc, gam[e - 1] * v[(i64)(e - 1) * a.s_mode]);
+        const double vv = v[(i64)(e - 1) * a.s_mode];
+        tan = fma(eps[e - 1], tan, deps[e - 1] * (acc - vv));
+        acc = fma(eps[e - 1], acc, gam[e - 1] * vv);
         L[(i64)(e + 1) * a.d_mode] = acc;
+        if (TL) TL[(i64)(e + 1) * a.d_mode] = tan;
     }
     acc = 0.0;
+    tan = 0.0;
     R[(i64)(M + 1) * a.d_mode] = 0.0;
     R[(i64)M * a.d_mode] = 0.0;
+    if (TR) { TR[(i64)(M + 1) * a.d_mode] = 0.0; TR[(i64)M * a.d_mode] = 0.0; }
     for (int e = M; e >= 1; --e) {
-        acc = fma(eps[e - 1], acc, gam[e - 1] * v[(i64)(e - 1) * a.s_mode]);
+        const double vv = v[(i64)(e - 1) * a.s_mode];
+        tan = fma(eps[e - 1], tan, deps[e - 1] * (acc - vv));
+        acc = fma(eps[e - 1], acc, gam[e - 1] * vv);
         R[(i64)(e - 1) * a.d_mode] = acc;
+        if (TR) TR[(i64)(e - 1) * a.d_mode] = tan;
+    }
+}
+
+// Adjoint of the three transforms along one mode, one thread per fibre:
+//   dv[i] = sum_e GL[e][i] gL[e] + GR[e][i] gR[e]  +  gC[i + 1]           (gC may be nullptr)
+// two sequential sweeps: a[e] = gL[e] + eps_{e-1} a[e+1] (e = M..1), dv[e-1] += gam_{e-1} a[e+1];
+//                        b[e] = gR[e] + eps_{e-1} b[e-1] (e = 1..M), dv[e-1] += gam_{e-1} b[e-1].
+// gL / gC / gR share the layout (g_hi, g_lo, g_mode) with E = M + 2 entries per fibre; dv has M entries per fibre.
+struct B0sAdjArgs {
+    const double* gL;
+    const double* gC;
+    const double* gR;
+    double* dv;
+    const double* eps;
+    int M;
+    i64 n_fibres, n_lo;
+    i64 g_hi, g_lo, g_mode;
+    i64 v_hi, v_lo, v_mode;
+};
+__global__ void __launch_bounds__(128) k_b0s_scan_adj(const __grid_constant__ B0sAdjArgs a) {
+    const i64 f = (i64)blockIdx.x * 128 + threadIdx.x;
+    if (f >= a.n_fibres) return;
+    const i64 fh = f / a.n_lo, fl = f - fh * a.n_lo;
+    const i64 go = fh * a.g_hi + fl * a.g_lo;
+    const double* __restrict__ gL = a.gL + go;
+    const double* __restrict__ gR = a.gR + go;
+    double* __restrict__ dv = a.dv + fh * a.v_hi + fl * a.v_lo;
+    const double* __restrict__ eps = a.eps;
+    const double* __restrict__ gam = a.eps + a.M;
+    const int M = a.M;
+    double carry = gL[(i64)(M + 1) * a.g_mode];               // a[M+1]
+    for (int e = M; e >= 1; --e) {
+        dv[(i64)(e - 1) * a.v_mode] = gam[e - 1] * carry + (a.gC ? a.gC[go + (i64)e * a.g_mode] : 0.0);
+        carry = fma(eps[e - 1], carry, gL[(i64)e * a.g_mode]);
+    }
+    carry = gR[0];                                            // b[0]
+    for (int e = 1; e <= M; ++e) {
+        dv[(i64)(e - 1) * a.v_mode] += gam[e - 1] * carry;
+        carry = fma(eps[e - 1], carry, gR[(i64)e * a.g_mode]);
     }
 }
 
@@ -626,15 +680,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_b0s_from_double(const double* __restrict__ src, T* __restrict__ dst, i64 n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = (T)src[i];
 }
-// dst (rows x cols, leading dimension ldd) = src view (leading dimension lds)
-__global__ void __launch_bounds__(256) k_b0s_copy2d(double* __restrict__ dst, i64 ldd, const double* __restrict__ src, i64 lds,
-                                                    int rows, int cols) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < (i64)rows * cols; i += (i64)gridDim.x * blockDim.x) {
-        const i64 r = i / cols, c = i - r * cols;
-        dst[r * ldd + c] = src[r * lds + c];
-    }
-}
-
 __device__ __forceinline__ double b0s_gw(const double* gw6, int X, int Y) { return gw6[b0s_sym_index(X, Y)]; }
 
 // One dimension, one matrix (mat 0 = P, 1 = Q):  S^X[e][i] = sum_Y gw^{XY}[e] G^Y[e][i]   (X = L, C, R; G^C[e] = unit row e-1)
@@ -659,53 +704,6 @@ __global__ void __launch_bounds__(256) k_b0s_S(int K, const double* __restrict__
     SR[idx] = out[2];
 }
 
-// Quadratic-form part of Gamma^X = d(objective) / d G^X for X = L, R (and, in 1-D, the mean part GT^X[e] A[i]):
-//   Gamma^X[e][i] = sum_Y gwP^{XY}[e] VP^Y[e][i] - gwQ^{XY}[e] VQ^Y[e][i],    V^C[e] = row e-1 of the matrix
-// grid (ceil(E M / 256)), 256 threads
-template <typename T>
-__global__ void __launch_bounds__(256) k_b0s_gamma_init(int K, const T* __restrict__ GW /* [2][6][E] */,
-                                                        const double* __restrict__ VPL, const double* __restrict__ VPR,
-                                                        const double* __restrict__ VQL, const double* __restrict__ VQR,
-                                                        const double* __restrict__ P, const double* __restrict__ Q,
-                                                        const double* __restrict__ GT1 /* 1-D: [3][E] float64, else nullptr */,
-                                                        const double* __restrict__ A1 /* 1-D: alpha */,
-                                                        double* __restrict__ GamL, double* __restrict__ GamR) {
-    const int M = K - 1, E = K + 1;
-    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (i64)E * M) return;
-    const int e = (int)(idx / M), i = (int)(idx % M), c = e - 1;
-    const bool real = c >= 0 && c < M;
-    double gp[6], gq[6];
-#pragma unroll
-    for (int s = 0; s < 6; ++s) { gp[s] = (double)GW[(i64)s * E + e]; gq[s] = (double)GW[(i64)(6 + s) * E + e]; }
-    const double vp[3] = {VPL[idx], real ? P[(i64)c * M + i] : 0.0, VPR[idx]};
-    const double vq[3] = {VQL[idx], real ? Q[(i64)c * M + i] : 0.0, VQR[idx]};
-    double out[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int X = k == 0 ? B0S_L : B0S_R;
-        double v = 0.0;
-#pragma unroll
-        for (int Y = 0; Y < 3; ++Y) v += b0s_gw(gp, X, Y) * vp[Y] - b0s_gw(gq, X, Y) * vq[Y];
-        if (GT1) v += GT1[(i64)X * E + e] * A1[i];
-        out[k] = v;
-    }
-    GamL[idx] = out[0];
-    GamR[idx] = out[1];
-}
-
-// out += <GamL, dGL> + <GamR, dGR>
-__global__ void __launch_bounds__(256) k_b0s_dot(const double* __restrict__ GamL, const double* __restrict__ GamR,
-                                                 const double* __restrict__ dGL, const double* __restrict__ dGR, i64 n,
-                                                 double* __restrict__ out) {
-    __shared__ double red[32];
-    double acc = 0.0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        acc += GamL[i] * dGL[i] + GamR[i] * dGR[i];
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
-}
-
 // 1-D d alpha: galpha[i] = sum_X sum_e G^X[e][i] GT^X[e]  (one thread per i)
 template <typename T>
 __global__ void __launch_bounds__(256) k_b0s_galpha1(int K, const double* __restrict__ GL, const double* __restrict__ GR,
@@ -717,6 +715,59 @@ __global__ void __launch_bounds__(256) k_b0s_galpha1(int K, const double* __rest
     for (int e = 0; e < E; ++e)
         acc += GL[(i64)e * M + i] * GT[(i64)B0S_L * E + e] + GR[(i64)e * M + i] * GT[(i64)B0S_R * E + e];
     galpha[i] = (T)acc;
+}
+
+// Table part of the lengthscale gradient that goes through the quadratic-form tables (and, in 1-D, the mean tables):
+//   out += sum_e sum_{X in L,R} sum_Y  gwP^{XY}[e] <VP^Y[e,:], dG^X[e,:]>  -  gwQ^{XY}[e] <VQ^Y[e,:], dG^X[e,:]>
+//          (+ 1-D:  GT^X[e] <A, dG^X[e,:]>),                      V^C[e,:] = row e-1 of the matrix
+// one warp per extended cell e.  grid (ceil(E / 8)), 256 threads
+template <typename T>
+__global__ void __launch_bounds__(256) k_b0s_gl_rows(int K, const T* __restrict__ GW /* [2][6][E] */,
+                                                     const double* __restrict__ VPL, const double* __restrict__ VPR,
+                                                     const double* __restrict__ VQL, const double* __restrict__ VQR,
+                                                     const double* __restrict__ P, const double* __restrict__ Q,
+                                                     const double* __restrict__ dGL, const double* __restrict__ dGR,
+                                                     const double* __restrict__ GT1 /* 1-D: [3][E] float64, else nullptr */,
+                                                     const double* __restrict__ A1, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int M = K - 1, E = K + 1;
+    const int lane = threadIdx.x & 31;
+    const int e = (int)blockIdx.x * 8 + (threadIdx.x >> 5);
+    double acc = 0.0;
+    if (e < E) {
+        const int c = e - 1;
+        const bool real = c >= 0 && c < M;
+        double gp[6], gq[6];
+#pragma unroll
+        for (int s = 0; s < 6; ++s) { gp[s] = (double)GW[(i64)s * E + e]; gq[s] = (double)GW[(i64)(6 + s) * E + e]; }
+        const i64 row = (i64)e * M;
+        for (int i = lane; i < M; i += 32) {
+            const double vp[3] = {VPL[row + i], real ? P[(i64)c * M + i] : 0.0, VPR[row + i]};
+            const double vq[3] = {VQL[row + i], real ? Q[(i64)c * M + i] : 0.0, VQR[row + i]};
+            const double dg[2] = {dGL[row + i], dGR[row + i]};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int X = k == 0 ? B0S_L : B0S_R;
+                double v = 0.0;
+#pragma unroll
+                for (int Y = 0; Y < 3; ++Y) v += b0s_gw(gp, X, Y) * vp[Y] - b0s_gw(gq, X, Y) * vq[Y];
+                if (GT1) v += GT1[(i64)X * E + e] * A1[i];
+                acc = fma(v, dg[k], acc);
+            }
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// out += sum_i a[i] b[i]
+__global__ void __launch_bounds__(256) k_b0s_dot1(const double* __restrict__ x, const double* __restrict__ y, i64 n,
+                                                  double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) acc = fma(x[i], y[i], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
 }  // namespace vggp

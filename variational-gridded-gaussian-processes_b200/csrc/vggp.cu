@@ -898,18 +898,6 @@ int obs_binned_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* 
 }
 
 // ---- B0 family, scan form (b0scan.cuh) -------------------------------------------------------------------
-// C (m x n, row-major, leading dimension ldc) = alpha * A * B + beta * C with arbitrary operand strides
-int gemm_rm(cudaStream_t st, int m, int n, int k, const double* A, i64 rsA, i64 csA, const double* B, i64 rsB, i64 csB,
-            double* C, i64 ldc, double alpha = 1.0, double beta = 0.0) {
-    GemmDesc d;
-    gemm_desc_defaults(d);
-    d.A = A; d.B = B; d.C = C;
-    d.m = m; d.n = n; d.k = k;
-    d.rsA = rsA; d.csA = csA; d.rsB = rsB; d.csB = csB; d.rsC = ldc; d.csC = 1;
-    d.alpha = alpha; d.beta = beta;
-    return launch_one(d, g_use_mma, st);
-}
-
 int b0scan_alloc(vggp_plan* p) {
     if (p->b0s_ready) return 0;
     if (p->family != VGGP_B0_GRIDDED || p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the scan form is built for the B0 family, D <= 2");
@@ -974,7 +962,7 @@ int b0scan_alloc(vggp_plan* p) {
 int b0s_scan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
              double* dstL, double* dstR, i64 d_hi, i64 d_lo, i64 d_mode) {
     B0sScanArgs a;
-    a.src = src; a.dstL = dstL; a.dstR = dstR; a.eps = eps; a.M = M;
+    a.src = src; a.dstL = dstL; a.dstR = dstR; a.tanL = nullptr; a.tanR = nullptr; a.eps = eps; a.M = M;
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
     a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
@@ -1078,8 +1066,39 @@ int launch_predict_b0s(vggp_plan* p, const void* const* x, i64 n, void* mean, vo
     return 0;
 }
 
+int b0s_scan_tan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
+                 double* dstL, double* dstR, double* tanL, double* tanR, i64 d_hi, i64 d_lo, i64 d_mode) {
+    B0sScanArgs a;
+    a.src = src; a.dstL = dstL; a.dstR = dstR; a.tanL = tanL; a.tanR = tanR; a.eps = eps; a.M = M;
+    a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
+    a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
+    a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
+    k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int b0s_scan_adj(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* gL, const double* gC, const double* gR,
+                 i64 g_hi, i64 g_lo, i64 g_mode, double* dv, i64 v_hi, i64 v_lo, i64 v_mode) {
+    B0sAdjArgs a;
+    a.gL = gL; a.gC = gC; a.gR = gR; a.dv = dv; a.eps = eps; a.M = M;
+    a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
+    a.g_hi = g_hi; a.g_lo = g_lo; a.g_mode = g_mode;
+    a.v_hi = v_hi; a.v_lo = v_lo; a.v_mode = v_mode;
+    k_b0s_scan_adj<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int b0s_dot(cudaStream_t st, const double* x, const double* y, i64 n, double* out) {
+    k_b0s_dot1<<<std::min<int>(ceil_div(n, 256), 64), 256, 0, st>>>(x, y, n, out);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
 // Adjoint of the table construction: raw per-cell sums of k_obs_b0s -> d alpha, [bP | bQ] and the table part of G_l, in
-// the gbuf layout of the B0 family (what k_obs_b0 would have written).
+// the gbuf layout of the B0 family (what k_obs_b0 would have written).  Like the forward, every product with G^L / G^R or
+// their lengthscale derivatives is a first-order recurrence along a mode (adjoint and tangent sweeps): O(M) per mode.
 template <typename T, int D>
 int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
     int rc;
@@ -1097,29 +1116,20 @@ int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     double* gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    auto GT = [&](int X, int Y) { return GTd + (i64)(3 * X + Y) * EE; };
     // ---- d alpha = sum_XY G1^X^T GT^{XY} G2^Y ----
     if (D == 1) {
         k_b0s_galpha1<T><<<ceil_div(M1, 256), 256, 0, st>>>(p->K[0], p->b0s_G[0][0], p->b0s_G[0][1], GTd, galpha);
         VGGP_LAUNCH_CHECK();
     } else {
-        for (int Y = 0; Y < 3; ++Y) {        // H^Y = sum_X G1^X^T GT^{XY}   (M1 x E2); X = C is a row shift
-            k_b0s_copy2d<<<ceil_div(M1 * E2, 256), 256, 0, st>>>(p->b0s_H[Y], E2, GTd + (3 * B0S_C + Y) * EE + E2, E2, (int)M1, (int)E2);
-            VGGP_LAUNCH_CHECK();
-            for (int x = 0; x < 2; ++x) {
-                const int X = x == 0 ? B0S_L : B0S_R;
-                if ((rc = gemm_rm(st, (int)M1, (int)E2, (int)E1, p->b0s_G[0][x], 1, M1, GTd + (3 * X + Y) * EE, E2, 1, p->b0s_H[Y], E2, 1.0, 1.0))) return rc;
-            }
-        }
-        k_b0s_copy2d<<<ceil_div(M1 * M2, 256), 256, 0, st>>>(p->b0s_dA, M2, p->b0s_H[B0S_C] + 1, E2, (int)M1, (int)M2);
-        VGGP_LAUNCH_CHECK();
-        for (int y = 0; y < 2; ++y) {
-            const int Y = y == 0 ? B0S_L : B0S_R;
-            if ((rc = gemm_rm(st, (int)M1, (int)M2, (int)E2, p->b0s_H[Y], E2, 1, p->b0s_G[1][y], M2, 1, p->b0s_dA, M2, 1.0, 1.0))) return rc;
-        }
+        for (int Y = 0; Y < 3; ++Y)          // H^Y = sum_X G1^X^T GT^{XY}  (M1 x E2): adjoint sweep along dimension 1, fibres = columns
+            if ((rc = b0s_scan_adj(st, p->b0s_eps[0], (int)M1, 1, E2, GT(B0S_L, Y), GT(B0S_C, Y), GT(B0S_R, Y), 0, 1, E2, p->b0s_H[Y], 0, 1, E2))) return rc;
+        // d alpha = sum_Y H^Y G2^Y  (M1 x M2): adjoint sweep along dimension 2, fibres = rows
+        if ((rc = b0s_scan_adj(st, p->b0s_eps[1], (int)M2, M1, 1, p->b0s_H[B0S_L], p->b0s_H[B0S_C], p->b0s_H[B0S_R], E2, 0, 1, p->b0s_dA, M2, 0, 1))) return rc;
         k_b0s_from_double<T><<<ceil_div(M1 * M2, 256), 256, 0, st>>>(p->b0s_dA, galpha, M1 * M2);
         VGGP_LAUNCH_CHECK();
     }
-    // ---- [bP | bQ]_d = sum_XY G^X^T diag(gw^{XY}) G^Y ----
+    // ---- [bP | bQ]_d = sum_XY G^X^T diag(gw^{XY}) G^Y = sum_X G^X^T S^X ----
     for (int d = 0; d < D; ++d) {
         const int K = p->K[d];
         const i64 M = K - 1, E = K + 1;
@@ -1127,43 +1137,46 @@ int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
             k_b0s_S<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, p->b0s_G[d][0], p->b0s_G[d][1], GW[d] + (i64)mat * 6 * E,
                                                              p->b0s_S[0], p->b0s_S[1], p->b0s_S[2]);
             VGGP_LAUNCH_CHECK();
-            k_b0s_copy2d<<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bM, M, p->b0s_S[B0S_C] + M, M, (int)M, (int)M);
-            VGGP_LAUNCH_CHECK();
-            for (int x = 0; x < 2; ++x)
-                if ((rc = gemm_rm(st, (int)M, (int)M, (int)E, p->b0s_G[d][x], 1, M, p->b0s_S[x == 0 ? B0S_L : B0S_R], M, 1, p->b0s_bM, M, 1.0, 1.0))) return rc;
+            if ((rc = b0s_scan_adj(st, p->b0s_eps[d], (int)M, 1, M, p->b0s_S[B0S_L], p->b0s_S[B0S_C], p->b0s_S[B0S_R], 0, 1, M, p->b0s_bM, 0, 1, M))) return rc;
             k_b0s_from_double<T><<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bM, gfac + p->gfac_off[d] + (i64)mat * M * M, M * M);
             VGGP_LAUNCH_CHECK();
         }
     }
-    // ---- table part of G_l[d] = sum_{X in L,R} <Gamma_d^X, dG_d^X / dl> ----
+    // ---- table part of G_l[d] = <GT, dT / dl_d> + <GW_d, dW_d / dl_d> ----
     for (int d = 0; d < D; ++d) {
         const int K = p->K[d];
-        const i64 M = K - 1, E = K + 1;
-        k_b0s_gamma_init<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, GW[d], p->b0s_V[d][0], p->b0s_V[d][1], p->b0s_V[d][2], p->b0s_V[d][3],
-                                                                  p->g.P[d], p->g.Q[d], D == 1 ? GTd : nullptr, D == 1 ? p->alpha : nullptr,
-                                                                  p->b0s_Gam[0], p->b0s_Gam[1]);
+        k_b0s_gl_rows<T><<<ceil_div(K + 1, 8), 256, 0, st>>>(K, GW[d], p->b0s_V[d][0], p->b0s_V[d][1], p->b0s_V[d][2], p->b0s_V[d][3],
+                                                             p->g.P[d], p->g.Q[d], p->b0s_G[d][2], p->b0s_G[d][3],
+                                                             D == 1 ? GTd : nullptr, D == 1 ? p->alpha : nullptr, gs + 3 + d);
         VGGP_LAUNCH_CHECK();
-        if (D == 2) {
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int S = s2 == 0 ? B0S_L : B0S_R;          // the side of THIS dimension
-                double* Gam = p->b0s_Gam[s2];
-                if (d == 0) {                                      // Gamma1^X += sum_Y GT^{XY} U^Y^T
-                    for (int y = 0; y < 2; ++y) {
-                        const int Y = y == 0 ? B0S_L : B0S_R;
-                        if ((rc = gemm_rm(st, (int)E1, (int)M1, (int)E2, GTd + (3 * S + Y) * EE, E2, 1, p->b0s_U[y], 1, E2, Gam, M1, 1.0, 1.0))) return rc;
-                    }
-                    if ((rc = gemm_rm(st, (int)E1, (int)M1, (int)M2, GTd + (3 * S + B0S_C) * EE + 1, E2, 1, p->alpha, 1, M2, Gam, M1, 1.0, 1.0))) return rc;
-                } else {                                           // Gamma2^Y += sum_X GT^{XY}^T B^X
-                    for (int x = 0; x < 2; ++x) {
-                        const int X = x == 0 ? B0S_L : B0S_R;
-                        if ((rc = gemm_rm(st, (int)E2, (int)M2, (int)E1, GTd + (3 * X + S) * EE, 1, E2, p->b0s_B[x], M2, 1, Gam, M2, 1.0, 1.0))) return rc;
-                    }
-                    if ((rc = gemm_rm(st, (int)E2, (int)M2, (int)M1, GTd + (3 * B0S_C + S) * EE + E2, 1, E2, p->alpha, M2, 1, Gam, M2, 1.0, 1.0))) return rc;
-                }
+    }
+    if (D == 2) {
+        // the forward's corner products are no longer needed: TT[0], TT[1] take the (unused) transforms, TT[2], TT[3] the tangents
+        double *sL = p->b0s_TT[0], *sR = p->b0s_TT[1], *tL = p->b0s_TT[2], *tR = p->b0s_TT[3];
+        // l_1: dT^{XY} / dl_1 = (dG1^X / dl_1) U^Y, X in {L, R}: tangent sweep along dimension 1 of U^Y (U^C = A in columns 1..M2)
+        for (int Y = 0; Y < 3; ++Y) {
+            if (Y == B0S_C) {
+                VGGP_CUDA(cudaMemsetAsync(tL, 0, sizeof(double) * EE, st));
+                VGGP_CUDA(cudaMemsetAsync(tR, 0, sizeof(double) * EE, st));
+                if ((rc = b0s_scan_tan(st, p->b0s_eps[0], (int)M1, 1, M2, p->alpha, 0, 1, M2, sL + 1, sR + 1, tL + 1, tR + 1, 0, 1, E2))) return rc;
+            } else {
+                if ((rc = b0s_scan_tan(st, p->b0s_eps[0], (int)M1, 1, E2, p->b0s_U[Y == B0S_L ? 0 : 1], 0, 1, E2, sL, sR, tL, tR, 0, 1, E2))) return rc;
             }
+            if ((rc = b0s_dot(st, GT(B0S_L, Y), tL, EE, gs + 3))) return rc;
+            if ((rc = b0s_dot(st, GT(B0S_R, Y), tR, EE, gs + 3))) return rc;
         }
-        k_b0s_dot<<<std::min<int>(ceil_div(E * M, 256), 64), 256, 0, st>>>(p->b0s_Gam[0], p->b0s_Gam[1], p->b0s_G[d][2], p->b0s_G[d][3], E * M, gs + 3 + d);
-        VGGP_LAUNCH_CHECK();
+        // l_2: dT^{XY} / dl_2 = B^X (dG2^Y / dl_2)^T, Y in {L, R}: tangent sweep along dimension 2 of B^X (B^C = A in rows 1..M1)
+        for (int X = 0; X < 3; ++X) {
+            if (X == B0S_C) {
+                VGGP_CUDA(cudaMemsetAsync(tL, 0, sizeof(double) * EE, st));
+                VGGP_CUDA(cudaMemsetAsync(tR, 0, sizeof(double) * EE, st));
+                if ((rc = b0s_scan_tan(st, p->b0s_eps[1], (int)M2, M1, 1, p->alpha, M2, 0, 1, sL + E2, sR + E2, tL + E2, tR + E2, E2, 0, 1))) return rc;
+            } else {
+                if ((rc = b0s_scan_tan(st, p->b0s_eps[1], (int)M2, E1, 1, p->b0s_B[X == B0S_L ? 0 : 1], M2, 0, 1, sL, sR, tL, tR, E2, 0, 1))) return rc;
+            }
+            if ((rc = b0s_dot(st, GT(X, B0S_L), tL, EE, gs + 4))) return rc;
+            if ((rc = b0s_dot(st, GT(X, B0S_R), tR, EE, gs + 4))) return rc;
+        }
     }
     return 0;
 }
