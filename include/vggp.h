@@ -157,7 +157,7 @@ int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64
  * B0 family (D <= 2): the same three calls select the SCAN form of the cell-integrated features (csrc/b0scan.cuh,
  * DESIGN.md section 10): cells are extended by one virtual cell on each side (observations outside the mesh do
  * contribute in this family, n_inside == n), the per-observation kernel does O(1) work against per-cell tables built by
- * dense products on the grid side, and an adjoint stage writes the same gbuf blocks vggp_obs_fwd_bwd writes for this
+ * first-order recurrences on the grid side, and an adjoint stage writes the same gbuf blocks vggp_obs_fwd_bwd writes for this
  * family.  The first vggp_obs_fwd_bwd_binned on a B0 plan allocates the tables inside the plan.
  * Status of this form: everything runs on the CPU under the SIMT emulator of tests/host_emul with oracle parity;
  * the device path is opt-in until it has been run on a B200 (DESIGN.md sections 8 - 10).
@@ -227,7 +227,8 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
  *   x [D] HOST array of device pointers (n values of obs_dtype each); mean, var: n values of obs_dtype.
  * B1 family: test points outside the mesh get mean 0 and the prior variance (their feature column is zero).
  * B0 family (D <= 2): the cell-integrated features are non-zero everywhere; they are evaluated in their scan form
- *   (three local features per dimension against per-cell tables built by dense products on the grid side, csrc/b0scan.cuh),
+ *   (three local features per dimension against per-cell tables built by first-order recurrences on the grid side,
+ *   csrc/b0scan.cuh),
  *   O(1) work per point.  The first call allocates the tables inside the plan.  Not yet run on a B200.
  */
 int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, void* var, void* stream);

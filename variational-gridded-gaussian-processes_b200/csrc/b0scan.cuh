@@ -9,7 +9,8 @@
 //     GL[e][i] = exp(-(t_c - t_{i+1}) / l) - exp(-(t_c - t_i) / l),   GR[e][i] = exp(-(t_i - t_{c+1}) / l) - exp(-(t_{i+1} - t_{c+1}) / l)
 // so that   mu = sum_{X,Y} f1^X f2^Y T^{XY}[e1][e2],  T^{XY} = G1^X A G2^Y^T      (X, Y in {L, C, R}, G^C[e] = unit row c)
 //           p_d = sum_{X,Y} f^X f^Y W^{XY}[e],        W^{XY}[e] = (G^X P_d G^Y^T)[e][e]   (q_d likewise from Q_d).
-// The tables are dense float64 products on the grid side (k_gemm_one), the per-point work is O(1).
+// GL and GR are rank-one decay (semiseparable) matrices, so the tables are first-order recurrences along the modes on the
+// grid side (k_b0s_scan, O(M) per mode); the per-point work is O(1).
 #pragma once
 #include "obs.cuh"
 #include "obs_binned.cuh"
