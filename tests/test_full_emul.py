@@ -313,6 +313,43 @@ def test_minmax_scaling_bit_exact_under_emulation(emu, dtype):
     assert lib.vggp_minmax(code, None, 0, emul_lib.ptr(mm), None) == -1
 
 
+@pytest.mark.parametrize("family", ["B1", "B0"])
+def test_binned_shards_sum_to_the_full_batch_under_emulation(emu, family):
+    """Sharding contract of SURVEY.md section 8e for the binned layouts: two ranks run the per-observation stage on their
+    halves, the gradient buffers are summed (what the all-reduce does), and the grid backward on the sum reproduces the
+    single-rank step.  For the B0 scan form this also checks that the adjoint stage is linear in the raw sums."""
+    lib, L = emu
+    fam = L.B1_ASVGP if family == "B1" else L.B0_GRIDDED
+    ofam = O.B1_ASVGP if family == "B1" else O.B0_GRIDDED
+    knots, N = (9, 7), 800
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=31, family=ofam, x_lo=-0.1, x_hi=1.1)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    mm = m.numpy().copy()
+    Lcat = torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
+    yy = y.numpy().copy()
+    full = emul_lib.EmuPlan(lib, L, fam, [t.numpy() for t in meshes], np.float64)
+    ref = full.step(theta, mm, Lcat, full.bin(xs, yy, run_cap=16), None, 1.0)
+    ranks = [emul_lib.EmuPlan(lib, L, fam, [t.numpy() for t in meshes], np.float64) for _ in range(2)]
+    cut = 317
+    total = np.zeros(ranks[0].gbuf_bytes, dtype=np.uint8)
+    acc_obs = np.zeros(ranks[0].gbuf_obs_elems)
+    acc_scal = np.zeros(8)
+    for r, (lo, hi) in zip(ranks, ((0, cut), (cut, N))):
+        r.grid_forward(theta, mm, Lcat)
+        r.obs_fwd_bwd(r.bin([x[lo:hi].copy() for x in xs], yy[lo:hi].copy(), run_cap=16))
+        acc_obs += r.gbuf[: r.gbuf_obs_elems * 8].view(np.float64)
+        acc_scal += r.gbuf[r.gbuf_scalar_offset: r.gbuf_scalar_offset + 64].view(np.float64)
+    r0 = ranks[0]
+    r0.gbuf[: r0.gbuf_obs_elems * 8].view(np.float64)[:] = acc_obs
+    r0.gbuf[r0.gbuf_scalar_offset: r0.gbuf_scalar_offset + 64].view(np.float64)[:] = acc_scal
+    got = r0.grid_backward(theta, mm, Lcat, 1.0)
+    for a, b in zip(got, ref):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-12)
+    for pl in [full] + ranks:
+        pl.close()
+
+
 def test_binned_abi_edge_cases_under_emulation(emu):
     lib, L = emu
     meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]
