@@ -15,13 +15,16 @@ note "== 1. default GPU suite (packed kernel, the verified path)"
 timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/pytest_default.log" 2>&1
 note "   rc=$? $(tail -n 1 "$OUT/pytest_default.log")"
 
-note "== 2. binned path, LDG stream first (tests are parametrised ldg/tma; -k ldg isolates a TMA hang)"
-VGGP_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -x -q -k "ldg or not tma" > "$OUT/pytest_binned_ldg.log" 2>&1
+note "== 2. binned K1 layout, LDG stream first (VGGP_TEST_STREAMS isolates a hang of the TMA variant)"
+VGGP_TEST_UNVERIFIED=1 VGGP_TEST_STREAMS=ldg timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -q -k "binned" > "$OUT/pytest_binned_ldg.log" 2>&1
 RC_LDG=$?
-note "   rc=$RC_LDG $(tail -n 1 "$OUT/pytest_binned_ldg.log")"
-VGGP_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -x -q -k "tma" > "$OUT/pytest_binned_tma.log" 2>&1
+note "   ldg rc=$RC_LDG $(tail -n 1 "$OUT/pytest_binned_ldg.log")"
+VGGP_TEST_UNVERIFIED=1 VGGP_TEST_STREAMS=tma timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -q -k "binned" > "$OUT/pytest_binned_tma.log" 2>&1
 RC_TMA=$?
 note "   tma rc=$RC_TMA $(tail -n 1 "$OUT/pytest_binned_tma.log")"
+note "== 2b. the other new paths: fused metrics, min-max scaling, B0 scan form (prediction and step)"
+VGGP_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_new_paths.py -m gpu -q -k "not binned" > "$OUT/pytest_other_new.log" 2>&1
+note "   rc=$? $(tail -n 1 "$OUT/pytest_other_new.log")"
 
 bench() {   # name, extra args...
     local name=$1; shift
