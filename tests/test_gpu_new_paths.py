@@ -284,3 +284,39 @@ def test_min_max_scaling_bit_exact(vg, dev, dtype):
     assert torch.equal(s2, (t - lo2) / (hi2 - lo2)) and lo2.item() == -200.0
     with pytest.raises(RuntimeError, match="CUDA"):
         dp.min_max_scaling(t.cpu())
+
+
+def test_binned_full_size_matches_packed_bench_config(vg, dev, stream_mode):
+    """BASELINE.json configs[2] / [4] shape (2-D along-track observations, 512 x 512 grid, float32, bench parameters),
+    N = 2^24, where the oracle cannot run: the binned layout must give the ELBO and gradients of the packed layout
+    (different summation orders only), count every observation once, and be linear in shards."""
+    import bench
+    N = 1 << 24
+    meshes = [torch.linspace(0, 1, k) for k in bench.KNOTS]
+    xs, y = bench.make_tracks(0, N, N, dev, torch.float32)
+    theta, m, Ls = bench.make_params(meshes, dev)
+    theta, m = theta.to(dev), m.to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    ref = [t.clone() for t in plan.step(theta, m, Lcat, plan.pack(xs, y, sort_by_cell=True), None)]
+    for cap in (128, 512):
+        b = plan.bin(xs, y, run_cap=cap)
+        assert b.n == N and b.streamed_bytes < 1.05 * 12 * N          # padding below 5 %
+        got = plan.step(theta, m, Lcat, b, None)
+        assert plan.read_info() == 0 and got[0][3].item() == N
+        assert abs(got[0][0].item() - ref[0][0].item()) < 1e-5 * abs(ref[0][0].item())
+        for a, r in zip(got[1:], ref[1:]):
+            assert relerr(a, r) < 1e-3
+    plan.grid_forward(theta, m, Lcat)
+    plan.obs_fwd_bwd(plan.bin(xs, y))
+    obs_full, scal_full = [t.clone() for t in plan.gbuf_views()]
+    half = N // 2 + 12345
+    acc_obs = torch.zeros_like(obs_full, dtype=torch.float64)
+    acc_scal = torch.zeros_like(scal_full)
+    for lo, hi in ((0, half), (half, N)):
+        plan.obs_fwd_bwd(plan.bin([x[lo:hi].contiguous() for x in xs], y[lo:hi].contiguous()))
+        o, sc = plan.gbuf_views()
+        acc_obs += o.to(torch.float64)
+        acc_scal += sc
+    assert relerr(acc_obs, obs_full) < 1e-4
+    assert acc_scal[1].item() == N and abs(acc_scal[0].item() - scal_full[0].item()) < 1e-5 * abs(scal_full[0].item())
