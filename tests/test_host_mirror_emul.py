@@ -131,3 +131,64 @@ def test_b0_family_binned_through_the_host_mirror(host):
         assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)
     mean, var = plan.predict(xs)                   # B0 point prediction in scan form
     assert torch.isfinite(mean).all() and (var > 0).all()
+
+
+@pytest.mark.parametrize("family,layout", [("asvgp", "packed"), ("asvgp", "binned"), ("gridded", "dense"), ("gridded", "binned")])
+def test_model_training_loop_over_the_emulator(host, monkeypatch, family, layout):
+    """The drop-in model classes (reference constructor signatures, parameters(), -_elbo().backward(), Adam) on the CPU:
+    the two CUDA gates of the product (GridPlan's constructor, the model's device check) are replaced for this test only,
+    everything else -- parameter containers, softplus constraints, the layout opt-in, the autograd bridge -- is the
+    product's code.  ELBO and raw-parameter gradients against the oracle; a few Adam steps increase the bound."""
+    plan_mod, EmuGridPlan, L = host
+    gmod = importlib.import_module(PKG + ".models._gridded")
+    gks = importlib.import_module(PKG + ".models.sparse.gridded_kronecker_structure")
+    monkeypatch.setattr(gmod, "GridPlan", lambda fam, meshes, dtype, device: EmuGridPlan(fam, meshes, dtype))
+    monkeypatch.setattr(gmod.GriddedVariationalGP, "_device_dtype", lambda self: (torch.device("cpu"), self.variational_mean.dtype))
+    if layout == "binned":
+        monkeypatch.setenv("VGGP_OBS_LAYOUT", "binned")
+    else:
+        monkeypatch.delenv("VGGP_OBS_LAYOUT", raising=False)
+    g = torch.Generator().manual_seed(0)
+    N = 400
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(5 * X[:, 0]) + torch.cos(7 * X[:, 1]) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    if family == "asvgp":
+        model = gks.GriddedMatern12ASVGP(X, y, 6, 1, (0, 1), (0, 1)).to(torch.float64)
+        ofam, meshes = O.B1_ASVGP, [O.make_padded_mesh(0, 1, 6, 1)] * 2
+    else:
+        model = gks.Matern12GriddedGP(X, y, 7, (0, 1), (0, 1)).to(torch.float64)
+        ofam, meshes = O.B0_GRIDDED, [O.make_mesh(0, 1, 7)] * 2
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.1)
+        model.kernel_1.base_kernel.lengthscale = 0.4
+        model.likelihood.noise = 0.05
+    elbo = model._elbo()
+    assert elbo.dim() == 0 and elbo.requires_grad
+    (-elbo).backward()
+    packed = model._packed
+    assert (packed is None) == (layout == "dense")
+    if layout == "binned":
+        assert type(packed).__name__ == "BinnedObs"
+    raw_l = torch.stack([model.kernel_1.base_kernel.raw_lengthscale.detach().reshape(()),
+                         model.kernel_2.base_kernel.raw_lengthscale.detach().reshape(())]).requires_grad_(True)
+    raw_s = torch.stack([model.kernel_1.raw_outputscale.detach(), model.kernel_2.raw_outputscale.detach()]).requires_grad_(True)
+    raw_n = model.likelihood.noise_covar.raw_noise.detach().reshape(()).requires_grad_(True)
+    l, s2, noise = O.constrain(raw_l, raw_s, raw_n)
+    ref = O.elbo_structured(ofam, meshes, X, y, l, s2, noise, model.variational_mean.detach(),
+                            [model.variational_chol_1.detach(), model.variational_chol_2.detach()], ref_quirks=False)
+    gl, gs, gn = torch.autograd.grad(-ref, [raw_l, raw_s, raw_n])
+    assert abs(elbo.item() - ref.item()) < 1e-8 * abs(ref.item())
+    assert abs(model.kernel_1.base_kernel.raw_lengthscale.grad.item() - gl[0].item()) < 1e-6 * abs(gl[0].item())
+    assert abs(model.kernel_2.raw_outputscale.grad.item() - gs[1].item()) < 1e-6 * abs(gs[1].item())
+    assert abs(model.likelihood.noise_covar.raw_noise.grad.item() - gn.item()) < 1e-6 * abs(gn.item())
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = -model._elbo()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    post = model.posterior(X[:50])
+    assert torch.isfinite(post.mean).all() and (post.variance > 0).all()
