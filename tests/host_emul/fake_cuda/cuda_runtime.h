@@ -130,6 +130,8 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
+inline int __float_as_int(float v) { int i; memcpy(&i, &v, 4); return i; }
+inline long long __double_as_longlong(double v) { long long i; memcpy(&i, &v, 8); return i; }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 inline double __longlong_as_double(long long v) { double f; memcpy(&f, &v, 8); return f; }
 

@@ -113,3 +113,22 @@ def test_binned_device_edge_cases(emu, layout):
         ea, eb, eE, n_in = expected(meshes, Xs, ys, alpha, bands, dtype)
         assert st[2] == n_in
         assert rel(ga, ea) < 1e-11 and rel(gb, eb) < 1e-11 and abs(gs[0] - eE) <= 1e-11 * max(abs(eE), 1.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("layout", ["packed_unsorted", "packed_sorted", "binned_ldg"])
+def test_first_knot_hit_followed_by_a_point_left_of_the_mesh(emu, layout, dtype):
+    """Regression (found by randomised emulator runs): in an unsorted stream, k_obs_b1 used to widen the cached lower
+    bound of cell 0 to -inf after an observation exactly on the first knot, so an observation LEFT of the mesh that
+    followed in the same lane run was taken as inside cell 0.  The bound is now lowered by one ulp only."""
+    rng = np.random.default_rng(5)
+    meshes, X, y, alpha, bands = make_problem(1, (5,), 64, dtype, seed=9, frac_outside=0.0, clustered=False, on_knots=False)
+    t0, t1 = float(meshes[0][0]), float(meshes[0][1])
+    X[:, 0] = (t0 + (t1 - t0) * rng.uniform(0.1, 0.9, 64)).astype(dtype)      # everything in cell 0 ...
+    X[10, 0] = dtype(t0)                                                        # ... one exact first-knot hit ...
+    X[11:20, 0] = dtype(t0) - dtype(0.05) * np.arange(1, 10, dtype=dtype)       # ... then points left of the mesh
+    ga, gb, gs, _ = run_device(emu, layout, meshes, X, y, alpha, bands, dtype, 32, blocks_cap=1)
+    ea, eb, eE, n_in = expected(meshes, X, y, alpha, bands, dtype)
+    assert n_in == 64 - 9
+    tol = 1e-11 if dtype == np.float64 else 3e-4
+    assert rel(ga, ea) < tol and rel(gb, eb) < tol and abs(gs[0] - eE) <= tol * abs(eE)

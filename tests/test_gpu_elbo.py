@@ -487,6 +487,33 @@ def test_full_size_properties_bench_config(vg, dev):
     assert abs(acc_scal[1].item() - N) == 0 and abs(acc_scal[0].item() - scal_full[0].item()) < 1e-5 * abs(scal_full[0].item())
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
+def test_first_knot_hit_followed_by_points_left_of_the_mesh(vg, dev, dtype, tol):
+    """Regression: an observation exactly on the first knot followed, in the same lane run of an UNSORTED stream, by
+    observations left of the mesh (they must contribute y^2 only).  Found under the SIMT emulator
+    (tests/test_device_emul.py); the plain-array entry point keeps the input order."""
+    meshes = [torch.linspace(0, 1, 5)]
+    g = torch.Generator().manual_seed(5)
+    N = 64
+    x = 0.025 + 0.2 * torch.rand(N, generator=g, dtype=torch.float64)          # everything in cell 0 ...
+    x[10] = 0.0                                                                # ... one exact first-knot hit ...
+    x[11:20] = -0.05 * torch.arange(1, 10, dtype=torch.float64)                # ... then points left of the mesh
+    y = torch.sin(3 * x) + 0.1 * torch.randn(N, generator=g, dtype=torch.float64)
+    l, s2, noise = torch.tensor([0.3], dtype=torch.float64), torch.tensor([0.9], dtype=torch.float64), torch.tensor(0.07, dtype=torch.float64)
+    m = 0.2 * torch.randn(5, generator=g, dtype=torch.float64)
+    Ls = [torch.eye(5, dtype=torch.float64) * 0.6 + 0.05 * torch.randn(5, 5, generator=g, dtype=torch.float64)]
+    xq, yq = x.to(dtype), y.to(dtype)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, xq.to(torch.float64).reshape(-1, 1), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    for layout in ("raw", "packed_unsorted"):
+        obs = [xq.to(dev)] if layout == "raw" else plan.pack([xq.to(dev)], yq.to(dev), sort_by_cell=False)
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Ls[0].reshape(-1).to(dev), obs, yq.to(dev) if layout == "raw" else None)
+        assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), layout
+        assert relerr(dm, g_ref[3]) < tol * 10, layout
+
+
 def test_model_refuses_cpu(vg):
     ks = _model_module("kronecker_structure")
     X = torch.rand(10, 2, dtype=torch.float64)

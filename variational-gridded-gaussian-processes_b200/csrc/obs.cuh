@@ -392,6 +392,16 @@ __device__ __forceinline__ void lane_load_cell(const PackedArgs<T, D>& a, LaneSt
     s.valid = true;
 }
 
+// the largest value strictly below a finite v (one step in the ordered bit pattern; -denorm_min below +-0)
+__device__ __forceinline__ float just_below(float v) {
+    const int b = __float_as_int(v);
+    return __int_as_float(v > 0.0f ? b - 1 : (v < 0.0f ? b + 1 : (int)0x80000001u));
+}
+__device__ __forceinline__ double just_below(double v) {
+    const long long b = __double_as_longlong(v);
+    return __longlong_as_double(v > 0.0 ? b - 1 : (v < 0.0 ? b + 1 : (long long)0x8000000000000001ull));
+}
+
 template <typename T, int D>
 __device__ __forceinline__ bool lane_in_cell(const LaneState<T, D>& s, const T (&x)[D]) {
     bool same = true;
@@ -448,11 +458,13 @@ __device__ __forceinline__ bool lane_switch(const PackedArgs<T, D>& a, LaneState
         lane_flush<T, D>(a, s, c);
         lane_load_cell<T, D>(a, s, c, tl, th, s_tab);
     } else {
-        // x == first knot of the mesh: it belongs to cell 0 although x > t_lo fails; widen the cached lower bound
-        // so that the fast check accepts it (the weight formula is unchanged: a = (x - t_0) / h = 0)
+        // x == first knot of the mesh: it belongs to cell 0 although x > t_lo fails; lower the cached bound by one ulp
+        // so that the fast check accepts x >= t_0 (the weight formula is unchanged: a = (x - t_0) / h = 0) and still
+        // rejects everything left of the mesh.  (Up to round 1 the bound was widened to -inf, which let an observation
+        // left of the mesh through when it followed a first-knot hit inside the same run of an unsorted stream.)
 #pragma unroll
         for (int d = 0; d < D; ++d)
-            if (c[d] == 0 && x[d] == s.tlo[d]) s.tlo_chk[d] = -INFINITY;
+            if (c[d] == 0 && x[d] == s.tlo[d]) s.tlo_chk[d] = just_below(s.tlo[d]);
     }
     return false;
 }
