@@ -67,6 +67,20 @@ def test_product_package_never_imports_the_oracle():
     assert n >= 10
 
 
+def test_product_never_references_the_emulator_and_exports_no_host_path():
+    """tests/host_emul (the SIMT emulator) is test infrastructure: nothing in the package, bench.py or __graft_entry__.py
+    names it, and the kernels' only concession to it is the VGGP_EMUL guard around the inline-PTX wrappers."""
+    pat = re.compile(r"host_emul|emul_lib|fake_cuda|VGGP_HOST_EMUL|libvggp_full_emul")
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for base, _, names in os.walk(os.path.join(ROOT, PKG)):
+        files += [os.path.join(base, f) for f in names if f.endswith(".py")]
+    for f in files:
+        assert not pat.search(open(f).read()), f"{f} references the emulator"
+    lib = ctypes.CDLL(importlib.import_module(PKG + ".build").build())
+    for sym in ("emul_device_run", "emul_binned_run", "emul_plan_bins"):
+        assert not hasattr(lib, sym)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_models_fail_loudly_without_cuda():
     ks = importlib.import_module(PKG + ".models.sparse.kronecker_structure")
