@@ -487,6 +487,25 @@ def test_full_size_properties_bench_config(vg, dev):
     assert abs(acc_scal[1].item() - N) == 0 and abs(acc_scal[0].item() - scal_full[0].item()) < 1e-5 * abs(scal_full[0].item())
 
 
+def test_bench_configuration_two_wave_run_length(vg, dev):
+    """The bench configuration itself (N = 2^26, 512 x 512, float32): above 48.5 M observations per GPU the packed layout
+    balances the run length to two waves of chunks per resident warp (pack_geometry).  The ELBO must be the one every
+    round-1 run of this data set and these parameters produced (-177008473.3, layouts agreeing to 1e-9), and every
+    observation must be counted once."""
+    import bench
+    N = bench.N_TOTAL
+    meshes = [torch.linspace(0, 1, k) for k in bench.KNOTS]
+    xs, y = bench.make_tracks(0, N, N, dev, torch.float32)
+    theta, m, Ls = bench.make_params(meshes, dev)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    pk = plan.pack(xs, y, sort_by_cell=True)
+    assert pk.run_len % 4 == 0 and 16 <= pk.run_len <= 512
+    out, dtheta, dm, dL = plan.step(theta.to(dev), m.to(dev), torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous(), pk, None)
+    assert plan.read_info() == 0 and out[3].item() == N
+    assert abs(out[0].item() - (-177008473.3)) < 1e-6 * 177008473.3
+    assert torch.isfinite(dtheta).all() and torch.isfinite(dm).all() and torch.isfinite(dL).all()
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
 def test_first_knot_hit_followed_by_points_left_of_the_mesh(vg, dev, dtype, tol):
     """Regression: an observation exactly on the first knot followed, in the same lane run of an UNSORTED stream, by
