@@ -170,12 +170,19 @@ int run(int layout, const int* K, const float* knots, const void* const* xv, con
     a.n_tasks = (int)L.n_tasks;
     a.knots_byte_off = tb.knots_byte_off; a.tables = tb.bytes.data();
     a.alpha = reinterpret_cast<const T*>(alphav);
-    a.galpha = gb; a.gband = gb + M; a.gs = gs; a.n_real = (double)n; a.counter = &counter;
+    // band sums go through replicas (3 here, so that CTAs share and do not share one) and k_band_reduce, as in the library
+    const int band_total = band_off[D - 1] + 4 * K[D - 1];
+    std::vector<T> rep((size_t)3 * band_total, (T)0);
+    a.galpha = gb; a.gband = rep.data(); a.n_rep = 3; a.band_rep_stride = band_total;
+    a.gs = gs; a.n_real = (double)n; a.counter = &counter;
     int64_t blocks = (L.n_tasks + BIN_WARPS - 1) / BIN_WARPS;
     blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, blocks_cap));
     if (n > 0) {
         if (layout == 3) cuda_emul::launch(dim3((unsigned)blocks), dim3(BIN_THREADS), [&] { k_obs_b1_binned_tma<T, D>(a); });
         else cuda_emul::launch(dim3((unsigned)blocks), dim3(BIN_THREADS), [&] { k_obs_b1_binned<T, D>(a); });
+        cuda_emul::launch(dim3((unsigned)((band_total + 63) / 64)), dim3(256),
+                          [&] { k_band_reduce<T>(rep.data(), 3, (int64_t)band_total, band_total, gb + M); });
+        for (T v : rep) if (v != (T)0) return -7;      // the reduce kernel leaves the replicas cleared
     }
     stats[0] = L.n_tasks; stats[1] = L.data_elems; stats[2] = L.n_inside; stats[3] = L.n_runs;
     return 0;

@@ -290,7 +290,11 @@ struct BinnedArgs {
                                      // per run (enter / flush), never in the per-observation loop, so they stay in L2
     const T* alpha;
     T* galpha;
-    T* gband;
+    T* gband;                        // band sums: replica r of the block starts at gband + r * band_rep_stride
+    int n_rep;                       // >= 1 replicas of the band block; a CTA adds into replica blockIdx.x % n_rep.  The band
+    i64 band_rep_stride;             // block is tiny (4 sum K_d values), so without replicas every flush of every warp hits
+                                     // the same few L2 lines and the atomic unit serialises them (ncu, round 2: the kernel
+                                     // time grew linearly with the number of runs); k_band_reduce sums the replicas
     double* gs;
     double n_real;
     unsigned int* counter;           // work-stealing counter over tasks (zeroed before the launch)
@@ -392,6 +396,7 @@ k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
     double etot = 0.0;
     BinLane<T, D> s;
     BinTask<T, D> t;
+    T* const gband = a.gband + (i64)(blockIdx.x % (unsigned)a.n_rep) * a.band_rep_stride;
     // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
     while (bin_next_task<T, D>(a, lane, s, t)) {
         // the loads of the next group of 4 observations are in flight while the current one is processed (no buffer
@@ -406,7 +411,7 @@ k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
             if (gi + 1 < t.groups) bin_group<T, D>(s, xb, yb, t.nrun - 4 * (gi + 1));
         }
         if (t.valid)
-            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, a.gband, add);
+            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, gband, add);
     }
     bin_finish<T, D>(a, etot, red);
 }
@@ -437,6 +442,7 @@ k_obs_b1_binned_tma(const __grid_constant__ BinnedArgs<T, D> a) {
     double etot = 0.0;
     BinLane<T, D> s;
     BinTask<T, D> t;
+    T* const gband = a.gband + (i64)(blockIdx.x % (unsigned)a.n_rep) * a.band_rep_stride;
     unsigned int k0 = 0;                 // stages this warp has consumed so far: slot = k % STAGES, phase = (k / STAGES) & 1
     while (bin_next_task<T, D>(a, lane, s, t)) {
         const T* src = t.base - lane * 4;                    // the task's first group
@@ -475,13 +481,33 @@ k_obs_b1_binned_tma(const __grid_constant__ BinnedArgs<T, D> a) {
         }
         k0 += (unsigned int)nst;
         if (t.valid)
-            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, a.gband, add);
+            etot += (double)bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, gband, add);
     }
     bin_finish<T, D>(a, etot, red);
 }
 
 template <typename T, int D>
 constexpr size_t bin_tma_smem_bytes() { return (size_t)BIN_WARPS * BIN_STAGES * BIN_GPS * (D + 1) * 128 * sizeof(T); }
+
+// Sum of the band replicas -> the band block of gbuf (overwritten); the replicas are cleared for the next launch.
+// grid (ceil(n / 64)), 256 threads = 64 elements x 4 replica groups.
+template <typename T>
+__global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_rep, i64 stride, int n, T* __restrict__ out) {
+    __shared__ T part[4][64];
+    const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int e = (int)blockIdx.x * 64 + el;
+    T acc = (T)0;
+    if (e < n) {
+        for (int r = grp; r < n_rep; r += 4) {
+            T* q = rep + (i64)r * stride + e;
+            acc += *q;
+            *q = (T)0;
+        }
+    }
+    part[grp][el] = acc;
+    __syncthreads();
+    if (grp == 0 && e < n) out[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+}
 
 // ---- packing (one-time setup) ---------------------------------------------------------------------------
 

@@ -21,6 +21,8 @@ static int g_use_mma = 1;
 static int g_bin_stream = 0;       // binned K1: 0 = LDG.128 register ping-pong, 1 = TMA ring through shared memory
 static int g_b1_structured = 2;    // B1 family: 0 dense, 1 twisted inverse + GEMMs, 2 + semiseparable products
 
+constexpr int BAND_REPLICAS = 128;
+
 struct Phase {
     GemmDesc* d_descs = nullptr;
     int ndesc = 0;
@@ -72,6 +74,8 @@ struct vggp_plan {
     double* b0s_bM = nullptr;              // (K-1) x (K-1), largest dimension
     double* b0s_Gam[2] = {};               // (K+1) x (K-1), largest dimension
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
+    void* band_rep = nullptr;              // B1 family, binned kernel: BAND_REPLICAS copies of the band block (obs dtype), kept zero
+                                           // between launches (k_band_reduce clears what it sums)
     // schedules
     std::vector<Phase> chol_trailing;      // one per panel (may be empty phase)
     int n_panels;
@@ -872,7 +876,9 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     a.alpha = reinterpret_cast<const T*>(p->alphaT);
     T* gb = reinterpret_cast<T*>(gbuf);
     a.galpha = gb;
-    a.gband = gb + p->M;
+    a.gband = reinterpret_cast<T*>(p->band_rep);
+    a.n_rep = BAND_REPLICAS;
+    a.band_rep_stride = p->band_total;
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
@@ -883,6 +889,8 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[mode]));
     if (mode) k_obs_b1_binned_tma<T, D><<<(unsigned)blocks, BIN_THREADS, smem, st>>>(a);
     else k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    k_band_reduce<T><<<ceil_div(p->band_total, 64), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -1368,6 +1376,11 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         unsigned char* a = nullptr;
         TRY(dev_alloc(p, &a, p->M * (i64)tsz));
         p->alphaT = a;
+    }
+    if (family == VGGP_B1_ASVGP) {
+        unsigned char* br = nullptr;
+        TRY(dev_alloc(p, &br, (i64)BAND_REPLICAS * p->band_total * (i64)tsz));
+        p->band_rep = br;
     }
     TRY(dev_alloc(p, &p->theta_dev, 2 * VGGP_MAX_D + 1));
     TRY(dev_alloc(p, &p->obs_counter, 4));
