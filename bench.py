@@ -210,13 +210,17 @@ class ClockSampler:
         return out
 
 
-def k1_traffic():
-    """DRAM bytes per launch of the per-observation kernel from the committed ncu capture (same config)."""
+def k1_traffic(layout, run_cap):
+    """DRAM bytes per launch of the per-observation kernel from the committed ncu --set full capture of the SAME kernel
+    and configuration (profiles/r2_k1_traffic.json lists layout, run_cap and n_obs it was taken on); None otherwise."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")) as f:
-            return float(json.load(f)["traffic"])
+        with open(os.path.join(ROOT, "profiles", "r2_k1_traffic.json")) as f:
+            rec = json.load(f)
+        if rec.get("layout") == layout and int(rec.get("run_cap", -1)) == int(run_cap) and int(rec.get("n_obs", -1)) == N_TOTAL:
+            return float(rec["traffic"])
     except Exception:
-        return None
+        pass
+    return None
 
 
 def measured_peaks():
@@ -330,9 +334,9 @@ def main():
     ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--obs-layout", default="packed", choices=["packed", "binned"],
-                    help="layout the fused per-observation kernel streams: 'packed' = k_obs_b1 (default, the kernel "
-                         "verified on B200 in round 1); 'binned' = k_obs_b1_binned (per-cell runs, opt-in)")
+    ap.add_argument("--obs-layout", default="binned", choices=["packed", "binned"],
+                    help="layout the fused per-observation kernel streams: 'binned' = k_obs_b1_binned (per-cell runs in "
+                         "warp tasks, default since round 2); 'packed' = k_obs_b1 (round-1 kernel, cross-check)")
     ap.add_argument("--run-cap", type=int, default=256, help="binned layout: longest run of one cell")
     ap.add_argument("--binned-stream", default="ldg", choices=["ldg", "tma"],
                     help="binned layout: 16-byte global loads into registers, or a per-warp shared-memory ring "
@@ -454,6 +458,8 @@ def main():
         torch.cuda.synchronize()
     launches0 = lib.vggp_launch_count()
     barrier()
+    if graphed is None:
+        plan.k1_timing(True)          # the library brackets the per-observation kernel itself with CUDA events
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -469,17 +475,21 @@ def main():
     if graphed is not None:
         # events cannot be recorded inside a replayed graph: time the per-observation kernel in a separate loop
         torch.cuda.synchronize()
+        plan.k1_timing(True)
         for i in range(args.steps):
             ev_a[i].record()
             plan.obs_fwd_bwd(packed)
             ev_b[i].record()
         torch.cuda.synchronize()
-    k1_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps
-    tt = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=device)
+    k1_kernel_ms, k1_launches = plan.k1_time_read()       # the kernel alone (events inside the C call, same stream)
+    plan.k1_timing(False)
+    k1_call_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps   # whole vggp_obs_fwd_bwd* call
+    tt = torch.tensor([ms_total, k1_kernel_ms, k1_call_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = tt[0].item() / args.steps
     k1_ms = tt[1].item()
+    k1_call_ms = tt[2].item()
     value = n_total / (ms_step * 1e-3)
 
     # ---- secondary leg: same step on observations left in acquisition (along-track) order
@@ -578,9 +588,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": ("k_obs_b1" if args.obs_layout == "packed" else "k_obs_b1_binned")
                          + " (fused per-observation ELBO forward+backward)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (k1_traffic() if (world == 1 and n_total == N_TOTAL
-                                                      and args.obs_layout == "packed") else None),
-                         "peak_source": peak_src, "kernel_ms": k1_ms,
+                         "traffic": (k1_traffic(args.obs_layout, args.run_cap) if (world == 1 and n_total == N_TOTAL) else None),
+                         "peak_source": peak_src, "kernel_ms": k1_ms, "kernel_launches_timed": k1_launches,
+                         "timing": "CUDA events recorded by the library immediately around the kernel launch, on the "
+                                   "launching stream, inside the timed region (vggp_k1_timing)",
+                         "call_ms": k1_call_ms,
+                         "call_note": "whole vggp_obs_fwd_bwd* call: gradient-buffer memset + kernel + band-replica reduction",
                          "algorithmic_bytes": alg_bytes,
                          "share_of_step": k1_ms / ms_step},
             "gpu_launches": int(launches),

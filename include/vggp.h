@@ -194,6 +194,17 @@ int vggp_grid_backward(vggp_plan* plan, const double* theta, const double* m, co
                        const void* gbuf, double ell_scale,
                        double* out, double* dtheta, double* dm, double* dL, void* stream);
 
+/*
+ * Device timing of the dominant kernel (the fused per-observation kernel), for roofline reporting: while enabled, every
+ * vggp_obs_fwd_bwd* call records one CUDA event immediately before and one immediately after the launch of that kernel
+ * on `stream` (not around the memsets / the band-replica reduction that belong to the same call).
+ *   vggp_k1_timing     enable != 0: (re)start collecting; 0: stop.
+ *   vggp_k1_time_read  mean duration in milliseconds over the launches recorded since the last (re)start (the most recent
+ *                      256 at most) and their number; synchronises the recorded events.
+ */
+int vggp_k1_timing(vggp_plan* plan, int enable);
+int vggp_k1_time_read(vggp_plan* plan, float* mean_ms, int* n_launches);
+
 /* Failed-factorisation flag of the last forward (0 = ok, d+1 = factor d not positive definite).
  * Synchronises `stream`. */
 int vggp_read_info(vggp_plan* plan, int* info_host, void* stream);

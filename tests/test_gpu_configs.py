@@ -1,0 +1,270 @@
+"""Parity of the CUDA path with the oracle AT THE BASELINE.json CONFIGURATIONS (SURVEY.md section 8, configs[0..4]).
+
+Every case compares the ELBO and every gradient block (d theta, d m, d L_d) produced through the C ABI with the CPU
+oracle on identical inputs, at the configuration's own size:
+
+  configs[0]  1-D, N = 10 000, 256 inducing variables, float64, both feature families, against the reference's LITERAL
+              collapsed bound (dense N x N algebra, univariate_structure.py:234-263 / gridded_univariate_structure.py:709-844)
+              at the reference's optimal q(u) = N(m*, S*) -- in 1-D S* = L L^T is a 'Kronecker product of one factor', so the
+              uncollapsed bound must reproduce the collapsed one, and by the envelope theorem so must the
+              hyper-parameter gradients; tolerance 1e-5 (north star, float64).
+  configs[1]  2-D meshgrid of 1000 x 1000 observations (gen_2d, datagenerators.py:37-73), 128 x 128 grid, float64, both
+              families (kronecker_structure.py:524-662, 671-849), structured oracle accumulated over chunks, 1e-5.
+  configs[2]  2-D along-track observations, N = 2^24, 512 x 512 grid, float32 observations, 1e-3 (B1 family at full size;
+              the B0 family on a 2^19 sample of the same generator -- its oracle is O(N M_d^2) dense algebra).
+  configs[4]  the bench configuration, N = 2^26 (same data and parameters as bench.py), 1e-3.
+  configs[3]  3-D: a (64, 64, 16) grid with 2^20 float32 observations (the 256 x 256 x 64 / 2^26 run is a bench workload).
+
+The structured oracle is evaluated in float64 on the float32-quantised inputs; it is accumulated over observation chunks
+(tests/chunked_oracle.py) because the expected log-likelihood is a plain sum.  Tolerances are the north star's: 1e-5
+relative with float64 observations, 1e-3 with float32 (gradients: relative in the 2-norm per block)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from chunked_oracle import elbo_and_grads_chunked
+from oracle import vggp_oracle as O
+from test_gpu_elbo import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vg():
+    import vggp_b200
+    vggp_b200._lib.load()
+    return vggp_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, tol, D, N, what=""):
+    assert plan.read_info() == 0
+    assert out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (what, out.cpu(), elbo_ref)
+    assert relerr(dtheta[:D], g_ref[0]) < tol, (what, "dl", dtheta[:D].cpu(), g_ref[0])
+    assert relerr(dtheta[D:2 * D], g_ref[1]) < tol, (what, "ds2", dtheta[D:2 * D].cpu(), g_ref[1])
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol, (what, "dnoise", dtheta[2 * D].cpu(), g_ref[2])
+    assert relerr(dm, g_ref[3]) < tol, (what, "dm", relerr(dm, g_ref[3]))
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n).cpu()
+        off += n * n
+        assert torch.count_nonzero(torch.triu(dLd, 1)) == 0
+        assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol, (what, "dL", d, relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])))
+
+
+def _layouts(vg, plan, xs, y, family):
+    """The hot-path layout (binned; B0: scan form) and, for the B1 family, the packed layout as a cross-check."""
+    yield "binned", plan.bin(xs, y, run_cap=256), None
+    if family == O.B1_ASVGP:
+        yield "packed", plan.pack(xs, y, sort_by_cell=True), None
+
+
+# ---- configs[0]: 1-D, N = 10 000, 256 inducing variables, float64 ------------------------------------------------------
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED], ids=["Matern12B1SplineASVGP", "Matern12B0SplineGriddedGP"])
+def test_config0_1d_literal_collapsed_bound(vg, dev, family):
+    N, n_ind = 10_000, 256
+    g = torch.Generator().manual_seed(0)
+    x = torch.linspace(0, 2, N, dtype=torch.float64)                      # gen_1d-style inputs (datagenerators.py:8-34)
+    y = torch.sin(x) + torch.cos(x) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    mesh = torch.linspace(0.0, 2.0, n_ind if family == O.B1_ASVGP else n_ind + 1)
+    raw0 = torch.zeros(1, dtype=torch.float64)
+    l, s2, noise = O.constrain(raw0, raw0.clone(), torch.zeros((), dtype=torch.float64))   # gpytorch defaults (raw = 0)
+    X = x.reshape(-1, 1)
+    # the reference's algorithm, literally (dense N x N evidence covariance), value only
+    with torch.no_grad():
+        elbo_lit = O.elbo_collapsed_literal(family, [mesh], X, y, l, s2, noise, ref_quirks=False)
+        m_star, S_star = O.optimal_q(family, [mesh], X, y, l, s2, noise, ref_quirks=False)
+    # the same bound through M x M algebra gives the hyper-parameter gradients (identity checked on the CPU suite)
+    lg, sg, ng = l.clone().requires_grad_(True), s2.clone().requires_grad_(True), noise.clone().requires_grad_(True)
+    elbo_w = O.elbo_collapsed_woodbury(family, [mesh], X, y, lg, sg, ng, ref_quirks=False)
+    gl, gs, gn = torch.autograd.grad(elbo_w, [lg, sg, ng])
+    assert abs(elbo_w.item() - elbo_lit.item()) < 1e-9 * abs(elbo_lit.item())
+    Lc = torch.linalg.cholesky(0.5 * (S_star + S_star.T))
+    plan = vg.GridPlan(family, [mesh], torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    xs = [x.to(dev).contiguous()]
+    yd = y.to(dev).contiguous()
+    for name, obs, yy in list(_layouts(vg, plan, xs, yd, family)) + [("raw", xs, yd)]:
+        out, dtheta, dm, dL = plan.step(theta, m_star.to(dev).contiguous(), Lc.reshape(-1).to(dev).contiguous(), obs, yy)
+        assert plan.read_info() == 0 and out[3].item() == N
+        assert abs(out[0].item() - elbo_lit.item()) < 1e-5 * abs(elbo_lit.item()), (name, out[0].item(), elbo_lit.item())
+        # envelope theorem: d/dtheta of the uncollapsed bound at its maximiser = d/dtheta of the collapsed bound
+        assert relerr(dtheta[0], gl) < 1e-5 and relerr(dtheta[1], gs) < 1e-5 and relerr(dtheta[2], gn) < 1e-5, \
+            (name, dtheta.cpu(), gl, gs, gn)
+        # (m*, S*) maximises the uncollapsed bound: the gradients with respect to m and L vanish there
+        alpha = plan.workspace(vg._lib.WS_ALPHA)
+        assert dm.abs().max().item() < 1e-5 * alpha.abs().max().item(), name
+        n = plan.m_per_dim[0]
+        dLn = torch.tril(dL.reshape(n, n)).norm().item()
+        scale_L = (float(n) / torch.diagonal(Lc).abs().min().item())       # size of the individual terms of dL
+        assert dLn < 1e-5 * scale_L * n, (name, dLn)
+
+
+# ---- configs[1]: 2-D meshgrid 1000 x 1000, 128 x 128 grid, float64 -----------------------------------------------------
+def _latent_2d(x1, x2):
+    return torch.sin(2 * math.pi * x1) * torch.cos(2 * math.pi * x2) + 0.5 * torch.sin(6 * x1 + 3 * x2)
+
+
+def _mid_params(family, meshes, seed):
+    """A point between prior and posterior: m = Kuu f0 + noise, L_d = chol(K_d)(I/2 + small lower-triangular noise)."""
+    g = torch.Generator().manual_seed(seed)
+    D = len(meshes)
+    l = torch.full((D,), 0.12, dtype=torch.float64) + 0.03 * torch.arange(D, dtype=torch.float64)
+    s2 = torch.full((D,), 1.1, dtype=torch.float64) - 0.1 * torch.arange(D, dtype=torch.float64)
+    noise = torch.tensor(0.02, dtype=torch.float64)
+    Ks = [O.kuu_factor(family, meshes[d], l[d], s2[d], ref_quirks=False).to(torch.float64) for d in range(D)]
+    Ms = [K.shape[0] for K in Ks]
+    if family == O.B1_ASVGP:
+        pts = [m_.to(torch.float64) for m_ in meshes]
+    else:
+        pts = [0.5 * (m_[1:] + m_[:-1]).to(torch.float64) for m_ in meshes]
+    grids = torch.meshgrid(*pts, indexing="ij")
+    f0 = torch.sin(5 * grids[0]) + torch.cos(7 * grids[-1])
+    mt = f0
+    for d in range(D):
+        mt = O.mode_product(mt, Ks[d], d)
+    m = (mt.reshape(-1) * (1.0 + 0.01 * torch.randn(mt.numel(), generator=g, dtype=torch.float64))).contiguous()
+    Ls = []
+    for K, n in zip(Ks, Ms):
+        Cc = torch.linalg.cholesky(K)
+        G = 0.5 * torch.eye(n, dtype=torch.float64) + 0.05 * torch.tril(torch.randn(n, n, generator=g, dtype=torch.float64)) / math.sqrt(n)
+        Ls.append(Cc @ G)
+    return l, s2, noise, m, Ls
+
+
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED], ids=["Matern12B1SplineASVGP", "Matern12B0SplineGriddedGP"])
+def test_config1_2d_meshgrid_1M_128x128_fp64(vg, dev, family):
+    nobs = 1000
+    g1 = torch.linspace(0, 1, nobs, dtype=torch.float64)
+    X1, X2 = torch.meshgrid(g1, g1, indexing="ij")
+    X = torch.stack([X1.reshape(-1), X2.reshape(-1)], dim=1)
+    gen = torch.Generator().manual_seed(1)
+    y = _latent_2d(X[:, 0], X[:, 1]) + 0.05 * torch.randn(X.shape[0], generator=gen, dtype=torch.float64)
+    knots = 128 if family == O.B1_ASVGP else 129
+    meshes = [torch.linspace(0, 1, knots), torch.linspace(0, 1, knots)]
+    l, s2, noise, m, Ls = _mid_params(family, meshes, seed=5)
+    chunk = 1 << 18 if family == O.B1_ASVGP else 1 << 16
+    elbo_ref, g_ref = elbo_and_grads_chunked(family, meshes, X, y, l, s2, noise, m, Ls, chunk=chunk)
+    plan = vg.GridPlan(family, meshes, torch.float64, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    xs = [X[:, d].contiguous().to(dev) for d in range(2)]
+    yd = y.to(dev)
+    for name, obs, yy in _layouts(vg, plan, xs, yd, family):
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, obs, yy)
+        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-5, 2, X.shape[0], name)
+
+
+# ---- configs[2] and configs[4]: along-track observations, 512 x 512 grid, float32 --------------------------------------
+def _track_problem(n, dev):
+    import bench
+    meshes = [torch.linspace(0, 1, k) for k in bench.KNOTS]
+    xs, y = bench.make_tracks(0, n, n, dev, torch.float32)
+    theta, m, Ls = bench.make_params(meshes, dev)
+    return meshes, xs, y, theta, m, Ls
+
+
+@pytest.mark.parametrize("log2n", [24, 26], ids=["configs2_N16M", "configs4_bench_N64M"])
+def test_config2_and_bench_tracks_512x512_fp32_b1(vg, dev, log2n):
+    N = 1 << log2n
+    meshes, xs, y, theta, m, Ls = _track_problem(N, dev)
+    X = torch.stack([x.cpu() for x in xs], dim=1)          # float32, what the kernel sees
+    elbo_ref, g_ref = elbo_and_grads_chunked(O.B1_ASVGP, meshes, X, y.cpu(), theta[:2].clone(), theta[2:4].clone(),
+                                             theta[4].clone(), m, Ls, chunk=1 << 21)
+    del X
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    theta_d, m_d = theta.to(dev), m.to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    for name, obs, yy in _layouts(vg, plan, xs, y, O.B1_ASVGP):
+        out, dtheta, dm, dL = plan.step(theta_d, m_d, Lcat, obs, yy)
+        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-3, 2, N, name)
+        del obs
+
+
+def test_config2_tracks_512x512_fp32_b0_sample(vg, dev):
+    """Matern12GriddedGP at the configs[2] grid (511 x 511 cells) on a 2^19 sample of the same track generator."""
+    import bench
+    N = 1 << 19
+    meshes = [torch.linspace(0, 1, k) for k in bench.KNOTS]
+    xs, y = bench.make_tracks(0, N, N, dev, torch.float32)
+    l, s2, noise, m, Ls = _mid_params(O.B0_GRIDDED, meshes, seed=7)
+    l = torch.tensor([0.02, 0.03], dtype=torch.float64)      # l / delta ~ 10 - 15: the reference's float32 Toeplitz row stays positive definite
+    X = torch.stack([x.cpu() for x in xs], dim=1)
+    elbo_ref, g_ref = elbo_and_grads_chunked(O.B0_GRIDDED, meshes, X, y.cpu(), l, s2, noise, m, Ls, chunk=1 << 15)
+    plan = vg.GridPlan(vg.B0_GRIDDED, meshes, torch.float32, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    for name, obs, yy in _layouts(vg, plan, xs, y, O.B0_GRIDDED):
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, obs, yy)
+        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-3, 2, N, name)
+
+
+# ---- configs[3] shape at reduced size: 3-D (64, 64, 16) grid, 2^20 float32 observations ---------------------------------
+def test_config3_shape_3d_64x64x16_fp32(vg, dev):
+    N = 1 << 20
+    knots = (64, 64, 16)
+    meshes = [torch.linspace(0, 1, k) for k in knots]
+    g = torch.Generator().manual_seed(11)
+    # track-like: two spatial coordinates from the 2-D generator, time increasing along the acquisition order
+    import bench
+    xs2, y2 = bench.make_tracks(0, N, N, torch.device("cpu"), torch.float32)
+    t = (torch.arange(N, dtype=torch.float64) + torch.rand(N, generator=g, dtype=torch.float64)) / N
+    X = torch.stack([xs2[0].to(torch.float64), xs2[1].to(torch.float64), t], dim=1).to(torch.float32)
+    y = (y2.to(torch.float64) + 0.3 * torch.sin(4 * t)).to(torch.float32)
+    l, s2, noise, m, Ls = _mid_params(O.B1_ASVGP, meshes, seed=13)
+    elbo_ref, g_ref = elbo_and_grads_chunked(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls, chunk=1 << 18)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float32, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    xs = [X[:, d].contiguous().to(dev) for d in range(3)]
+    for name, obs, yy in _layouts(vg, plan, xs, y.to(dev), O.B1_ASVGP):
+        out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, obs, yy)
+        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-3, 3, N, name)
+
+
+# ---- model-level minibatch: _elbo(batch=idx) scales the expected log-likelihood by N / B -----------------------------
+def test_model_minibatch_elbo_matches_oracle(vg, dev):
+    import importlib
+    gks = importlib.import_module("variational-gridded-gaussian-processes_b200.models.sparse.gridded_kronecker_structure")
+    N, B = 20_000, 2_500
+    g = torch.Generator().manual_seed(21)
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64)
+    y = _latent_2d(X[:, 0], X[:, 1]) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    model = gks.GriddedMatern12ASVGP(X, y, 24, 0, (0.0, 1.0), (0.0, 1.0)).to(torch.float64).to(dev)
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.1)
+        model.variational_chol_1.add_(0.05 * torch.tril(torch.randn_like(model.variational_chol_1)))
+        model.variational_chol_2.add_(0.05 * torch.tril(torch.randn_like(model.variational_chol_2)))
+        model.kernel_1.base_kernel.lengthscale = 0.3
+        model.kernel_2.base_kernel.lengthscale = 0.25
+        model.likelihood.noise = 0.05
+    idx = torch.randperm(N, generator=g)[:B]
+    params = list(model.parameters())
+    elbo = model._elbo(batch=idx.to(dev))
+    elbo.backward()
+    # oracle at the model's current constrained values, expected log-likelihood scaled by N / B
+    l = torch.stack([model.kernel_1.base_kernel.lengthscale.reshape(()), model.kernel_2.base_kernel.lengthscale.reshape(())]).detach().cpu()
+    s2 = torch.stack([model.kernel_1.outputscale.reshape(()), model.kernel_2.outputscale.reshape(())]).detach().cpu()
+    noise = model.likelihood.noise.reshape(()).detach().cpu()
+    m = model.variational_mean.detach().cpu().reshape(-1)
+    Ls = [model.variational_chol_1.detach().cpu(), model.variational_chol_2.detach().cpu()]
+    meshes = [O.make_padded_mesh(0, 1, 24, 0)] * 2
+    elbo_ref, g_ref = elbo_and_grads_chunked(O.B1_ASVGP, meshes, X[idx], y[idx], l, s2, noise, m, Ls, scale=N / B)
+    assert abs(elbo.item() - elbo_ref.item()) < 1e-8 * abs(elbo_ref.item()), (elbo.item(), elbo_ref.item())
+    assert relerr(model.variational_mean.grad.reshape(-1), g_ref[3]) < 1e-7
+    assert relerr(torch.tril(model.variational_chol_1.grad), torch.tril(g_ref[4])) < 1e-7
+    assert relerr(torch.tril(model.variational_chol_2.grad), torch.tril(g_ref[5])) < 1e-7
+    assert len(params) > 0 and all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+    # the full-batch bound of the same model through the default (binned) layout
+    model.zero_grad()
+    full = model._elbo()
+    ref_full, _ = elbo_and_grads_chunked(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls)
+    assert abs(full.item() - ref_full.item()) < 1e-8 * abs(ref_full.item())

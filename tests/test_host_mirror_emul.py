@@ -147,7 +147,7 @@ def test_model_training_loop_over_the_emulator(host, monkeypatch, family, layout
     if layout == "binned":
         monkeypatch.setenv("VGGP_OBS_LAYOUT", "binned")
     else:
-        monkeypatch.delenv("VGGP_OBS_LAYOUT", raising=False)
+        monkeypatch.setenv("VGGP_OBS_LAYOUT", "packed")       # the round-1 layouts (B1: packed runs, B0: dense-feature kernel)
     g = torch.Generator().manual_seed(0)
     N = 400
     X = torch.rand(N, 2, generator=g, dtype=torch.float64)

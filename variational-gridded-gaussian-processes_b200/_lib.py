@@ -46,6 +46,8 @@ SIGNATURES = {
     "vggp_set_binned_stream": (C.c_int, [C.c_int]),
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
+    "vggp_k1_timing": (C.c_int, [_vp, C.c_int]),
+    "vggp_k1_time_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vggp_predict": (C.c_int, [_vp, C.POINTER(_vp), _i64, _dp, _dp, _vp]),
     "vggp_metrics": (C.c_int, [C.c_int, _dp, _dp, _i64, _dp, _vp]),
     "vggp_predict_metrics": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),

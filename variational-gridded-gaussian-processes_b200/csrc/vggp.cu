@@ -74,6 +74,8 @@ struct vggp_plan {
     double* b0s_bM = nullptr;              // (K-1) x (K-1), largest dimension
     double* b0s_Gam[2] = {};               // (K+1) x (K-1), largest dimension
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
+    // optional device timing of the per-observation kernel (vggp_k1_timing)
+    bool k1_timing = false; std::vector<cudaEvent_t> k1_ev; int k1_count = 0;
     void* band_rep = nullptr;              // B1 family, binned kernel: BAND_REPLICAS copies of the band block (obs dtype), kept zero
                                            // between launches (k_band_reduce clears what it sums)
     // schedules
@@ -469,6 +471,13 @@ int build_schedules(vggp_plan* p) {
     return 0;
 }
 
+constexpr int K1_EVENT_PAIRS = 256;
+inline void k1_mark(vggp_plan* p, int which, cudaStream_t st) {
+    if (!p->k1_timing || p->k1_ev.empty()) return;
+    cudaEventRecord(p->k1_ev[2 * (p->k1_count % K1_EVENT_PAIRS) + which], st);
+    if (which == 1) ++p->k1_count;
+}
+
 PackGeom pack_geometry(const vggp_plan* p, i64 n) {
     PackGeom g;
     // Chunks of 32 lanes x R observations are handed out dynamically to the resident (persistent) warps.  R is chosen so
@@ -533,7 +542,9 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
     i64 blocks = (a.geo.nwarps + (OBS_THREADS / 32) - 1) / (OBS_THREADS / 32);
     blocks = std::min<i64>(blocks, (i64)p->sm_count * p->obs_blocks_per_sm);
+    k1_mark(p, 0, st);
     k_obs_b1<T, D><<<(unsigned)blocks, OBS_THREADS, obs_smem_bytes<T, D>(p), st>>>(a);
+    k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -619,7 +630,9 @@ int launch_obs_b0(vggp_plan* p, const void* const* x, const void* y, i64 n, void
     VGGP_CUDA(cudaFuncSetAttribute(k_obs_b0<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 tiles = (n + B0_TN - 1) / B0_TN;
     const int blocks = (int)std::min<i64>(tiles, (i64)p->sm_count * 2);
+    k1_mark(p, 0, st);
     k_obs_b0<T, D><<<blocks, 256, smem, st>>>(a);
+    k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -887,8 +900,10 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
     i64 blocks = (desc->n_tasks + BIN_WARPS - 1) / BIN_WARPS;
     blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[mode]));
+    k1_mark(p, 0, st);
     if (mode) k_obs_b1_binned_tma<T, D><<<(unsigned)blocks, BIN_THREADS, smem, st>>>(a);
     else k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a);
+    k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
     k_band_reduce<T><<<ceil_div(p->band_total, 64), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M);
     VGGP_LAUNCH_CHECK();
@@ -1213,7 +1228,9 @@ int launch_obs_b0s(vggp_plan* p, const vggp_binned_desc* desc, const void* binne
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
     i64 blocks = (desc->n_tasks + (B0S_THREADS / 32) - 1) / (B0S_THREADS / 32);
     blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * 2));
+    k1_mark(p, 0, st);
     k_obs_b0s<T, D><<<(unsigned)blocks, B0S_THREADS, 0, st>>>(a);
+    k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
     return b0scan_adjoint<T, D>(p, gbuf, st);
 }
@@ -1426,6 +1443,7 @@ int vggp_plan_destroy(vggp_plan* p) {
         if (p->pk_x[d]) cudaFree(p->pk_x[d]);
     if (p->pk_y) cudaFree(p->pk_y);
     if (p->bin_perm) cudaFree(p->bin_perm);
+    for (auto& e : p->k1_ev) cudaEventDestroy(e);
     void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
     for (void* ptr : st)
         if (ptr) cudaFree(ptr);
@@ -1700,6 +1718,32 @@ int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const
     VGGP_CUDA(cudaMemsetAsync(dtheta, 0, sizeof(double) * (2 * D + 1), st));
     k_bwd_theta<<<dim3(p->g.structured == 2 ? 96 : (p->g.structured ? 24 : 64), D), 256, 0, st>>>(p->g, theta, gscal, ell_scale, out, dtheta);
     VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int vggp_k1_timing(vggp_plan* p, int enable) {
+    if (!p) return fail(VGGP_E_ARG, "null plan");
+    if (enable && p->k1_ev.empty()) {
+        p->k1_ev.resize(2 * K1_EVENT_PAIRS);
+        for (auto& e : p->k1_ev) VGGP_CUDA(cudaEventCreate(&e));
+    }
+    p->k1_timing = enable != 0;
+    if (enable) p->k1_count = 0;
+    return 0;
+}
+
+int vggp_k1_time_read(vggp_plan* p, float* mean_ms, int* n_launches) {
+    if (!p || !mean_ms || !n_launches) return fail(VGGP_E_ARG, "null argument");
+    const int n = std::min(p->k1_count, K1_EVENT_PAIRS);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        VGGP_CUDA(cudaEventSynchronize(p->k1_ev[2 * i + 1]));
+        VGGP_CUDA(cudaEventElapsedTime(&ms, p->k1_ev[2 * i], p->k1_ev[2 * i + 1]));
+        acc += ms;
+    }
+    *mean_ms = n > 0 ? (float)(acc / n) : 0.f;
+    *n_launches = p->k1_count;
     return 0;
 }
 

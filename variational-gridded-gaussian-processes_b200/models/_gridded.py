@@ -108,10 +108,13 @@ class GriddedVariationalGP(nn.Module):
             xs = [Xd[:, d].contiguous() for d in range(self.D)]       # structure of arrays, made once
             y = self.train_targets.reshape(-1).to(device=device, dtype=dtype).contiguous()
             self._obs = (xs, y)
-            # one-time layout pass: order by grid cell + warp-transposed packing (setup, X is constant); the packed
-            # layout belongs to the compact-stencil (B1) kernel, the dense-feature (B0) kernel streams plain arrays
-            if os.environ.get("VGGP_OBS_LAYOUT", "packed") == "binned":       # opt-in, DESIGN.md sections 8 and 10:
-                self._packed = self._plan.bin(xs, y)                          # B1: k_obs_b1_binned, B0: scan form
+            # one-time layout pass (setup, X is constant over optimisation steps).  Default: per-cell runs grouped into warp
+            # tasks (B1: k_obs_b1_binned; B0, D <= 2: scan form of the cell-integrated features), DESIGN.md sections 8 and 10.
+            # VGGP_OBS_LAYOUT=packed selects the round-1 layouts (B1: cell-sorted packed runs, B0: plain arrays through the
+            # dense-feature kernel), kept as cross-checks.
+            layout = os.environ.get("VGGP_OBS_LAYOUT", "binned")
+            if layout == "binned" and not (self.family != _lib.B1_ASVGP and self.D > 2):
+                self._packed = self._plan.bin(xs, y)
             elif self.family != _lib.B1_ASVGP:
                 self._packed = None
             else:

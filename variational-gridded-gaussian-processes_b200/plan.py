@@ -104,8 +104,8 @@ class GridPlan:
 
     def bin(self, xs: Sequence[torch.Tensor], y: torch.Tensor, run_cap: int = 256) -> "BinnedObs":
         """One-time layout pass, second form (include/vggp.h, vggp_obs_bin_*): observations ordered by grid cell, cut
-        into per-cell runs of at most `run_cap`, 32 equally long runs per warp task.  Opt-in until it has been run
-        on a B200; `pack` is the default hot-path layout."""
+        into per-cell runs of at most `run_cap`, 32 equally long runs per warp task.  The hot-path layout of both
+        families since round 2 (DESIGN.md sections 8 and 10); `pack` stays as the any-order cross-check."""
         n = int(y.numel())
         self._check_obs(xs, y, n)
         desc = _lib.BinnedDesc()
@@ -236,6 +236,16 @@ class GridPlan:
             with torch.cuda.graph(gs.back):
                 gs.outs = self.grid_backward(theta, m, L, ell_scale)
         return gs
+
+    def k1_timing(self, enable: bool = True):
+        """Start / stop the library's own device timing of the per-observation kernel (vggp_k1_timing)."""
+        _lib.check(self.lib.vggp_k1_timing(self.handle, 1 if enable else 0))
+
+    def k1_time_read(self):
+        """(mean milliseconds, launches) of the per-observation kernel since k1_timing(True); synchronises."""
+        ms, n = C.c_float(0.0), C.c_int(0)
+        _lib.check(self.lib.vggp_k1_time_read(self.handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def read_info(self) -> int:
         info = C.c_int(0)
