@@ -84,6 +84,24 @@ def test_b1_step_matches_oracle_under_emulation(emu, knots, N, dtype, tol, layou
         plan.close()
 
 
+@pytest.mark.parametrize("knots,N", [((600,), 900), ((70, 45), 1500), ((40, 33, 35), 1200)])
+def test_fused_grid_side_larger_meshes_under_emulation(emu, knots, N):
+    """csrc/grid_b1.cuh beyond the small meshes above: several chunks in the generator scan (k_b1_gens), lanes owning more
+    than 16 elements of a fibre (600 knots: the shared-memory sweep of fp_fibre), tiles that straddle fibres of different
+    outer index (3-D middle mode), partial tiles."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=77 + D)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, X, y, l, s2, noise, m, Ls, scale=1.3)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    plan.bin(xs, y.numpy().copy(), run_cap=64), None, 1.3)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, 1e-9)
+    plan.close()
+
+
 @pytest.mark.parametrize("layout", ["packed_sorted", "binned_ldg"])
 def test_two_wave_run_length_under_emulation(emu, layout):
     """Enough observations that the packed layout needs two waves of chunks per resident warp (the emulated device
@@ -109,10 +127,11 @@ def test_two_wave_run_length_under_emulation(emu, layout):
     plan.close()
 
 
-@pytest.mark.parametrize("structured", [0, 1])
+@pytest.mark.parametrize("structured", [0, 1, 2])
 def test_dense_factor_paths_under_emulation(emu, structured):
-    """B1 family through the dense Cholesky + GEMM path (0) and the twisted inverse + GEMM products (1): grouped DMMA
-    GEMMs (mma.m8n8k4 and cp.async stand-ins) on the CPU."""
+    """B1 family through the dense Cholesky + GEMM path (0), the twisted inverse + GEMM products (1) and the round-1
+    semiseparable launches (2): grouped DMMA GEMMs (mma.m8n8k4 and cp.async stand-ins) on the CPU.  Every other test of
+    this file runs the default, the fused fibre passes of csrc/grid_b1.cuh (3)."""
     lib, L = emu
     knots, N = (10, 8), 600
     meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5)
@@ -121,7 +140,7 @@ def test_dense_factor_paths_under_emulation(emu, structured):
     try:
         plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
     finally:
-        lib.vggp_set_b1_structured(2)
+        lib.vggp_set_b1_structured(3)
     theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
     xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
     out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),

@@ -195,8 +195,8 @@ def test_simt_and_dmma_paths_agree(vg, dev):
 
 
 def test_structured_and_dense_factor_paths_agree(vg, dev):
-    """B1 family: twisted factorisation + semiseparable products (2, default) and twisted factorisation + DMMA GEMM
-    products (1) against the dense Cholesky path (0), whole step."""
+    """B1 family: the fused fibre passes (3, default), the round-1 semiseparable launches (2) and twisted factorisation +
+    DMMA GEMM products (1) against the dense Cholesky path (0), whole step."""
     knots, N = (150, 70), 3000
     meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=6)
     theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
@@ -204,16 +204,16 @@ def test_structured_and_dense_factor_paths_agree(vg, dev):
     xs = [X[:, d].contiguous().to(dev) for d in range(2)]
     res = []
     try:
-        for mode in (2, 1, 0):
+        for mode in (3, 2, 1, 0):
             vg._lib.load().vggp_set_b1_structured(mode)
             plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
             out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, y.to(dev))
             assert plan.read_info() == 0
             res.append((out.clone(), dtheta.clone(), dm.clone(), dL.clone()))
     finally:
-        vg._lib.load().vggp_set_b1_structured(2)
-    for k in (0, 1):
-        for a, b in zip(res[k], res[2]):
+        vg._lib.load().vggp_set_b1_structured(3)
+    for k in (0, 1, 2):
+        for a, b in zip(res[k], res[3]):
             assert relerr(a, b) < 1e-8
 
 
@@ -226,15 +226,16 @@ def test_structured_3d_and_odd_sizes(vg, dev):
     xs = [X[:, d].contiguous().to(dev) for d in range(3)]
     res = []
     try:
-        for mode in (2, 0):
+        for mode in (3, 2, 0):
             vg._lib.load().vggp_set_b1_structured(mode)
             plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
             out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, y.to(dev))
             res.append((out.clone(), dtheta.clone(), dm.clone(), dL.clone()))
     finally:
-        vg._lib.load().vggp_set_b1_structured(2)
-    for a, b in zip(res[0], res[1]):
-        assert relerr(a, b) < 1e-8
+        vg._lib.load().vggp_set_b1_structured(3)
+    for k in (0, 1):
+        for a, b in zip(res[k], res[2]):
+            assert relerr(a, b) < 1e-8
 
 
 def test_all_observations_outside_the_mesh(vg, dev):

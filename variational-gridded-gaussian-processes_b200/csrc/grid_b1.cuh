@@ -1,0 +1,666 @@
+// Fused grid side of the B1 (ASVGP) family: the whole replicated part of a step in a handful of launches.
+//
+// The per-dimension factor K_d of this family is tridiagonal (gridded_kronecker_structure.py:731-780), so P_d = K_d^-1 is
+// semiseparable and every product with it is a pair of first-order recurrences along a fibre (grid.cuh, k_ss_apply).  Round 1
+// ran those as 14 dependent small launches (0.2 ms per step: the Amdahl term of the multi-GPU run).  Here
+//   k_b1_gens     pivots of the twisted factorisation by a chunk-parallel scan (2 x 2 Moebius composition for the chunk
+//                 carries, the plain recurrence inside a chunk), generators, log det K_d, the P-band tables
+//   k_fibre_pass  ONE engine for every product with P_d: a CTA stages a tile of F fibres in shared memory (coalesced for
+//                 strided and for contiguous modes), one warp per fibre runs the two recurrences (lane-local sweeps + a
+//                 5-step affine scan across lanes), and a kind-specific prologue / epilogue fuses what round 1 did in
+//                 separate elementwise kernels (tril mask, casts, <m, alpha>, g / ghat from the gradient buffer, band
+//                 scatter, dR from R, tril / diagonal terms of dL, band dot products for dK)
+//   k_b1_theta    band of dK_d -> d theta, ELBO scalars
+// A step is: gens, pass F1 (R_d = P_d tril L_d, first mode of alpha), pass F2 (last mode of alpha + casts + row reductions
+// of R_d), the per-observation kernel, pass B1 (last mode of (kron P) g, A_e, X_d P_d), pass B2 (first mode, dL, P X P),
+// theta: 6 launches for D = 2 (one more forward and backward pass for D = 3).
+// Maths: SURVEY.md appendix A; same formulas as the round-1 path (grid.cuh), which stays as the cross-check.
+#pragma once
+#include "grid.cuh"
+
+namespace vggp {
+
+constexpr int FP_THREADS = 256;
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_MAX_TASKS = 14;
+constexpr int GEN_CHUNK = 32;            // pivots per thread in k_b1_gens
+constexpr int GEN_THREADS = 256;
+
+enum FpKind {
+    FP_R = 0,       // R_d = P_d tril(L_d): column k of tril(L_d) -> column k of R_d
+    FP_PROD,        // dst = src x_e P_e
+    FP_ALPHA,       // alpha = src x_e P_e, + cast to the observation dtype + <m, alpha>
+    FP_GA,          // g = c galpha, ghat = g - m / 2 from the gradient buffer; V = g x_e P_e (or dm = V - alpha), A_e = ghat x_e P_e
+                    // is only contracted: acc_e[i][i + dl] += sum_rest A_e[.. i ..] alpha[.. i + dl ..]
+    FP_GAONLY,      // the A_e contraction alone (modes other than the one the dm chain starts with)
+    FP_YP,          // Y'_d = X_d P_d, X_d = tridiagonal band scatter of the per-observation sums bp (row k synthesised)
+    FP_DM,          // dm = src x_e P_e - alpha
+    FP_DL,          // column k of dR_d = 2 cQ tridiag(bq) R_d -> dLraw = P_d dR; dL = tril(dLraw - c_d R + (M/M_d) diag(1/L_ii));
+                    // acc_d[i][i + dl] += dLraw[i][k] R[i + dl][k]
+    FP_Z,           // Z_d = P_d Y'_d, band only: acc_d[j + dl][j] += Z[j + dl][j]
+    FP_QROW         // no product: row reductions of R_d (band of Q_d, tr(P_d S_d), log det S_d, Q-band tables)
+};
+
+struct FpTask {
+    int kind, d, n, F;            // d: dimension whose P_d is applied; n = M_d; F = fibres of one tile (in shared memory)
+    i64 inner, nfib;              // fibre f = (o, r): element i at (o n + i) inner + r; nfib = outer * inner
+    int tile0, ntiles;
+    const double* s0;             // PROD / ALPHA / DM: source tensor;  R / DL: L_d resp. R_d;  Z: Y'_d;  GA*: m
+    const double* s1;             // ALPHA: m;  GA / GAONLY / DM: alpha;  DL: L_d
+    double* o0;                   // PROD / ALPHA / R / YP: destination;  GA: V (or dm when `direct`);  DM: dm;  DL: dL
+    const void* t0;               // GA*: galpha;  YP / DL: band sums of dimension d [bp_d | bp_o | bq_d | bq_o] (obs dtype)
+    void* t1;                     // ALPHA: alpha in the observation dtype
+    int direct;                   // GA with D == 1: o0 receives dm = V - alpha
+};
+
+struct FpPass {
+    FpTask t[FP_MAX_TASKS];
+    int ntasks;
+    int D, obs_f32;
+    i64 M;
+    double ell_scale;
+    const double* theta;
+    double* gen[VGGP_MAX_D];      // generators of P_d: [pd | ru | rl] (n each; the other slots belong to the round-1 path)
+    double* acc[VGGP_MAX_D];      // band accumulators of dK_d: [3][n], slot (dl + 1, i) = W[i][i + dl]
+    double* sc;                   // SC_* scalars
+    double* Qb[VGGP_MAX_D];
+    void* bandT;                  // per-cell tables (obs dtype)
+    int tab_off[VGGP_MAX_D];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Generators.  Top-down pivots d_k = a_k - b_{k-1}^2 / d_{k-1} and bottom-up pivots e_k = a_k - b_k^2 / e_{k+1} are
+// Moebius maps of the previous pivot; a chunk of GEN_CHUNK of them composes to one 2 x 2 matrix (entries are minors of
+// K_d, rescaled by exact powers of two), a single thread chains the 2 x n/GEN_CHUNK carries, and every chunk then runs the
+// plain recurrence from its carry -- which contracts the (already small) error of the carry.  512 pivots: 3 x 32
+// dependent steps instead of 512.
+// grid (D), GEN_THREADS threads, dynamic smem 4 n doubles.
+// ---------------------------------------------------------------------------------------------------------
+struct Mob { double a, b, c, d; };     // x -> (a x + b) / (c x + d)
+
+__device__ __forceinline__ void mob_rescale(Mob& m) {
+    const double mx = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
+    if (mx > 1e100 || mx < 1e-100) {
+        int ex;
+        frexp(mx, &ex);
+        m.a = ldexp(m.a, -ex); m.b = ldexp(m.b, -ex); m.c = ldexp(m.c, -ex); m.d = ldexp(m.d, -ex);
+    }
+}
+// apply x -> p - q / x after m:  (p (a x + b) - q (c x + d)) / (a x + b)
+__device__ __forceinline__ void mob_push(Mob& m, double p, double q) {
+    const double na = fma(p, m.a, -q * m.c), nb = fma(p, m.b, -q * m.d);
+    m.c = m.a; m.d = m.b; m.a = na; m.b = nb;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+                                                         double* __restrict__ acc_all, int acc_total) {
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ double carry_d[GEN_THREADS], carry_e[GEN_THREADS];
+    __shared__ Mob comp_d[GEN_THREADS], comp_e[GEN_THREADS];
+    __shared__ int bad_flag;
+    const int d = blockIdx.x;
+    const int n = g.n[d];
+    const int tid = threadIdx.x;
+    double* a = sm;
+    double* b = a + n;
+    double* dd = b + n;
+    double* ee = dd + n;
+    if (tid == 0) bad_flag = 0;
+    if (d == 0) {
+        if (tid < SC_COUNT) g.sc[tid] = 0.0;
+        if (tid == 0) *g.info = 0;
+    }
+    // the band accumulators of every dimension are cleared here, at the start of the step
+    for (int i = (int)blockIdx.x * GEN_THREADS + tid; i < acc_total; i += (int)gridDim.x * GEN_THREADS) acc_all[i] = 0.0;
+    for (int i = tid; i < n; i += GEN_THREADS) {
+        a[i] = factor_entry(g, theta, d, i, i);
+        b[i] = (i + 1 < n) ? factor_entry(g, theta, d, i, i + 1) : 0.0;
+    }
+    __syncthreads();
+    const int nch = (n + GEN_CHUNK - 1) / GEN_CHUNK;      // <= GEN_THREADS / 2 (n <= 2560: 80 chunks)
+    // threads [0, nch): top-down chunk composites; threads [128, 128 + nch): bottom-up
+    const bool up = tid >= GEN_THREADS / 2;
+    const int ch = up ? tid - GEN_THREADS / 2 : tid;
+    if (ch < nch) {
+        Mob m = {1.0, 0.0, 0.0, 1.0};
+        if (!up) {
+            // chunk covers k in [k0, k1); maps d_{k0 - 1} -> d_{k1 - 1}
+            const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
+            for (int k = max(k0, 1); k < k1; ++k) {
+                mob_push(m, a[k], b[k - 1] * b[k - 1]);
+                if ((k & 7) == 7) mob_rescale(m);
+            }
+            comp_d[ch] = m;
+        } else {
+            // chunk covers k in [k0, k1) walked downwards; maps e_{k1} -> e_{k0}
+            const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
+            for (int k = min(k1 - 1, n - 2); k >= k0; --k) {
+                mob_push(m, a[k], b[k] * b[k]);
+                if ((k & 7) == 0) mob_rescale(m);
+            }
+            comp_e[ch] = m;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double x = a[0];                                   // d_0; chunk 0's composite starts from it
+        for (int c = 0; c < nch; ++c) {
+            carry_d[c] = x;                                // value entering chunk c (d_{k0 - 1}; for c = 0: d_0 itself)
+            const Mob m = comp_d[c];
+            x = (m.a * x + m.b) / (m.c * x + m.d);
+        }
+    } else if (tid == 32) {
+        double x = a[n - 1];                               // e_{n-1}
+        for (int c = nch - 1; c >= 0; --c) {
+            carry_e[c] = x;                                // value entering chunk c from above (e_{k1}; top chunk: e_{n-1} itself)
+            const Mob m = comp_e[c];
+            x = (m.a * x + m.b) / (m.c * x + m.d);
+        }
+    }
+    __syncthreads();
+    if (ch < nch) {
+        const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
+        bool bad = false;
+        if (!up) {
+            double prev = carry_d[ch];
+            int k = k0;
+            if (ch == 0) { dd[0] = prev; bad = !(prev > 0.0); k = 1; }
+            for (; k < k1; ++k) {
+                const double bk = b[k - 1];
+                prev = a[k] - bk * bk / prev;
+                dd[k] = prev;
+                bad = bad || !(prev > 0.0);
+            }
+        } else {
+            double nxt = carry_e[ch];
+            int k = k1 - 1;
+            if (k1 == n) { ee[n - 1] = nxt; k = n - 2; }
+            for (; k >= k0; --k) {
+                const double bk = b[k];
+                nxt = a[k] - bk * bk / nxt;
+                ee[k] = nxt;
+                bad = bad || !(nxt > 0.0);
+            }
+        }
+        if (bad) bad_flag = 1;
+    }
+    __syncthreads();
+    if (tid == 0 && bad_flag) atomicMax(g.info, d + 1);
+    double* gen = g.gen[d];
+    double ld = 0.0;
+    for (int i = tid; i < n; i += GEN_THREADS) {
+        const double pdv = 1.0 / (dd[i] + ee[i] - a[i]);
+        const double ruv = (i + 1 < n) ? -b[i] / dd[i] : 0.0;
+        const double rlv = (i + 1 < n) ? -b[i] / ee[i + 1] : 0.0;
+        gen[i] = pdv; gen[n + i] = ruv; gen[2 * n + i] = rlv;
+        ld += log(dd[i]);
+        a[i] = pdv;            // reuse: a = pd, b = ru  (P-band tables below)
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += GEN_THREADS) if (i + 1 < n) dd[i] = -b[i] / dd[i];   // dd = ru
+    __syncthreads();
+    // per-cell tables of the band of P_d, monomial basis in the hat weight (same as k_fwd_reduce)
+    T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];
+    for (int i = tid; i < n; i += GEN_THREADS) {
+        const bool last = (i + 1 >= n);
+        const double A = a[i];
+        const double B2 = last ? 0.0 : 2.0 * a[i + 1] * dd[i];        // 2 P[i][i+1] = 2 pd[i+1] ru[i]
+        const double Cc = last ? 0.0 : a[i + 1];
+        tab[i] = (T)A; tab[n + i] = (T)(B2 - 2.0 * A); tab[2 * n + i] = (T)(A - B2 + Cc);
+    }
+    ld = block_sum(ld, red);
+    if (tid == 0) g.sc[SC_LOGDETK + d] = ld;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The fibre engine.
+// Shared memory (dynamic):  [pd | ru | rl] padded, then tile arrays X (source -> result), C (auxiliary fibres), U (upper
+// sweep values, only when a lane owns more than 16 elements), then F fibre bases.
+// Padded index of element i of a fibre: i + i / S, S = ceil(n / 32) elements per lane (lane l owns [l S, (l+1) S)); the
+// extra slot per lane makes the lane-strided accesses of the sweeps conflict-free.
+// ---------------------------------------------------------------------------------------------------------
+struct FpGeom {
+    int n, S, pitch;     // pitch of one fibre in shared memory (doubles)
+};
+__host__ __device__ inline FpGeom fp_geom(int n) {
+    FpGeom q;
+    q.n = n;
+    q.S = (n + 31) / 32;
+    int len = n + (n + q.S - 1) / q.S + 1;
+    len = (len + 15) / 16 * 16 + 2;            // consecutive fibres start 2 banks (of 8 bytes) apart: transposed stores spread
+    q.pitch = len;
+    return q;
+}
+__host__ __device__ inline size_t fp_smem_bytes(int n, int F, bool aux) {
+    const FpGeom q = fp_geom(n);
+    const int narr = 1 + (aux ? 1 : 0) + (q.S > 16 ? 1 : 0);
+    return sizeof(double) * ((size_t)3 * q.pitch + (size_t)narr * F * q.pitch) + sizeof(i64) * F;
+}
+__device__ __forceinline__ int fp_pidx(int i, int S) { return i + i / S; }
+
+__host__ __device__ inline bool fp_kind_has_aux(int kind) { return kind == FP_GA || kind == FP_GAONLY || kind == FP_DL; }
+
+// one warp, one fibre: X holds x_i on entry and y_i = (P x)_i on exit
+__device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restrict__ pd, const double* __restrict__ ru,
+                                         const double* __restrict__ rl, double* __restrict__ X, double* __restrict__ U, int lane) {
+    const int S = q.S, n = q.n;
+    const int i0 = lane * S;
+    const int cnt = max(0, min(S, n - i0));
+    const int p0 = lane * (S + 1);
+    // phase 1: affine summaries of the lane's segment for both sweeps
+    double lA = 1.0, lB = 0.0, uA = 1.0, uB = 0.0;
+    for (int j = 0; j < cnt; ++j) {
+        const double r = rl[p0 + j];
+        const double s = pd[p0 + j] * X[p0 + j];
+        lB = fma(r, lB, r * s);
+        lA *= r;
+    }
+    for (int j = cnt - 1; j >= 0; --j) {
+        const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+        const double s = pd[p0 + j] * X[p0 + j];
+        uB = fma(r, uB, r * s);
+        uA *= r;
+    }
+    // inclusive scans of the affine maps across lanes (ascending for l, descending for u)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ap = __shfl_sync(0xffffffffu, lA, (lane - o) & 31), Bp = __shfl_sync(0xffffffffu, lB, (lane - o) & 31);
+        const double Aq = __shfl_sync(0xffffffffu, uA, (lane + o) & 31), Bq = __shfl_sync(0xffffffffu, uB, (lane + o) & 31);
+        if (lane >= o) { lB = fma(lA, Bp, lB); lA *= Ap; }
+        if (lane + o < 32) { uB = fma(uA, Bq, uB); uA *= Aq; }
+    }
+    double l = __shfl_sync(0xffffffffu, lB, (lane - 1) & 31);
+    double u = __shfl_sync(0xffffffffu, uB, (lane + 1) & 31);
+    if (lane == 0) l = 0.0;
+    if (lane == 31) u = 0.0;
+    // phase 2: the sweeps with their true carries
+    if (S <= 16) {
+        double uu[16];
+#pragma unroll
+        for (int j = 15; j >= 0; --j) {
+            if (j < cnt) {
+                uu[j] = u;
+                const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+                const double s = pd[p0 + j] * X[p0 + j];
+                u = fma(r, u, r * s);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < cnt) {
+                const double r = rl[p0 + j];
+                const double s = pd[p0 + j] * X[p0 + j];
+                X[p0 + j] = s + l + uu[j];
+                l = fma(r, l, r * s);
+            }
+        }
+    } else {
+        for (int j = cnt - 1; j >= 0; --j) {
+            U[p0 + j] = u;
+            const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+            const double s = pd[p0 + j] * X[p0 + j];
+            u = fma(r, u, r * s);
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const double r = rl[p0 + j];
+            const double s = pd[p0 + j] * X[p0 + j];
+            X[p0 + j] = s + l + U[p0 + j];
+            l = fma(r, l, r * s);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int tile);
+
+// acc[dl + 1][i] += sum over the fibres [f0, f1) of Y[f][i] * Cx[f - f0][i + dl]
+__device__ __forceinline__ void fp_band_dots(const FpGeom& q, const double* __restrict__ Y, const double* __restrict__ Cx,
+                                             int f0, int f1, double* __restrict__ acc) {
+    const int n = q.n, S = q.S;
+    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+        const int p = fp_pidx(i, S);
+        const int pm = (i > 0) ? fp_pidx(i - 1, S) : p, pp = (i + 1 < n) ? fp_pidx(i + 1, S) : p;
+        double am = 0.0, a0 = 0.0, ap = 0.0;
+        for (int f = f0; f < f1; ++f) {
+            const double y = Y[(size_t)f * q.pitch + p];
+            const double* c = Cx + (size_t)(f - f0) * q.pitch;
+            am = fma(y, c[pm], am);
+            a0 = fma(y, c[p], a0);
+            ap = fma(y, c[pp], ap);
+        }
+        if (i > 0) atomicAdd(acc + i, am);
+        atomicAdd(acc + n + i, a0);
+        if (i + 1 < n) atomicAdd(acc + 2 * n + i, ap);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant__ FpPass P) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[32];
+    // which task does this tile belong to
+    int ti = 0;
+    while (ti + 1 < P.ntasks && (int)blockIdx.x >= P.t[ti + 1].tile0) ++ti;
+    const FpTask& tk = P.t[ti];
+    const int tile = (int)blockIdx.x - tk.tile0;
+    if (tile >= tk.ntiles) return;
+    if (tk.kind == FP_QROW) { fp_qrow<T>(P, tk, tile); return; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = tk.n, d = tk.d, F = tk.F;
+    const FpGeom q = fp_geom(n);
+    const int S = q.S;
+    double* pd = reinterpret_cast<double*>(smraw);
+    double* ru = pd + q.pitch;
+    double* rl = ru + q.pitch;
+    double* X = rl + q.pitch;
+    const bool aux = fp_kind_has_aux(tk.kind);
+    double* Cx = X + (size_t)F * q.pitch;                               // valid only if aux
+    double* U = X + (size_t)(aux ? 2 : 1) * F * q.pitch;                // valid only if S > 16
+    i64* fbase = reinterpret_cast<i64*>(X + (size_t)((aux ? 2 : 1) + (S > 16 ? 1 : 0)) * F * q.pitch);
+    // ---- generators of dimension d
+    {
+        const double* __restrict__ gen = P.gen[d];
+        for (int i = tid; i < n; i += FP_THREADS) {
+            const int p = fp_pidx(i, S);
+            pd[p] = gen[i]; ru[p] = gen[n + i]; rl[p] = gen[2 * n + i];
+        }
+    }
+    // ---- source fibres of this tile: GA carries g and ghat of the same F / 2 source fibres
+    const int nsrc = (tk.kind == FP_GA) ? F / 2 : F;
+    const i64 fib0 = (i64)tile * nsrc;
+    const int nf = (int)min((i64)nsrc, tk.nfib - fib0);                 // source fibres present in this tile
+    if (tid < nsrc) {
+        const i64 f = fib0 + tid;
+        const i64 o = f / tk.inner, r = f - o * tk.inner;
+        fbase[tid] = o * (i64)n * tk.inner + r;
+    }
+    __syncthreads();
+    const double noise = P.theta[2 * P.D];
+    const double cg = P.ell_scale / noise;
+    const double cP = P.ell_scale / (2.0 * noise), cQ = -P.ell_scale / (2.0 * noise);
+    const bool contiguous = (tk.inner == 1);
+    // element-parallel loop over (fibre, element): for strided modes consecutive threads take consecutive fibres of one
+    // element index (they are adjacent in memory), for the contiguous mode consecutive elements of one fibre
+    const int total = nsrc * n;
+    switch (tk.kind) {
+        case FP_R: {
+            const double* __restrict__ L = tk.s0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int i = e / nsrc, f = e - i * nsrc;
+                const i64 k = fib0 + f;
+                X[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0;
+            }
+        } break;
+        case FP_PROD: case FP_ALPHA: case FP_DM: case FP_Z: {
+            const double* __restrict__ src = tk.s0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                int i, f;
+                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+                X[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0;
+            }
+        } break;
+        case FP_GA: case FP_GAONLY: {
+            const T* __restrict__ ga = reinterpret_cast<const T*>(tk.t0);
+            const double* __restrict__ m = tk.s0;
+            const double* __restrict__ al = tk.s1;
+            const bool both = (tk.kind == FP_GA);
+            for (int e = tid; e < total; e += FP_THREADS) {
+                int i, f;
+                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+                const int p = fp_pidx(i, S);
+                double gv = 0.0, hv = 0.0, av = 0.0;
+                if (f < nf) {
+                    const i64 a = fbase[f] + (i64)i * tk.inner;
+                    gv = cg * (double)ga[a];
+                    hv = gv - 0.5 * m[a];
+                    av = al[a];
+                }
+                if (both) {
+                    X[(size_t)f * q.pitch + p] = gv;
+                    X[(size_t)(nsrc + f) * q.pitch + p] = hv;
+                } else {
+                    X[(size_t)f * q.pitch + p] = hv;
+                }
+                Cx[(size_t)f * q.pitch + p] = av;
+            }
+        } break;
+        case FP_YP: {
+            // row k of X_d = cP tridiag(bp_diag, bp_off)
+            const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int f = e / n, i = e - f * n;
+                const int k = (int)(fib0 + f);
+                double v = 0.0;
+                if (f < nf) {
+                    if (i == k) v = cP * (double)bnd[k];
+                    else if (i == k - 1) v = cP * (double)bnd[n + i];
+                    else if (i == k + 1) v = cP * (double)bnd[n + k];
+                }
+                X[(size_t)f * q.pitch + fp_pidx(i, S)] = v;
+            }
+        } break;
+        case FP_DL: {
+            // column k of R_d -> Cx; then column k of dR_d = 2 cQ tridiag(bq_diag, bq_off) R_d -> X
+            const double* __restrict__ R = tk.s0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int i = e / nsrc, f = e - i * nsrc;
+                Cx[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0;
+            }
+            __syncthreads();
+            const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int f = e / n, i = e - f * n;
+                const double* c = Cx + (size_t)f * q.pitch;
+                double r = (double)bnd[2 * n + i] * c[fp_pidx(i, S)];
+                if (i > 0) r = fma((double)bnd[3 * n + i - 1], c[fp_pidx(i - 1, S)], r);
+                if (i + 1 < n) r = fma((double)bnd[3 * n + i], c[fp_pidx(i + 1, S)], r);
+                X[(size_t)f * q.pitch + fp_pidx(i, S)] = 2.0 * cQ * r;
+            }
+        } break;
+        default: break;
+    }
+    __syncthreads();
+    // ---- recurrences: one warp per fibre
+    for (int f = warp; f < F; f += FP_WARPS)
+        fp_fibre(q, pd, ru, rl, X + (size_t)f * q.pitch, U + (size_t)f * q.pitch, lane);
+    __syncthreads();
+    // ---- epilogues
+    switch (tk.kind) {
+        case FP_R: {
+            double* __restrict__ R = tk.o0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int i = e / nsrc, f = e - i * nsrc;
+                if (f < nf) R[(i64)i * n + (fib0 + f)] = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+            }
+        } break;
+        case FP_PROD: case FP_DM: case FP_ALPHA: {
+            double* __restrict__ dst = tk.o0;
+            const double* __restrict__ al = tk.s1;
+            T* __restrict__ aT = reinterpret_cast<T*>(tk.t1);
+            double dot = 0.0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                int i, f;
+                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+                if (f >= nf) continue;
+                const i64 a = fbase[f] + (i64)i * tk.inner;
+                const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                if (tk.kind == FP_DM) {
+                    dst[a] = y - al[a];
+                } else {
+                    dst[a] = y;
+                    if (tk.kind == FP_ALPHA) {
+                        aT[a] = (T)y;
+                        dot = fma(y, al[a], dot);            // s1 = m for this kind
+                    }
+                }
+            }
+            if (tk.kind == FP_ALPHA) {
+                dot = block_sum(dot, red);
+                if (tid == 0) atomicAdd(P.sc + SC_MALPHA, dot);
+            }
+        } break;
+        case FP_GA: {
+            double* __restrict__ dst = tk.o0;
+            const double* __restrict__ al = tk.s1;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                int i, f;
+                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+                if (f >= nf) continue;
+                const i64 a = fbase[f] + (i64)i * tk.inner;
+                const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                dst[a] = tk.direct ? y - al[a] : y;
+            }
+            fp_band_dots(q, X, Cx, nsrc, nsrc + nf, P.acc[d]);
+        } break;
+        case FP_GAONLY:
+            fp_band_dots(q, X, Cx, 0, nf, P.acc[d]);
+            break;
+        case FP_YP: {
+            double* __restrict__ Y = tk.o0;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int f = e / n, i = e - f * n;
+                if (f < nf) Y[(fib0 + f) * (i64)n + i] = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+            }
+        } break;
+        case FP_DL: {
+            double* __restrict__ dL = tk.o0;
+            const double* __restrict__ L = tk.s1;
+            double trO = 1.0;
+            for (int e2 = 0; e2 < P.D; ++e2)
+                if (e2 != d) trO *= P.sc[SC_TR + e2];
+            const double ratio = (double)P.M / (double)n;
+            for (int e = tid; e < total; e += FP_THREADS) {
+                const int i = e / nsrc, f = e - i * nsrc;
+                if (f >= nf) continue;
+                const i64 k = fib0 + f;
+                const int p = fp_pidx(i, S);
+                double v = 0.0;
+                if ((i64)i >= k) {
+                    v = X[(size_t)f * q.pitch + p] - trO * Cx[(size_t)f * q.pitch + p];
+                    if ((i64)i == k) v += ratio / L[(i64)i * n + k];
+                }
+                dL[(i64)i * n + k] = v;
+            }
+            fp_band_dots(q, X, Cx, 0, nf, P.acc[d]);
+        } break;
+        case FP_Z: {
+            // column j of Z_d: only Z[j - 1 .. j + 1][j] is needed
+            double* __restrict__ acc = P.acc[d];
+            for (int e = tid; e < 3 * nf; e += FP_THREADS) {
+                const int f = e / 3, dl = e - f * 3 - 1;
+                const int j = (int)(fib0 + f);
+                const int i = j + dl;
+                if (i < 0 || i >= n) continue;
+                // W[i][j] with j = i - dl: slot (-dl + 1, i)
+                atomicAdd(acc + (1 - dl) * n + i, X[(size_t)f * q.pitch + fp_pidx(i, S)]);
+            }
+        } break;
+        default: break;
+    }
+}
+
+// Row reductions of R_d: one warp per row i (tile = 8 rows).  tk.s0 = R_d, tk.s1 = L_d.
+template <typename T>
+__device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int tile) {
+    const int d = tk.d, n = tk.n;
+    const int lane = threadIdx.x & 31;
+    const int i = tile * FP_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const double* __restrict__ R = tk.s0;
+    const double* __restrict__ L = tk.s1;
+    const bool last = (i + 1 >= n);
+    const double* Ri = R + (i64)i * n;
+    const double* Rn = R + (i64)(last ? i : i + 1) * n;
+    const double* Li = L + (i64)i * n;
+    double qd = 0.0, qo = 0.0, qn = 0.0, tr = 0.0;
+#pragma unroll 4
+    for (int k = lane; k < n; k += 32) {
+        const double r = Ri[k], rn = Rn[k];
+        qd = fma(r, r, qd);
+        qo = fma(r, rn, qo);
+        qn = fma(rn, rn, qn);
+        if (k <= i) tr = fma(r, Li[k], tr);
+    }
+    qd = warp_sum(qd); qo = warp_sum(qo); qn = warp_sum(qn); tr = warp_sum(tr);
+    if (lane == 0) {
+        if (last) { qo = 0.0; qn = 0.0; }
+        P.Qb[d][i] = qd;
+        P.Qb[d][n + i] = qo;
+        T* tab = reinterpret_cast<T*>(P.bandT) + P.tab_off[d];
+        const double B2 = 2.0 * qo;
+        tab[3 * n + i] = (T)qd; tab[4 * n + i] = (T)(B2 - 2.0 * qd); tab[5 * n + i] = (T)(qd - B2 + qn);
+        atomicAdd(P.sc + SC_TR + d, tr);
+        atomicAdd(P.sc + SC_LOGDETS + d, 2.0 * log(fabs(Li[i])));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// d theta and the ELBO scalars from the band accumulators:
+//   dK_d[i][j] = -W_d[i][j] + (c_d / 2) Q_d[i][j] - (M / (2 M_d)) P_d[i][j]   on |i - j| <= 1   (K_d and dK_d / d theta are tridiagonal)
+// grid (D), 256 threads.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+                                                  const double* __restrict__ acc, const double* __restrict__ gscal,
+                                                  double ell_scale, double* __restrict__ out, double* __restrict__ dtheta) {
+    __shared__ double red[32];
+    const int d = blockIdx.x;
+    const int n = g.n[d];
+    const int D = g.D;
+    const double half_ratio = 0.5 * (double)g.M / (double)n;
+    const double half_c = 0.5 * tr_others(g, d);
+    const double* __restrict__ gen = g.gen[d];
+    for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
+    double sl = 0.0, ss = 0.0;
+    for (int e = threadIdx.x; e < 3 * n; e += 256) {
+        const int dl = e / n - 1, i = e - (dl + 1) * n;
+        const int j = i + dl;
+        if (j < 0 || j >= n) continue;
+        const double qv = (i == j) ? g.Qb[d][i] : g.Qb[d][n + (i < j ? i : j)];
+        const double pij = b1_P_band(gen, n, i, j);
+        const double v = -acc[e] + half_c * qv - half_ratio * pij;
+        double a, b;
+        factor_entry_grad(g, theta, d, i, j, a, b);
+        sl = fma(v, a, sl);
+        ss = fma(v, b, ss);
+    }
+    sl = block_sum(sl, red);
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+        const double noise = theta[2 * D];
+        double kff = 1.0;
+        for (int e = 0; e < D; ++e) kff *= theta[D + e];
+        const double E = gscal[0], nobs = gscal[1];
+        const double dkff = -ell_scale * nobs / (2.0 * noise);
+        dtheta[d] = sl;
+        dtheta[D + d] = ss + dkff * kff / theta[D + d];
+        if (d == 0) {
+            const double tot = E + nobs * kff;
+            const double ell = -0.5 * nobs * log(2.0 * 3.14159265358979323846 * noise) - tot / (2.0 * noise);
+            dtheta[2 * D] = ell_scale * (-nobs / (2.0 * noise) + tot / (2.0 * noise * noise));
+            double trp = 1.0, lds = 0.0;
+            for (int e = 0; e < D; ++e) {
+                trp *= g.sc[SC_TR + e];
+                lds += ((double)g.M / (double)g.n[e]) * (g.sc[SC_LOGDETK + e] - g.sc[SC_LOGDETS + e]);
+            }
+            const double kl = 0.5 * (trp + g.sc[SC_MALPHA] - (double)g.M + lds);
+            out[0] = ell_scale * ell - kl;
+            out[1] = ell_scale * ell;
+            out[2] = kl;
+            out[3] = nobs;
+        }
+    }
+}
+
+// K_d as a dense matrix, on demand (vggp_workspace_ptr): the fused path never materialises it in a step.
+// grid (ceil(nmax^2 / 256), D)
+__global__ void __launch_bounds__(256) k_b1_fill_Kraw(const __grid_constant__ GridDims g, const double* __restrict__ theta) {
+    const int d = blockIdx.y;
+    const int n = g.n[d];
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (i64)n * n) return;
+    g.Kraw[d][e] = factor_entry(g, theta, d, (int)(e / n), (int)(e % n));
+}
+
+}  // namespace vggp

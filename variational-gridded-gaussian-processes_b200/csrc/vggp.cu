@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "grid.cuh"
+#include "grid_b1.cuh"
 #include "obs.cuh"
 #include "obs_binned.cuh"
 #include "metrics.cuh"
@@ -19,7 +20,8 @@ thread_local char g_err[512] = {0};
 unsigned long long g_launches = 0;
 static int g_use_mma = 1;
 static int g_bin_stream = 0;       // binned K1: 0 = LDG.128 register ping-pong, 1 = TMA ring through shared memory
-static int g_b1_structured = 2;    // B1 family: 0 dense, 1 twisted inverse + GEMMs, 2 + semiseparable products
+static int g_b1_structured = 3;    // B1 family: 0 dense, 1 twisted inverse + GEMMs, 2 + semiseparable products (round 1),
+                                   // 3 (default) fused fibre passes (grid_b1.cuh)
 
 constexpr int BAND_REPLICAS = 128;
 
@@ -76,6 +78,8 @@ struct vggp_plan {
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // optional device timing of the per-observation kernel (vggp_k1_timing)
     bool k1_timing = false; std::vector<cudaEvent_t> k1_ev; int k1_count = 0;
+    double* b1_acc = nullptr; int b1_acc_total = 0;      // structured == 3: band accumulators of dK_d, [3][n_d] per dimension
+    cudaStream_t last_stream = nullptr;                  // stream of the last grid forward (on-demand workspace fills)
     void* band_rep = nullptr;              // B1 family, binned kernel: BAND_REPLICAS copies of the band block (obs dtype), kept zero
                                            // between launches (k_band_reduce clears what it sums)
     // schedules
@@ -468,6 +472,189 @@ int build_schedules(vggp_plan* p) {
         p->ss_Z.ntasks = 0;
         if (D == 1) p->ss_Z.t[p->ss_Z.ntasks++] = ss_task(g.gen[0], p->n[0], p->n[0], 1, g.Y[0], g.dK[0]);
     }
+    return 0;
+}
+
+
+// ---- fused B1 grid side (grid_b1.cuh) -------------------------------------------------------------------
+int g_fp_smem_hwm[2] = {0, 0};      // high-water mark of the dynamic shared memory opted in for k_fibre_pass<float / double>
+
+int fp_tile_F(int n, int want) {
+    int F = want;
+    while (F > 2 && fp_smem_bytes(n, F, true) > (size_t)200 * 1024) F >>= 1;
+    return F;
+}
+
+FpTask fp_task(const vggp_plan* p, int kind, int d, i64 outer, i64 inner) {
+    FpTask t;
+    memset(&t, 0, sizeof(t));
+    t.kind = kind; t.d = d; t.n = p->n[d];
+    t.inner = inner; t.nfib = outer * inner;
+    t.F = fp_tile_F(t.n, 8);
+    if (kind == FP_QROW) {
+        t.ntiles = (t.n + FP_WARPS - 1) / FP_WARPS;
+    } else {
+        const int nsrc = (kind == FP_GA) ? t.F / 2 : t.F;
+        t.ntiles = (int)((t.nfib + nsrc - 1) / nsrc);
+    }
+    return t;
+}
+
+FpTask fp_mode_task(const vggp_plan* p, int kind, int e) {
+    i64 outer = 1, inner = 1;
+    for (int f = 0; f < e; ++f) outer *= p->n[f];
+    for (int f = e + 1; f < p->D; ++f) inner *= p->n[f];
+    return fp_task(p, kind, e, outer, inner);
+}
+
+void fp_pass_init(const vggp_plan* p, FpPass& P, const double* theta, double ell_scale) {
+    memset(&P, 0, sizeof(P));
+    P.D = p->D; P.obs_f32 = p->obs_dtype == VGGP_F32; P.M = p->M;
+    P.ell_scale = ell_scale; P.theta = theta;
+    int off = 0;
+    for (int d = 0; d < p->D; ++d) {
+        P.gen[d] = p->g.gen[d];
+        P.acc[d] = p->b1_acc + off;
+        off += 3 * p->n[d];
+        P.Qb[d] = p->g.Qb[d];
+        P.tab_off[d] = p->tab_off[d];
+    }
+    P.sc = p->g.sc;
+    P.bandT = p->tables;
+}
+
+int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
+    if (P.ntasks == 0) return 0;
+    int tiles = 0;
+    size_t smem = 0;
+    for (int i = 0; i < P.ntasks; ++i) {
+        P.t[i].tile0 = tiles;
+        tiles += P.t[i].ntiles;
+        if (P.t[i].kind != FP_QROW)
+            smem = std::max(smem, fp_smem_bytes(P.t[i].n, P.t[i].F, fp_kind_has_aux(P.t[i].kind)));
+    }
+    const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
+    if ((int)smem > g_fp_smem_hwm[ti]) {      // the attribute is per function and process-wide: only ever raise it
+        if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_fp_smem_hwm[ti] = (int)smem;
+    }
+    if (ti == 0) k_fibre_pass<float><<<tiles, FP_THREADS, smem, st>>>(P);
+    else k_fibre_pass<double><<<tiles, FP_THREADS, smem, st>>>(P);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
+int b1f_forward(vggp_plan* p, const double* theta, const double* m, const double* L, cudaStream_t st) {
+    const int D = p->D;
+    int rc;
+    const size_t gsm = 4 * (size_t)p->nmax * sizeof(double);
+    if (p->obs_dtype == VGGP_F32) k_b1_gens<float><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total);
+    else k_b1_gens<double><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total);
+    VGGP_LAUNCH_CHECK();
+    VGGP_CUDA(cudaMemcpyAsync(p->theta_dev, theta, sizeof(double) * (2 * D + 1), cudaMemcpyDeviceToDevice, st));
+    FpPass P;
+    auto qrows = [&](FpPass& Q) {
+        for (int d = 0; d < D; ++d) {
+            FpTask t = fp_task(p, FP_QROW, d, 1, p->n[d]);
+            t.s0 = p->g.R[d]; t.s1 = L + p->g.Loff[d];
+            Q.t[Q.ntasks++] = t;
+        }
+    };
+    // pass 1: R_d = P_d tril(L_d) for every d, and the first mode of alpha = (kron P) m
+    fp_pass_init(p, P, theta, 1.0);
+    for (int d = 0; d < D; ++d) {
+        FpTask t = fp_task(p, FP_R, d, 1, p->n[d]);
+        t.s0 = L + p->g.Loff[d]; t.o0 = p->g.R[d];
+        P.t[P.ntasks++] = t;
+    }
+    {
+        FpTask t = fp_mode_task(p, D == 1 ? FP_ALPHA : FP_PROD, 0);
+        t.s0 = m; t.s1 = m;
+        t.o0 = D == 1 ? p->alpha : p->pgA;
+        t.t1 = p->alphaT;
+        P.t[P.ntasks++] = t;
+    }
+    if ((rc = fp_launch(p, P, st))) return rc;
+    const double* src = p->pgA;
+    if (D == 3) {     // middle mode, with the row reductions of R_d riding along
+        fp_pass_init(p, P, theta, 1.0);
+        FpTask t = fp_mode_task(p, FP_PROD, 1);
+        t.s0 = p->pgA; t.o0 = p->pgB;
+        P.t[P.ntasks++] = t;
+        qrows(P);
+        if ((rc = fp_launch(p, P, st))) return rc;
+        src = p->pgB;
+    }
+    // last pass: last mode of alpha (+ cast, <m, alpha>) and the row reductions of R_d
+    fp_pass_init(p, P, theta, 1.0);
+    if (D >= 2) {
+        FpTask t = fp_mode_task(p, FP_ALPHA, D - 1);
+        t.s0 = src; t.s1 = m; t.o0 = p->alpha; t.t1 = p->alphaT;
+        P.t[P.ntasks++] = t;
+    }
+    if (D != 3) qrows(P);
+    return fp_launch(p, P, st);
+}
+
+int b1f_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf, double ell_scale,
+                 double* out, double* dtheta, double* dm, double* dL, cudaStream_t st) {
+    const int D = p->D;
+    int rc;
+    const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    const unsigned char* gb = reinterpret_cast<const unsigned char*>(gbuf);
+    const double* gscal = reinterpret_cast<const double*>(gb + soff);
+    auto band = [&](int d) { return (const void*)(gb + ((size_t)p->M + p->band_off[d]) * tsz); };
+    FpPass P;
+    // pass 1 (last mode): V = g x P, A = ghat x P contracted with alpha; Y'_d = X_d P_d
+    fp_pass_init(p, P, theta, ell_scale);
+    {
+        FpTask t = fp_mode_task(p, FP_GA, D - 1);
+        t.s0 = m; t.s1 = p->alpha; t.t0 = gbuf;
+        t.direct = (D == 1);
+        t.o0 = D == 1 ? dm : p->pgA;
+        P.t[P.ntasks++] = t;
+    }
+    for (int d = 0; d < D; ++d) {
+        FpTask t = fp_task(p, FP_YP, d, p->n[d], 1);
+        t.t0 = band(d); t.o0 = p->g.Y[d];
+        P.t[P.ntasks++] = t;
+    }
+    if ((rc = fp_launch(p, P, st))) return rc;
+    // pass 2: next mode of the dm chain, its A_e contraction, dL_d and the band of P_d X_d P_d
+    fp_pass_init(p, P, theta, ell_scale);
+    if (D >= 2) {
+        const int e = D - 2;
+        FpTask t = fp_mode_task(p, e == 0 ? FP_DM : FP_PROD, e);
+        t.s0 = p->pgA; t.s1 = p->alpha; t.o0 = e == 0 ? dm : p->pgB;
+        P.t[P.ntasks++] = t;
+        FpTask a = fp_mode_task(p, FP_GAONLY, e);
+        a.s0 = m; a.s1 = p->alpha; a.t0 = gbuf;
+        P.t[P.ntasks++] = a;
+    }
+    for (int d = 0; d < D; ++d) {
+        FpTask t = fp_task(p, FP_DL, d, 1, p->n[d]);
+        t.s0 = p->g.R[d]; t.s1 = L + p->g.Loff[d]; t.t0 = band(d); t.o0 = dL + p->g.Loff[d];
+        P.t[P.ntasks++] = t;
+        FpTask z = fp_task(p, FP_Z, d, 1, p->n[d]);
+        z.s0 = p->g.Y[d];
+        P.t[P.ntasks++] = z;
+    }
+    if ((rc = fp_launch(p, P, st))) return rc;
+    if (D == 3) {
+        fp_pass_init(p, P, theta, ell_scale);
+        FpTask t = fp_mode_task(p, FP_DM, 0);
+        t.s0 = p->pgB; t.s1 = p->alpha; t.o0 = dm;
+        P.t[P.ntasks++] = t;
+        FpTask a = fp_mode_task(p, FP_GAONLY, 0);
+        a.s0 = m; a.s1 = p->alpha; a.t0 = gbuf;
+        P.t[P.ntasks++] = a;
+        if ((rc = fp_launch(p, P, st))) return rc;
+    }
+    k_b1_theta<<<D, 256, 0, st>>>(p->g, theta, p->b1_acc, gscal, ell_scale, out, dtheta);
+    VGGP_LAUNCH_CHECK();
     return 0;
 }
 
@@ -1268,7 +1455,7 @@ int vggp_set_binned_stream(int mode) {
 }
 
 int vggp_set_b1_structured(int on) {
-    g_b1_structured = on < 0 ? 0 : (on > 2 ? 2 : on);
+    g_b1_structured = on < 0 ? 0 : (on > 3 ? 3 : on);
     return 0;
 }
 
@@ -1395,6 +1582,10 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->alphaT = a;
     }
     if (family == VGGP_B1_ASVGP) {
+        int acc_total = 0;
+        for (int d = 0; d < D; ++d) acc_total += 3 * p->n[d];
+        p->b1_acc_total = acc_total;
+        TRY(dev_alloc(p, &p->b1_acc, acc_total));
         unsigned char* br = nullptr;
         TRY(dev_alloc(p, &br, (i64)BAND_REPLICAS * p->band_total * (i64)tsz));
         p->band_rep = br;
@@ -1477,6 +1668,8 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->D;
     int rc;
+    p->last_stream = st;
+    if (p->g.structured == 3) return b1f_forward(p, theta, m, L, st);
     VGGP_CUDA(cudaMemcpyAsync(p->mws, m, sizeof(double) * p->M, cudaMemcpyDeviceToDevice, st));
     VGGP_CUDA(cudaMemcpyAsync(p->theta_dev, theta, sizeof(double) * (2 * D + 1), cudaMemcpyDeviceToDevice, st));
     const i64 nn = (i64)p->nmax * p->nmax;
@@ -1659,10 +1852,10 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
 int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,
                        double ell_scale, double* out, double* dtheta, double* dm, double* dL, void* stream) {
     if (!p || !theta || !m || !L || !gbuf || !out || !dtheta || !dm || !dL) return fail(VGGP_E_ARG, "null argument");
-    (void)L;
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->D;
     int rc;
+    if (p->g.structured == 3) return b1f_backward(p, theta, m, L, gbuf, ell_scale, out, dtheta, dm, dL, st);
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     const double* gscal = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(gbuf) + soff);
@@ -1929,16 +2122,20 @@ int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int
     switch (which) {
         case VGGP_WS_K: *ptr = p->g.Kc[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_P:
-            if (p->g.structured == 2) {      // not materialised in a step: fill it now (synchronous, debugging / tests only)
-                k_b1_fill_P<<<dim3(ceil_div(p->nmax, 256), p->D), 256>>>(p->g);
+            if (p->g.structured >= 2) {      // not materialised in a step: filled now, ordered on the stream of the last forward
+                k_b1_fill_P<<<dim3(ceil_div(p->nmax, 256), p->D), 256, 0, p->last_stream>>>(p->g);
                 VGGP_LAUNCH_CHECK();
-                VGGP_CUDA(cudaDeviceSynchronize());
             }
             *ptr = p->g.P[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_R: *ptr = p->g.R[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_Q: *ptr = p->g.Q[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_S: return fail(VGGP_E_UNSUPPORTED, "S_d is no longer materialised");
-        case VGGP_WS_KRAW: *ptr = p->g.Kraw[dim]; if (n_elems) *n_elems = nn; return 0;
+        case VGGP_WS_KRAW:
+            if (p->g.structured == 3) {      // as VGGP_WS_P
+                k_b1_fill_Kraw<<<dim3(ceil_div((i64)p->nmax * p->nmax, 256), p->D), 256, 0, p->last_stream>>>(p->g, p->theta_dev);
+                VGGP_LAUNCH_CHECK();
+            }
+            *ptr = p->g.Kraw[dim]; if (n_elems) *n_elems = nn; return 0;
         case VGGP_WS_QBAND: *ptr = p->g.Qb[dim]; if (n_elems) *n_elems = 2 * (i64)p->n[dim]; return 0;
         case VGGP_WS_ALPHA: *ptr = p->alpha; if (n_elems) *n_elems = p->M; return 0;
         case VGGP_WS_SCAL: *ptr = p->g.sc; if (n_elems) *n_elems = SC_COUNT; return 0;
