@@ -44,7 +44,7 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, tol, D, N, what="", ks=None):
+def _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, tol, D, N, what="", ks=None, dm_direct_tol=None):
     assert plan.read_info() == 0
     assert out[3].item() == N
     assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item()), (what, out.cpu(), elbo_ref)
@@ -57,7 +57,7 @@ def _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, tol, D, N, what="", ks=No
         # gradient amplifies the lowest modes of alpha by ~1e6, and two float64 algorithms (dense Cholesky inverse, twisted
         # factorisation) each sit 1e-4 from a long-double evaluation at the configs[2] point (DESIGN.md section 2,
         # tools/conditioning_dm.py).  The whitened gradient (kron K) dm removes that amplification and must meet `tol`.
-        assert ks is not None and err_dm < 10 * tol, (what, "dm", err_dm)
+        assert ks is not None and err_dm < (10 * tol if dm_direct_tol is None else dm_direct_tol), (what, "dm", err_dm)
         def whiten(v):
             t = v.detach().cpu().to(torch.float64).reshape(plan.m_per_dim)
             for d_, K_ in enumerate(ks):
@@ -216,9 +216,11 @@ def test_config2_tracks_512x512_fp32_b0_sample(vg, dev):
     plan = vg.GridPlan(vg.B0_GRIDDED, meshes, torch.float32, dev)
     theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
     Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev).contiguous()
+    # cond(K_d) ~ 1e4 ... 1e5 for the Toeplitz factor at 511 cells: d ELBO / d m is compared in whitened form (see _check)
+    ks = [O.kuu_factor(O.B0_GRIDDED, meshes[d], l[d], s2[d], ref_quirks=False).to(torch.float64) for d in range(2)]
     for name, obs, yy in _layouts(vg, plan, xs, y, O.B0_GRIDDED):
         out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, obs, yy)
-        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-3, 2, N, name)
+        _check(plan, out, dtheta, dm, dL, elbo_ref, g_ref, 1e-3, 2, N, name, ks=ks, dm_direct_tol=0.1)
 
 
 # ---- configs[3] shape at reduced size: 3-D (64, 64, 16) grid, 2^20 float32 observations ---------------------------------

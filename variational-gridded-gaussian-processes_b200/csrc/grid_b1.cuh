@@ -78,9 +78,9 @@ struct FpPass {
 // ---------------------------------------------------------------------------------------------------------
 struct Mob { double a, b, c, d; };     // x -> (a x + b) / (c x + d)
 
-__device__ __forceinline__ void mob_rescale(Mob& m) {
+__device__ __forceinline__ void mob_rescale(Mob& m, bool always = false) {
     const double mx = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
-    if (mx > 1e100 || mx < 1e-100) {
+    if (always || mx > 1e100 || mx < 1e-100) {
         int ex;
         frexp(mx, &ex);
         m.a = ldexp(m.a, -ex); m.b = ldexp(m.b, -ex); m.c = ldexp(m.c, -ex); m.d = ldexp(m.d, -ex);
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
                 mob_push(m, a[k], b[k - 1] * b[k - 1]);
                 if ((k & 7) == 7) mob_rescale(m);
             }
+            mob_rescale(m, true);          // entries in [0.5, 1): the serial chain below cannot overflow between its own rescalings
             comp_d[ch] = m;
         } else {
             // chunk covers k in [k0, k1) walked downwards; maps e_{k1} -> e_{k0}
@@ -140,48 +141,77 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
                 mob_push(m, a[k], b[k] * b[k]);
                 if ((k & 7) == 0) mob_rescale(m);
             }
+            mob_rescale(m, true);
             comp_e[ch] = m;
         }
     }
     __syncthreads();
+    // the carries are chained in homogeneous coordinates x = num / den (no division on the serial path; exact power-of-two
+    // rescaling), every chunk divides its own carry afterwards
     if (tid == 0) {
-        double x = a[0];                                   // d_0; chunk 0's composite starts from it
+        double num = a[0], den = 1.0;                      // d_0; chunk 0's composite starts from it
         for (int c = 0; c < nch; ++c) {
-            carry_d[c] = x;                                // value entering chunk c (d_{k0 - 1}; for c = 0: d_0 itself)
+            carry_d[c] = num; carry_d[GEN_THREADS / 2 + c] = den;    // value entering chunk c (d_{k0 - 1}; for c = 0: d_0 itself)
             const Mob m = comp_d[c];
-            x = (m.a * x + m.b) / (m.c * x + m.d);
+            const double nn = fma(m.a, num, m.b * den), dn = fma(m.c, num, m.d * den);
+            num = nn; den = dn;
+            if ((c & 3) == 3) {
+                int ex;
+                frexp(fmax(fabs(num), fabs(den)), &ex);
+                num = ldexp(num, -ex); den = ldexp(den, -ex);
+            }
         }
     } else if (tid == 32) {
-        double x = a[n - 1];                               // e_{n-1}
+        double num = a[n - 1], den = 1.0;                  // e_{n-1}
         for (int c = nch - 1; c >= 0; --c) {
-            carry_e[c] = x;                                // value entering chunk c from above (e_{k1}; top chunk: e_{n-1} itself)
+            carry_e[c] = num; carry_e[GEN_THREADS / 2 + c] = den;    // value entering chunk c from above (e_{k1}; top chunk: e_{n-1})
             const Mob m = comp_e[c];
-            x = (m.a * x + m.b) / (m.c * x + m.d);
+            const double nn = fma(m.a, num, m.b * den), dn = fma(m.c, num, m.d * den);
+            num = nn; den = dn;
+            if ((c & 3) == 0) {
+                int ex;
+                frexp(fmax(fabs(num), fabs(den)), &ex);
+                num = ldexp(num, -ex); den = ldexp(den, -ex);
+            }
         }
     }
     __syncthreads();
+    // plain recurrences inside the chunks.  1 / pivot is carried along by one Newton step from the previous reciprocal
+    // (the pivots change slowly) with an exact division whenever the residual is not at rounding level (round-1 scheme).
     if (ch < nch) {
         const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
         bool bad = false;
         if (!up) {
-            double prev = carry_d[ch];
+            double prev = carry_d[ch] / carry_d[GEN_THREADS / 2 + ch];
             int k = k0;
             if (ch == 0) { dd[0] = prev; bad = !(prev > 0.0); k = 1; }
+            double r = 1.0 / prev;
             for (; k < k1; ++k) {
                 const double bk = b[k - 1];
-                prev = a[k] - bk * bk / prev;
-                dd[k] = prev;
-                bad = bad || !(prev > 0.0);
+                const double nxt = fma(-bk * bk, r, a[k]);
+                dd[k] = nxt;
+                bad = bad || !(nxt > 0.0);
+                double e = fma(-nxt, r, 1.0);
+                double rn = fma(r, e, r);
+                e = fma(-nxt, rn, 1.0);
+                if (!(fabs(e) < 3e-16)) rn = 1.0 / nxt;
+                r = rn;
             }
         } else {
-            double nxt = carry_e[ch];
+            double nxt = carry_e[ch] / carry_e[GEN_THREADS / 2 + ch];
             int k = k1 - 1;
             if (k1 == n) { ee[n - 1] = nxt; k = n - 2; }
+            double r = 1.0 / nxt;
             for (; k >= k0; --k) {
                 const double bk = b[k];
-                nxt = a[k] - bk * bk / nxt;
-                ee[k] = nxt;
-                bad = bad || !(nxt > 0.0);
+                const double cur = fma(-bk * bk, r, a[k]);
+                ee[k] = cur;
+                bad = bad || !(cur > 0.0);
+                double e = fma(-cur, r, 1.0);
+                double rn = fma(r, e, r);
+                e = fma(-cur, rn, 1.0);
+                if (!(fabs(e) < 3e-16)) rn = 1.0 / cur;
+                r = rn;
             }
         }
         if (bad) bad_flag = 1;
@@ -312,6 +342,27 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
     }
 }
 
+
+// Element-parallel loop with U independent global loads in flight per thread before the first use: without it the
+// compiler issues one load per iteration and the warp waits for each (16 serialised L2 / HBM round trips per phase).
+template <int U, typename LoadF, typename StoreF>
+__device__ __forceinline__ void fp_batched(int total, LoadF ld, StoreF st) {
+    for (int e0 = threadIdx.x; e0 < total; e0 += U * FP_THREADS) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * FP_THREADS;
+            v[u] = (e < total) ? ld(e) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * FP_THREADS;
+            if (e < total) st(e, v[u]);
+        }
+    }
+}
+constexpr int FP_U = 8;
+
 template <typename T>
 __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int tile);
 
@@ -384,70 +435,78 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     // element-parallel loop over (fibre, element): for strided modes consecutive threads take consecutive fibres of one
     // element index (they are adjacent in memory), for the contiguous mode consecutive elements of one fibre
     const int total = nsrc * n;
+    auto split = [&](int e, int& i, int& f) {        // element index -> (element of the fibre, fibre of the tile)
+        if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+    };
     switch (tk.kind) {
         case FP_R: {
             const double* __restrict__ L = tk.s0;
-            for (int e = tid; e < total; e += FP_THREADS) {
-                const int i = e / nsrc, f = e - i * nsrc;
-                const i64 k = fib0 + f;
-                X[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0;
-            }
+            fp_batched<FP_U>(total,
+                [&](int e) { const int i = e / nsrc, f = e - i * nsrc; const i64 k = fib0 + f;
+                             return (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0; },
+                [&](int e, double v) { const int i = e / nsrc, f = e - i * nsrc; X[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
         } break;
         case FP_PROD: case FP_ALPHA: case FP_DM: case FP_Z: {
             const double* __restrict__ src = tk.s0;
-            for (int e = tid; e < total; e += FP_THREADS) {
-                int i, f;
-                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
-                X[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0;
-            }
+            fp_batched<FP_U>(total,
+                [&](int e) { int i, f; split(e, i, f); return (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0; },
+                [&](int e, double v) { int i, f; split(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
         } break;
         case FP_GA: case FP_GAONLY: {
             const T* __restrict__ ga = reinterpret_cast<const T*>(tk.t0);
             const double* __restrict__ m = tk.s0;
             const double* __restrict__ al = tk.s1;
             const bool both = (tk.kind == FP_GA);
-            for (int e = tid; e < total; e += FP_THREADS) {
-                int i, f;
-                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
-                const int p = fp_pidx(i, S);
-                double gv = 0.0, hv = 0.0, av = 0.0;
-                if (f < nf) {
-                    const i64 a = fbase[f] + (i64)i * tk.inner;
-                    gv = cg * (double)ga[a];
-                    hv = gv - 0.5 * m[a];
-                    av = al[a];
+            for (int e0 = tid; e0 < total; e0 += 4 * FP_THREADS) {
+                double gv[4], mv[4], av[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * FP_THREADS;
+                    gv[u] = mv[u] = av[u] = 0.0;
+                    if (e < total) {
+                        int i, f; split(e, i, f);
+                        if (f < nf) {
+                            const i64 a = fbase[f] + (i64)i * tk.inner;
+                            gv[u] = (double)ga[a]; mv[u] = m[a]; av[u] = al[a];
+                        }
+                    }
                 }
-                if (both) {
-                    X[(size_t)f * q.pitch + p] = gv;
-                    X[(size_t)(nsrc + f) * q.pitch + p] = hv;
-                } else {
-                    X[(size_t)f * q.pitch + p] = hv;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * FP_THREADS;
+                    if (e < total) {
+                        int i, f; split(e, i, f);
+                        const int p = fp_pidx(i, S);
+                        const double g1 = cg * gv[u], h1 = g1 - 0.5 * mv[u];
+                        if (both) {
+                            X[(size_t)f * q.pitch + p] = g1;
+                            X[(size_t)(nsrc + f) * q.pitch + p] = h1;
+                        } else {
+                            X[(size_t)f * q.pitch + p] = h1;
+                        }
+                        Cx[(size_t)f * q.pitch + p] = av[u];
+                    }
                 }
-                Cx[(size_t)f * q.pitch + p] = av;
             }
         } break;
         case FP_YP: {
-            // row k of X_d = cP tridiag(bp_diag, bp_off)
+            // row k of X_d = cP tridiag(bp_diag, bp_off): three non-zeros
             const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
-            for (int e = tid; e < total; e += FP_THREADS) {
-                const int f = e / n, i = e - f * n;
-                const int k = (int)(fib0 + f);
-                double v = 0.0;
-                if (f < nf) {
-                    if (i == k) v = cP * (double)bnd[k];
-                    else if (i == k - 1) v = cP * (double)bnd[n + i];
-                    else if (i == k + 1) v = cP * (double)bnd[n + k];
-                }
-                X[(size_t)f * q.pitch + fp_pidx(i, S)] = v;
+            for (int e = tid; e < total; e += FP_THREADS) X[(size_t)(e / n) * q.pitch + fp_pidx(e % n, S)] = 0.0;
+            __syncthreads();
+            if (tid < 3 * nf) {
+                const int f = tid / 3, dl = tid - 3 * f - 1;
+                const int k = (int)(fib0 + f), i = k + dl;
+                if (i >= 0 && i < n)
+                    X[(size_t)f * q.pitch + fp_pidx(i, S)] = cP * (double)(dl == 0 ? bnd[k] : bnd[n + (dl < 0 ? i : k)]);
             }
         } break;
         case FP_DL: {
             // column k of R_d -> Cx; then column k of dR_d = 2 cQ tridiag(bq_diag, bq_off) R_d -> X
             const double* __restrict__ R = tk.s0;
-            for (int e = tid; e < total; e += FP_THREADS) {
-                const int i = e / nsrc, f = e - i * nsrc;
-                Cx[(size_t)f * q.pitch + fp_pidx(i, S)] = (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0;
-            }
+            fp_batched<FP_U>(total,
+                [&](int e) { const int i = e / nsrc, f = e - i * nsrc; return (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0; },
+                [&](int e, double v) { const int i = e / nsrc, f = e - i * nsrc; Cx[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
             __syncthreads();
             const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
             for (int e = tid; e < total; e += FP_THREADS) {
@@ -477,26 +536,26 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         } break;
         case FP_PROD: case FP_DM: case FP_ALPHA: {
             double* __restrict__ dst = tk.o0;
-            const double* __restrict__ al = tk.s1;
+            const double* __restrict__ al = tk.s1;            // DM: alpha; ALPHA: m
             T* __restrict__ aT = reinterpret_cast<T*>(tk.t1);
             double dot = 0.0;
-            for (int e = tid; e < total; e += FP_THREADS) {
-                int i, f;
-                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
-                if (f >= nf) continue;
-                const i64 a = fbase[f] + (i64)i * tk.inner;
-                const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
-                if (tk.kind == FP_DM) {
-                    dst[a] = y - al[a];
-                } else {
-                    dst[a] = y;
-                    if (tk.kind == FP_ALPHA) {
-                        aT[a] = (T)y;
-                        dot = fma(y, al[a], dot);            // s1 = m for this kind
+            const int kind = tk.kind;
+            fp_batched<FP_U>(total,
+                [&](int e) { int i, f; split(e, i, f);
+                             return (kind != FP_PROD && f < nf) ? al[fbase[f] + (i64)i * tk.inner] : 0.0; },
+                [&](int e, double v) {
+                    int i, f; split(e, i, f);
+                    if (f >= nf) return;
+                    const i64 a = fbase[f] + (i64)i * tk.inner;
+                    const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                    if (kind == FP_DM) {
+                        dst[a] = y - v;
+                    } else {
+                        dst[a] = y;
+                        if (kind == FP_ALPHA) { aT[a] = (T)y; dot = fma(y, v, dot); }
                     }
-                }
-            }
-            if (tk.kind == FP_ALPHA) {
+                });
+            if (kind == FP_ALPHA) {
                 dot = block_sum(dot, red);
                 if (tid == 0) atomicAdd(P.sc + SC_MALPHA, dot);
             }
@@ -504,13 +563,14 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         case FP_GA: {
             double* __restrict__ dst = tk.o0;
             const double* __restrict__ al = tk.s1;
+            (void)al;
             for (int e = tid; e < total; e += FP_THREADS) {
-                int i, f;
-                if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
+                int i, f; split(e, i, f);
                 if (f >= nf) continue;
                 const i64 a = fbase[f] + (i64)i * tk.inner;
-                const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
-                dst[a] = tk.direct ? y - al[a] : y;
+                const int pp = fp_pidx(i, S);
+                const double y = X[(size_t)f * q.pitch + pp];
+                dst[a] = tk.direct ? y - Cx[(size_t)f * q.pitch + pp] : y;      // Cx holds alpha of these fibres
             }
             fp_band_dots(q, X, Cx, nsrc, nsrc + nf, P.acc[d]);
         } break;
@@ -575,7 +635,7 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
     const double* Rn = R + (i64)(last ? i : i + 1) * n;
     const double* Li = L + (i64)i * n;
     double qd = 0.0, qo = 0.0, qn = 0.0, tr = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = lane; k < n; k += 32) {
         const double r = Ri[k], rn = Rn[k];
         qd = fma(r, r, qd);
@@ -599,9 +659,9 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
 // ---------------------------------------------------------------------------------------------------------
 // d theta and the ELBO scalars from the band accumulators:
 //   dK_d[i][j] = -W_d[i][j] + (c_d / 2) Q_d[i][j] - (M / (2 M_d)) P_d[i][j]   on |i - j| <= 1   (K_d and dK_d / d theta are tridiagonal)
-// grid (D), 256 threads.
+// grid (D), 512 threads.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
+__global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
                                                   const double* __restrict__ acc, const double* __restrict__ gscal,
                                                   double ell_scale, double* __restrict__ out, double* __restrict__ dtheta) {
     __shared__ double red[32];
@@ -613,7 +673,8 @@ __global__ void __launch_bounds__(256) k_b1_theta(const __grid_constant__ GridDi
     const double* __restrict__ gen = g.gen[d];
     for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
     double sl = 0.0, ss = 0.0;
-    for (int e = threadIdx.x; e < 3 * n; e += 256) {
+#pragma unroll 2
+    for (int e = threadIdx.x; e < 3 * n; e += 512) {
         const int dl = e / n - 1, i = e - (dl + 1) * n;
         const int j = i + dl;
         if (j < 0 || j >= n) continue;

@@ -489,19 +489,33 @@ k_obs_b1_binned_tma(const __grid_constant__ BinnedArgs<T, D> a) {
 template <typename T, int D>
 constexpr size_t bin_tma_smem_bytes() { return (size_t)BIN_WARPS * BIN_STAGES * BIN_GPS * (D + 1) * 128 * sizeof(T); }
 
-// Sum of the band replicas -> the band block of gbuf (overwritten); the replicas are cleared for the next launch.
+// Sum of the band replicas -> the band block of gbuf (overwritten); the replicas and the work-stealing counter are cleared
+// for the next launch (both start zeroed at plan creation), so the per-observation call needs no memset of its own for them.
 // grid (ceil(n / 64)), 256 threads = 64 elements x 4 replica groups.
 template <typename T>
-__global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_rep, i64 stride, int n, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_rep, i64 stride, int n, T* __restrict__ out,
+                                                     unsigned int* __restrict__ counter) {
     __shared__ T part[4][64];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;      // the task counter of the kernel that just ran: ready for the next launch
     const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int e = (int)blockIdx.x * 64 + el;
     T acc = (T)0;
     if (e < n) {
-        for (int r = grp; r < n_rep; r += 4) {
-            T* q = rep + (i64)r * stride + e;
-            acc += *q;
-            *q = (T)0;
+        // all loads of a batch before the first store: the stores may alias the later loads as far as the compiler knows,
+        // and one load per iteration made this tiny kernel 32 serialised memory round trips long
+        for (int r0 = grp; r0 < n_rep; r0 += 4 * 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 4 * u;
+                v[u] = (r < n_rep) ? rep[(i64)r * stride + e] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 4 * u;
+                acc += v[u];
+                if (r < n_rep) rep[(i64)r * stride + e] = (T)0;
+            }
         }
     }
     part[grp][el] = acc;

@@ -653,7 +653,7 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         P.t[P.ntasks++] = a;
         if ((rc = fp_launch(p, P, st))) return rc;
     }
-    k_b1_theta<<<D, 256, 0, st>>>(p->g, theta, p->b1_acc, gscal, ell_scale, out, dtheta);
+    k_b1_theta<<<D, 512, 0, st>>>(p->g, theta, p->b1_acc, gscal, ell_scale, out, dtheta);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -1083,8 +1083,7 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
     a.n_real = (double)desc->n;
-    a.counter = p->obs_counter;
-    VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
+    a.counter = p->obs_counter + 1;              // slot 1: reset by k_band_reduce after every launch (slot 0: the other kernels)
     i64 blocks = (desc->n_tasks + BIN_WARPS - 1) / BIN_WARPS;
     blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[mode]));
     k1_mark(p, 0, st);
@@ -1092,7 +1091,7 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     else k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a);
     k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
-    k_band_reduce<T><<<ceil_div(p->band_total, 64), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M);
+    k_band_reduce<T><<<ceil_div(p->band_total, 64), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M, a.counter);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
