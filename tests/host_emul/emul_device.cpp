@@ -180,7 +180,7 @@ int run(int layout, const int* K, const float* knots, const void* const* xv, con
     if (n > 0) {
         if (layout == 3) cuda_emul::launch(dim3((unsigned)blocks), dim3(BIN_THREADS), [&] { k_obs_b1_binned_tma<T, D>(a); });
         else cuda_emul::launch(dim3((unsigned)blocks), dim3(BIN_THREADS), [&] { k_obs_b1_binned<T, D>(a); });
-        cuda_emul::launch(dim3((unsigned)((band_total + 63) / 64)), dim3(256),
+        cuda_emul::launch(dim3((unsigned)((band_total + 15) / 16)), dim3(256),
                           [&] { k_band_reduce<T>(rep.data(), 3, (int64_t)band_total, band_total, gb + M, &counter); });
         for (T v : rep) if (v != (T)0) return -7;      // the reduce kernel leaves the replicas cleared
     }

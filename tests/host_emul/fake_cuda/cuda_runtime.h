@@ -143,6 +143,8 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
+inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((uint64_t)a * (uint64_t)b) >> 32); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __float_as_int(float v) { int i; memcpy(&i, &v, 4); return i; }
 inline long long __double_as_longlong(double v) { long long i; memcpy(&i, &v, 8); return i; }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

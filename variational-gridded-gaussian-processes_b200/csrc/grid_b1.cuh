@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------
 struct FpGeom {
     int n, S, pitch;     // pitch of one fibre in shared memory (doubles)
+    unsigned magic;      // ceil(2^32 / S): i / S == umulhi(i, magic) for 0 <= i < 2^16
 };
 __host__ __device__ inline FpGeom fp_geom(int n) {
     FpGeom q;
@@ -261,6 +262,7 @@ __host__ __device__ inline FpGeom fp_geom(int n) {
     int len = n + (n + q.S - 1) / q.S + 1;
     len = (len + 15) / 16 * 16 + 2;            // consecutive fibres start 2 banks (of 8 bytes) apart: transposed stores spread
     q.pitch = len;
+    q.magic = (unsigned)((0x100000000ull + (unsigned long long)q.S - 1) / (unsigned long long)q.S);
     return q;
 }
 __host__ __device__ inline size_t fp_smem_bytes(int n, int F, bool aux) {
@@ -268,7 +270,8 @@ __host__ __device__ inline size_t fp_smem_bytes(int n, int F, bool aux) {
     const int narr = 1 + (aux ? 1 : 0) + (q.S > 16 ? 1 : 0);
     return sizeof(double) * ((size_t)3 * q.pitch + (size_t)narr * F * q.pitch) + sizeof(i64) * F;
 }
-__device__ __forceinline__ int fp_pidx(int i, int S) { return i + i / S; }
+// padded index; `SM` = FpGeom::magic (S == 1 gives magic 2^32, which does not fit: n <= 32 is handled by the S == 1 branch)
+__device__ __forceinline__ int fp_pidx(int i, unsigned SM) { return SM ? i + (int)__umulhi((unsigned)i, SM) : 2 * i; }
 
 __host__ __device__ inline bool fp_kind_has_aux(int kind) { return kind == FP_GA || kind == FP_GAONLY || kind == FP_DL; }
 
@@ -288,7 +291,7 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
         lA *= r;
     }
     for (int j = cnt - 1; j >= 0; --j) {
-        const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+        const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
         const double s = pd[p0 + j] * X[p0 + j];
         uB = fma(r, uB, r * s);
         uA *= r;
@@ -312,7 +315,7 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
         for (int j = 15; j >= 0; --j) {
             if (j < cnt) {
                 uu[j] = u;
-                const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+                const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
                 const double s = pd[p0 + j] * X[p0 + j];
                 u = fma(r, u, r * s);
             }
@@ -329,7 +332,7 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
     } else {
         for (int j = cnt - 1; j >= 0; --j) {
             U[p0 + j] = u;
-            const double r = (i0 + j > 0) ? ru[fp_pidx(i0 + j - 1, S)] : 0.0;
+            const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
             const double s = pd[p0 + j] * X[p0 + j];
             u = fma(r, u, r * s);
         }
@@ -369,10 +372,11 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
 // acc[dl + 1][i] += sum over the fibres [f0, f1) of Y[f][i] * Cx[f - f0][i + dl]
 __device__ __forceinline__ void fp_band_dots(const FpGeom& q, const double* __restrict__ Y, const double* __restrict__ Cx,
                                              int f0, int f1, double* __restrict__ acc) {
-    const int n = q.n, S = q.S;
+    const int n = q.n;
+    const unsigned SM = q.magic;
     for (int i = threadIdx.x; i < n; i += FP_THREADS) {
-        const int p = fp_pidx(i, S);
-        const int pm = (i > 0) ? fp_pidx(i - 1, S) : p, pp = (i + 1 < n) ? fp_pidx(i + 1, S) : p;
+        const int p = fp_pidx(i, SM);
+        const int pm = (i > 0) ? fp_pidx(i - 1, SM) : p, pp = (i + 1 < n) ? fp_pidx(i + 1, SM) : p;
         double am = 0.0, a0 = 0.0, ap = 0.0;
         for (int f = f0; f < f1; ++f) {
             const double y = Y[(size_t)f * q.pitch + p];
@@ -402,6 +406,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     const int n = tk.n, d = tk.d, F = tk.F;
     const FpGeom q = fp_geom(n);
     const int S = q.S;
+    const unsigned SM = q.magic;
     double* pd = reinterpret_cast<double*>(smraw);
     double* ru = pd + q.pitch;
     double* rl = ru + q.pitch;
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     {
         const double* __restrict__ gen = P.gen[d];
         for (int i = tid; i < n; i += FP_THREADS) {
-            const int p = fp_pidx(i, S);
+            const int p = fp_pidx(i, SM);
             pd[p] = gen[i]; ru[p] = gen[n + i]; rl[p] = gen[2 * n + i];
         }
     }
@@ -435,22 +440,26 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     // element-parallel loop over (fibre, element): for strided modes consecutive threads take consecutive fibres of one
     // element index (they are adjacent in memory), for the contiguous mode consecutive elements of one fibre
     const int total = nsrc * n;
-    auto split = [&](int e, int& i, int& f) {        // element index -> (element of the fibre, fibre of the tile)
-        if (contiguous) { f = e / n; i = e - f * n; } else { i = e / nsrc; f = e - i * nsrc; }
-    };
+    // element index of the tile -> (element of the fibre, fibre of the tile) without integer divisions: nsrc is a power of
+    // two, e / n goes through a multiply-high (e < 2^16)
+    const int nsrc_sh = 31 - __clz(nsrc);
+    const unsigned n_magic = (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n);
+    auto split_s = [&](int e, int& i, int& f) { i = e >> nsrc_sh; f = e & (nsrc - 1); };                 // strided modes
+    auto split_c = [&](int e, int& i, int& f) { f = (int)__umulhi((unsigned)e, n_magic); i = e - f * n; };  // contiguous mode
+    auto split = [&](int e, int& i, int& f) { if (contiguous) split_c(e, i, f); else split_s(e, i, f); };
     switch (tk.kind) {
         case FP_R: {
             const double* __restrict__ L = tk.s0;
             fp_batched<FP_U>(total,
-                [&](int e) { const int i = e / nsrc, f = e - i * nsrc; const i64 k = fib0 + f;
+                [&](int e) { int i, f; split_s(e, i, f); const i64 k = fib0 + f;
                              return (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0; },
-                [&](int e, double v) { const int i = e / nsrc, f = e - i * nsrc; X[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
+                [&](int e, double v) { int i, f; split_s(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
         } break;
         case FP_PROD: case FP_ALPHA: case FP_DM: case FP_Z: {
             const double* __restrict__ src = tk.s0;
             fp_batched<FP_U>(total,
                 [&](int e) { int i, f; split(e, i, f); return (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0; },
-                [&](int e, double v) { int i, f; split(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
+                [&](int e, double v) { int i, f; split(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
         } break;
         case FP_GA: case FP_GAONLY: {
             const T* __restrict__ ga = reinterpret_cast<const T*>(tk.t0);
@@ -476,7 +485,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                     const int e = e0 + u * FP_THREADS;
                     if (e < total) {
                         int i, f; split(e, i, f);
-                        const int p = fp_pidx(i, S);
+                        const int p = fp_pidx(i, SM);
                         const double g1 = cg * gv[u], h1 = g1 - 0.5 * mv[u];
                         if (both) {
                             X[(size_t)f * q.pitch + p] = g1;
@@ -492,30 +501,30 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         case FP_YP: {
             // row k of X_d = cP tridiag(bp_diag, bp_off): three non-zeros
             const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
-            for (int e = tid; e < total; e += FP_THREADS) X[(size_t)(e / n) * q.pitch + fp_pidx(e % n, S)] = 0.0;
+            for (int e = tid; e < total; e += FP_THREADS) { int i, f; split_c(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = 0.0; }
             __syncthreads();
             if (tid < 3 * nf) {
                 const int f = tid / 3, dl = tid - 3 * f - 1;
                 const int k = (int)(fib0 + f), i = k + dl;
                 if (i >= 0 && i < n)
-                    X[(size_t)f * q.pitch + fp_pidx(i, S)] = cP * (double)(dl == 0 ? bnd[k] : bnd[n + (dl < 0 ? i : k)]);
+                    X[(size_t)f * q.pitch + fp_pidx(i, SM)] = cP * (double)(dl == 0 ? bnd[k] : bnd[n + (dl < 0 ? i : k)]);
             }
         } break;
         case FP_DL: {
             // column k of R_d -> Cx; then column k of dR_d = 2 cQ tridiag(bq_diag, bq_off) R_d -> X
             const double* __restrict__ R = tk.s0;
             fp_batched<FP_U>(total,
-                [&](int e) { const int i = e / nsrc, f = e - i * nsrc; return (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0; },
-                [&](int e, double v) { const int i = e / nsrc, f = e - i * nsrc; Cx[(size_t)f * q.pitch + fp_pidx(i, S)] = v; });
+                [&](int e) { int i, f; split_s(e, i, f); return (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0; },
+                [&](int e, double v) { int i, f; split_s(e, i, f); Cx[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
             __syncthreads();
             const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
             for (int e = tid; e < total; e += FP_THREADS) {
-                const int f = e / n, i = e - f * n;
+                int i, f; split_c(e, i, f);
                 const double* c = Cx + (size_t)f * q.pitch;
-                double r = (double)bnd[2 * n + i] * c[fp_pidx(i, S)];
-                if (i > 0) r = fma((double)bnd[3 * n + i - 1], c[fp_pidx(i - 1, S)], r);
-                if (i + 1 < n) r = fma((double)bnd[3 * n + i], c[fp_pidx(i + 1, S)], r);
-                X[(size_t)f * q.pitch + fp_pidx(i, S)] = 2.0 * cQ * r;
+                double r = (double)bnd[2 * n + i] * c[fp_pidx(i, SM)];
+                if (i > 0) r = fma((double)bnd[3 * n + i - 1], c[fp_pidx(i - 1, SM)], r);
+                if (i + 1 < n) r = fma((double)bnd[3 * n + i], c[fp_pidx(i + 1, SM)], r);
+                X[(size_t)f * q.pitch + fp_pidx(i, SM)] = 2.0 * cQ * r;
             }
         } break;
         default: break;
@@ -530,8 +539,8 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         case FP_R: {
             double* __restrict__ R = tk.o0;
             for (int e = tid; e < total; e += FP_THREADS) {
-                const int i = e / nsrc, f = e - i * nsrc;
-                if (f < nf) R[(i64)i * n + (fib0 + f)] = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                int i, f; split_s(e, i, f);
+                if (f < nf) R[(i64)i * n + (fib0 + f)] = X[(size_t)f * q.pitch + fp_pidx(i, SM)];
             }
         } break;
         case FP_PROD: case FP_DM: case FP_ALPHA: {
@@ -547,7 +556,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                     int i, f; split(e, i, f);
                     if (f >= nf) return;
                     const i64 a = fbase[f] + (i64)i * tk.inner;
-                    const double y = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                    const double y = X[(size_t)f * q.pitch + fp_pidx(i, SM)];
                     if (kind == FP_DM) {
                         dst[a] = y - v;
                     } else {
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                 int i, f; split(e, i, f);
                 if (f >= nf) continue;
                 const i64 a = fbase[f] + (i64)i * tk.inner;
-                const int pp = fp_pidx(i, S);
+                const int pp = fp_pidx(i, SM);
                 const double y = X[(size_t)f * q.pitch + pp];
                 dst[a] = tk.direct ? y - Cx[(size_t)f * q.pitch + pp] : y;      // Cx holds alpha of these fibres
             }
@@ -580,8 +589,8 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         case FP_YP: {
             double* __restrict__ Y = tk.o0;
             for (int e = tid; e < total; e += FP_THREADS) {
-                const int f = e / n, i = e - f * n;
-                if (f < nf) Y[(fib0 + f) * (i64)n + i] = X[(size_t)f * q.pitch + fp_pidx(i, S)];
+                int i, f; split_c(e, i, f);
+                if (f < nf) Y[(fib0 + f) * (i64)n + i] = X[(size_t)f * q.pitch + fp_pidx(i, SM)];
             }
         } break;
         case FP_DL: {
@@ -592,10 +601,10 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                 if (e2 != d) trO *= P.sc[SC_TR + e2];
             const double ratio = (double)P.M / (double)n;
             for (int e = tid; e < total; e += FP_THREADS) {
-                const int i = e / nsrc, f = e - i * nsrc;
+                int i, f; split_s(e, i, f);
                 if (f >= nf) continue;
                 const i64 k = fib0 + f;
-                const int p = fp_pidx(i, S);
+                const int p = fp_pidx(i, SM);
                 double v = 0.0;
                 if ((i64)i >= k) {
                     v = X[(size_t)f * q.pitch + p] - trO * Cx[(size_t)f * q.pitch + p];
@@ -614,7 +623,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                 const int i = j + dl;
                 if (i < 0 || i >= n) continue;
                 // W[i][j] with j = i - dl: slot (-dl + 1, i)
-                atomicAdd(acc + (1 - dl) * n + i, X[(size_t)f * q.pitch + fp_pidx(i, S)]);
+                atomicAdd(acc + (1 - dl) * n + i, X[(size_t)f * q.pitch + fp_pidx(i, SM)]);
             }
         } break;
         default: break;

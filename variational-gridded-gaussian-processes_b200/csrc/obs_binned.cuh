@@ -491,28 +491,27 @@ constexpr size_t bin_tma_smem_bytes() { return (size_t)BIN_WARPS * BIN_STAGES * 
 
 // Sum of the band replicas -> the band block of gbuf (overwritten); the replicas and the work-stealing counter are cleared
 // for the next launch (both start zeroed at plan creation), so the per-observation call needs no memset of its own for them.
-// grid (ceil(n / 64)), 256 threads = 64 elements x 4 replica groups.
+// grid (ceil(n / 16)), 256 threads = 16 elements x 16 replica groups; every thread has all its loads in flight at once.
 template <typename T>
 __global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_rep, i64 stride, int n, T* __restrict__ out,
                                                      unsigned int* __restrict__ counter) {
-    __shared__ T part[4][64];
+    __shared__ T part[16][17];
     if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;      // the task counter of the kernel that just ran: ready for the next launch
-    const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    const int e = (int)blockIdx.x * 64 + el;
+    const int el = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const int e = (int)blockIdx.x * 16 + el;
     T acc = (T)0;
     if (e < n) {
-        // all loads of a batch before the first store: the stores may alias the later loads as far as the compiler knows,
-        // and one load per iteration made this tiny kernel 32 serialised memory round trips long
-        for (int r0 = grp; r0 < n_rep; r0 += 4 * 8) {
+        // all loads of a batch before the first store: as far as the compiler knows the stores may alias the later loads
+        for (int r0 = grp; r0 < n_rep; r0 += 16 * 8) {
             T v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int r = r0 + 4 * u;
+                const int r = r0 + 16 * u;
                 v[u] = (r < n_rep) ? rep[(i64)r * stride + e] : (T)0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int r = r0 + 4 * u;
+                const int r = r0 + 16 * u;
                 acc += v[u];
                 if (r < n_rep) rep[(i64)r * stride + e] = (T)0;
             }
@@ -520,7 +519,12 @@ __global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_
     }
     part[grp][el] = acc;
     __syncthreads();
-    if (grp == 0 && e < n) out[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+    if (grp == 0 && e < n) {
+        T t = (T)0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t += part[k][el];
+        out[e] = t;
+    }
 }
 
 // ---- packing (one-time setup) ---------------------------------------------------------------------------

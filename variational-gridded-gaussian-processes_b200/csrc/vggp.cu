@@ -1091,7 +1091,7 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     else k_obs_b1_binned<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a);
     k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
-    k_band_reduce<T><<<ceil_div(p->band_total, 64), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M, a.counter);
+    k_band_reduce<T><<<ceil_div(p->band_total, 16), 256, 0, st>>>(a.gband, BAND_REPLICAS, a.band_rep_stride, p->band_total, gb + p->M, a.counter);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
