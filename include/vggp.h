@@ -208,6 +208,10 @@ int vggp_k1_time_read(vggp_plan* plan, float* mean_ms, int* n_launches);
 /* Failed-factorisation flag of the last forward (0 = ok, d+1 = factor d not positive definite).
  * Synchronises `stream`. */
 int vggp_read_info(vggp_plan* plan, int* info_host, void* stream);
+/* The same flag copied to `info_pinned_host` (page-locked host memory) in stream order WITHOUT synchronising: the host
+ * mirror records an event after it and raises torch.linalg.LinAlgError from the next call that finds the event complete
+ * (the reference raises at the failing Cholesky: 61_envisat_gulfstream_experiment.ipynb:746). */
+int vggp_info_async(vggp_plan* plan, int* info_pinned_host, void* stream);
 
 /*
  * Whole step through HOST buffers (the call a ctypes binding inside the reference's `_elbo` would make):

@@ -54,6 +54,18 @@ def host(monkeypatch_module):
             self.gbuf_obs_elems, self.gbuf_scalar_offset = int(ne.value), int(so.value)
             self.gbuf_scalars, self.gbuf_bytes = int(ns.value), int(tot.value)
             self.gbuf = torch.zeros(self.gbuf_bytes, dtype=torch.uint8)
+            self.last_out = None
+            self._armed = False
+
+        # no CUDA events / pinned memory on the CPU: the emulated library is synchronous, read the flag directly
+        def arm_info_check(self):
+            self._armed = True
+
+        def poll_info(self, wait):
+            if not self._armed:
+                return None
+            self._armed = False
+            return self.read_info()
 
     # status checking of the product binding, against the emulated library
     def check(status):

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vggp_set_binned_stream": (C.c_int, [C.c_int]),
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
+    "vggp_info_async": (C.c_int, [_vp, _vp, _vp]),
     "vggp_k1_timing": (C.c_int, [_vp, C.c_int]),
     "vggp_k1_time_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vggp_predict": (C.c_int, [_vp, C.POINTER(_vp), _i64, _dp, _dp, _vp]),

@@ -1947,6 +1947,12 @@ int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
     return 0;
 }
 
+int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
+    if (!p || !info_pinned_host) return fail(VGGP_E_ARG, "null argument");
+    VGGP_CUDA(cudaMemcpyAsync(info_pinned_host, p->g.info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
 int vggp_elbo_host(vggp_plan* p, const void* const* x_host, const void* y_host, int64_t n, const double* theta_host,
                    const double* m_host, const double* L_host, double ell_scale, double* out_host,
                    double* dtheta_host, double* dm_host, double* dL_host, void* stream) {

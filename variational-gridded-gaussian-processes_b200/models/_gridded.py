@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from ..params import GaussianLikelihood, GriddedMarginals, GriddedNormal, MaternKernel, ScaleKernel
+from ..params import DenseNormal, GaussianLikelihood, GriddedMarginals, GriddedNormal, MaternKernel, ScaleKernel
 from ..plan import GridPlan, gridded_elbo
 from ..dist import shard_bounds
 
@@ -59,6 +59,8 @@ class GriddedVariationalGP(nn.Module):
         self._packed = None
         self._group = None
         self._n_total = int(y.numel())
+        self._terms = None                      # [ELBO, scaled ELL, KL, n_obs] of the last _elbo() (device tensor)
+        self.strict_checks = bool(int(os.environ.get("VGGP_STRICT", "0")))   # synchronise and check after every _elbo()
 
     # ---- parameters as the kernels see them -----------------------------------------------------------------
     def _chols(self) -> List[torch.Tensor]:
@@ -122,9 +124,29 @@ class GriddedVariationalGP(nn.Module):
         return self._plan
 
     # ---- the hot path ---------------------------------------------------------------------------------------
+    def _raise_if_failed(self, wait: bool):
+        """The reference raises LinAlgError where a covariance stops being positive definite (gpytorch's Cholesky;
+        61_envisat_gulfstream_experiment.ipynb:746 catches it).  The library sets a device flag instead of synchronising
+        the step; it is copied to pinned memory behind every step and turned into the exception here -- at the next
+        `_elbo()` that finds the copy complete, or immediately with `strict_checks` / `check_factorisation()`."""
+        if self._plan is None:
+            return
+        flag = self._plan.poll_info(wait)
+        if flag is None:
+            return
+        if flag != 0:
+            raise torch.linalg.LinAlgError(
+                f"the per-dimension factor K_{flag} = Kuu along dimension {flag} is not positive definite at the current "
+                "hyper-parameters (Cholesky / pivot recurrence failed); the ELBO of that step is invalid")
+
+    def check_factorisation(self) -> None:
+        """Synchronise and raise torch.linalg.LinAlgError if the last `_elbo()` hit a non-positive-definite factor."""
+        self._raise_if_failed(wait=True)
+
     def _elbo(self, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Evidence lower bound (0-dim tensor with grad_fn).  `batch`: optional index tensor / slice selecting a
         minibatch of this rank's observations; the expected log-likelihood is rescaled by N / B."""
+        self._raise_if_failed(wait=False)
         plan = self._ensure_plan()
         if self._packed is not None:
             xs, y = self._packed, None
@@ -137,12 +159,20 @@ class GriddedVariationalGP(nn.Module):
             n_local = self._obs[1].numel()
             scale = float(n_local) / float(max(1, y.numel()))
         ls, os_, noise = self._hyper()
-        return gridded_elbo(plan, xs, y, ls, os_, noise, self.variational_mean, self._chols(),
+        elbo = gridded_elbo(plan, xs, y, ls, os_, noise, self.variational_mean, self._chols(),
                             ell_scale=scale, group=self._group)
+        self._terms = plan.last_out
+        plan.arm_info_check()
+        if self.strict_checks:
+            self._raise_if_failed(wait=True)
+        return elbo
 
     def elbo_terms(self) -> torch.Tensor:
-        """[ELBO, scaled ELL, KL, n_obs] of the last `_elbo()` call (device tensor, no sync)."""
-        raise NotImplementedError
+        """[ELBO, scaled expected log-likelihood, KL, n_obs over all ranks] of the last `_elbo()` call (float64 device
+        tensor, no synchronisation)."""
+        if self._terms is None:
+            raise RuntimeError("elbo_terms() needs a previous _elbo() call")
+        return self._terms
 
     # ---- variational distribution ---------------------------------------------------------------------------
     def q_u(self) -> GriddedNormal:

@@ -119,6 +119,27 @@ class GriddedNormal:
         return self.mean - s2, self.mean + s2
 
 
+class DenseNormal:
+    """MultivariateNormal-like result of the reference's closed-form (dense, small-M) formulas: .mean, .covariance_matrix."""
+
+    def __init__(self, mean: torch.Tensor, covariance_matrix: torch.Tensor):
+        self.mean = mean
+        self.loc = mean
+        self.covariance_matrix = covariance_matrix
+
+    @property
+    def variance(self) -> torch.Tensor:
+        return torch.diagonal(self.covariance_matrix)
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.variance.clamp_min(0).sqrt()
+
+    def confidence_region(self):
+        s2 = 2 * self.stddev
+        return self.mean - s2, self.mean + s2
+
+
 class GriddedMarginals:
     """Result of posterior(x*) / posterior_predictive(x*): marginal mean and variance at the test points.  The
     reference returns a dense N* x N* MultivariateNormal (kronecker_structure.py:199-247); only its marginals --

@@ -53,6 +53,7 @@ class GridPlan:
         self.gbuf_obs_elems, self.gbuf_scalar_offset = int(ne.value), int(so.value)
         self.gbuf_scalars, self.gbuf_bytes = int(ns.value), int(tot.value)
         self.gbuf = torch.zeros(self.gbuf_bytes, dtype=torch.uint8, device=self.device)
+        self.last_out = None                   # [ELBO, scaled ELL, KL, n_obs] of the last step (device tensor)
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -210,7 +211,9 @@ class GridPlan:
         self.obs_fwd_bwd(xs, y)
         if group is not None:
             self.allreduce_gbuf(None if isinstance(group, str) else group)
-        return self.grid_backward(theta, m, L, ell_scale)
+        res = self.grid_backward(theta, m, L, ell_scale)
+        self.last_out = res[0]
+        return res
 
     def graphed_step(self, theta, m, L, xs, y=None, ell_scale: float = 1.0, group=None, warmup: int = 3):
         """Capture the C-ABI launches of one step into CUDA graphs (opt-in; removes the launch gaps between the ~15
@@ -246,6 +249,28 @@ class GridPlan:
         ms, n = C.c_float(0.0), C.c_int(0)
         _lib.check(self.lib.vggp_k1_time_read(self.handle, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def arm_info_check(self):
+        """Copy the factorisation flag of the last forward into pinned host memory in stream order, without synchronising
+        (vggp_info_async), and record an event behind the copy; `poll_info` turns it into a value later."""
+        if getattr(self, "_info_host", None) is None:
+            self._info_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.check(self.lib.vggp_info_async(self.handle, self._info_host.data_ptr(), _stream_ptr(self.device)))
+        self._info_event = torch.cuda.Event()
+        self._info_event.record(torch.cuda.current_stream(self.device))
+
+    def poll_info(self, wait: bool) -> Optional[int]:
+        """Flag armed by `arm_info_check` (0 = ok, d + 1 = factor d not positive definite), or None if nothing is armed /
+        the copy has not completed yet and `wait` is False."""
+        ev = getattr(self, "_info_event", None)
+        if ev is None:
+            return None
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return None
+        self._info_event = None
+        return int(self._info_host[0])
 
     def read_info(self) -> int:
         info = C.c_int(0)
