@@ -145,6 +145,8 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((uint64_t)a * (uint64_t)b) >> 32); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline int __double2hiint(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); }
+inline double __hiloint2double(int hi, int lo) { const int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double v; memcpy(&v, &b, 8); return v; }
 inline int __float_as_int(float v) { int i; memcpy(&i, &v, 4); return i; }
 inline long long __double_as_longlong(double v) { long long i; memcpy(&i, &v, 8); return i; }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

@@ -78,13 +78,14 @@ struct FpPass {
 // ---------------------------------------------------------------------------------------------------------
 struct Mob { double a, b, c, d; };     // x -> (a x + b) / (c x + d)
 
-__device__ __forceinline__ void mob_rescale(Mob& m, bool always = false) {
-    const double mx = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
-    if (always || mx > 1e100 || mx < 1e-100) {
-        int ex;
-        frexp(mx, &ex);
-        m.a = ldexp(m.a, -ex); m.b = ldexp(m.b, -ex); m.c = ldexp(m.c, -ex); m.d = ldexp(m.d, -ex);
-    }
+// 2^-e for the binary exponent e of |x| (x normal, non-zero): an exact scaling that brings x into [1, 2)
+__device__ __forceinline__ double pow2_inv_scale(double x) {
+    const int e = (__double2hiint(x) >> 20) & 0x7ff;
+    return __hiloint2double((2046 - e) << 20, 0);
+}
+__device__ __forceinline__ void mob_rescale(Mob& m) {
+    const double sc = pow2_inv_scale(fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d))));
+    m.a *= sc; m.b *= sc; m.c *= sc; m.d *= sc;
 }
 // apply x -> p - q / x after m:  (p (a x + b) - q (c x + d)) / (a x + b)
 __device__ __forceinline__ void mob_push(Mob& m, double p, double q) {
@@ -92,56 +93,68 @@ __device__ __forceinline__ void mob_push(Mob& m, double p, double q) {
     m.c = m.a; m.d = m.b; m.a = na; m.b = nb;
 }
 
+// The factor of this family is Toeplitz apart from its two corner entries (one knot spacing delta32 for the whole matrix,
+// as in the reference): three numbers describe it.
+struct B1Coef { double a_in, a_bd, b; };      // interior diagonal, corner diagonal, off-diagonal
+__device__ __forceinline__ B1Coef b1_coef(const GridDims& g, const double* theta, int d) {
+    B1Coef c;
+    const int n = g.n[d];
+    c.a_bd = factor_entry(g, theta, d, 0, 0);
+    c.a_in = factor_entry(g, theta, d, 1, 1);
+    c.b = factor_entry(g, theta, d, 0, 1);
+    if (n < 3) c.a_in = c.a_bd;
+    return c;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__ GridDims g, const double* __restrict__ theta,
-                                                         double* __restrict__ acc_all, int acc_total) {
+                                                         double* __restrict__ acc_all, int acc_total,
+                                                         double* __restrict__ theta_copy) {
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ double carry_d[GEN_THREADS], carry_e[GEN_THREADS];
-    __shared__ Mob comp_d[GEN_THREADS], comp_e[GEN_THREADS];
+    __shared__ Mob comp_d[GEN_THREADS / 2], comp_e[GEN_THREADS / 2];
     __shared__ int bad_flag;
     const int d = blockIdx.x;
     const int n = g.n[d];
     const int tid = threadIdx.x;
-    double* a = sm;
-    double* b = a + n;
-    double* dd = b + n;
-    double* ee = dd + n;
+    double* dd = sm;                 // top-down pivots, later ru
+    double* ee = dd + n;             // bottom-up pivots
+    double* rd = ee + n;             // 1 / dd
+    double* re = rd + n;             // 1 / ee
     if (tid == 0) bad_flag = 0;
     if (d == 0) {
         if (tid < SC_COUNT) g.sc[tid] = 0.0;
         if (tid == 0) *g.info = 0;
+        if (tid < 2 * g.D + 1) theta_copy[tid] = theta[tid];       // the plan's copy of theta (features / predictions read it)
     }
     // the band accumulators of every dimension are cleared here, at the start of the step
     for (int i = (int)blockIdx.x * GEN_THREADS + tid; i < acc_total; i += (int)gridDim.x * GEN_THREADS) acc_all[i] = 0.0;
-    for (int i = tid; i < n; i += GEN_THREADS) {
-        a[i] = factor_entry(g, theta, d, i, i);
-        b[i] = (i + 1 < n) ? factor_entry(g, theta, d, i, i + 1) : 0.0;
-    }
-    __syncthreads();
+    const B1Coef cf = b1_coef(g, theta, d);
+    const double b2 = cf.b * cf.b;
+    auto diag = [&](int k) { return (k == 0 || k == n - 1) ? cf.a_bd : cf.a_in; };
     const int nch = (n + GEN_CHUNK - 1) / GEN_CHUNK;      // <= GEN_THREADS / 2 (n <= 2560: 80 chunks)
     // threads [0, nch): top-down chunk composites; threads [128, 128 + nch): bottom-up
     const bool up = tid >= GEN_THREADS / 2;
     const int ch = up ? tid - GEN_THREADS / 2 : tid;
     if (ch < nch) {
         Mob m = {1.0, 0.0, 0.0, 1.0};
+        const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
         if (!up) {
             // chunk covers k in [k0, k1); maps d_{k0 - 1} -> d_{k1 - 1}
-            const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
             for (int k = max(k0, 1); k < k1; ++k) {
-                mob_push(m, a[k], b[k - 1] * b[k - 1]);
+                mob_push(m, diag(k), b2);
                 if ((k & 7) == 7) mob_rescale(m);
             }
-            mob_rescale(m, true);          // entries in [0.5, 1): the serial chain below cannot overflow between its own rescalings
+            mob_rescale(m);            // entries in [1, 2): the serial chain below cannot overflow between its own rescalings
             comp_d[ch] = m;
         } else {
             // chunk covers k in [k0, k1) walked downwards; maps e_{k1} -> e_{k0}
-            const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
             for (int k = min(k1 - 1, n - 2); k >= k0; --k) {
-                mob_push(m, a[k], b[k] * b[k]);
+                mob_push(m, diag(k), b2);
                 if ((k & 7) == 0) mob_rescale(m);
             }
-            mob_rescale(m, true);
+            mob_rescale(m);
             comp_e[ch] = m;
         }
     }
@@ -149,69 +162,60 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
     // the carries are chained in homogeneous coordinates x = num / den (no division on the serial path; exact power-of-two
     // rescaling), every chunk divides its own carry afterwards
     if (tid == 0) {
-        double num = a[0], den = 1.0;                      // d_0; chunk 0's composite starts from it
+        double num = cf.a_bd, den = 1.0;                   // d_0; chunk 0's composite starts from it
         for (int c = 0; c < nch; ++c) {
             carry_d[c] = num; carry_d[GEN_THREADS / 2 + c] = den;    // value entering chunk c (d_{k0 - 1}; for c = 0: d_0 itself)
             const Mob m = comp_d[c];
             const double nn = fma(m.a, num, m.b * den), dn = fma(m.c, num, m.d * den);
-            num = nn; den = dn;
-            if ((c & 3) == 3) {
-                int ex;
-                frexp(fmax(fabs(num), fabs(den)), &ex);
-                num = ldexp(num, -ex); den = ldexp(den, -ex);
-            }
+            const double sc = pow2_inv_scale(fmax(fabs(nn), fabs(dn)));
+            num = nn * sc; den = dn * sc;
         }
     } else if (tid == 32) {
-        double num = a[n - 1], den = 1.0;                  // e_{n-1}
+        double num = cf.a_bd, den = 1.0;                   // e_{n-1}
         for (int c = nch - 1; c >= 0; --c) {
             carry_e[c] = num; carry_e[GEN_THREADS / 2 + c] = den;    // value entering chunk c from above (e_{k1}; top chunk: e_{n-1})
             const Mob m = comp_e[c];
             const double nn = fma(m.a, num, m.b * den), dn = fma(m.c, num, m.d * den);
-            num = nn; den = dn;
-            if ((c & 3) == 0) {
-                int ex;
-                frexp(fmax(fabs(num), fabs(den)), &ex);
-                num = ldexp(num, -ex); den = ldexp(den, -ex);
-            }
+            const double sc = pow2_inv_scale(fmax(fabs(nn), fabs(dn)));
+            num = nn * sc; den = dn * sc;
         }
     }
     __syncthreads();
     // plain recurrences inside the chunks.  1 / pivot is carried along by one Newton step from the previous reciprocal
-    // (the pivots change slowly) with an exact division whenever the residual is not at rounding level (round-1 scheme).
+    // (the pivots change slowly) with an exact division whenever the residual is not at rounding level (round-1 scheme);
+    // the reciprocals are kept: the generators need them.
     if (ch < nch) {
         const int k0 = ch * GEN_CHUNK, k1 = min(n, k0 + GEN_CHUNK);
         bool bad = false;
         if (!up) {
             double prev = carry_d[ch] / carry_d[GEN_THREADS / 2 + ch];
-            int k = k0;
-            if (ch == 0) { dd[0] = prev; bad = !(prev > 0.0); k = 1; }
             double r = 1.0 / prev;
+            int k = k0;
+            if (ch == 0) { dd[0] = prev; rd[0] = r; bad = !(prev > 0.0); k = 1; }
             for (; k < k1; ++k) {
-                const double bk = b[k - 1];
-                const double nxt = fma(-bk * bk, r, a[k]);
-                dd[k] = nxt;
+                const double nxt = fma(-b2, r, diag(k));
                 bad = bad || !(nxt > 0.0);
                 double e = fma(-nxt, r, 1.0);
                 double rn = fma(r, e, r);
                 e = fma(-nxt, rn, 1.0);
                 if (!(fabs(e) < 3e-16)) rn = 1.0 / nxt;
                 r = rn;
+                dd[k] = nxt; rd[k] = r;
             }
         } else {
             double nxt = carry_e[ch] / carry_e[GEN_THREADS / 2 + ch];
-            int k = k1 - 1;
-            if (k1 == n) { ee[n - 1] = nxt; k = n - 2; }
             double r = 1.0 / nxt;
+            int k = k1 - 1;
+            if (k1 == n) { ee[n - 1] = nxt; re[n - 1] = r; bad = !(nxt > 0.0); k = n - 2; }
             for (; k >= k0; --k) {
-                const double bk = b[k];
-                const double cur = fma(-bk * bk, r, a[k]);
-                ee[k] = cur;
+                const double cur = fma(-b2, r, diag(k));
                 bad = bad || !(cur > 0.0);
                 double e = fma(-cur, r, 1.0);
                 double rn = fma(r, e, r);
                 e = fma(-cur, rn, 1.0);
                 if (!(fabs(e) < 3e-16)) rn = 1.0 / cur;
                 r = rn;
+                ee[k] = cur; re[k] = r;
             }
         }
         if (bad) bad_flag = 1;
@@ -219,25 +223,27 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
     __syncthreads();
     if (tid == 0 && bad_flag) atomicMax(g.info, d + 1);
     double* gen = g.gen[d];
+    double prod = 1.0;
     double ld = 0.0;
     for (int i = tid; i < n; i += GEN_THREADS) {
-        const double pdv = 1.0 / (dd[i] + ee[i] - a[i]);
-        const double ruv = (i + 1 < n) ? -b[i] / dd[i] : 0.0;
-        const double rlv = (i + 1 < n) ? -b[i] / ee[i + 1] : 0.0;
+        const double di = dd[i];
+        const double pdv = 1.0 / (di + ee[i] - diag(i));
+        const double ruv = (i + 1 < n) ? -cf.b * rd[i] : 0.0;
+        const double rlv = (i + 1 < n) ? -cf.b * re[i + 1] : 0.0;
         gen[i] = pdv; gen[n + i] = ruv; gen[2 * n + i] = rlv;
-        ld += log(dd[i]);
-        a[i] = pdv;            // reuse: a = pd, b = ru  (P-band tables below)
+        ee[i] = pdv; dd[i] = ruv;          // reuse (only this thread reads dd[i], ee[i] above): ee = pd, dd = ru for the tables
+        prod *= di;                        // log det K_d = sum log d_k: one log per thread
+        if (prod > 1e200 || prod < 1e-200) { ld += log(prod); prod = 1.0; }
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += GEN_THREADS) if (i + 1 < n) dd[i] = -b[i] / dd[i];   // dd = ru
+    ld += log(prod);
     __syncthreads();
     // per-cell tables of the band of P_d, monomial basis in the hat weight (same as k_fwd_reduce)
     T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];
     for (int i = tid; i < n; i += GEN_THREADS) {
         const bool last = (i + 1 >= n);
-        const double A = a[i];
-        const double B2 = last ? 0.0 : 2.0 * a[i + 1] * dd[i];        // 2 P[i][i+1] = 2 pd[i+1] ru[i]
-        const double Cc = last ? 0.0 : a[i + 1];
+        const double A = ee[i];
+        const double B2 = last ? 0.0 : 2.0 * ee[i + 1] * dd[i];        // 2 P[i][i+1] = 2 pd[i+1] ru[i]
+        const double Cc = last ? 0.0 : ee[i + 1];
         tab[i] = (T)A; tab[n + i] = (T)(B2 - 2.0 * A); tab[2 * n + i] = (T)(A - B2 + Cc);
     }
     ld = block_sum(ld, red);
@@ -282,19 +288,42 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
     const int i0 = lane * S;
     const int cnt = max(0, min(S, n - i0));
     const int p0 = lane * (S + 1);
-    // phase 1: affine summaries of the lane's segment for both sweeps
+    // phase 1: affine summaries of the lane's segment for both sweeps.  Up to 16 elements per lane (n <= 512) live in
+    // registers and the loops are fully unrolled, so the shared-memory loads are issued ahead of the dependent chains.
     double lA = 1.0, lB = 0.0, uA = 1.0, uB = 0.0;
-    for (int j = 0; j < cnt; ++j) {
-        const double r = rl[p0 + j];
-        const double s = pd[p0 + j] * X[p0 + j];
-        lB = fma(r, lB, r * s);
-        lA *= r;
-    }
-    for (int j = cnt - 1; j >= 0; --j) {
-        const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
-        const double s = pd[p0 + j] * X[p0 + j];
-        uB = fma(r, uB, r * s);
-        uA *= r;
+    double sv[16];
+    if (S <= 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[j] = (j < cnt) ? pd[p0 + j] * X[p0 + j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < cnt) {
+                const double r = rl[p0 + j];
+                lB = fma(r, lB, r * sv[j]);
+                lA *= r;
+            }
+        }
+#pragma unroll
+        for (int j = 15; j >= 0; --j) {
+            if (j < cnt) {
+                const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
+                uB = fma(r, uB, r * sv[j]);
+                uA *= r;
+            }
+        }
+    } else {
+        for (int j = 0; j < cnt; ++j) {
+            const double r = rl[p0 + j];
+            const double s = pd[p0 + j] * X[p0 + j];
+            lB = fma(r, lB, r * s);
+            lA *= r;
+        }
+        for (int j = cnt - 1; j >= 0; --j) {
+            const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
+            const double s = pd[p0 + j] * X[p0 + j];
+            uB = fma(r, uB, r * s);
+            uA *= r;
+        }
     }
     // inclusive scans of the affine maps across lanes (ascending for l, descending for u)
 #pragma unroll
@@ -316,17 +345,15 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
             if (j < cnt) {
                 uu[j] = u;
                 const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
-                const double s = pd[p0 + j] * X[p0 + j];
-                u = fma(r, u, r * s);
+                u = fma(r, u, r * sv[j]);
             }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             if (j < cnt) {
                 const double r = rl[p0 + j];
-                const double s = pd[p0 + j] * X[p0 + j];
-                X[p0 + j] = s + l + uu[j];
-                l = fma(r, l, r * s);
+                X[p0 + j] = sv[j] + l + uu[j];
+                l = fma(r, l, r * sv[j]);
             }
         }
     } else {
@@ -673,7 +700,6 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
 __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
                                                   const double* __restrict__ acc, const double* __restrict__ gscal,
                                                   double ell_scale, double* __restrict__ out, double* __restrict__ dtheta) {
-    __shared__ double red[32];
     const int d = blockIdx.x;
     const int n = g.n[d];
     const int D = g.D;
@@ -681,22 +707,37 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
     const double half_c = 0.5 * tr_others(g, d);
     const double* __restrict__ gen = g.gen[d];
     for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
+    // d K / d l and d K / d s2 take three distinct values each (corner diagonal, interior diagonal, off-diagonal)
+    double gl[3], gs[3];
+    factor_entry_grad(g, theta, d, 0, 0, gl[0], gs[0]);
+    factor_entry_grad(g, theta, d, 1, 1, gl[1], gs[1]);
+    factor_entry_grad(g, theta, d, 0, 1, gl[2], gs[2]);
+    const double* __restrict__ Qb = g.Qb[d];
     double sl = 0.0, ss = 0.0;
-#pragma unroll 2
+#pragma unroll 3
     for (int e = threadIdx.x; e < 3 * n; e += 512) {
-        const int dl = e / n - 1, i = e - (dl + 1) * n;
+        const int dl = (e >= 2 * n) ? 1 : (e >= n ? 0 : -1);
+        const int i = e - (dl + 1) * n;
         const int j = i + dl;
         if (j < 0 || j >= n) continue;
-        const double qv = (i == j) ? g.Qb[d][i] : g.Qb[d][n + (i < j ? i : j)];
-        const double pij = b1_P_band(gen, n, i, j);
+        const int lo = i < j ? i : j;
+        const double qv = (dl == 0) ? Qb[i] : Qb[n + lo];
+        // P_d on the band from the generators: pd_i on the diagonal, pd_{lo+1} ru_lo above, pd_lo rl_lo below it
+        const double pij = (dl == 0) ? gen[i] : (dl > 0 ? gen[j] * gen[n + i] : gen[j] * gen[2 * n + j]);
         const double v = -acc[e] + half_c * qv - half_ratio * pij;
-        double a, b;
-        factor_entry_grad(g, theta, d, i, j, a, b);
-        sl = fma(v, a, sl);
-        ss = fma(v, b, ss);
+        const bool corner = (i == 0 || i == n - 1);
+        sl = fma(v, (dl != 0) ? gl[2] : (corner ? gl[0] : gl[1]), sl);
+        ss = fma(v, (dl != 0) ? gs[2] : (corner ? gs[0] : gs[1]), ss);
     }
-    sl = block_sum(sl, red);
-    ss = block_sum(ss, red);
+    sl = warp_sum(sl);
+    ss = warp_sum(ss);
+    __shared__ double red2[2][16];
+    if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = sl; red2[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sl = 0.0; ss = 0.0;
+        for (int w = 0; w < 16; ++w) { sl += red2[0][w]; ss += red2[1][w]; }
+    }
     if (threadIdx.x == 0) {
         const double noise = theta[2 * D];
         double kff = 1.0;

@@ -549,10 +549,9 @@ int b1f_forward(vggp_plan* p, const double* theta, const double* m, const double
     const int D = p->D;
     int rc;
     const size_t gsm = 4 * (size_t)p->nmax * sizeof(double);
-    if (p->obs_dtype == VGGP_F32) k_b1_gens<float><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total);
-    else k_b1_gens<double><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total);
+    if (p->obs_dtype == VGGP_F32) k_b1_gens<float><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total, p->theta_dev);
+    else k_b1_gens<double><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total, p->theta_dev);
     VGGP_LAUNCH_CHECK();
-    VGGP_CUDA(cudaMemcpyAsync(p->theta_dev, theta, sizeof(double) * (2 * D + 1), cudaMemcpyDeviceToDevice, st));
     FpPass P;
     auto qrows = [&](FpPass& Q) {
         for (int d = 0; d < D; ++d) {
