@@ -29,6 +29,10 @@ def host(monkeypatch_module):
     plan_mod = importlib.import_module(PKG + ".plan")
     monkeypatch_module.setattr(plan_mod, "_stream_ptr", lambda device: None)
 
+    def check(status):      # status checking of the product binding, against the emulated library
+        if status != 0:
+            raise RuntimeError(f"libvggp status {status}: {lib.vggp_last_error().decode()}")
+
     class EmuGridPlan(plan_mod.GridPlan):
         def __init__(self, family, meshes, obs_dtype):          # device-independent part of GridPlan.__init__
             self.lib = lib
@@ -57,6 +61,16 @@ def host(monkeypatch_module):
             self.last_out = None
             self._armed = False
 
+        def workspace(self, which, dim=0):                      # host pointer -> tensor (the product wraps a device pointer)
+            ptr, n = C.c_void_p(), C.c_int64()
+            check(lib.vggp_workspace_ptr(self.handle, which, dim, C.byref(ptr), C.byref(n)))
+            arr = np.ctypeslib.as_array(C.cast(ptr.value, C.POINTER(C.c_double)), shape=(int(n.value),)).copy()
+            out = torch.from_numpy(arr)
+            if which in (plan_mod._lib.WS_ALPHA, plan_mod._lib.WS_SCAL, plan_mod._lib.WS_QBAND):
+                return out
+            nd = self.m_per_dim[dim]
+            return out.view(nd, nd)
+
         # no CUDA events / pinned memory on the CPU: the emulated library is synchronous, read the flag directly
         def arm_info_check(self):
             self._armed = True
@@ -67,10 +81,6 @@ def host(monkeypatch_module):
             self._armed = False
             return self.read_info()
 
-    # status checking of the product binding, against the emulated library
-    def check(status):
-        if status != 0:
-            raise RuntimeError(f"libvggp status {status}: {lib.vggp_last_error().decode()}")
     monkeypatch_module.setattr(plan_mod._lib, "check", check)
     return plan_mod, EmuGridPlan, L
 
@@ -204,3 +214,135 @@ def test_model_training_loop_over_the_emulator(host, monkeypatch, family, layout
     assert losses[-1] < losses[0]
     post = model.posterior(X[:50])
     assert torch.isfinite(post.mean).all() and (post.variance > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's closed-form quantities (q_u / q_v of the collapsed bound) against numbers produced by the reference's own
+# code (tests/golden/reference_models.npz, oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+def _patched_models(host, monkeypatch):
+    plan_mod, EmuGridPlan, L = host
+    gmod = importlib.import_module(PKG + ".models._gridded")
+    monkeypatch.setattr(gmod, "GridPlan", lambda fam, meshes, dtype, device: EmuGridPlan(fam, meshes, dtype))
+    monkeypatch.setattr(gmod.GriddedVariationalGP, "_device_dtype", lambda self: (torch.device("cpu"), self.variational_mean.dtype))
+    return gmod
+
+
+def _set_raw(model, spec):
+    sd = dict(model.named_parameters())
+    for k, v in spec.items():
+        sd[k].data.fill_(v)
+
+
+@pytest.mark.parametrize("pset", ["raw0", "raw1"])
+def test_closed_form_q_1d_matches_reference_run(host, monkeypatch, golden_dir, pset):
+    """gridded_univariate_structure.Matern12GriddedGP: q_u_optimal() / q_v(optimal=True) reproduce the reference's q_v(), and
+    after set_optimal_q() the uncollapsed `_elbo()` IS the reference's collapsed `_elbo()` (case G3 of the golden file)."""
+    import os
+    _patched_models(host, monkeypatch)
+    gus = importlib.import_module(PKG + ".models.sparse.gridded_univariate_structure")
+    ref = np.load(os.path.join(golden_dir, "reference_models.npz"))
+    key = f"G3_griddedgp1d.{pset}"
+    x, y = torch.from_numpy(ref["g3.x"]), torch.from_numpy(ref["g3.y"])
+    model = gus.Matern12GriddedGP(x, y, 32, (0., 2.)).to(torch.float64)
+    _set_raw(model, {"raw0": {}, "raw1": {"kernel.raw_outputscale": 0.5, "kernel.base_kernel.raw_lengthscale": -0.3,
+                                          "likelihood.noise_covar.raw_noise": -3.0}}[pset])
+    assert relerr(model._Kuu(), torch.from_numpy(ref[key + ".Kuu"])) < 1e-12
+    q = model.q_v(optimal=True)
+    assert relerr(q.mean, torch.from_numpy(ref[key + ".q_mean"])) < 1e-8
+    assert relerr(q.covariance_matrix, torch.from_numpy(ref[key + ".q_cov"])) < 1e-8
+    Sig = model._sigma()
+    assert Sig.shape == (32, 32) and torch.allclose(Sig, Sig.T)
+    model.set_optimal_q()
+    elbo = model._elbo()
+    assert abs(elbo.item() - float(ref[key + ".elbo"])) < 1e-6 * abs(float(ref[key + ".elbo"]))
+    model.check_factorisation()
+    terms = model.elbo_terms()
+    assert abs(terms[0].item() - elbo.item()) < 1e-12 * abs(elbo.item()) and abs((terms[1] - terms[2]).item() - elbo.item()) < 1e-9 * abs(elbo.item())
+    assert terms[3].item() == 600
+
+
+@pytest.mark.parametrize("case,pset", [("G1_griddedgp2d", "raw0"), ("G1_griddedgp2d", "raw1"), ("K_b0gridded2d", "raw1")])
+def test_closed_form_q_2d_matches_reference_run(host, monkeypatch, golden_dir, case, pset):
+    """2-D B0 models (gridded_kronecker_structure.Matern12GriddedGP, kronecker_structure.Matern12B0SplineGriddedGP): the dense
+    closed-form q(u) against the reference's own q_u() / q_v() output; set_optimal_q() loads m* and the nearest Kronecker
+    factorisation of S*, whose bound cannot exceed the collapsed one and must be close to it."""
+    import os
+    _patched_models(host, monkeypatch)
+    ref = np.load(os.path.join(golden_dir, "reference_models.npz"))
+    X, y = torch.from_numpy(ref["nb5.X"]).to(torch.float64), torch.from_numpy(ref["nb5.y"]).to(torch.float64)
+    if case.startswith("G1"):
+        mod = importlib.import_module(PKG + ".models.sparse.gridded_kronecker_structure")
+        model = mod.Matern12GriddedGP(X, y, 11, (0, 1), (0, 1)).to(torch.float64)
+    else:
+        mod = importlib.import_module(PKG + ".models.sparse.kronecker_structure")
+        model = mod.Matern12B0SplineGriddedGP(X, y, 9, (0, 1), (0, 1)).to(torch.float64)
+    _set_raw(model, {"raw0": {}, "raw1": {"kernel_1.raw_outputscale": 0.3, "kernel_1.base_kernel.raw_lengthscale": -0.7,
+                                          "kernel_2.raw_outputscale": -0.2, "kernel_2.base_kernel.raw_lengthscale": 0.4,
+                                          "likelihood.noise_covar.raw_noise": -2.0}}[pset])
+    key = f"{case}.{pset}"
+    assert relerr(model._Kuu(), torch.from_numpy(ref[key + ".Kuu"])) < 1e-12
+    q = model.q_v(optimal=True)
+    assert relerr(q.mean, torch.from_numpy(ref[key + ".q_mean"])) < 1e-7
+    assert relerr(q.covariance_matrix, torch.from_numpy(ref[key + ".q_cov"])) < 1e-7
+    model.set_optimal_q()
+    elbo, collapsed = model._elbo().item(), float(ref[key + ".elbo"])
+    assert elbo <= collapsed + 1e-8 * abs(collapsed)          # the collapsed bound is the maximum over q(u)
+    assert collapsed - elbo < 0.2 * abs(collapsed)            # Kronecker S is a restriction, not a different model
+    # full-covariance posterior of the dense formulas against the marginals of the structured path
+    xs = X[:40]
+    dense = model.posterior_dense(xs)
+    marg = model.posterior(xs)
+    assert relerr(dense.mean, marg.mean) < 1e-8 and relerr(dense.variance, marg.variance) < 1e-7
+
+
+def test_gridded_part_dense_matrices_asvgp(host, monkeypatch):
+    """GriddedMatern12ASVGP (2-D) and its 1-D twin: _Kvu / _Kvv / p_v_u / q_v against the reference's constructions restated
+    with torch (gridded_kronecker_structure.py:831-947, gridded_univariate_structure.py:595-700)."""
+    _patched_models(host, monkeypatch)
+    gks = importlib.import_module(PKG + ".models.sparse.gridded_kronecker_structure")
+    gus = importlib.import_module(PKG + ".models.sparse.gridded_univariate_structure")
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(300, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(4 * X[:, 0]) * torch.cos(3 * X[:, 1]) + 0.05 * torch.randn(300, generator=g, dtype=torch.float64)
+    model = gks.GriddedMatern12ASVGP(X, y, 6, 1, (0, 1), (0, 1)).to(torch.float64)
+    # reference construction of Kvu_along_dim: padded [delta, delta] rolled by the cell index
+    delta = model.b1_basis_1.delta
+    nk = model.b1_basis_1.n_basis_functions
+    first = torch.nn.functional.pad(torch.tensor([delta, delta]), (1, nk - 3))
+    Kvu_ref = torch.vstack([torch.roll(first, i) for i in range(6)]).to(torch.float64)
+    assert torch.equal(model._Kvu_along_dim(0), Kvu_ref)
+    assert model._Kvu().shape == (36, nk * nk) and model._Kvv().shape == (36, 36)
+    assert relerr(model._Kvv_along_dim(0), O.kuu_b0(model.b0_mesh_1, model.kernel_1.base_kernel.lengthscale.detach().reshape(()),
+                                                    model.kernel_1.outputscale.detach().reshape(()))) < 1e-12
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.3)
+    qd = model.q_v_dense()
+    qm = model.q_v()                       # structured marginals (band formulas) of the same q(u)
+    assert relerr(qd.mean, qm.mean) < 1e-9 and relerr(qd.variance, qm.variance) < 1e-8
+    pv = model.p_v_u()
+    assert relerr(pv.mean, qd.mean) < 1e-12 and (torch.diagonal(pv.covariance_matrix) <= qd.variance + 1e-12).all()
+    # optimal q(u): the reference's formulas through Sigma^-1
+    qo = model.q_v_dense(optimal=True)
+    Kuu, Kvu, Kvv = model._Kuu(), model._Kvu(), model._Kvv()
+    Kuf = model._Kuf(X).to(torch.float64)
+    noise = model.likelihood.noise.detach().reshape(())
+    Sig = Kuu + Kuf @ Kuf.T / noise
+    mean_ref = Kvu @ torch.linalg.solve(Sig, Kuf @ y) / noise
+    cov_ref = Kvv - Kvu @ torch.linalg.solve(Kuu, Kvu.T) + Kvu @ torch.linalg.solve(Sig, Kvu.T)
+    assert relerr(qo.mean, mean_ref) < 1e-7 and relerr(qo.covariance_matrix, cov_ref) < 1e-6
+    # 1-D twin
+    x1 = torch.rand(200, generator=g, dtype=torch.float64) * 2
+    y1 = torch.sin(x1) + 0.05 * torch.randn(200, generator=g, dtype=torch.float64)
+    m1 = gus.GriddedMatern12ASVGP(x1, y1, 8, 3, (0., 2.)).to(torch.float64)
+    Kvu1 = m1._Kvu()
+    assert Kvu1.shape == (8, m1.b1_basis_1.n_basis_functions)
+    d1 = m1.b1_basis_1.delta.to(torch.float64)
+    assert torch.allclose(Kvu1.sum(1), 4 * d1.expand(8))        # delta/2 + 3 delta + delta/2 = the cell width
+    q1 = m1.q_v(optimal=True)
+    Kuu1, Kuf1 = m1._Kuu(), m1._Kuf(x1.reshape(-1, 1)).to(torch.float64)
+    n1 = m1.likelihood.noise.detach().reshape(())
+    Sig1 = Kuu1 + Kuf1 @ Kuf1.T / n1
+    assert relerr(q1.mean, Kvu1 @ torch.linalg.solve(Sig1, Kuf1 @ y1) / n1) < 1e-7
+    cov1 = m1._Kvv() - Kvu1 @ torch.linalg.solve(Kuu1, Kvu1.T) + Kvu1 @ torch.linalg.solve(Sig1, Kvu1.T)
+    assert relerr(q1.covariance_matrix, cov1) < 1e-6

@@ -175,14 +175,118 @@ class GriddedVariationalGP(nn.Module):
         return self._terms
 
     # ---- variational distribution ---------------------------------------------------------------------------
-    def q_u(self) -> GriddedNormal:
-        """q(u) = N(m, kron_d L_d L_d^T): the *learned* variational distribution.  (The reference's q_u() returns
-        the analytically optimal one, gridded_kronecker_structure.py:903-916; the two agree at the optimum.)"""
+    def q_u(self, optimal: bool = False):
+        """q(u).  Default: the *learned* variational distribution N(m, kron_d L_d L_d^T) (GriddedNormal).  `optimal=True`:
+        the reference's closed form (its `q_u()`, gridded_kronecker_structure.py:903-916), dense -- see `q_u_optimal`.
+        The two agree where the learned q(u) has converged (tests/test_oracle_identities.py)."""
+        if optimal:
+            return self.q_u_optimal()
         Ss = []
         for L in self._chols():
             Lt = torch.tril(L.detach())
             Ss.append(Lt @ Lt.T)
         return GriddedNormal(self.variational_mean.detach(), Ss)
+
+    # ---- the reference's closed-form (collapsed) quantities: dense M x M algebra, small problems only -------------
+    DENSE_LIMIT = 4096          # largest M for which dense M x M matrices are formed (128 MiB in float64)
+
+    def _dense_guard(self, what: str) -> None:
+        if self.M > self.DENSE_LIMIT:
+            raise RuntimeError(f"{what} forms dense {self.M} x {self.M} matrices (the reference's algorithm); it is offered up to "
+                               f"M = {self.DENSE_LIMIT}.  Use the structured path instead: _elbo(), q_u(), posterior(), q_v()")
+
+    def _X2d(self) -> torch.Tensor:
+        X = self.train_inputs[0]
+        return X.reshape(X.shape[0], -1) if X.dim() > 1 else X.reshape(-1, 1)
+
+    def _gram_and_moment(self, chunk: int = 1 << 16):
+        """A = Kuf Kuf^T (M x M) and b = Kuf y (M), accumulated over chunks of observations (Kuf itself is M x N)."""
+        plan = self._ensure_plan()
+        X, y = self._X2d(), self.train_targets.reshape(-1)
+        A = torch.zeros(self.M, self.M, dtype=torch.float64, device=plan.device)
+        b = torch.zeros(self.M, dtype=torch.float64, device=plan.device)
+        for lo in range(0, X.shape[0], chunk):
+            Kuf = self._Kuf(X[lo:lo + chunk]).to(torch.float64)
+            A += Kuf @ Kuf.T
+            b += Kuf @ y[lo:lo + chunk].to(device=plan.device, dtype=torch.float64)
+        return A, b
+
+    def _sigma(self) -> torch.Tensor:
+        """Sigma = Kuu + Kuf Kuf^T / noise (kronecker_structure.py:134-150, univariate_structure.py:104-120), dense."""
+        self._dense_guard("_sigma()")
+        A, _ = self._gram_and_moment()
+        noise = self.likelihood.noise.detach().to(torch.float64).reshape(()).to(A.device)
+        return self._Kuu() + A / noise
+
+    def q_u_optimal(self) -> DenseNormal:
+        """The analytically optimal q(u) = N(m*, S*) of the collapsed bound, as the reference's `q_u()` / `q_v()` return it
+        (gridded_kronecker_structure.py:903-916, 1409-1433; univariate_structure.py:693-717):
+            m* = Kuu Sigma^-1 Kuf y / noise,   S* = Kuu Sigma^-1 Kuu   (symmetrised)
+        Raises torch.linalg.LinAlgError if Sigma is not positive definite, like the reference's Cholesky."""
+        self._dense_guard("q_u_optimal()")
+        A, b = self._gram_and_moment()
+        noise = self.likelihood.noise.detach().to(torch.float64).reshape(()).to(A.device)
+        Kuu = self._Kuu()
+        Ls = torch.linalg.cholesky(Kuu + A / noise)
+        mean = Kuu @ torch.cholesky_solve(b.unsqueeze(-1), Ls).squeeze(-1) / noise
+        cov = Kuu @ torch.cholesky_solve(Kuu, Ls)
+        return DenseNormal(mean, 0.5 * (cov + cov.T))
+
+    @torch.no_grad()
+    def set_optimal_q(self) -> None:
+        """Load the reference's closed-form q(u) into the variational parameters: m <- m*, and L_d <- Cholesky factors of
+        the Kronecker product nearest to S* in the Frobenius norm (Van Loan & Pitsianis; exact for D = 1, where the
+        uncollapsed bound then equals the reference's collapsed `_elbo()`).  D <= 2."""
+        if self.D > 2:
+            raise NotImplementedError("set_optimal_q() is offered for D <= 2, the dimensions the reference has")
+        q = self.q_u_optimal()
+        self.variational_mean.copy_(q.mean.to(self.variational_mean.dtype))
+        S = q.covariance_matrix
+        if self.D == 1:
+            factors = [S]
+        else:
+            n1, n2 = self.m_per_dim
+            R = S.reshape(n1, n2, n1, n2).permute(0, 2, 1, 3).reshape(n1 * n1, n2 * n2)
+            v = torch.eye(n2, dtype=S.dtype, device=S.device).reshape(-1)
+            for _ in range(30):                  # power iteration for the leading singular pair of the rearrangement
+                u = R @ v
+                u = u / u.norm()
+                v = R.T @ u
+                sig = v.norm()
+                v = v / sig
+            S1, S2 = u.reshape(n1, n1), v.reshape(n2, n2)
+            if torch.trace(S1) < 0:
+                S1, S2 = -S1, -S2
+            S1 = 0.5 * (S1 + S1.T) * sig.sqrt()
+            S2 = 0.5 * (S2 + S2.T) * sig.sqrt()
+            factors = [S1, S2]
+        for name, Sd in zip(self._chol_names, factors):
+            getattr(self, name).copy_(torch.linalg.cholesky(Sd).to(getattr(self, name).dtype))
+
+    def prior(self, x: torch.Tensor) -> DenseNormal:
+        """GP prior over f(x): zero mean, product Matern-1/2 kernel (kronecker_structure.py:90-104); dense N* x N*."""
+        x = x.reshape(x.shape[0], -1) if x.dim() > 1 else x.reshape(-1, 1)
+        ls, os_, _ = self._hyper()
+        K = torch.ones(x.shape[0], x.shape[0], dtype=x.dtype, device=x.device)
+        for d in range(self.D):
+            dist = (x[:, d, None] - x[None, :, d]).abs()
+            K = K * (os_[d].detach().to(x) * torch.exp(-dist / ls[d].detach().to(x)))
+        return DenseNormal(torch.zeros(x.shape[0], dtype=x.dtype, device=x.device), K)
+
+    def posterior_dense(self, x: torch.Tensor, optimal: bool = False) -> DenseNormal:
+        """q(f(x*)) with its full N* x N* covariance (kronecker_structure.py:199-230), small problems only:
+            mean = Kuf*^T Kuu^-1 m,   cov = K** - Kuf*^T Kuu^-1 Kuf* + Kuf*^T Kuu^-1 S Kuu^-1 Kuf*
+        with (m, S) the learned q(u), or the reference's optimal one (`optimal=True`, its Sigma^-1 form)."""
+        self._dense_guard("posterior_dense()")
+        q = self.q_u_optimal() if optimal else self.q_u()
+        Kuu = self._Kuu()
+        Ks = self._Kuf(x).to(torch.float64)
+        Lk = torch.linalg.cholesky(Kuu)
+        B = torch.cholesky_solve(Ks, Lk)                                  # Kuu^-1 Kuf*
+        S = q.covariance_matrix.to(torch.float64)
+        mean = B.T @ q.mean.to(torch.float64)
+        cov = self.prior(x.to(device=Kuu.device, dtype=torch.float64)).covariance_matrix - Ks.T @ B + B.T @ S @ B
+        return DenseNormal(mean, cov)
 
     # ---- predictions (kronecker_structure.py:199-247, marginals only) --------------------------------------------
     def posterior(self, x: torch.Tensor) -> GriddedMarginals:
@@ -255,6 +359,22 @@ class GriddedVariationalGP(nn.Module):
             k.base_kernel.lengthscale = X[:, d].std() / lmbda
         mean_os = sum(k.outputscale for k in self._kernels) / len(self._kernels)
         self.likelihood.noise = y.var() - mean_os
+
+
+def b0_cell_cov(delta32: torch.Tensor, m: int, lengthscale: torch.Tensor, outputscale: torch.Tensor) -> torch.Tensor:
+    """Cov[v_i, v_j] of the B0 cell integrals of a Matern-1/2 process: the Toeplitz matrix of `_Kvv_along_dim`
+    (gridded_kronecker_structure.py:847-885; gridded_univariate_structure.py:612-646), float64, with the reference's
+    float32 rounding of (k +- 1) * delta (int64 tensor times 0-dim float32)."""
+    k = torch.arange(m)
+    d32 = delta32.detach().to("cpu", torch.float32)
+    l = lengthscale.detach().to("cpu", torch.float64).reshape(())
+    s2 = outputscale.detach().to("cpu", torch.float64).reshape(())
+    km, kp, k0 = ((k - 1) * d32).to(torch.float64), ((k + 1) * d32).to(torch.float64), (k * d32).to(torch.float64)
+    row = torch.exp(-km / l) + torch.exp(-kp / l) - 2 * torch.exp(-k0 / l)
+    dl = d32.to(torch.float64) / l
+    row[0] = 2 * (torch.exp(-dl) + dl - 1)
+    idx = (k[:, None] - k[None, :]).abs()
+    return row[idx] * (l * l * s2)
 
 
 def linspace_mesh(lims, n_knots: int) -> torch.Tensor:

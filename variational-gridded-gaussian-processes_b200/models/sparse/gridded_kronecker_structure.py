@@ -5,7 +5,7 @@ import torch
 
 from ... import _lib
 from ...basis import B0SplineBasis, B1SplineBasis
-from .._gridded import GriddedVariationalGP, linspace_mesh, padded_b0_mesh
+from .._gridded import GriddedVariationalGP, b0_cell_cov, linspace_mesh, padded_b0_mesh
 from .kronecker_structure import KroneckerStructure
 
 
@@ -28,6 +28,56 @@ class GriddedMatern12ASVGP(KroneckerStructure):
         self.b0_basis_1, self.b0_basis_2 = B0SplineBasis(b0_1), B0SplineBasis(b0_2)
         self.b1_basis_1, self.b1_basis_2 = B1SplineBasis(pad_1), B1SplineBasis(pad_2)
 
+
+    # ---- dense pieces of the gridded part, as the reference builds them (small problems) ------------------------
+    def _Kvu_along_dim(self, dim: int) -> torch.Tensor:
+        """Rows [delta, delta] on the two knots of each B0 cell (gridded_kronecker_structure.py:831-839; the reference's
+        values are kept)."""
+        basis = (self.b1_basis_1, self.b1_basis_2)[dim]
+        delta = basis.delta.to(torch.float64)
+        nb, pad, nk = self.n_b0_splines, self.padding_factor, basis.n_basis_functions
+        Kvu = torch.zeros(nb, nk, dtype=torch.float64)
+        i = torch.arange(nb)
+        Kvu[i, pad + i] = delta
+        Kvu[i, pad + i + 1] = delta
+        return Kvu
+
+    def _Kvu(self) -> torch.Tensor:
+        """torch.kron(Kvu_1, Kvu_2) (:841-845)."""
+        dev = self.variational_mean.device
+        return torch.kron(self._Kvu_along_dim(0), self._Kvu_along_dim(1)).to(dev)
+
+    def _Kvv_along_dim(self, dim: int) -> torch.Tensor:
+        """Toeplitz covariance of the cell integrals along one dimension (:847-885)."""
+        k = self._kernels[dim]
+        return b0_cell_cov((self.b0_delta_1, self.b0_delta_2)[dim], self.n_b0_splines, k.base_kernel.lengthscale, k.outputscale)
+
+    def _Kvv(self) -> torch.Tensor:
+        """torch.kron(Kvv_1, Kvv_2) (:887-901)."""
+        dev = self.variational_mean.device
+        return torch.kron(self._Kvv_along_dim(0), self._Kvv_along_dim(1)).to(dev)
+
+    def p_v_u(self, optimal: bool = False):
+        """p(v | u = E_q[u]) (:918-928): mean = Kvu Kuu^-1 m, cov = Kvv - Kvu Kuu^-1 Kuv; dense."""
+        from ...params import DenseNormal
+        self._dense_guard("p_v_u()")
+        Kuu, Kvu = self._Kuu(), self._Kvu()
+        Lk = torch.linalg.cholesky(Kuu)
+        B = torch.cholesky_solve(Kvu.T.contiguous(), Lk)                   # Kuu^-1 Kuv
+        mean_u = (self.q_u_optimal() if optimal else self.q_u()).mean.to(torch.float64)
+        return DenseNormal(B.T @ mean_u, self._Kvv() - Kvu @ B)
+
+    def q_v_dense(self, optimal: bool = False):
+        """q(v) with its full covariance (:930-947): mean = Kvu Kuu^-1 m, cov = Kvv - Kvu Kuu^-1 Kuv + Kvu Kuu^-1 S Kuu^-1 Kuv
+        (the reference writes S^-1 in the last term, its 1-D twin Sigma^-1 = Kuu^-1 S* Kuu^-1: the latter is implemented)."""
+        from ...params import DenseNormal
+        self._dense_guard("q_v_dense()")
+        q = self.q_u_optimal() if optimal else self.q_u()
+        Kuu, Kvu = self._Kuu(), self._Kvu()
+        Lk = torch.linalg.cholesky(Kuu)
+        B = torch.cholesky_solve(Kvu.T.contiguous(), Lk)
+        S = q.covariance_matrix.to(torch.float64)
+        return DenseNormal(B.T @ q.mean.to(torch.float64), self._Kvv() - Kvu @ B + B.T @ S @ B)
 
     def q_v(self):
         """q(v) for the B0 cell integrals v_c = int_cell f (gridded_kronecker_structure.py:831-947), marginals only:
@@ -84,6 +134,7 @@ class Matern12GriddedGP(KroneckerStructure):
         self.delta_2 = mesh_2[1] - mesh_2[0]
         self.basis_1, self.basis_2 = B0SplineBasis(mesh_1), B0SplineBasis(mesh_2)
 
-    def q_v(self):
-        """For this model the inducing variables are the gridded cell integrals: q(v) is q(u) (:1409-1433)."""
-        return self.q_u()
+    def q_v(self, optimal: bool = False):
+        """For this model the inducing variables are the gridded cell integrals: q(v) is q(u) (:1409-1433) -- the learned
+        one, or with `optimal=True` the reference's closed form."""
+        return self.q_u(optimal)

@@ -44,3 +44,8 @@ class Matern12B0SplineGriddedGP(_TwoDimMesh):
         super().__init__(X, y, nknots, dim1lims, dim2lims)
         self.basis_1 = B0SplineBasis(self.mesh_1)
         self.basis_2 = B0SplineBasis(self.mesh_2)
+
+    def q_v(self, optimal: bool = False):
+        """q(v) = q(u): the inducing variables are the cell integrals (kronecker_structure.py:825-849 returns the
+        closed-form optimum: `optimal=True`; default: the learned q(u))."""
+        return self.q_u(optimal)
