@@ -38,14 +38,31 @@ KNOTS = (512, 512)
 PASSES = 1024          # ascending passes; as many descending ones (SURVEY.md section 8d, config 3 geometry)
 TRACK_GRADIENT = 2.0
 
+# The headline line is `tracks512` (BASELINE.json configs[4], the configuration the metric is quoted on).  The other
+# workloads are the remaining GPU configurations of BASELINE.json, run with --workload for the profiles / DESIGN.md tables.
+WORKLOADS = {
+    "tracks512": {"family": "B1_ASVGP", "knots": (512, 512), "n_total": 1 << 26,
+                  "desc": "configs[4]: 2-D B1-spline ASVGP, 512x512 inducing grid, N=2^26 synthetic along-track "
+                          "observations (acquisition order), fp32 observations / fp64 grid side, full batch"},
+    "b1_cfg3": {"family": "B1_ASVGP", "knots": (512, 512), "n_total": 1 << 24,
+                "desc": "configs[2]: 2-D B1-spline ASVGP (GriddedMatern12ASVGP), 512x512 grid, N=2^24 along-track observations, fp32"},
+    "b0_cfg3": {"family": "B0_GRIDDED", "knots": (512, 512), "n_total": 1 << 24,
+                "desc": "configs[2]: 2-D cell-integrated Matern-1/2 features (Matern12GriddedGP), 511x511 cells, N=2^24 "
+                        "along-track observations, fp32 observations / fp64 grid side, scan form of the features"},
+    "3d": {"family": "B1_ASVGP", "knots": (256, 256, 64), "n_total": 1 << 26,
+           "desc": "configs[3]: 3-D (lon, lat, time) B1-spline ASVGP, 256x256x64 inducing grid, N=2^26 along-track observations "
+                   "with time increasing along the acquisition order, fp32 observations / fp64 grid side"},
+}
 
-def workload_config(n_total, world, extra=None):
+
+def workload_config(n_total, world, extra=None, workload="tracks512"):
+    w = WORKLOADS[workload]
+    D = len(w["knots"])
     cfg = {
-        "workload": "configs[4]: 2-D B1-spline ASVGP, 512x512 inducing grid, N=2^26 synthetic along-track "
-                    "observations (acquisition order), fp32 observations / fp64 grid side, full batch",
-        "n_obs_total": n_total, "grid": list(KNOTS), "family": "B1_ASVGP", "obs_dtype": "float32",
+        "workload": w["desc"], "workload_key": workload,
+        "n_obs_total": n_total, "grid": list(w["knots"]), "family": w["family"], "obs_dtype": "float32",
         "sharding": f"observation axis, {world} contiguous shard(s), one all-reduce(sum) of the gradient buffer",
-        "l2_policy": "inputs larger than L2 (805 MB of observations per step vs 126 MB L2); no explicit flush",
+        "l2_policy": f"inputs larger than L2 ({n_total * (D + 1) * 4 / 1e6:.0f} MB of observations per step vs 126 MB L2); no explicit flush",
     }
     if extra:
         cfg.update(extra)
@@ -72,8 +89,10 @@ def _hash_uniform(idx, salt):
     return ((h >> 11) & ((1 << 40) - 1)).to(torch.float64) / float(1 << 40)
 
 
-def make_tracks(lo, hi, n_total, device, dtype, seed=0):
-    """Observations lo..hi-1 (global acquisition order) of the synthetic track data set."""
+def make_tracks(lo, hi, n_total, device, dtype, seed=0, D=2):
+    """Observations lo..hi-1 (global acquisition order) of the synthetic track data set.  D = 3 adds the acquisition time
+    as third coordinate (monotone along the concatenated passes) and a slow drift of the
+    field in time."""
     idx = torch.arange(lo, hi, device=device, dtype=torch.int64)
     per_pass = max(1, n_total // (2 * PASSES))
     j = torch.clamp(idx // per_pass, max=2 * PASSES - 1)
@@ -88,6 +107,10 @@ def make_tracks(lo, hi, n_total, device, dtype, seed=0):
     # noise: sum of 4 uniforms (Irwin-Hall), variance 4/12 -> scaled to sigma = 0.05
     u = sum(_hash_uniform(idx, 2 * seed + 10 + q) for q in range(4)) - 2.0
     y = field(x1, x2) + 0.05 * math.sqrt(3.0) * u
+    if D == 3:
+        x3 = ((idx.to(torch.float64) + _hash_uniform(idx, 2 * seed + 31)) / float(n_total)).clamp_(0.0, 1.0)
+        y = y + 0.3 * torch.sin(4.0 * x3) * torch.cos(3.0 * x1)
+        return [x1.to(dtype).contiguous(), x2.to(dtype).contiguous(), x3.to(dtype).contiguous()], y.to(dtype).contiguous()
     return [x1.to(dtype).contiguous(), x2.to(dtype).contiguous()], y.to(dtype).contiguous()
 
 
@@ -111,9 +134,21 @@ def b1_factor(mesh, l, s2):
     return (A * l + B / l + BC) / (2.0 * s2)
 
 
-def make_params(meshes, device, seed=1):
+def b0_factor(mesh, l, s2):
+    """Cov of the B0 cell integrals of a Matern-1/2 process along one dimension (gridded_kronecker_structure.py:1286-1323),
+    float64 throughout (only used to place the variational parameters of the bench)."""
+    m = mesh.numel() - 1
+    d = (mesh[1] - mesh[0]).to(torch.float64)
+    k = torch.arange(m, dtype=torch.float64)
+    row = torch.exp(-(k - 1) * d / l) + torch.exp(-(k + 1) * d / l) - 2 * torch.exp(-k * d / l)
+    row[0] = 2 * (torch.exp(-d / l) + d / l - 1)
+    i = torch.arange(m)
+    return row[(i[:, None] - i[None, :]).abs()] * (l * l * s2)
+
+
+def make_params(meshes, device, seed=1, family="B1_ASVGP"):
     """A sensible point of the optimisation: theta as non_informative_initialise(lmbda=5, kappa=10) would set it,
-    m = Kuu f0 (so that the predictive mean interpolates the field f0 at the knots) plus noise, and
+    m = Kuu f0 (so that the predictive mean interpolates the field f0 at the knots / cell centres) plus noise, and
     L_d = chol(K_d) (I/2 + small random lower-triangular matrix) (q(u) between prior and posterior)."""
     g = torch.Generator().manual_seed(seed)
     D = len(meshes)
@@ -121,9 +156,14 @@ def make_params(meshes, device, seed=1):
     s2 = torch.full((D,), 1.2, dtype=torch.float64)
     noise = torch.tensor([1.2 / 100.0], dtype=torch.float64)
     theta = torch.cat([l, s2, noise])
-    Ks = [b1_factor(meshes[d], l[d], s2[d]) for d in range(D)]
-    grids = torch.meshgrid(*[m.to(torch.float64) for m in meshes], indexing="ij")
-    f0 = field(grids[0], grids[-1])          # smooth: its RKHS norm (the <m, alpha> term of the KL) stays moderate
+    if family == "B1_ASVGP":
+        Ks = [b1_factor(meshes[d], l[d], s2[d]) for d in range(D)]
+        pts = [m.to(torch.float64) for m in meshes]
+    else:
+        Ks = [b0_factor(meshes[d], l[d], s2[d]) for d in range(D)]
+        pts = [0.5 * (m[1:] + m[:-1]).to(torch.float64) for m in meshes]
+    grids = torch.meshgrid(*pts, indexing="ij")
+    f0 = field(grids[0], grids[1] if D > 1 else grids[0])     # smooth: its RKHS norm (the <m, alpha> term of the KL) stays moderate
     mt = f0
     for d in range(D):
         mt = torch.movedim(torch.tensordot(Ks[d], mt, dims=([1], [d])), 0, d)
@@ -236,14 +276,16 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's structured ELBO (float32 per-observation arithmetic) + autograd on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_step_fn(n_sample, seed=0):
+def cpu_oracle_step_fn(n_sample, seed=0, workload="tracks512"):
     from oracle import vggp_oracle as O
-    meshes = [torch.linspace(0, 1, k) for k in KNOTS]
-    xs, y = make_tracks(0, n_sample, n_sample, torch.device("cpu"), torch.float32, seed)
+    w = WORKLOADS[workload]
+    meshes = [torch.linspace(0, 1, k) for k in w["knots"]]
+    D = len(meshes)
+    xs, y = make_tracks(0, n_sample, n_sample, torch.device("cpu"), torch.float32, seed, D=D)
     X = torch.stack(xs, dim=1).to(torch.float64)
     y = y.to(torch.float64)
-    theta, m, Ls = make_params(meshes, "cpu")
-    D = len(meshes)
+    theta, m, Ls = make_params(meshes, "cpu", family=w["family"])
+    ofam = O.B1_ASVGP if w["family"] == "B1_ASVGP" else O.B0_GRIDDED
 
     def step():
         l = theta[:D].clone().requires_grad_(True)
@@ -251,7 +293,7 @@ def cpu_oracle_step_fn(n_sample, seed=0):
         nz = theta[2 * D].clone().requires_grad_(True)
         mm = m.clone().requires_grad_(True)
         LL = [L.clone().requires_grad_(True) for L in Ls]
-        elbo = O.elbo_structured(O.B1_ASVGP, meshes, X, y, l, s2, nz, mm, LL, ref_quirks=False,
+        elbo = O.elbo_structured(ofam, meshes, X, y, l, s2, nz, mm, LL, ref_quirks=False,
                                  work_dtype=torch.float32)
         torch.autograd.grad(elbo, [l, s2, nz, mm] + LL)
         return float(elbo.detach())
@@ -259,11 +301,16 @@ def cpu_oracle_step_fn(n_sample, seed=0):
     return step
 
 
-def time_cpu_baseline(budget_s=20.0, steps=3, warmup=1, n_cap=1 << 22):
+def _calib_n(workload):
+    """First sample size of the CPU legs: the dense-feature (B0) oracle costs O(N M_d^2), the stencil one O(N)."""
+    return 1 << (12 if WORKLOADS[workload]["family"] != "B1_ASVGP" else 17)
+
+
+def time_cpu_baseline(budget_s=20.0, steps=3, warmup=1, n_cap=1 << 22, workload="tracks512"):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = 1 << 17
-    step = cpu_oracle_step_fn(n)
+    n = _calib_n(workload)
+    step = cpu_oracle_step_fn(n, workload=workload)
     step()
     t0 = time.perf_counter()
     step()
@@ -272,15 +319,16 @@ def time_cpu_baseline(budget_s=20.0, steps=3, warmup=1, n_cap=1 << 22):
     scale = max(1.0, budget_s / max(dt * (steps + warmup), 1e-3))
     n_sample = int(min(n_cap, max(n, (1 << int(math.log2(n * scale))))))
     if n_sample != n:
-        step = cpu_oracle_step_fn(n_sample)
+        step = cpu_oracle_step_fn(n_sample, workload=workload)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
+    grid = "x".join(str(k) for k in WORKLOADS[workload]["knots"])
     return {"value": n_sample / dt, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
-            "sample": f"{n_sample} observations of the same track workload on the full 512x512 grid, fp32 "
+            "sample": f"{n_sample} observations of the same track workload on the full {grid} grid, fp32 "
                       f"per-observation arithmetic, {steps} timed fwd+bwd steps after {warmup} warm-up "
                       f"({dt * 1e3:.1f} ms/step), torch CPU + autograd",
             "ms_per_step": dt * 1e3, "n_sample": n_sample}
@@ -291,9 +339,10 @@ def run_reference_arm(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: calibrate on 2^17 observations, then size the sample so the whole run ends in ~2 minutes
-    n = 1 << 17
-    step = cpu_oracle_step_fn(n)
+    # bounded sample: calibrate on a small sample, then size the sample so the whole run ends in ~2 minutes
+    workload = args.workload
+    n = _calib_n(workload)
+    step = cpu_oracle_step_fn(n, workload=workload)
     step()
     t0 = time.perf_counter()
     step()
@@ -302,7 +351,7 @@ def run_reference_arm(args, rank, world):
     scale = max(1.0, 120.0 / max(dt * total, 1e-3))
     n_sample = int(min(1 << 22, max(n, 1 << int(math.log2(n * scale)))))
     if n_sample != n:
-        step = cpu_oracle_step_fn(n_sample)
+        step = cpu_oracle_step_fn(n_sample, workload=workload)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -314,10 +363,10 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(N_TOTAL, world, {"cpu_sample_obs": n_sample}),
+        "config": workload_config(WORKLOADS[workload]["n_total"], world, {"cpu_sample_obs": n_sample}, workload),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
-                         "sample": f"{n_sample} observations per step (bounded sample of the 2^26 workload), full "
-                                   f"512x512 grid, structured torch-CPU restatement of the reference maths + autograd"},
+                         "sample": f"{n_sample} observations per step (bounded sample of the workload), full "
+                                   f"grid, structured torch-CPU restatement of the reference maths + autograd"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -331,7 +380,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n-obs", type=int, default=N_TOTAL, help="total observations over all ranks (default 2^26)")
+    ap.add_argument("--workload", default="tracks512", choices=sorted(WORKLOADS),
+                    help="tracks512 = BASELINE.json configs[4] (the headline); b1_cfg3 / b0_cfg3 = configs[2]; 3d = configs[3]")
+    ap.add_argument("--n-obs", type=int, default=None, help="total observations over all ranks (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--obs-layout", default="binned", choices=["packed", "binned"],
@@ -368,13 +419,18 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     lib = vg._lib.load()
 
-    n_total = int(args.n_obs)
+    wl = WORKLOADS[args.workload]
+    knots, fam_name = wl["knots"], wl["family"]
+    n_total = int(args.n_obs) if args.n_obs else wl["n_total"]
     lo, hi = vg.shard_bounds(n_total, rank, world)
     n_local = hi - lo
     dtype = torch.float32
-    meshes = [torch.linspace(0, 1, k) for k in KNOTS]
-    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, device)
-    xs, y = make_tracks(lo, hi, n_total, device, dtype)
+    meshes = [torch.linspace(0, 1, k) for k in knots]
+    is_b1 = fam_name == "B1_ASVGP"
+    if not is_b1:
+        args.obs_layout = "binned"          # the B0 family streams per-cell runs too (scan form); there is no packed layout for it
+    plan = vg.GridPlan(vg.B1_ASVGP if is_b1 else vg.B0_GRIDDED, meshes, dtype, device)
+    xs, y = make_tracks(lo, hi, n_total, device, dtype, D=len(knots))
     sharding = "contiguous in acquisition order"
     if world > 1 and args.spatial_reshard:
         # one-time setup exchange: every rank ends up owning a contiguous range of grid cells (dist.spatial_reshard)
@@ -394,7 +450,7 @@ def main():
         packed = plan.pack(xs, y, sort_by_cell=True)
     torch.cuda.synchronize()
     setup_ms = (time.perf_counter() - t0) * 1e3
-    theta, m, Ls = make_params(meshes, device)
+    theta, m, Ls = make_params(meshes, device, family=fam_name)
     theta_d = theta.to(device)
     m_d = m.to(device)
     L_d = torch.cat([L.reshape(-1) for L in Ls]).to(device).contiguous()
@@ -492,23 +548,26 @@ def main():
     k1_call_ms = tt[2].item()
     value = n_total / (ms_step * 1e-3)
 
-    # ---- secondary leg: same step on observations left in acquisition (along-track) order
-    packed_acq = plan.pack(xs, y, sort_by_cell=False)
-    for _ in range(2):
-        step(None, packed_acq)
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    acq_steps = max(3, min(args.steps, 10))
-    a0.record()
-    for _ in range(acq_steps):
-        step(None, packed_acq)
-    a1.record()
-    barrier()
-    ta = torch.tensor([a0.elapsed_time(a1) / acq_steps], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-    acq_ms = ta.item()
-    del packed_acq
+    # ---- secondary leg: same step on observations left in acquisition (along-track) order (B1 family: the packed kernel
+    # takes any order; the B0 scan form needs per-cell runs)
+    acq_ms = None
+    if is_b1:
+        packed_acq = plan.pack(xs, y, sort_by_cell=False)
+        for _ in range(2):
+            step(None, packed_acq)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acq_steps = max(3, min(args.steps, 10))
+        a0.record()
+        for _ in range(acq_steps):
+            step(None, packed_acq)
+        a1.record()
+        barrier()
+        ta = torch.tensor([a0.elapsed_time(a1) / acq_steps], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        acq_ms = ta.item()
+        del packed_acq
 
     # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of its results inside the timed region
     e2e = None
@@ -527,7 +586,20 @@ def main():
         stream = torch.cuda.current_stream(device).cuda_stream
 
         def e2e_step():
-            if world == 1:
+            if not is_b1:
+                # B0 family: host observations -> device, per-cell runs (sort + gather: the scan form needs them), step
+                for dst, src in zip(xs + [y], xs_h + [y_h]):
+                    dst.copy_(src, non_blocking=True)
+                theta_d.copy_(th_h, non_blocking=True)
+                m_d.copy_(m_h, non_blocking=True)
+                L_d.copy_(L_h, non_blocking=True)
+                o, dth, dm, dL = step(None, plan.bin(xs, y, run_cap=args.run_cap))
+                out_h.copy_(o, non_blocking=True)
+                dth_h.copy_(dth, non_blocking=True)
+                dm_h.copy_(dm, non_blocking=True)
+                dL_h.copy_(dL, non_blocking=True)
+                torch.cuda.synchronize()
+            elif world == 1:
                 ptrs = (C.c_void_p * D)(*[t.data_ptr() for t in xs_h])
                 vg._lib.check(lib.vggp_elbo_host(plan.handle, ptrs, y_h.data_ptr(), n_local, th_h.data_ptr(),
                                                  m_h.data_ptr(), L_h.data_ptr(), 1.0, out_h.data_ptr(),
@@ -559,12 +631,13 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
-               "path": "vggp_elbo_host (C ABI, pinned host buffers)" if world == 1 else
-                       "pinned host -> device copies + plan.step + device -> host of ELBO and gradients"}
+               "path": "vggp_elbo_host (C ABI, pinned host buffers)" if (world == 1 and is_b1) else
+                       "pinned host -> device copies" + ("" if is_b1 else " + vggp_obs_bin_* (per-cell runs)")
+                       + " + plan.step + device -> host of ELBO and gradients"}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg_bytes = n_local * (len(KNOTS) + 1) * 4 + 2 * plan.M * 4
+        alg_bytes = n_local * (len(knots) + 1) * 4 + 2 * plan.M * 4
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -582,13 +655,15 @@ def main():
                     "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
                               "setup; setup is outside the timed region"}),
                 "setup_ms": setup_ms, "cuda_graph": bool(args.cuda_graph),
-                "acquisition_order": {"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
-                                      "note": "same step without the cell binning (along-track order kept)"}}),
+                "acquisition_order": ({"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
+                                       "note": "same step without the cell binning (along-track order kept)"}
+                                      if acq_ms is not None else None)}, args.workload),
             "elbo": out[0][0].item(),
-            "roofline": {"bound": "hbm", "kernel": ("k_obs_b1" if args.obs_layout == "packed" else "k_obs_b1_binned")
-                         + " (fused per-observation ELBO forward+backward)",
+            "roofline": {"bound": "hbm", "kernel": (("k_obs_b1" if args.obs_layout == "packed" else "k_obs_b1_binned") if is_b1
+                                                    else "k_obs_b0s") + " (fused per-observation ELBO forward+backward)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (k1_traffic(args.obs_layout, args.run_cap) if (world == 1 and n_total == N_TOTAL) else None),
+                         "traffic": (k1_traffic(args.obs_layout, args.run_cap)
+                                     if (world == 1 and args.workload == "tracks512" and n_total == N_TOTAL) else None),
                          "peak_source": peak_src, "kernel_ms": k1_ms, "kernel_launches_timed": k1_launches,
                          "timing": "CUDA events recorded by the library immediately around the kernel launch, on the "
                                    "launching stream, inside the timed region (vggp_k1_timing)",
@@ -603,7 +678,7 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = time_cpu_baseline()
+            line["cpu_baseline"] = time_cpu_baseline(workload=args.workload)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

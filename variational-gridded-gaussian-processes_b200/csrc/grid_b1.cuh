@@ -10,10 +10,10 @@
 //                 5-step affine scan across lanes), and a kind-specific prologue / epilogue fuses what round 1 did in
 //                 separate elementwise kernels (tril mask, casts, <m, alpha>, g / ghat from the gradient buffer, band
 //                 scatter, dR from R, tril / diagonal terms of dL, band dot products for dK)
-//   k_b1_theta    band of dK_d -> d theta, ELBO scalars
+//   k_b1_theta    band of P_d X_d P_d by two first-order recurrences, band of dK_d -> d theta, ELBO scalars
 // A step is: gens, pass F1 (R_d = P_d tril L_d, first mode of alpha), pass F2 (last mode of alpha + casts + row reductions
-// of R_d), the per-observation kernel, pass B1 (last mode of (kron P) g, A_e, X_d P_d), pass B2 (first mode, dL, P X P),
-// theta: 6 launches for D = 2 (one more forward and backward pass for D = 3).
+// of R_d), the per-observation kernel, pass B1 (last mode of (kron P) g, A_e), pass B2 (first mode, dL), theta (which also
+// forms the band of P X P by O(n) recurrences): 6 launches for D = 2 (one more forward and backward pass for D = 3).
 // Maths: SURVEY.md appendix A; same formulas as the round-1 path (grid.cuh), which stays as the cross-check.
 #pragma once
 #include "grid.cuh"
@@ -33,11 +33,9 @@ enum FpKind {
     FP_GA,          // g = c galpha, ghat = g - m / 2 from the gradient buffer; V = g x_e P_e (or dm = V - alpha), A_e = ghat x_e P_e
                     // is only contracted: acc_e[i][i + dl] += sum_rest A_e[.. i ..] alpha[.. i + dl ..]
     FP_GAONLY,      // the A_e contraction alone (modes other than the one the dm chain starts with)
-    FP_YP,          // Y'_d = X_d P_d, X_d = tridiagonal band scatter of the per-observation sums bp (row k synthesised)
     FP_DM,          // dm = src x_e P_e - alpha
     FP_DL,          // column k of dR_d = 2 cQ tridiag(bq) R_d -> dLraw = P_d dR; dL = tril(dLraw - c_d R + (M/M_d) diag(1/L_ii));
                     // acc_d[i][i + dl] += dLraw[i][k] R[i + dl][k]
-    FP_Z,           // Z_d = P_d Y'_d, band only: acc_d[j + dl][j] += Z[j + dl][j]
     FP_QROW         // no product: row reductions of R_d (band of Q_d, tr(P_d S_d), log det S_d, Q-band tables)
 };
 
@@ -45,10 +43,10 @@ struct FpTask {
     int kind, d, n, F;            // d: dimension whose P_d is applied; n = M_d; F = fibres of one tile (in shared memory)
     i64 inner, nfib;              // fibre f = (o, r): element i at (o n + i) inner + r; nfib = outer * inner
     int tile0, ntiles;
-    const double* s0;             // PROD / ALPHA / DM: source tensor;  R / DL: L_d resp. R_d;  Z: Y'_d;  GA*: m
+    const double* s0;             // PROD / ALPHA / DM: source tensor;  R / DL: L_d resp. R_d;  GA*: m
     const double* s1;             // ALPHA: m;  GA / GAONLY / DM: alpha;  DL: L_d
-    double* o0;                   // PROD / ALPHA / R / YP: destination;  GA: V (or dm when `direct`);  DM: dm;  DL: dL
-    const void* t0;               // GA*: galpha;  YP / DL: band sums of dimension d [bp_d | bp_o | bq_d | bq_o] (obs dtype)
+    double* o0;                   // PROD / ALPHA / R: destination;  GA: V (or dm when `direct`);  DM: dm;  DL: dL
+    const void* t0;               // GA*: galpha;  DL: band sums of dimension d [bp_d | bp_o | bq_d | bq_o] (obs dtype)
     void* t1;                     // ALPHA: alpha in the observation dtype
     int direct;                   // GA with D == 1: o0 receives dm = V - alpha
 };
@@ -482,7 +480,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                              return (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0; },
                 [&](int e, double v) { int i, f; split_s(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
         } break;
-        case FP_PROD: case FP_ALPHA: case FP_DM: case FP_Z: {
+        case FP_PROD: case FP_ALPHA: case FP_DM: {
             const double* __restrict__ src = tk.s0;
             fp_batched<FP_U>(total,
                 [&](int e) { int i, f; split(e, i, f); return (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0; },
@@ -523,18 +521,6 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                         Cx[(size_t)f * q.pitch + p] = av[u];
                     }
                 }
-            }
-        } break;
-        case FP_YP: {
-            // row k of X_d = cP tridiag(bp_diag, bp_off): three non-zeros
-            const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
-            for (int e = tid; e < total; e += FP_THREADS) { int i, f; split_c(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = 0.0; }
-            __syncthreads();
-            if (tid < 3 * nf) {
-                const int f = tid / 3, dl = tid - 3 * f - 1;
-                const int k = (int)(fib0 + f), i = k + dl;
-                if (i >= 0 && i < n)
-                    X[(size_t)f * q.pitch + fp_pidx(i, SM)] = cP * (double)(dl == 0 ? bnd[k] : bnd[n + (dl < 0 ? i : k)]);
             }
         } break;
         case FP_DL: {
@@ -613,13 +599,6 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         case FP_GAONLY:
             fp_band_dots(q, X, Cx, 0, nf, P.acc[d]);
             break;
-        case FP_YP: {
-            double* __restrict__ Y = tk.o0;
-            for (int e = tid; e < total; e += FP_THREADS) {
-                int i, f; split_c(e, i, f);
-                if (f < nf) Y[(fib0 + f) * (i64)n + i] = X[(size_t)f * q.pitch + fp_pidx(i, SM)];
-            }
-        } break;
         case FP_DL: {
             double* __restrict__ dL = tk.o0;
             const double* __restrict__ L = tk.s1;
@@ -640,18 +619,6 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
                 dL[(i64)i * n + k] = v;
             }
             fp_band_dots(q, X, Cx, 0, nf, P.acc[d]);
-        } break;
-        case FP_Z: {
-            // column j of Z_d: only Z[j - 1 .. j + 1][j] is needed
-            double* __restrict__ acc = P.acc[d];
-            for (int e = tid; e < 3 * nf; e += FP_THREADS) {
-                const int f = e / 3, dl = e - f * 3 - 1;
-                const int j = (int)(fib0 + f);
-                const int i = j + dl;
-                if (i < 0 || i >= n) continue;
-                // W[i][j] with j = i - dl: slot (-dl + 1, i)
-                atomicAdd(acc + (1 - dl) * n + i, X[(size_t)f * q.pitch + fp_pidx(i, SM)]);
-            }
         } break;
         default: break;
     }
@@ -693,26 +660,89 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// d theta and the ELBO scalars from the band accumulators:
-//   dK_d[i][j] = -W_d[i][j] + (c_d / 2) Q_d[i][j] - (M / (2 M_d)) P_d[i][j]   on |i - j| <= 1   (K_d and dK_d / d theta are tridiagonal)
-// grid (D), 512 threads.
+// First-order linear recurrence t_i = b_i + a_i t_prev over i = 0 .. n-1 (ascending: t_prev = t_{i-1}; descending: t_{i+1}),
+// t_prev = 0 at the start, by ONE warp: lane-local sweeps + a 5-step affine scan across lanes.  a(i), b(i) are functors.
 // ---------------------------------------------------------------------------------------------------------
+template <bool ASC, typename FA, typename FB>
+__device__ __forceinline__ void warp_recurrence(int n, FA a, FB b, double* __restrict__ out, int lane) {
+    const int S = (n + 31) / 32;
+    // lane l owns [l S, (l + 1) S); for the descending sweep the lane order is reversed so that the scan still runs upwards
+    const int seg = ASC ? lane : 31 - lane;
+    const int i0 = seg * S, cnt = max(0, min(S, n - i0));
+    double A = 1.0, B = 0.0;
+    for (int j = 0; j < cnt; ++j) {
+        const int i = ASC ? i0 + j : i0 + cnt - 1 - j;
+        const double ai = a(i);
+        B = fma(ai, B, b(i));
+        A *= ai;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ap = __shfl_sync(0xffffffffu, A, (lane - o) & 31), Bp = __shfl_sync(0xffffffffu, B, (lane - o) & 31);
+        if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
+    }
+    double t = __shfl_sync(0xffffffffu, B, (lane - 1) & 31);
+    if (lane == 0) t = 0.0;
+    for (int j = 0; j < cnt; ++j) {
+        const int i = ASC ? i0 + j : i0 + cnt - 1 - j;
+        t = fma(a(i), t, b(i));
+        out[i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// d theta and the ELBO scalars.
+//   dK_d[i][j] = -W_d[i][j] + (c_d / 2) Q_d[i][j] - (M / (2 M_d)) P_d[i][j]   on |i - j| <= 1   (K_d and dK_d / d theta are tridiagonal)
+// W_d = band of P_d (dP_d) P_d.  Its Gram and dR L^T parts arrive in the accumulators `acc` (fibre passes); the part that
+// goes through the band scatter X_d = cP tridiag(bp_diag, bp_off) of the per-observation sums is formed here in O(n):
+// with P semiseparable, the quadratic forms of a row of P_d restricted to the indices >= i (T_i) and <= i (S_i) obey
+//   T_i = xd_i pd_i^2 + 2 xo_i pd_i P[i][i+1] + ru_i^2 T_{i+1},      S_i = xd_i pd_i^2 + 2 xo_{i-1} pd_i P[i][i-1] + rl_{i-1}^2 S_{i-1}
+//   (P X P)[i][i]   = T_i + rl_{i-1}^2 S_{i-1} + 2 xo_{i-1} P[i][i-1] pd_i
+//   (P X P)[i][i+1] = ru_i T_{i+1} + rl_i S_i + xo_i (pd_i pd_{i+1} + P[i][i+1]^2)
+// (round 1 formed X_d P_d and P_d (X_d P_d) as two n x n semiseparable products for these 3 n numbers).
+// grid (D), 512 threads, dynamic smem 2 n doubles.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
-                                                  const double* __restrict__ acc, const double* __restrict__ gscal,
+                                                  const double* __restrict__ acc, const T* __restrict__ gband,
+                                                  const double* __restrict__ gscal,
                                                   double ell_scale, double* __restrict__ out, double* __restrict__ dtheta) {
+    extern __shared__ double sm[];
     const int d = blockIdx.x;
     const int n = g.n[d];
     const int D = g.D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Tt = sm;
+    double* Ss = sm + n;
     const double half_ratio = 0.5 * (double)g.M / (double)n;
     const double half_c = 0.5 * tr_others(g, d);
     const double* __restrict__ gen = g.gen[d];
+    const double* __restrict__ pd = gen;
+    const double* __restrict__ ru = gen + n;
+    const double* __restrict__ rl = gen + 2 * n;
+    const T* __restrict__ bp = gband + g.band_off[d];           // [bp_diag | bp_off | bq_diag | bq_off]
+    const double cP = ell_scale / (2.0 * theta[2 * D]);
     for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
+    if (warp == 0) {
+        warp_recurrence<false>(n,
+            [&](int i) { return (i + 1 < n) ? ru[i] * ru[i] : 0.0; },
+            [&](int i) { const double x = cP * (double)bp[i] * pd[i] * pd[i];
+                         return (i + 1 < n) ? x + 2.0 * cP * (double)bp[n + i] * pd[i] * (ru[i] * pd[i + 1]) : x; },
+            Tt, lane);
+    } else if (warp == 1) {
+        warp_recurrence<true>(n,
+            [&](int i) { return (i > 0) ? rl[i - 1] * rl[i - 1] : 0.0; },
+            [&](int i) { const double x = cP * (double)bp[i] * pd[i] * pd[i];
+                         return (i > 0) ? x + 2.0 * cP * (double)bp[n + i - 1] * pd[i] * (rl[i - 1] * pd[i - 1]) : x; },
+            Ss, lane);
+    }
     // d K / d l and d K / d s2 take three distinct values each (corner diagonal, interior diagonal, off-diagonal)
     double gl[3], gs[3];
     factor_entry_grad(g, theta, d, 0, 0, gl[0], gs[0]);
     factor_entry_grad(g, theta, d, 1, 1, gl[1], gs[1]);
     factor_entry_grad(g, theta, d, 0, 1, gl[2], gs[2]);
     const double* __restrict__ Qb = g.Qb[d];
+    __syncthreads();
     double sl = 0.0, ss = 0.0;
 #pragma unroll 3
     for (int e = threadIdx.x; e < 3 * n; e += 512) {
@@ -721,10 +751,22 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
         const int j = i + dl;
         if (j < 0 || j >= n) continue;
         const int lo = i < j ? i : j;
-        const double qv = (dl == 0) ? Qb[i] : Qb[n + lo];
-        // P_d on the band from the generators: pd_i on the diagonal, pd_{lo+1} ru_lo above, pd_lo rl_lo below it
-        const double pij = (dl == 0) ? gen[i] : (dl > 0 ? gen[j] * gen[n + i] : gen[j] * gen[2 * n + j]);
-        const double v = -acc[e] + half_c * qv - half_ratio * pij;
+        double qv, pij, w;
+        if (dl == 0) {
+            qv = Qb[i];
+            pij = pd[i];
+            w = Tt[i];
+            if (i > 0) {
+                const double pl = rl[i - 1] * pd[i - 1];                       // P[i][i-1]
+                w += rl[i - 1] * rl[i - 1] * Ss[i - 1] + 2.0 * cP * (double)bp[n + i - 1] * pl * pd[i];
+            }
+        } else {
+            qv = Qb[n + lo];
+            const double pu = ru[lo] * pd[lo + 1];                             // P[lo][lo+1]
+            pij = pu;
+            w = ru[lo] * Tt[lo + 1] + rl[lo] * Ss[lo] + cP * (double)bp[n + lo] * (pd[lo] * pd[lo + 1] + pu * pu);
+        }
+        const double v = -(acc[e] + w) + half_c * qv - half_ratio * pij;
         const bool corner = (i == 0 || i == n - 1);
         sl = fma(v, (dl != 0) ? gl[2] : (corner ? gl[0] : gl[1]), sl);
         ss = fma(v, (dl != 0) ? gs[2] : (corner ? gs[0] : gs[1]), ss);
@@ -732,13 +774,11 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
     sl = warp_sum(sl);
     ss = warp_sum(ss);
     __shared__ double red2[2][16];
-    if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = sl; red2[1][threadIdx.x >> 5] = ss; }
+    if (lane == 0) { red2[0][warp] = sl; red2[1][warp] = ss; }
     __syncthreads();
     if (threadIdx.x == 0) {
         sl = 0.0; ss = 0.0;
         for (int w = 0; w < 16; ++w) { sl += red2[0][w]; ss += red2[1][w]; }
-    }
-    if (threadIdx.x == 0) {
         const double noise = theta[2 * D];
         double kff = 1.0;
         for (int e = 0; e < D; ++e) kff *= theta[D + e];

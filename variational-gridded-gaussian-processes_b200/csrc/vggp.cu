@@ -607,7 +607,7 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
     const double* gscal = reinterpret_cast<const double*>(gb + soff);
     auto band = [&](int d) { return (const void*)(gb + ((size_t)p->M + p->band_off[d]) * tsz); };
     FpPass P;
-    // pass 1 (last mode): V = g x P, A = ghat x P contracted with alpha; Y'_d = X_d P_d
+    // pass 1 (last mode): V = g x P, A = ghat x P contracted with alpha
     fp_pass_init(p, P, theta, ell_scale);
     {
         FpTask t = fp_mode_task(p, FP_GA, D - 1);
@@ -616,13 +616,8 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         t.o0 = D == 1 ? dm : p->pgA;
         P.t[P.ntasks++] = t;
     }
-    for (int d = 0; d < D; ++d) {
-        FpTask t = fp_task(p, FP_YP, d, p->n[d], 1);
-        t.t0 = band(d); t.o0 = p->g.Y[d];
-        P.t[P.ntasks++] = t;
-    }
     if ((rc = fp_launch(p, P, st))) return rc;
-    // pass 2: next mode of the dm chain, its A_e contraction, dL_d and the band of P_d X_d P_d
+    // pass 2: next mode of the dm chain, its A_e contraction, dL_d (the band of P_d X_d P_d is formed in k_b1_theta)
     fp_pass_init(p, P, theta, ell_scale);
     if (D >= 2) {
         const int e = D - 2;
@@ -637,9 +632,6 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         FpTask t = fp_task(p, FP_DL, d, 1, p->n[d]);
         t.s0 = p->g.R[d]; t.s1 = L + p->g.Loff[d]; t.t0 = band(d); t.o0 = dL + p->g.Loff[d];
         P.t[P.ntasks++] = t;
-        FpTask z = fp_task(p, FP_Z, d, 1, p->n[d]);
-        z.s0 = p->g.Y[d];
-        P.t[P.ntasks++] = z;
     }
     if ((rc = fp_launch(p, P, st))) return rc;
     if (D == 3) {
@@ -652,7 +644,11 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         P.t[P.ntasks++] = a;
         if ((rc = fp_launch(p, P, st))) return rc;
     }
-    k_b1_theta<<<D, 512, 0, st>>>(p->g, theta, p->b1_acc, gscal, ell_scale, out, dtheta);
+    const size_t tsm = 2 * (size_t)p->nmax * sizeof(double);
+    if (p->obs_dtype == VGGP_F32)
+        k_b1_theta<float><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const float*>(gb) + p->M, gscal, ell_scale, out, dtheta);
+    else
+        k_b1_theta<double><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const double*>(gb) + p->M, gscal, ell_scale, out, dtheta);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
