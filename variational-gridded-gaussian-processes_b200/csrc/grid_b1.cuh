@@ -64,6 +64,7 @@ struct FpPass {
     double* Qb[VGGP_MAX_D];
     void* bandT;                  // per-cell tables (obs dtype)
     int tab_off[VGGP_MAX_D];
+    long long* dbg;               // optional phase stamps (tools/gpu_phase_stamps.py): [tile][8] of clock64 / globaltimer, or null
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -264,6 +265,7 @@ __host__ __device__ inline FpGeom fp_geom(int n) {
     q.n = n;
     q.S = (n + 31) / 32;
     int len = n + (n + q.S - 1) / q.S + 1;
+    if (len < 32 * (q.S + 1) + 16) len = 32 * (q.S + 1) + 16;      // every lane may read 16 slots from its segment start
     len = (len + 15) / 16 * 16 + 2;            // consecutive fibres start 2 banks (of 8 bytes) apart: transposed stores spread
     q.pitch = len;
     q.magic = (unsigned)((0x100000000ull + (unsigned long long)q.S - 1) / (unsigned long long)q.S);
@@ -272,7 +274,7 @@ __host__ __device__ inline FpGeom fp_geom(int n) {
 __host__ __device__ inline size_t fp_smem_bytes(int n, int F, bool aux) {
     const FpGeom q = fp_geom(n);
     const int narr = 1 + (aux ? 1 : 0) + (q.S > 16 ? 1 : 0);
-    return sizeof(double) * ((size_t)3 * q.pitch + (size_t)narr * F * q.pitch) + sizeof(i64) * F;
+    return sizeof(double) * ((size_t)5 * q.pitch + (size_t)narr * F * q.pitch);      // [pd | ru | rl | bq_diag | bq_off] + tiles
 }
 // padded index; `SM` = FpGeom::magic (S == 1 gives magic 2^32, which does not fit: n <= 32 is handled by the S == 1 branch)
 __device__ __forceinline__ int fp_pidx(int i, unsigned SM) { return SM ? i + (int)__umulhi((unsigned)i, SM) : 2 * i; }
@@ -291,23 +293,24 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
     double lA = 1.0, lB = 0.0, uA = 1.0, uB = 0.0;
     double sv[16];
     if (S <= 16) {
+        // straight-line code: every shared-memory load is unconditional (the slots exist, fp_geom) and the updates are
+        // selects, so the loads are scheduled ahead of the dependent chains instead of one branch region per element
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sv[j] = (j < cnt) ? pd[p0 + j] * X[p0 + j] : 0.0;
+        for (int j = 0; j < 16; ++j) sv[j] = pd[p0 + j] * X[p0 + j];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            if (j < cnt) {
-                const double r = rl[p0 + j];
-                lB = fma(r, lB, r * sv[j]);
-                lA *= r;
-            }
+            const double r = rl[p0 + j];
+            const double nb = fma(r, lB, r * sv[j]), na = lA * r;
+            lB = (j < cnt) ? nb : lB;
+            lA = (j < cnt) ? na : lA;
         }
 #pragma unroll
         for (int j = 15; j >= 0; --j) {
-            if (j < cnt) {
-                const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
-                uB = fma(r, uB, r * sv[j]);
-                uA *= r;
-            }
+            const double rr = ru[j > 0 ? p0 + j - 1 : (p0 >= 2 ? p0 - 2 : 0)];     // slot of element i - 1
+            const double r = (i0 + j > 0) ? rr : 0.0;
+            const double nb = fma(r, uB, r * sv[j]), na = uA * r;
+            uB = (j < cnt) ? nb : uB;
+            uA = (j < cnt) ? na : uA;
         }
     } else {
         for (int j = 0; j < cnt; ++j) {
@@ -340,19 +343,18 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
         double uu[16];
 #pragma unroll
         for (int j = 15; j >= 0; --j) {
-            if (j < cnt) {
-                uu[j] = u;
-                const double r = (i0 + j > 0) ? ru[j > 0 ? p0 + j - 1 : p0 - 2] : 0.0;     // slot of element i - 1
-                u = fma(r, u, r * sv[j]);
-            }
+            uu[j] = u;
+            const double rr = ru[j > 0 ? p0 + j - 1 : (p0 >= 2 ? p0 - 2 : 0)];     // slot of element i - 1
+            const double r = (i0 + j > 0) ? rr : 0.0;
+            const double nu = fma(r, u, r * sv[j]);
+            u = (j < cnt) ? nu : u;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            if (j < cnt) {
-                const double r = rl[p0 + j];
-                X[p0 + j] = sv[j] + l + uu[j];
-                l = fma(r, l, r * sv[j]);
-            }
+            const double r = rl[p0 + j];
+            if (j < cnt) X[p0 + j] = sv[j] + l + uu[j];
+            const double nl = fma(r, l, r * sv[j]);
+            l = (j < cnt) ? nl : l;
         }
     } else {
         for (int j = cnt - 1; j >= 0; --j) {
@@ -373,8 +375,10 @@ __device__ __forceinline__ void fp_fibre(const FpGeom& q, const double* __restri
 
 // Element-parallel loop with U independent global loads in flight per thread before the first use: without it the
 // compiler issues one load per iteration and the warp waits for each (16 serialised L2 / HBM round trips per phase).
-template <int U, typename LoadF, typename StoreF>
-__device__ __forceinline__ void fp_batched(int total, LoadF ld, StoreF st) {
+struct FpNoHook { __device__ __forceinline__ void operator()() const {} };
+template <int U, typename LoadF, typename StoreF, typename HookF = FpNoHook>
+__device__ __forceinline__ void fp_batched(int total, LoadF ld, StoreF st, HookF after_first_loads = HookF()) {
+    bool first = true;
     for (int e0 = threadIdx.x; e0 < total; e0 += U * FP_THREADS) {
         double v[U];
 #pragma unroll
@@ -382,6 +386,7 @@ __device__ __forceinline__ void fp_batched(int total, LoadF ld, StoreF st) {
             const int e = e0 + u * FP_THREADS;
             v[u] = (e < total) ? ld(e) : 0.0;
         }
+        if (first) { after_first_loads(); first = false; }      // e.g. the stores of values whose loads were issued earlier
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int e = e0 + u * FP_THREADS;
@@ -429,40 +434,34 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     if (tk.kind == FP_QROW) { fp_qrow<T>(P, tk, tile); return; }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = tk.n, d = tk.d, F = tk.F;
+#ifndef VGGP_EMUL
+    long long* stamp = (P.dbg && tid == 0) ? P.dbg + (size_t)blockIdx.x * 8 : nullptr;
+#define FP_STAMP(k) do { if (stamp) { stamp[k] = clock64(); } } while (0)
+    if (stamp) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); stamp[6] = (long long)gt; stamp[7] = tk.kind; }
+#else
+#define FP_STAMP(k) do { } while (0)
+#endif
+    FP_STAMP(0);
     const FpGeom q = fp_geom(n);
     const int S = q.S;
     const unsigned SM = q.magic;
     double* pd = reinterpret_cast<double*>(smraw);
     double* ru = pd + q.pitch;
     double* rl = ru + q.pitch;
-    double* X = rl + q.pitch;
+    double* bqs = rl + q.pitch;                                         // DL: 2 cQ [bq_diag | bq_off], plain indexing
+    double* X = bqs + 2 * q.pitch;
     const bool aux = fp_kind_has_aux(tk.kind);
     double* Cx = X + (size_t)F * q.pitch;                               // valid only if aux
     double* U = X + (size_t)(aux ? 2 : 1) * F * q.pitch;                // valid only if S > 16
-    i64* fbase = reinterpret_cast<i64*>(X + (size_t)((aux ? 2 : 1) + (S > 16 ? 1 : 0)) * F * q.pitch);
-    // ---- generators of dimension d
-    {
-        const double* __restrict__ gen = P.gen[d];
-        for (int i = tid; i < n; i += FP_THREADS) {
-            const int p = fp_pidx(i, SM);
-            pd[p] = gen[i]; ru[p] = gen[n + i]; rl[p] = gen[2 * n + i];
-        }
-    }
+    const double noise = P.theta[2 * P.D];
+    const double cg = P.ell_scale / noise;
+    const double cQ = -P.ell_scale / (2.0 * noise);
+    const bool contiguous = (tk.inner == 1);
     // ---- source fibres of this tile: GA carries g and ghat of the same F / 2 source fibres
     const int nsrc = (tk.kind == FP_GA) ? F / 2 : F;
     const i64 fib0 = (i64)tile * nsrc;
     const int nf = (int)min((i64)nsrc, tk.nfib - fib0);                 // source fibres present in this tile
-    if (tid < nsrc) {
-        const i64 f = fib0 + tid;
-        const i64 o = f / tk.inner, r = f - o * tk.inner;
-        fbase[tid] = o * (i64)n * tk.inner + r;
-    }
-    __syncthreads();
-    const double noise = P.theta[2 * P.D];
-    const double cg = P.ell_scale / noise;
-    const double cP = P.ell_scale / (2.0 * noise), cQ = -P.ell_scale / (2.0 * noise);
-    const bool contiguous = (tk.inner == 1);
-    // element-parallel loop over (fibre, element): for strided modes consecutive threads take consecutive fibres of one
+    // element-parallel loops over (fibre, element): for strided modes consecutive threads take consecutive fibres of one
     // element index (they are adjacent in memory), for the contiguous mode consecutive elements of one fibre
     const int total = nsrc * n;
     // element index of the tile -> (element of the fibre, fibre of the tile) without integer divisions: nsrc is a power of
@@ -472,41 +471,80 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
     auto split_s = [&](int e, int& i, int& f) { i = e >> nsrc_sh; f = e & (nsrc - 1); };                 // strided modes
     auto split_c = [&](int e, int& i, int& f) { f = (int)__umulhi((unsigned)e, n_magic); i = e - f * n; };  // contiguous mode
     auto split = [&](int e, int& i, int& f) { if (contiguous) split_c(e, i, f); else split_s(e, i, f); };
+    // address of element i of tile fibre f.  Strided modes: FP_THREADS is a multiple of nsrc, so a thread only ever touches
+    // fibre tid & (nsrc - 1) and keeps its base in a register; contiguous mode: fibre f starts at f n.
+    i64 my_base = 0;
+    bool my_ok = false;
+    if (!contiguous) {
+        const i64 fg = fib0 + (tid & (nsrc - 1));
+        my_ok = fg < tk.nfib;
+        const i64 o = fg / tk.inner, r = fg - o * tk.inner;
+        my_base = o * (i64)n * tk.inner + r;
+    }
+    auto addr = [&](int i, int f) -> i64 { return contiguous ? (fib0 + f) * (i64)n + i : my_base + (i64)i * tk.inner; };
+    auto live = [&](int f) -> bool { return contiguous ? f < nf : my_ok; };
+    // ---- generators of dimension d ([pd | ru | rl], 3 n contiguous doubles): the loads are issued before those of the
+    // tile, the shared-memory stores follow, so that both round trips to L2 overlap
+    const double* __restrict__ gen = P.gen[d];
+    constexpr int GB = 6;                       // 3 n / FP_THREADS for n <= 512
+    double gq[GB];
+#pragma unroll
+    for (int u = 0; u < GB; ++u) {
+        const int e = tid + u * FP_THREADS;
+        gq[u] = (e < 3 * n) ? gen[e] : 0.0;
+    }
+    FP_STAMP(1);
+    auto gens_store = [&]() {
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            const int e = tid + u * FP_THREADS;
+            if (e < 3 * n) {
+                const int arr = (int)__umulhi((unsigned)e, n_magic), i = e - arr * n;
+                pd[arr * q.pitch + fp_pidx(i, SM)] = gq[u];
+            }
+        }
+        for (int e = tid + GB * FP_THREADS; e < 3 * n; e += FP_THREADS) {      // n > 512
+            const int arr = (int)__umulhi((unsigned)e, n_magic), i = e - arr * n;
+            pd[arr * q.pitch + fp_pidx(i, SM)] = gen[e];
+        }
+    };
     switch (tk.kind) {
         case FP_R: {
             const double* __restrict__ L = tk.s0;
             fp_batched<FP_U>(total,
                 [&](int e) { int i, f; split_s(e, i, f); const i64 k = fib0 + f;
                              return (f < nf && (i64)i >= k) ? L[(i64)i * n + k] : 0.0; },
-                [&](int e, double v) { int i, f; split_s(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
+                [&](int e, double v) { int i, f; split_s(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; }, gens_store);
         } break;
         case FP_PROD: case FP_ALPHA: case FP_DM: {
             const double* __restrict__ src = tk.s0;
             fp_batched<FP_U>(total,
-                [&](int e) { int i, f; split(e, i, f); return (f < nf) ? src[fbase[f] + (i64)i * tk.inner] : 0.0; },
-                [&](int e, double v) { int i, f; split(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
+                [&](int e) { int i, f; split(e, i, f); return live(f) ? src[addr(i, f)] : 0.0; },
+                [&](int e, double v) { int i, f; split(e, i, f); X[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; }, gens_store);
         } break;
         case FP_GA: case FP_GAONLY: {
             const T* __restrict__ ga = reinterpret_cast<const T*>(tk.t0);
             const double* __restrict__ m = tk.s0;
             const double* __restrict__ al = tk.s1;
             const bool both = (tk.kind == FP_GA);
-            for (int e0 = tid; e0 < total; e0 += 4 * FP_THREADS) {
-                double gv[4], mv[4], av[4];
+            bool first = true;
+            for (int e0 = tid; e0 < total; e0 += 8 * FP_THREADS) {
+                double gv[8], mv[8], av[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int e = e0 + u * FP_THREADS;
                     gv[u] = mv[u] = av[u] = 0.0;
                     if (e < total) {
                         int i, f; split(e, i, f);
-                        if (f < nf) {
-                            const i64 a = fbase[f] + (i64)i * tk.inner;
+                        if (live(f)) {
+                            const i64 a = addr(i, f);
                             gv[u] = (double)ga[a]; mv[u] = m[a]; av[u] = al[a];
                         }
                     }
                 }
+                if (first) { gens_store(); first = false; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int e = e0 + u * FP_THREADS;
                     if (e < total) {
                         int i, f; split(e, i, f);
@@ -524,29 +562,44 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
             }
         } break;
         case FP_DL: {
-            // column k of R_d -> Cx; then column k of dR_d = 2 cQ tridiag(bq_diag, bq_off) R_d -> X
+            // column k of R_d -> Cx and the bq band (scaled by 2 cQ) -> shared; then column k of dR_d = 2 cQ tridiag(bq) R_d -> X
             const double* __restrict__ R = tk.s0;
+            const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0) + 2 * n;        // [bq_diag | bq_off]
+            constexpr int BB = 4;               // 2 n / FP_THREADS for n <= 512
+            T bq[BB];
+#pragma unroll
+            for (int u = 0; u < BB; ++u) {
+                const int e = tid + u * FP_THREADS;
+                bq[u] = (e < 2 * n) ? bnd[e] : (T)0;
+            }
             fp_batched<FP_U>(total,
                 [&](int e) { int i, f; split_s(e, i, f); return (f < nf) ? R[(i64)i * n + (fib0 + f)] : 0.0; },
-                [&](int e, double v) { int i, f; split_s(e, i, f); Cx[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; });
+                [&](int e, double v) { int i, f; split_s(e, i, f); Cx[(size_t)f * q.pitch + fp_pidx(i, SM)] = v; }, gens_store);
+#pragma unroll
+            for (int u = 0; u < BB; ++u) {
+                const int e = tid + u * FP_THREADS;
+                if (e < 2 * n) bqs[e] = 2.0 * cQ * (double)bq[u];
+            }
+            for (int e = tid + BB * FP_THREADS; e < 2 * n; e += FP_THREADS) bqs[e] = 2.0 * cQ * (double)bnd[e];      // n > 512
             __syncthreads();
-            const T* __restrict__ bnd = reinterpret_cast<const T*>(tk.t0);
             for (int e = tid; e < total; e += FP_THREADS) {
                 int i, f; split_c(e, i, f);
                 const double* c = Cx + (size_t)f * q.pitch;
-                double r = (double)bnd[2 * n + i] * c[fp_pidx(i, SM)];
-                if (i > 0) r = fma((double)bnd[3 * n + i - 1], c[fp_pidx(i - 1, SM)], r);
-                if (i + 1 < n) r = fma((double)bnd[3 * n + i], c[fp_pidx(i + 1, SM)], r);
-                X[(size_t)f * q.pitch + fp_pidx(i, SM)] = 2.0 * cQ * r;
+                double r = bqs[i] * c[fp_pidx(i, SM)];
+                if (i > 0) r = fma(bqs[n + i - 1], c[fp_pidx(i - 1, SM)], r);
+                if (i + 1 < n) r = fma(bqs[n + i], c[fp_pidx(i + 1, SM)], r);
+                X[(size_t)f * q.pitch + fp_pidx(i, SM)] = r;
             }
         } break;
         default: break;
     }
     __syncthreads();
+    FP_STAMP(2);
     // ---- recurrences: one warp per fibre
     for (int f = warp; f < F; f += FP_WARPS)
         fp_fibre(q, pd, ru, rl, X + (size_t)f * q.pitch, U + (size_t)f * q.pitch, lane);
     __syncthreads();
+    FP_STAMP(3);
     // ---- epilogues
     switch (tk.kind) {
         case FP_R: {
@@ -564,11 +617,11 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
             const int kind = tk.kind;
             fp_batched<FP_U>(total,
                 [&](int e) { int i, f; split(e, i, f);
-                             return (kind != FP_PROD && f < nf) ? al[fbase[f] + (i64)i * tk.inner] : 0.0; },
+                             return (kind != FP_PROD && live(f)) ? al[addr(i, f)] : 0.0; },
                 [&](int e, double v) {
                     int i, f; split(e, i, f);
-                    if (f >= nf) return;
-                    const i64 a = fbase[f] + (i64)i * tk.inner;
+                    if (!live(f)) return;
+                    const i64 a = addr(i, f);
                     const double y = X[(size_t)f * q.pitch + fp_pidx(i, SM)];
                     if (kind == FP_DM) {
                         dst[a] = y - v;
@@ -588,8 +641,8 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
             (void)al;
             for (int e = tid; e < total; e += FP_THREADS) {
                 int i, f; split(e, i, f);
-                if (f >= nf) continue;
-                const i64 a = fbase[f] + (i64)i * tk.inner;
+                if (!live(f)) continue;
+                const i64 a = addr(i, f);
                 const int pp = fp_pidx(i, SM);
                 const double y = X[(size_t)f * q.pitch + pp];
                 dst[a] = tk.direct ? y - Cx[(size_t)f * q.pitch + pp] : y;      // Cx holds alpha of these fibres
@@ -622,6 +675,9 @@ __global__ void __launch_bounds__(FP_THREADS) k_fibre_pass(const __grid_constant
         } break;
         default: break;
     }
+    __syncthreads();
+    FP_STAMP(4);
+#undef FP_STAMP
 }
 
 // Row reductions of R_d: one warp per row i (tile = 8 rows).  tk.s0 = R_d, tk.s1 = L_d.
@@ -700,7 +756,7 @@ __device__ __forceinline__ void warp_recurrence(int n, FA a, FB b, double* __res
 //   (P X P)[i][i]   = T_i + rl_{i-1}^2 S_{i-1} + 2 xo_{i-1} P[i][i-1] pd_i
 //   (P X P)[i][i+1] = ru_i T_{i+1} + rl_i S_i + xo_i (pd_i pd_{i+1} + P[i][i+1]^2)
 // (round 1 formed X_d P_d and P_d (X_d P_d) as two n x n semiseparable products for these 3 n numbers).
-// grid (D), 512 threads, dynamic smem 2 n doubles.
+// grid (D), 512 threads, dynamic smem 7 n doubles.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
@@ -712,28 +768,39 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
     const int n = g.n[d];
     const int D = g.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // shared: generators, the band scatter X_d and the two recurrences (7 n doubles): the serial sweeps must not wait for
+    // global memory at every step
     double* Tt = sm;
     double* Ss = sm + n;
+    double* pd = sm + 2 * n;
+    double* ru = sm + 3 * n;
+    double* rl = sm + 4 * n;
+    double* xd = sm + 5 * n;
+    double* xo = sm + 6 * n;
     const double half_ratio = 0.5 * (double)g.M / (double)n;
     const double half_c = 0.5 * tr_others(g, d);
-    const double* __restrict__ gen = g.gen[d];
-    const double* __restrict__ pd = gen;
-    const double* __restrict__ ru = gen + n;
-    const double* __restrict__ rl = gen + 2 * n;
-    const T* __restrict__ bp = gband + g.band_off[d];           // [bp_diag | bp_off | bq_diag | bq_off]
     const double cP = ell_scale / (2.0 * theta[2 * D]);
+    {
+        const double* __restrict__ gen = g.gen[d];
+        const T* __restrict__ bp = gband + g.band_off[d];           // [bp_diag | bp_off | bq_diag | bq_off]
+        for (int i = threadIdx.x; i < n; i += 512) {
+            pd[i] = gen[i]; ru[i] = gen[n + i]; rl[i] = gen[2 * n + i];
+            xd[i] = cP * (double)bp[i]; xo[i] = cP * (double)bp[n + i];
+        }
+    }
     for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
+    __syncthreads();
     if (warp == 0) {
         warp_recurrence<false>(n,
             [&](int i) { return (i + 1 < n) ? ru[i] * ru[i] : 0.0; },
-            [&](int i) { const double x = cP * (double)bp[i] * pd[i] * pd[i];
-                         return (i + 1 < n) ? x + 2.0 * cP * (double)bp[n + i] * pd[i] * (ru[i] * pd[i + 1]) : x; },
+            [&](int i) { const double x = xd[i] * pd[i] * pd[i];
+                         return (i + 1 < n) ? x + 2.0 * xo[i] * pd[i] * (ru[i] * pd[i + 1]) : x; },
             Tt, lane);
     } else if (warp == 1) {
         warp_recurrence<true>(n,
             [&](int i) { return (i > 0) ? rl[i - 1] * rl[i - 1] : 0.0; },
-            [&](int i) { const double x = cP * (double)bp[i] * pd[i] * pd[i];
-                         return (i > 0) ? x + 2.0 * cP * (double)bp[n + i - 1] * pd[i] * (rl[i - 1] * pd[i - 1]) : x; },
+            [&](int i) { const double x = xd[i] * pd[i] * pd[i];
+                         return (i > 0) ? x + 2.0 * xo[i - 1] * pd[i] * (rl[i - 1] * pd[i - 1]) : x; },
             Ss, lane);
     }
     // d K / d l and d K / d s2 take three distinct values each (corner diagonal, interior diagonal, off-diagonal)
@@ -758,13 +825,13 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
             w = Tt[i];
             if (i > 0) {
                 const double pl = rl[i - 1] * pd[i - 1];                       // P[i][i-1]
-                w += rl[i - 1] * rl[i - 1] * Ss[i - 1] + 2.0 * cP * (double)bp[n + i - 1] * pl * pd[i];
+                w += rl[i - 1] * rl[i - 1] * Ss[i - 1] + 2.0 * xo[i - 1] * pl * pd[i];
             }
         } else {
             qv = Qb[n + lo];
             const double pu = ru[lo] * pd[lo + 1];                             // P[lo][lo+1]
             pij = pu;
-            w = ru[lo] * Tt[lo + 1] + rl[lo] * Ss[lo] + cP * (double)bp[n + lo] * (pd[lo] * pd[lo + 1] + pu * pu);
+            w = ru[lo] * Tt[lo + 1] + rl[lo] * Ss[lo] + xo[lo] * (pd[lo] * pd[lo + 1] + pu * pu);
         }
         const double v = -(acc[e] + w) + half_c * qv - half_ratio * pij;
         const bool corner = (i == 0 || i == n - 1);

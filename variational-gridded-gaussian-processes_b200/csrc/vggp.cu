@@ -477,6 +477,7 @@ int build_schedules(vggp_plan* p) {
 
 
 // ---- fused B1 grid side (grid_b1.cuh) -------------------------------------------------------------------
+long long* g_fp_dbg = nullptr;        // debug: phase stamps of the next fibre passes (vggp_debug_fp_stamps)
 int g_fp_smem_hwm[2] = {0, 0};      // high-water mark of the dynamic shared memory opted in for k_fibre_pass<float / double>
 
 int fp_tile_F(int n, int want) {
@@ -521,6 +522,7 @@ void fp_pass_init(const vggp_plan* p, FpPass& P, const double* theta, double ell
     }
     P.sc = p->g.sc;
     P.bandT = p->tables;
+    P.dbg = g_fp_dbg;
 }
 
 int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
@@ -644,7 +646,16 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         P.t[P.ntasks++] = a;
         if ((rc = fp_launch(p, P, st))) return rc;
     }
-    const size_t tsm = 2 * (size_t)p->nmax * sizeof(double);
+    const size_t tsm = 7 * (size_t)p->nmax * sizeof(double);
+    {
+        static int hwm[2] = {0, 0};              // per-function attribute, process-wide: only ever raised
+        const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
+        if ((int)tsm > 48 * 1024 && (int)tsm > hwm[ti]) {
+            if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_b1_theta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            else VGGP_CUDA(cudaFuncSetAttribute(k_b1_theta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            hwm[ti] = (int)tsm;
+        }
+    }
     if (p->obs_dtype == VGGP_F32)
         k_b1_theta<float><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const float*>(gb) + p->M, gscal, ell_scale, out, dtheta);
     else
@@ -1941,6 +1952,10 @@ int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
     VGGP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+
+/* debugging aid, not part of the documented ABI: every k_fibre_pass launched afterwards writes 8 int64 per CTA
+ * (clock64 at the phase boundaries, globaltimer, kind) to `buf` (device, >= 8 * tiles of the largest pass); NULL switches it off */
+int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
     if (!p || !info_pinned_host) return fail(VGGP_E_ARG, "null argument");
