@@ -102,6 +102,29 @@ def test_fused_grid_side_larger_meshes_under_emulation(emu, knots, N):
     plan.close()
 
 
+def test_fast_and_generic_fibre_kernels_agree_under_emulation(emu):
+    """k_fibre_pass_fast (M_d <= 512, the default) against the generic k_fibre_pass on the same step (2-D and 3-D, sizes that
+    leave partial tiles, partial lanes and absent fibres)."""
+    lib, L = emu
+    for knots, N in (((37, 50), 1200), ((21, 13, 18), 900), ((300,), 700)):
+        D = len(knots)
+        meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5 + D)
+        theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+        xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
+        res = []
+        for fast in (1, 0):
+            lib.vggp_debug_fp_fast(fast)
+            try:
+                plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+                res.append(plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                     plan.bin(xs, y.numpy().copy(), run_cap=64), None, 1.1))
+                plan.close()
+            finally:
+                lib.vggp_debug_fp_fast(1)
+        for a, b in zip(res[0], res[1]):
+            assert relerr(a, torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-11
+
+
 @pytest.mark.parametrize("layout", ["packed_sorted", "binned_ldg"])
 def test_two_wave_run_length_under_emulation(emu, layout):
     """Enough observations that the packed layout needs two waves of chunks per resident warp (the emulated device

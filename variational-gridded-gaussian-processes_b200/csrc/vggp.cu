@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "grid.cuh"
 #include "grid_b1.cuh"
+#include "grid_b1_fast.cuh"
 #include "obs.cuh"
 #include "obs_binned.cuh"
 #include "metrics.cuh"
@@ -525,18 +526,37 @@ void fp_pass_init(const vggp_plan* p, FpPass& P, const double* theta, double ell
     P.dbg = g_fp_dbg;
 }
 
+int g_fp_fast = 1;                   // use k_fibre_pass_fast where it applies (M_d <= 512); 0: always the generic kernel (cross-check)
+int g_ff_smem_hwm[2] = {0, 0};
+
 int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
     if (P.ntasks == 0) return 0;
     int tiles = 0;
-    size_t smem = 0;
+    size_t smem = 0, smem_fast = 0;
+    bool fast = g_fp_fast != 0;
     for (int i = 0; i < P.ntasks; ++i) {
         P.t[i].tile0 = tiles;
         tiles += P.t[i].ntiles;
-        if (P.t[i].kind != FP_QROW)
-            smem = std::max(smem, fp_smem_bytes(P.t[i].n, P.t[i].F, fp_kind_has_aux(P.t[i].kind)));
+        if (P.t[i].kind != FP_QROW) {
+            const bool aux = fp_kind_has_aux(P.t[i].kind);
+            smem = std::max(smem, fp_smem_bytes(P.t[i].n, P.t[i].F, aux));
+            smem_fast = std::max(smem_fast, ff_smem_bytes(aux));
+            if (P.t[i].n > 512 || P.t[i].F != FF_F) fast = false;
+        }
     }
     const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
-    if ((int)smem > g_fp_smem_hwm[ti]) {      // the attribute is per function and process-wide: only ever raise it
+    if (fast) {
+        if ((int)smem_fast > g_ff_smem_hwm[ti]) {      // the attribute is per function and process-wide: only ever raise it
+            if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            else VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            g_ff_smem_hwm[ti] = (int)smem_fast;
+        }
+        if (ti == 0) k_fibre_pass_fast<float><<<tiles, FP_THREADS, smem_fast, st>>>(P);
+        else k_fibre_pass_fast<double><<<tiles, FP_THREADS, smem_fast, st>>>(P);
+        VGGP_LAUNCH_CHECK();
+        return 0;
+    }
+    if ((int)smem > g_fp_smem_hwm[ti]) {
         if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_fp_smem_hwm[ti] = (int)smem;
@@ -1956,6 +1976,8 @@ int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
 /* debugging aid, not part of the documented ABI: every k_fibre_pass launched afterwards writes 8 int64 per CTA
  * (clock64 at the phase boundaries, globaltimer, kind) to `buf` (device, >= 8 * tiles of the largest pass); NULL switches it off */
 int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
+/* debugging aid: 0 = run every fibre pass through the generic kernel (cross-check of k_fibre_pass_fast), 1 = default */
+int vggp_debug_fp_fast(int on) { g_fp_fast = on ? 1 : 0; return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
     if (!p || !info_pinned_host) return fail(VGGP_E_ARG, "null argument");

@@ -17,14 +17,20 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def allreduce_gbuf_views(raw: torch.Tensor, obs: torch.Tensor, scal: torch.Tensor, group=None) -> None:
-    """Sum the gradient buffer over ranks.  float64 observations: the whole allocation is one float64 vector and
-    one collective; float32 observations: the float32 block and the float64 scalar block are two typed views of
-    the same allocation and go out as two collectives issued back to back."""
+    """Sum the gradient buffer over ranks with ONE collective launch.  float64 observations: the whole allocation is one
+    float64 vector.  float32 observations: the float32 block and the float64 scalar block are two typed views of the same
+    allocation; on NCCL they go out inside one group (ncclGroupStart / End through torch's coalescing manager: one kernel
+    launch, one pass over NVLink), on backends without coalescing (gloo, the CPU tests) as two calls back to back."""
     if obs.dtype == torch.float64 and raw.numel() % 8 == 0:
         dist.all_reduce(raw.view(torch.float64), op=dist.ReduceOp.SUM, group=group)
-    else:
-        dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
+        return
+    if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+        with dist._coalescing_manager(group=group, device=obs.device, async_ops=False):
+            dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
+        return
+    dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
 
 
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
