@@ -183,6 +183,27 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* plan, const vggp_binned_desc* desc, const
 int vggp_set_binned_stream(int mode);
 
 /*
+ * The one collective of a sharded step as a single kernel over peer memory (csrc/collective.cuh): gbuf <- sum over the ranks
+ * of one NVSwitch node, in place, on `stream`, between vggp_obs_fwd_bwd* and vggp_grid_backward.  It replaces the
+ * ncclAllReduce the north star names where the gradient buffers are SYMMETRIC allocations: same
+ * size on every rank and mapped into every process (the host mirror uses torch.distributed._symmetric_memory for the
+ * allocation and the handle exchange).  With a multicast address the reduction happens in the switch (multimem.ld_reduce /
+ * multimem.st on slice `rank` of the buffer); without one, rank r reads slice r from every peer and writes the sum back to
+ * every peer.  world <= 8.
+ *   desc->pad_ptrs  every rank's signal pad (128 uint32 words, zeroed once at setup), mapped like the buffers
+ *   seq             barrier sequence number: the first call passes 1, every call consumes two numbers (seq, seq + 1);
+ *                   all ranks must pass the same value
+ *   err_flag        DEVICE int, set to 1 if a barrier timed out (a rank is missing): the poll loops are bounded
+ */
+typedef struct vggp_ar_desc {
+    void* mc_ptr;
+    void* buf_ptrs[8];
+    void* pad_ptrs[8];
+    int32_t rank, world;
+} vggp_ar_desc;
+int vggp_allreduce_gbuf(vggp_plan* plan, const vggp_ar_desc* desc, uint32_t seq, int* err_flag, void* stream);
+
+/*
  * Grid-side backward + ELBO assembly from the (all-reduced) gbuf.
  *   ell_scale   N / B minibatch scaling of the expected log-likelihood (1 for full batch)
  *   out    [4]    float64: ELBO, ell_scale * ELL, KL, n_obs(all ranks)

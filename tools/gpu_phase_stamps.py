@@ -33,6 +33,9 @@ def show(name, fn):
     lib.vggp_debug_fp_stamps(None)
     b = buf.view(-1, 8).cpu()
     b = b[b[:, 4] != 0]          # CTAs of the LAST pass of the call overwrite earlier ones: rows are per blockIdx
+    if b.shape[0] == 0:
+        print(f"== {name}: no stamps (the fast kernel is not instrumented; vggp_debug_fp_fast(0) selects the generic one)")
+        return
     t0 = b[:, 6].min()
     print(f"== {name}: {b.shape[0]} stamped CTAs, span of CTA starts {(b[:, 6].max() - t0).item() / 1e3:.1f} us")
     for k in sorted(set(b[:, 7].tolist())):
@@ -42,3 +45,13 @@ def show(name, fn):
 show("forward (last pass: F2)", lambda: plan.grid_forward(theta, m, L))
 plan.obs_fwd_bwd(obs)
 show("backward (last pass: B2)", lambda: plan.grid_backward(theta, m, L, 1.0))
+# theta kernel: it runs last in grid_backward and overwrites rows 0..D-1 of the buffer with its own stamps
+buf.zero_(); torch.cuda.synchronize()
+lib.vggp_debug_fp_stamps(buf.data_ptr())
+plan.grid_backward(theta, m, L, 1.0)
+torch.cuda.synchronize()
+lib.vggp_debug_fp_stamps(None)
+b = buf.view(-1, 8).cpu()[:2].double()
+names = ["stage loads", "recurrences (warps 0,1) + dK/dtheta constants", "barrier wait", "band loop + reduce", "scalar tail"]
+for d_ in range(2):
+    print(f"== k_b1_theta block {d_}: " + ", ".join(f"{names[i]} {(b[d_, i + 1] - b[d_, i]).item():.0f}" for i in range(5)) + " cycles")

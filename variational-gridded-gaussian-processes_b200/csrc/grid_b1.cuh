@@ -73,7 +73,7 @@ struct FpPass {
 // K_d, rescaled by exact powers of two), a single thread chains the 2 x n/GEN_CHUNK carries, and every chunk then runs the
 // plain recurrence from its carry -- which contracts the (already small) error of the carry.  512 pivots: 3 x 32
 // dependent steps instead of 512.
-// grid (D), GEN_THREADS threads, dynamic smem 4 n doubles.
+// grid (D), GEN_THREADS threads, dynamic smem 4 (n + n / 32 + 1) doubles.
 // ---------------------------------------------------------------------------------------------------------
 struct Mob { double a, b, c, d; };     // x -> (a x + b) / (c x + d)
 
@@ -117,10 +117,14 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
     const int d = blockIdx.x;
     const int n = g.n[d];
     const int tid = threadIdx.x;
+    // position of pivot k: one pad slot per chunk, so that the chunk-strided accesses of the sweeps (thread = chunk) spread
+    // over the banks
+    auto G = [](int k) { return k + (k >> 5); };
+    const int npad = n + (n >> 5) + 1;
     double* dd = sm;                 // top-down pivots, later ru
-    double* ee = dd + n;             // bottom-up pivots
-    double* rd = ee + n;             // 1 / dd
-    double* re = rd + n;             // 1 / ee
+    double* ee = dd + npad;          // bottom-up pivots
+    double* rd = ee + npad;          // 1 / dd
+    double* re = rd + npad;          // 1 / ee
     if (tid == 0) bad_flag = 0;
     if (d == 0) {
         if (tid < SC_COUNT) g.sc[tid] = 0.0;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
             double prev = carry_d[ch] / carry_d[GEN_THREADS / 2 + ch];
             double r = 1.0 / prev;
             int k = k0;
-            if (ch == 0) { dd[0] = prev; rd[0] = r; bad = !(prev > 0.0); k = 1; }
+            if (ch == 0) { dd[G(0)] = prev; rd[G(0)] = r; bad = !(prev > 0.0); k = 1; }
             for (; k < k1; ++k) {
                 const double nxt = fma(-b2, r, diag(k));
                 bad = bad || !(nxt > 0.0);
@@ -199,13 +203,13 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
                 e = fma(-nxt, rn, 1.0);
                 if (!(fabs(e) < 3e-16)) rn = 1.0 / nxt;
                 r = rn;
-                dd[k] = nxt; rd[k] = r;
+                dd[G(k)] = nxt; rd[G(k)] = r;
             }
         } else {
             double nxt = carry_e[ch] / carry_e[GEN_THREADS / 2 + ch];
             double r = 1.0 / nxt;
             int k = k1 - 1;
-            if (k1 == n) { ee[n - 1] = nxt; re[n - 1] = r; bad = !(nxt > 0.0); k = n - 2; }
+            if (k1 == n) { ee[G(n - 1)] = nxt; re[G(n - 1)] = r; bad = !(nxt > 0.0); k = n - 2; }
             for (; k >= k0; --k) {
                 const double cur = fma(-b2, r, diag(k));
                 bad = bad || !(cur > 0.0);
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
                 e = fma(-cur, rn, 1.0);
                 if (!(fabs(e) < 3e-16)) rn = 1.0 / cur;
                 r = rn;
-                ee[k] = cur; re[k] = r;
+                ee[G(k)] = cur; re[G(k)] = r;
             }
         }
         if (bad) bad_flag = 1;
@@ -225,12 +229,12 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
     double prod = 1.0;
     double ld = 0.0;
     for (int i = tid; i < n; i += GEN_THREADS) {
-        const double di = dd[i];
-        const double pdv = 1.0 / (di + ee[i] - diag(i));
-        const double ruv = (i + 1 < n) ? -cf.b * rd[i] : 0.0;
-        const double rlv = (i + 1 < n) ? -cf.b * re[i + 1] : 0.0;
+        const double di = dd[G(i)];
+        const double pdv = 1.0 / (di + ee[G(i)] - diag(i));
+        const double ruv = (i + 1 < n) ? -cf.b * rd[G(i)] : 0.0;
+        const double rlv = (i + 1 < n) ? -cf.b * re[G(i + 1)] : 0.0;
         gen[i] = pdv; gen[n + i] = ruv; gen[2 * n + i] = rlv;
-        ee[i] = pdv; dd[i] = ruv;          // reuse (only this thread reads dd[i], ee[i] above): ee = pd, dd = ru for the tables
+        ee[G(i)] = pdv; dd[G(i)] = ruv;          // reuse (only this thread reads dd[G(i)], ee[G(i)] above): ee = pd, dd = ru for the tables
         prod *= di;                        // log det K_d = sum log d_k: one log per thread
         if (prod > 1e200 || prod < 1e-200) { ld += log(prod); prod = 1.0; }
     }
@@ -240,9 +244,9 @@ __global__ void __launch_bounds__(GEN_THREADS) k_b1_gens(const __grid_constant__
     T* tab = reinterpret_cast<T*>(g.bandT) + g.tab_off[d];
     for (int i = tid; i < n; i += GEN_THREADS) {
         const bool last = (i + 1 >= n);
-        const double A = ee[i];
-        const double B2 = last ? 0.0 : 2.0 * ee[i + 1] * dd[i];        // 2 P[i][i+1] = 2 pd[i+1] ru[i]
-        const double Cc = last ? 0.0 : ee[i + 1];
+        const double A = ee[G(i)];
+        const double B2 = last ? 0.0 : 2.0 * ee[G(i + 1)] * dd[G(i)];        // 2 P[i][i+1] = 2 pd[i+1] ru[i]
+        const double Cc = last ? 0.0 : ee[G(i + 1)];
         tab[i] = (T)A; tab[n + i] = (T)(B2 - 2.0 * A); tab[2 * n + i] = (T)(A - B2 + Cc);
     }
     ld = block_sum(ld, red);
@@ -722,14 +726,17 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
 template <bool ASC, typename FA, typename FB>
 __device__ __forceinline__ void warp_recurrence(int n, FA a, FB b, double* __restrict__ out, int lane) {
     const int S = (n + 31) / 32;
-    // lane l owns [l S, (l + 1) S); for the descending sweep the lane order is reversed so that the scan still runs upwards
+    // lane l owns [l S, (l + 1) S); for the descending sweep the lane order is reversed so that the scan still runs upwards.
+    // a(i, p), b(i, p) and out[] use the padded position p = i + i / S of element i (lane stride S + 1: the lane-strided
+    // shared-memory accesses of the sweeps are then conflict-free; unpadded they were 32-way conflicts)
     const int seg = ASC ? lane : 31 - lane;
     const int i0 = seg * S, cnt = max(0, min(S, n - i0));
+    const int q0 = seg * (S + 1);
     double A = 1.0, B = 0.0;
     for (int j = 0; j < cnt; ++j) {
-        const int i = ASC ? i0 + j : i0 + cnt - 1 - j;
-        const double ai = a(i);
-        B = fma(ai, B, b(i));
+        const int jj = ASC ? j : cnt - 1 - j;
+        const double ai = a(i0 + jj, q0 + jj);
+        B = fma(ai, B, b(i0 + jj, q0 + jj));
         A *= ai;
     }
 #pragma unroll
@@ -740,9 +747,9 @@ __device__ __forceinline__ void warp_recurrence(int n, FA a, FB b, double* __res
     double t = __shfl_sync(0xffffffffu, B, (lane - 1) & 31);
     if (lane == 0) t = 0.0;
     for (int j = 0; j < cnt; ++j) {
-        const int i = ASC ? i0 + j : i0 + cnt - 1 - j;
-        t = fma(a(i), t, b(i));
-        out[i] = t;
+        const int jj = ASC ? j : cnt - 1 - j;
+        t = fma(a(i0 + jj, q0 + jj), t, b(i0 + jj, q0 + jj));
+        out[q0 + jj] = t;
     }
 }
 
@@ -756,27 +763,38 @@ __device__ __forceinline__ void warp_recurrence(int n, FA a, FB b, double* __res
 //   (P X P)[i][i]   = T_i + rl_{i-1}^2 S_{i-1} + 2 xo_{i-1} P[i][i-1] pd_i
 //   (P X P)[i][i+1] = ru_i T_{i+1} + rl_i S_i + xo_i (pd_i pd_{i+1} + P[i][i+1]^2)
 // (round 1 formed X_d P_d and P_d (X_d P_d) as two n x n semiseparable products for these 3 n numbers).
-// grid (D), 512 threads, dynamic smem 7 n doubles.
+// grid (D), 512 threads, dynamic smem 7 (n + n / S + 2) doubles.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDims g, const double* __restrict__ theta,
                                                   const double* __restrict__ acc, const T* __restrict__ gband,
                                                   const double* __restrict__ gscal,
-                                                  double ell_scale, double* __restrict__ out, double* __restrict__ dtheta) {
+                                                  double ell_scale, double* __restrict__ out, double* __restrict__ dtheta,
+                                                  long long* __restrict__ dbg) {
     extern __shared__ double sm[];
     const int d = blockIdx.x;
     const int n = g.n[d];
     const int D = g.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // shared: generators, the band scatter X_d and the two recurrences (7 n doubles): the serial sweeps must not wait for
-    // global memory at every step
+#ifndef VGGP_EMUL
+#define TH_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define TH_STAMP(k) do { } while (0)
+#endif
+    TH_STAMP(0);
+    // shared: generators, the band scatter X_d and the two recurrences, 7 arrays in PADDED positions p(i) = i + i / S
+    // (S = elements per lane of the sweeps): the serial sweeps must neither wait for global memory nor collide on banks
+    const int S = (n + 31) / 32;
+    const int np = n + (n + S - 1) / S + 2;
+    const unsigned SM = (unsigned)((0x100000000ull + (unsigned)S - 1) / (unsigned)S);
+    auto P_ = [&](int i) { return fp_pidx(i, SM); };
     double* Tt = sm;
-    double* Ss = sm + n;
-    double* pd = sm + 2 * n;
-    double* ru = sm + 3 * n;
-    double* rl = sm + 4 * n;
-    double* xd = sm + 5 * n;
-    double* xo = sm + 6 * n;
+    double* Ss = sm + np;
+    double* pd = sm + 2 * np;
+    double* ru = sm + 3 * np;
+    double* rl = sm + 4 * np;
+    double* xd = sm + 5 * np;
+    double* xo = sm + 6 * np;
     const double half_ratio = 0.5 * (double)g.M / (double)n;
     const double half_c = 0.5 * tr_others(g, d);
     const double cP = ell_scale / (2.0 * theta[2 * D]);
@@ -784,23 +802,28 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
         const double* __restrict__ gen = g.gen[d];
         const T* __restrict__ bp = gband + g.band_off[d];           // [bp_diag | bp_off | bq_diag | bq_off]
         for (int i = threadIdx.x; i < n; i += 512) {
-            pd[i] = gen[i]; ru[i] = gen[n + i]; rl[i] = gen[2 * n + i];
-            xd[i] = cP * (double)bp[i]; xo[i] = cP * (double)bp[n + i];
+            const int p = P_(i);
+            pd[p] = gen[i]; ru[p] = gen[n + i]; rl[p] = gen[2 * n + i];
+            xd[p] = cP * (double)bp[i]; xo[p] = cP * (double)bp[n + i];
         }
     }
     for (int e = 0; e < d; ++e) acc += 3 * g.n[e];          // this dimension's block of the accumulators
     __syncthreads();
+    TH_STAMP(1);
+    // neighbours of element i in padded positions: i + 1 is p + 1 unless i closes a lane segment (then p + 2); likewise i - 1
     if (warp == 0) {
         warp_recurrence<false>(n,
-            [&](int i) { return (i + 1 < n) ? ru[i] * ru[i] : 0.0; },
-            [&](int i) { const double x = xd[i] * pd[i] * pd[i];
-                         return (i + 1 < n) ? x + 2.0 * xo[i] * pd[i] * (ru[i] * pd[i + 1]) : x; },
+            [&](int i, int p) { return (i + 1 < n) ? ru[p] * ru[p] : 0.0; },
+            [&](int i, int p) { const double x = xd[p] * pd[p] * pd[p];
+                                return (i + 1 < n) ? x + 2.0 * xo[p] * pd[p] * (ru[p] * pd[P_(i + 1)]) : x; },
             Tt, lane);
     } else if (warp == 1) {
         warp_recurrence<true>(n,
-            [&](int i) { return (i > 0) ? rl[i - 1] * rl[i - 1] : 0.0; },
-            [&](int i) { const double x = xd[i] * pd[i] * pd[i];
-                         return (i > 0) ? x + 2.0 * xo[i - 1] * pd[i] * (rl[i - 1] * pd[i - 1]) : x; },
+            [&](int i, int p) { return (i > 0) ? rl[P_(i - 1)] * rl[P_(i - 1)] : 0.0; },
+            [&](int i, int p) { const double x = xd[p] * pd[p] * pd[p];
+                                if (i == 0) return x;
+                                const int pm = P_(i - 1);
+                                return x + 2.0 * xo[pm] * pd[p] * (rl[pm] * pd[pm]); },
             Ss, lane);
     }
     // d K / d l and d K / d s2 take three distinct values each (corner diagonal, interior diagonal, off-diagonal)
@@ -809,7 +832,9 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
     factor_entry_grad(g, theta, d, 1, 1, gl[1], gs[1]);
     factor_entry_grad(g, theta, d, 0, 1, gl[2], gs[2]);
     const double* __restrict__ Qb = g.Qb[d];
+    TH_STAMP(2);
     __syncthreads();
+    TH_STAMP(3);
     double sl = 0.0, ss = 0.0;
 #pragma unroll 3
     for (int e = threadIdx.x; e < 3 * n; e += 512) {
@@ -820,18 +845,21 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
         const int lo = i < j ? i : j;
         double qv, pij, w;
         if (dl == 0) {
+            const int p = P_(i);
             qv = Qb[i];
-            pij = pd[i];
-            w = Tt[i];
+            pij = pd[p];
+            w = Tt[p];
             if (i > 0) {
-                const double pl = rl[i - 1] * pd[i - 1];                       // P[i][i-1]
-                w += rl[i - 1] * rl[i - 1] * Ss[i - 1] + 2.0 * xo[i - 1] * pl * pd[i];
+                const int pm = P_(i - 1);
+                const double pl = rl[pm] * pd[pm];                             // P[i][i-1]
+                w += rl[pm] * rl[pm] * Ss[pm] + 2.0 * xo[pm] * pl * pd[p];
             }
         } else {
+            const int p = P_(lo), pn = P_(lo + 1);
             qv = Qb[n + lo];
-            const double pu = ru[lo] * pd[lo + 1];                             // P[lo][lo+1]
+            const double pu = ru[p] * pd[pn];                                  // P[lo][lo+1]
             pij = pu;
-            w = ru[lo] * Tt[lo + 1] + rl[lo] * Ss[lo] + xo[lo] * (pd[lo] * pd[lo + 1] + pu * pu);
+            w = ru[p] * Tt[pn] + rl[p] * Ss[p] + xo[p] * (pd[p] * pd[pn] + pu * pu);
         }
         const double v = -(acc[e] + w) + half_c * qv - half_ratio * pij;
         const bool corner = (i == 0 || i == n - 1);
@@ -843,6 +871,7 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
     __shared__ double red2[2][16];
     if (lane == 0) { red2[0][warp] = sl; red2[1][warp] = ss; }
     __syncthreads();
+    TH_STAMP(4);
     if (threadIdx.x == 0) {
         sl = 0.0; ss = 0.0;
         for (int w = 0; w < 16; ++w) { sl += red2[0][w]; ss += red2[1][w]; }
@@ -869,6 +898,8 @@ __global__ void __launch_bounds__(512) k_b1_theta(const __grid_constant__ GridDi
             out[3] = nobs;
         }
     }
+    TH_STAMP(5);
+#undef TH_STAMP
 }
 
 // K_d as a dense matrix, on demand (vggp_workspace_ptr): the fused path never materialises it in a step.

@@ -15,6 +15,7 @@
 #include "obs_binned.cuh"
 #include "metrics.cuh"
 #include "b0scan.cuh"
+#include "collective.cuh"
 
 namespace vggp {
 thread_local char g_err[512] = {0};
@@ -570,7 +571,7 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
 int b1f_forward(vggp_plan* p, const double* theta, const double* m, const double* L, cudaStream_t st) {
     const int D = p->D;
     int rc;
-    const size_t gsm = 4 * (size_t)p->nmax * sizeof(double);
+    const size_t gsm = 4 * ((size_t)p->nmax + p->nmax / 32 + 1) * sizeof(double);
     if (p->obs_dtype == VGGP_F32) k_b1_gens<float><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total, p->theta_dev);
     else k_b1_gens<double><<<D, GEN_THREADS, gsm, st>>>(p->g, theta, p->b1_acc, p->b1_acc_total, p->theta_dev);
     VGGP_LAUNCH_CHECK();
@@ -666,7 +667,7 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         P.t[P.ntasks++] = a;
         if ((rc = fp_launch(p, P, st))) return rc;
     }
-    const size_t tsm = 7 * (size_t)p->nmax * sizeof(double);
+    const size_t tsm = 7 * ((size_t)p->nmax + 34) * sizeof(double);
     {
         static int hwm[2] = {0, 0};              // per-function attribute, process-wide: only ever raised
         const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
@@ -677,9 +678,9 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         }
     }
     if (p->obs_dtype == VGGP_F32)
-        k_b1_theta<float><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const float*>(gb) + p->M, gscal, ell_scale, out, dtheta);
+        k_b1_theta<float><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const float*>(gb) + p->M, gscal, ell_scale, out, dtheta, g_fp_dbg);
     else
-        k_b1_theta<double><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const double*>(gb) + p->M, gscal, ell_scale, out, dtheta);
+        k_b1_theta<double><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const double*>(gb) + p->M, gscal, ell_scale, out, dtheta, g_fp_dbg);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -1872,6 +1873,34 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
     if (!binned) return fail(VGGP_E_ARG, "null binned buffer");
     if (p->family == VGGP_B0_GRIDDED) return obs_b0s_dispatch(p, desc, binned, gbuf, st);     // scan form (b0scan.cuh)
     return obs_binned_dispatch(p, desc, binned, gbuf, st);
+}
+
+int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, uint32_t seq, int* err_flag, void* stream) {
+    if (!p || !desc || !err_flag) return fail(VGGP_E_ARG, "null argument");
+    if (desc->world < 1 || desc->world > AR_MAX_RANKS || desc->rank < 0 || desc->rank >= desc->world)
+        return fail(VGGP_E_ARG, "world must be 1..8 and rank inside it");
+#ifdef VGGP_EMUL
+    (void)seq; (void)stream;
+    return fail(VGGP_E_UNSUPPORTED, "the peer-memory collective needs NVLink peers");
+#else
+    if (desc->world == 1) return 0;
+    ArArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mc = desc->mc_ptr;
+    for (int r = 0; r < desc->world; ++r) {
+        if (!desc->buf_ptrs[r] || !desc->pad_ptrs[r]) return fail(VGGP_E_ARG, "null peer pointer");
+        a.buf[r] = desc->buf_ptrs[r];
+        a.pad[r] = reinterpret_cast<unsigned int*>(desc->pad_ptrs[r]);
+    }
+    a.rank = desc->rank; a.world = desc->world;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.n_obs = n_elems; a.obs_f32 = p->obs_dtype == VGGP_F32; a.scal_off = soff; a.n_scal = (int)nsc;
+    a.seq = seq; a.err = err_flag;
+    k_allreduce_gbuf<<<AR_BLOCKS, AR_THREADS, 0, (cudaStream_t)stream>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+#endif
 }
 
 int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,

@@ -196,11 +196,57 @@ class GridPlan:
                                                dm.data_ptr(), dL.data_ptr(), _stream_ptr(self.device)))
         return out, dtheta, dm, dL
 
+    def enable_peer_allreduce(self, group=None) -> bool:
+        """Make `allreduce_gbuf` the library's own one-kernel collective over NVLink peer memory (vggp_allreduce_gbuf,
+        csrc/collective.cuh) instead of NCCL: the plan's gradient buffer is re-allocated as a SYMMETRIC buffer (same size on
+        every rank, mapped into every process) together with a small signal pad.  torch.distributed._symmetric_memory does
+        the allocation and the handle exchange (plumbing); the reduction kernel is ours.  Collective call: every rank of
+        `group` (<= 8 ranks of one NVSwitch node) must make it.  Returns whether the multicast (in-switch reduction) path
+        is available; without it the kernel uses peer loads / stores."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = dist.group.WORLD if group is None else group
+        world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+        if world > 8:
+            raise ValueError("the peer-memory collective covers one NVSwitch node (<= 8 ranks)")
+        with torch.cuda.device(self.device):
+            buf = symm.empty(self.gbuf_bytes, dtype=torch.uint8, device=self.device)
+            pad = symm.empty(16 * 8, dtype=torch.int32, device=self.device)
+            buf.zero_()
+            pad.zero_()
+            hb = symm.rendezvous(buf, grp)
+            hp = symm.rendezvous(pad, grp)
+        desc = _lib.ArDesc()
+        mc = int(getattr(hb, "multicast_ptr", 0) or 0)
+        desc.mc_ptr = mc if mc else None
+        for r in range(world):
+            desc.buf_ptrs[r] = int(hb.buffer_ptrs[r])
+            desc.pad_ptrs[r] = int(hp.buffer_ptrs[r])
+        desc.rank, desc.world = rank, world
+        self.gbuf = buf
+        self._ar = {"desc": desc, "handles": (hb, hp), "pad": pad, "seq": 1,
+                    "err": torch.zeros(1, dtype=torch.int32, device=self.device)}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(grp)                   # every pad is zeroed before the first signal arrives
+        return bool(mc)
+
+    def peer_allreduce_failed(self) -> bool:
+        """True if a barrier of the peer-memory collective timed out (synchronises)."""
+        ar = getattr(self, "_ar", None)
+        return bool(ar is not None and int(ar["err"].item()) != 0)
+
     def allreduce_gbuf(self, group=None, gbuf: Optional[torch.Tensor] = None):
-        """One sum-all-reduce of the per-observation gradient buffer (two typed views of one allocation when the
+        """One sum-all-reduce of the per-observation gradient buffer: the library's peer-memory kernel after
+        `enable_peer_allreduce`, otherwise one NCCL launch (two typed views of one allocation inside one group when the
         observation dtype is float32, a single float64 view otherwise)."""
         from .dist import allreduce_gbuf_views
         g = self.gbuf if gbuf is None else gbuf
+        ar = getattr(self, "_ar", None)
+        if ar is not None and g is self.gbuf:
+            _lib.check(self.lib.vggp_allreduce_gbuf(self.handle, C.byref(ar["desc"]), ar["seq"], ar["err"].data_ptr(),
+                                                    _stream_ptr(self.device)))
+            ar["seq"] = (ar["seq"] + 2) & 0xFFFFFFFF
+            return
         obs, scal = self.gbuf_views(g)
         allreduce_gbuf_views(g, obs, scal, group)
 
