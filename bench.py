@@ -394,6 +394,11 @@ def main():
                          "filled by TMA bulk copies (vggp_set_binned_stream)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the step from CUDA graphs (the all-reduce stays outside the graphs); opt-in")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer"],
+                    help="the one collective of a sharded step: NCCL, or the library's own one-kernel all-reduce over NVLink "
+                         "peer memory (vggp_allreduce_gbuf: in-switch multimem reduction; graph-capturable)")
+    ap.add_argument("--reshard-balance", default="count", choices=["count", "cells"],
+                    help="--spatial-reshard: cut the cell ranges at observation-count quantiles (default) or evenly")
     ap.add_argument("--spatial-reshard", action="store_true",
                     help="multi-GPU: exchange the acquisition-order shards by grid-cell range at setup "
                          "(dist.spatial_reshard; measured slower at 8 x B200 in round 1, off by default)")
@@ -430,12 +435,15 @@ def main():
     if not is_b1:
         args.obs_layout = "binned"          # the B0 family streams per-cell runs too (scan form); there is no packed layout for it
     plan = vg.GridPlan(vg.B1_ASVGP if is_b1 else vg.B0_GRIDDED, meshes, dtype, device)
+    multicast = None
+    if world > 1 and args.allreduce == "peer":
+        multicast = plan.enable_peer_allreduce()
     xs, y = make_tracks(lo, hi, n_total, device, dtype, D=len(knots))
     sharding = "contiguous in acquisition order"
     if world > 1 and args.spatial_reshard:
         # one-time setup exchange: every rank ends up owning a contiguous range of grid cells (dist.spatial_reshard)
         keys = plan.cell_keys(xs)
-        xs, y = vg.spatial_reshard(xs, y, keys, plan.n_cells)
+        xs, y = vg.spatial_reshard(xs, y, keys, plan.n_cells, balance=args.reshard_balance)
         n_local = int(y.numel())
         sharding = "by grid-cell range (one-time all-to-all of the acquisition-order shards at setup)"
         del keys
@@ -524,6 +532,8 @@ def main():
     t_end.record()
     barrier()
     launches = lib.vggp_launch_count() - launches0
+    if plan.peer_allreduce_failed():
+        raise SystemExit("a barrier of the peer-memory all-reduce timed out (a rank went missing)")
     if graphed is not None:
         launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
@@ -540,12 +550,13 @@ def main():
     k1_kernel_ms, k1_launches = plan.k1_time_read()       # the kernel alone (events inside the C call, same stream)
     plan.k1_timing(False)
     k1_call_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps   # whole vggp_obs_fwd_bwd* call
-    tt = torch.tensor([ms_total, k1_kernel_ms, k1_call_ms], dtype=torch.float64, device=device)
+    tt = torch.tensor([ms_total, k1_kernel_ms, k1_call_ms, float(n_local)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = tt[0].item() / args.steps
     k1_ms = tt[1].item()
     k1_call_ms = tt[2].item()
+    n_local_max = int(tt[3].item())        # the roofline pairs the slowest rank's kernel time with the largest shard
     value = n_total / (ms_step * 1e-3)
 
     # ---- secondary leg: same step on observations left in acquisition (along-track) order (B1 family: the packed kernel
@@ -637,14 +648,14 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg_bytes = n_local * (len(knots) + 1) * 4 + 2 * plan.M * 4
+        alg_bytes = n_local_max * (len(knots) + 1) * 4 + 2 * plan.M * 4
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_total, world, {
-                "n_obs_per_gpu": n_local, "observation_sharding": sharding,
+                "n_obs_per_gpu": n_local_max, "observation_sharding": sharding,
                 **({"run_len": packed.run_len,
                     "layout": "observations binned by grid cell + warp-transposed packing, done once at setup "
                               "(X is constant over optimisation steps); setup is outside the timed region"}
@@ -655,6 +666,10 @@ def main():
                     "layout": "per-cell runs, 32 equally long runs per warp task (vggp_obs_bin_pack), done once at "
                               "setup; setup is outside the timed region"}),
                 "setup_ms": setup_ms, "cuda_graph": bool(args.cuda_graph),
+                "allreduce": (None if world == 1 else
+                              ("NCCL" if args.allreduce == "nccl" else
+                               "vggp_allreduce_gbuf (one kernel over NVLink peer memory, %s)"
+                               % ("multimem in-switch reduction" if multicast else "two-shot P2P loads/stores"))),
                 "acquisition_order": ({"ms_per_step": acq_ms, "value": n_total / (acq_ms * 1e-3),
                                        "note": "same step without the cell binning (along-track order kept)"}
                                       if acq_ms is not None else None)}, args.workload),

@@ -190,9 +190,10 @@ int vggp_set_binned_stream(int mode);
  * allocation and the handle exchange).  With a multicast address the reduction happens in the switch (multimem.ld_reduce /
  * multimem.st on slice `rank` of the buffer); without one, rank r reads slice r from every peer and writes the sum back to
  * every peer.  world <= 8.
- *   desc->pad_ptrs  every rank's signal pad (128 uint32 words, zeroed once at setup), mapped like the buffers
- *   seq             barrier sequence number: the first call passes 1, every call consumes two numbers (seq, seq + 1);
- *                   all ranks must pass the same value
+ *   desc->pad_ptrs  every rank's signal pad (VGGP_AR_PAD_WORDS uint32 words, zeroed once at setup), mapped like the
+ *                   buffers.  The barrier sequence numbers live in the pad and are advanced by the kernel itself, so the
+ *                   call has no per-call argument and can be captured into a CUDA graph and replayed; all ranks must make
+ *                   the same sequence of calls
  *   err_flag        DEVICE int, set to 1 if a barrier timed out (a rank is missing): the poll loops are bounded
  */
 typedef struct vggp_ar_desc {
@@ -201,7 +202,8 @@ typedef struct vggp_ar_desc {
     void* pad_ptrs[8];
     int32_t rank, world;
 } vggp_ar_desc;
-int vggp_allreduce_gbuf(vggp_plan* plan, const vggp_ar_desc* desc, uint32_t seq, int* err_flag, void* stream);
+#define VGGP_AR_PAD_WORDS 576
+int vggp_allreduce_gbuf(vggp_plan* plan, const vggp_ar_desc* desc, int* err_flag, void* stream);
 
 /*
  * Grid-side backward + ELBO assembly from the (all-reduced) gbuf.

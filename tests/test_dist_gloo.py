@@ -166,7 +166,7 @@ def test_shard_bounds_partition(n, world):
         vdist.shard_bounds(n, world, world)
 
 
-def _reshard_worker(rank, world, port, out_dir):
+def _reshard_worker(rank, world, port, out_dir, balance="cells"):
     import importlib
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -181,10 +181,12 @@ def _reshard_worker(rank, world, port, out_dir):
         n = 500 + 37 * rank
         n_keys = 48
         keys = torch.randint(0, n_keys + 1, (n,), generator=g)          # n_keys = "outside the mesh"
+        if balance == "count":                                           # uneven coverage: most observations in few cells
+            keys = (keys.double() / (n_keys + 1)).pow(3.0).mul(n_keys + 1).floor().long().clamp(0, n_keys)
         x1 = torch.rand(n, generator=g, dtype=torch.float64)
         x2 = keys.to(torch.float64) + 0.25                               # lets the test recover the key afterwards
         y = torch.rand(n, generator=g, dtype=torch.float64) + rank
-        xs, yy = vdist.spatial_reshard([x1, x2], y, keys, n_keys, None)
+        xs, yy = vdist.spatial_reshard([x1, x2], y, keys, n_keys, None, balance=balance)
         torch.save({"x1": xs[0], "x2": xs[1], "y": yy, "in_x1": x1, "in_y": y}, os.path.join(out_dir, f"reshard{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -205,3 +207,20 @@ def test_spatial_reshard_two_ranks(tmp_path):
         keys = (d["x2"] - 0.25).round().to(torch.int64)
         assert torch.all((keys * world) // (n_keys + 1) == r)
         assert d["x1"].numel() == d["y"].numel() == d["x2"].numel()
+
+
+def test_spatial_reshard_count_balanced_two_ranks(tmp_path):
+    """balance="count": ranks own disjoint contiguous cell ranges cut at the quantiles of the global histogram, so the
+    observation counts are even although three quarters of the observations sit in the first third of the cells."""
+    world = 2
+    mp.spawn(_reshard_worker, args=(world, _free_port(), str(tmp_path), "count"), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), f"reshard{r}.pt")) for r in range(world)]
+    before = torch.sort(torch.cat([r["in_x1"] * 3.0 + r["in_y"] for r in res]))[0]
+    after = torch.sort(torch.cat([r["x1"] * 3.0 + r["y"] for r in res]))[0]
+    assert torch.equal(before, after)
+    keys = [(d["x2"] - 0.25).round().to(torch.int64) for d in res]
+    assert keys[0].max() < keys[1].min()                 # contiguous, disjoint cell ranges in rank order
+    n = [k.numel() for k in keys]
+    biggest_cell = max(torch.bincount(torch.cat(keys)).max().item(), 1)
+    assert abs(n[0] - n[1]) <= 2 * biggest_cell          # balanced up to one cell's worth of observations
+    assert min(n) > 0.35 * sum(n)

@@ -53,7 +53,7 @@ SIGNATURES = {
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
     "vggp_info_async": (C.c_int, [_vp, _vp, _vp]),
-    "vggp_allreduce_gbuf": (C.c_int, [_vp, C.POINTER(ArDesc), C.c_uint32, _dp, _vp]),
+    "vggp_allreduce_gbuf": (C.c_int, [_vp, C.POINTER(ArDesc), _dp, _vp]),
     "vggp_k1_timing": (C.c_int, [_vp, C.c_int]),
     "vggp_k1_time_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vggp_predict": (C.c_int, [_vp, C.POINTER(_vp), _i64, _dp, _dp, _vp]),

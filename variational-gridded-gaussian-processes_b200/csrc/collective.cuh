@@ -9,28 +9,33 @@
 //   peer loads         without multicast support: rank r reads slice r from every peer, sums in registers, writes it to every
 //                      peer (two-shot all-reduce over plain P2P loads / stores).
 // Barriers: one signal word per (block, peer) in a small symmetric pad; a rank publishes a monotone sequence number with
-// st.release.sys and polls its own pad with ld.acquire.sys -- no reset, no ABA.  Every poll loop is bounded; a timeout sets
-// an error flag instead of hanging the device.
+// st.release.sys and polls its own pad with ld.acquire.sys -- no reset, no ABA.  The sequence number lives in DEVICE memory
+// (one call counter per block behind the signal words of the local pad, advanced by the kernel itself), so the launch has no
+// per-call argument and can be captured into a CUDA graph and replayed: a whole sharded step -- forward, per-observation
+// kernel, this collective, backward -- is then one graph launch.  Every poll loop is bounded; a timeout sets an error flag
+// instead of hanging the device.
 #pragma once
 #include "common.cuh"
 
 namespace vggp {
 
 constexpr int AR_MAX_RANKS = 8;
-constexpr int AR_BLOCKS = 16;
-constexpr int AR_THREADS = 256;
+constexpr int AR_BLOCKS = 64;              // most blocks a call uses (the launch picks 8..64 from the buffer size: ar_blocks)
+constexpr int AR_THREADS = 512;
+constexpr int AR_UNROLL = 4;               // 16-byte units a thread keeps in flight
+constexpr int AR_PAD_WORDS = AR_BLOCKS * AR_MAX_RANKS + AR_BLOCKS;
 constexpr unsigned int AR_SPIN_LIMIT = 1u << 24;      // ~ 0.1 - 1 s of polling, then give up
 
 struct ArArgs {
     void* mc;                              // multicast address of the buffer, or null
     void* buf[AR_MAX_RANKS];               // unicast address of every rank's buffer in this process (buf[rank] = local)
-    unsigned int* pad[AR_MAX_RANKS];       // every rank's signal pad: AR_BLOCKS x AR_MAX_RANKS words
+    unsigned int* pad[AR_MAX_RANKS];       // every rank's signal pad: AR_BLOCKS x AR_MAX_RANKS signal words, then (local
+                                           // use only) AR_BLOCKS call counters; AR_PAD_WORDS words, zeroed once at setup
     int rank, world;
     i64 n_obs;                             // values of the observation dtype in the first block
     int obs_f32;
     i64 scal_off;                          // byte offset of the float64 scalars
     int n_scal;
-    unsigned int seq;                      // barrier sequence number of this call (two are used: seq, seq + 1)
     int* err;                              // device flag: set to 1 on a barrier timeout
 };
 
@@ -109,22 +114,40 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a, unsigned int seq) {
 }
 
 __global__ void __launch_bounds__(AR_THREADS) k_allreduce_gbuf(const __grid_constant__ ArArgs a) {
-    ar_barrier(a, a.seq);                  // every rank's buffer is complete (its producers ran earlier on its stream)
+    // call number of this block (same on every rank: all ranks make the same sequence of calls); barrier numbers 2 c + 1, 2 c + 2
+    unsigned int* counter = a.pad[a.rank] + AR_BLOCKS * AR_MAX_RANKS + blockIdx.x;
+    const unsigned int seq = 2u * *counter + 1u;
+    ar_barrier(a, seq);                    // every rank's buffer is complete (its producers ran earlier on its stream)
     const int W = a.world, r = a.rank;
-    const i64 tid = (i64)blockIdx.x * AR_THREADS + threadIdx.x, nthr = (i64)AR_BLOCKS * AR_THREADS;
+    const i64 tid = (i64)blockIdx.x * AR_THREADS + threadIdx.x, nthr = (i64)gridDim.x * AR_THREADS;
     const i64 esz = a.obs_f32 ? 4 : 8;
-    // the observation block in units of 16 bytes; rank r owns units [lo, hi)
+    // the observation block in units of 16 bytes; rank r owns units [lo, hi).  A thread keeps AR_UNROLL units in flight: the
+    // loads of a batch are all issued before the first store (a reduction in the switch is a round trip of a few microseconds)
     const i64 units = a.n_obs * esz / 16;
     const i64 lo = units * r / W, hi = units * (r + 1) / W;
     if (a.mc) {
         unsigned char* mc = reinterpret_cast<unsigned char*>(a.mc);
         if (a.obs_f32) {
-            for (i64 u = lo + tid; u < hi; u += nthr) mc_st_f32x4(mc + 16 * u, mc_ld_reduce_f32x4(mc + 16 * u));
+            for (i64 u = lo + tid; u < hi; u += AR_UNROLL * nthr) {
+                float4 v[AR_UNROLL];
+#pragma unroll
+                for (int k = 0; k < AR_UNROLL; ++k) if (u + k * nthr < hi) v[k] = mc_ld_reduce_f32x4(mc + 16 * (u + k * nthr));
+#pragma unroll
+                for (int k = 0; k < AR_UNROLL; ++k) if (u + k * nthr < hi) mc_st_f32x4(mc + 16 * (u + k * nthr), v[k]);
+            }
         } else {
-            for (i64 u = lo + tid; u < hi; u += nthr) {
-                const double x = mc_ld_reduce_f64(mc + 16 * u), y = mc_ld_reduce_f64(mc + 16 * u + 8);
-                mc_st_f64(mc + 16 * u, x);
-                mc_st_f64(mc + 16 * u + 8, y);
+            for (i64 u = lo + tid; u < hi; u += AR_UNROLL * nthr) {
+                double x[AR_UNROLL], y[AR_UNROLL];
+#pragma unroll
+                for (int k = 0; k < AR_UNROLL; ++k) if (u + k * nthr < hi) {
+                    x[k] = mc_ld_reduce_f64(mc + 16 * (u + k * nthr));
+                    y[k] = mc_ld_reduce_f64(mc + 16 * (u + k * nthr) + 8);
+                }
+#pragma unroll
+                for (int k = 0; k < AR_UNROLL; ++k) if (u + k * nthr < hi) {
+                    mc_st_f64(mc + 16 * (u + k * nthr), x[k]);
+                    mc_st_f64(mc + 16 * (u + k * nthr) + 8, y[k]);
+                }
             }
         }
         if (r == 0 && blockIdx.x == 0) {           // tail of the observation block and the float64 scalars
@@ -141,20 +164,24 @@ __global__ void __launch_bounds__(AR_THREADS) k_allreduce_gbuf(const __grid_cons
     } else {
         if (a.obs_f32) {
             for (i64 u = lo + tid; u < hi; u += nthr) {
+                float4 v[AR_MAX_RANKS];
+#pragma unroll
+                for (int p = 0; p < AR_MAX_RANKS; ++p)
+                    if (p < W) v[p] = ld_sys_f32x4(reinterpret_cast<const unsigned char*>(a.buf[p]) + 16 * u);
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int p = 0; p < W; ++p) {
-                    const float4 v = ld_sys_f32x4(reinterpret_cast<const unsigned char*>(a.buf[p]) + 16 * u);
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                }
+#pragma unroll
+                for (int p = 0; p < AR_MAX_RANKS; ++p) if (p < W) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
                 for (int p = 0; p < W; ++p) *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(a.buf[p]) + 16 * u) = s;
             }
         } else {
             for (i64 u = lo + tid; u < hi; u += nthr) {
+                double2 v[AR_MAX_RANKS];
+#pragma unroll
+                for (int p = 0; p < AR_MAX_RANKS; ++p)
+                    if (p < W) v[p] = ld_sys_f64x2(reinterpret_cast<const unsigned char*>(a.buf[p]) + 16 * u);
                 double2 s = make_double2(0.0, 0.0);
-                for (int p = 0; p < W; ++p) {
-                    const double2 v = ld_sys_f64x2(reinterpret_cast<const unsigned char*>(a.buf[p]) + 16 * u);
-                    s.x += v.x; s.y += v.y;
-                }
+#pragma unroll
+                for (int p = 0; p < AR_MAX_RANKS; ++p) if (p < W) { s.x += v[p].x; s.y += v[p].y; }
                 for (int p = 0; p < W; ++p) *reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(a.buf[p]) + 16 * u) = s;
             }
         }
@@ -181,7 +208,15 @@ __global__ void __launch_bounds__(AR_THREADS) k_allreduce_gbuf(const __grid_cons
         }
     }
     __threadfence_system();
-    ar_barrier(a, a.seq + 1);              // every slice has been written everywhere
+    ar_barrier(a, seq + 1);                // every slice has been written everywhere
+    if (threadIdx.x == 0) *counter = (seq + 1u) >> 1;
+}
+
+// blocks of a call: enough threads for AR_UNROLL units each, 8..AR_BLOCKS; a function of the sizes only (identical on all ranks)
+inline int ar_blocks(i64 n_obs, int esz, int world) {
+    const i64 per_rank = n_obs * esz / 16 / world;
+    const i64 b = (per_rank + (i64)AR_THREADS * AR_UNROLL - 1) / ((i64)AR_THREADS * AR_UNROLL);
+    return (int)(b < 8 ? 8 : (b > AR_BLOCKS ? AR_BLOCKS : b));
 }
 #endif  // VGGP_EMUL
 

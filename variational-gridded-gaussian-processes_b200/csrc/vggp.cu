@@ -1875,12 +1875,12 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
     return obs_binned_dispatch(p, desc, binned, gbuf, st);
 }
 
-int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, uint32_t seq, int* err_flag, void* stream) {
+int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, int* err_flag, void* stream) {
     if (!p || !desc || !err_flag) return fail(VGGP_E_ARG, "null argument");
     if (desc->world < 1 || desc->world > AR_MAX_RANKS || desc->rank < 0 || desc->rank >= desc->world)
         return fail(VGGP_E_ARG, "world must be 1..8 and rank inside it");
 #ifdef VGGP_EMUL
-    (void)seq; (void)stream;
+    (void)stream;
     return fail(VGGP_E_UNSUPPORTED, "the peer-memory collective needs NVLink peers");
 #else
     if (desc->world == 1) return 0;
@@ -1896,8 +1896,8 @@ int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, uint32_t seq, in
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.n_obs = n_elems; a.obs_f32 = p->obs_dtype == VGGP_F32; a.scal_off = soff; a.n_scal = (int)nsc;
-    a.seq = seq; a.err = err_flag;
-    k_allreduce_gbuf<<<AR_BLOCKS, AR_THREADS, 0, (cudaStream_t)stream>>>(a);
+    a.err = err_flag;
+    k_allreduce_gbuf<<<ar_blocks(n_elems, a.obs_f32 ? 4 : 8, a.world), AR_THREADS, 0, (cudaStream_t)stream>>>(a);
     VGGP_LAUNCH_CHECK();
     return 0;
 #endif

@@ -53,18 +53,36 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
-def spatial_reshard(xs, y, keys: torch.Tensor, n_keys: int, group=None):
+def spatial_reshard(xs, y, keys: torch.Tensor, n_keys: int, group=None, balance: str = "count"):
     """One-time exchange (setup): give every rank a contiguous range of grid cells instead of a contiguous range of
     acquisition order, so that each rank's observations stay dense per cell (the fused kernel flushes gradients per
-    cell, its cost per observation grows when a rank sees only a few observations of each cell).
+    cell run, its cost per observation grows when a rank sees only a few observations of each cell).
 
     xs, y   this rank's observations (any order); keys = flat cell id of each observation in [0, n_keys]
-            (n_keys = outside the mesh).  Observation k goes to rank  keys[k] * world // (n_keys + 1).
-    Returns the observations this rank owns afterwards.  Pure torch.distributed plumbing (all_to_all_single)."""
+            (n_keys = outside the mesh).
+    balance "count": the cell ranges are cut at the quantiles of the GLOBAL per-cell observation histogram, so every
+            rank ends up with about N / world observations however uneven the coverage (satellite tracks revisit some
+            cells far more often); "cells": equal cell ranges, observation k goes to rank keys[k] * world // (n_keys + 1)
+            (round-1 behaviour: unbalanced for track data).
+    Returns the observations this rank owns afterwards.  Pure torch.distributed plumbing (all_reduce of the histogram,
+    all_to_all_single of the data)."""
     world = dist.get_world_size(group)
     if world == 1:
         return xs, y
-    dest = (keys.to(torch.int64) * world) // (n_keys + 1)
+    k64 = keys.to(torch.int64)
+    if balance == "count":
+        hist = torch.bincount(k64, minlength=n_keys + 1)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        csum = torch.cumsum(hist, 0)
+        total = csum[-1]
+        # cut r (r = 1 .. world - 1): first cell whose cumulative count reaches r N / world
+        targets = (total * torch.arange(1, world, device=keys.device, dtype=torch.int64)) // world
+        cuts = torch.searchsorted(csum, targets, right=False)
+        dest = torch.searchsorted(cuts, k64, right=False)
+    elif balance == "cells":
+        dest = (k64 * world) // (n_keys + 1)
+    else:
+        raise ValueError("balance must be 'count' or 'cells'")
     order = torch.argsort(dest, stable=True)
     send_counts = torch.bincount(dest, minlength=world)
     recv_counts = torch.empty_like(send_counts)

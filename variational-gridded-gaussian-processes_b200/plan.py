@@ -211,20 +211,24 @@ class GridPlan:
             raise ValueError("the peer-memory collective covers one NVSwitch node (<= 8 ranks)")
         with torch.cuda.device(self.device):
             buf = symm.empty(self.gbuf_bytes, dtype=torch.uint8, device=self.device)
-            pad = symm.empty(16 * 8, dtype=torch.int32, device=self.device)
+            pad = symm.empty(576, dtype=torch.int32, device=self.device)     # VGGP_AR_PAD_WORDS
             buf.zero_()
             pad.zero_()
             hb = symm.rendezvous(buf, grp)
             hp = symm.rendezvous(pad, grp)
         desc = _lib.ArDesc()
+        # the handle's pointers address the allocation block; the tensor sits `offset` bytes into it (0 for its own block)
+        ob, op = int(getattr(hb, "offset", 0) or 0), int(getattr(hp, "offset", 0) or 0)
         mc = int(getattr(hb, "multicast_ptr", 0) or 0)
-        desc.mc_ptr = mc if mc else None
+        desc.mc_ptr = (mc + ob) if mc else None
         for r in range(world):
-            desc.buf_ptrs[r] = int(hb.buffer_ptrs[r])
-            desc.pad_ptrs[r] = int(hp.buffer_ptrs[r])
+            desc.buf_ptrs[r] = int(hb.buffer_ptrs[r]) + ob
+            desc.pad_ptrs[r] = int(hp.buffer_ptrs[r]) + op
+        if desc.buf_ptrs[rank] != buf.data_ptr() or desc.pad_ptrs[rank] != pad.data_ptr():
+            raise RuntimeError("symmetric-memory handle does not address the local tensors")
         desc.rank, desc.world = rank, world
         self.gbuf = buf
-        self._ar = {"desc": desc, "handles": (hb, hp), "pad": pad, "seq": 1,
+        self._ar = {"desc": desc, "handles": (hb, hp), "pad": pad,
                     "err": torch.zeros(1, dtype=torch.int32, device=self.device)}
         torch.cuda.synchronize(self.device)
         dist.barrier(grp)                   # every pad is zeroed before the first signal arrives
@@ -243,9 +247,8 @@ class GridPlan:
         g = self.gbuf if gbuf is None else gbuf
         ar = getattr(self, "_ar", None)
         if ar is not None and g is self.gbuf:
-            _lib.check(self.lib.vggp_allreduce_gbuf(self.handle, C.byref(ar["desc"]), ar["seq"], ar["err"].data_ptr(),
+            _lib.check(self.lib.vggp_allreduce_gbuf(self.handle, C.byref(ar["desc"]), ar["err"].data_ptr(),
                                                     _stream_ptr(self.device)))
-            ar["seq"] = (ar["seq"] + 2) & 0xFFFFFFFF
             return
         obs, scal = self.gbuf_views(g)
         allreduce_gbuf_views(g, obs, scal, group)
@@ -264,9 +267,12 @@ class GridPlan:
     def graphed_step(self, theta, m, L, xs, y=None, ell_scale: float = 1.0, group=None, warmup: int = 3):
         """Capture the C-ABI launches of one step into CUDA graphs (opt-in; removes the launch gaps between the ~15
         small kernels).  `theta`, `m`, `L` and the observations are STATIC device buffers: write new parameter values
-        into them (copy_) and call `.replay()`.  The all-reduce is NOT captured -- a round-1 run with NCCL inside the
-        graph did not shut down cleanly -- so a sharded step is two graphs around one eager all-reduce."""
+        into them (copy_) and call `.replay()`.  An NCCL all-reduce is NOT captured -- a round-1 run with NCCL inside the
+        graph did not shut down cleanly -- so a sharded step over NCCL is two graphs around one eager all-reduce.  After
+        `enable_peer_allreduce` the collective is this library's own kernel (no per-call argument) and the whole sharded
+        step is ONE graph."""
         gs = GraphedStep(self, group)
+        peer = group is not None and getattr(self, "_ar", None) is not None
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -278,9 +284,11 @@ class GridPlan:
         with torch.cuda.graph(gs.front):
             self.grid_forward(theta, m, L)
             self.obs_fwd_bwd(xs, y)
-            if group is None:
+            if peer:
+                self.allreduce_gbuf(None)
+            if group is None or peer:
                 gs.outs = self.grid_backward(theta, m, L, ell_scale)
-        if group is not None:
+        if group is not None and not peer:
             gs.back = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gs.back):
                 gs.outs = self.grid_backward(theta, m, L, ell_scale)
@@ -386,7 +394,7 @@ class GraphedStep:
 
     def replay(self):
         self.front.replay()
-        if self.group is not None:
+        if self.back is not None:
             self.plan.allreduce_gbuf(None if isinstance(self.group, str) else self.group)
             self.back.replay()
         return self.outs
