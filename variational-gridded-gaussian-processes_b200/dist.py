@@ -17,17 +17,13 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def allreduce_gbuf_views(raw: torch.Tensor, obs: torch.Tensor, scal: torch.Tensor, group=None) -> None:
-    """Sum the gradient buffer over ranks with ONE collective launch.  float64 observations: the whole allocation is one
-    float64 vector.  float32 observations: the float32 block and the float64 scalar block are two typed views of the same
-    allocation; on NCCL they go out inside one group (ncclGroupStart / End through torch's coalescing manager: one kernel
-    launch, one pass over NVLink), on backends without coalescing (gloo, the CPU tests) as two calls back to back."""
+    """Sum the gradient buffer over ranks through torch.distributed (the fallback; the product's collective is the library's own
+    one-kernel all-reduce over NVLink peer memory, GridPlan.enable_peer_allreduce).  float64 observations: the whole allocation
+    is one float64 vector, one call.  float32 observations: the float32 block and the 8 float64 scalars are two typed views of
+    the same allocation and go out as two calls back to back (NCCL cannot mix element types in one launch: torch's coalescing
+    manager rejects it, "Tensors must have identical type", measured on B200 in round 2)."""
     if obs.dtype == torch.float64 and raw.numel() % 8 == 0:
         dist.all_reduce(raw.view(torch.float64), op=dist.ReduceOp.SUM, group=group)
-        return
-    if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
-        with dist._coalescing_manager(group=group, device=obs.device, async_ops=False):
-            dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
         return
     dist.all_reduce(obs, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
