@@ -106,13 +106,15 @@ def test_fast_and_generic_fibre_kernels_agree_under_emulation(emu):
     """k_fibre_pass_fast (M_d <= 512, the default) against the generic k_fibre_pass on the same step (2-D and 3-D, sizes that
     leave partial tiles, partial lanes and absent fibres)."""
     lib, L = emu
-    for knots, N in (((37, 50), 1200), ((21, 13, 18), 900), ((300,), 700)):
+    for knots, N in (((37, 50), 1200), ((21, 13, 18), 900), ((300,), 700), ((70, 130), 1500), ((9, 200, 33), 1500)):
         D = len(knots)
         meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5 + D)
         theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
         xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
         res = []
-        for fast in (1, 0):
+        # 5 = fast kernel with fibre packing forced (2, 4 or 8 fibres per 512-slot row: contiguous and strided modes, windows
+        # wider than n, partial rows and tiles), 3 = fast kernel without packing, 0 = generic kernel
+        for fast in (5, 3, 0):
             lib.vggp_debug_fp_fast(fast)
             try:
                 plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
@@ -121,8 +123,9 @@ def test_fast_and_generic_fibre_kernels_agree_under_emulation(emu):
                 plan.close()
             finally:
                 lib.vggp_debug_fp_fast(1)
-        for a, b in zip(res[0], res[1]):
-            assert relerr(a, torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-11
+        for other in res[:2]:
+            for a, b in zip(other, res[2]):
+                assert relerr(a, torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-11
 
 
 @pytest.mark.parametrize("layout", ["packed_sorted", "binned_ldg"])

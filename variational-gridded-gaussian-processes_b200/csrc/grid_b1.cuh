@@ -49,6 +49,7 @@ struct FpTask {
     const void* t0;               // GA*: galpha;  DL: band sums of dimension d [bp_d | bp_o | bq_d | bq_o] (obs dtype)
     void* t1;                     // ALPHA: alpha in the observation dtype
     int direct;                   // GA with D == 1: o0 receives dm = V - alpha
+    int pk;                       // k_fibre_pass_fast only: a 512-slot row of the tile holds 2^pk fibres (mode-product kinds, M_d <= 256)
 };
 
 struct FpPass {

@@ -7,7 +7,11 @@
 //     without a single select or branch;
 //   * a thread's elements are an arithmetic progression in both the global and the shared address (element step 32 .. 256,
 //     a multiple of 16), so all index arithmetic is two additions per element;
-//   * the generator loads, the tile loads and (dL tasks) the band loads are all issued before the first shared-memory store.
+//   * the generator loads, the tile loads and (dL tasks) the band loads are all issued before the first shared-memory store;
+//   * FIBRE PACKING (mode-product kinds, FpTask::pk): for M_d <= 256 a 512-slot row holds 2^pk real fibres side by side, each in
+//     its own window of npad = 512 >> pk slots.  The recurrences need no change: the generators are staged periodically and
+//     rl[n - 1] = 0 = ru[-1], so nothing carries from one fibre into the next, and identity slots between fibres carry zeros.
+//     A 3-D 256 x 256 x 64 grid swept 512 slots for 64 live elements (8 x the work, 8 x the CTAs) before this.
 #pragma once
 #include "grid_b1.cuh"
 
@@ -26,7 +30,7 @@ __device__ __forceinline__ int ff_p(int i) { return i + (i >> 4); }
 // one warp, one fibre (see fp_fibre): X holds x_i on entry and y_i = (P x)_i on exit; pd / rl / rup are padded with the
 // identity (0, 1, 1) past n and rup[p(i)] = ru[i - 1] (0 for i = 0)
 __device__ __forceinline__ void ff_fibre(const double* __restrict__ pd, const double* __restrict__ rl,
-                                         const double* __restrict__ rup, double* __restrict__ X, int lane, int n) {
+                                         const double* __restrict__ rup, double* __restrict__ X, int lane, int n, int mask) {
     const int p0 = lane * FF_LS;
     double sv[16];
 #pragma unroll
@@ -66,28 +70,47 @@ __device__ __forceinline__ void ff_fibre(const double* __restrict__ pd, const do
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const double r = rl[p0 + j];
-        if (i0 + j < n) X[p0 + j] = sv[j] + l + uu[j];
+        if (((i0 + j) & mask) < n) X[p0 + j] = sv[j] + l + uu[j];
         l = fma(r, l, r * sv[j]);
     }
 }
 
-// acc[dl + 1][i] += sum over the fibres [f0, f1) of Y[f][i] * Cx[f - f0][i + dl]
+// acc[dl + 1][i] += sum over the rows [f0, f1) and the 2^lg-slot windows of a row of Y[f][w + i] * Cx[f - f0][w + i + dl].
+// `scr` (3 x 512 doubles: the generator arrays, free after the recurrences) holds the per-window partial sums so that one
+// atomic per (dl, i) leaves the CTA however many fibres a row packs.
 __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const double* __restrict__ Cx, int f0, int f1, int n,
-                                             double* __restrict__ acc) {
-    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
-        const int p = ff_p(i);
-        const int pm = (i > 0) ? ff_p(i - 1) : p, pp = (i + 1 < n) ? ff_p(i + 1) : p;
+                                             int lg, double* __restrict__ scr, double* __restrict__ acc) {
+    const int mask = (1 << lg) - 1;
+    const bool packed = lg < 9;
+    for (int s_ = threadIdx.x; s_ < 512; s_ += FP_THREADS) {
+        const int i = s_ & mask;
         double am = 0.0, a0 = 0.0, ap = 0.0;
-        for (int f = f0; f < f1; ++f) {
-            const double y = Y[f * FF_PITCH + p];
-            const double* c = Cx + (f - f0) * FF_PITCH;
-            am = fma(y, c[pm], am);
-            a0 = fma(y, c[p], a0);
-            ap = fma(y, c[pp], ap);
+        if (i < n) {
+            const int p = ff_p(s_);
+            const int pm = (i > 0) ? ff_p(s_ - 1) : p, pp = (i + 1 < n) ? ff_p(s_ + 1) : p;
+            for (int f = f0; f < f1; ++f) {
+                const double y = Y[f * FF_PITCH + p];
+                const double* c = Cx + (f - f0) * FF_PITCH;
+                am = fma(y, c[pm], am);
+                a0 = fma(y, c[p], a0);
+                ap = fma(y, c[pp], ap);
+            }
+            if (!packed) {
+                if (i > 0) atomicAdd(acc + i, am);
+                atomicAdd(acc + n + i, a0);
+                if (i + 1 < n) atomicAdd(acc + 2 * n + i, ap);
+            }
         }
-        if (i > 0) atomicAdd(acc + i, am);
-        atomicAdd(acc + n + i, a0);
-        if (i + 1 < n) atomicAdd(acc + 2 * n + i, ap);
+        if (packed) { scr[s_] = am; scr[512 + s_] = a0; scr[1024 + s_] = ap; }
+    }
+    if (!packed) return;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 3 * n; e += FP_THREADS) {
+        const int k = e / n, i = e - k * n;
+        double v = 0.0;
+        for (int w = 0; w < 512; w += mask + 1) v += scr[k * 512 + w + i];
+        if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
+        atomicAdd(acc + k * n + i, v);
     }
 }
 
@@ -113,39 +136,59 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
     const double cg = P.ell_scale / noise;
     const double cQ = -P.ell_scale / (2.0 * noise);
     const bool contiguous = (tk.inner == 1);
-    const int nsrc = (kind == FP_GA) ? FF_F / 2 : FF_F;               // source fibres of a tile
+    const int nsrc = (kind == FP_GA) ? FF_F / 2 : FF_F;               // source rows of a tile
     const int sh = (kind == FP_GA) ? 2 : 3;
-    const i64 fib0 = (i64)tile * nsrc;
-    const int nf = (int)min((i64)nsrc, tk.nfib - fib0);
-    // ---- this thread's elements: fibre f, elements i0, i0 + di, ... (< n): arithmetic progressions everywhere
-    int f, i0, di;
-    i64 a0, da;
-    if (contiguous) {                               // FP_THREADS / nsrc consecutive threads walk one fibre
-        di = FP_THREADS >> sh;
+    // fibre packing: a row holds 2^pk real fibres in windows of npad = 512 >> pk slots (pk = 0: one fibre per row)
+    const int pk = tk.pk, lg = 9 - pk, npad = 1 << lg, mask = npad - 1;
+    const i64 fib0 = (i64)tile * (nsrc << pk);                        // first real fibre of the tile
+    const int nf = (int)min((i64)(nsrc << pk), tk.nfib - fib0);       // real fibres of the tile
+    // rows that hold at least one of them (contiguous: fibre q in row q >> pk; strided: in row q mod nsrc)
+    const int nrows = contiguous ? (nf + (1 << pk) - 1) >> pk : min(nf, nsrc);
+    // ---- this thread's slots: row f, slots s0, s0 + ds, ... (< 512): arithmetic progressions in the shared AND the global
+    // address, up to a correction per window for non-power-of-two n in the contiguous case:
+    //   slot(u) = s0 + u ds,   element = slot & mask,   window = slot >> lg,
+    //   global address = a0 + u da - window * gap,   real fibre = fid0 + window * fstep
+    int f, s0, ds, gap, fstep;
+    i64 a0, da, fid0;
+    if (contiguous) {                               // FP_THREADS / nsrc consecutive threads walk one row
+        ds = FP_THREADS >> sh;
         f = tid >> (8 - sh);
-        i0 = tid & (di - 1);
-        a0 = (fib0 + f) * (i64)n + i0;
-        da = di;
-    } else {                                        // nsrc consecutive threads take the nsrc fibres of one element index
-        di = FP_THREADS >> sh;
-        f = tid & (nsrc - 1);
-        i0 = tid >> sh;
-        const i64 fg = fib0 + f;
+        s0 = tid & (ds - 1);
+        fid0 = fib0 + ((i64)f << pk);
+        a0 = fid0 * (i64)n + s0;
+        da = ds;
+        gap = npad - n;
+        fstep = 1;
+    } else {                                        // nsrc 2^pk consecutive threads take the tile's fibres at one element index
+        const int q = tid & ((nsrc << pk) - 1);     // real fibre of the tile; consecutive q are adjacent in memory
+        f = q & (nsrc - 1);
+        const int e0 = tid >> (sh + pk);
+        ds = FP_THREADS >> (sh + pk);
+        s0 = (q >> sh) * npad + e0;
+        fid0 = fib0 + q;
         const unsigned inner = (unsigned)tk.inner;
-        const unsigned o = (unsigned)fg / inner, r = (unsigned)fg - o * inner;      // fg, inner < 2^31
-        a0 = ((i64)o * n + i0) * (i64)inner + r;
-        da = (i64)di * (i64)inner;
+        const unsigned o = (unsigned)fid0 / inner, r = (unsigned)fid0 - o * inner;      // fid0, inner < 2^31
+        a0 = ((i64)o * n + e0) * (i64)inner + r;
+        da = (i64)ds * (i64)inner;
+        gap = 0;
+        fstep = 0;
     }
-    const bool live = f < nf;
-    const int p0 = ff_p(i0), dp = di + (di >> 4);
-    const int xo = f * FF_PITCH + p0;               // shared offset of (f, i0)
+    const int xrow = f * FF_PITCH;
+    const i64 nfib = tk.nfib;
+#define FF_SLOT(u) (s0 + (u) * ds)
+#define FF_OK(u) (FF_SLOT(u) < 512 && (FF_SLOT(u) & mask) < n && fid0 + (i64)((FF_SLOT(u) >> lg) * fstep) < nfib)
+#define FF_GA(u) (a0 + (u) * da - (i64)((FF_SLOT(u) >> lg) * gap))
+#define FF_SO(u) (xrow + ff_p(FF_SLOT(u)))
+    // R / DL tasks (pk == 0, strided in the factor): column k = fib0 + f, rows i0 + u di
+    const int i0 = s0, di = ds;
+    const bool live = fib0 + f < nfib;
     constexpr int MAXU = 16;                        // n / di <= 512 / 32
     // ---- issue every global load of the prologue, then store
     const double* __restrict__ gen = P.gen[d];
     double g0[2], g1[2], g2[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        const int i = tid + u * FP_THREADS;
+        const int i = (tid + u * FP_THREADS) & mask;                // periodic over the windows of a row
         g0[u] = (i < n) ? gen[i] : 0.0;                              // pd
         g1[u] = (i < n) ? gen[2 * n + i] : 1.0;                      // rl (0 at n - 1)
         g2[u] = (i < n) ? (i > 0 ? gen[n + i - 1] : 0.0) : 1.0;      // ru shifted by one
@@ -164,7 +207,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
         case FP_PROD: case FP_ALPHA: case FP_DM: {
             const double* __restrict__ src = tk.s0;
 #pragma unroll
-            for (int u = 0; u < MAXU; ++u) v[u] = (live && i0 + u * di < n) ? src[a0 + u * da] : 0.0;
+            for (int u = 0; u < MAXU; ++u) v[u] = FF_OK(u) ? src[FF_GA(u)] : 0.0;
         } break;
         case FP_DL: {
             const double* __restrict__ R = tk.s0;
@@ -189,23 +232,23 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
 #pragma unroll
             for (int u8 = 0; u8 < 8; ++u8) {
                 const int u = h * 8 + u8;
-                const bool ok = live && i0 + u * di < n;
-                gv[u8] = ok ? (double)ga[a0 + u * da] : 0.0;
-                mv[u8] = ok ? m[a0 + u * da] : 0.0;
-                av[u8] = ok ? al[a0 + u * da] : 0.0;
+                const bool ok = FF_OK(u);
+                gv[u8] = ok ? (double)ga[FF_GA(u)] : 0.0;
+                mv[u8] = ok ? m[FF_GA(u)] : 0.0;
+                av[u8] = ok ? al[FF_GA(u)] : 0.0;
             }
 #pragma unroll
             for (int u8 = 0; u8 < 8; ++u8) {
                 const int u = h * 8 + u8;
-                if (i0 + u * di < 512) {               // all 512 slots are written: zeros past n and for absent fibres
+                if (FF_SLOT(u) < 512) {                // all 512 slots are written: zeros past n and for absent fibres
                     const double gg = cg * gv[u8], hh = gg - 0.5 * mv[u8];
                     if (both) {
-                        X[xo + u * dp] = gg;
-                        X[xo + nsrc * FF_PITCH + u * dp] = hh;
+                        X[FF_SO(u)] = gg;
+                        X[FF_SO(u) + nsrc * FF_PITCH] = hh;
                     } else {
-                        X[xo + u * dp] = hh;
+                        X[FF_SO(u)] = hh;
                     }
-                    Cx[xo + u * dp] = av[u8];
+                    Cx[FF_SO(u)] = av[u8];
                 }
             }
         }
@@ -219,7 +262,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
         }
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (i0 + u * di < 512) Cx[xo + u * dp] = v[u];
+            if (FF_SLOT(u) < 512) Cx[FF_SO(u)] = v[u];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + u * FP_THREADS;
@@ -228,7 +271,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
     } else {
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (i0 + u * di < 512) X[xo + u * dp] = v[u];
+            if (FF_SLOT(u) < 512) X[FF_SO(u)] = v[u];
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -246,18 +289,18 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
             if (i < 512) {
                 double r = 0.0;
                 if (i < n) {
-                    const int p = p0 + u * dp;
+                    const int p = ff_p(i);
                     r = bqs[i] * c[p];
                     if (i > 0) r = fma(bqs[512 + i - 1], c[ff_p(i - 1)], r);
                     if (i + 1 < n) r = fma(bqs[512 + i], c[ff_p(i + 1)], r);
                 }
-                X[xo + u * dp] = r;
+                X[FF_SO(u)] = r;
             }
         }
         __syncthreads();
     }
     // ---- recurrences: one warp per fibre
-    ff_fibre(pd, rl, rup, X + warp * FF_PITCH, lane, n);
+    ff_fibre(pd, rl, rup, X + warp * FF_PITCH, lane, n, mask);
     __syncthreads();
     // ---- epilogues
     switch (kind) {
@@ -267,14 +310,14 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
                 const int i = i0 + u * di;
-                if (live && i < n) R[(i64)i * n + k] = X[xo + u * dp];
+                if (live && i < n) R[(i64)i * n + k] = X[FF_SO(u)];
             }
         } break;
         case FP_PROD: {
             double* __restrict__ dst = tk.o0;
 #pragma unroll
             for (int u = 0; u < MAXU; ++u)
-                if (live && i0 + u * di < n) dst[a0 + u * da] = X[xo + u * dp];
+                if (FF_OK(u)) dst[FF_GA(u)] = X[FF_SO(u)];
         } break;
         case FP_DM: case FP_ALPHA: {
             double* __restrict__ dst = tk.o0;
@@ -282,17 +325,17 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
             T* __restrict__ aT = reinterpret_cast<T*>(tk.t1);
             double w[MAXU];
 #pragma unroll
-            for (int u = 0; u < MAXU; ++u) w[u] = (live && i0 + u * di < n) ? al[a0 + u * da] : 0.0;
+            for (int u = 0; u < MAXU; ++u) w[u] = FF_OK(u) ? al[FF_GA(u)] : 0.0;
             double dot = 0.0;
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
-                if (live && i0 + u * di < n) {
-                    const double y = X[xo + u * dp];
+                if (FF_OK(u)) {
+                    const double y = X[FF_SO(u)];
                     if (kind == FP_DM) {
-                        dst[a0 + u * da] = y - w[u];
+                        dst[FF_GA(u)] = y - w[u];
                     } else {
-                        dst[a0 + u * da] = y;
-                        aT[a0 + u * da] = (T)y;
+                        dst[FF_GA(u)] = y;
+                        aT[FF_GA(u)] = (T)y;
                         dot = fma(y, w[u], dot);
                     }
                 }
@@ -306,15 +349,15 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
             double* __restrict__ dst = tk.o0;
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
-                if (live && i0 + u * di < n) {
-                    const double y = X[xo + u * dp];
-                    dst[a0 + u * da] = tk.direct ? y - Cx[xo + u * dp] : y;      // Cx holds alpha of these fibres
+                if (FF_OK(u)) {
+                    const double y = X[FF_SO(u)];
+                    dst[FF_GA(u)] = tk.direct ? y - Cx[FF_SO(u)] : y;            // Cx holds alpha of these fibres
                 }
             }
-            ff_band_dots(X, Cx, nsrc, nsrc + nf, n, P.acc[d]);
+            ff_band_dots(X, Cx, nsrc, nsrc + nrows, n, lg, pd, P.acc[d]);       // the generator arrays are scratch by now
         } break;
         case FP_GAONLY:
-            ff_band_dots(X, Cx, 0, nf, n, P.acc[d]);
+            ff_band_dots(X, Cx, 0, nrows, n, lg, pd, P.acc[d]);
             break;
         case FP_DL: {
             double* __restrict__ dL = tk.o0;
@@ -331,16 +374,20 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
                 if (live && i < n) {
                     double vv = 0.0;
                     if ((i64)i >= k) {
-                        vv = X[xo + u * dp] - trO * Cx[xo + u * dp];
+                        vv = X[FF_SO(u)] - trO * Cx[FF_SO(u)];
                         if ((i64)i == k) vv += ratio / Lkk;
                     }
                     dL[(i64)i * n + k] = vv;
                 }
             }
-            ff_band_dots(X, Cx, 0, nf, n, P.acc[d]);
+            ff_band_dots(X, Cx, 0, nf, n, 9, pd, P.acc[d]);
         } break;
         default: break;
     }
+#undef FF_SLOT
+#undef FF_OK
+#undef FF_GA
+#undef FF_SO
 }
 
 }  // namespace vggp

@@ -503,6 +503,20 @@ FpTask fp_task(const vggp_plan* p, int kind, int d, i64 outer, i64 inner) {
     return t;
 }
 
+// Fibre packing of k_fibre_pass_fast: how many fibres (2^pk) share one 512-slot row.  Only the mode-product kinds, only while
+// the launch still has about two tiles per SM (small problems are latency-bound: more, smaller CTAs finish sooner).
+int g_fp_pack = 1;                   // 0: never, 1: by the tile-count rule below, 2: always (tests)
+int fp_pack_log2(const FpTask& t) {
+    if (!g_fp_pack || t.n > 256) return 0;
+    if (!(t.kind == FP_PROD || t.kind == FP_ALPHA || t.kind == FP_DM || t.kind == FP_GA || t.kind == FP_GAONLY)) return 0;
+    int npad = 64;
+    while (npad < t.n) npad <<= 1;
+    const int nsrc = (t.kind == FP_GA) ? FF_F / 2 : FF_F;
+    int pk = 0;
+    while ((512 >> (pk + 1)) >= npad && (g_fp_pack == 2 || t.nfib / ((i64)nsrc << (pk + 1)) >= 296)) ++pk;
+    return pk;
+}
+
 FpTask fp_mode_task(const vggp_plan* p, int kind, int e) {
     i64 outer = 1, inner = 1;
     for (int f = 0; f < e; ++f) outer *= p->n[f];
@@ -535,15 +549,20 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
     int tiles = 0;
     size_t smem = 0, smem_fast = 0;
     bool fast = g_fp_fast != 0;
+    for (int i = 0; i < P.ntasks; ++i)
+        if (P.t[i].kind != FP_QROW && (P.t[i].n > 512 || P.t[i].F != FF_F)) fast = false;
     for (int i = 0; i < P.ntasks; ++i) {
-        P.t[i].tile0 = tiles;
-        tiles += P.t[i].ntiles;
-        if (P.t[i].kind != FP_QROW) {
-            const bool aux = fp_kind_has_aux(P.t[i].kind);
-            smem = std::max(smem, fp_smem_bytes(P.t[i].n, P.t[i].F, aux));
+        FpTask& t = P.t[i];
+        if (t.kind != FP_QROW) {
+            const bool aux = fp_kind_has_aux(t.kind);
+            smem = std::max(smem, fp_smem_bytes(t.n, t.F, aux));
             smem_fast = std::max(smem_fast, ff_smem_bytes(aux));
-            if (P.t[i].n > 512 || P.t[i].F != FF_F) fast = false;
+            const int nsrc = (t.kind == FP_GA) ? t.F / 2 : t.F;
+            t.pk = fast ? fp_pack_log2(t) : 0;
+            t.ntiles = (int)((t.nfib + ((i64)nsrc << t.pk) - 1) / ((i64)nsrc << t.pk));
         }
+        t.tile0 = tiles;
+        tiles += t.ntiles;
     }
     const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
     if (fast) {
@@ -2006,7 +2025,8 @@ int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
  * (clock64 at the phase boundaries, globaltimer, kind) to `buf` (device, >= 8 * tiles of the largest pass); NULL switches it off */
 int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 /* debugging aid: 0 = run every fibre pass through the generic kernel (cross-check of k_fibre_pass_fast), 1 = default */
-int vggp_debug_fp_fast(int on) { g_fp_fast = on ? 1 : 0; return 0; }
+// 0: generic kernel; 1: fast kernel, fibre packing by rule (default); 3: fast, no packing; 5: fast, packing forced (tests)
+int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
     if (!p || !info_pinned_host) return fail(VGGP_E_ARG, "null argument");
