@@ -42,11 +42,18 @@ def read_launches(path):
 
 
 def breakdown(launches):
-    """The last complete step = the launches between the last two k_build_factors (first kernel of a step), K1 included."""
-    starts = [i for i, (k, _, _) in enumerate(launches) if "k_build_factors" in k]
+    """The last complete step = the launches between the last two first-kernels of a step (k_b1_gens on the fused B1 grid side,
+    k_build_factors on the dense path), K1 included."""
+    first = "k_b1_gens" if any("k_b1_gens" in k for k, _, _ in launches) else "k_build_factors"
+    starts = [i for i, (k, _, _) in enumerate(launches) if first in k]
     if len(starts) < 2:
         return launches
-    return launches[starts[-2]:starts[-1]]
+    steps = [launches[a:b] for a, b in zip(starts[:-1], starts[1:])]
+    # bench.py ends with a leg on the round-1 packed kernel (acquisition order): the timed steps are the ones on the default layout
+    default = [s for s in steps if any("k_obs_b1_binned" in k or "k_obs_b0s" in k for k, _, _ in s)]
+    step = (default or steps)[-1]
+    last = [i for i, (k, _, _) in enumerate(step) if "k_b1_theta" in k or "k_bwd_theta" in k]     # a step ends with the theta kernel;
+    return step[:last[-1] + 1] if last else step                                               # what follows is setup of the next leg
 
 
 def main():

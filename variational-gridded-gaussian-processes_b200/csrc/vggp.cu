@@ -3,6 +3,7 @@
 #include <vector>
 #include <algorithm>
 #include <new>
+#include <mutex>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -16,6 +17,43 @@
 #include "metrics.cuh"
 #include "b0scan.cuh"
 #include "collective.cuh"
+
+// Every plan-taking entry point runs with the plan's device current and restores the caller's device on return
+// (launches on a stream of another device fail with "invalid resource handle"; plan creation must not silently switch
+// the process's current device).
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int dev) : want(dev) {
+        if (dev < 0 || cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function attribute that lives as long as the process (per device):
+// a second, smaller plan must never lower what an earlier, larger plan opted in.  Every opt-in goes through this
+// high-water mark keyed by (function, device).
+struct SmemHwm { const void* fn; int dev; int bytes; };
+static std::vector<SmemHwm> g_smem_hwm;
+static std::mutex g_smem_mu;
+template <typename F>
+int raise_dyn_smem(F fn, size_t bytes) {
+    int dev = 0;
+    VGGP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    for (auto& e : g_smem_hwm)
+        if (e.fn == (const void*)fn && e.dev == dev) {
+            if ((int)bytes <= e.bytes) return 0;
+            VGGP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.bytes = (int)bytes;
+            return 0;
+        }
+    if (bytes > 48 * 1024) VGGP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    g_smem_hwm.push_back({(const void*)fn, dev, bytes > 48 * 1024 ? (int)bytes : 48 * 1024});
+    return 0;
+}
 
 namespace vggp {
 thread_local char g_err[512] = {0};
@@ -480,7 +518,6 @@ int build_schedules(vggp_plan* p) {
 
 // ---- fused B1 grid side (grid_b1.cuh) -------------------------------------------------------------------
 long long* g_fp_dbg = nullptr;        // debug: phase stamps of the next fibre passes (vggp_debug_fp_stamps)
-int g_fp_smem_hwm[2] = {0, 0};      // high-water mark of the dynamic shared memory opted in for k_fibre_pass<float / double>
 
 int fp_tile_F(int n, int want) {
     int F = want;
@@ -542,7 +579,6 @@ void fp_pass_init(const vggp_plan* p, FpPass& P, const double* theta, double ell
 }
 
 int g_fp_fast = 1;                   // use k_fibre_pass_fast where it applies (M_d <= 512); 0: always the generic kernel (cross-check)
-int g_ff_smem_hwm[2] = {0, 0};
 
 int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
     if (P.ntasks == 0) return 0;
@@ -566,21 +602,13 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
     }
     const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
     if (fast) {
-        if ((int)smem_fast > g_ff_smem_hwm[ti]) {      // the attribute is per function and process-wide: only ever raise it
-            if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-            else VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-            g_ff_smem_hwm[ti] = (int)smem_fast;
-        }
+        if (int rc = ti == 0 ? raise_dyn_smem(k_fibre_pass_fast<float>, smem_fast) : raise_dyn_smem(k_fibre_pass_fast<double>, smem_fast)) return rc;
         if (ti == 0) k_fibre_pass_fast<float><<<tiles, FP_THREADS, smem_fast, st>>>(P);
         else k_fibre_pass_fast<double><<<tiles, FP_THREADS, smem_fast, st>>>(P);
         VGGP_LAUNCH_CHECK();
         return 0;
     }
-    if ((int)smem > g_fp_smem_hwm[ti]) {
-        if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else VGGP_CUDA(cudaFuncSetAttribute(k_fibre_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_fp_smem_hwm[ti] = (int)smem;
-    }
+    if (int rc = ti == 0 ? raise_dyn_smem(k_fibre_pass<float>, smem) : raise_dyn_smem(k_fibre_pass<double>, smem)) return rc;
     if (ti == 0) k_fibre_pass<float><<<tiles, FP_THREADS, smem, st>>>(P);
     else k_fibre_pass<double><<<tiles, FP_THREADS, smem, st>>>(P);
     VGGP_LAUNCH_CHECK();
@@ -687,15 +715,7 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
         if ((rc = fp_launch(p, P, st))) return rc;
     }
     const size_t tsm = 7 * ((size_t)p->nmax + 34) * sizeof(double);
-    {
-        static int hwm[2] = {0, 0};              // per-function attribute, process-wide: only ever raised
-        const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
-        if ((int)tsm > 48 * 1024 && (int)tsm > hwm[ti]) {
-            if (ti == 0) VGGP_CUDA(cudaFuncSetAttribute(k_b1_theta<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-            else VGGP_CUDA(cudaFuncSetAttribute(k_b1_theta<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-            hwm[ti] = (int)tsm;
-        }
-    }
+    if (int rc = p->obs_dtype == VGGP_F32 ? raise_dyn_smem(k_b1_theta<float>, tsm) : raise_dyn_smem(k_b1_theta<double>, tsm)) return rc;
     if (p->obs_dtype == VGGP_F32)
         k_b1_theta<float><<<D, 512, tsm, st>>>(p->g, theta, p->b1_acc, reinterpret_cast<const float*>(gb) + p->M, gscal, ell_scale, out, dtheta, g_fp_dbg);
     else
@@ -740,7 +760,7 @@ template <typename T, int D>
 int obs_prepare(vggp_plan* p) {
     const size_t smem = obs_smem_bytes<T, D>(p);
     if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "band tables do not fit in shared memory");
-    VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = raise_dyn_smem(k_obs_b1<T, D>, smem)) return rc;
     int nb = 0;
     VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1<T, D>, OBS_THREADS, smem));
     p->obs_blocks_per_sm = nb < 1 ? 1 : nb;
@@ -782,6 +802,21 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
     return 0;
 }
 
+// device temporaries of a setup call: freed on every exit path unless released to a longer-lived owner
+struct DevTemps {
+    std::vector<void*> ptrs;
+    ~DevTemps() { for (void* q : ptrs) if (q) cudaFree(q); }
+    template <typename P>
+    cudaError_t alloc(P** out, size_t bytes) {
+        void* q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *out = reinterpret_cast<P*>(q);
+        return e;
+    }
+    void release(void* q) { for (void*& r : ptrs) if (r == q) r = nullptr; }
+};
+
 template <typename T, int D>
 int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort_by_cell, void* const* xp, void* yp,
               cudaStream_t st) {
@@ -797,8 +832,9 @@ int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort
     ga.yp = reinterpret_cast<T*>(yp);
     uint32_t *keys_in = nullptr, *keys_out = nullptr, *idx_in = nullptr, *idx_out = nullptr;
     void* temp = nullptr;
+    DevTemps tmp;                 // freed on every return path; the stream is drained first on the normal path
     if (sort_by_cell && n > 0) {
-        if (n >= ((i64)1 << 32)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^32 observations per shard");
+        if (n >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^31 observations per shard");
         i64 ncells = 1;
         KeyArgs<T, D> ka;
         ka.n = n;
@@ -808,10 +844,10 @@ int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort
             ncells *= (p->K[d] - 1);
         }
         if (ncells >= ((i64)1 << 32) - 1) return fail(VGGP_E_UNSUPPORTED, "too many cells for 32-bit keys");
-        VGGP_CUDA(cudaMalloc(&keys_in, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&keys_out, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&idx_in, sizeof(uint32_t) * n));
-        VGGP_CUDA(cudaMalloc(&idx_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&keys_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&keys_out, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&idx_in, sizeof(uint32_t) * n));
+        VGGP_CUDA(tmp.alloc(&idx_out, sizeof(uint32_t) * n));
         const int blocks = (int)std::min<i64>((n + 255) / 256, 148 * 16);
         k_cell_keys<T, D><<<blocks, 256, 0, st>>>(ka, (uint32_t)ncells, keys_in, idx_in);
         VGGP_LAUNCH_CHECK();
@@ -819,7 +855,7 @@ int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort
         while (((i64)1 << end_bit) <= ncells) ++end_bit;
         size_t temp_bytes = 0;
         VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
-        VGGP_CUDA(cudaMalloc(&temp, temp_bytes));
+        VGGP_CUDA(tmp.alloc(&temp, temp_bytes));
         VGGP_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, end_bit, st));
         ga.perm = idx_out;
     }
@@ -828,10 +864,7 @@ int pack_impl(vggp_plan* p, const void* const* x, const void* y, i64 n, int sort
         k_pack_gather<T, D><<<blocks, 256, 0, st>>>(ga);
         VGGP_LAUNCH_CHECK();
     }
-    if (keys_in) {
-        VGGP_CUDA(cudaStreamSynchronize(st));
-        cudaFree(keys_in); cudaFree(keys_out); cudaFree(idx_in); cudaFree(idx_out); cudaFree(temp);
-    }
+    if (keys_in) VGGP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -860,7 +893,7 @@ int launch_obs_b0(vggp_plan* p, const void* const* x, const void* y, i64 n, void
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
     const size_t smem = (size_t)5 * ntot * B0_TN * sizeof(T);
     if (smem > 200 * 1024) return fail(VGGP_E_UNSUPPORTED, "B0 feature tiles do not fit in shared memory");
-    VGGP_CUDA(cudaFuncSetAttribute(k_obs_b0<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = raise_dyn_smem(k_obs_b0<T, D>, smem)) return rc;
     const i64 tiles = (n + B0_TN - 1) / B0_TN;
     const int blocks = (int)std::min<i64>(tiles, (i64)p->sm_count * 2);
     k1_mark(p, 0, st);
@@ -955,21 +988,6 @@ int pack_dispatch(vggp_plan* p, const void* const* x, const void* y, i64 n, int 
 }
 
 // ---- binned layout (obs_binned.cuh) ---------------------------------------------------------------------
-// device temporaries of a setup call: freed on every exit path unless released to a longer-lived owner
-struct DevTemps {
-    std::vector<void*> ptrs;
-    ~DevTemps() { for (void* q : ptrs) if (q) cudaFree(q); }
-    template <typename P>
-    cudaError_t alloc(P** out, size_t bytes) {
-        void* q = nullptr;
-        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
-        if (e == cudaSuccess) ptrs.push_back(q);
-        *out = reinterpret_cast<P*>(q);
-        return e;
-    }
-    void release(void* q) { for (void*& r : ptrs) if (r == q) r = nullptr; }
-};
-
 template <typename T, int D>
 int bin_prepare_impl(vggp_plan* p, const void* const* x, i64 n, int run_cap, vggp_binned_desc* desc, cudaStream_t st) {
     i64 ncells = 1;
@@ -1098,7 +1116,7 @@ int launch_obs_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* bi
     if (p->bin_blocks_per_sm[mode] == 0) {
         int nb = 0;
         if (mode) {
-            VGGP_CUDA(cudaFuncSetAttribute(k_obs_b1_binned_tma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (int rc2 = raise_dyn_smem(k_obs_b1_binned_tma<T, D>, smem)) return rc2;
             VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned_tma<T, D>, BIN_THREADS, smem));
         } else {
             VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, smem));
@@ -1521,7 +1539,8 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         for (int d = 0; d < D; ++d) Mchk *= (double)n_knots[d];
         if (Mchk >= 2147483647.0) return fail(VGGP_E_ARG, "M = prod M_d must be below 2^31");
     }
-    VGGP_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
+    { int cur = -1; VGGP_CUDA(cudaGetDevice(&cur)); if (cur != device) return fail(VGGP_E_ARG, "cannot select the device"); }
     vggp_plan* p = new (std::nothrow) vggp_plan();
     if (!p) return fail(VGGP_E_NOMEM, "out of host memory");
     p->family = family; p->D = D; p->obs_dtype = obs_dtype; p->device = device;
@@ -1656,15 +1675,11 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->obs_blocks_per_sm = 1;
         if (family == VGGP_B1_ASVGP) TRY(obs_prepare_dispatch(p));
     }
-    if (!rc) rc = (int)cudaFuncSetAttribute(k_b1_factor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(7 * (size_t)p->nmax * sizeof(double)));
-    if (!rc) rc = (int)cudaFuncSetAttribute(k_ss_apply, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(5 * (size_t)p->nmax * sizeof(double)));
+    if (!rc) rc = raise_dyn_smem(k_b1_factor, 7 * (size_t)p->nmax * sizeof(double));
+    if (!rc) rc = raise_dyn_smem(k_ss_apply, 5 * (size_t)p->nmax * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_factor / k_ss_apply) failed"); }
-    rc = (int)cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * NB * (NB + 1) * sizeof(double)));
-    if (!rc) rc = (int)cudaFuncSetAttribute(k_triinv_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(2 * NB * (NB + 1) * sizeof(double)));
+    rc = raise_dyn_smem(k_chol_panel, 2 * NB * (NB + 1) * sizeof(double));
+    if (!rc) rc = raise_dyn_smem(k_triinv_leaf, 2 * NB * (NB + 1) * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
 #undef TRY
     *out = p;
@@ -1673,7 +1688,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
 
 int vggp_plan_destroy(vggp_plan* p) {
     if (!p) return 0;
-    cudaSetDevice(p->device);
+    DeviceGuard dev_guard(p->device);
     for (void* ptr : p->allocs) cudaFree(ptr);
     for (int d = 0; d < VGGP_MAX_D; ++d)
         if (p->pk_x[d]) cudaFree(p->pk_x[d]);
@@ -1709,6 +1724,7 @@ int vggp_gbuf_layout(const vggp_plan* p, int64_t* n_obs_elems, int64_t* scalar_o
 }
 
 int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const double* L, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !theta || !m || !L) return fail(VGGP_E_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->D;
@@ -1791,6 +1807,7 @@ int vggp_obs_pack_geometry(const vggp_plan* p, int64_t n, int64_t* n_packed, int
 
 int vggp_obs_pack(vggp_plan* p, const void* const* x, const void* y, int64_t n, int sort_by_cell, void* const* xp,
                   void* yp, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "the packed layout is used by the B1 family only");
@@ -1801,6 +1818,7 @@ int vggp_obs_pack(vggp_plan* p, const void* const* x, const void* y, int64_t n, 
 }
 
 int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp, int64_t n, void* gbuf, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!xp || !yp)) return fail(VGGP_E_ARG, "null observation pointers");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1816,6 +1834,7 @@ int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp,
 }
 
 int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
     if (n == 0 || p->family != VGGP_B1_ASVGP) {
@@ -1850,6 +1869,7 @@ int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t 
 }
 
 int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_cap, vggp_binned_desc* desc, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4");
@@ -1867,6 +1887,7 @@ int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_
 
 int vggp_obs_bin_pack(vggp_plan* p, const vggp_binned_desc* desc, const void* const* x, const void* y, void* binned,
                       void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || !binned) return fail(VGGP_E_ARG, "bad argument");
     if (!p->bin_has_pending) return fail(VGGP_E_ARG, "vggp_obs_bin_pack without a pending vggp_obs_bin_prepare on this plan");
     const BinLayout& L = p->bin_pending;
@@ -1881,6 +1902,7 @@ int vggp_obs_bin_pack(vggp_plan* p, const vggp_binned_desc* desc, const void* co
 }
 
 int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || !gbuf) return fail(VGGP_E_ARG, "bad argument");
     if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (desc->D != p->D) return fail(VGGP_E_ARG, "descriptor belongs to a plan of another dimension");
@@ -1895,6 +1917,7 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
 }
 
 int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, int* err_flag, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || !err_flag) return fail(VGGP_E_ARG, "null argument");
     if (desc->world < 1 || desc->world > AR_MAX_RANKS || desc->rank < 0 || desc->rank >= desc->world)
         return fail(VGGP_E_ARG, "world must be 1..8 and rank inside it");
@@ -1924,6 +1947,7 @@ int vggp_allreduce_gbuf(vggp_plan* p, const vggp_ar_desc* desc, int* err_flag, v
 
 int vggp_grid_backward(vggp_plan* p, const double* theta, const double* m, const double* L, const void* gbuf,
                        double ell_scale, double* out, double* dtheta, double* dm, double* dL, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !theta || !m || !L || !gbuf || !out || !dtheta || !dm || !dL) return fail(VGGP_E_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->D;
@@ -1999,6 +2023,7 @@ int vggp_k1_timing(vggp_plan* p, int enable) {
 }
 
 int vggp_k1_time_read(vggp_plan* p, float* mean_ms, int* n_launches) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !mean_ms || !n_launches) return fail(VGGP_E_ARG, "null argument");
     const int n = std::min(p->k1_count, K1_EVENT_PAIRS);
     double acc = 0.0;
@@ -2014,6 +2039,7 @@ int vggp_k1_time_read(vggp_plan* p, float* mean_ms, int* n_launches) {
 }
 
 int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !info_host) return fail(VGGP_E_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     VGGP_CUDA(cudaMemcpyAsync(info_host, p->g.info, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2029,6 +2055,7 @@ int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !info_pinned_host) return fail(VGGP_E_ARG, "null argument");
     VGGP_CUDA(cudaMemcpyAsync(info_pinned_host, p->g.info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
@@ -2037,6 +2064,7 @@ int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
 int vggp_elbo_host(vggp_plan* p, const void* const* x_host, const void* y_host, int64_t n, const double* theta_host,
                    const double* m_host, const double* L_host, double ell_scale, double* out_host,
                    double* dtheta_host, double* dm_host, double* dL_host, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !theta_host || !m_host || !L_host || !out_host || !dtheta_host || !dm_host || !dL_host || n < 0)
         return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!x_host || !y_host)) return fail(VGGP_E_ARG, "null observation pointers");
@@ -2088,6 +2116,7 @@ int vggp_elbo_host(vggp_plan* p, const void* const* x_host, const void* y_host, 
 
 int vggp_b1_stencil(const vggp_plan* p, int dim, const void* x, int64_t n, int32_t* c, void* w_lo, void* w_hi,
                     void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || dim < 0 || dim >= p->D || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (!x || !c || !w_lo || !w_hi) return fail(VGGP_E_ARG, "null argument");
@@ -2103,6 +2132,7 @@ int vggp_b1_stencil(const vggp_plan* p, int dim, const void* x, int64_t n, int32
 
 int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, const double* theta, void* phi,
                         void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || dim < 0 || dim >= p->D || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (!x || !phi) return fail(VGGP_E_ARG, "null argument");
@@ -2129,6 +2159,7 @@ int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, c
 }
 
 int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void* var, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n == 0) return 0;
     if (!x || !mean || !var) return fail(VGGP_E_ARG, "null argument");
@@ -2154,6 +2185,7 @@ int vggp_metrics(int dtype, const void* truth, const void* pred, int64_t n, doub
 }
 
 int vggp_predict_metrics(vggp_plan* p, const void* const* x, const void* y, int64_t n, double* out, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !out || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (p->family != VGGP_B1_ASVGP) return fail(VGGP_E_UNSUPPORTED, "point prediction is built for the B1 family");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2202,6 +2234,7 @@ int vggp_minmax_scale(int dtype, const void* x, int64_t n, const void* minmax, i
 }
 
 int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !ptr) return fail(VGGP_E_ARG, "null argument");
     if (which != VGGP_WS_ALPHA && which != VGGP_WS_SCAL && (dim < 0 || dim >= p->D)) return fail(VGGP_E_ARG, "bad dim");
     const i64 nn = (which == VGGP_WS_ALPHA || which == VGGP_WS_SCAL) ? 0 : (i64)p->n[dim] * p->n[dim];
@@ -2242,6 +2275,7 @@ int vggp_gemm_f64(int use_mma, int batch, int m, int n, int k, double alpha, con
 }
 
 int vggp_mode_product(vggp_plan* p, int dim, const double* A, const double* src, double* dst, void* stream) {
+    DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !A || !src || !dst || dim < 0 || dim >= p->D) return fail(VGGP_E_ARG, "bad argument");
     return launch_one(mode_desc(p, dim, A, src, dst), g_use_mma, (cudaStream_t)stream);
 }
