@@ -227,6 +227,10 @@ int vggp_grid_backward(vggp_plan* plan, const double* theta, const double* m, co
  */
 int vggp_k1_timing(vggp_plan* plan, int enable);
 int vggp_k1_time_read(vggp_plan* plan, float* mean_ms, int* n_launches);
+/* The same kernel inside a captured CUDA graph: when vggp_k1_timing is on while the caller's stream is being captured, the two
+ * records become external event-record nodes of the graph (cudaEventRecordExternal), re-recorded by every replay.
+ *   vggp_k1_graph_time_read  duration in milliseconds of the kernel in the most recent replay; synchronises its end event. */
+int vggp_k1_graph_time_read(vggp_plan* plan, float* ms);
 
 /* Failed-factorisation flag of the last forward (0 = ok, d+1 = factor d not positive definite).
  * Synchronises `stream`. */

@@ -262,6 +262,35 @@ def test_b0_step_scan_form_matches_oracle_under_emulation(emu, knots, N, dtype, 
     plan.close()
 
 
+@pytest.mark.parametrize("knots,N", [((71,), 300), ((41, 76), 350), ((100, 34), 350)])
+def test_b0_segmented_sweeps_under_emulation(emu, knots, N):
+    """The segmented sweeps of the scan form (k_b0s_scan_seg / k_b0s_scan_adj_seg: a fibre cut into ceil(M / 16) segments with
+    carries folded through shared memory; here 3 - 7 segments with a partial last one, row and column fibres, the tangent
+    variant included) against the one-thread-per-fibre kernels on the same step, and against the oracle."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=31 + D, family=O.B0_GRIDDED, x_lo=-0.1, x_hi=1.1)
+    l = l * 0.04                                         # l ~ delta: the float32-rounded Toeplitz row of the reference stays positive definite
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes, X, y, l, s2, noise, m, Ls, scale=1.2)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
+    res = []
+    for seg in (1, 0):
+        lib.vggp_debug_b0s_seg(seg)
+        try:
+            plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, [t.numpy() for t in meshes], np.float64)
+            out = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                            plan.bin(xs, np.ascontiguousarray(y.numpy()), run_cap=16), None, 1.2)
+            if seg:
+                check_against_oracle(plan, *out, elbo_ref, g_ref, N, 1e-7)
+            res.append(out)
+            plan.close()
+        finally:
+            lib.vggp_debug_b0s_seg(1)
+    for a, b in zip(res[0], res[1]):
+        assert relerr(torch.from_numpy(np.asarray(a, dtype=np.float64)), torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-10
+
+
 @pytest.mark.parametrize("knots", [(11,), (8, 7)])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
 def test_b0_point_prediction_scan_form_under_emulation(emu, knots, dtype, tol):

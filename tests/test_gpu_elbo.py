@@ -541,3 +541,39 @@ def test_model_refuses_cpu(vg):
     model = ks.Matern12B1SplineASVGP(X, y, 5, (0, 1), (0, 1))
     with pytest.raises(RuntimeError):
         model._elbo()
+
+
+def test_two_live_plans_of_different_sizes(vg, dev):
+    """The dynamic-shared-memory opt-in of a kernel is a per-function, process-wide attribute: creating (and using) a
+    second, smaller plan must not lower what an earlier, larger plan needs (1-D, 1100 knots, float64: the band tables of
+    the per-observation kernel and the staging of the theta kernel are both above the 48 KB default)."""
+    def run(plan, prob, packed):
+        meshes, X, y, l, s2, noise, m, Ls = prob
+        theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+        Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+        xs = [X[:, d].contiguous().to(dev) for d in range(X.shape[1])]
+        if packed:
+            out = plan.step(theta, m.to(dev), Lcat, plan.pack(xs, y.to(dev), sort_by_cell=True), None)
+        else:
+            out = plan.step(theta, m.to(dev), Lcat, xs, y.to(dev))
+        torch.cuda.synchronize()
+        assert plan.read_info() == 0
+        return [t.clone() for t in out]
+
+    big = make_problem((1100,), 6000, seed=5)
+    small = make_problem((9, 7), 500, seed=6)
+    plan_big = vg.GridPlan(vg.B1_ASVGP, big[0], torch.float64, dev)
+    first = [run(plan_big, big, packed) for packed in (False, True)]
+    plan_small = vg.GridPlan(vg.B1_ASVGP, small[0], torch.float64, dev)
+    for packed in (False, True):
+        run(plan_small, small, packed)
+    plan_1d = vg.GridPlan(vg.B1_ASVGP, [torch.linspace(0, 1, 12)], torch.float32, dev)      # what B1SplineBasis._plan makes
+    assert plan_1d.M == 12
+    again = [run(plan_big, big, packed) for packed in (False, True)]
+    for which, (a, b) in enumerate(zip(first, again)):
+        for k, (ta, tb) in enumerate(zip(a, b)):
+            assert relerr(ta, tb) < 1e-9, ("the large plan changed its results after smaller plans were used", which, k)
+    # and it is the right answer (1100 knots: the factor's condition number limits the agreement, not the kernels)
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, *big)
+    for which in range(2):
+        assert abs(again[which][0][0].item() - elbo_ref.item()) <= 1e-6 * abs(elbo_ref.item()), (which, again[which][0][0].item(), elbo_ref.item())

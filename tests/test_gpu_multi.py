@@ -63,7 +63,7 @@ def test_peer_allreduce_matches_nccl_and_single_process(tmp_path, dtype_name):
     from test_gpu_elbo import make_problem, relerr
     mp.spawn(_worker, args=(2, _free_port(), dtype_name, str(tmp_path)), nprocs=2, join=True)
     res = torch.load(os.path.join(str(tmp_path), f"res_{dtype_name}.pt"))
-    tol = 1e-12 if dtype_name == "float64" else 1e-5
+    tol = 1e-10 if dtype_name == "float64" else 1e-5       # the two collectives sum in different orders
     for a, b in zip(res["peer"], res["nccl"]):
         assert relerr(a, b) < tol
     # against the single-process step on the whole data set

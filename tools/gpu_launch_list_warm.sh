@@ -4,9 +4,10 @@ set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p "$OUT"
 ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline ${1:-}"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 300 --csv --log-file "$OUT/launches_warm.csv" \
-    python bench.py $ARGS > "$OUT/ncu_launches_warm.log" 2>&1
-python - "$OUT/launches_warm.csv" <<'PY'
+TAG=${2:-warm}
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c ${NLAUNCH:-300} --csv --log-file "$OUT/launches_$TAG.csv" \
+    python bench.py $ARGS > "$OUT/ncu_launches_$TAG.log" 2>&1
+python - "$OUT/launches_$TAG.csv" <<'PY'
 import csv, io, sys
 lines = [l for l in open(sys.argv[1]) if l.startswith('"')]
 rows = list(csv.DictReader(io.StringIO("".join(lines))))

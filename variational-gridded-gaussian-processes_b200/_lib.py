@@ -56,6 +56,7 @@ SIGNATURES = {
     "vggp_allreduce_gbuf": (C.c_int, [_vp, C.POINTER(ArDesc), _dp, _vp]),
     "vggp_k1_timing": (C.c_int, [_vp, C.c_int]),
     "vggp_k1_time_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "vggp_k1_graph_time_read": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "vggp_predict": (C.c_int, [_vp, C.POINTER(_vp), _i64, _dp, _dp, _vp]),
     "vggp_metrics": (C.c_int, [C.c_int, _dp, _dp, _i64, _dp, _vp]),
     "vggp_predict_metrics": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),

@@ -181,6 +181,208 @@ __global__ void __launch_bounds__(128) k_b0s_scan_adj(const __grid_constant__ B0
     }
 }
 
+// ---- segmented forms of the two sweeps kernels above (the ones the library launches) --------------------------------------
+// One thread per fibre runs 2 M dependent steps on 4 - 5 CTAs (0.1 - 0.35 ms per launch at M = 511).  Every sweep is a
+// first-order affine recurrence  state' = eps_i state + add_i  whose multiplier does not depend on the fibre, so a fibre is
+// cut into S = ceil(M / B0S_SEG) segments, one thread each:
+//   pass 1   the segment's composite map from a zero state (B, with the tangent also T) -> shared memory; the multiplier
+//            product of a segment, a dual number (A, dA) with the tangent, is the same for every fibre: once per CTA;
+//   carry    every thread folds the maps of the segments before it (<= S - 1 steps);
+//   pass 2   the segment again from its true carry-in, writing the outputs.
+// The thread keeps its B0S_SEG source values in registers (all loads in flight before the first dependent step), the
+// coefficient rows [eps | gam | deps] sit in shared memory with one double of skew per segment (lanes of different
+// segments hit different banks).  2 B0S_SEG + S dependent steps per sweep instead of M; F = B0S_SEG_THREADS / S fibres per CTA.
+// Thread mapping: fibres fastest when neighbouring fibres are contiguous in memory (column fibres), segments fastest when
+// the mode itself is contiguous (row fibres) -- either way a warp's accesses fall into few lines.
+constexpr int B0S_SEG = 16;
+constexpr int B0S_SEG_THREADS = 128;
+__host__ __device__ __forceinline__ int b0s_skew(int i) { return i + i / B0S_SEG; }
+inline size_t b0s_seg_smem_bytes(int M, bool tan) {
+    const int S = (M + B0S_SEG - 1) / B0S_SEG;
+    (void)tan;
+    return sizeof(double) * ((size_t)3 * (M + S + 1) + 2 * (size_t)S + 2 * (size_t)B0S_SEG_THREADS);
+}
+
+template <bool TAN, int dir>
+__device__ __forceinline__ void b0s_seg_sweep(const B0sScanArgs& a, const double (&vv)[B0S_SEG], const double* ceps, const double* cgam,
+                                          const double* cdeps, const double* cA, const double* cdA, double* maps, int S, int fl,
+                                          int s, int slot, int i0, int len, bool live, i64 dbase) {
+    const int M = a.M;
+    // pass 1: composite map of the segment from a zero state
+    double acc = 0.0, tan = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < B0S_SEG; ++kk) {
+        const int k = dir ? B0S_SEG - 1 - kk : kk;
+        if (k < len) {
+            const double e = ceps[b0s_skew(i0 + k)];
+            if (TAN) tan = fma(e, tan, cdeps[b0s_skew(i0 + k)] * (acc - vv[k]));
+            acc = fma(e, acc, cgam[b0s_skew(i0 + k)] * vv[k]);
+        }
+    }
+    if (dir) __syncthreads();             // the maps of the L sweep have been consumed
+    if (live) {
+        maps[slot] = acc;
+        if (TAN) maps[B0S_SEG_THREADS + slot] = tan;
+    }
+    __syncthreads();
+    // carry-in: fold the segments before this one in sweep order
+    double cin = 0.0, tin = 0.0;
+    if (live) {
+        const int qa = dir ? S - 1 : 0, qstep = dir ? -1 : 1;
+        for (int q = qa; q != s; q += qstep) {
+            if (TAN) tin = fma(cA[q], tin, fma(cdA[q], cin, maps[B0S_SEG_THREADS + fl * S + q]));
+            cin = fma(cA[q], cin, maps[fl * S + q]);
+        }
+    }
+    // pass 2: the segment from its true carry-in
+    double* __restrict__ O = (dir ? a.dstR : a.dstL) + dbase;
+    double* __restrict__ TO = TAN ? (dir ? a.tanR : a.tanL) + dbase : nullptr;
+    acc = cin;
+    tan = tin;
+    if (live && s == (dir ? S - 1 : 0)) {  // the two zero entries at the start of the sweep
+        const i64 z0 = dir ? (i64)(M + 1) * a.d_mode : 0, z1 = dir ? (i64)M * a.d_mode : a.d_mode;
+        O[z0] = 0.0; O[z1] = 0.0;
+        if (TAN) { TO[z0] = 0.0; TO[z1] = 0.0; }
+    }
+#pragma unroll
+    for (int kk = 0; kk < B0S_SEG; ++kk) {
+        const int k = dir ? B0S_SEG - 1 - kk : kk;
+        if (k < len) {
+            const double e = ceps[b0s_skew(i0 + k)];
+            if (TAN) tan = fma(e, tan, cdeps[b0s_skew(i0 + k)] * (acc - vv[k]));
+            acc = fma(e, acc, cgam[b0s_skew(i0 + k)] * vv[k]);
+            const i64 o = (i64)(dir ? i0 + k : i0 + k + 2) * a.d_mode;
+            O[o] = acc;
+            if (TAN) TO[o] = tan;
+        }
+    }
+}
+
+template <bool TAN>
+__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_seg(const __grid_constant__ B0sScanArgs a, int S, int F, int f_fast) {
+    extern __shared__ double sm[];
+    const int M = a.M, P = M + S + 1;
+    double* ceps = sm;
+    double* cgam = ceps + P;
+    double* cdeps = cgam + P;
+    double* cA = cdeps + P;                   // dual number (A, dA) of the multiplier product of every segment: fibre independent
+    double* cdA = cA + S;
+    double* maps = cdA + S;                   // [B | T][fl * S + s]
+    for (int i = threadIdx.x; i < M; i += B0S_SEG_THREADS) {
+        ceps[b0s_skew(i)] = a.eps[i];
+        cgam[b0s_skew(i)] = a.eps[M + i];
+        if (TAN) cdeps[b0s_skew(i)] = a.eps[2 * M + i];
+    }
+    const int t = threadIdx.x;
+    const int fl = f_fast ? t % F : t / S, s = f_fast ? t / F : t % S;
+    const i64 f = (i64)blockIdx.x * F + fl;
+    const bool live = fl < F && s < S && f < a.n_fibres;
+    const i64 fh = live ? f / a.n_lo : 0, fo = live ? f - fh * a.n_lo : 0;
+    const double* __restrict__ v = a.src + fh * a.s_hi + fo * a.s_lo;
+    const i64 dbase = fh * a.d_hi + fo * a.d_lo;
+    const int i0 = s * B0S_SEG;
+    const int len = live ? (M - i0 < B0S_SEG ? M - i0 : B0S_SEG) : 0;
+    double vv[B0S_SEG];
+#pragma unroll
+    for (int k = 0; k < B0S_SEG; ++k) vv[k] = k < len ? v[(i64)(i0 + k) * a.s_mode] : 0.0;
+    const int slot = fl * S + s;
+    __syncthreads();
+    if (t < S) {                              // the product is commutative: one (A, dA) per segment serves both sweeps
+        double A = 1.0, dA = 0.0;
+        const int q0 = t * B0S_SEG, ql = M - q0 < B0S_SEG ? M - q0 : B0S_SEG;
+        for (int k = 0; k < ql; ++k) {
+            const double e = ceps[b0s_skew(q0 + k)];
+            if (TAN) dA = fma(e, dA, cdeps[b0s_skew(q0 + k)] * A);
+            A *= e;
+        }
+        cA[t] = A;
+        if (TAN) cdA[t] = dA;
+    }
+    b0s_seg_sweep<TAN, 0>(a, vv, ceps, cgam, cdeps, cA, cdA, maps, S, fl, s, slot, i0, len, live, dbase);     // L sweep (ascending)
+    b0s_seg_sweep<TAN, 1>(a, vv, ceps, cgam, cdeps, cA, cdA, maps, S, fl, s, slot, i0, len, live, dbase);     // R sweep (descending)
+}
+
+template <int dir>
+__device__ __forceinline__ void b0s_seg_adj_sweep(const B0sAdjArgs& a, double (&g)[B0S_SEG], double (&out)[B0S_SEG], const double* ceps,
+                                                  const double* cgam, const double* cA, double* maps, int S, int fl, int s, int slot,
+                                                  int i0, int len, bool live, i64 go) {
+    const int M = a.M;
+    if (dir) {
+#pragma unroll
+        for (int k = 0; k < B0S_SEG; ++k) g[k] = k < len ? a.gR[go + (i64)(i0 + k + 1) * a.g_mode] : 0.0;
+    }
+    double c = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < B0S_SEG; ++kk) {
+        const int k = dir ? kk : B0S_SEG - 1 - kk;
+        if (k < len) c = fma(ceps[b0s_skew(i0 + k)], c, g[k]);
+    }
+    if (dir) __syncthreads();
+    if (live) maps[slot] = c;
+    __syncthreads();
+    double cin = 0.0;
+    if (live) {
+        if (!dir) {
+            cin = a.gL[go + (i64)(M + 1) * a.g_mode];
+            for (int q = S - 1; q > s; --q) cin = fma(cA[q], cin, maps[fl * S + q]);
+        } else {
+            cin = a.gR[go];
+            for (int q = 0; q < s; ++q) cin = fma(cA[q], cin, maps[fl * S + q]);
+        }
+    }
+    c = cin;
+#pragma unroll
+    for (int kk = 0; kk < B0S_SEG; ++kk) {
+        const int k = dir ? kk : B0S_SEG - 1 - kk;
+        if (k < len) {
+            out[k] = fma(cgam[b0s_skew(i0 + k)], c, out[k]);
+            c = fma(ceps[b0s_skew(i0 + k)], c, g[k]);
+        }
+    }
+}
+
+// Segmented adjoint sweeps (same decomposition): sweep 1 descending, c <- eps_i c + gL[i + 1] from c = gL[M + 1],
+// dv[i] = gam_i c + gC[i + 1]; sweep 2 ascending, c <- eps_i c + gR[i + 1] from c = gR[0], dv[i] += gam_i c
+// (c = the state BEFORE the step in both).  dv stays in registers between the sweeps.
+__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_adj_seg(const __grid_constant__ B0sAdjArgs a, int S, int F, int f_fast) {
+    extern __shared__ double sm[];
+    const int M = a.M, P = M + S + 1;
+    double* ceps = sm;
+    double* cgam = ceps + P;
+    double* cA = cgam + P;                    // multiplier product of every segment (fibre independent), S entries (of P)
+    double* maps = cA + P;
+    for (int i = threadIdx.x; i < M; i += B0S_SEG_THREADS) {
+        ceps[b0s_skew(i)] = a.eps[i];
+        cgam[b0s_skew(i)] = a.eps[M + i];
+    }
+    const int t = threadIdx.x;
+    const int fl = f_fast ? t % F : t / S, s = f_fast ? t / F : t % S;
+    const i64 f = (i64)blockIdx.x * F + fl;
+    const bool live = fl < F && s < S && f < a.n_fibres;
+    const i64 fh = live ? f / a.n_lo : 0, fo = live ? f - fh * a.n_lo : 0;
+    const i64 go = fh * a.g_hi + fo * a.g_lo;
+    double* __restrict__ dv = a.dv + fh * a.v_hi + fo * a.v_lo;
+    const int i0 = s * B0S_SEG;
+    const int len = live ? (M - i0 < B0S_SEG ? M - i0 : B0S_SEG) : 0;
+    double g[B0S_SEG], out[B0S_SEG];
+#pragma unroll
+    for (int k = 0; k < B0S_SEG; ++k) g[k] = k < len ? a.gL[go + (i64)(i0 + k + 1) * a.g_mode] : 0.0;
+#pragma unroll
+    for (int k = 0; k < B0S_SEG; ++k) out[k] = (k < len && a.gC) ? a.gC[go + (i64)(i0 + k + 1) * a.g_mode] : 0.0;
+    __syncthreads();
+    if (t < S) {
+        double A = 1.0;
+        const int q0 = t * B0S_SEG, ql = M - q0 < B0S_SEG ? M - q0 : B0S_SEG;
+        for (int k = 0; k < ql; ++k) A *= ceps[b0s_skew(q0 + k)];
+        cA[t] = A;
+    }
+    const int slot = fl * S + s;
+    b0s_seg_adj_sweep<0>(a, g, out, ceps, cgam, cA, maps, S, fl, s, slot, i0, len, live, go);     // descending sweep over gL
+    b0s_seg_adj_sweep<1>(a, g, out, ceps, cgam, cA, maps, S, fl, s, slot, i0, len, live, go);     // ascending sweep over gR
+#pragma unroll
+    for (int k = 0; k < B0S_SEG; ++k) if (k < len) dv[(i64)(i0 + k) * a.v_mode] = out[k];
+}
+
 // Per-cell quadratic-form tables of dimension blockIdx.y, one warp per extended cell e:
 //   W[mat][s][e], mat 0 = P, 1 = Q, s = LL, LC, LR, CC, CR, RR, from V^X = G^X Mat (E x M) and the rows of G^Y.
 // grid (ceil((K+1) / 8), D), 256 threads

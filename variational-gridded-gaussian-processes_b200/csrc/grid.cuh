@@ -31,6 +31,7 @@ struct GridDims {
     int tab_off[VGGP_MAX_D];      // offset (elements) of dim d's block inside the per-cell tables (8 n_d each)
     i64 gfac_off[VGGP_MAX_D];     // B0 family: offset of dim d's [bP | bQ] block inside the gbuf factor part
     double* Kraw[VGGP_MAX_D];
+    double* cdiag[VGGP_MAX_D];    // NB x NB: factored diagonal block of the previous Cholesky panel (see k_chol_panel)
     double* Kc[VGGP_MAX_D];       // factored in place -> Cholesky factor (lower)
     double* W[VGGP_MAX_D];        // C^-1
     double* P[VGGP_MAX_D];
@@ -148,14 +149,20 @@ __global__ void k_build_factors(const __grid_constant__ GridDims g, const double
 
 // ---------------------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky, one panel per launch: every CTA factors the NB x NB diagonal block in
-// shared memory (redundantly -- it is tiny), CTA 0 writes it back and accumulates the log-det, CTA c >= 1
+// shared memory (redundantly -- it is tiny), CTA 0 keeps the result and accumulates the log-det, CTA c >= 1
 // solves its NB rows of the panel against it.  The trailing update is a grouped GEMM launch.
-// grid (row chunks, D), 256 threads, dynamic smem 2 * NB * (NB+1) doubles.
+// CTA 0 must not overwrite the diagonal block in place while the other CTAs of the launch may still have to read
+// the unfactored block (nothing orders CTAs of one launch; sequential execution of the blocks, as under the test
+// emulator, reads a half-factored block): unless it is the only CTA of its dimension it parks the factor in
+// g.cdiag[d], and CTA 0 of the next panel launch moves it into place (nothing in between reads that block).
+// grid (row chunks, D), 256 threads, dynamic smem (2 * NB * CHOL_PITCH + NB) doubles.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int CHOL_PITCH = NB + 4;      // 4 lanes per row read s[r][q], s[r][q + 4], ...: pitch = 4 (mod 16) doubles keeps them on distinct banks
 __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ GridDims g, int j0) {
     extern __shared__ double sm[];
-    double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm);
-    double (*a)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm + NB * (NB + 1));
+    double (*s)[CHOL_PITCH] = reinterpret_cast<double (*)[CHOL_PITCH]>(sm);
+    double (*a)[CHOL_PITCH] = reinterpret_cast<double (*)[CHOL_PITCH]>(sm + NB * CHOL_PITCH);
+    double* dg = sm + 2 * NB * CHOL_PITCH;    // the diagonal of the factor: kept apart until the block is done (see below)
     const int d = blockIdx.y;
     const int n = g.n[d];
     if (j0 >= n) return;
@@ -165,32 +172,57 @@ __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ Grid
     double* __restrict__ A = g.Kc[d];
     const int tid = threadIdx.x, nt = blockDim.x;
 
+    if (blockIdx.x == 0 && j0 > 0) {          // the previous panel's diagonal factor, parked by its CTA 0 (full NB x NB block)
+        for (int e = tid; e < NB * NB; e += nt) {
+            const int i = e / NB, j = e % NB;
+            if (j <= i) A[(i64)(j0 - NB + i) * n + (j0 - NB + j)] = g.cdiag[d][e];
+        }
+    }
     for (int e = tid; e < w * w; e += nt) {
         const int i = e / w, j = e % w;
         s[i][j] = A[(i64)(j0 + i) * n + (j0 + j)];
     }
     __syncthreads();
+    // Left-looking factorisation of the diagonal block, 4 lanes per row (256 threads = 64 rows): column c of row r is
+    // s[r][c] - sum_{k<c} s[r][k] s[c][k], the lanes split k modulo 4 and meet by two shuffles.  Every row group also forms the
+    // pivot sum_{k<c} s[c][k]^2 itself (same operations in the same order: bit-identical everywhere), so one barrier per
+    // column is enough -- the right-looking version needed three and ran at 1.4 us per column.  The new diagonal entry goes
+    // to dg[c], not to s[c][c]: the other row groups read s[c][c] in the same iteration.
+    const int r = tid >> 2, q = tid & 3;
     for (int c = 0; c < w; ++c) {
-        if (tid == 0) {
-            const double piv = s[c][c];
-            if (!(piv > 0.0)) atomicMax(g.info, d + 1);
-            s[c][c] = sqrt(piv);
+        double part = 0.0, pp = 0.0;
+        if (r >= c && r < w) {
+            for (int k = q; k < c; k += 4) {
+                const double sc = s[c][k];
+                part = fma(s[r][k], sc, part);
+                pp = fma(sc, sc, pp);
+            }
         }
-        __syncthreads();
-        const double dcc = s[c][c];
-        for (int r = c + 1 + tid; r < w; r += nt) s[r][c] /= dcc;
-        __syncthreads();
-        const int rem = w - c - 1;
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int r = c + 1 + e / rem, cc = c + 1 + e % rem;
-            if (cc <= r) s[r][cc] -= s[r][c] * s[cc][c];
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        pp += __shfl_xor_sync(0xffffffffu, pp, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        pp += __shfl_xor_sync(0xffffffffu, pp, 2);
+        if (r >= c && r < w && q == 0) {
+            const double piv = s[c][c] - pp;
+            if (r == c) {
+                if (!(piv > 0.0)) atomicMax(g.info, d + 1);
+                dg[c] = sqrt(piv);
+            } else {
+                s[r][c] = (s[r][c] - part) / sqrt(piv);
+            }
         }
         __syncthreads();
     }
+    if (tid < w) s[tid][tid] = dg[tid];
+    __syncthreads();
     if (blockIdx.x == 0) {
+        const bool alone = j0 + NB >= n;      // last panel of this dimension: no other CTA reads the block
         for (int e = tid; e < w * w; e += nt) {
             const int i = e / w, j = e % w;
-            if (j <= i) A[(i64)(j0 + i) * n + (j0 + j)] = s[i][j];
+            if (j <= i) {
+                if (alone) A[(i64)(j0 + i) * n + (j0 + j)] = s[i][j];
+                else g.cdiag[d][i * NB + j] = s[i][j];          // w == NB here
+            }
         }
         if (tid == 0) {
             double ld = 0.0;
@@ -205,12 +237,15 @@ __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ Grid
         a[i][j] = A[(i64)(r0 + i) * n + (j0 + j)];
     }
     __syncthreads();
-    if (tid < rows) {
-        for (int c = 0; c < w; ++c) {
-            double v = a[tid][c];
-            for (int k = 0; k < c; ++k) v -= a[tid][k] * s[c][k];
-            a[tid][c] = v / s[c][c];
-        }
+    // rows of the panel against the factored block: independent rows, 4 lanes each (all in one warp: __syncwarp orders them)
+    for (int c = 0; c < w; ++c) {
+        double part = 0.0;
+        if (r < rows)
+            for (int k = q; k < c; k += 4) part = fma(a[r][k], s[c][k], part);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (r < rows && q == 0) a[r][c] = (a[r][c] - part) / s[c][c];
+        __syncwarp();
     }
     __syncthreads();
     for (int e = tid; e < rows * w; e += nt) {

@@ -118,6 +118,8 @@ struct vggp_plan {
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // optional device timing of the per-observation kernel (vggp_k1_timing)
     bool k1_timing = false; std::vector<cudaEvent_t> k1_ev; int k1_count = 0;
+    cudaEvent_t k1_gev[2] = {nullptr, nullptr};      // the pair recorded by event nodes of a captured graph (vggp_k1_graph_time_read)
+    bool k1_gev_captured = false;
     double* b1_acc = nullptr; int b1_acc_total = 0;      // structured == 3: band accumulators of dK_d, [3][n_d] per dimension
     cudaStream_t last_stream = nullptr;                  // stream of the last grid forward (on-demand workspace fills)
     void* band_rep = nullptr;              // B1 family, binned kernel: BAND_REPLICAS copies of the band block (obs dtype), kept zero
@@ -727,6 +729,12 @@ int b1f_backward(vggp_plan* p, const double* theta, const double* m, const doubl
 constexpr int K1_EVENT_PAIRS = 256;
 inline void k1_mark(vggp_plan* p, int which, cudaStream_t st) {
     if (!p->k1_timing || p->k1_ev.empty()) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive) {
+        // inside a stream capture: an external event-record node; every replay of the graph re-records the same pair
+        if (p->k1_gev[which]) { cudaEventRecordWithFlags(p->k1_gev[which], st, cudaEventRecordExternal); p->k1_gev_captured = true; }
+        return;
+    }
     cudaEventRecord(p->k1_ev[2 * (p->k1_count % K1_EVENT_PAIRS) + which], st);
     if (which == 1) ++p->k1_count;
 }
@@ -1231,6 +1239,42 @@ int b0scan_alloc(vggp_plan* p) {
     return 0;
 }
 
+// The sweeps of the scan form run segmented (k_b0s_scan_seg / k_b0s_scan_adj_seg: S = ceil(M / 16) threads per fibre);
+// 0 selects the one-thread-per-fibre kernels they were derived from (cross-check, vggp_debug_b0s_seg).
+int g_b0s_seg = 1;
+
+struct B0sSegGeom { int S, F, f_fast; unsigned blocks; size_t smem; };
+inline B0sSegGeom b0s_seg_geom(int M, i64 n_fibres, i64 n_lo, i64 lo_stride, bool tan) {
+    B0sSegGeom g;
+    g.S = (M + B0S_SEG - 1) / B0S_SEG;
+    if (g.S < 1) g.S = 1;
+    g.F = B0S_SEG_THREADS / g.S;
+    g.f_fast = (n_lo > 1 && lo_stride == 1) ? 1 : 0;      // neighbouring fibres contiguous in memory
+    g.blocks = (unsigned)((n_fibres + g.F - 1) / g.F);
+    g.smem = b0s_seg_smem_bytes(M, tan);
+    return g;
+}
+
+int b0s_scan_launch(const B0sScanArgs& a, cudaStream_t st) {
+    if (a.n_fibres <= 0 || a.M <= 0) return 0;
+    const bool tan = a.tanL != nullptr;
+    if (!g_b0s_seg || (a.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {
+        k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+        VGGP_LAUNCH_CHECK();
+        return 0;
+    }
+    const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.s_lo, tan);
+    if (tan) {
+        if (int rc = raise_dyn_smem(k_b0s_scan_seg<true>, g.smem)) return rc;
+        k_b0s_scan_seg<true><<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
+    } else {
+        if (int rc = raise_dyn_smem(k_b0s_scan_seg<false>, g.smem)) return rc;
+        k_b0s_scan_seg<false><<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
+    }
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
 // dstL = G^L src, dstR = G^R src along one mode (k_b0s_scan): n_hi x n_lo fibres of M elements -> M + 2 entries
 int b0s_scan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
              double* dstL, double* dstR, i64 d_hi, i64 d_lo, i64 d_mode) {
@@ -1239,9 +1283,7 @@ int b0s_scan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, cons
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
     a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
-    k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
-    VGGP_LAUNCH_CHECK();
-    return 0;
+    return b0s_scan_launch(a, st);
 }
 
 // Per-cell tables from the state of the last grid forward (alpha, P_d, Q_d, theta).  Every product with G^L / G^R is a
@@ -1346,9 +1388,7 @@ int b0s_scan_tan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, 
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
     a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
-    k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
-    VGGP_LAUNCH_CHECK();
-    return 0;
+    return b0s_scan_launch(a, st);
 }
 
 int b0s_scan_adj(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* gL, const double* gC, const double* gR,
@@ -1358,7 +1398,15 @@ int b0s_scan_adj(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, 
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.g_hi = g_hi; a.g_lo = g_lo; a.g_mode = g_mode;
     a.v_hi = v_hi; a.v_lo = v_lo; a.v_mode = v_mode;
-    k_b0s_scan_adj<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+    if (a.n_fibres <= 0 || a.M <= 0) return 0;
+    if (!g_b0s_seg || (a.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {
+        k_b0s_scan_adj<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
+        VGGP_LAUNCH_CHECK();
+        return 0;
+    }
+    const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.g_lo, false);
+    if (int rc = raise_dyn_smem(k_b0s_scan_adj_seg, g.smem)) return rc;
+    k_b0s_scan_adj_seg<<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -1598,6 +1646,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         }
         const i64 nn = (i64)p->n[d] * p->n[d];
         TRY(dev_alloc(p, &g.Kraw[d], nn)); TRY(dev_alloc(p, &g.Kc[d], nn)); TRY(dev_alloc(p, &g.W[d], nn));
+        TRY(dev_alloc(p, &g.cdiag[d], (i64)NB * NB));
         TRY(dev_alloc(p, &g.P[d], nn)); TRY(dev_alloc(p, &g.Lt[d], nn)); TRY(dev_alloc(p, &g.R[d], nn));
         TRY(dev_alloc(p, &g.Q[d], nn)); TRY(dev_alloc(p, &g.dP[d], nn));
         TRY(dev_alloc(p, &g.dR[d], nn)); TRY(dev_alloc(p, &g.X[d], nn)); TRY(dev_alloc(p, &g.Y[d], nn));
@@ -1678,7 +1727,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     if (!rc) rc = raise_dyn_smem(k_b1_factor, 7 * (size_t)p->nmax * sizeof(double));
     if (!rc) rc = raise_dyn_smem(k_ss_apply, 5 * (size_t)p->nmax * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_factor / k_ss_apply) failed"); }
-    rc = raise_dyn_smem(k_chol_panel, 2 * NB * (NB + 1) * sizeof(double));
+    rc = raise_dyn_smem(k_chol_panel, (2 * NB * CHOL_PITCH + NB) * sizeof(double));
     if (!rc) rc = raise_dyn_smem(k_triinv_leaf, 2 * NB * (NB + 1) * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
 #undef TRY
@@ -1695,6 +1744,7 @@ int vggp_plan_destroy(vggp_plan* p) {
     if (p->pk_y) cudaFree(p->pk_y);
     if (p->bin_perm) cudaFree(p->bin_perm);
     for (auto& e : p->k1_ev) cudaEventDestroy(e);
+    for (auto& e : p->k1_gev) if (e) cudaEventDestroy(e);
     void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
     for (void* ptr : st)
         if (ptr) cudaFree(ptr);
@@ -1746,11 +1796,11 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
             VGGP_LAUNCH_CHECK();
         }
     } else {
-        const size_t csm = 2 * NB * (NB + 1) * sizeof(double);
+        const size_t csm = 2 * NB * (NB + 1) * sizeof(double), cpsm = (2 * NB * CHOL_PITCH + NB) * sizeof(double);
         for (int j = 0; j < p->n_panels; ++j) {
             const int j0 = j * NB;
             dim3 grid(ceil_div(p->nmax - j0, NB), D);
-            k_chol_panel<<<grid, 256, csm, st>>>(p->g, j0);
+            k_chol_panel<<<grid, 256, cpsm, st>>>(p->g, j0);
             VGGP_LAUNCH_CHECK();
             if ((rc = launch_phase(p->chol_trailing[j], st))) return rc;
         }
@@ -2016,6 +2066,7 @@ int vggp_k1_timing(vggp_plan* p, int enable) {
     if (enable && p->k1_ev.empty()) {
         p->k1_ev.resize(2 * K1_EVENT_PAIRS);
         for (auto& e : p->k1_ev) VGGP_CUDA(cudaEventCreate(&e));
+        for (auto& e : p->k1_gev) VGGP_CUDA(cudaEventCreate(&e));
     }
     p->k1_timing = enable != 0;
     if (enable) p->k1_count = 0;
@@ -2038,6 +2089,15 @@ int vggp_k1_time_read(vggp_plan* p, float* mean_ms, int* n_launches) {
     return 0;
 }
 
+int vggp_k1_graph_time_read(vggp_plan* p, float* ms) {
+    DeviceGuard dev_guard(p ? p->device : -1);
+    if (!p || !ms) return fail(VGGP_E_ARG, "null argument");
+    if (!p->k1_gev_captured) return fail(VGGP_E_ARG, "no captured graph holds the timing events (enable vggp_k1_timing before the capture)");
+    VGGP_CUDA(cudaEventSynchronize(p->k1_gev[1]));
+    VGGP_CUDA(cudaEventElapsedTime(ms, p->k1_gev[0], p->k1_gev[1]));
+    return 0;
+}
+
 int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
     DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !info_host) return fail(VGGP_E_ARG, "null argument");
@@ -2052,6 +2112,8 @@ int vggp_read_info(vggp_plan* p, int* info_host, void* stream) {
 int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 /* debugging aid: 0 = run every fibre pass through the generic kernel (cross-check of k_fibre_pass_fast), 1 = default */
 // 0: generic kernel; 1: fast kernel, fibre packing by rule (default); 3: fast, no packing; 5: fast, packing forced (tests)
+/* debugging aid: 0 = one-thread-per-fibre sweeps of the B0 scan form (cross-check of the segmented kernels), 1 = default */
+int vggp_debug_b0s_seg(int on) { g_b0s_seg = on ? 1 : 0; return 0; }
 int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {

@@ -304,6 +304,13 @@ class GridPlan:
         _lib.check(self.lib.vggp_k1_time_read(self.handle, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def k1_graph_time_read(self) -> float:
+        """Milliseconds of the per-observation kernel in the most recent replay of a graph captured while k1_timing was on
+        (external event-record nodes inside the graph); synchronises."""
+        ms = C.c_float()
+        _lib.check(self.lib.vggp_k1_graph_time_read(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def arm_info_check(self):
         """Copy the factorisation flag of the last forward into pinned host memory in stream order, without synchronising
         (vggp_info_async), and record an event behind the copy; `poll_info` turns it into a value later."""
