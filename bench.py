@@ -392,8 +392,11 @@ def main():
     ap.add_argument("--binned-stream", default="ldg", choices=["ldg", "tma"],
                     help="binned layout: 16-byte global loads into registers, or a per-warp shared-memory ring "
                          "filled by TMA bulk copies (vggp_set_binned_stream)")
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the step from CUDA graphs (the all-reduce stays outside the graphs); opt-in")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=True,
+                    help="replay the step from CUDA graphs (default; an NCCL all-reduce stays outside the graphs, the "
+                         "library's own collective is captured with the rest)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="launch the ~8 kernels of a step eagerly (three C calls per step)")
     ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer"],
                     help="the one collective of a sharded step: NCCL, or the library's own one-kernel all-reduce over NVLink "
                          "peer memory (vggp_allreduce_gbuf: in-switch multimem reduction; graph-capturable)")
@@ -470,7 +473,10 @@ def main():
         plan.grid_forward(theta_d, m_d, L_d)
         if i is not None:
             ev_a[i].record()
-        plan.obs_fwd_bwd(packed if obs is None else obs)
+        if isinstance(obs, tuple):
+            plan.obs_fwd_bwd(obs[0], obs[1])          # plain arrays in the order given (the e2e leg: what was just copied in)
+        else:
+            plan.obs_fwd_bwd(packed if obs is None else obs)
         if i is not None:
             ev_b[i].record()
         if group is not None:
@@ -484,12 +490,17 @@ def main():
 
     graphed = None
     launches_per_step = None
+    plain_step = step
     if args.cuda_graph:
         c0 = lib.vggp_launch_count()
         step()
         launches_per_step = lib.vggp_launch_count() - c0      # kernels of this library in one step (replayed by the graphs)
         graphed = plan.graphed_step(theta_d, m_d, L_d, packed, None, 1.0, group)
-        plain_step = step
+        # an instrumented twin of the same step for the roofline: captured with the library's timing on, it holds two event-record
+        # nodes around the per-observation kernel (they cost ~10 us per replay, so the timed region replays the clean graph)
+        plan.k1_timing(True)
+        graphed_timed = plan.graphed_step(theta_d, m_d, L_d, packed, None, 1.0, group, warmup=1)
+        plan.k1_timing(False)
 
         def step(i=None, obs=None):          # noqa: F811  (the graphs hold the cell-sorted observations)
             if obs is not None:
@@ -539,16 +550,23 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
     if graphed is not None:
-        # events cannot be recorded inside a replayed graph: time the per-observation kernel in a separate loop
+        # The instrumented twin graph holds two external event-record nodes around the per-observation kernel; every replay
+        # re-records the same pair, so each sample is one replay of the whole step followed by the read (a synchronisation).
+        samples = []
+        for _ in range(args.steps):
+            graphed_timed.replay()
+            samples.append(plan.k1_graph_time_read())
+        k1_kernel_ms, k1_launches = sum(samples) / len(samples), len(samples)
+        # the whole C call (memset + kernel + band-replica reduction) cannot be bracketed inside the graph: eager loop
         torch.cuda.synchronize()
-        plan.k1_timing(True)
         for i in range(args.steps):
             ev_a[i].record()
             plan.obs_fwd_bwd(packed)
             ev_b[i].record()
         torch.cuda.synchronize()
-    k1_kernel_ms, k1_launches = plan.k1_time_read()       # the kernel alone (events inside the C call, same stream)
-    plan.k1_timing(False)
+    else:
+        k1_kernel_ms, k1_launches = plan.k1_time_read()       # the kernel alone (events inside the C call, same stream)
+        plan.k1_timing(False)
     k1_call_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / args.steps   # whole vggp_obs_fwd_bwd* call
     tt = torch.tensor([ms_total, k1_kernel_ms, k1_call_ms, float(n_local)], dtype=torch.float64, device=device)
     if world > 1:
@@ -621,7 +639,7 @@ def main():
                 theta_d.copy_(th_h, non_blocking=True)
                 m_d.copy_(m_h, non_blocking=True)
                 L_d.copy_(L_h, non_blocking=True)
-                o, dth, dm, dL = step()
+                o, dth, dm, dL = plain_step(None, (xs, y))          # the step consumes the arrays that were just copied in
                 out_h.copy_(o, non_blocking=True)
                 dth_h.copy_(dth, non_blocking=True)
                 dm_h.copy_(dm, non_blocking=True)
@@ -680,8 +698,12 @@ def main():
                          "traffic": (k1_traffic(args.obs_layout, args.run_cap)
                                      if (world == 1 and args.workload == "tracks512" and n_total == N_TOTAL) else None),
                          "peak_source": peak_src, "kernel_ms": k1_ms, "kernel_launches_timed": k1_launches,
-                         "timing": "CUDA events recorded by the library immediately around the kernel launch, on the "
-                                   "launching stream, inside the timed region (vggp_k1_timing)",
+                         "timing": ("CUDA events recorded by the library immediately around the kernel launch, on the "
+                                    "launching stream, inside the timed region (vggp_k1_timing)" if graphed is None else
+                                    "CUDA events recorded by event-record nodes immediately around the kernel inside a replayed "
+                                    "graph of the whole step (vggp_k1_graph_time_read): %d replays, right after the timed region, "
+                                    "of a twin of the timed graph that differs only by the two event nodes (they cost ~10 us "
+                                    "per replay, hence the twin)" % k1_launches),
                          "call_ms": k1_call_ms,
                          "call_note": "whole vggp_obs_fwd_bwd* call: gradient-buffer memset + kernel + band-replica reduction",
                          "algorithmic_bytes": alg_bytes,

@@ -452,3 +452,39 @@ def test_binned_abi_edge_cases_under_emulation(emu):
     buf = np.zeros(int(d1.bytes) + 512, dtype=np.uint8)
     assert lib.vggp_obs_bin_pack(plan.h, C.byref(d1), plan._xptrs(xs), emul_lib.ptr(rng.standard_normal(30)), emul_lib.ptr(buf), None) == -1      # VGGP_E_ARG
     plan.close()
+
+
+@pytest.mark.parametrize("knots,N,chunk", [((17, 12), 1500, 200), ((9, 7, 5), 900, 128), ((40,), 700, 64)])
+def test_host_entry_point_chunked_transfer_under_emulation(emu, knots, N, chunk):
+    """vggp_elbo_host (the whole step from host buffers): with the observations crossing in chunks -- copy stream, one
+    event per chunk, the per-observation kernel accumulating chunk by chunk into one gradient buffer -- the results equal
+    those of the one-shot step, and the count the kernel reports is the shard's, not a chunk's."""
+    import ctypes as C
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=9 + D)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    mm = m.numpy().copy()
+    Lcat = torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(D)]
+    yy = np.ascontiguousarray(y.numpy())
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+    ref = plan.step(theta, mm, Lcat, xs, yy, 1.4)
+    res = []
+    for target in (chunk, 1 << 23):
+        lib.vggp_debug_host_chunk(target)
+        try:
+            out, dth = np.zeros(4), np.zeros(2 * D + 1)
+            dm, dL = np.zeros(plan.M), np.zeros(plan.L_total)
+            ptrs = (C.c_void_p * D)(*[x.ctypes.data for x in xs])
+            rc = lib.vggp_elbo_host(plan.h, ptrs, yy.ctypes.data, N, theta.ctypes.data, mm.ctypes.data, Lcat.ctypes.data,
+                                    C.c_double(1.4), out.ctypes.data, dth.ctypes.data, dm.ctypes.data, dL.ctypes.data, None)
+            assert rc == 0, lib.vggp_last_error()
+            res.append((out, dth, dm, dL))
+        finally:
+            lib.vggp_debug_host_chunk(1 << 23)
+    assert res[0][0][3] == N and res[1][0][3] == N
+    for got in res:
+        for a, b in zip(got, ref):
+            assert relerr(torch.from_numpy(a), torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-11
+    plan.close()

@@ -577,3 +577,42 @@ def test_two_live_plans_of_different_sizes(vg, dev):
     elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, *big)
     for which in range(2):
         assert abs(again[which][0][0].item() - elbo_ref.item()) <= 1e-6 * abs(elbo_ref.item()), (which, again[which][0][0].item(), elbo_ref.item())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)])
+def test_host_entry_point_matches_device_step(vg, dev, dtype, tol):
+    """vggp_elbo_host (pinned host buffers in, host results out; the call bench.py's e2e leg times): single-shot for a small
+    shard, and with the observations crossing PCIe in chunks on a second stream while the per-observation kernel of the
+    previous chunk runs (chunk size lowered through the debug hook so that 300 000 observations make 5 chunks)."""
+    import ctypes as C
+    knots, N = (70, 33), 300_000
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=8)
+    Xq, yq = X.to(dtype), y.to(dtype)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)])
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).contiguous()
+    xs = [Xq[:, d].contiguous() for d in range(D)]
+    ref = plan.step(theta.to(dev), m.to(dev), Lcat.to(dev), [x.to(dev) for x in xs], yq.to(dev), ell_scale=1.3)
+    ref = [t.cpu().clone() for t in ref]
+    lib = vg._lib.load()
+    xs_h = [x.pin_memory() for x in xs]
+    y_h, th_h, m_h, L_h = yq.pin_memory(), theta.pin_memory(), m.pin_memory(), Lcat.pin_memory()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for chunk in (1 << 23, 65536):
+        lib.vggp_debug_host_chunk(chunk)
+        try:
+            out_h = torch.empty(4, dtype=torch.float64).pin_memory()
+            dth_h = torch.empty(2 * D + 1, dtype=torch.float64).pin_memory()
+            dm_h = torch.empty(plan.M, dtype=torch.float64).pin_memory()
+            dL_h = torch.empty(plan.L_total, dtype=torch.float64).pin_memory()
+            ptrs = (C.c_void_p * D)(*[t.data_ptr() for t in xs_h])
+            for _ in range(2):          # the second call reuses the staging buffers, the copy stream and the events
+                vg._lib.check(lib.vggp_elbo_host(plan.handle, ptrs, y_h.data_ptr(), N, th_h.data_ptr(), m_h.data_ptr(),
+                                                 L_h.data_ptr(), 1.3, out_h.data_ptr(), dth_h.data_ptr(), dm_h.data_ptr(),
+                                                 dL_h.data_ptr(), stream))
+            assert out_h[3].item() == N
+            for got, want in zip((out_h, dth_h, dm_h, dL_h), ref):
+                assert relerr(got, want) < tol, chunk
+        finally:
+            lib.vggp_debug_host_chunk(1 << 23)

@@ -3,7 +3,7 @@
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p "$OUT"
-ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline ${1:-}"
+ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-cuda-graph ${1:-}"
 TAG=${2:-warm}
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c ${NLAUNCH:-300} --csv --log-file "$OUT/launches_$TAG.csv" \
     python bench.py $ARGS > "$OUT/ncu_launches_$TAG.log" 2>&1

@@ -27,14 +27,15 @@ PY
     [ $rc -ne 0 ] && tail -5 gpurun_out/multi${N}_$name.err
 }
 if [ "${RUNSET:-full}" = "full" ]; then
-run nccl --allreduce nccl
+run nccl --allreduce nccl --no-cuda-graph
 run nccl_graph --allreduce nccl --cuda-graph
-run peer --allreduce peer
+run peer --allreduce peer --no-cuda-graph
 run peer_graph --allreduce peer --cuda-graph
 run peer_graph_reshard --allreduce peer --cuda-graph --spatial-reshard
-run nccl_reshard --allreduce nccl --spatial-reshard
+run nccl_reshard --allreduce nccl --spatial-reshard --no-cuda-graph
 else      # the short set for a large-N call
-run nccl --allreduce nccl
+run nccl_graph --allreduce nccl --cuda-graph
+run nccl_graph_reshard --allreduce nccl --cuda-graph --spatial-reshard
 run peer_graph --allreduce peer --cuda-graph
 run peer_graph_reshard --allreduce peer --cuda-graph --spatial-reshard
 run 3d_peer_graph --workload 3d --allreduce peer --cuda-graph

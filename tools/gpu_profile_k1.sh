@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 LAYOUT=${1:-packed}; STREAM=${2:-ldg}; CAP=${3:-256}
 OUT=gpurun_out
 mkdir -p "$OUT"
-ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline --obs-layout $LAYOUT --binned-stream $STREAM --run-cap $CAP"
+ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-cuda-graph --obs-layout $LAYOUT --binned-stream $STREAM --run-cap $CAP"
 TAG="${LAYOUT}_${STREAM}_cap${CAP}"
 python bench.py $ARGS > "$OUT/plain_$TAG.log" 2>&1 || { echo "plain run failed"; tail -n 5 "$OUT/plain_$TAG.log"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_$TAG.csv" \

@@ -13,10 +13,10 @@ grep -E "FAILED|ERROR" "$OUT/pytest_gpu_all.log" | head -20
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$? $(tail -n 1 $OUT/smoke.log)"
 timeout 600 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "bench default rc=$?"
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"; echo "bench reference rc=$?"
-timeout 300 python bench.py --no-e2e --no-cpu-baseline --cuda-graph > "$OUT/bench_graph.json" 2> "$OUT/bench_graph.err"; echo "bench graph rc=$?"
+timeout 300 python bench.py --no-e2e --no-cpu-baseline --no-cuda-graph > "$OUT/bench_eager.json" 2> "$OUT/bench_eager.err"; echo "bench eager rc=$?"
 python - <<'PY'
 import json
-for tag in ("default", "graph", "reference"):
+for tag in ("default", "eager", "reference"):
     try:
         d = json.loads([l for l in open(f"gpurun_out/bench_{tag}.json") if l.startswith("{")][-1])
         r = d.get("roofline") or {}
@@ -25,9 +25,10 @@ for tag in ("default", "graph", "reference"):
         print(tag, "no line", e)
 PY
 bash tools/gpu_workloads.sh
-ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+ARGS="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-cuda-graph"
+# the launch list of the bench command itself (graph replays: ncu lists the kernel nodes one by one), then the eager variants
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_cold.csv" \
-    python bench.py $ARGS > "$OUT/ncu_launches_cold.log" 2>&1; echo "cold launch list rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_launches_cold.log" 2>&1; echo "cold launch list rc=$?"
 bash tools/gpu_launch_list_warm.sh
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_obs_b1 -s 3 -c 1 -f -o "$OUT/prof_k1" \
     python bench.py $ARGS > "$OUT/ncu_full_k1.log" 2>&1; echo "ncu k1 rc=$?"

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q --durations=8 > "$OUT/pytest_gpu
 echo "pytest rc=$? $(tail -n 1 $OUT/pytest_gpu_all.log)"
 ARGS="--no-e2e --no-cpu-baseline"
 for tag in plain graph; do
-  extra=""; [ "$tag" = graph ] && extra="--cuda-graph"
+  extra="--no-cuda-graph"; [ "$tag" = graph ] && extra="--cuda-graph"
   timeout 300 python bench.py $ARGS $extra > "$OUT/bench_$tag.json" 2> "$OUT/bench_$tag.err"
   python - "$OUT/bench_$tag.json" "$tag" <<'PY'
 import json, sys

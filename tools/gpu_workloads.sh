@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for wl in b1_cfg3 b0_cfg3 3d; do
   for tag in plain graph; do
-    extra=""; [ "$tag" = graph ] && extra="--cuda-graph"
+    extra="--no-cuda-graph"; [ "$tag" = graph ] && extra="--cuda-graph"
     timeout 300 python bench.py --workload $wl --no-e2e --no-cpu-baseline $extra ${BENCH_EXTRA:-} > gpurun_out/wl_${wl}_$tag.json 2> gpurun_out/wl_${wl}_$tag.err
     rc=$?
     python - $wl $tag $rc <<'PY'

@@ -137,6 +137,8 @@ struct vggp_plan {
     std::vector<void*> allocs;
     // staging for vggp_elbo_host
     void* st_x = nullptr; void* st_y = nullptr; i64 st_n = 0;
+    cudaStream_t st_copy = nullptr; std::vector<cudaEvent_t> st_ev;      // vggp_elbo_host: copy stream + one event per chunk
+    double n_real_override = -1.0;      // >= 0: the observation count a chunked launch reports (vggp_elbo_host)
     double *st_theta = nullptr, *st_m = nullptr, *st_L = nullptr, *st_out = nullptr, *st_dtheta = nullptr,
            *st_dm = nullptr, *st_dL = nullptr;
     void* st_gbuf = nullptr;
@@ -798,7 +800,7 @@ int launch_obs_packed(vggp_plan* p, const void* const* xp, const void* yp, i64 n
     i64 n_elems, soff, nsc, total;
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
-    a.n_real = (double)n;
+    a.n_real = p->n_real_override >= 0.0 ? p->n_real_override : (double)n;
     a.counter = p->obs_counter;
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
     i64 blocks = (a.geo.nwarps + (OBS_THREADS / 32) - 1) / (OBS_THREADS / 32);
@@ -1242,6 +1244,7 @@ int b0scan_alloc(vggp_plan* p) {
 // The sweeps of the scan form run segmented (k_b0s_scan_seg / k_b0s_scan_adj_seg: S = ceil(M / 16) threads per fibre);
 // 0 selects the one-thread-per-fibre kernels they were derived from (cross-check, vggp_debug_b0s_seg).
 int g_b0s_seg = 1;
+i64 g_host_chunk = (i64)1 << 23;      // observations per PCIe chunk of vggp_elbo_host (vggp_debug_host_chunk)
 
 struct B0sSegGeom { int S, F, f_fast; unsigned blocks; size_t smem; };
 inline B0sSegGeom b0s_seg_geom(int M, i64 n_fibres, i64 n_lo, i64 lo_stride, bool tan) {
@@ -1745,6 +1748,8 @@ int vggp_plan_destroy(vggp_plan* p) {
     if (p->bin_perm) cudaFree(p->bin_perm);
     for (auto& e : p->k1_ev) cudaEventDestroy(e);
     for (auto& e : p->k1_gev) if (e) cudaEventDestroy(e);
+    for (auto& e : p->st_ev) cudaEventDestroy(e);
+    if (p->st_copy) cudaStreamDestroy(p->st_copy);
     void* st[] = {p->st_x, p->st_y, p->st_theta, p->st_m, p->st_L, p->st_out, p->st_dtheta, p->st_dm, p->st_dL, p->st_gbuf};
     for (void* ptr : st)
         if (ptr) cudaFree(ptr);
@@ -2114,6 +2119,8 @@ int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 // 0: generic kernel; 1: fast kernel, fibre packing by rule (default); 3: fast, no packing; 5: fast, packing forced (tests)
 /* debugging aid: 0 = one-thread-per-fibre sweeps of the B0 scan form (cross-check of the segmented kernels), 1 = default */
 int vggp_debug_b0s_seg(int on) { g_b0s_seg = on ? 1 : 0; return 0; }
+/* debugging aid: observations per host-to-device chunk of vggp_elbo_host (default 2^23; tests use small values) */
+int vggp_debug_host_chunk(long long n) { g_host_chunk = n > 4 ? n : 4; return 0; }
 int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
 
 int vggp_info_async(vggp_plan* p, int* info_pinned_host, void* stream) {
@@ -2153,19 +2160,70 @@ int vggp_elbo_host(vggp_plan* p, const void* const* x_host, const void* y_host, 
         VGGP_CUDA(cudaMalloc(&p->st_y, tsz * (size_t)n));
         p->st_n = n;
     }
-    const void* xdev[VGGP_MAX_D] = {nullptr, nullptr, nullptr};
-    for (int d = 0; d < D && n > 0; ++d) {
-        unsigned char* dst = reinterpret_cast<unsigned char*>(p->st_x) + (size_t)d * n * tsz;
-        VGGP_CUDA(cudaMemcpyAsync(dst, x_host[d], tsz * (size_t)n, cudaMemcpyHostToDevice, st));
-        xdev[d] = dst;
-    }
-    if (n > 0) VGGP_CUDA(cudaMemcpyAsync(p->st_y, y_host, tsz * (size_t)n, cudaMemcpyHostToDevice, st));
+    // parameters first (6 MB at 512^2), so that the grid-side forward runs while the observations are still on their way
     VGGP_CUDA(cudaMemcpyAsync(p->st_theta, theta_host, sizeof(double) * (2 * D + 1), cudaMemcpyHostToDevice, st));
     VGGP_CUDA(cudaMemcpyAsync(p->st_m, m_host, sizeof(double) * p->M, cudaMemcpyHostToDevice, st));
     VGGP_CUDA(cudaMemcpyAsync(p->st_L, L_host, sizeof(double) * p->Lsize, cudaMemcpyHostToDevice, st));
     int rc;
     if ((rc = vggp_grid_forward(p, p->st_theta, p->st_m, p->st_L, stream))) return rc;
-    if ((rc = vggp_obs_fwd_bwd(p, xdev, p->st_y, n, p->st_gbuf, stream))) return rc;
+    // The observations cross PCIe in chunks on a second stream; the per-observation kernel of chunk c runs on `stream` as
+    // soon as its copy has landed, accumulating into one gradient buffer, so only the last chunk's kernel, the backward and
+    // the read-back are not hidden behind the transfer.  (B1 family; the B0 kernels take the whole shard in one call.)
+    const i64 chunk_target = g_host_chunk;
+    const int nchunks = (p->family == VGGP_B1_ASVGP && n > chunk_target) ? (int)std::min<i64>(32, (n + chunk_target - 1) / chunk_target) : 1;
+    if (nchunks == 1) {
+        const void* xdev[VGGP_MAX_D] = {nullptr, nullptr, nullptr};
+        for (int d = 0; d < D && n > 0; ++d) {
+            unsigned char* dst = reinterpret_cast<unsigned char*>(p->st_x) + (size_t)d * n * tsz;
+            VGGP_CUDA(cudaMemcpyAsync(dst, x_host[d], tsz * (size_t)n, cudaMemcpyHostToDevice, st));
+            xdev[d] = dst;
+        }
+        if (n > 0) VGGP_CUDA(cudaMemcpyAsync(p->st_y, y_host, tsz * (size_t)n, cudaMemcpyHostToDevice, st));
+        if ((rc = vggp_obs_fwd_bwd(p, xdev, p->st_y, n, p->st_gbuf, stream))) return rc;
+    } else {
+        if (!p->st_copy) VGGP_CUDA(cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking));
+        while ((int)p->st_ev.size() < nchunks + 1) {
+            cudaEvent_t e;
+            VGGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->st_ev.push_back(e);
+        }
+        // the copy stream starts after whatever `stream` already holds (earlier users of the staging buffers)
+        VGGP_CUDA(cudaEventRecord(p->st_ev[nchunks], st));
+        VGGP_CUDA(cudaStreamWaitEvent(p->st_copy, p->st_ev[nchunks], 0));
+        VGGP_CUDA(cudaMemsetAsync(p->st_gbuf, 0, (size_t)total, st));
+        const i64 per = ((n + nchunks - 1) / nchunks + 3) / 4 * 4;
+        const PackGeom g = pack_geometry(p, per);
+        if (g.n_packed > p->pk_cap) {
+            VGGP_CUDA(cudaStreamSynchronize(st));
+            for (int d = 0; d < D; ++d) { if (p->pk_x[d]) cudaFree(p->pk_x[d]); p->pk_x[d] = nullptr; }
+            if (p->pk_y) cudaFree(p->pk_y);
+            p->pk_y = nullptr; p->pk_cap = 0;
+            for (int d = 0; d < D; ++d) VGGP_CUDA(cudaMalloc(&p->pk_x[d], tsz * (size_t)g.n_packed));
+            VGGP_CUDA(cudaMalloc(&p->pk_y, tsz * (size_t)g.n_packed));
+            p->pk_cap = g.n_packed;
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const i64 lo = (i64)c * per, hi = std::min<i64>(n, lo + per);
+            if (lo >= hi) break;
+            const void* xdev[VGGP_MAX_D] = {nullptr, nullptr, nullptr};
+            for (int d = 0; d < D; ++d) {
+                unsigned char* dst = reinterpret_cast<unsigned char*>(p->st_x) + ((size_t)d * n + lo) * tsz;
+                VGGP_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const unsigned char*>(x_host[d]) + lo * tsz, tsz * (size_t)(hi - lo),
+                                          cudaMemcpyHostToDevice, p->st_copy));
+                xdev[d] = dst;
+            }
+            unsigned char* ydst = reinterpret_cast<unsigned char*>(p->st_y) + lo * tsz;
+            VGGP_CUDA(cudaMemcpyAsync(ydst, reinterpret_cast<const unsigned char*>(y_host) + lo * tsz, tsz * (size_t)(hi - lo),
+                                      cudaMemcpyHostToDevice, p->st_copy));
+            VGGP_CUDA(cudaEventRecord(p->st_ev[c], p->st_copy));
+            VGGP_CUDA(cudaStreamWaitEvent(st, p->st_ev[c], 0));
+            if ((rc = vggp_obs_pack(p, xdev, ydst, hi - lo, 0, p->pk_x, p->pk_y, stream))) return rc;
+            p->n_real_override = (double)n;                    // every launch stores the shard's count, not its chunk's
+            rc = obs_packed_dispatch(p, p->pk_x, p->pk_y, hi - lo, p->st_gbuf, st);        // accumulates: no memset
+            p->n_real_override = -1.0;
+            if (rc) return rc;
+        }
+    }
     if ((rc = vggp_grid_backward(p, p->st_theta, p->st_m, p->st_L, p->st_gbuf, ell_scale, p->st_out, p->st_dtheta,
                                  p->st_dm, p->st_dL, stream))) return rc;
     VGGP_CUDA(cudaMemcpyAsync(out_host, p->st_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
