@@ -263,6 +263,48 @@ def k1_traffic(layout, run_cap):
     return None
 
 
+def dmma_peak():
+    """FP64 tensor-pipe peak measured on a B200 of this pool by tools/microbench/dmma_peak.cu (pure mma.sync.m8n8k4.f64 on
+    register operands); MEASURED_PEAKS.json has no FP64 entry and the profiling recipe states no fallback for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dmma_peak.json")) as f:
+            return float(json.load(f)["dmma_f64_tflops"]), "measured (profiles/r2_dmma_peak.json, tools/microbench/dmma_peak.cu)"
+    except Exception:
+        return None, "unmeasured"
+
+
+def tensor_roofline(vg, plan, device, reps=20):
+    """The Kronecker mode-n products of the dense grid side (B0 family: alpha = (P_1 x P_2) m and its reverse), timed alone
+    through vggp_mode_product = k_gemm_group (4-stage cp.async pipeline, mma.sync.m8n8k4.f64): FLOPs = 2 M M_d per product."""
+    M = plan.M
+    src = torch.randn(M, dtype=torch.float64, device=device)
+    per_dim, flops, ms_tot = [], 0.0, 0.0
+    for d, n in enumerate(plan.m_per_dim):
+        A = plan.workspace(vg._lib.WS_P, d).clone()
+        for _ in range(3):
+            plan.mode_product(d, A, src)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            plan.mode_product(d, A, src)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        f = 2.0 * M * n
+        per_dim.append({"mode": d, "m_d": n, "ms": ms, "tflops": f / (ms * 1e-3) / 1e12})
+        flops += f
+        ms_tot += ms
+    peak, src_txt = dmma_peak()
+    achieved = flops / (ms_tot * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "k_gemm_group (Kronecker mode-n products T x_d P_d, mma.sync.m8n8k4.f64 = DMMA)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
+            "peak_source": src_txt, "flops": flops, "per_mode": per_dim,
+            "timing": "CUDA events around %d back-to-back launches per mode on the current stream, after 3 warm-up launches" % reps,
+            "note": "FP64 only: the grid side needs float64 (cond(K_d) ~ 1e7) and tcgen05 has no f64 kind, so the tensor "
+                    "instruction is the warp-level DMMA"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -397,9 +439,11 @@ def main():
                          "library's own collective is captured with the rest)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="launch the ~8 kernels of a step eagerly (three C calls per step)")
-    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer"],
                     help="the one collective of a sharded step: NCCL, or the library's own one-kernel all-reduce over NVLink "
-                         "peer memory (vggp_allreduce_gbuf: in-switch multimem reduction; graph-capturable)")
+                         "peer memory (vggp_allreduce_gbuf: in-switch multimem reduction; captured into the step's CUDA graph). "
+                         "auto = peer from 4 ranks up (measured on 8 x B200: 0.118 vs 0.149 ms per step), NCCL for 2 ranks "
+                         "(0.173 vs 0.186 ms) and whenever peer memory cannot be set up")
     ap.add_argument("--reshard-balance", default="count", choices=["count", "cells"],
                     help="--spatial-reshard: cut the cell ranges at observation-count quantiles (default) or evenly")
     ap.add_argument("--spatial-reshard", action="store_true",
@@ -439,7 +483,16 @@ def main():
         args.obs_layout = "binned"          # the B0 family streams per-cell runs too (scan form); there is no packed layout for it
     plan = vg.GridPlan(vg.B1_ASVGP if is_b1 else vg.B0_GRIDDED, meshes, dtype, device)
     multicast = None
-    if world > 1 and args.allreduce == "peer":
+    if args.allreduce == "auto":
+        args.allreduce = "peer" if world >= 4 else "nccl"
+        if world >= 4:
+            try:
+                multicast = plan.enable_peer_allreduce()
+            except Exception as exc:          # no peer access / symmetric memory: every rank fails alike
+                if rank == 0:
+                    print(f"peer-memory all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+                args.allreduce = "nccl"
+    elif world > 1 and args.allreduce == "peer":
         multicast = plan.enable_peer_allreduce()
     xs, y = make_tracks(lo, hi, n_total, device, dtype, D=len(knots))
     sharding = "contiguous in acquisition order"
@@ -712,6 +765,8 @@ def main():
             "clocks": dict(clocks, window="sampled every 20 ms over the last warm-up steps and the timed region "
                                           "(identical step loop; %d extra untimed steps)" % extra_warm),
         }
+        if not is_b1:
+            line["tensor_roofline"] = tensor_roofline(vg, plan, device)
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

@@ -12,7 +12,7 @@ fi
 run() {   # name, extra args
     name=$1; shift
     timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) \
-        bench.py --gpus $N --steps 50 --warmup 5 --no-e2e --no-cpu-baseline "$@" > gpurun_out/multi${N}_$name.json 2> gpurun_out/multi${N}_$name.err
+        bench.py --gpus $N --steps ${STEPS:-50} --warmup 5 --no-e2e --no-cpu-baseline "$@" > gpurun_out/multi${N}_$name.json 2> gpurun_out/multi${N}_$name.err
     rc=$?
     python - "$name" $rc gpurun_out/multi${N}_$name.json <<'PY'
 import json, sys
@@ -33,11 +33,11 @@ run peer --allreduce peer --no-cuda-graph
 run peer_graph --allreduce peer --cuda-graph
 run peer_graph_reshard --allreduce peer --cuda-graph --spatial-reshard
 run nccl_reshard --allreduce nccl --spatial-reshard --no-cuda-graph
-else      # the short set for a large-N call
-run nccl_graph --allreduce nccl --cuda-graph
-run nccl_graph_reshard --allreduce nccl --cuda-graph --spatial-reshard
-run peer_graph --allreduce peer --cuda-graph
-run peer_graph_reshard --allreduce peer --cuda-graph --spatial-reshard
-run 3d_peer_graph --workload 3d --allreduce peer --cuda-graph
-run 3d_peer_graph_reshard --workload 3d --allreduce peer --cuda-graph --spatial-reshard
+else      # the short set for a large-N call (every line replays CUDA graphs, the bench default)
+run nccl_graph --allreduce nccl
+run nccl_graph_reshard --allreduce nccl --spatial-reshard
+run peer_graph --allreduce peer
+run peer_graph_reshard --allreduce peer --spatial-reshard
+run 3d_nccl_graph --workload 3d --allreduce nccl
+run 3d_peer_graph --workload 3d --allreduce peer
 fi

@@ -168,14 +168,17 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pipelined path: 64 x 64 x 16 tiles, two cp.async stages, 8 warps of 32 x 16 (4 x 2 DMMA m8n8k4 tiles each);
-// two warps per scheduler are needed to keep the DMMA pipe busy (ncu: 40 % with one warp per scheduler).
+// Pipelined path: 64 x 64 x 16 tiles, GF_NSTAGE cp.async stages (the round-1 kernel had two: with a k-step of 16 the DMMA work
+// of one stage is shorter than an L2 round trip, so the pipe idled at every stage switch), 8 warps of 32 x 16 (4 x 2 DMMA
+// m8n8k4 tiles each); two warps per scheduler are needed to keep the DMMA pipe busy (ncu: 40 % with one warp per scheduler).
 // Operand tiles keep their memory orientation in shared memory (rows along the contiguous index) with row
 // pitches chosen so that the DMMA fragment reads are bank-conflict free:
 //   k-contiguous operand : [64][20]  (element (mn, k) at mn * 20 + k)
 //   mn-contiguous operand: [16][68]  (element (mn, k) at k * 68 + mn)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GF_STAGE = 2560;     // doubles per stage: A 1280 + B 1280
+constexpr int GF_NSTAGE = 4;       // 80 KB of dynamic shared memory per CTA: two CTAs per SM
+constexpr size_t GEMM_SMEM_BYTES = sizeof(double) * GF_NSTAGE * GF_STAGE;
 
 #ifndef VGGP_EMUL   // tests/host_emul supplies CPU stand-ins
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
@@ -253,22 +256,31 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         for (int j = 0; j < GEMM_NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nk = (kend - kbeg + GBK - 1) / GBK;
-    gemm_stage_tile(sm, Ab, lda, akc, d.a_vec2 != 0, m0, kbeg, d.m, kend, tid);
-    gemm_stage_tile(sm + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, kbeg, d.n, kend, tid);
-    cp_async_commit();
-    for (int it = 0; it < nk; ++it) {
-        if (it + 1 < nk) {
-            double* nx = sm + ((it + 1) & 1) * GF_STAGE;
-            const int k0 = kbeg + (it + 1) * GBK;
+    // prologue: GF_NSTAGE - 1 stages in flight (one commit group per stage, empty groups past the end keep the count uniform)
+#pragma unroll
+    for (int s = 0; s < GF_NSTAGE - 1; ++s) {
+        if (s < nk) {
+            double* nx = sm + s * GF_STAGE;
+            const int k0 = kbeg + s * GBK;
             gemm_stage_tile(nx, Ab, lda, akc, d.a_vec2 != 0, m0, k0, d.m, kend, tid);
             gemm_stage_tile(nx + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, k0, d.n, kend, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
-        const double* As = sm + (it & 1) * GF_STAGE;
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<GF_NSTAGE - 2>();          // stage `it` has landed (for this thread's copies) ...
+        __syncthreads();                         // ... and for everybody's; everybody has also left stage it - 1
+        {
+            const int nxt = it + GF_NSTAGE - 1;  // refill the slot that stage it - 1 occupied
+            if (nxt < nk) {
+                double* nx = sm + (nxt % GF_NSTAGE) * GF_STAGE;
+                const int k0 = kbeg + nxt * GBK;
+                gemm_stage_tile(nx, Ab, lda, akc, d.a_vec2 != 0, m0, k0, d.m, kend, tid);
+                gemm_stage_tile(nx + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, k0, d.n, kend, tid);
+            }
+            cp_async_commit();
+        }
+        const double* As = sm + (it % GF_NSTAGE) * GF_STAGE;
         const double* Bs = As + 1280;
 #pragma unroll
         for (int ks = 0; ks < GBK / 4; ++ks) {
@@ -282,8 +294,8 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
 #pragma unroll
                 for (int ni = 0; ni < GEMM_NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -299,7 +311,8 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
 template <bool MMA>
 __global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
 k_gemm_group(const GemmDesc* __restrict__ descs, int ndesc) {
-    __shared__ __align__(16) double smem[2 * GF_STAGE];
+    extern __shared__ double sm[];          // GEMM_SMEM_BYTES
+    double* smem = sm;
     __shared__ GemmDesc sd;
     const int z = blockIdx.z;
     int p = 0;
@@ -320,7 +333,8 @@ k_gemm_group(const GemmDesc* __restrict__ descs, int ndesc) {
 template <bool MMA>
 __global__ void __launch_bounds__(MMA ? GEMM_THREADS_MMA : GEMM_THREADS_SIMT)
 k_gemm_one(const __grid_constant__ GemmDesc d) {
-    __shared__ __align__(16) double smem[2 * GF_STAGE];
+    extern __shared__ double sm[];          // GEMM_SMEM_BYTES
+    double* smem = sm;
     if (MMA && d.fast) {
         gemm_fast_body(d, blockIdx.z, smem);
     } else {

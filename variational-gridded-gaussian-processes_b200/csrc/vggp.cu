@@ -65,10 +65,12 @@ static int g_b1_structured = 3;    // B1 family: 0 dense, 1 twisted inverse + GE
 
 constexpr int BAND_REPLICAS = 128;
 
+struct ZeroJob { void* ptr; size_t pitch, width, height; };      // cudaMemset2DAsync of a split-K destination (beta = 0)
 struct Phase {
     GemmDesc* d_descs = nullptr;
     int ndesc = 0;
     GemmGroupDims dims = {0, 0, 0};
+    std::vector<ZeroJob> zero;
 };
 }  // namespace vggp
 
@@ -157,9 +159,44 @@ int dev_alloc(vggp_plan* p, T** out, i64 count) {
     return 0;
 }
 
+// A group with fewer output tiles than SMs (one 512^3 product is 64 CTAs on 148 SMs, each at ~45 % of its SM's DMMA rate)
+// is cut along k so that about two CTAs land on every SM: partial sums go through float64 atomics into a destination that
+// already holds beta * C (beta = 1: nothing to do; beta = 0: zero-filled by a cudaMemset2DAsync queued before the launch).
+int g_auto_splitk = 1;
+void auto_splitk(std::vector<GemmDesc>& descs, std::vector<ZeroJob>& zero) {
+    zero.clear();
+    if (!g_auto_splitk) return;
+    i64 ctas = 0;
+    int kmin = 1 << 30;
+    for (const GemmDesc& d : descs) {
+        const i64 tm = (d.m + GBM - 1) / GBM, tn = (d.n + GBN - 1) / GBN;
+        ctas += (d.lower_only ? (tm * (tm + 1)) / 2 : tm * tn) * std::max(1, d.batch) * std::max(1, d.splitk);
+        kmin = std::min(kmin, d.tri_b ? d.k / 2 : d.k);
+        if (d.splitk > 1 || d.kinner != 0) return;
+        if (!(d.beta == 0.0 || d.beta == 1.0)) return;
+        if (d.beta == 0.0 && !(d.csC == 1 || d.rsC == 1)) return;
+    }
+    if (ctas <= 0 || ctas >= 148) return;
+    int sk = (int)std::min<i64>(4, (2 * 148) / ctas);
+    while (sk > 1 && kmin / sk < 4 * GBK) --sk;
+    if (sk <= 1) return;
+    for (GemmDesc& d : descs) {
+        d.splitk = sk;
+        if (d.beta != 0.0) continue;
+        for (int b = 0; b < std::max(1, d.batch); ++b) {
+            ZeroJob z;
+            z.ptr = d.C + (i64)b * d.bsC;
+            if (d.csC == 1) { z.pitch = sizeof(double) * (size_t)d.rsC; z.width = sizeof(double) * (size_t)d.n; z.height = (size_t)d.m; }
+            else { z.pitch = sizeof(double) * (size_t)d.csC; z.width = sizeof(double) * (size_t)d.m; z.height = (size_t)d.n; }
+            zero.push_back(z);
+        }
+    }
+}
+
 int make_phase(vggp_plan* p, std::vector<GemmDesc>& descs, Phase& ph) {
     ph.ndesc = (int)descs.size();
     if (ph.ndesc == 0) return 0;
+    auto_splitk(descs, ph.zero);
     ph.dims = gemm_finalize_group(descs.data(), ph.ndesc);
     int rc = dev_alloc(p, &ph.d_descs, ph.ndesc);
     if (rc) return rc;
@@ -170,18 +207,34 @@ int make_phase(vggp_plan* p, std::vector<GemmDesc>& descs, Phase& ph) {
 int launch_phase(const Phase& ph, cudaStream_t st) {
     if (ph.ndesc == 0) return 0;
     dim3 grid(ph.dims.gx, ph.dims.gy, ph.dims.gz);
-    if (g_use_mma) k_gemm_group<true><<<grid, GEMM_THREADS_MMA, 0, st>>>(ph.d_descs, ph.ndesc);
-    else k_gemm_group<false><<<grid, GEMM_THREADS_SIMT, 0, st>>>(ph.d_descs, ph.ndesc);
+    for (const ZeroJob& z : ph.zero) VGGP_CUDA(cudaMemset2DAsync(z.ptr, z.pitch, 0, z.width, z.height, st));
+    if (g_use_mma) {
+        if (int rc = raise_dyn_smem(k_gemm_group<true>, GEMM_SMEM_BYTES)) return rc;
+        k_gemm_group<true><<<grid, GEMM_THREADS_MMA, GEMM_SMEM_BYTES, st>>>(ph.d_descs, ph.ndesc);
+    } else {
+        if (int rc = raise_dyn_smem(k_gemm_group<false>, GEMM_SMEM_BYTES)) return rc;
+        k_gemm_group<false><<<grid, GEMM_THREADS_SIMT, GEMM_SMEM_BYTES, st>>>(ph.d_descs, ph.ndesc);
+    }
     VGGP_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_one(GemmDesc d, int use_mma, cudaStream_t st) {
-    GemmGroupDims dims = gemm_finalize_group(&d, 1);
     if (d.m <= 0 || d.n <= 0) return 0;
+    std::vector<GemmDesc> one(1, d);
+    std::vector<ZeroJob> zero;
+    if (d.splitk <= 1) auto_splitk(one, zero);
+    d = one[0];
+    GemmGroupDims dims = gemm_finalize_group(&d, 1);
+    for (const ZeroJob& z : zero) VGGP_CUDA(cudaMemset2DAsync(z.ptr, z.pitch, 0, z.width, z.height, st));
     dim3 grid(dims.gx, dims.gy, dims.gz);
-    if (use_mma) k_gemm_one<true><<<grid, GEMM_THREADS_MMA, 0, st>>>(d);
-    else k_gemm_one<false><<<grid, GEMM_THREADS_SIMT, 0, st>>>(d);
+    if (use_mma) {
+        if (int rc = raise_dyn_smem(k_gemm_one<true>, GEMM_SMEM_BYTES)) return rc;
+        k_gemm_one<true><<<grid, GEMM_THREADS_MMA, GEMM_SMEM_BYTES, st>>>(d);
+    } else {
+        if (int rc = raise_dyn_smem(k_gemm_one<false>, GEMM_SMEM_BYTES)) return rc;
+        k_gemm_one<false><<<grid, GEMM_THREADS_SIMT, GEMM_SMEM_BYTES, st>>>(d);
+    }
     VGGP_LAUNCH_CHECK();
     return 0;
 }
@@ -2119,6 +2172,8 @@ int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 // 0: generic kernel; 1: fast kernel, fibre packing by rule (default); 3: fast, no packing; 5: fast, packing forced (tests)
 /* debugging aid: 0 = one-thread-per-fibre sweeps of the B0 scan form (cross-check of the segmented kernels), 1 = default */
 int vggp_debug_b0s_seg(int on) { g_b0s_seg = on ? 1 : 0; return 0; }
+/* debugging aid: 0 = never cut a small GEMM group along k (plans created afterwards), 1 = default */
+int vggp_debug_auto_splitk(int on) { g_auto_splitk = on ? 1 : 0; return 0; }
 /* debugging aid: observations per host-to-device chunk of vggp_elbo_host (default 2^23; tests use small values) */
 int vggp_debug_host_chunk(long long n) { g_host_chunk = n > 4 ? n : 4; return 0; }
 int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
