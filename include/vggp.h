@@ -50,6 +50,9 @@ extern "C" {
 /* feature family */
 #define VGGP_B1_ASVGP   0   /* B1-spline (hat) features, tridiagonal RKHS Kuu: GriddedMatern12ASVGP, Matern12B1SplineASVGP */
 #define VGGP_B0_GRIDDED 1   /* cell-integrated Matern-1/2 features, Toeplitz Kuu: Matern12GriddedGP, Matern12B0SplineGriddedGP */
+#define VGGP_SVGP_GRID  2   /* inducing POINTS on a product grid (kronecker_structure.py:287-338, Matern12SVGP): features
+                             * phi_d(x)[i] = s2_d exp(-|x - z_i| / l_d), Kuu_d = s2_d exp(-|z_i - z_j| / l_d); the knots ARE the inducing
+                             * locations z (M_d = n_knots[d]).  Dense-feature kernel (D <= 2, plain observation arrays); Z is fixed. */
 
 /* observation dtype */
 #define VGGP_F32 0
@@ -74,7 +77,7 @@ uint64_t vggp_launch_count(void);
 
 /*
  * Plan = grid descriptor + workspace, one per (model, device).
- *   family      VGGP_B1_ASVGP | VGGP_B0_GRIDDED
+ *   family      VGGP_B1_ASVGP | VGGP_B0_GRIDDED | VGGP_SVGP_GRID
  *   D           number of input dimensions, 1..VGGP_MAX_D
  *   n_knots     [D] number of knots of each per-dimension mesh (B1: M_d = n_knots, B0: M_d = n_knots-1)
  *   knots_host  [D] host pointers to the float32 knot arrays, exactly as the reference builds them

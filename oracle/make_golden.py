@@ -149,6 +149,11 @@ def golden_models(ks, gks, us, gus):
     # kronecker_structure.py twins (non-square grids are not expressible: nknots shared)
     run2d("K_b1asvgp2d", lambda: ks.Matern12B1SplineASVGP(Xt, yt, 9, (0, 1), (0, 1)))
     run2d("K_b0gridded2d", lambda: ks.Matern12B0SplineGriddedGP(Xt, yt, 9, (0, 1), (0, 1)))
+    # product-grid SVGP (kronecker_structure.py:287-338): inducing points Z (m x 2), one column per dimension, the second
+    # column non-uniform; Z is a parameter of the reference's class (its gradient is recorded, not used)
+    Zs = torch.stack([torch.linspace(0, 1, 7), torch.linspace(0, 1, 7) ** 1.3], dim=1)
+    out["svgp.Z"] = Zs.numpy()
+    run2d("K_svgp2d", lambda: ks.Matern12SVGP(Xt, yt, Zs))
 
     # 1-D: gridded_univariate_structure.Matern12GriddedGP (:709-844).  Its twin
     # univariate_structure.Matern12B0SplineGriddedGP (:721-825) builds a float32 Kuu (0-dim lengthscale) and then

@@ -22,6 +22,7 @@ import torch
 
 B1_ASVGP = 0      # B1-spline (hat) features, tridiagonal RKHS Kuu      (GriddedMatern12ASVGP, Matern12B1SplineASVGP)
 B0_GRIDDED = 1    # cell-integrated Matern-1/2 features, Toeplitz Kuu     (Matern12GriddedGP, Matern12B0SplineGriddedGP)
+SVGP_GRID = 2     # inducing points on a product grid, kernel Kuu / Kuf       (kronecker_structure.py:287-338 Matern12SVGP)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -167,16 +168,36 @@ def kuu_b1(mesh: torch.Tensor, l: torch.Tensor, s2: torch.Tensor, ref_quirks: bo
     return (A.mul(ls) + B.mul(1 / ls) + BC).mul(1 / (2 * sc))        # float32 under ref_quirks (cast after kron)
 
 
+def kuu_svgp(z, l, s2):
+    """Per-dimension factor of Matern12SVGP._Kuu (kronecker_structure.py:321-322): `self.kernel_d(self.Z).evaluate()` with
+    kernel_d = ScaleKernel(MaternKernel(nu = 1/2, active_dims = [d])) (:30-31), i.e. s2 exp(-|z_i - z_j| / l) at the inducing
+    locations `z` (float32 in the reference's parameter, promoted here)."""
+    zz = z.to(torch.float64)
+    return s2.reshape(()) * torch.exp(-(zz[:, None] - zz[None, :]).abs() / l.reshape(()))
+
+
+def svgp_features_dense(z, x, l, s2):
+    """Per-dimension factor of Matern12SVGP._Kuf (kronecker_structure.py:337-338): `self.kernel(full_Z, x).evaluate()` with the
+    product kernel k1 * k2 (:32) on the Cartesian product of the per-dimension inducing locations factorises into
+    prod_d s2_d exp(-|z_{i_d} - x_d| / l_d); this is the d-th factor, an (M_d, N) matrix."""
+    zz = z.to(torch.float64)
+    return s2.reshape(()) * torch.exp(-(zz[:, None] - x.to(torch.float64)[None, :]).abs() / l.reshape(()))
+
+
 def kuu_factor(family: int, mesh, l, s2, ref_quirks=True):
+    if family == SVGP_GRID:
+        return kuu_svgp(mesh, l, s2)
     return kuu_b1(mesh, l, s2, ref_quirks) if family == B1_ASVGP else kuu_b0(mesh, l, s2)
 
 
 def features_dense(family: int, mesh, x, l, s2):
+    if family == SVGP_GRID:
+        return svgp_features_dense(mesh, x, l, s2)
     return b1_features_dense(mesh, x) if family == B1_ASVGP else b0_features_dense(mesh, x, l, s2)
 
 
 def n_inducing(family: int, mesh) -> int:
-    return mesh.numel() if family == B1_ASVGP else mesh.numel() - 1
+    return mesh.numel() - 1 if family == B0_GRIDDED else mesh.numel()
 
 
 def khatri_rao(feats: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -336,7 +357,7 @@ def elbo_structured(family, meshes, X, y, l, s2, noise, m, Ls: Sequence[torch.Te
         p = torch.stack(ps).prod(0)
         q = torch.stack(qs).prod(0)
     else:
-        Fs = [b0_features_dense(meshes[d], Xc[:, d], l[d], s2[d]).to(wd) for d in range(D)]
+        Fs = [features_dense(family, meshes[d], Xc[:, d], l[d], s2[d]).to(wd) for d in range(D)]
         t = alpha.to(wd)
         # contract modes one at a time: t[(i_1..i_D)] with Phi_d[i_d, n]
         t = torch.tensordot(Fs[0].T, t, dims=([1], [0]))                 # (N, M_2..M_D)

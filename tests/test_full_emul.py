@@ -190,6 +190,34 @@ def test_b0_family_under_emulation(emu, knots, N):
     plan.close()
 
 
+@pytest.mark.parametrize("knots,N", [((11,), 300), ((8, 7), 300), ((70, 6), 250)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-3)])
+def test_svgp_product_grid_family_under_emulation(emu, knots, N, dtype, tol):
+    """Product-grid SVGP (kronecker_structure.py:287-338, Matern12SVGP): inducing points on non-uniform per-dimension grids,
+    features s2 exp(-|x - z_i| / l), Kuu_d the kernel matrix of the points; the whole step (dense Cholesky path, dense-feature
+    per-observation kernel with the feature-path hyper-parameter gradients) against the oracle, observations outside the hull
+    of the inducing points included."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=13 + D, family=O.SVGP_GRID, x_lo=-0.2, x_hi=1.2)
+    meshes = [(t ** (1.0 + 0.3 * d)).to(torch.float32) for d, t in enumerate(meshes)]          # strictly increasing, non-uniform
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq, yq = X.to(tdt), y.to(tdt)
+    elbo_ref, g_ref = oracle_value_and_grads(O.SVGP_GRID, meshes, Xq.to(torch.float64), yq.to(torch.float64), l, s2, noise, m, Ls, scale=1.1)
+    plan = emul_lib.EmuPlan(lib, L, L.SVGP_GRID, [t.numpy() for t in meshes], dtype)
+    assert plan.m_per_dim == list(knots)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    xs, np.ascontiguousarray(yq.numpy()), 1.1)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, tol)
+    # the exported dense features are the oracle's
+    phi = plan.features_dense(0, xs[0], theta)
+    ref = O.svgp_features_dense(meshes[0], Xq[:, 0], l[0], s2[0]).numpy()
+    assert np.max(np.abs(phi - ref)) <= (1e-13 if dtype == np.float64 else 1e-6) * np.max(np.abs(ref))
+    plan.close()
+
+
 @pytest.mark.parametrize("name", ["lin11_01", "lin129_01", "lin16_02", "lin21_m3_7", "padded21_pad2"])
 @pytest.mark.parametrize("tag,dtype", [("f64", np.float64), ("f32", np.float32)])
 def test_b1_stencil_kernel_bit_exact_vs_reference_golden(emu, golden_dir, name, tag, dtype):

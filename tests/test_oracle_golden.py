@@ -53,6 +53,8 @@ CASES_2D = {
     "G2q_asvgp2d_pad1": (O.B1_ASVGP, lambda: [O.make_padded_mesh(0, 1, 10, 1)] * 2),
     "K_b1asvgp2d": (O.B1_ASVGP, lambda: [O.make_mesh(0, 1, 9)] * 2),
     "K_b0gridded2d": (O.B0_GRIDDED, lambda: [O.make_mesh(0, 1, 9)] * 2),
+    # kronecker_structure.Matern12SVGP (:287-338): the "meshes" are the columns of its inducing-point parameter Z
+    "K_svgp2d": (O.SVGP_GRID, None),
 }
 
 
@@ -67,7 +69,7 @@ def _params(ps, D):
 @pytest.mark.parametrize("pset", list(PSETS_2D))
 def test_literal_elbo_matches_reference_2d(ref, tag, pset):
     family, mk = CASES_2D[tag]
-    meshes = mk()
+    meshes = mk() if mk is not None else [torch.from_numpy(ref["svgp.Z"][:, d].copy()) for d in range(2)]
     X = torch.from_numpy(ref["nb5.X"])
     y = torch.from_numpy(ref["nb5.y"])
     rl, rs, rn = _params(PSETS_2D[pset], 2)

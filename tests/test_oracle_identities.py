@@ -23,7 +23,7 @@ def _hyp(D, seed=1):
     return rl, rs, rn
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
 @pytest.mark.parametrize("D", [1, 2])
 def test_literal_equals_woodbury(family, D):
     X, y = _data(150, D)
@@ -39,7 +39,7 @@ def test_literal_equals_woodbury(family, D):
         assert torch.allclose(u, v, rtol=1e-8, atol=1e-9)
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
 @pytest.mark.parametrize("D", [1, 2])
 def test_uncollapsed_at_optimum_equals_collapsed(family, D):
     """ELBO(m*, S*) == collapsed bound, and (envelope theorem) so are the hyper-parameter gradients."""
@@ -59,7 +59,7 @@ def test_uncollapsed_at_optimum_equals_collapsed(family, D):
         assert torch.allclose(u, v, rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
 @pytest.mark.parametrize("D,knots", [(1, [9]), (2, [9, 7]), (3, [5, 4, 6])])
 def test_structured_equals_dense_uncollapsed(family, D, knots):
     """G4: Kronecker-factored q(u) through mode products == dense M x M algebra (values and all gradients)."""

@@ -25,6 +25,7 @@ struct GridDims {
     int n[VGGP_MAX_D];            // M_d
     int K[VGGP_MAX_D];            // knots
     float delta32[VGGP_MAX_D];    // mesh[1] - mesh[0] in float32 (reference: SplineBasis.delta, bspline.py:89)
+    const float* knots[VGGP_MAX_D];   // device copy of the knots (SVGP family: the inducing locations z_i)
     i64 M;
     i64 Loff[VGGP_MAX_D];         // offset of L_d inside the concatenated L / dL arrays
     int band_off[VGGP_MAX_D];     // offset (elements) of dim d's block inside the gbuf band part [bp_d|bp_o|bq_d|bq_o]
@@ -101,6 +102,9 @@ __device__ __forceinline__ double factor_entry(const GridDims& g, const double* 
         const int dist = i > j ? i - j : j - i;
         if (dist > 1) return 0.0;
         return (b1_A(i, j, n, dl) * l + b1_B(i, j, n, dl) * (1.0 / l) + b1_BC(i, j, n)) * (1.0 / (2.0 * s2));
+    } else if (g.family == VGGP_SVGP_GRID) {
+        // kernel_d(Z).evaluate(), kronecker_structure.py:321-322: ScaleKernel(MaternKernel(nu = 1/2)) at the inducing points
+        return s2 * exp(-fabs((double)g.knots[d][i] - (double)g.knots[d][j]) / l);
     } else {
         double r, dr;
         b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
@@ -120,6 +124,10 @@ __device__ __forceinline__ void factor_entry_grad(const GridDims& g, const doubl
         const double A = b1_A(i, j, n, dl), B = b1_B(i, j, n, dl), BC = b1_BC(i, j, n);
         dKdl = (A - B / (l * l)) / (2.0 * s2);
         dKds2 = -(A * l + B / l + BC) / (2.0 * s2 * s2);
+    } else if (g.family == VGGP_SVGP_GRID) {
+        const double a = fabs((double)g.knots[d][i] - (double)g.knots[d][j]), e = exp(-a / l);
+        dKdl = s2 * e * a / (l * l);
+        dKds2 = e;
     } else {
         double r, dr;
         b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
@@ -794,7 +802,7 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
             const double E = gscal[0], nobs = gscal[1];
             const double dkff = -ell_scale * nobs / (2.0 * noise);
             atomicAdd(dtheta + D + d, dkff * kff / theta[D + d]);
-            if (g.family == VGGP_B0_GRIDDED) {
+            if (g.family != VGGP_B1_ASVGP) {
                 // the features themselves depend on (l_d, s2_d): sums accumulated by the per-observation kernel
                 atomicAdd(dtheta + d, (ell_scale / noise) * gscal[3 + d]);
                 atomicAdd(dtheta + D + d, (ell_scale / noise) * gscal[5 + d] / theta[D + d]);

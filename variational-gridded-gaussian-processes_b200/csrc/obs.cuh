@@ -139,6 +139,16 @@ __global__ void __launch_bounds__(256) k_b0_dense(MeshView mv, const T* __restri
     phi[(i64)k * n + i] = b0_feature<T>(mv.t, k, idx, xv, (T)l, (T)s2);
 }
 
+// Dense (K, n) SVGP feature matrix: phi[k][i] = s2 exp(-|x_i - z_k| / l).  grid (ceil(n/256), K)
+template <typename T>
+__global__ void __launch_bounds__(256) k_svgp_dense(MeshView mv, const T* __restrict__ x, i64 n, double l, double s2,
+                                                    T* __restrict__ phi) {
+    const int k = blockIdx.y;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    phi[(i64)k * n + i] = (T)s2 * exp(-fabs(x[i] - (T)mv.t[k]) / (T)l);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Packed observation layout.
 //
@@ -706,7 +716,8 @@ struct B0Args {
     const T* y;
     i64 n;
     MeshView mesh[D];
-    int nd[D];               // M_d = K_d - 1
+    int nd[D];               // M_d = K_d - 1 (B0 cells) or K_d (SVGP points)
+    int family;              // VGGP_B0_GRIDDED or VGGP_SVGP_GRID
     const double* theta;     // l[D], s2[D], noise
     const T* alpha;          // (M_1, M_2) row-major, obs dtype
     const double* P[D];
@@ -746,7 +757,12 @@ __global__ void __launch_bounds__(256) k_obs_b0(const __grid_constant__ B0Args<T
             for (int e = tid; e < a.nd[d] * B0_TN; e += blockDim.x) {
                 const int k = e / B0_TN, t = e % B0_TN;
                 T f = (T)0, df = (T)0;
-                if (n0 + t < a.n) {
+                if (n0 + t < a.n && a.family == VGGP_SVGP_GRID) {
+                    // k(z_k, x) of a ScaleKernel(MaternKernel(1/2)) and its lengthscale derivative (kronecker_structure.py:337-338)
+                    const T A1 = fabs(a.x[d][n0 + t] - (T)a.mesh[d].t[k]);
+                    f = s2 * exp(-A1 / l);
+                    df = f * A1 / (l * l);
+                } else if (n0 + t < a.n) {
                     const T xv = a.x[d][n0 + t];
                     const int idx = lower_bound_knots<T>(a.mesh[d].t, a.mesh[d].K, xv);
                     const T A1 = fabs(xv - (T)a.mesh[d].t[k]), A2 = fabs(xv - (T)a.mesh[d].t[k + 1]);

@@ -944,6 +944,7 @@ int launch_obs_b0(vggp_plan* p, const void* const* x, const void* y, i64 n, void
         a.gfac_off[d] = p->gfac_off[d];
         ntot += p->n[d];
     }
+    a.family = p->family;
     a.y = reinterpret_cast<const T*>(y);
     a.n = n;
     a.theta = p->theta_dev;
@@ -1629,7 +1630,8 @@ int vggp_set_b1_structured(int on) {
 int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, const float* const* knots_host,
                      int obs_dtype, int device) {
     if (!out || !n_knots || !knots_host) return fail(VGGP_E_ARG, "null argument");
-    if (family != VGGP_B1_ASVGP && family != VGGP_B0_GRIDDED) return fail(VGGP_E_FAMILY, "unknown feature family");
+    if (family != VGGP_B1_ASVGP && family != VGGP_B0_GRIDDED && family != VGGP_SVGP_GRID) return fail(VGGP_E_FAMILY, "unknown feature family");
+    if (family == VGGP_SVGP_GRID && D > 2) return fail(VGGP_E_UNSUPPORTED, "the SVGP product-grid family is built for D <= 2, as in the reference");
     if (D < 1 || D > VGGP_MAX_D) return fail(VGGP_E_DIM, "D must be 1..3");
     if (obs_dtype != VGGP_F32 && obs_dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "obs_dtype must be VGGP_F32 or VGGP_F64");
     for (int d = 0; d < D; ++d) {
@@ -1658,7 +1660,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     i64 foff = 0;
     for (int d = 0; d < D; ++d) {
         p->K[d] = n_knots[d];
-        p->n[d] = (family == VGGP_B1_ASVGP) ? n_knots[d] : n_knots[d] - 1;
+        p->n[d] = (family == VGGP_B0_GRIDDED) ? n_knots[d] - 1 : n_knots[d];      // B0: cells; B1 / SVGP: one inducing variable per knot
         p->M *= p->n[d];
         g.n[d] = p->n[d]; g.K[d] = p->K[d];
         g.delta32[d] = knots_host[d][1] - knots_host[d][0];
@@ -1690,6 +1692,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         TRY(dev_alloc(p, &p->d_knots[d], K));
         rc = (int)cudaMemcpy(p->d_knots[d], knots_host[d], sizeof(float) * K, cudaMemcpyHostToDevice);
         if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaMemcpy(knots) failed"); }
+        g.knots[d] = p->d_knots[d];
         MeshView& mv = p->mesh[d];
         mv.t = p->d_knots[d]; mv.K = K; mv.t0 = knots_host[d][0];
         mv.inv_h = (float)((double)(K - 1) / ((double)knots_host[d][K - 1] - (double)knots_host[d][0]));
@@ -1822,7 +1825,7 @@ int vggp_gbuf_layout(const vggp_plan* p, int64_t* n_obs_elems, int64_t* scalar_o
                      int64_t* total_bytes) {
     if (!p) return fail(VGGP_E_ARG, "null plan");
     const i64 tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
-    const i64 ne = p->M + (p->family == VGGP_B0_GRIDDED ? p->gfac_total : (i64)p->band_total);
+    const i64 ne = p->M + (p->family != VGGP_B1_ASVGP ? p->gfac_total : (i64)p->band_total);
     const i64 soff = (ne * tsz + 7) / 8 * 8;
     if (n_obs_elems) *n_obs_elems = ne;
     if (scalar_offset_bytes) *scalar_offset_bytes = soff;
@@ -1980,6 +1983,7 @@ int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_
     DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
+    if (p->family == VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP family takes plain observation arrays (vggp_obs_fwd_bwd)");
     if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4");
     if (n >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^31 observations per shard");
     if (n > 0) {
@@ -2020,6 +2024,7 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
     VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
     if (desc->n == 0) return 0;
     if (!binned) return fail(VGGP_E_ARG, "null binned buffer");
+    if (p->family == VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP family takes plain observation arrays (vggp_obs_fwd_bwd)");
     if (p->family == VGGP_B0_GRIDDED) return obs_b0s_dispatch(p, desc, binned, gbuf, st);     // scan form (b0scan.cuh)
     return obs_binned_dispatch(p, desc, binned, gbuf, st);
 }
@@ -2324,7 +2329,12 @@ int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, c
         VGGP_CUDA(cudaMemcpyAsync(th, theta, sizeof(double) * (2 * p->D + 1), cudaMemcpyDeviceToHost, st));
         VGGP_CUDA(cudaStreamSynchronize(st));
         dim3 grid(ceil_div(n, 256), p->n[dim]);
-        if (p->obs_dtype == VGGP_F32)
+        if (p->family == VGGP_SVGP_GRID) {
+            if (p->obs_dtype == VGGP_F32)
+                k_svgp_dense<float><<<grid, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, th[dim], th[p->D + dim], (float*)phi);
+            else
+                k_svgp_dense<double><<<grid, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, th[dim], th[p->D + dim], (double*)phi);
+        } else if (p->obs_dtype == VGGP_F32)
             k_b0_dense<float><<<grid, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, th[dim], th[p->D + dim], (float*)phi);
         else
             k_b0_dense<double><<<grid, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, th[dim], th[p->D + dim], (double*)phi);
@@ -2340,6 +2350,8 @@ int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void
     if (!x || !mean || !var) return fail(VGGP_E_ARG, "null argument");
     for (int d = 0; d < p->D; ++d)
         if (!x[d]) return fail(VGGP_E_ARG, "null test-point pointer");
+    if (p->family == VGGP_SVGP_GRID)
+        return fail(VGGP_E_UNSUPPORTED, "SVGP family: predictions are assembled from vggp_features_dense by the host mirror");
     if (p->family != VGGP_B1_ASVGP)      // B0 family: scan form, O(1) per point (b0scan.cuh)
         return predict_b0s_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
     return predict_dispatch(p, x, n, mean, var, (cudaStream_t)stream);

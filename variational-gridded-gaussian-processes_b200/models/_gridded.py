@@ -42,7 +42,7 @@ class GriddedVariationalGP(nn.Module):
                 k = ScaleKernel(MaternKernel(nu=0.5, active_dims=[d]))
                 setattr(self, f"kernel_{d + 1}", k)
                 self._kernels.append(k)
-        self.m_per_dim = [m.numel() if self.family == _lib.B1_ASVGP else m.numel() - 1 for m in self._meshes]
+        self.m_per_dim = [m.numel() - 1 if self.family == _lib.B0_GRIDDED else m.numel() for m in self._meshes]
         M = 1
         for n in self.m_per_dim:
             M *= n
@@ -115,7 +115,9 @@ class GriddedVariationalGP(nn.Module):
             # VGGP_OBS_LAYOUT=packed selects the round-1 layouts (B1: cell-sorted packed runs, B0: plain arrays through the
             # dense-feature kernel), kept as cross-checks.
             layout = os.environ.get("VGGP_OBS_LAYOUT", "binned")
-            if layout == "binned" and not (self.family != _lib.B1_ASVGP and self.D > 2):
+            if self.family == _lib.SVGP_GRID:
+                self._packed = None                 # dense-feature kernel: plain arrays
+            elif layout == "binned" and not (self.family != _lib.B1_ASVGP and self.D > 2):
                 self._packed = self._plan.bin(xs, y)
             elif self.family != _lib.B1_ASVGP:
                 self._packed = None
