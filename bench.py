@@ -430,7 +430,9 @@ def main():
     ap.add_argument("--obs-layout", default="binned", choices=["packed", "binned"],
                     help="layout the fused per-observation kernel streams: 'binned' = k_obs_b1_binned (per-cell runs in "
                          "warp tasks, default since round 2); 'packed' = k_obs_b1 (round-1 kernel, cross-check)")
-    ap.add_argument("--run-cap", type=int, default=256, help="binned layout: longest run of one cell")
+    ap.add_argument("--run-cap", type=int, default=256,
+                    help="binned layout: longest run of one cell (0 = automatic, smaller caps for thin shards: measured equal to "
+                         "256 at 2 x B200, profiles/r2_s3/multi2/run_cap.txt)")
     ap.add_argument("--binned-stream", default="ldg", choices=["ldg", "tma"],
                     help="binned layout: 16-byte global loads into registers, or a per-warp shared-memory ring "
                          "filled by TMA bulk copies (vggp_set_binned_stream)")
@@ -748,7 +750,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": (("k_obs_b1" if args.obs_layout == "packed" else "k_obs_b1_binned") if is_b1
                                                     else "k_obs_b0s") + " (fused per-observation ELBO forward+backward)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (k1_traffic(args.obs_layout, args.run_cap)
+                         "traffic": (k1_traffic(args.obs_layout, packed.run_cap if args.obs_layout == "binned" else args.run_cap)
                                      if (world == 1 and args.workload == "tracks512" and n_total == N_TOTAL) else None),
                          "peak_source": peak_src, "kernel_ms": k1_ms, "kernel_launches_timed": k1_launches,
                          "timing": ("CUDA events recorded by the library immediately around the kernel launch, on the "

@@ -33,6 +33,11 @@ run peer --allreduce peer --no-cuda-graph
 run peer_graph --allreduce peer --cuda-graph
 run peer_graph_reshard --allreduce peer --cuda-graph --spatial-reshard
 run nccl_reshard --allreduce nccl --spatial-reshard --no-cuda-graph
+elif [ "${RUNSET}" = "cap" ]; then      # run-cap check: automatic against 256, time- and cell-range shards
+run auto --allreduce ${AR:-nccl}
+run cap256 --allreduce ${AR:-nccl} --run-cap 256
+run auto_reshard --allreduce ${AR:-nccl} --spatial-reshard
+run cap256_reshard --allreduce ${AR:-nccl} --spatial-reshard --run-cap 256
 else      # the short set for a large-N call (every line replays CUDA graphs, the bench default)
 run nccl_graph --allreduce nccl
 run nccl_graph_reshard --allreduce nccl --spatial-reshard

@@ -192,27 +192,52 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 #endif
 
-// Stage one operand tile.  `kc`: the k index is the contiguous one.  Rows of the tile run along the other index.
-//   kc  : 64 rows (mn) x 16 (k),  global (mn, k) at base + mn * ld + k
-//   !kc : 16 rows (k)  x 64 (mn), global (mn, k) at base + k * ld + mn
-__device__ __forceinline__ void gemm_stage_tile(double* sm, const double* __restrict__ base, i64 ld, bool kc, bool vec2,
-                                                int mn0, int k0, int mn_lim, int k_lim, int tid) {
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int c = tid + it * 256;
-        int row, col, grow, gcol, row_lim, col_lim;
-        double* dst;
-        if (kc) { row = c >> 3; col = (c & 7) << 1; grow = mn0 + row; gcol = k0 + col; row_lim = mn_lim; col_lim = k_lim; dst = sm + row * 20 + col; }
-        else    { row = c >> 5; col = (c & 31) << 1; grow = k0 + row; gcol = mn0 + col; row_lim = k_lim; col_lim = mn_lim; dst = sm + row * 68 + col; }
-        int valid = (grow < row_lim) ? (col_lim - gcol) : 0;
-        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
-        const double* src = valid ? base + (i64)grow * ld + gcol : base;
-        if (vec2) {
-            cp_async16(dst, src, valid * 8);
-        } else {
-            cp_async8(dst, src, valid > 0 ? 8 : 0);
-            cp_async8(dst + 1, valid > 1 ? src + 1 : base, valid > 1 ? 8 : 0);
-        }
+// Staging of one operand tile, two 16-byte slots per thread and stage.  `kc`: the k index is the contiguous one.
+//   kc  : 64 rows (mn) x 16 (k),  global (mn, k) at base + mn * ld + k,  shared [64][20]
+//   !kc : 16 rows (k)  x 64 (mn), global (mn, k) at base + k * ld + mn,  shared [16][68]
+// Everything that does not depend on the k-step -- source pointer at kbeg, shared-memory offset, the row / column validity --
+// is worked out once per slot before the main loop (the first version recomputed it for every stage: 12 instructions per
+// DMMA in the ncu capture of round 2); a stage then costs a clamp, the copy and nothing else.
+struct GemmSlot {
+    const double* src;      // element at k = kbeg (may point outside the operand when the slot is never valid)
+    int dst;                // offset inside the stage's operand tile
+    int kpos;               // k offset of the slot inside a stage (kc: column, !kc: row)
+    int fixed;              // kc: 1 if the row exists; !kc: number of valid elements along mn (0..2)
+};
+__device__ __forceinline__ GemmSlot gemm_slot(const double* __restrict__ base, i64 ld, bool kc, int mn0, int kbeg, int mn_lim,
+                                              int tid, int it) {
+    const int c = tid + it * 256;
+    GemmSlot s;
+    if (kc) {
+        const int row = c >> 3, col = (c & 7) << 1;
+        s.dst = row * 20 + col;
+        s.kpos = col;
+        s.fixed = (mn0 + row < mn_lim) ? 1 : 0;
+        s.src = base + (i64)(mn0 + row) * ld + (kbeg + col);
+    } else {
+        const int row = c >> 5, col = (c & 31) << 1;
+        s.dst = row * 68 + col;
+        s.kpos = row;
+        int v = mn_lim - (mn0 + col);
+        s.fixed = v < 0 ? 0 : (v > 2 ? 2 : v);
+        s.src = base + (i64)(kbeg + row) * ld + (mn0 + col);
+    }
+    return s;
+}
+// copy the slot for the stage that starts at k = kbeg + koff (koff a multiple of GBK); `kstep` = ld for !kc, 1 for kc
+__device__ __forceinline__ void gemm_stage_slot(double* sm, const GemmSlot& s, bool kc, bool vec2, i64 kstep, int koff, int krem,
+                                                const double* __restrict__ base) {
+    // krem = k_lim - (kbeg + koff): k values left from the start of this stage
+    int valid;
+    if (kc) { valid = s.fixed ? krem - s.kpos : 0; valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid); }
+    else valid = (s.kpos < krem) ? s.fixed : 0;
+    const double* src = valid ? s.src + (i64)koff * kstep : base;
+    double* dst = sm + s.dst;
+    if (vec2) {
+        cp_async16(dst, src, valid * 8);
+    } else {
+        cp_async8(dst, src, valid > 0 ? 8 : 0);
+        cp_async8(dst + 1, valid > 1 ? src + 1 : base, valid > 1 ? 8 : 0);
     }
 }
 
@@ -256,30 +281,29 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         for (int j = 0; j < GEMM_NI; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nk = (kend - kbeg + GBK - 1) / GBK;
+    const bool av2 = d.a_vec2 != 0, bv2 = d.b_vec2 != 0;
+    const GemmSlot sa0 = gemm_slot(Ab, lda, akc, m0, kbeg, d.m, tid, 0), sa1 = gemm_slot(Ab, lda, akc, m0, kbeg, d.m, tid, 1);
+    const GemmSlot sb0 = gemm_slot(Bb, ldb, !bnc, n0, kbeg, d.n, tid, 0), sb1 = gemm_slot(Bb, ldb, !bnc, n0, kbeg, d.n, tid, 1);
+    const i64 ksa = akc ? 1 : lda, ksb = !bnc ? 1 : ldb;
+    auto stage = [&](int st) {
+        double* nx = sm + (st % GF_NSTAGE) * GF_STAGE;
+        const int koff = st * GBK, krem = kend - kbeg - koff;
+        gemm_stage_slot(nx, sa0, akc, av2, ksa, koff, krem, Ab);
+        gemm_stage_slot(nx, sa1, akc, av2, ksa, koff, krem, Ab);
+        gemm_stage_slot(nx + 1280, sb0, !bnc, bv2, ksb, koff, krem, Bb);
+        gemm_stage_slot(nx + 1280, sb1, !bnc, bv2, ksb, koff, krem, Bb);
+    };
     // prologue: GF_NSTAGE - 1 stages in flight (one commit group per stage, empty groups past the end keep the count uniform)
 #pragma unroll
     for (int s = 0; s < GF_NSTAGE - 1; ++s) {
-        if (s < nk) {
-            double* nx = sm + s * GF_STAGE;
-            const int k0 = kbeg + s * GBK;
-            gemm_stage_tile(nx, Ab, lda, akc, d.a_vec2 != 0, m0, k0, d.m, kend, tid);
-            gemm_stage_tile(nx + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, k0, d.n, kend, tid);
-        }
+        if (s < nk) stage(s);
         cp_async_commit();
     }
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<GF_NSTAGE - 2>();          // stage `it` has landed (for this thread's copies) ...
         __syncthreads();                         // ... and for everybody's; everybody has also left stage it - 1
-        {
-            const int nxt = it + GF_NSTAGE - 1;  // refill the slot that stage it - 1 occupied
-            if (nxt < nk) {
-                double* nx = sm + (nxt % GF_NSTAGE) * GF_STAGE;
-                const int k0 = kbeg + nxt * GBK;
-                gemm_stage_tile(nx, Ab, lda, akc, d.a_vec2 != 0, m0, k0, d.m, kend, tid);
-                gemm_stage_tile(nx + 1280, Bb, ldb, !bnc, d.b_vec2 != 0, n0, k0, d.n, kend, tid);
-            }
-            cp_async_commit();
-        }
+        if (it + GF_NSTAGE - 1 < nk) stage(it + GF_NSTAGE - 1);      // refill the slot that stage it - 1 occupied
+        cp_async_commit();
         const double* As = sm + (it % GF_NSTAGE) * GF_STAGE;
         const double* Bs = As + 1280;
 #pragma unroll

@@ -1984,7 +1984,14 @@ int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_
     if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
     if (p->family == VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP family takes plain observation arrays (vggp_obs_fwd_bwd)");
-    if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4");
+    if (run_cap == 0) {
+        // automatic: about two tasks (of 32 runs) per resident warp, so that thin shards and cell-range shards (few, full cells)
+        // still spread over the whole GPU; 256 (the value the 1-GPU measurements settled on) from 2^25.8 observations up
+        const i64 warps = (i64)p->sm_count * 24;
+        const i64 want = (n + 64 * warps - 1) / (64 * warps);
+        run_cap = (int)std::min<i64>(256, std::max<i64>(32, (want + 3) / 4 * 4));
+    }
+    if (run_cap < 4) return fail(VGGP_E_ARG, "run_cap must be >= 4 (0 = automatic)");
     if (n >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "binning supports n < 2^31 observations per shard");
     if (n > 0) {
         if (!x) return fail(VGGP_E_ARG, "null observation pointers");
