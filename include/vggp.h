@@ -301,6 +301,18 @@ int vggp_predict_metrics(vggp_plan* plan, const void* const* x, const void* y, i
 int vggp_minmax(int dtype, const void* x, int64_t n, void* minmax, void* stream);
 int vggp_minmax_scale(int dtype, const void* x, int64_t n, const void* minmax, int inverse, void* y, void* stream);
 
+/*
+ * Synthetic satellite-track observations generated on the device: the geometry of the
+ * reference's generate_track (src/utils/dataloaders.py:290-377, notebook call trajectory_gradient = 2): `passes` ascending
+ * passes x1 = j / passes + t / gradient (wrapped into [0, 1)), x2 = t, then as many descending ones (x2 = 1 - t), in
+ * acquisition order; targets = a smooth field + noise of standard deviation 0.05; D = 3 adds the acquisition time as x3 and a
+ * slow drift of the field.  Observation i of the data set is a pure function of (i, seed): a rank generates its shard
+ * [lo, hi) of the same n_total observations whatever the sharding.
+ *   x [D] HOST array of device pointers, hi - lo values of `dtype` each; y likewise.  Asynchronous on `stream`.
+ */
+int vggp_generate_tracks(int dtype, int D, int64_t n_total, int64_t lo, int64_t hi, int64_t seed, int passes, double gradient,
+                         void* const* x, void* y, void* stream);
+
 /* ---- workspace views and primitives (tests, predictions, debugging) ------------------------------------ */
 
 /* Device pointer to a float64 workspace array of the last forward.  which: */

@@ -516,3 +516,37 @@ def test_host_entry_point_chunked_transfer_under_emulation(emu, knots, N, chunk)
         for a, b in zip(got, ref):
             assert relerr(torch.from_numpy(a), torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-11
     plan.close()
+
+
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_track_generator_under_emulation(emu, D, dtype):
+    """vggp_generate_tracks (the synthetic along-track data set of the bench, generated by the library) against the torch
+    restatement in bench.py: identical coordinates (integer hash + separately rounded float64 operations), targets equal up to
+    the last bits of sin / cos; a shard [lo, hi) is the corresponding slice of the whole data set."""
+    import ctypes as C
+    import bench
+    lib, L = emu
+    n_total, seed = 6000, 3
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    xs_ref, y_ref = bench.make_tracks_torch(0, n_total, n_total, torch.device("cpu"), tdt, seed=seed, D=D)
+
+    def gen(lo, hi):
+        xs = [np.zeros(hi - lo, dtype=dtype) for _ in range(D)]
+        y = np.zeros(hi - lo, dtype=dtype)
+        ptrs = (C.c_void_p * D)(*[x.ctypes.data for x in xs])
+        rc = lib.vggp_generate_tracks(L.F32 if dtype == np.float32 else L.F64, D, n_total, lo, hi, seed, bench.PASSES,
+                                      C.c_double(bench.TRACK_GRADIENT), ptrs, y.ctypes.data, None)
+        assert rc == 0, lib.vggp_last_error()
+        return xs, y
+
+    xs, y = gen(0, n_total)
+    for d in range(D):
+        assert np.array_equal(xs[d], xs_ref[d].numpy()), d
+    tol = 2e-7 if dtype == np.float32 else 1e-14
+    assert np.max(np.abs(y - y_ref.numpy())) <= tol * max(1.0, float(y_ref.abs().max()))
+    assert 0.0 <= min(x.min() for x in xs) and max(x.max() for x in xs) <= 1.0
+    xs_s, y_s = gen(1234, 4321)
+    for d in range(D):
+        assert np.array_equal(xs_s[d], xs[d][1234:4321])
+    assert np.array_equal(y_s, y[1234:4321])

@@ -317,3 +317,23 @@ def test_binned_full_size_matches_packed_bench_config(vg, dev, stream_mode):
         acc_scal += sc
     assert relerr(acc_obs, obs_full) < 1e-4
     assert acc_scal[1].item() == N and abs(acc_scal[0].item() - scal_full[0].item()) < 1e-5 * abs(scal_full[0].item())
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_track_generator_matches_torch_restatement(vg, dev, D):
+    """vggp_generate_tracks on the device against bench.make_tracks_torch (the same expressions as torch device ops): same
+    coordinates bit for bit, targets within one float32 ulp (sin / cos of the same libdevice), shards are slices."""
+    import bench
+    n_total = 1 << 20
+    xs, y = bench.make_tracks(0, n_total, n_total, dev, torch.float32, seed=1, D=D)
+    xs_ref, y_ref = bench.make_tracks_torch(0, n_total, n_total, dev, torch.float32, seed=1, D=D)
+    for d in range(D):
+        assert torch.equal(xs[d], xs_ref[d]), d
+    assert (y - y_ref).abs().max().item() <= 5e-7
+    gen = importlib.import_module("variational-gridded-gaussian-processes_b200.utils.dataloaders")
+    xs_s, y_s = gen.generate_tracks(1000, 500000, n_total, dev, torch.float32, seed=1, D=D)
+    for d in range(D):
+        assert torch.equal(xs_s[d], xs[d][1000:500000])
+    assert torch.equal(y_s, y[1000:500000])
+    with pytest.raises(RuntimeError):
+        gen.generate_tracks(0, 10, 10, "cpu")

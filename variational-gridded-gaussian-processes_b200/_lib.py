@@ -62,6 +62,7 @@ SIGNATURES = {
     "vggp_predict_metrics": (C.c_int, [_vp, C.POINTER(_vp), _dp, _i64, _dp, _vp]),
     "vggp_minmax": (C.c_int, [C.c_int, _dp, _i64, _dp, _vp]),
     "vggp_minmax_scale": (C.c_int, [C.c_int, _dp, _i64, _dp, C.c_int, _dp, _vp]),
+    "vggp_generate_tracks": (C.c_int, [C.c_int, C.c_int, _i64, _i64, _i64, _i64, C.c_int, C.c_double, C.POINTER(_vp), _vp, _vp]),
     "vggp_elbo_host": (C.c_int, [_vp, C.POINTER(_vp), _vp, _i64, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "vggp_b1_stencil": (C.c_int, [_vp, C.c_int, _dp, _i64, _dp, _dp, _dp, _vp]),
     "vggp_features_dense": (C.c_int, [_vp, C.c_int, _dp, _i64, _dp, _dp, _vp]),

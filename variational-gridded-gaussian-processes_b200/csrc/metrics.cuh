@@ -179,4 +179,70 @@ __global__ void __launch_bounds__(256) k_minmax_scale(const T* __restrict__ x, i
         y[i] = inverse ? rn_add(rn_mul(x[i], span), lo) : rn_div(rn_sub(x[i], lo), span);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Synthetic satellite-track observations generated on the device: the geometry of the
+// reference's `generate_track` (src/utils/dataloaders.py:290-377; notebook call trajectory_gradient = 2) -- `passes`
+// ascending passes x1 = o_j + t / g, x2 = t followed by as many descending ones (x2 = 1 - t), offsets o_j = j / passes, x1
+// wrapped into [0, 1) -- in acquisition order (pass-major), a smooth field plus noise as targets, and for D = 3 the
+// acquisition time as third coordinate.  Every observation is a pure function of its GLOBAL index (counter-based hash), so a
+// rank generates exactly its shard [lo, hi) of the same data set whatever the sharding.  All arithmetic is float64 with
+// separately rounded operations (no FMA contraction): bit for bit the torch expressions of bench.py's make_tracks_torch.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double track_hash_uniform(i64 idx, i64 salt) {
+    unsigned long long h = (unsigned long long)idx * 6364136223846793005ull
+                           + (1442695040888963407ull + (unsigned long long)salt * 7046029254386353131ull);
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return (double)((h >> 11) & ((1ull << 40) - 1ull)) / 1099511627776.0;      // 2^40
+}
+
+template <typename T, int D>
+struct TrackArgs {
+    T* x[D];
+    T* y;
+    i64 lo, hi, n_total;
+    i64 seed;
+    int passes;
+    double gradient;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_generate_tracks(const __grid_constant__ TrackArgs<T, D> a) {
+    i64 per_pass = a.n_total / (2 * (i64)a.passes);
+    if (per_pass < 1) per_pass = 1;
+    const double noise_c = 0.05 * 1.7320508075688772;          // 0.05 * sqrt(3): sum of 4 uniforms has variance 1 / 3
+    for (i64 i = a.lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi; i += (i64)gridDim.x * blockDim.x) {
+        i64 j = i / per_pass;
+        if (j > 2 * (i64)a.passes - 1) j = 2 * (i64)a.passes - 1;
+        const i64 k = i - j * per_pass;
+        const double jitter = track_hash_uniform(i, 2 * a.seed + 1);
+        double t = __ddiv_rn(__dadd_rn((double)k, jitter), (double)per_pass);
+        t = fmin(fmax(t, 0.0), 1.0);
+        const bool asc = j < a.passes;
+        const double off = __ddiv_rn((double)(j % a.passes), (double)a.passes);
+        double x1 = __dadd_rn(off, __ddiv_rn(t, a.gradient));
+        x1 = __dsub_rn(x1, floor(x1));
+        const double x2 = asc ? t : __dsub_rn(1.0, t);
+        double u = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u = __dadd_rn(u, track_hash_uniform(i, 2 * a.seed + 10 + q));
+        u = __dsub_rn(u, 2.0);
+        double f = __dadd_rn(sin(__dmul_rn(5.0, x1)), cos(__dmul_rn(7.0, x2)));
+        f = __dadd_rn(f, __dmul_rn(0.5, sin(__dmul_rn(15.0, x1))));
+        f = __dadd_rn(f, __dmul_rn(0.5, cos(__dmul_rn(12.0, x2))));
+        double yv = __dadd_rn(f, __dmul_rn(noise_c, u));
+        const i64 o = i - a.lo;
+        a.x[0][o] = (T)x1;
+        if (D >= 2) a.x[D >= 2 ? 1 : 0][o] = (T)x2;
+        if (D == 3) {
+            double x3 = __ddiv_rn(__dadd_rn((double)i, track_hash_uniform(i, 2 * a.seed + 31)), (double)a.n_total);
+            x3 = fmin(fmax(x3, 0.0), 1.0);
+            yv = __dadd_rn(yv, __dmul_rn(__dmul_rn(0.3, sin(__dmul_rn(4.0, x3))), cos(__dmul_rn(3.0, x1))));
+            a.x[D - 1][o] = (T)x3;
+        }
+        a.y[o] = (T)yv;
+    }
+}
+
 }  // namespace vggp

@@ -1606,6 +1606,18 @@ int predict_b0s_dispatch(vggp_plan* p, const void* const* x, i64 n, void* mean, 
 }  // namespace
 
 // =========================================================================================================
+template <typename T, int D>
+int launch_tracks(void* const* x, void* y, i64 lo, i64 hi, i64 n_total, i64 seed, int passes, double gradient, cudaStream_t st) {
+    TrackArgs<T, D> a;
+    for (int d = 0; d < D; ++d) a.x[d] = reinterpret_cast<T*>(x[d]);
+    a.y = reinterpret_cast<T*>(y);
+    a.lo = lo; a.hi = hi; a.n_total = n_total; a.seed = seed; a.passes = passes; a.gradient = gradient;
+    const int blocks = (int)std::min<i64>((hi - lo + 255) / 256, 148 * 16);
+    k_generate_tracks<T, D><<<blocks, 256, 0, st>>>(a);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" {
 
 int vggp_abi_version(void) { return VGGP_ABI_VERSION; }
@@ -2425,6 +2437,26 @@ int vggp_minmax_scale(int dtype, const void* x, int64_t n, const void* minmax, i
     else k_minmax_scale<double><<<blocks, 256, 0, st>>>((const double*)x, n, (const double*)minmax, inverse, (double*)y);
     VGGP_LAUNCH_CHECK();
     return 0;
+}
+
+int vggp_generate_tracks(int dtype, int D, int64_t n_total, int64_t lo, int64_t hi, int64_t seed, int passes, double gradient,
+                         void* const* x, void* y, void* stream) {
+    if (dtype != VGGP_F32 && dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "dtype must be VGGP_F32 or VGGP_F64");
+    if (D < 1 || D > VGGP_MAX_D) return fail(VGGP_E_DIM, "D must be 1..3");
+    if (n_total < 1 || lo < 0 || hi < lo || hi > n_total || passes < 1 || !(gradient > 0.0)) return fail(VGGP_E_ARG, "bad argument");
+    if (hi == lo) return 0;
+    if (!x || !y) return fail(VGGP_E_ARG, "null argument");
+    for (int d = 0; d < D; ++d)
+        if (!x[d]) return fail(VGGP_E_ARG, "null coordinate pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VGGP_F32) {
+        if (D == 1) return launch_tracks<float, 1>(x, y, lo, hi, n_total, seed, passes, gradient, st);
+        if (D == 2) return launch_tracks<float, 2>(x, y, lo, hi, n_total, seed, passes, gradient, st);
+        return launch_tracks<float, 3>(x, y, lo, hi, n_total, seed, passes, gradient, st);
+    }
+    if (D == 1) return launch_tracks<double, 1>(x, y, lo, hi, n_total, seed, passes, gradient, st);
+    if (D == 2) return launch_tracks<double, 2>(x, y, lo, hi, n_total, seed, passes, gradient, st);
+    return launch_tracks<double, 3>(x, y, lo, hi, n_total, seed, passes, gradient, st);
 }
 
 int vggp_workspace_ptr(const vggp_plan* p, int which, int dim, double** ptr, int64_t* n_elems) {
