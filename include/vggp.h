@@ -53,6 +53,10 @@ extern "C" {
 #define VGGP_SVGP_GRID  2   /* inducing POINTS on a product grid (kronecker_structure.py:287-338, Matern12SVGP): features
                              * phi_d(x)[i] = s2_d exp(-|x - z_i| / l_d), Kuu_d = s2_d exp(-|z_i - z_j| / l_d); the knots ARE the inducing
                              * locations z (M_d = n_knots[d]).  Dense-feature kernel (D <= 2, plain observation arrays); Z is fixed. */
+#define VGGP_VFF_GRID   3   /* variational Fourier features (kronecker_structure.py:347-514 Matern12VFFGP, src/basis/fourier.py:58-88):
+                             * per dimension M + 1 cosines and M sines of w_k = 2 pi k / (b - a) on the domain [a, b), exp(-r / l) outside,
+                             * Kuu_d = diag(alpha) + beta beta^T.  The mesh of a dimension has 2 M + 1 knots spanning [a, b]: only its end
+                             * points and its size are used (M_d = n_knots[d], odd).  Dense-feature kernel, D <= 2. */
 
 /* observation dtype */
 #define VGGP_F32 0
@@ -77,7 +81,7 @@ uint64_t vggp_launch_count(void);
 
 /*
  * Plan = grid descriptor + workspace, one per (model, device).
- *   family      VGGP_B1_ASVGP | VGGP_B0_GRIDDED | VGGP_SVGP_GRID
+ *   family      VGGP_B1_ASVGP | VGGP_B0_GRIDDED | VGGP_SVGP_GRID | VGGP_VFF_GRID
  *   D           number of input dimensions, 1..VGGP_MAX_D
  *   n_knots     [D] number of knots of each per-dimension mesh (B1: M_d = n_knots, B0: M_d = n_knots-1)
  *   knots_host  [D] host pointers to the float32 knot arrays, exactly as the reference builds them

@@ -154,6 +154,10 @@ def golden_models(ks, gks, us, gus):
     Zs = torch.stack([torch.linspace(0, 1, 7), torch.linspace(0, 1, 7) ** 1.3], dim=1)
     out["svgp.Z"] = Zs.numpy()
     run2d("K_svgp2d", lambda: ks.Matern12SVGP(Xt, yt, Zs))
+    # variational Fourier features (kronecker_structure.py:347-514): 4 frequencies per dimension; the second domain is smaller
+    # than the data, so the outside-of-domain branch of the basis (fourier.py:64-75) is part of the fixture; limits exactly
+    # representable in float32 (the library sees them as float32 knots)
+    run2d("K_vff2d", lambda: ks.Matern12VFFGP(Xt, yt, 4, (-0.125, 1.125), (0.25, 0.75)))
 
     # 1-D: gridded_univariate_structure.Matern12GriddedGP (:709-844).  Its twin
     # univariate_structure.Matern12B0SplineGriddedGP (:721-825) builds a float32 Kuu (0-dim lengthscale) and then

@@ -52,6 +52,10 @@ class _DenseLazy:
     def add_diagonal(self, diag):
         return _DenseLazy(self.tensor + torch.diag_embed(diag.to(self.tensor.dtype)))
 
+    def add_low_rank(self, low_rank_mat):
+        # LinearOperator.add_low_rank: A + B B^T (call site: kronecker_structure.py:462, DiagLinearOperator(alpha).add_low_rank(beta))
+        return _DenseLazy(self.tensor + low_rank_mat @ low_rank_mat.transpose(-1, -2))
+
     def mul(self, other):
         if isinstance(other, _DenseLazy):
             other = other.tensor

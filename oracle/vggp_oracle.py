@@ -23,6 +23,7 @@ import torch
 B1_ASVGP = 0      # B1-spline (hat) features, tridiagonal RKHS Kuu      (GriddedMatern12ASVGP, Matern12B1SplineASVGP)
 B0_GRIDDED = 1    # cell-integrated Matern-1/2 features, Toeplitz Kuu     (Matern12GriddedGP, Matern12B0SplineGriddedGP)
 SVGP_GRID = 2     # inducing points on a product grid, kernel Kuu / Kuf       (kronecker_structure.py:287-338 Matern12SVGP)
+VFF_GRID = 3      # variational Fourier features, diagonal + rank-one Kuu    (kronecker_structure.py:347-514 Matern12VFFGP)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -184,13 +185,65 @@ def svgp_features_dense(z, x, l, s2):
     return s2.reshape(()) * torch.exp(-(zz[:, None] - x.to(torch.float64)[None, :]).abs() / l.reshape(()))
 
 
+def vff_domain(mesh):
+    """The library describes a VFF dimension by a float32 mesh of 2 M + 1 knots spanning the domain [a, b]: only its end points
+    and its size (the number of features: M + 1 cosines, M sines) are used."""
+    n = int(mesh.numel())
+    assert n % 2 == 1 and n >= 3, "a VFF mesh has 2 * nfrequencies + 1 knots"
+    return float(mesh[0]), float(mesh[-1]), (n - 1) // 2
+
+
+def kuu_vff(mesh, l, s2, ref_quirks=True):
+    """Matern12VFFGP._Kuu_along_dim (kronecker_structure.py:447-462): DiagLinearOperator(alpha).add_low_rank(beta) with
+    alpha = (b - a) / 2 [2 / S(0), 1 / S(w_1..w_M), 1 / S(w_1..w_M)] (:403-420), S(w) = 2 s2 lambda / (lambda^2 + w^2), lambda = 1 / l
+    (:373-392), beta = [1 / sqrt(s2) (M + 1 times), 0 (M times)] (:422-445).  ref_quirks: the reference's frequencies are a
+    float32 tensor (fourier.py:13), which makes alpha, beta and hence Kuu float32 before the final cast (:462 'TODO: this is also
+    wrong')."""
+    a, b, Mf = vff_domain(mesh)
+    wd = torch.float32 if ref_quirks else torch.float64
+    omegas = ((2 * torch.pi) * torch.arange(Mf + 1, dtype=wd) / (b - a)).to(wd)       # fourier.py:13 (float32 there)
+    lmbda = 1 / l.reshape(())
+    num = 2 * s2.reshape(()) * lmbda                                    # float64
+    den = (lmbda ** 2).to(wd) + omegas ** 2
+    sd = (num.to(wd) / den) if ref_quirks else num / den
+    S_inv = 1 / sd
+    alpha = ((b - a) / 2) * torch.cat([2 * S_inv[0][None], S_inv[1:], S_inv[1:]])
+    beta = torch.cat([torch.ones(Mf + 1, dtype=wd) / s2.reshape(()).sqrt().to(wd), torch.zeros(Mf, dtype=wd)])
+    return (torch.diag_embed(alpha) + beta[:, None] * beta[None, :]).to(torch.float64)
+
+
+def vff_features_dense(mesh, x, l, s2, ref_quirks=True):
+    """Matern12VFFGP._Kuf_along_dim (kronecker_structure.py:464-480) = FourierBasisMatern12(nfrequencies, a, b, l)(x)
+    (fourier.py:58-88): inside the domain a <= x < b the M + 1 cosines cos(w_k (x - a)) followed by the M sines sin(w_k (x - a));
+    outside exp(-r / l) with r the distance to the nearer end for the cosine rows and zero for the sine rows.  They do not depend
+    on s2.  ref_quirks: the products with the float32 frequencies are float32 (the 0-dim float64 coordinate is cast), as is the
+    outside value once it multiplies torch.ones(M + 1)."""
+    a, b, Mf = vff_domain(mesh)
+    wd = torch.float32 if ref_quirks else torch.float64
+    omegas = ((2 * torch.pi) * torch.arange(Mf + 1, dtype=wd) / (b - a)).to(wd)       # fourier.py:13 (float32 there)
+    xx = x.to(torch.float64)
+    inside = (xx >= a) & (xx < b)
+    t = (xx - a).to(wd)
+    cosr = torch.cos(omegas[:, None] * t[None, :])
+    sinr = torch.sin(omegas[1:, None] * t[None, :])
+    r = torch.minimum((xx - a).abs(), (xx - b).abs())
+    out_val = torch.exp(-(1 / l.reshape(())) * r).to(wd)
+    real = torch.where(inside[None, :], cosr, out_val[None, :].expand(Mf + 1, -1))
+    imag = torch.where(inside[None, :], sinr, torch.zeros((), dtype=wd))
+    return torch.cat([real, imag], dim=0).to(torch.float64)
+
+
 def kuu_factor(family: int, mesh, l, s2, ref_quirks=True):
+    if family == VFF_GRID:
+        return kuu_vff(mesh, l, s2, ref_quirks)
     if family == SVGP_GRID:
         return kuu_svgp(mesh, l, s2)
     return kuu_b1(mesh, l, s2, ref_quirks) if family == B1_ASVGP else kuu_b0(mesh, l, s2)
 
 
-def features_dense(family: int, mesh, x, l, s2):
+def features_dense(family: int, mesh, x, l, s2, ref_quirks=False):
+    if family == VFF_GRID:
+        return vff_features_dense(mesh, x, l, s2, ref_quirks)
     if family == SVGP_GRID:
         return svgp_features_dense(mesh, x, l, s2)
     return b1_features_dense(mesh, x) if family == B1_ASVGP else b0_features_dense(mesh, x, l, s2)
@@ -229,7 +282,7 @@ def dense_Kuu_Kuf(family, meshes, X, l, s2, ref_quirks=True):
     D = len(meshes)
     Xc = X.reshape(X.shape[0], D)
     Ks = [kuu_factor(family, meshes[d], l[d], s2[d], ref_quirks) for d in range(D)]
-    Fs = [features_dense(family, meshes[d], Xc[:, d], l[d], s2[d]) for d in range(D)]
+    Fs = [features_dense(family, meshes[d], Xc[:, d], l[d], s2[d], ref_quirks) for d in range(D)]
     return kron_all(Ks).to(torch.float64), khatri_rao(Fs).to(torch.float64), Ks, Fs
 
 

@@ -218,6 +218,33 @@ def test_svgp_product_grid_family_under_emulation(emu, knots, N, dtype, tol):
     plan.close()
 
 
+@pytest.mark.parametrize("knots,N", [((9,), 300), ((7, 11), 300), ((71, 5), 250)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 1e-3)])
+def test_vff_family_under_emulation(emu, knots, N, dtype, tol):
+    """Variational Fourier features (kronecker_structure.py:347-514 Matern12VFFGP, fourier.py:58-88): cosines / sines on a domain
+    smaller than the data (so the exp(-r / l) branch outside [a, b) and its lengthscale gradient are exercised), Kuu_d =
+    diag(alpha) + beta beta^T through the dense Cholesky path; the whole step against the oracle (float64 semantics)."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=17 + D, family=O.VFF_GRID, x_lo=-0.2, x_hi=1.2)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq, yq = X.to(tdt), y.to(tdt)
+    Xq[::7, 0] = 0.0                                   # on the lower end of the domain (inside), and on the upper end (outside)
+    Xq[3::11, D - 1] = 1.0
+    elbo_ref, g_ref = oracle_value_and_grads(O.VFF_GRID, meshes, Xq.to(torch.float64), yq.to(torch.float64), l, s2, noise, m, Ls, scale=1.2)
+    plan = emul_lib.EmuPlan(lib, L, L.VFF_GRID, [t.numpy() for t in meshes], dtype)
+    assert plan.m_per_dim == list(knots)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                    xs, np.ascontiguousarray(yq.numpy()), 1.2)
+    check_against_oracle(plan, out, dtheta, dm, dL, elbo_ref, g_ref, N, tol)
+    phi = plan.features_dense(0, xs[0], theta)
+    ref = O.vff_features_dense(meshes[0], Xq[:, 0], l[0], s2[0], ref_quirks=False).numpy()
+    assert np.max(np.abs(phi - ref)) <= (1e-12 if dtype == np.float64 else 2e-5)
+    plan.close()
+
+
 @pytest.mark.parametrize("name", ["lin11_01", "lin129_01", "lin16_02", "lin21_m3_7", "padded21_pad2"])
 @pytest.mark.parametrize("tag,dtype", [("f64", np.float64), ("f32", np.float32)])
 def test_b1_stencil_kernel_bit_exact_vs_reference_golden(emu, golden_dir, name, tag, dtype):

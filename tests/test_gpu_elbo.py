@@ -687,3 +687,69 @@ def test_svgp_model_class_on_the_gpu(vg, dev):
     assert losses[-1] < losses[0]
     post = model.posterior(X[:64].to(dev))
     assert torch.isfinite(post.mean).all() and (post.variance > 0).all()
+
+
+@pytest.mark.parametrize("knots,N", [((9,), 600), ((7, 11), 700), ((71, 13), 1500)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 1e-3)])
+def test_elbo_and_grads_match_oracle_vff(vg, dev, knots, N, dtype, tol):
+    """Variational Fourier features (kronecker_structure.py:347-514 Matern12VFFGP, fourier.py:58-88) on domains smaller than
+    the data: cosine / sine features inside, exp(-r / l) outside, Kuu_d = diag(alpha) + beta beta^T; every gradient block."""
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=66 + D, family=O.VFF_GRID, x_lo=-0.2, x_hi=1.2)
+    Xq, yq = X.to(dtype), y.to(dtype)
+    scale = 1.3
+    elbo_ref, g_ref = oracle_value_and_grads(O.VFF_GRID, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = vg.GridPlan(vg.VFF_GRID, meshes, dtype, dev)
+    assert plan.m_per_dim == list(knots)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
+    out, dtheta, dm, dL = plan.step(theta, m.to(dev), Lcat, xs, yq.to(dev), ell_scale=scale)
+    assert plan.read_info() == 0
+    assert out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item())
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10
+    assert relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10
+    assert relerr(dm, g_ref[3]) < tol * 10
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n).cpu()
+        off += n * n
+        assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
+    with pytest.raises(RuntimeError):
+        vg.GridPlan(vg.VFF_GRID, [torch.linspace(0, 1, 8)], dtype, dev)          # 2 M + 1 knots
+
+
+def test_vff_model_class_on_the_gpu(vg, dev):
+    """kronecker_structure.Matern12VFFGP on the device: ELBO against the oracle, Adam improves the bound, posterior() finite."""
+    ks = importlib.import_module("variational-gridded-gaussian-processes_b200.models.sparse.kronecker_structure")
+    g = torch.Generator().manual_seed(4)
+    N = 2000
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(5 * X[:, 0]) + torch.cos(7 * X[:, 1]) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    model = ks.Matern12VFFGP(X, y, 6, (-0.125, 1.125), (0.125, 0.875)).to(torch.float64).to(dev)
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.1)
+        model.kernel_1.base_kernel.lengthscale = 0.3
+        model.likelihood.noise = 0.05
+    elbo = model._elbo()
+    l = torch.stack([model.kernel_1.base_kernel.lengthscale.detach().reshape(()), model.kernel_2.base_kernel.lengthscale.detach().reshape(())]).cpu()
+    s2 = torch.stack([model.kernel_1.outputscale.detach().reshape(()), model.kernel_2.outputscale.detach().reshape(())]).cpu()
+    meshes = [torch.linspace(-0.125, 1.125, 13), torch.linspace(0.125, 0.875, 13)]
+    ref = O.elbo_structured(O.VFF_GRID, meshes, X, y, l.to(torch.float64), s2.to(torch.float64),
+                            model.likelihood.noise.detach().reshape(()).cpu().to(torch.float64), model.variational_mean.detach().cpu(),
+                            [model.variational_chol_1.detach().cpu(), model.variational_chol_2.detach().cpu()], ref_quirks=False)
+    assert abs(elbo.item() - ref.item()) < 1e-8 * abs(ref.item())
+    opt = torch.optim.Adam(model.parameters(), lr=0.02)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = -model._elbo()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    post = model.posterior(X[:64].to(dev))
+    assert torch.isfinite(post.mean).all() and (post.variance > 0).all()

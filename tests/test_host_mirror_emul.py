@@ -352,6 +352,61 @@ def test_svgp_model_class_matches_reference_run(host, monkeypatch, golden_dir, p
     assert losses[-1] < losses[0]
 
 
+@pytest.mark.parametrize("pset", ["raw0", "raw1"])
+def test_vff_model_class_matches_reference_run(host, monkeypatch, golden_dir, pset):
+    """kronecker_structure.Matern12VFFGP (variational Fourier features, :347-514) as a drop-in class: its Kuu equals the
+    reference's own (float32-computed) `_Kuu()` output to float32 accuracy, the uncollapsed bound at the closed-form q(u) stays
+    below the reference's collapsed ELBO and close to it, ELBO and raw hyper-parameter gradients equal the oracle's (float64
+    semantics), posterior() equals the dense formulas, Adam improves the bound.  The second domain is smaller than the data."""
+    import os
+    _patched_models(host, monkeypatch)
+    ref = np.load(os.path.join(golden_dir, "reference_models.npz"))
+    X, y = torch.from_numpy(ref["nb5.X"]).to(torch.float64), torch.from_numpy(ref["nb5.y"]).to(torch.float64)
+    mod = importlib.import_module(PKG + ".models.sparse.kronecker_structure")
+    model = mod.Matern12VFFGP(X, y, 4, (-0.125, 1.125), (0.25, 0.75)).to(torch.float64)
+    assert model.m_per_dim == [9, 9] and model._packed is None
+    _set_raw(model, {"raw0": {}, "raw1": {"kernel_1.raw_outputscale": 0.3, "kernel_1.base_kernel.raw_lengthscale": -0.7,
+                                          "kernel_2.raw_outputscale": -0.2, "kernel_2.base_kernel.raw_lengthscale": 0.4,
+                                          "likelihood.noise_covar.raw_noise": -2.0}}[pset])
+    key = f"K_vff2d.{pset}"
+    assert relerr(model._Kuu(), torch.from_numpy(ref[key + ".Kuu"])) < 1e-6
+    model.set_optimal_q()
+    elbo, collapsed = model._elbo().item(), float(ref[key + ".elbo"])
+    assert elbo <= collapsed + 1e-6 * abs(collapsed)
+    assert collapsed - elbo < 0.2 * abs(collapsed)
+    with torch.no_grad():
+        model.variational_mean.add_(0.05 * torch.randn(model.M, generator=torch.Generator().manual_seed(1), dtype=torch.float64))
+    model.zero_grad()
+    e = model._elbo()
+    (-e).backward()
+    raw_l = torch.stack([model.kernel_1.base_kernel.raw_lengthscale.detach().reshape(()),
+                         model.kernel_2.base_kernel.raw_lengthscale.detach().reshape(())]).requires_grad_(True)
+    raw_s = torch.stack([model.kernel_1.raw_outputscale.detach(), model.kernel_2.raw_outputscale.detach()]).requires_grad_(True)
+    raw_n = model.likelihood.noise_covar.raw_noise.detach().reshape(()).requires_grad_(True)
+    l, s2, noise = O.constrain(raw_l, raw_s, raw_n)
+    meshes = [torch.linspace(-0.125, 1.125, 9), torch.linspace(0.25, 0.75, 9)]
+    oref = O.elbo_structured(O.VFF_GRID, meshes, X, y, l, s2, noise, model.variational_mean.detach(),
+                             [model.variational_chol_1.detach(), model.variational_chol_2.detach()], ref_quirks=False)
+    gl, gs, gn = torch.autograd.grad(-oref, [raw_l, raw_s, raw_n])
+    assert abs(e.item() - oref.item()) < 1e-8 * abs(oref.item())
+    assert abs(model.kernel_2.base_kernel.raw_lengthscale.grad.item() - gl[1].item()) < 1e-6 * abs(gl[1].item())
+    assert abs(model.kernel_1.raw_outputscale.grad.item() - gs[0].item()) < 1e-6 * abs(gs[0].item())
+    assert abs(model.likelihood.noise_covar.raw_noise.grad.item() - gn.item()) < 1e-6 * abs(gn.item())
+    xs = X[:40]
+    dense = model.posterior_dense(xs)
+    marg = model.posterior(xs)
+    assert relerr(dense.mean, marg.mean) < 1e-8 and relerr(dense.variance, marg.variance) < 1e-7
+    opt = torch.optim.Adam(model.parameters(), lr=0.02)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = -model._elbo()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+
+
 def test_gridded_part_dense_matrices_asvgp(host, monkeypatch):
     """GriddedMatern12ASVGP (2-D) and its 1-D twin: _Kvu / _Kvv / p_v_u / q_v against the reference's constructions restated
     with torch (gridded_kronecker_structure.py:831-947, gridded_univariate_structure.py:595-700)."""

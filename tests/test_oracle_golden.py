@@ -55,6 +55,8 @@ CASES_2D = {
     "K_b0gridded2d": (O.B0_GRIDDED, lambda: [O.make_mesh(0, 1, 9)] * 2),
     # kronecker_structure.Matern12SVGP (:287-338): the "meshes" are the columns of its inducing-point parameter Z
     "K_svgp2d": (O.SVGP_GRID, None),
+    # kronecker_structure.Matern12VFFGP (:347-514), 4 frequencies: a mesh of 9 knots spanning each domain
+    "K_vff2d": (O.VFF_GRID, lambda: [torch.linspace(-0.125, 1.125, 9), torch.linspace(0.25, 0.75, 9)]),
 }
 
 

@@ -15,6 +15,11 @@ def _data(N, D, seed=0, lo=0.0, hi=1.0):
     return X, y
 
 
+def _nk(family, n):
+    """knot count for a test mesh: a VFF mesh has 2 * nfrequencies + 1 knots"""
+    return n + 1 - n % 2 if family == O.VFF_GRID else n
+
+
 def _hyp(D, seed=1):
     g = torch.Generator().manual_seed(seed)
     rl = (torch.randn(D, generator=g, dtype=torch.float64) * 0.5).requires_grad_()
@@ -23,11 +28,11 @@ def _hyp(D, seed=1):
     return rl, rs, rn
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID, O.VFF_GRID])
 @pytest.mark.parametrize("D", [1, 2])
 def test_literal_equals_woodbury(family, D):
     X, y = _data(150, D)
-    meshes = [O.make_mesh(0, 1, 7 + d) for d in range(D)]
+    meshes = [O.make_mesh(0, 1, _nk(family, 7 + d)) for d in range(D)]
     rl, rs, rn = _hyp(D)
     l, s2, nz = O.constrain(rl, rs, rn)
     a = O.elbo_collapsed_literal(family, meshes, X, y, l, s2, nz, ref_quirks=False)
@@ -39,12 +44,12 @@ def test_literal_equals_woodbury(family, D):
         assert torch.allclose(u, v, rtol=1e-8, atol=1e-9)
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID, O.VFF_GRID])
 @pytest.mark.parametrize("D", [1, 2])
 def test_uncollapsed_at_optimum_equals_collapsed(family, D):
     """ELBO(m*, S*) == collapsed bound, and (envelope theorem) so are the hyper-parameter gradients."""
     X, y = _data(120, D)
-    meshes = [O.make_mesh(0, 1, 6 + d) for d in range(D)]
+    meshes = [O.make_mesh(0, 1, _nk(family, 6 + d)) for d in range(D)]
     rl, rs, rn = _hyp(D)
     l, s2, nz = O.constrain(rl, rs, rn)
     a = O.elbo_collapsed_literal(family, meshes, X, y, l, s2, nz, ref_quirks=False)
@@ -59,14 +64,14 @@ def test_uncollapsed_at_optimum_equals_collapsed(family, D):
         assert torch.allclose(u, v, rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID])
+@pytest.mark.parametrize("family", [O.B1_ASVGP, O.B0_GRIDDED, O.SVGP_GRID, O.VFF_GRID])
 @pytest.mark.parametrize("D,knots", [(1, [9]), (2, [9, 7]), (3, [5, 4, 6])])
 def test_structured_equals_dense_uncollapsed(family, D, knots):
     """G4: Kronecker-factored q(u) through mode products == dense M x M algebra (values and all gradients)."""
     X, y = _data(200, D, seed=3, lo=-0.05, hi=1.05)          # some observations outside the mesh
     if D == 3:
         y = y + torch.sin(3 * X[:, 2])
-    meshes = [O.make_mesh(0, 1, k) for k in knots]
+    meshes = [O.make_mesh(0, 1, _nk(family, k)) for k in knots]
     Ms = [O.n_inducing(family, mh) for mh in meshes]
     M = int(np.prod(Ms))
     rl, rs, rn = _hyp(D, seed=5)

@@ -16,3 +16,4 @@ from .models._gridded import GriddedVariationalGP  # noqa: F401
 B1_ASVGP = _lib.B1_ASVGP
 B0_GRIDDED = _lib.B0_GRIDDED
 SVGP_GRID = _lib.SVGP_GRID
+VFF_GRID = _lib.VFF_GRID

@@ -105,6 +105,18 @@ __device__ __forceinline__ double factor_entry(const GridDims& g, const double* 
     } else if (g.family == VGGP_SVGP_GRID) {
         // kernel_d(Z).evaluate(), kronecker_structure.py:321-322: ScaleKernel(MaternKernel(nu = 1/2)) at the inducing points
         return s2 * exp(-fabs((double)g.knots[d][i] - (double)g.knots[d][j]) / l);
+    } else if (g.family == VGGP_VFF_GRID) {
+        // DiagLinearOperator(alpha).add_low_rank(beta), kronecker_structure.py:403-462: alpha_i = (b - a) / 2 c_i / S(w_i) with
+        // 1 / S(w) = (1 / l + w^2 l) / (2 s2), c_0 = 2; beta = 1 / sqrt(s2) on the M + 1 cosine rows, 0 on the M sine rows
+        const int Mf = (n - 1) / 2;
+        double v = (i <= Mf && j <= Mf) ? 1.0 / s2 : 0.0;
+        if (i == j) {
+            const double a = (double)g.knots[d][0], b = (double)g.knots[d][n - 1];
+            const int kf = i <= Mf ? i : i - Mf;
+            const double w = 6.283185307179586476925286766559 * (double)kf / (b - a);
+            v += 0.5 * (b - a) * (i == 0 ? 2.0 : 1.0) * (1.0 / l + w * w * l) / (2.0 * s2);
+        }
+        return v;
     } else {
         double r, dr;
         b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
@@ -128,6 +140,18 @@ __device__ __forceinline__ void factor_entry_grad(const GridDims& g, const doubl
         const double a = fabs((double)g.knots[d][i] - (double)g.knots[d][j]), e = exp(-a / l);
         dKdl = s2 * e * a / (l * l);
         dKds2 = e;
+    } else if (g.family == VGGP_VFF_GRID) {
+        const int Mf = (n - 1) / 2;
+        dKdl = 0.0;
+        dKds2 = (i <= Mf && j <= Mf) ? -1.0 / (s2 * s2) : 0.0;
+        if (i == j) {
+            const double a = (double)g.knots[d][0], b = (double)g.knots[d][n - 1];
+            const int kf = i <= Mf ? i : i - Mf;
+            const double w = 6.283185307179586476925286766559 * (double)kf / (b - a);
+            const double c = 0.5 * (b - a) * (i == 0 ? 2.0 : 1.0);
+            dKdl = c * (-1.0 / (l * l) + w * w) / (2.0 * s2);
+            dKds2 -= c * (1.0 / l + w * w * l) / (2.0 * s2 * s2);
+        }
     } else {
         double r, dr;
         b0_row(i > j ? i - j : j - i, g.delta32[d], l, r, dr);
@@ -805,7 +829,8 @@ __global__ void __launch_bounds__(256) k_bwd_theta(const __grid_constant__ GridD
             if (g.family != VGGP_B1_ASVGP) {
                 // the features themselves depend on (l_d, s2_d): sums accumulated by the per-observation kernel
                 atomicAdd(dtheta + d, (ell_scale / noise) * gscal[3 + d]);
-                atomicAdd(dtheta + D + d, (ell_scale / noise) * gscal[5 + d] / theta[D + d]);
+                if (g.family != VGGP_VFF_GRID)      // Fourier features do not scale with s2_d (phi = s2 * ... in the other families)
+                    atomicAdd(dtheta + D + d, (ell_scale / noise) * gscal[5 + d] / theta[D + d]);
             }
             if (d == 0) {
                 const double tot = E + nobs * kff;

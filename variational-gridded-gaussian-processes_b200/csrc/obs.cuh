@@ -139,6 +139,24 @@ __global__ void __launch_bounds__(256) k_b0_dense(MeshView mv, const T* __restri
     phi[(i64)k * n + i] = b0_feature<T>(mv.t, k, idx, xv, (T)l, (T)s2);
 }
 
+// Dense (K, n) Fourier feature matrix (K = 2 M + 1 rows: cosines, then sines).  grid (ceil(n/256), K)
+template <typename T>
+__global__ void __launch_bounds__(256) k_vff_dense(MeshView mv, const T* __restrict__ x, i64 n, double l, T* __restrict__ phi) {
+    const int k = blockIdx.y, Mf = (mv.K - 1) / 2;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T xa = (T)mv.t[0], xb = (T)mv.t[mv.K - 1], xv = x[i];
+    T f = (T)0;
+    if (xv >= xa && xv < xb) {
+        const int kf = k <= Mf ? k : k - Mf;
+        const T arg = ((T)6.283185307179586476925286766559 * (T)kf / (xb - xa)) * (xv - xa);
+        f = k <= Mf ? cos(arg) : sin(arg);
+    } else if (k <= Mf) {
+        f = exp(-fmin(fabs(xv - xa), fabs(xv - xb)) / (T)l);
+    }
+    phi[(i64)k * n + i] = f;
+}
+
 // Dense (K, n) SVGP feature matrix: phi[k][i] = s2 exp(-|x_i - z_k| / l).  grid (ceil(n/256), K)
 template <typename T>
 __global__ void __launch_bounds__(256) k_svgp_dense(MeshView mv, const T* __restrict__ x, i64 n, double l, double s2,
@@ -717,7 +735,7 @@ struct B0Args {
     i64 n;
     MeshView mesh[D];
     int nd[D];               // M_d = K_d - 1 (B0 cells) or K_d (SVGP points)
-    int family;              // VGGP_B0_GRIDDED or VGGP_SVGP_GRID
+    int family;              // VGGP_B0_GRIDDED, VGGP_SVGP_GRID or VGGP_VFF_GRID
     const double* theta;     // l[D], s2[D], noise
     const T* alpha;          // (M_1, M_2) row-major, obs dtype
     const double* P[D];
@@ -757,7 +775,21 @@ __global__ void __launch_bounds__(256) k_obs_b0(const __grid_constant__ B0Args<T
             for (int e = tid; e < a.nd[d] * B0_TN; e += blockDim.x) {
                 const int k = e / B0_TN, t = e % B0_TN;
                 T f = (T)0, df = (T)0;
-                if (n0 + t < a.n && a.family == VGGP_SVGP_GRID) {
+                if (n0 + t < a.n && a.family == VGGP_VFF_GRID) {
+                    // FourierBasisMatern12(x), fourier.py:16-19, 30-48, 58-88: cosines then sines on [a, b), exp(-r / l) outside
+                    const int Kk = a.mesh[d].K, Mf = (Kk - 1) / 2;
+                    const T xa = (T)a.mesh[d].t[0], xb = (T)a.mesh[d].t[Kk - 1];
+                    const T xv = a.x[d][n0 + t];
+                    if (xv >= xa && xv < xb) {
+                        const int kf = k <= Mf ? k : k - Mf;
+                        const T arg = ((T)6.283185307179586476925286766559 * (T)kf / (xb - xa)) * (xv - xa);
+                        f = k <= Mf ? cos(arg) : sin(arg);
+                    } else if (k <= Mf) {
+                        const T r = fmin(fabs(xv - xa), fabs(xv - xb));
+                        f = exp(-r / l);
+                        df = f * r / (l * l);
+                    }
+                } else if (n0 + t < a.n && a.family == VGGP_SVGP_GRID) {
                     // k(z_k, x) of a ScaleKernel(MaternKernel(1/2)) and its lengthscale derivative (kronecker_structure.py:337-338)
                     const T A1 = fabs(a.x[d][n0 + t] - (T)a.mesh[d].t[k]);
                     f = s2 * exp(-A1 / l);

@@ -1642,8 +1642,13 @@ int vggp_set_b1_structured(int on) {
 int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, const float* const* knots_host,
                      int obs_dtype, int device) {
     if (!out || !n_knots || !knots_host) return fail(VGGP_E_ARG, "null argument");
-    if (family != VGGP_B1_ASVGP && family != VGGP_B0_GRIDDED && family != VGGP_SVGP_GRID) return fail(VGGP_E_FAMILY, "unknown feature family");
-    if (family == VGGP_SVGP_GRID && D > 2) return fail(VGGP_E_UNSUPPORTED, "the SVGP product-grid family is built for D <= 2, as in the reference");
+    if (family != VGGP_B1_ASVGP && family != VGGP_B0_GRIDDED && family != VGGP_SVGP_GRID && family != VGGP_VFF_GRID)
+        return fail(VGGP_E_FAMILY, "unknown feature family");
+    if ((family == VGGP_SVGP_GRID || family == VGGP_VFF_GRID) && D > 2)
+        return fail(VGGP_E_UNSUPPORTED, "the SVGP and VFF families are built for D <= 2, as in the reference");
+    if (family == VGGP_VFF_GRID)
+        for (int d = 0; d < D; ++d)
+            if (n_knots && n_knots[d] % 2 == 0) return fail(VGGP_E_ARG, "a VFF mesh has 2 * nfrequencies + 1 knots");
     if (D < 1 || D > VGGP_MAX_D) return fail(VGGP_E_DIM, "D must be 1..3");
     if (obs_dtype != VGGP_F32 && obs_dtype != VGGP_F64) return fail(VGGP_E_DTYPE, "obs_dtype must be VGGP_F32 or VGGP_F64");
     for (int d = 0; d < D; ++d) {
@@ -1995,7 +2000,7 @@ int vggp_obs_bin_prepare(vggp_plan* p, const void* const* x, int64_t n, int run_
     DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !desc || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (p->family == VGGP_B0_GRIDDED && p->D > 2) return fail(VGGP_E_UNSUPPORTED, "the B0 (cell-integrated) family is built for D <= 2, as in the reference");
-    if (p->family == VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP family takes plain observation arrays (vggp_obs_fwd_bwd)");
+    if (p->family >= VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP and VFF families take plain observation arrays (vggp_obs_fwd_bwd)");
     if (run_cap == 0) {
         // automatic: about two tasks (of 32 runs) per resident warp, so that thin shards and cell-range shards (few, full cells)
         // still spread over the whole GPU; 256 (the value the 1-GPU measurements settled on) from 2^25.8 observations up
@@ -2043,7 +2048,7 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* p, const vggp_binned_desc* desc, const vo
     VGGP_CUDA(cudaMemsetAsync(gbuf, 0, (size_t)total, st));
     if (desc->n == 0) return 0;
     if (!binned) return fail(VGGP_E_ARG, "null binned buffer");
-    if (p->family == VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP family takes plain observation arrays (vggp_obs_fwd_bwd)");
+    if (p->family >= VGGP_SVGP_GRID) return fail(VGGP_E_UNSUPPORTED, "the SVGP and VFF families take plain observation arrays (vggp_obs_fwd_bwd)");
     if (p->family == VGGP_B0_GRIDDED) return obs_b0s_dispatch(p, desc, binned, gbuf, st);     // scan form (b0scan.cuh)
     return obs_binned_dispatch(p, desc, binned, gbuf, st);
 }
@@ -2348,7 +2353,10 @@ int vggp_features_dense(const vggp_plan* p, int dim, const void* x, int64_t n, c
         VGGP_CUDA(cudaMemcpyAsync(th, theta, sizeof(double) * (2 * p->D + 1), cudaMemcpyDeviceToHost, st));
         VGGP_CUDA(cudaStreamSynchronize(st));
         dim3 grid(ceil_div(n, 256), p->n[dim]);
-        if (p->family == VGGP_SVGP_GRID) {
+        if (p->family == VGGP_VFF_GRID) {
+            if (p->obs_dtype == VGGP_F32) k_vff_dense<float><<<grid, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, th[dim], (float*)phi);
+            else k_vff_dense<double><<<grid, 256, 0, st>>>(p->mesh[dim], (const double*)x, n, th[dim], (double*)phi);
+        } else if (p->family == VGGP_SVGP_GRID) {
             if (p->obs_dtype == VGGP_F32)
                 k_svgp_dense<float><<<grid, 256, 0, st>>>(p->mesh[dim], (const float*)x, n, th[dim], th[p->D + dim], (float*)phi);
             else
@@ -2369,8 +2377,8 @@ int vggp_predict(vggp_plan* p, const void* const* x, int64_t n, void* mean, void
     if (!x || !mean || !var) return fail(VGGP_E_ARG, "null argument");
     for (int d = 0; d < p->D; ++d)
         if (!x[d]) return fail(VGGP_E_ARG, "null test-point pointer");
-    if (p->family == VGGP_SVGP_GRID)
-        return fail(VGGP_E_UNSUPPORTED, "SVGP family: predictions are assembled from vggp_features_dense by the host mirror");
+    if (p->family >= VGGP_SVGP_GRID)
+        return fail(VGGP_E_UNSUPPORTED, "SVGP / VFF families: predictions are assembled from vggp_features_dense by the host mirror");
     if (p->family != VGGP_B1_ASVGP)      // B0 family: scan form, O(1) per point (b0scan.cuh)
         return predict_b0s_dispatch(p, x, n, mean, var, (cudaStream_t)stream);
     return predict_dispatch(p, x, n, mean, var, (cudaStream_t)stream);

@@ -115,7 +115,7 @@ class GriddedVariationalGP(nn.Module):
             # VGGP_OBS_LAYOUT=packed selects the round-1 layouts (B1: cell-sorted packed runs, B0: plain arrays through the
             # dense-feature kernel), kept as cross-checks.
             layout = os.environ.get("VGGP_OBS_LAYOUT", "binned")
-            if self.family == _lib.SVGP_GRID:
+            if self.family in (_lib.SVGP_GRID, _lib.VFF_GRID):
                 self._packed = None                 # dense-feature kernel: plain arrays
             elif layout == "binned" and not (self.family != _lib.B1_ASVGP and self.D > 2):
                 self._packed = self._plan.bin(xs, y)
