@@ -6,6 +6,7 @@ These paths were written at the end of round 1 against the SIMT emulator only; t
 (tools/gpu_check_binned.sh, profiles/r2_call1_binned_summary.txt) ran them on a B200 and they are part of the default
 GPU suite since.  VGGP_TEST_STREAMS=ldg|tma restricts the binned tests to one streaming variant.
 """
+import importlib
 import os
 
 import pytest

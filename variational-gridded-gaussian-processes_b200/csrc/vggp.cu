@@ -50,8 +50,10 @@ int raise_dyn_smem(F fn, size_t bytes) {
             e.bytes = (int)bytes;
             return 0;
         }
-    if (bytes > 48 * 1024) VGGP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    g_smem_hwm.push_back({(const void*)fn, dev, bytes > 48 * 1024 ? (int)bytes : 48 * 1024});
+    // first use: opt in whatever the size -- static shared memory counts against the 48 KB default too, so a kernel asking for
+    // exactly 48 KB of dynamic memory already needs it
+    VGGP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    g_smem_hwm.push_back({(const void*)fn, dev, (int)bytes});
     return 0;
 }
 
