@@ -714,10 +714,17 @@ __global__ void __launch_bounds__(B0S_THREADS) k_obs_b0s(const __grid_constant__
         s2[d] = (T)a.tab.theta[D + d];
     }
     const i64 EE = D == 1 ? (i64)a.tab.E[0] : (i64)a.tab.E[0] * a.tab.E[D - 1];
+    bool first = true;                  // first task = the warp's global index, later ones from the counter (see bin_next_task)
+    const unsigned int nwarps_all = gridDim.x * (blockDim.x >> 5);
     for (;;) {
         unsigned int task = 0;
-        if (lane == 0) task = atomicAdd(a.counter, 1u);
-        task = __shfl_sync(0xffffffffu, task, 0);
+        if (first) {
+            task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            first = false;
+        } else {
+            if (lane == 0) task = atomicAdd(a.counter, 1u) + nwarps_all;
+            task = __shfl_sync(0xffffffffu, task, 0);
+        }
         if (task >= (unsigned int)a.n_tasks) break;
         const i64 slot = (i64)task * 32 + lane;
         const uint32_t cell = __ldg(reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell) + slot);

@@ -606,10 +606,17 @@ __global__ void __launch_bounds__(OBS_THREADS, (sizeof(T) == 4 ? (D == 3 ? 4 : 5
     // persistent warps: every warp takes the next chunk (32 lanes x R observations) from a global counter, so the
     // data-dependent cost of the cell switches balances over the SMs
     const int groups = a.geo.R >> 2;
+    bool first = true;                  // first chunk = the warp's global index, later ones from the counter (see bin_next_task)
+    const unsigned int nwarps_all = gridDim.x * (blockDim.x >> 5);
     for (;;) {
         unsigned int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(a.counter, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (first) {
+            chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            first = false;
+        } else {
+            if (lane == 0) chunk = atomicAdd(a.counter, 1u) + nwarps_all;
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        }
         if ((i64)chunk >= a.geo.nwarps) break;
         const i64 base = (i64)chunk * 32 * a.geo.R + lane * 4;
         T xa[D][4], ya[4], xb[D][4], yb[4];

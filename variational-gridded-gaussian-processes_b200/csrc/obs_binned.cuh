@@ -354,11 +354,20 @@ struct BinTask {
     bool valid;
 };
 
+// `first`: the warp's first task is its own global index -- no atomic.  (All resident warps asking one counter for their first
+// task at kernel start serialise on a single L2 address: ~3500 same-address atomics, the ~12 us that separated the kernel from
+// the roofline at every problem size.)  Later tasks come from the counter, offset by the number of warps of the launch.
 template <typename T, int D>
-__device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lane, BinLane<T, D>& s, BinTask<T, D>& t) {
+__device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lane, BinLane<T, D>& s, BinTask<T, D>& t, bool& first) {
+    const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
     unsigned int task = 0;
-    if (lane == 0) task = atomicAdd(a.counter, 1u);
-    task = __shfl_sync(0xffffffffu, task, 0);
+    if (first) {
+        task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        first = false;
+    } else {
+        if (lane == 0) task = atomicAdd(a.counter, 1u) + nwarps;
+        task = __shfl_sync(0xffffffffu, task, 0);
+    }
     if (task >= (unsigned int)a.n_tasks) return false;
     const i64 slot = (i64)task * 32 + lane;
     const uint32_t cell = __ldg(reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell) + slot);
@@ -398,7 +407,8 @@ k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
     BinTask<T, D> t;
     T* const gband = a.gband + (i64)(blockIdx.x % (unsigned)a.n_rep) * a.band_rep_stride;
     // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
-    while (bin_next_task<T, D>(a, lane, s, t)) {
+    bool first = true;
+    while (bin_next_task<T, D>(a, lane, s, t, first)) {
         // the loads of the next group of 4 observations are in flight while the current one is processed (no buffer
         // rotation: the loop body handles two groups)
         T xa[D][4], ya[4], xb[D][4], yb[4];
@@ -444,7 +454,8 @@ k_obs_b1_binned_tma(const __grid_constant__ BinnedArgs<T, D> a) {
     BinTask<T, D> t;
     T* const gband = a.gband + (i64)(blockIdx.x % (unsigned)a.n_rep) * a.band_rep_stride;
     unsigned int k0 = 0;                 // stages this warp has consumed so far: slot = k % STAGES, phase = (k / STAGES) & 1
-    while (bin_next_task<T, D>(a, lane, s, t)) {
+    bool first = true;
+    while (bin_next_task<T, D>(a, lane, s, t, first)) {
         const T* src = t.base - lane * 4;                    // the task's first group
         const int nst = (t.groups + BIN_GPS - 1) / BIN_GPS;  // stages of this task (the last one may be partial)
         if (lane == 0) {
