@@ -165,7 +165,7 @@ int vggp_obs_fwd_bwd(vggp_plan* plan, const void* const* x, const void* y, int64
  * DESIGN.md section 4): cells are extended by one virtual cell on each side (observations outside the mesh do
  * contribute in this family, n_inside == n), the per-observation kernel does O(1) work against per-cell tables built by
  * first-order recurrences on the grid side, and an adjoint stage writes the same gbuf blocks vggp_obs_fwd_bwd writes for this
- * family.  The first vggp_obs_fwd_bwd_binned on a B0 plan allocates the tables inside the plan.
+ * family.  The tables live in the plan (allocated by vggp_plan_create).
  * Status: the default observation layout of both families since round 2 (GPU-verified against the oracle and against the
  * packed layout).  run_cap: longest run of one cell; 0 = automatic (about two warp tasks per resident
  * warp: 256 from ~2^25.8 observations per shard up, smaller for thin or cell-range shards, never below 32).
@@ -279,7 +279,7 @@ int vggp_features_dense(const vggp_plan* plan, int dim, const void* x, int64_t n
  * B0 family (D <= 2): the cell-integrated features are non-zero everywhere; they are evaluated in their scan form
  *   (three local features per dimension against per-cell tables built by first-order recurrences on the grid side,
  *   csrc/b0scan.cuh),
- *   O(1) work per point.  The first call allocates the tables inside the plan (GPU-verified in round 2).
+ *   O(1) work per point.  The tables are part of the plan (GPU-verified in round 2).
  */
 int vggp_predict(vggp_plan* plan, const void* const* x, int64_t n, void* mean, void* var, void* stream);
 

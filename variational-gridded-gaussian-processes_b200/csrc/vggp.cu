@@ -1801,6 +1801,9 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
         p->sm_count = prop.multiProcessorCount;
         p->obs_blocks_per_sm = 1;
         if (family == VGGP_B1_ASVGP) TRY(obs_prepare_dispatch(p));
+        // the scan form of the cell-integrated family (default for binned observations and for point prediction): its tables
+        // (~75 MB at 512 x 512) belong to the plan's one allocation phase, not to the first stream-ordered call that needs them
+        if (family == VGGP_B0_GRIDDED && D <= 2) TRY(b0scan_alloc(p));
     }
     if (!rc) rc = raise_dyn_smem(k_b1_factor, 7 * (size_t)p->nmax * sizeof(double));
     if (!rc) rc = raise_dyn_smem(k_ss_apply, 5 * (size_t)p->nmax * sizeof(double));
