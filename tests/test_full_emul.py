@@ -577,3 +577,23 @@ def test_track_generator_under_emulation(emu, D, dtype):
     for d in range(D):
         assert np.array_equal(xs_s[d], xs[d][1234:4321])
     assert np.array_equal(y_s, y[1234:4321])
+
+
+def test_automatic_run_cap_under_emulation(emu):
+    """vggp_obs_bin_prepare with run_cap = 0 picks the cap from the shard size (never below 32, 256 for large shards); the
+    step over that layout equals the step over an explicit cap."""
+    lib, L = emu
+    knots, N = (9, 7), 4000
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=2)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    mm, Lcat = m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy()
+    xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
+    yy = np.ascontiguousarray(y.numpy())
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float64)
+    auto = plan.bin(xs, yy, run_cap=0)
+    assert auto[2].run_cap == 32
+    ref = plan.step(theta, mm, Lcat, plan.bin(xs, yy, run_cap=32), None, 1.0)
+    got = plan.step(theta, mm, Lcat, auto, None, 1.0)
+    for a, b in zip(got, ref):
+        assert relerr(torch.from_numpy(np.asarray(a, dtype=np.float64)), torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-12
+    plan.close()

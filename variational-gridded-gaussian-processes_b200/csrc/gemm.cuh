@@ -306,17 +306,26 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         cp_async_commit();
         const double* As = sm + (it % GF_NSTAGE) * GF_STAGE;
         const double* Bs = As + 1280;
+        // fragments of k-step ks + 1 are loaded before the DMMAs of k-step ks are issued (register double buffer): the
+        // shared-memory latency sits under the tensor instructions instead of in front of them
+        double a[2][4], bb[2][GEMM_NI];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[0][mi] = As[aoff + mi * 8 * sAm];
+#pragma unroll
+        for (int ni = 0; ni < GEMM_NI; ++ni) bb[0][ni] = Bs[boff + ni * 8 * sBn];
 #pragma unroll
         for (int ks = 0; ks < GBK / 4; ++ks) {
-            double a[4], bb[GEMM_NI];
+            const int cur = ks & 1, nxt = cur ^ 1;
+            if (ks + 1 < GBK / 4) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = As[aoff + mi * 8 * sAm + ks * 4 * sAk];
+                for (int mi = 0; mi < 4; ++mi) a[nxt][mi] = As[aoff + mi * 8 * sAm + (ks + 1) * 4 * sAk];
 #pragma unroll
-            for (int ni = 0; ni < GEMM_NI; ++ni) bb[ni] = Bs[boff + ks * 4 * sBk + ni * 8 * sBn];
+                for (int ni = 0; ni < GEMM_NI; ++ni) bb[nxt][ni] = Bs[boff + (ks + 1) * 4 * sBk + ni * 8 * sBn];
+            }
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < GEMM_NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                for (int ni = 0; ni < GEMM_NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], bb[cur][ni]);
         }
     }
     cp_async_wait<0>();
