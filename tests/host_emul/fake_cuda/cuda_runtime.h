@@ -147,6 +147,7 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }

@@ -187,7 +187,7 @@ __global__ void k_build_factors(const __grid_constant__ GridDims g, const double
 // the unfactored block (nothing orders CTAs of one launch; sequential execution of the blocks, as under the test
 // emulator, reads a half-factored block): unless it is the only CTA of its dimension it parks the factor in
 // g.cdiag[d], and CTA 0 of the next panel launch moves it into place (nothing in between reads that block).
-// grid (row chunks, D), 256 threads, dynamic smem (2 * NB * CHOL_PITCH + NB) doubles.
+// grid (row chunks, D), 256 threads, dynamic smem (2 * NB * CHOL_PITCH + 2 * NB) doubles.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CHOL_PITCH = NB + 4;      // 4 lanes per row read s[r][q], s[r][q + 4], ...: pitch = 4 (mod 16) doubles keeps them on distinct banks
 __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ GridDims g, int j0) {
@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ Grid
     double (*s)[CHOL_PITCH] = reinterpret_cast<double (*)[CHOL_PITCH]>(sm);
     double (*a)[CHOL_PITCH] = reinterpret_cast<double (*)[CHOL_PITCH]>(sm + NB * CHOL_PITCH);
     double* dg = sm + 2 * NB * CHOL_PITCH;    // the diagonal of the factor: kept apart until the block is done (see below)
+    double* idg = dg + NB;                    // and its reciprocals, for the panel rows
     const int d = blockIdx.y;
     const int n = g.n[d];
     if (j0 >= n) return;
@@ -236,11 +237,16 @@ __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ Grid
         pp += __shfl_xor_sync(0xffffffffu, pp, 2);
         if (r >= c && r < w && q == 0) {
             const double piv = s[c][c] - pp;
+            // one reciprocal square root per row instead of a square root and a division (both software sequences in float64);
+            // a Newton step makes it as accurate as 1 / sqrt computed separately
+            double rs = rsqrt(piv);
+            rs = fma(rs * 0.5, fma(-piv * rs, rs, 1.0), rs);
             if (r == c) {
                 if (!(piv > 0.0)) atomicMax(g.info, d + 1);
-                dg[c] = sqrt(piv);
+                dg[c] = piv * rs;
+                idg[c] = rs;
             } else {
-                s[r][c] = (s[r][c] - part) / sqrt(piv);
+                s[r][c] = (s[r][c] - part) * rs;
             }
         }
         __syncthreads();
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(256) k_chol_panel(const __grid_constant__ Grid
             for (int k = q; k < c; k += 4) part = fma(a[r][k], s[c][k], part);
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
-        if (r < rows && q == 0) a[r][c] = (a[r][c] - part) / s[c][c];
+        if (r < rows && q == 0) a[r][c] = (a[r][c] - part) * idg[c];
         __syncwarp();
     }
     __syncthreads();

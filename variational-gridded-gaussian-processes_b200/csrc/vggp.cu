@@ -1808,7 +1808,7 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots, con
     if (!rc) rc = raise_dyn_smem(k_b1_factor, 7 * (size_t)p->nmax * sizeof(double));
     if (!rc) rc = raise_dyn_smem(k_ss_apply, 5 * (size_t)p->nmax * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute(k_b1_factor / k_ss_apply) failed"); }
-    rc = raise_dyn_smem(k_chol_panel, (2 * NB * CHOL_PITCH + NB) * sizeof(double));
+    rc = raise_dyn_smem(k_chol_panel, (2 * NB * CHOL_PITCH + 2 * NB) * sizeof(double));
     if (!rc) rc = raise_dyn_smem(k_triinv_leaf, 2 * NB * (NB + 1) * sizeof(double));
     if (rc) { vggp_plan_destroy(p); return fail(rc, "cudaFuncSetAttribute failed (is this an sm_100a device?)"); }
 #undef TRY
@@ -1879,7 +1879,7 @@ int vggp_grid_forward(vggp_plan* p, const double* theta, const double* m, const 
             VGGP_LAUNCH_CHECK();
         }
     } else {
-        const size_t csm = 2 * NB * (NB + 1) * sizeof(double), cpsm = (2 * NB * CHOL_PITCH + NB) * sizeof(double);
+        const size_t csm = 2 * NB * (NB + 1) * sizeof(double), cpsm = (2 * NB * CHOL_PITCH + 2 * NB) * sizeof(double);
         for (int j = 0; j < p->n_panels; ++j) {
             const int j0 = j * NB;
             dim3 grid(ceil_div(p->nmax - j0, NB), D);
