@@ -203,6 +203,13 @@ inline size_t b0s_seg_smem_bytes(int M, bool tan) {
     return sizeof(double) * ((size_t)3 * (M + S + 1) + 2 * (size_t)S + 2 * (size_t)B0S_SEG_THREADS);
 }
 
+// Several independent transforms in one launch (blockIdx.y selects the entry): the 22 sweeps of a step are 128-CTA kernels
+// of ~20 us each, too small to fill the GPU one at a time.
+constexpr int B0S_MAX_BATCH = 6;
+struct B0sSegGeo { int S, F, f_fast, blocks; };
+struct B0sScanBatch { B0sScanArgs a[B0S_MAX_BATCH]; B0sSegGeo g[B0S_MAX_BATCH]; };
+struct B0sAdjBatch { B0sAdjArgs a[B0S_MAX_BATCH]; B0sSegGeo g[B0S_MAX_BATCH]; };
+
 template <bool TAN, int dir>
 __device__ __forceinline__ void b0s_seg_sweep(const B0sScanArgs& a, const double (&vv)[B0S_SEG], const double* ceps, const double* cgam,
                                           const double* cdeps, const double* cA, const double* cdA, double* maps, int S, int fl,
@@ -259,7 +266,10 @@ __device__ __forceinline__ void b0s_seg_sweep(const B0sScanArgs& a, const double
 }
 
 template <bool TAN>
-__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_seg(const __grid_constant__ B0sScanArgs a, int S, int F, int f_fast) {
+__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_seg(const __grid_constant__ B0sScanBatch bt) {
+    const B0sScanArgs& a = bt.a[blockIdx.y];
+    const int S = bt.g[blockIdx.y].S, F = bt.g[blockIdx.y].F, f_fast = bt.g[blockIdx.y].f_fast;
+    if ((int)blockIdx.x >= bt.g[blockIdx.y].blocks) return;
     extern __shared__ double sm[];
     const int M = a.M, P = M + S + 1;
     double* ceps = sm;
@@ -344,7 +354,10 @@ __device__ __forceinline__ void b0s_seg_adj_sweep(const B0sAdjArgs& a, double (&
 // Segmented adjoint sweeps (same decomposition): sweep 1 descending, c <- eps_i c + gL[i + 1] from c = gL[M + 1],
 // dv[i] = gam_i c + gC[i + 1]; sweep 2 ascending, c <- eps_i c + gR[i + 1] from c = gR[0], dv[i] += gam_i c
 // (c = the state BEFORE the step in both).  dv stays in registers between the sweeps.
-__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_adj_seg(const __grid_constant__ B0sAdjArgs a, int S, int F, int f_fast) {
+__global__ void __launch_bounds__(B0S_SEG_THREADS) k_b0s_scan_adj_seg(const __grid_constant__ B0sAdjBatch bt) {
+    const B0sAdjArgs& a = bt.a[blockIdx.y];
+    const int S = bt.g[blockIdx.y].S, F = bt.g[blockIdx.y].F, f_fast = bt.g[blockIdx.y].f_fast;
+    if ((int)blockIdx.x >= bt.g[blockIdx.y].blocks) return;
     extern __shared__ double sm[];
     const int M = a.M, P = M + S + 1;
     double* ceps = sm;
@@ -701,7 +714,7 @@ struct B0sObsArgs {
 constexpr int B0S_THREADS = 128;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(B0S_THREADS) k_obs_b0s(const __grid_constant__ B0sObsArgs<T, D> a) {
+__global__ void __launch_bounds__(B0S_THREADS, (sizeof(T) == 4 ? 4 : 2)) k_obs_b0s(const __grid_constant__ B0sObsArgs<T, D> a) {
     __shared__ double red[32];
     constexpr int NT = D == 1 ? 3 : 9;
     const int lane = threadIdx.x & 31;
@@ -978,6 +991,18 @@ __global__ void __launch_bounds__(256) k_b0s_dot1(const double* __restrict__ x, 
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) acc = fma(x[i], y[i], acc);
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// several dot products in one launch: out[e] += sum_i x_e[i] y_e[i], blockIdx.y = e
+struct B0sDotBatch { const double* x[B0S_MAX_BATCH]; const double* y[B0S_MAX_BATCH]; double* out[B0S_MAX_BATCH]; i64 n; };
+__global__ void __launch_bounds__(256) k_b0s_dot_batch(const __grid_constant__ B0sDotBatch b) {
+    __shared__ double red[32];
+    const double* __restrict__ x = b.x[blockIdx.y];
+    const double* __restrict__ y = b.y[blockIdx.y];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (i64)gridDim.x * blockDim.x) acc = fma(x[i], y[i], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(b.out[blockIdx.y], acc);
 }
 
 }  // namespace vggp

@@ -116,8 +116,9 @@ struct vggp_plan {
     double* b0s_GTd = nullptr;             // GT in float64
     double* b0s_H[3] = {};                 // M1 x E2
     double* b0s_dA = nullptr;              // M1 x M2
-    double* b0s_S[3] = {};                 // (K+1) x (K-1), largest dimension
-    double* b0s_bM = nullptr;              // (K-1) x (K-1), largest dimension
+    double* b0s_Sx[4][3] = {};             // (K+1) x (K-1), largest dimension: one set per (dimension, matrix) pair
+    double* b0s_bMx[4] = {};               // (K-1) x (K-1), largest dimension, likewise
+    double* b0s_tan[6][4] = {};            // D = 2: scratch sets of the six tangent sweeps, E1 x E2 each (set 0 = b0s_TT)
     double* b0s_Gam[2] = {};               // (K+1) x (K-1), largest dimension
     int bin_blocks_per_sm[2] = {0, 0};     // resident CTAs of k_obs_b1_binned / k_obs_b1_binned_tma (queried at first use)
     // optional device timing of the per-observation kernel (vggp_k1_timing)
@@ -1282,15 +1283,21 @@ int b0scan_alloc(vggp_plan* p) {
     if ((rc = dev_alloc(p, &raw, p->b0s_raw_bytes))) return rc;
     p->b0s_raw = raw;
     if ((rc = dev_alloc(p, &p->b0s_GTd, nt * EE))) return rc;
-    for (int k = 0; k < 3; ++k)
-        if ((rc = dev_alloc(p, &p->b0s_S[k], emmax))) return rc;
+    for (int pr = 0; pr < 2 * p->D; ++pr) {
+        for (int k = 0; k < 3; ++k)
+            if ((rc = dev_alloc(p, &p->b0s_Sx[pr][k], emmax))) return rc;
+        if ((rc = dev_alloc(p, &p->b0s_bMx[pr], mmmax))) return rc;
+    }
     for (int k = 0; k < 2; ++k)
         if ((rc = dev_alloc(p, &p->b0s_Gam[k], emmax))) return rc;
-    if ((rc = dev_alloc(p, &p->b0s_bM, mmmax))) return rc;
     if (p->D == 2) {
         const i64 E2 = p->K[1] + 1, M2 = p->K[1] - 1;
         for (int k = 0; k < 3; ++k)
             if ((rc = dev_alloc(p, &p->b0s_H[k], M1 * E2))) return rc;
+        for (int k = 0; k < 4; ++k) p->b0s_tan[0][k] = p->b0s_TT[k];
+        for (int set = 1; set < 6; ++set)
+            for (int k = 0; k < 4; ++k)
+                if ((rc = dev_alloc(p, &p->b0s_tan[set][k], E1 * E2))) return rc;
         if ((rc = dev_alloc(p, &p->b0s_dA, M1 * M2))) return rc;
     }
     p->b0s_ready = true;
@@ -1314,35 +1321,111 @@ inline B0sSegGeom b0s_seg_geom(int M, i64 n_fibres, i64 n_lo, i64 lo_stride, boo
     return g;
 }
 
-int b0s_scan_launch(const B0sScanArgs& a, cudaStream_t st) {
-    if (a.n_fibres <= 0 || a.M <= 0) return 0;
-    const bool tan = a.tanL != nullptr;
-    if (!g_b0s_seg || (a.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {
-        k_b0s_scan<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
-        VGGP_LAUNCH_CHECK();
+// Independent sweeps are queued and launched together (blockIdx.y = entry, up to B0S_MAX_BATCH per launch): forward / tangent
+// transforms (k_b0s_scan_seg) and adjoint transforms (k_b0s_scan_adj_seg).  flush() is called wherever the next step reads
+// what the queued sweeps write.
+struct B0sBatcher {
+    cudaStream_t st;
+    std::vector<B0sScanArgs> scans;
+    std::vector<B0sAdjArgs> adjs;
+    explicit B0sBatcher(cudaStream_t s) : st(s) {}
+
+    int flush_scans() {
+        size_t i = 0;
+        while (i < scans.size()) {
+            const B0sScanArgs& a0 = scans[i];
+            const bool tan = a0.tanL != nullptr;
+            if (!g_b0s_seg || (a0.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {     // one-thread-per-fibre kernel, one at a time
+                if (a0.n_fibres > 0 && a0.M > 0) {
+                    k_b0s_scan<<<ceil_div(a0.n_fibres, 128), 128, 0, st>>>(a0);
+                    VGGP_LAUNCH_CHECK();
+                }
+                ++i;
+                continue;
+            }
+            B0sScanBatch bt;
+            memset(&bt, 0, sizeof(bt));
+            int n = 0;
+            unsigned gx = 1;
+            size_t smem = 0;
+            while (i < scans.size() && n < B0S_MAX_BATCH && (scans[i].tanL != nullptr) == tan
+                   && (scans[i].M + B0S_SEG - 1) / B0S_SEG <= B0S_SEG_THREADS) {
+                const B0sScanArgs& a = scans[i];
+                ++i;
+                if (a.n_fibres <= 0 || a.M <= 0) continue;
+                const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.s_lo, tan);
+                bt.a[n] = a;
+                bt.g[n].S = g.S; bt.g[n].F = g.F; bt.g[n].f_fast = g.f_fast; bt.g[n].blocks = (int)g.blocks;
+                gx = std::max(gx, g.blocks);
+                smem = std::max(smem, g.smem);
+                ++n;
+            }
+            if (n == 0) continue;
+            if (tan) {
+                if (int rc = raise_dyn_smem(k_b0s_scan_seg<true>, smem)) return rc;
+                k_b0s_scan_seg<true><<<dim3(gx, n), B0S_SEG_THREADS, smem, st>>>(bt);
+            } else {
+                if (int rc = raise_dyn_smem(k_b0s_scan_seg<false>, smem)) return rc;
+                k_b0s_scan_seg<false><<<dim3(gx, n), B0S_SEG_THREADS, smem, st>>>(bt);
+            }
+            VGGP_LAUNCH_CHECK();
+        }
+        scans.clear();
         return 0;
     }
-    const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.s_lo, tan);
-    if (tan) {
-        if (int rc = raise_dyn_smem(k_b0s_scan_seg<true>, g.smem)) return rc;
-        k_b0s_scan_seg<true><<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
-    } else {
-        if (int rc = raise_dyn_smem(k_b0s_scan_seg<false>, g.smem)) return rc;
-        k_b0s_scan_seg<false><<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
+
+    int flush_adjs() {
+        size_t i = 0;
+        while (i < adjs.size()) {
+            const B0sAdjArgs& a0 = adjs[i];
+            if (!g_b0s_seg || (a0.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {
+                if (a0.n_fibres > 0 && a0.M > 0) {
+                    k_b0s_scan_adj<<<ceil_div(a0.n_fibres, 128), 128, 0, st>>>(a0);
+                    VGGP_LAUNCH_CHECK();
+                }
+                ++i;
+                continue;
+            }
+            B0sAdjBatch bt;
+            memset(&bt, 0, sizeof(bt));
+            int n = 0;
+            unsigned gx = 1;
+            size_t smem = 0;
+            while (i < adjs.size() && n < B0S_MAX_BATCH && (adjs[i].M + B0S_SEG - 1) / B0S_SEG <= B0S_SEG_THREADS) {
+                const B0sAdjArgs& a = adjs[i];
+                ++i;
+                if (a.n_fibres <= 0 || a.M <= 0) continue;
+                const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.g_lo, false);
+                bt.a[n] = a;
+                bt.g[n].S = g.S; bt.g[n].F = g.F; bt.g[n].f_fast = g.f_fast; bt.g[n].blocks = (int)g.blocks;
+                gx = std::max(gx, g.blocks);
+                smem = std::max(smem, g.smem);
+                ++n;
+            }
+            if (n == 0) continue;
+            if (int rc = raise_dyn_smem(k_b0s_scan_adj_seg, smem)) return rc;
+            k_b0s_scan_adj_seg<<<dim3(gx, n), B0S_SEG_THREADS, smem, st>>>(bt);
+            VGGP_LAUNCH_CHECK();
+        }
+        adjs.clear();
+        return 0;
     }
-    VGGP_LAUNCH_CHECK();
-    return 0;
-}
+
+    int flush() {
+        if (int rc = flush_scans()) return rc;
+        return flush_adjs();
+    }
+};
 
 // dstL = G^L src, dstR = G^R src along one mode (k_b0s_scan): n_hi x n_lo fibres of M elements -> M + 2 entries
-int b0s_scan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
-             double* dstL, double* dstR, i64 d_hi, i64 d_lo, i64 d_mode) {
+void b0s_scan(B0sBatcher& q, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
+              double* dstL, double* dstR, i64 d_hi, i64 d_lo, i64 d_mode) {
     B0sScanArgs a;
     a.src = src; a.dstL = dstL; a.dstR = dstR; a.tanL = nullptr; a.tanR = nullptr; a.eps = eps; a.M = M;
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
     a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
-    return b0s_scan_launch(a, st);
+    q.scans.push_back(a);
 }
 
 // Per-cell tables from the state of the last grid forward (alpha, P_d, Q_d, theta).  Every product with G^L / G^R is a
@@ -1353,6 +1436,7 @@ int b0scan_tables(vggp_plan* p, cudaStream_t st) {
     int rc = b0scan_alloc(p);
     if (rc) return rc;
     const int D = p->D;
+    B0sBatcher q(st);
     B0sGArgs ga;
     B0sEpsArgs ea;
     int emax = 0, mmax = 0;
@@ -1378,7 +1462,7 @@ int b0scan_tables(vggp_plan* p, cudaStream_t st) {
         const int M = p->K[d] - 1, E = p->K[d] + 1;
         const double* mats[2] = {p->g.P[d], p->g.Q[d]};
         for (int mat = 0; mat < 2; ++mat)       // V^x = G^x Mat (E x M): transform along the row index, fibres = columns
-            if ((rc = b0s_scan(st, p->b0s_eps[d], M, 1, M, mats[mat], 0, 1, M, p->b0s_V[d][2 * mat], p->b0s_V[d][2 * mat + 1], 0, 1, M))) return rc;
+            b0s_scan(q, p->b0s_eps[d], M, 1, M, mats[mat], 0, 1, M, p->b0s_V[d][2 * mat], p->b0s_V[d][2 * mat + 1], 0, 1, M);
         wa.K[d] = p->K[d];
         wa.GL[d] = p->b0s_G[d][0]; wa.GR[d] = p->b0s_G[d][1];
         for (int k = 0; k < 4; ++k) wa.V[d][k] = p->b0s_V[d][k];
@@ -1386,6 +1470,7 @@ int b0scan_tables(vggp_plan* p, cudaStream_t st) {
         wa.W[d] = reinterpret_cast<T*>(p->b0s_W[d]);
         kmax = std::max(kmax, E);
     }
+    if ((rc = q.flush())) return rc;            // the 2 D transforms of P_d, Q_d: one launch
     k_b0s_W<T><<<dim3(ceil_div(kmax, 8), D), 256, 0, st>>>(wa);
     VGGP_LAUNCH_CHECK();
     const int E1 = p->K[0] + 1, M1 = p->K[0] - 1;
@@ -1396,12 +1481,14 @@ int b0scan_tables(vggp_plan* p, cudaStream_t st) {
     }
     const int E2 = p->K[1] + 1, M2 = p->K[1] - 1;
     // U^y = A G2^y^T (M1 x E2): transform along dimension 2, fibres = rows of A
-    if ((rc = b0s_scan(st, p->b0s_eps[1], M2, M1, 1, p->alpha, M2, 0, 1, p->b0s_U[0], p->b0s_U[1], E2, 0, 1))) return rc;
+    b0s_scan(q, p->b0s_eps[1], M2, M1, 1, p->alpha, M2, 0, 1, p->b0s_U[0], p->b0s_U[1], E2, 0, 1);
     // B^x = G1^x A (E1 x M2): transform along dimension 1, fibres = columns of A
-    if ((rc = b0s_scan(st, p->b0s_eps[0], M1, 1, M2, p->alpha, 0, 1, M2, p->b0s_B[0], p->b0s_B[1], 0, 1, M2))) return rc;
+    b0s_scan(q, p->b0s_eps[0], M1, 1, M2, p->alpha, 0, 1, M2, p->b0s_B[0], p->b0s_B[1], 0, 1, M2);
+    if ((rc = q.flush())) return rc;
     // TT[2x+y] = G1^x U^y (E1 x E2): transform along dimension 1 of U^y, fibres = its columns
     for (int y = 0; y < 2; ++y)
-        if ((rc = b0s_scan(st, p->b0s_eps[0], M1, 1, E2, p->b0s_U[y], 0, 1, E2, p->b0s_TT[y], p->b0s_TT[2 + y], 0, 1, E2))) return rc;
+        b0s_scan(q, p->b0s_eps[0], M1, 1, E2, p->b0s_U[y], 0, 1, E2, p->b0s_TT[y], p->b0s_TT[2 + y], 0, 1, E2);
+    if ((rc = q.flush())) return rc;
     B0sT2Args<T> ta;
     ta.E1 = E1; ta.E2 = E2; ta.M1 = M1; ta.M2 = M2;
     for (int k = 0; k < 4; ++k) ta.TT[k] = p->b0s_TT[k];
@@ -1440,39 +1527,39 @@ int launch_predict_b0s(vggp_plan* p, const void* const* x, i64 n, void* mean, vo
     return 0;
 }
 
-int b0s_scan_tan(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
-                 double* dstL, double* dstR, double* tanL, double* tanR, i64 d_hi, i64 d_lo, i64 d_mode) {
+void b0s_scan_tan(B0sBatcher& q, const double* eps, int M, i64 n_hi, i64 n_lo, const double* src, i64 s_hi, i64 s_lo, i64 s_mode,
+                  double* dstL, double* dstR, double* tanL, double* tanR, i64 d_hi, i64 d_lo, i64 d_mode) {
     B0sScanArgs a;
     a.src = src; a.dstL = dstL; a.dstR = dstR; a.tanL = tanL; a.tanR = tanR; a.eps = eps; a.M = M;
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.s_hi = s_hi; a.s_lo = s_lo; a.s_mode = s_mode;
     a.d_hi = d_hi; a.d_lo = d_lo; a.d_mode = d_mode;
-    return b0s_scan_launch(a, st);
+    q.scans.push_back(a);
 }
 
-int b0s_scan_adj(cudaStream_t st, const double* eps, int M, i64 n_hi, i64 n_lo, const double* gL, const double* gC, const double* gR,
-                 i64 g_hi, i64 g_lo, i64 g_mode, double* dv, i64 v_hi, i64 v_lo, i64 v_mode) {
+void b0s_scan_adj(B0sBatcher& q, const double* eps, int M, i64 n_hi, i64 n_lo, const double* gL, const double* gC, const double* gR,
+                  i64 g_hi, i64 g_lo, i64 g_mode, double* dv, i64 v_hi, i64 v_lo, i64 v_mode) {
     B0sAdjArgs a;
     a.gL = gL; a.gC = gC; a.gR = gR; a.dv = dv; a.eps = eps; a.M = M;
     a.n_fibres = n_hi * n_lo; a.n_lo = n_lo;
     a.g_hi = g_hi; a.g_lo = g_lo; a.g_mode = g_mode;
     a.v_hi = v_hi; a.v_lo = v_lo; a.v_mode = v_mode;
-    if (a.n_fibres <= 0 || a.M <= 0) return 0;
-    if (!g_b0s_seg || (a.M + B0S_SEG - 1) / B0S_SEG > B0S_SEG_THREADS) {
-        k_b0s_scan_adj<<<ceil_div(a.n_fibres, 128), 128, 0, st>>>(a);
-        VGGP_LAUNCH_CHECK();
-        return 0;
-    }
-    const B0sSegGeom g = b0s_seg_geom(a.M, a.n_fibres, a.n_lo, a.g_lo, false);
-    if (int rc = raise_dyn_smem(k_b0s_scan_adj_seg, g.smem)) return rc;
-    k_b0s_scan_adj_seg<<<g.blocks, B0S_SEG_THREADS, g.smem, st>>>(a, g.S, g.F, g.f_fast);
-    VGGP_LAUNCH_CHECK();
-    return 0;
+    q.adjs.push_back(a);
 }
 
-int b0s_dot(cudaStream_t st, const double* x, const double* y, i64 n, double* out) {
-    k_b0s_dot1<<<std::min<int>(ceil_div(n, 256), 64), 256, 0, st>>>(x, y, n, out);
-    VGGP_LAUNCH_CHECK();
+// out[e] += <x_e, y_e> for up to B0S_MAX_BATCH pairs of n elements each, one launch
+int b0s_dots(cudaStream_t st, const std::vector<const double*>& x, const std::vector<const double*>& y,
+             const std::vector<double*>& out, i64 n) {
+    size_t i = 0;
+    while (i < x.size()) {
+        B0sDotBatch b;
+        memset(&b, 0, sizeof(b));
+        int k = 0;
+        for (; i < x.size() && k < B0S_MAX_BATCH; ++i, ++k) { b.x[k] = x[i]; b.y[k] = y[i]; b.out[k] = out[i]; }
+        b.n = n;
+        k_b0s_dot_batch<<<dim3(std::min<int>(ceil_div(n, 256), 64), k), 256, 0, st>>>(b);
+        VGGP_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -1497,28 +1584,50 @@ int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
     vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
     double* gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
     auto GT = [&](int X, int Y) { return GTd + (i64)(3 * X + Y) * EE; };
+    B0sBatcher q(st);
+    // the S^X = diag(gw^{X.}) G^. products of the four (dimension, matrix) pairs first: their adjoint sweeps then share launches
+    // with the sweeps of d alpha
+    int pair = 0;
+    for (int d = 0; d < D; ++d) {
+        const int K = p->K[d];
+        const i64 M = K - 1, E = K + 1;
+        for (int mat = 0; mat < 2; ++mat, ++pair) {
+            k_b0s_S<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, p->b0s_G[d][0], p->b0s_G[d][1], GW[d] + (i64)mat * 6 * E,
+                                                             p->b0s_Sx[pair][0], p->b0s_Sx[pair][1], p->b0s_Sx[pair][2]);
+            VGGP_LAUNCH_CHECK();
+        }
+    }
     // ---- d alpha = sum_XY G1^X^T GT^{XY} G2^Y ----
     if (D == 1) {
         k_b0s_galpha1<T><<<ceil_div(M1, 256), 256, 0, st>>>(p->K[0], p->b0s_G[0][0], p->b0s_G[0][1], GTd, galpha);
         VGGP_LAUNCH_CHECK();
     } else {
         for (int Y = 0; Y < 3; ++Y)          // H^Y = sum_X G1^X^T GT^{XY}  (M1 x E2): adjoint sweep along dimension 1, fibres = columns
-            if ((rc = b0s_scan_adj(st, p->b0s_eps[0], (int)M1, 1, E2, GT(B0S_L, Y), GT(B0S_C, Y), GT(B0S_R, Y), 0, 1, E2, p->b0s_H[Y], 0, 1, E2))) return rc;
-        // d alpha = sum_Y H^Y G2^Y  (M1 x M2): adjoint sweep along dimension 2, fibres = rows
-        if ((rc = b0s_scan_adj(st, p->b0s_eps[1], (int)M2, M1, 1, p->b0s_H[B0S_L], p->b0s_H[B0S_C], p->b0s_H[B0S_R], E2, 0, 1, p->b0s_dA, M2, 0, 1))) return rc;
+            b0s_scan_adj(q, p->b0s_eps[0], (int)M1, 1, E2, GT(B0S_L, Y), GT(B0S_C, Y), GT(B0S_R, Y), 0, 1, E2, p->b0s_H[Y], 0, 1, E2);
+    }
+    // ---- [bP | bQ]_d = sum_XY G^X^T diag(gw^{XY}) G^Y = sum_X G^X^T S^X ----
+    pair = 0;
+    for (int d = 0; d < D; ++d) {
+        const i64 M = p->K[d] - 1;
+        for (int mat = 0; mat < 2; ++mat, ++pair) {
+            if (D == 2 && pair == 3) {        // H^Y are complete after the first launch: d alpha = sum_Y H^Y G2^Y rides with the last pair
+                if ((rc = q.flush())) return rc;
+                b0s_scan_adj(q, p->b0s_eps[1], (int)M2, M1, 1, p->b0s_H[B0S_L], p->b0s_H[B0S_C], p->b0s_H[B0S_R], E2, 0, 1, p->b0s_dA, M2, 0, 1);
+            }
+            b0s_scan_adj(q, p->b0s_eps[d], (int)M, 1, M, p->b0s_Sx[pair][B0S_L], p->b0s_Sx[pair][B0S_C], p->b0s_Sx[pair][B0S_R], 0, 1, M,
+                         p->b0s_bMx[pair], 0, 1, M);
+        }
+    }
+    if ((rc = q.flush())) return rc;
+    if (D == 2) {
         k_b0s_from_double<T><<<ceil_div(M1 * M2, 256), 256, 0, st>>>(p->b0s_dA, galpha, M1 * M2);
         VGGP_LAUNCH_CHECK();
     }
-    // ---- [bP | bQ]_d = sum_XY G^X^T diag(gw^{XY}) G^Y = sum_X G^X^T S^X ----
+    pair = 0;
     for (int d = 0; d < D; ++d) {
-        const int K = p->K[d];
-        const i64 M = K - 1, E = K + 1;
-        for (int mat = 0; mat < 2; ++mat) {
-            k_b0s_S<T><<<ceil_div(E * M, 256), 256, 0, st>>>(K, p->b0s_G[d][0], p->b0s_G[d][1], GW[d] + (i64)mat * 6 * E,
-                                                             p->b0s_S[0], p->b0s_S[1], p->b0s_S[2]);
-            VGGP_LAUNCH_CHECK();
-            if ((rc = b0s_scan_adj(st, p->b0s_eps[d], (int)M, 1, M, p->b0s_S[B0S_L], p->b0s_S[B0S_C], p->b0s_S[B0S_R], 0, 1, M, p->b0s_bM, 0, 1, M))) return rc;
-            k_b0s_from_double<T><<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bM, gfac + p->gfac_off[d] + (i64)mat * M * M, M * M);
+        const i64 M = p->K[d] - 1;
+        for (int mat = 0; mat < 2; ++mat, ++pair) {
+            k_b0s_from_double<T><<<ceil_div(M * M, 256), 256, 0, st>>>(p->b0s_bMx[pair], gfac + p->gfac_off[d] + (i64)mat * M * M, M * M);
             VGGP_LAUNCH_CHECK();
         }
     }
@@ -1531,32 +1640,38 @@ int b0scan_adjoint(vggp_plan* p, void* gbuf, cudaStream_t st) {
         VGGP_LAUNCH_CHECK();
     }
     if (D == 2) {
-        // the forward's corner products are no longer needed: TT[0], TT[1] take the (unused) transforms, TT[2], TT[3] the tangents
-        double *sL = p->b0s_TT[0], *sR = p->b0s_TT[1], *tL = p->b0s_TT[2], *tR = p->b0s_TT[3];
+        // six tangent sweeps, each into its own scratch set [transform L | transform R | tangent L | tangent R] (the forward's corner
+        // products in TT[] are no longer needed: they are set 0), one launch; then the twelve inner products in two launches
+        std::vector<const double*> dx, dy;
+        std::vector<double*> dout;
         // l_1: dT^{XY} / dl_1 = (dG1^X / dl_1) U^Y, X in {L, R}: tangent sweep along dimension 1 of U^Y (U^C = A in columns 1..M2)
         for (int Y = 0; Y < 3; ++Y) {
+            double* const* sc = p->b0s_tan[Y];
             if (Y == B0S_C) {
-                VGGP_CUDA(cudaMemsetAsync(tL, 0, sizeof(double) * EE, st));
-                VGGP_CUDA(cudaMemsetAsync(tR, 0, sizeof(double) * EE, st));
-                if ((rc = b0s_scan_tan(st, p->b0s_eps[0], (int)M1, 1, M2, p->alpha, 0, 1, M2, sL + 1, sR + 1, tL + 1, tR + 1, 0, 1, E2))) return rc;
+                VGGP_CUDA(cudaMemsetAsync(sc[2], 0, sizeof(double) * EE, st));
+                VGGP_CUDA(cudaMemsetAsync(sc[3], 0, sizeof(double) * EE, st));
+                b0s_scan_tan(q, p->b0s_eps[0], (int)M1, 1, M2, p->alpha, 0, 1, M2, sc[0] + 1, sc[1] + 1, sc[2] + 1, sc[3] + 1, 0, 1, E2);
             } else {
-                if ((rc = b0s_scan_tan(st, p->b0s_eps[0], (int)M1, 1, E2, p->b0s_U[Y == B0S_L ? 0 : 1], 0, 1, E2, sL, sR, tL, tR, 0, 1, E2))) return rc;
+                b0s_scan_tan(q, p->b0s_eps[0], (int)M1, 1, E2, p->b0s_U[Y == B0S_L ? 0 : 1], 0, 1, E2, sc[0], sc[1], sc[2], sc[3], 0, 1, E2);
             }
-            if ((rc = b0s_dot(st, GT(B0S_L, Y), tL, EE, gs + 3))) return rc;
-            if ((rc = b0s_dot(st, GT(B0S_R, Y), tR, EE, gs + 3))) return rc;
+            dx.push_back(GT(B0S_L, Y)); dy.push_back(sc[2]); dout.push_back(gs + 3);
+            dx.push_back(GT(B0S_R, Y)); dy.push_back(sc[3]); dout.push_back(gs + 3);
         }
         // l_2: dT^{XY} / dl_2 = B^X (dG2^Y / dl_2)^T, Y in {L, R}: tangent sweep along dimension 2 of B^X (B^C = A in rows 1..M1)
         for (int X = 0; X < 3; ++X) {
+            double* const* sc = p->b0s_tan[3 + X];
             if (X == B0S_C) {
-                VGGP_CUDA(cudaMemsetAsync(tL, 0, sizeof(double) * EE, st));
-                VGGP_CUDA(cudaMemsetAsync(tR, 0, sizeof(double) * EE, st));
-                if ((rc = b0s_scan_tan(st, p->b0s_eps[1], (int)M2, M1, 1, p->alpha, M2, 0, 1, sL + E2, sR + E2, tL + E2, tR + E2, E2, 0, 1))) return rc;
+                VGGP_CUDA(cudaMemsetAsync(sc[2], 0, sizeof(double) * EE, st));
+                VGGP_CUDA(cudaMemsetAsync(sc[3], 0, sizeof(double) * EE, st));
+                b0s_scan_tan(q, p->b0s_eps[1], (int)M2, M1, 1, p->alpha, M2, 0, 1, sc[0] + E2, sc[1] + E2, sc[2] + E2, sc[3] + E2, E2, 0, 1);
             } else {
-                if ((rc = b0s_scan_tan(st, p->b0s_eps[1], (int)M2, E1, 1, p->b0s_B[X == B0S_L ? 0 : 1], M2, 0, 1, sL, sR, tL, tR, E2, 0, 1))) return rc;
+                b0s_scan_tan(q, p->b0s_eps[1], (int)M2, E1, 1, p->b0s_B[X == B0S_L ? 0 : 1], M2, 0, 1, sc[0], sc[1], sc[2], sc[3], E2, 0, 1);
             }
-            if ((rc = b0s_dot(st, GT(X, B0S_L), tL, EE, gs + 4))) return rc;
-            if ((rc = b0s_dot(st, GT(X, B0S_R), tR, EE, gs + 4))) return rc;
+            dx.push_back(GT(X, B0S_L)); dy.push_back(sc[2]); dout.push_back(gs + 4);
+            dx.push_back(GT(X, B0S_R)); dy.push_back(sc[3]); dout.push_back(gs + 4);
         }
+        if ((rc = q.flush())) return rc;
+        if ((rc = b0s_dots(st, dx, dy, dout, EE))) return rc;
     }
     return 0;
 }
@@ -1584,7 +1699,9 @@ int launch_obs_b0s(vggp_plan* p, const vggp_binned_desc* desc, const void* binne
     a.counter = p->obs_counter;
     VGGP_CUDA(cudaMemsetAsync(p->obs_counter, 0, sizeof(unsigned int), st));
     i64 blocks = (desc->n_tasks + (B0S_THREADS / 32) - 1) / (B0S_THREADS / 32);
-    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * 2));
+    int per_sm = 0;                             // as many persistent CTAs as fit (167 registers: 3 per SM; the first version launched 2)
+    VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_obs_b0s<T, D>, B0S_THREADS, 0));
+    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * std::max(1, per_sm)));
     k1_mark(p, 0, st);
     k_obs_b0s<T, D><<<(unsigned)blocks, B0S_THREADS, 0, st>>>(a);
     k1_mark(p, 1, st);
