@@ -207,6 +207,10 @@ inline void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
 // cp.async: the copy is DEFERRED until the group it belongs to is waited for (a missing wait reads stale data)
 inline void cp_async16(void* dst, const void* src, int src_bytes) { cuda_emul::cp_async_enqueue(dst, src, 16, src_bytes); }
 inline void cp_async8(void* dst, const void* src, int src_bytes) { cuda_emul::cp_async_enqueue(dst, src, 8, src_bytes); }
+typedef char* smaddr_t;
+inline smaddr_t sm_addr(const void* p) { return (char*)const_cast<void*>(p); }
+inline void cp_async16_p(smaddr_t dst, const void* src, bool ignore) { cuda_emul::cp_async_enqueue(dst, src, 16, ignore ? 0 : 16); }
+inline void cp_async8_p(smaddr_t dst, const void* src, bool ignore) { cuda_emul::cp_async_enqueue(dst, src, 8, ignore ? 0 : 8); }
 inline void cp_async_commit() { cuda_emul::cp_async_commit_group(); }
 template <int N>
 inline void cp_async_wait() { cuda_emul::cp_async_wait_group(N); }

@@ -187,6 +187,15 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 __device__ __forceinline__ void cp_async8(void* dst, const void* src, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes));
 }
+// predicate forms on a shared-window address: `ignore` = write zeros, read nothing
+typedef uint32_t smaddr_t;
+__device__ __forceinline__ smaddr_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_p(smaddr_t dst, const void* src, bool ignore) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n cp.async.cg.shared.global [%0], [%1], 16, p;\n}\n" ::"r"(dst), "l"(src), "r"((int)ignore));
+}
+__device__ __forceinline__ void cp_async8_p(smaddr_t dst, const void* src, bool ignore) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n cp.async.ca.shared.global [%0], [%1], 8, p;\n}\n" ::"r"(dst), "l"(src), "r"((int)ignore));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -241,6 +250,54 @@ __device__ __forceinline__ void gemm_stage_slot(double* sm, const GemmSlot& s, b
     }
 }
 
+// The same slot for a stage that lies entirely inside the k range ("lean" form).  Rows past the m / n edge are CLAMPED to the
+// last row instead of zero-filled: they only feed output rows / columns that are never stored, so no predicate and no byte
+// count is left -- per copy one address (32-bit element offset from the operand base, advanced by a uniform step per
+// stage) and the LDGSTS.  Only the k edge needs zeros; the one partial stage of a k range keeps the general form.
+struct GemmLean {
+    int o0, o1;             // element offsets of the copy (16 bytes at o0 when aligned, else 8 bytes at o0 and at o1)
+    smaddr_t dst;           // destination inside stage 0
+};
+__device__ __forceinline__ GemmLean gemm_lean(i64 ld, bool kc, bool vec2, int mn0, int kbeg, int mn_lim, int tid, int it,
+                                              double* sm_operand) {
+    const int c = tid + it * 256;
+    GemmLean l;
+    if (kc) {
+        const int row = c >> 3, col = (c & 7) << 1;
+        const int rr = min(mn0 + row, mn_lim - 1);
+        l.o0 = (int)((i64)rr * ld) + kbeg + col;
+        l.o1 = l.o0 + 1;
+        l.dst = sm_addr(sm_operand + row * 20 + col);
+    } else {
+        const int row = c >> 5, col = (c & 31) << 1;
+        const int rowoff = (int)((i64)(kbeg + row) * ld);
+        // aligned pairs stay aligned: with 16-byte copies the edge is even (gemm_lean_ok), so the last pair starts at lim - 2
+        l.o0 = rowoff + min(mn0 + col, vec2 ? mn_lim - 2 : mn_lim - 1);
+        l.o1 = rowoff + min(mn0 + col + 1, mn_lim - 1);
+        l.dst = sm_addr(sm_operand + row * 68 + col);
+    }
+    return l;
+}
+// is the lean form usable for this operand tile?  (offsets fit 32 bits; an aligned 16-byte copy never straddles the edge)
+__device__ __forceinline__ bool gemm_lean_ok(i64 ld, bool kc, bool vec2, int mn0, int mn_lim, int kend) {
+    const i64 span = kc ? (i64)mn_lim * ld + kend : (i64)(kend + GBK) * ld + mn_lim;
+    if (span >= ((i64)1 << 31) || mn_lim < 1) return false;
+    if (vec2 && !kc && mn_lim < mn0 + 64 && (mn_lim & 1)) return false;
+    if (vec2 && !kc && (mn_lim <= mn0 || mn_lim < 2)) return false;
+    return true;
+}
+__device__ __forceinline__ void gemm_stage_lean(const double* __restrict__ base, int stage_bytes, GemmLean& l, bool vec2, int inc) {
+    const smaddr_t dst = l.dst + stage_bytes;
+    if (vec2) {
+        cp_async16_p(dst, base + l.o0, false);
+    } else {
+        cp_async8_p(dst, base + l.o0, false);
+        cp_async8_p(dst + 8, base + l.o1, false);
+    }
+    l.o0 += inc;
+    l.o1 += inc;
+}
+
 __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double* sm) {
     const int tid = threadIdx.x;
     const int tile_m = blockIdx.y, tile_n = blockIdx.x;
@@ -285,16 +342,32 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
     const GemmSlot sa0 = gemm_slot(Ab, lda, akc, m0, kbeg, d.m, tid, 0), sa1 = gemm_slot(Ab, lda, akc, m0, kbeg, d.m, tid, 1);
     const GemmSlot sb0 = gemm_slot(Bb, ldb, !bnc, n0, kbeg, d.n, tid, 0), sb1 = gemm_slot(Bb, ldb, !bnc, n0, kbeg, d.n, tid, 1);
     const i64 ksa = akc ? 1 : lda, ksb = !bnc ? 1 : ldb;
+    // Full stages (all but possibly the last one) go through the lean form (SASS of round 2: 250 of the 330 instructions of a
+    // k-step were staging, issued by every warp right after the barrier while the tensor pipe idled).  Stages are issued in
+    // order, so the offsets just advance.
+    const bool lean = gemm_lean_ok(lda, akc, av2, m0, d.m, kend) && gemm_lean_ok(ldb, !bnc, bv2, n0, d.n, kend);
+    const int nfull = lean ? (kend - kbeg) / GBK : 0;       // stages that lie entirely inside the k range
+    GemmLean la0 = gemm_lean(lda, akc, av2, m0, kbeg, d.m, tid, 0, sm), la1 = gemm_lean(lda, akc, av2, m0, kbeg, d.m, tid, 1, sm);
+    GemmLean lb0 = gemm_lean(ldb, !bnc, bv2, n0, kbeg, d.n, tid, 0, sm + 1280), lb1 = gemm_lean(ldb, !bnc, bv2, n0, kbeg, d.n, tid, 1, sm + 1280);
+    const int inca = (int)(ksa * GBK), incb = (int)(ksb * GBK);
     auto stage = [&](int st) {
         double* nx = sm + (st % GF_NSTAGE) * GF_STAGE;
-        const int koff = st * GBK, krem = kend - kbeg - koff;
-        gemm_stage_slot(nx, sa0, akc, av2, ksa, koff, krem, Ab);
-        gemm_stage_slot(nx, sa1, akc, av2, ksa, koff, krem, Ab);
-        gemm_stage_slot(nx + 1280, sb0, !bnc, bv2, ksb, koff, krem, Bb);
-        gemm_stage_slot(nx + 1280, sb1, !bnc, bv2, ksb, koff, krem, Bb);
+        if (st < nfull) {
+            const int sb = (st % GF_NSTAGE) * (GF_STAGE * (int)sizeof(double));
+            gemm_stage_lean(Ab, sb, la0, av2, inca);
+            gemm_stage_lean(Ab, sb, la1, av2, inca);
+            gemm_stage_lean(Bb, sb, lb0, bv2, incb);
+            gemm_stage_lean(Bb, sb, lb1, bv2, incb);
+        } else {
+            const int koff = st * GBK, krem = kend - kbeg - koff;
+            gemm_stage_slot(nx, sa0, akc, av2, ksa, koff, krem, Ab);
+            gemm_stage_slot(nx, sa1, akc, av2, ksa, koff, krem, Ab);
+            gemm_stage_slot(nx + 1280, sb0, !bnc, bv2, ksb, koff, krem, Bb);
+            gemm_stage_slot(nx + 1280, sb1, !bnc, bv2, ksb, koff, krem, Bb);
+        }
     };
     // prologue: GF_NSTAGE - 1 stages in flight (one commit group per stage, empty groups past the end keep the count uniform)
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < GF_NSTAGE - 1; ++s) {
         if (s < nk) stage(s);
         cp_async_commit();
