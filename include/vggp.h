@@ -191,6 +191,19 @@ int vggp_obs_fwd_bwd_binned(vggp_plan* plan, const vggp_binned_desc* desc, const
 int vggp_set_binned_stream(int mode);
 
 /*
+ * Deterministic mode: on = 1 makes a step of this plan -- vggp_grid_forward,
+ * vggp_obs_fwd_bwd_binned, vggp_grid_backward -- bitwise reproducible from run to run, whatever the grid size, the work
+ * stealing order or the load of the machine.  No floating-point atomic is left on the path: every run of the binned
+ * layout writes its flush values as a record and the records are summed in the order of the cell-sorted stream
+ * (csrc/obs_binned.cuh); the fibre passes leave per-CTA partials that are summed in tile order (csrc/grid_b1_fast.cuh).
+ * Covered: the B1 (ASVGP) family on its default fused grid path with M_d <= 512 and the binned observation layout
+ * (VGGP_E_UNSUPPORTED otherwise, also from vggp_obs_fwd_bwd / _packed while the mode is on).  The scratch is sized at the
+ * first deterministic step (cudaMalloc): run one step eagerly before capturing a graph.  Costs a sort of the run list
+ * and five small reductions per step; the default (0) is the atomics path.
+ */
+int vggp_set_deterministic(vggp_plan* plan, int on);
+
+/*
  * The one collective of a sharded step as a single kernel over peer memory (csrc/collective.cuh): gbuf <- sum over the ranks
  * of one NVSwitch node, in place, on `stream`, between vggp_obs_fwd_bwd* and vggp_grid_backward.  It replaces the
  * ncclAllReduce the north star names where the gradient buffers are SYMMETRIC allocations: same

@@ -597,3 +597,44 @@ def test_automatic_run_cap_under_emulation(emu):
     for a, b in zip(got, ref):
         assert relerr(torch.from_numpy(np.asarray(a, dtype=np.float64)), torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-12
     plan.close()
+
+
+@pytest.mark.parametrize("knots,N", B1_CASES)
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-3)])
+def test_deterministic_mode_matches_oracle_under_emulation(emu, knots, N, dtype, tol):
+    """vggp_set_deterministic (include/vggp.h): run records + ordered reductions instead of the atomics of the per-observation
+    kernel, per-CTA partials instead of the atomics of the fibre passes -- same ELBO and gradients as the oracle, identical
+    bits from two runs, and the plain-array entry point refuses while the mode is on."""
+    lib, L = emu
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=7 + D)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Xq, yq = X.to(tdt), y.to(tdt)
+    scale = 1.3
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], dtype)
+    theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+    mm = m.numpy().copy()
+    Lcat = torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy()
+    xs = [np.ascontiguousarray(Xq[:, d].numpy()) for d in range(D)]
+    yy = np.ascontiguousarray(yq.numpy())
+    try:
+        binned = plan.bin(xs, yy, run_cap=8)          # cells split into several runs: the ordered sum has something to order
+        plain = plan.step(theta, mm, Lcat, binned, None, scale)
+        plan.check(lib.vggp_set_deterministic(plan.h, 1))
+        a = plan.step(theta, mm, Lcat, binned, None, scale)
+        b = plan.step(theta, mm, Lcat, binned, None, scale)
+        check_against_oracle(plan, *a, elbo_ref, g_ref, N, tol)
+        for u, v in zip(a, b):
+            assert np.array_equal(np.asarray(u), np.asarray(v))
+        for u, v in zip(a, plain):
+            assert relerr(u, torch.from_numpy(np.asarray(v, dtype=np.float64))) < tol * 10
+        rc = lib.vggp_obs_fwd_bwd(plan.h, plan._xptrs(xs), emul_lib.ptr(yy), N, emul_lib.ptr(plan.gbuf), None)
+        assert rc == -6
+        plan.check(lib.vggp_set_deterministic(plan.h, 0))
+        c = plan.step(theta, mm, Lcat, binned, None, scale)
+        for u, v in zip(c, plain):
+            assert relerr(u, torch.from_numpy(np.asarray(v, dtype=np.float64))) < tol * 10
+    finally:
+        plan.close()

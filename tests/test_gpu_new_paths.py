@@ -338,3 +338,71 @@ def test_track_generator_matches_torch_restatement(vg, dev, D):
     assert torch.equal(y_s, y[1000:500000])
     with pytest.raises(RuntimeError):
         gen.generate_tracks(0, 10, 10, "cpu")
+
+
+@pytest.mark.parametrize("knots,N,run_cap", [((130,), 40000, 64), ((65, 33), 200000, 16), ((130, 9), 5000, 256), ((17, 12, 9), 60000, 8)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-3)])
+def test_deterministic_mode_bitwise_reproducible(vg, dev, knots, N, run_cap, dtype, tol):
+    """vggp_set_deterministic (include/vggp.h): six steps over the same binned buffer -- with another
+    kernel hogging the machine in between, so that the warps of the per-observation kernel finish in another order -- give
+    identical bits for the ELBO and every gradient; the results agree with the oracle like the atomics path does, a CUDA
+    graph of the deterministic step replays them bit for bit, and the plain-array entry point refuses while the mode is on."""
+    D = len(knots)
+    meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=11 + D)
+    Xq, yq = X.to(dtype), y.to(dtype)
+    scale = 1.3
+    elbo_ref, g_ref = oracle_value_and_grads(O.B1_ASVGP, meshes, Xq.to(torch.float64), yq.to(torch.float64),
+                                             l, s2, noise, m, Ls, scale=scale)
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, dtype, dev)
+    theta = torch.cat([l, s2, noise.reshape(1)]).to(dev)
+    md = m.to(dev)
+    Lcat = torch.cat([L.reshape(-1) for L in Ls]).to(dev)
+    xs = [Xq[:, d].contiguous().to(dev) for d in range(D)]
+    yd = yq.to(dev)
+    binned = plan.bin(xs, yd, run_cap=run_cap)
+    plain = [t.clone() for t in plan.step(theta, md, Lcat, binned, None, ell_scale=scale)]
+    plan.set_deterministic(True)
+    runs = []
+    noise_a = torch.randn(4096, 4096, device=dev)
+    for k in range(6):
+        if k % 2:
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                for _ in range(4):
+                    noise_a = torch.tanh(noise_a @ noise_a * 1e-3)
+        runs.append([t.clone() for t in plan.step(theta, md, Lcat, binned, None, ell_scale=scale)])
+        torch.cuda.synchronize()
+    assert plan.read_info() == 0
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+    out, dtheta, dm, dL = runs[0]
+    assert out[3].item() == N
+    assert abs(out[0].item() - elbo_ref.item()) <= tol * abs(elbo_ref.item())
+    assert relerr(dtheta[:D], g_ref[0]) < tol * 10 and relerr(dtheta[D:2 * D], g_ref[1]) < tol * 10
+    assert relerr(dtheta[2 * D], g_ref[2]) < tol * 10 and relerr(dm, g_ref[3]) < tol * 10
+    off = 0
+    for d, n in enumerate(plan.m_per_dim):
+        dLd = dL[off:off + n * n].reshape(n, n).cpu()
+        off += n * n
+        assert relerr(torch.tril(dLd), torch.tril(g_ref[4 + d])) < tol * 10, ("dL", d)
+    for a, b in zip(runs[0], plain):
+        assert relerr(a, b.cpu()) < tol * 10
+    gs = plan.graphed_step(theta, md, Lcat, binned, None, scale, None)
+    got = gs.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(got, runs[0]):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        plan.step(theta, md, Lcat, xs, yd, ell_scale=scale)
+    plan.set_deterministic(False)
+    again = plan.step(theta, md, Lcat, binned, None, ell_scale=scale)
+    for a, b in zip(again, plain):
+        assert relerr(a, b.cpu()) < tol * 10
+
+
+def test_deterministic_mode_refuses_other_families(vg, dev):
+    meshes = [torch.linspace(0, 1, 17), torch.linspace(0, 1, 9)]
+    plan = vg.GridPlan(vg.B0_GRIDDED, meshes, torch.float64, dev)
+    with pytest.raises(RuntimeError):
+        plan.set_deterministic(True)

@@ -25,6 +25,12 @@ constexpr int FP_WARPS = FP_THREADS / 32;
 constexpr int FP_MAX_TASKS = 14;
 constexpr int GEN_CHUNK = 32;            // pivots per thread in k_b1_gens
 constexpr int GEN_THREADS = 256;
+// deterministic mode: what one CTA of a fibre pass leaves for k_fp_det_reduce (grid_b1_fast.cuh)
+constexpr int FP_DET_BAND = 0;                     // [3][512] band partials (dl + 1, i)
+constexpr int FP_DET_MALPHA = 3 * 512;             // <m, alpha> partial
+constexpr int FP_DET_TR = FP_DET_MALPHA + 1;       // [FP_WARPS] tr terms of the rows of a QROW tile
+constexpr int FP_DET_LOGDET = FP_DET_TR + 8;       // [FP_WARPS] log det terms
+constexpr int FP_DET_SLOT = FP_DET_LOGDET + 8;
 
 enum FpKind {
     FP_R = 0,       // R_d = P_d tril(L_d): column k of tril(L_d) -> column k of R_d
@@ -65,6 +71,7 @@ struct FpPass {
     double* Qb[VGGP_MAX_D];
     void* bandT;                  // per-cell tables (obs dtype)
     int tab_off[VGGP_MAX_D];
+    double* det;                  // deterministic mode: per-CTA partials [FP_DET_SLOT] instead of atomics (summed by k_fp_det_reduce), or null
     long long* dbg;               // optional phase stamps (tools/gpu_phase_stamps.py): [tile][8] of clock64 / globaltimer, or null
 };
 
@@ -715,8 +722,14 @@ __device__ __forceinline__ void fp_qrow(const FpPass& P, const FpTask& tk, int t
         T* tab = reinterpret_cast<T*>(P.bandT) + P.tab_off[d];
         const double B2 = 2.0 * qo;
         tab[3 * n + i] = (T)qd; tab[4 * n + i] = (T)(B2 - 2.0 * qd); tab[5 * n + i] = (T)(qd - B2 + qn);
-        atomicAdd(P.sc + SC_TR + d, tr);
-        atomicAdd(P.sc + SC_LOGDETS + d, 2.0 * log(fabs(Li[i])));
+        if (P.det) {
+            double* ds = P.det + (i64)blockIdx.x * FP_DET_SLOT;
+            ds[FP_DET_TR + (threadIdx.x >> 5)] = tr;
+            ds[FP_DET_LOGDET + (threadIdx.x >> 5)] = 2.0 * log(fabs(Li[i]));
+        } else {
+            atomicAdd(P.sc + SC_TR + d, tr);
+            atomicAdd(P.sc + SC_LOGDETS + d, 2.0 * log(fabs(Li[i])));
+        }
     }
 }
 

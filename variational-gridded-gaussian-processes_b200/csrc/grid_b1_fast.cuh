@@ -79,7 +79,7 @@ __device__ __forceinline__ void ff_fibre(const double* __restrict__ pd, const do
 // `scr` (3 x 512 doubles: the generator arrays, free after the recurrences) holds the per-window partial sums so that one
 // atomic per (dl, i) leaves the CTA however many fibres a row packs.
 __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const double* __restrict__ Cx, int f0, int f1, int n,
-                                             int lg, double* __restrict__ scr, double* __restrict__ acc) {
+                                             int lg, double* __restrict__ scr, double* __restrict__ acc, double* __restrict__ det) {
     const int mask = (1 << lg) - 1;
     const bool packed = lg < 9;
     for (int s_ = threadIdx.x; s_ < 512; s_ += FP_THREADS) {
@@ -96,9 +96,13 @@ __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const
                 ap = fma(y, c[pp], ap);
             }
             if (!packed) {
-                if (i > 0) atomicAdd(acc + i, am);
-                atomicAdd(acc + n + i, a0);
-                if (i + 1 < n) atomicAdd(acc + 2 * n + i, ap);
+                if (det) {          // deterministic mode: this CTA's partials, summed in tile order by k_fp_det_reduce
+                    det[FP_DET_BAND + i] = am; det[FP_DET_BAND + 512 + i] = a0; det[FP_DET_BAND + 1024 + i] = ap;
+                } else {
+                    if (i > 0) atomicAdd(acc + i, am);
+                    atomicAdd(acc + n + i, a0);
+                    if (i + 1 < n) atomicAdd(acc + 2 * n + i, ap);
+                }
             }
         }
         if (packed) { scr[s_] = am; scr[512 + s_] = a0; scr[1024 + s_] = ap; }
@@ -110,7 +114,8 @@ __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const
         double v = 0.0;
         for (int w = 0; w < 512; w += mask + 1) v += scr[k * 512 + w + i];
         if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
-        atomicAdd(acc + k * n + i, v);
+        if (det) det[FP_DET_BAND + k * 512 + i] = v;
+        else atomicAdd(acc + k * n + i, v);
     }
 }
 
@@ -342,7 +347,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
             }
             if (kind == FP_ALPHA) {
                 dot = block_sum(dot, red);
-                if (tid == 0) atomicAdd(P.sc + SC_MALPHA, dot);
+                if (tid == 0) {
+                    if (P.det) P.det[(i64)blockIdx.x * FP_DET_SLOT + FP_DET_MALPHA] = dot;
+                    else atomicAdd(P.sc + SC_MALPHA, dot);
+                }
             }
         } break;
         case FP_GA: {
@@ -354,10 +362,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
                     dst[FF_GA(u)] = tk.direct ? y - Cx[FF_SO(u)] : y;            // Cx holds alpha of these fibres
                 }
             }
-            ff_band_dots(X, Cx, nsrc, nsrc + nrows, n, lg, pd, P.acc[d]);       // the generator arrays are scratch by now
+            ff_band_dots(X, Cx, nsrc, nsrc + nrows, n, lg, pd, P.acc[d], P.det ? P.det + (i64)blockIdx.x * FP_DET_SLOT : nullptr);       // the generator arrays are scratch by now
         } break;
         case FP_GAONLY:
-            ff_band_dots(X, Cx, 0, nrows, n, lg, pd, P.acc[d]);
+            ff_band_dots(X, Cx, 0, nrows, n, lg, pd, P.acc[d], P.det ? P.det + (i64)blockIdx.x * FP_DET_SLOT : nullptr);
             break;
         case FP_DL: {
             double* __restrict__ dL = tk.o0;
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
                     dL[(i64)i * n + k] = vv;
                 }
             }
-            ff_band_dots(X, Cx, 0, nf, n, 9, pd, P.acc[d]);
+            ff_band_dots(X, Cx, 0, nf, n, 9, pd, P.acc[d], P.det ? P.det + (i64)blockIdx.x * FP_DET_SLOT : nullptr);
         } break;
         default: break;
     }
@@ -388,6 +396,41 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
 #undef FF_OK
 #undef FF_GA
 #undef FF_SO
+}
+
+// Deterministic mode: sum the per-CTA partials of the pass that just ran, tiles in order, into the accumulators the atomics
+// would have hit.  grid (D): CTA d walks the tasks of dimension d in task order (two tasks of a pass may feed the same band).
+__global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ FpPass P) {
+    const int d = blockIdx.x;
+    for (int ti = 0; ti < P.ntasks; ++ti) {
+        const FpTask& tk = P.t[ti];
+        if (tk.d != d) continue;
+        const int n = tk.n, kind = tk.kind;
+        const double* base = P.det + (i64)tk.tile0 * FP_DET_SLOT;
+        if (kind == FP_GA || kind == FP_GAONLY || kind == FP_DL) {
+            for (int e = threadIdx.x; e < 3 * n; e += 256) {
+                const int k = e / n, i = e - k * n;
+                if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
+                double v = 0.0;
+                for (int t = 0; t < tk.ntiles; ++t) v += base[(i64)t * FP_DET_SLOT + FP_DET_BAND + k * 512 + i];
+                P.acc[d][e] += v;
+            }
+        } else if (kind == FP_ALPHA) {
+            if (threadIdx.x == 0) {
+                double v = 0.0;
+                for (int t = 0; t < tk.ntiles; ++t) v += base[(i64)t * FP_DET_SLOT + FP_DET_MALPHA];
+                P.sc[SC_MALPHA] += v;
+            }
+        } else if (kind == FP_QROW) {
+            if (threadIdx.x < 2) {
+                const int off = threadIdx.x == 0 ? FP_DET_TR : FP_DET_LOGDET;
+                double v = 0.0;
+                for (int i = 0; i < n; ++i) v += base[(i64)(i / FP_WARPS) * FP_DET_SLOT + off + (i % FP_WARPS)];
+                P.sc[(threadIdx.x == 0 ? SC_TR : SC_LOGDETS) + d] += v;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace vggp

@@ -352,6 +352,7 @@ struct BinTask {
     const T* base;      // first value of this lane's first group
     int groups, nrun;
     bool valid;
+    i64 slot;           // 32 task + lane (deterministic mode: where this run's record goes)
 };
 
 // `first`: the warp's first task is its own global index -- no atomic.  (All resident warps asking one counter for their first
@@ -370,6 +371,7 @@ __device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lan
     }
     if (task >= (unsigned int)a.n_tasks) return false;
     const i64 slot = (i64)task * 32 + lane;
+    t.slot = slot;
     const uint32_t cell = __ldg(reinterpret_cast<const uint32_t*>(a.buf + a.off_run_cell) + slot);
     t.nrun = __ldg(reinterpret_cast<const int*>(a.buf + a.off_run_n) + slot);
     t.groups = __ldg(reinterpret_cast<const int*>(a.buf + a.off_task_R) + task) >> 2;
@@ -535,6 +537,199 @@ __global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_
 #pragma unroll
         for (int k = 0; k < 16; ++k) t += part[k][el];
         out[e] = t;
+    }
+}
+
+// ---- deterministic mode (vggp_set_deterministic) ----------------------------------------------------------
+// Floating-point atomics make the sums above depend on the order in which warps finish.  In deterministic mode a run does
+// not add anything: it writes its flush values as a RECORD (in the fixed order of the `add` calls of bin_lane_flush, then the
+// run's scalar term), and the reductions below sum the records in an order that depends only on the binned layout -- runs
+// sorted by their position in the cell-sorted stream -- so that two launches over the same buffer agree bit for bit whatever
+// the grid size, the work stealing or the machine load.
+template <int D> struct BinRec { static constexpr int v = (1 << D) + 6 * D + 1; };
+
+template <typename T>
+struct RecordAdder {
+    T* rec;
+    mutable int k;
+    __device__ __forceinline__ void operator()(T*, T v) const { rec[k++] = v; }
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(BIN_THREADS, (bin_min_blocks<T, D>()))
+k_obs_b1_binned_det(const __grid_constant__ BinnedArgs<T, D> a, T* __restrict__ rec) {
+    constexpr int R = BinRec<D>::v;
+    const int lane = threadIdx.x & 31;
+    BinLane<T, D> s;
+    BinTask<T, D> t;
+    bool first = true;
+    while (bin_next_task<T, D>(a, lane, s, t, first)) {
+        T xa[D][4], ya[4], xb[D][4], yb[4];
+        bin_load_group<T, D>(t.base, xa, ya);
+#pragma unroll 1
+        for (int gi = 0; gi < t.groups; gi += 2) {
+            if (gi + 1 < t.groups) bin_load_group<T, D>(t.base + (i64)(gi + 1) * ((D + 1) * 128), xb, yb);
+            bin_group<T, D>(s, xa, ya, t.nrun - 4 * gi);
+            if (gi + 2 < t.groups) bin_load_group<T, D>(t.base + (i64)(gi + 2) * ((D + 1) * 128), xa, ya);
+            if (gi + 1 < t.groups) bin_group<T, D>(s, xb, yb, t.nrun - 4 * (gi + 1));
+        }
+        if (t.valid) {
+            T* r = rec + t.slot * R;
+            const RecordAdder<T> add{r, 0};
+            const T e = bin_lane_flush<T, D>(a.geo, s, t.nrun, reinterpret_cast<const T*>(a.tables), a.galpha, a.gband, add);
+            r[R - 1] = e;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.gs[1] = a.n_real;
+}
+
+// sort keys of the run slots: position of the run in the cell-sorted stream; empty slots go to the end
+__global__ void __launch_bounds__(256) k_det_keys(const uint32_t* __restrict__ run_cell, const uint32_t* __restrict__ run_start,
+                                                  i64 nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    keys[i] = run_cell[i] != BIN_EMPTY ? run_start[i] : 0xffffffffu;
+    idx[i] = (uint32_t)i;
+}
+
+// [cell_first, cell_end) = positions in the sorted slot list of the runs of a cell (both zero-filled before: no runs)
+__global__ void __launch_bounds__(256) k_det_mark(const uint32_t* __restrict__ run_cell, const uint32_t* __restrict__ sorted_slot,
+                                                  i64 nslots, uint32_t* __restrict__ cell_first, uint32_t* __restrict__ cell_end) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const uint32_t c = run_cell[sorted_slot[i]];
+    if (c == BIN_EMPTY) return;
+    const uint32_t prev = i > 0 ? run_cell[sorted_slot[i - 1]] : BIN_EMPTY;
+    const uint32_t next = i + 1 < nslots ? run_cell[sorted_slot[i + 1]] : BIN_EMPTY;
+    if (prev != c) cell_first[c] = (uint32_t)i;
+    if (next != c) cell_end[c] = (uint32_t)(i + 1);
+}
+
+struct DetIndex {
+    const uint32_t* sorted_slot;
+    const uint32_t* cell_first;
+    const uint32_t* cell_end;
+};
+
+// d alpha: one thread per node sums the (up to 2^D) cells it is a corner of, cells in corner order, runs in stream order
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_det_alpha(const BinGeom<D> geo, const DetIndex ix, const T* __restrict__ rec,
+                                                   T* __restrict__ galpha, i64 M) {
+    constexpr int R = BinRec<D>::v;
+    const i64 node = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= M) return;
+    int idx[D];
+    {
+        i64 rem = node;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { idx[d] = (int)(rem / geo.stride[d]); rem -= (i64)idx[d] * geo.stride[d]; }
+    }
+    T acc = (T)0;
+#pragma unroll
+    for (int b = 0; b < (1 << D); ++b) {
+        bool ok = true;
+        i64 flat = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int c = idx[d] - ((b >> (D - 1 - d)) & 1);
+            ok = ok && c >= 0 && c <= geo.K[d] - 2;
+            flat = flat * (geo.K[d] - 1) + c;
+        }
+        if (!ok) continue;
+        const uint32_t e = ix.cell_end[flat];
+        for (uint32_t i = ix.cell_first[flat]; i < e; ++i) acc += rec[(i64)ix.sorted_slot[i] * R + b];
+    }
+    galpha[node] = acc;
+}
+
+// fixed-shape tree sum over a block of 256 threads of NV values per thread; result in thread 0
+template <typename A, int NV>
+__device__ __forceinline__ void det_block_sum(A (&v)[NV], A (*sh)[256]) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sh[j][threadIdx.x] = v[j];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = sh[j][0];
+    __syncthreads();
+}
+
+// band sums: CTA (d, c) sums the six band values of every run of the hyperplane of cells with index c in dimension d
+// (thread t takes the hyperplane's cells t, t + 256, ... in row-major order) -> S[(hoff_d + c) * 6 + j]
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_det_band(const BinGeom<D> geo, const DetIndex ix, const T* __restrict__ rec,
+                                                  T* __restrict__ S) {
+    constexpr int R = BinRec<D>::v;
+    __shared__ T sh[6][256];
+    int d = 0, c = (int)blockIdx.x, hoff = 0;
+    while (d + 1 < D && c >= geo.K[d] - 1) { c -= geo.K[d] - 1; hoff += geo.K[d] - 1; ++d; }
+    i64 plane = 1;
+#pragma unroll
+    for (int e = 0; e < D; ++e)
+        if (e != d) plane *= geo.K[e] - 1;
+    T v[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
+    for (i64 q = threadIdx.x; q < plane; q += 256) {
+        // q enumerates the other dimensions row-major; insert c at dimension d
+        i64 rem = q, flat = 0, mul = 1;
+#pragma unroll
+        for (int e = D - 1; e >= 0; --e) {
+            int ce;
+            if (e == d) ce = c;
+            else { ce = (int)(rem % (geo.K[e] - 1)); rem /= geo.K[e] - 1; }
+            flat += (i64)ce * mul;
+            mul *= geo.K[e] - 1;
+        }
+        const uint32_t en = ix.cell_end[flat];
+        for (uint32_t i = ix.cell_first[flat]; i < en; ++i) {
+            const T* r = rec + (i64)ix.sorted_slot[i] * R + (1 << D) + 6 * d;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] += r[j];
+        }
+    }
+    det_block_sum<T, 6>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) S[(i64)(hoff + c) * 6 + j] = v[j];
+    }
+}
+
+// last step, one CTA: the band block from the hyperplane sums (same destinations as the adds of bin_lane_flush), the scalar
+// term (double, slots in order), the sum y^2 of the observations outside the mesh, and the reset of the task counter
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_det_final(const BinGeom<D> geo, const T* __restrict__ S, const T* __restrict__ rec,
+                                                   const uint32_t* __restrict__ run_cell, i64 nslots, T* __restrict__ gband,
+                                                   double* __restrict__ gs, const unsigned char* __restrict__ buf,
+                                                   unsigned int* __restrict__ counter) {
+    constexpr int R = BinRec<D>::v;
+    __shared__ double sh[1][256];
+    int hoff = 0;
+    for (int d = 0; d < D; ++d) {
+        const int n = geo.K[d], nc = n - 1;
+        T* gb = gband + geo.band_off[d];
+        for (int i = threadIdx.x; i < n; i += 256) {
+            const T* lo = S + (i64)(hoff + i) * 6;          // cell i (i < nc)
+            const T* hi = S + (i64)(hoff + i - 1) * 6;      // cell i - 1 (i > 0)
+            T pd = (T)0, qd = (T)0;
+            if (i < nc) { pd = lo[0]; qd = lo[3]; gb[n + i] = lo[1]; gb[3 * n + i] = lo[4]; }
+            if (i > 0) { pd += hi[2]; qd += hi[5]; }
+            gb[i] = pd;
+            gb[2 * n + i] = qd;
+        }
+        hoff += nc;
+    }
+    double e[1] = {0.0};
+    for (i64 i = threadIdx.x; i < nslots; i += 256)
+        if (run_cell[i] != BIN_EMPTY) e[0] += (double)rec[i * R + R - 1];
+    det_block_sum<double, 1>(e, sh);
+    if (threadIdx.x == 0) {
+        gs[0] = e[0] + *reinterpret_cast<const double*>(buf);
+        *counter = 0u;
     }
 }
 

@@ -127,6 +127,11 @@ struct vggp_plan {
     bool k1_gev_captured = false;
     double* b1_acc = nullptr; int b1_acc_total = 0;      // structured == 3: band accumulators of dK_d, [3][n_d] per dimension
     cudaStream_t last_stream = nullptr;                  // stream of the last grid forward (on-demand workspace fills)
+    // deterministic mode (vggp_set_deterministic): run records + sort scratch of the per-observation kernel, per-CTA partials
+    // of the fibre passes; both grown on demand (the first deterministic step must not run inside a stream capture)
+    int det = 0;
+    void* det_buf = nullptr; size_t det_bytes = 0;
+    double* det_fp = nullptr; size_t det_fp_elems = 0;
     void* band_rep = nullptr;              // B1 family, binned kernel: BAND_REPLICAS copies of the band block (obs dtype), kept zero
                                            // between launches (k_band_reduce clears what it sums)
     // schedules
@@ -638,6 +643,7 @@ void fp_pass_init(const vggp_plan* p, FpPass& P, const double* theta, double ell
     P.dbg = g_fp_dbg;
 }
 
+int det_reserve(void** buf, size_t* have, size_t want, cudaStream_t st);
 int g_fp_fast = 1;                   // use k_fibre_pass_fast where it applies (M_d <= 512); 0: always the generic kernel (cross-check)
 
 int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
@@ -661,11 +667,22 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
         tiles += t.ntiles;
     }
     const int ti = p->obs_dtype == VGGP_F32 ? 0 : 1;
+    if (p->det) {
+        if (!fast) return fail(VGGP_E_UNSUPPORTED, "deterministic mode needs the fast fibre engine (M_d <= 512)");
+        void* buf = p->det_fp; size_t have = p->det_fp_elems * sizeof(double);
+        if (int rc = det_reserve(&buf, &have, (size_t)tiles * FP_DET_SLOT * sizeof(double), st)) { p->det_fp = nullptr; p->det_fp_elems = 0; return rc; }
+        p->det_fp = reinterpret_cast<double*>(buf); p->det_fp_elems = have / sizeof(double);
+        P.det = p->det_fp;
+    }
     if (fast) {
         if (int rc = ti == 0 ? raise_dyn_smem(k_fibre_pass_fast<float>, smem_fast) : raise_dyn_smem(k_fibre_pass_fast<double>, smem_fast)) return rc;
         if (ti == 0) k_fibre_pass_fast<float><<<tiles, FP_THREADS, smem_fast, st>>>(P);
         else k_fibre_pass_fast<double><<<tiles, FP_THREADS, smem_fast, st>>>(P);
         VGGP_LAUNCH_CHECK();
+        if (P.det) {
+            k_fp_det_reduce<<<P.D, 256, 0, st>>>(P);
+            VGGP_LAUNCH_CHECK();
+        }
         return 0;
     }
     if (int rc = ti == 0 ? raise_dyn_smem(k_fibre_pass<float>, smem) : raise_dyn_smem(k_fibre_pass<double>, smem)) return rc;
@@ -1233,7 +1250,102 @@ int bin_prepare_dispatch(vggp_plan* p, const void* const* x, i64 n, int cap, vgg
 int bin_pack_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* const* x, const void* y, void* binned, cudaStream_t st) {
     VGGP_DISPATCH_TD(p, bin_pack_impl, p, desc, x, y, binned, st);
 }
+// grow-only scratch (never inside a stream capture: cudaMalloc is not capturable)
+int det_reserve(void** buf, size_t* have, size_t want, cudaStream_t st) {
+    if (*have >= want) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive)
+        return fail(VGGP_E_UNSUPPORTED, "deterministic mode: run one eager step before capturing a graph (its scratch is sized at first use)");
+    VGGP_CUDA(cudaStreamSynchronize(st));
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    VGGP_CUDA(cudaMalloc(buf, want));
+    *have = want;
+    return 0;
+}
+
+// Deterministic variant of launch_obs_binned: records, then reductions in an order fixed by the binned layout (obs_binned.cuh).
+template <typename T, int D>
+int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    constexpr int R = BinRec<D>::v;
+    const i64 nslots = (i64)desc->n_tasks * 32;
+    i64 ncells = 1, nplanes = 0;
+    for (int d = 0; d < D; ++d) { ncells *= p->K[d] - 1; nplanes += p->K[d] - 1; }
+    if (nslots >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "deterministic mode: too many runs");
+    size_t temp_bytes = 0;
+    {
+        const uint32_t* k = nullptr; uint32_t* ko = nullptr;
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, k, ko, k, ko, (int)nslots, 0, 32, st));
+    }
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o_rec = 0, o_k0 = al(o_rec + sizeof(T) * (size_t)nslots * R), o_k1 = al(o_k0 + 4 * (size_t)nslots),
+                 o_i0 = al(o_k1 + 4 * (size_t)nslots), o_i1 = al(o_i0 + 4 * (size_t)nslots), o_cf = al(o_i1 + 4 * (size_t)nslots),
+                 o_ce = al(o_cf + 4 * (size_t)ncells), o_S = al(o_ce + 4 * (size_t)ncells), o_tmp = al(o_S + sizeof(T) * 6 * (size_t)nplanes),
+                 total_bytes = al(o_tmp + temp_bytes);
+    if (int rc = det_reserve(&p->det_buf, &p->det_bytes, total_bytes, st)) return rc;
+    unsigned char* base = reinterpret_cast<unsigned char*>(p->det_buf);
+    T* rec = reinterpret_cast<T*>(base + o_rec);
+    uint32_t *k0 = reinterpret_cast<uint32_t*>(base + o_k0), *k1 = reinterpret_cast<uint32_t*>(base + o_k1),
+             *i0 = reinterpret_cast<uint32_t*>(base + o_i0), *i1 = reinterpret_cast<uint32_t*>(base + o_i1),
+             *cf = reinterpret_cast<uint32_t*>(base + o_cf), *ce = reinterpret_cast<uint32_t*>(base + o_ce);
+    T* S = reinterpret_cast<T*>(base + o_S);
+    if (p->bin_blocks_per_sm[0] == 0) {
+        int nb = 0;
+        VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, 0));
+        p->bin_blocks_per_sm[0] = nb < 1 ? 1 : nb;
+    }
+    BinnedArgs<T, D> a;
+    for (int d = 0; d < D; ++d) {
+        a.geo.K[d] = p->K[d];
+        a.geo.stride[d] = (int)p->stride[d];
+        a.geo.band_off[d] = p->band_off[d];
+        a.geo.tab_off[d] = p->tab_off[d];
+        a.geo.knot_off[d] = p->knot_off[d];
+    }
+    a.buf = reinterpret_cast<const unsigned char*>(binned);
+    a.off_task_off = desc->off_task_off; a.off_task_R = desc->off_task_R; a.off_run_cell = desc->off_run_cell;
+    a.off_run_n = desc->off_run_n; a.off_data = desc->off_data;
+    a.n_tasks = (int)desc->n_tasks;
+    a.knots_byte_off = p->knots_byte_off;
+    a.tables = p->tables;
+    a.alpha = reinterpret_cast<const T*>(p->alphaT);
+    T* gb = reinterpret_cast<T*>(gbuf);
+    a.galpha = gb;
+    a.gband = gb + p->M;
+    a.n_rep = 1;
+    a.band_rep_stride = 0;
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    a.gs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(gbuf) + soff);
+    a.n_real = (double)desc->n;
+    a.counter = p->obs_counter + 1;
+    i64 blocks = (desc->n_tasks + BIN_WARPS - 1) / BIN_WARPS;
+    blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[0]));
+    const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + desc->off_run_cell);
+    const uint32_t* run_start = reinterpret_cast<const uint32_t*>(a.buf + desc->off_run_start);
+    k1_mark(p, 0, st);
+    k_obs_b1_binned_det<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a, rec);
+    k1_mark(p, 1, st);
+    VGGP_LAUNCH_CHECK();
+    k_det_keys<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, run_start, nslots, k0, i0);
+    VGGP_LAUNCH_CHECK();
+    VGGP_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, (const uint32_t*)k0, k1, (const uint32_t*)i0, i1, (int)nslots, 0, 32, st));
+    VGGP_CUDA(cudaMemsetAsync(cf, 0, (o_S - o_cf), st));
+    k_det_mark<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, i1, nslots, cf, ce);
+    VGGP_LAUNCH_CHECK();
+    DetIndex ix;
+    ix.sorted_slot = i1; ix.cell_first = cf; ix.cell_end = ce;
+    k_det_alpha<T, D><<<ceil_div(p->M, 256), 256, 0, st>>>(a.geo, ix, rec, a.galpha, p->M);
+    VGGP_LAUNCH_CHECK();
+    k_det_band<T, D><<<(unsigned)nplanes, 256, 0, st>>>(a.geo, ix, rec, S);
+    VGGP_LAUNCH_CHECK();
+    k_det_final<T, D><<<1, 256, 0, st>>>(a.geo, S, rec, run_cell, nslots, a.gband, a.gs, a.buf, a.counter);
+    VGGP_LAUNCH_CHECK();
+    return 0;
+}
+
 int obs_binned_dispatch(vggp_plan* p, const vggp_binned_desc* desc, const void* binned, void* gbuf, cudaStream_t st) {
+    if (p->det) { VGGP_DISPATCH_TD(p, launch_obs_binned_det, p, desc, binned, gbuf, st); }
     VGGP_DISPATCH_TD(p, launch_obs_binned, p, desc, binned, gbuf, st);
 }
 
@@ -1753,6 +1865,17 @@ int vggp_set_binned_stream(int mode) {
     return 0;
 }
 
+int vggp_set_deterministic(vggp_plan* p, int on) {
+    if (!p) return fail(VGGP_E_ARG, "null plan");
+    if (on && !(p->family == VGGP_B1_ASVGP && p->g.structured == 3))
+        return fail(VGGP_E_UNSUPPORTED, "deterministic mode covers the B1 (ASVGP) family on its default fused grid path");
+    if (on)
+        for (int d = 0; d < p->D; ++d)
+            if (p->n[d] > 512) return fail(VGGP_E_UNSUPPORTED, "deterministic mode needs M_d <= 512");
+    p->det = on ? 1 : 0;
+    return 0;
+}
+
 int vggp_set_b1_structured(int on) {
     g_b1_structured = on < 0 ? 0 : (on > 3 ? 3 : on);
     return 0;
@@ -1941,6 +2064,8 @@ int vggp_plan_destroy(vggp_plan* p) {
         if (p->pk_x[d]) cudaFree(p->pk_x[d]);
     if (p->pk_y) cudaFree(p->pk_y);
     if (p->bin_perm) cudaFree(p->bin_perm);
+    if (p->det_buf) cudaFree(p->det_buf);
+    if (p->det_fp) cudaFree(p->det_fp);
     for (auto& e : p->k1_ev) cudaEventDestroy(e);
     for (auto& e : p->k1_gev) if (e) cudaEventDestroy(e);
     for (auto& e : p->st_ev) cudaEventDestroy(e);
@@ -2069,6 +2194,7 @@ int vggp_obs_pack(vggp_plan* p, const void* const* x, const void* y, int64_t n, 
 
 int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp, int64_t n, void* gbuf, void* stream) {
     DeviceGuard dev_guard(p ? p->device : -1);
+    if (p && p->det) return fail(VGGP_E_UNSUPPORTED, "deterministic mode takes the binned layout (vggp_obs_fwd_bwd_binned)");
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!xp || !yp)) return fail(VGGP_E_ARG, "null observation pointers");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2085,6 +2211,7 @@ int vggp_obs_fwd_bwd_packed(vggp_plan* p, const void* const* xp, const void* yp,
 
 int vggp_obs_fwd_bwd(vggp_plan* p, const void* const* x, const void* y, int64_t n, void* gbuf, void* stream) {
     DeviceGuard dev_guard(p ? p->device : -1);
+    if (p && p->det) return fail(VGGP_E_UNSUPPORTED, "deterministic mode takes the binned layout (vggp_obs_fwd_bwd_binned)");
     if (!p || !gbuf || n < 0) return fail(VGGP_E_ARG, "bad argument");
     if (n > 0 && (!x || !y)) return fail(VGGP_E_ARG, "null observation pointers");
     if (n == 0 || p->family != VGGP_B1_ASVGP) {

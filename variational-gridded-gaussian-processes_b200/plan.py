@@ -294,6 +294,10 @@ class GridPlan:
                 gs.outs = self.grid_backward(theta, m, L, ell_scale)
         return gs
 
+    def set_deterministic(self, on: bool = True):
+        """Bitwise run-to-run reproducible steps (vggp_set_deterministic): B1 family, binned layout, M_d <= 512."""
+        _lib.check(self.lib.vggp_set_deterministic(self.handle, 1 if on else 0))
+
     def k1_timing(self, enable: bool = True):
         """Start / stop the library's own device timing of the per-observation kernel (vggp_k1_timing)."""
         _lib.check(self.lib.vggp_k1_timing(self.handle, 1 if enable else 0))
