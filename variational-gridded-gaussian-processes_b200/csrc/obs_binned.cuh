@@ -353,12 +353,23 @@ struct BinTask {
     int groups, nrun;
     bool valid;
     i64 slot;           // 32 task + lane (deterministic mode: where this run's record goes)
+    uint32_t cell;      // flat cell id of the run (0 for an empty slot)
 };
+
+// cell constants of the task's run (tables and alpha corners from L2).  The LDG kernel calls it AFTER it has issued the loads of
+// the run's first group, so that the two round trips overlap instead of queueing behind each other at every task switch.
+template <typename T, int D>
+__device__ __forceinline__ void bin_task_enter(const BinnedArgs<T, D>& a, BinLane<T, D>& s, const BinTask<T, D>& t) {
+    int c[D];
+    bin_decode_cell<D>(t.cell, a.geo.K, c);
+    bin_lane_enter<T, D>(a.geo, s, c, reinterpret_cast<const T*>(a.tables),
+                         reinterpret_cast<const float*>(a.tables + a.knots_byte_off), a.alpha);
+}
 
 // `first`: the warp's first task is its own global index -- no atomic.  (All resident warps asking one counter for their first
 // task at kernel start serialise on a single L2 address: ~3500 same-address atomics, the ~12 us that separated the kernel from
 // the roofline at every problem size.)  Later tasks come from the counter, offset by the number of warps of the launch.
-template <typename T, int D>
+template <typename T, int D, bool ENTER = true>
 __device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lane, BinLane<T, D>& s, BinTask<T, D>& t, bool& first) {
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
     unsigned int task = 0;
@@ -377,10 +388,8 @@ __device__ __forceinline__ bool bin_next_task(const BinnedArgs<T, D>& a, int lan
     t.groups = __ldg(reinterpret_cast<const int*>(a.buf + a.off_task_R) + task) >> 2;
     t.base = reinterpret_cast<const T*>(a.buf + a.off_data) + __ldg(reinterpret_cast<const i64*>(a.buf + a.off_task_off) + task) + lane * 4;
     t.valid = cell != BIN_EMPTY;
-    int c[D];
-    bin_decode_cell<D>(t.valid ? cell : 0u, a.geo.K, c);
-    bin_lane_enter<T, D>(a.geo, s, c, reinterpret_cast<const T*>(a.tables),
-                         reinterpret_cast<const float*>(a.tables + a.knots_byte_off), a.alpha);
+    t.cell = t.valid ? cell : 0u;
+    if (ENTER) bin_task_enter<T, D>(a, s, t);
     return true;
 }
 
@@ -410,11 +419,12 @@ k_obs_b1_binned(const __grid_constant__ BinnedArgs<T, D> a) {
     T* const gband = a.gband + (i64)(blockIdx.x % (unsigned)a.n_rep) * a.band_rep_stride;
     // persistent warps: tasks are ordered longest first and handed out from a global counter (LPT scheduling)
     bool first = true;
-    while (bin_next_task<T, D>(a, lane, s, t, first)) {
+    while (bin_next_task<T, D, false>(a, lane, s, t, first)) {
         // the loads of the next group of 4 observations are in flight while the current one is processed (no buffer
         // rotation: the loop body handles two groups)
         T xa[D][4], ya[4], xb[D][4], yb[4];
         bin_load_group<T, D>(t.base, xa, ya);
+        bin_task_enter<T, D>(a, s, t);
 #pragma unroll 1
         for (int gi = 0; gi < t.groups; gi += 2) {
             if (gi + 1 < t.groups) bin_load_group<T, D>(t.base + (i64)(gi + 1) * ((D + 1) * 128), xb, yb);
