@@ -106,7 +106,10 @@ def test_fast_and_generic_fibre_kernels_agree_under_emulation(emu):
     """k_fibre_pass_fast (M_d <= 512, the default) against the generic k_fibre_pass on the same step (2-D and 3-D, sizes that
     leave partial tiles, partial lanes and absent fibres)."""
     lib, L = emu
-    for knots, N in (((37, 50), 1200), ((21, 13, 18), 900), ((300,), 700), ((70, 130), 1500), ((9, 200, 33), 1500)):
+    # the power-of-two meshes fill their window of the 512-slot row exactly: full tiles take the SIMPLE specialisation of
+    # ff_pass_body (validity = slot < 512, addresses in arithmetic progression), partial ones the general form
+    for knots, N in (((37, 50), 1200), ((21, 13, 18), 900), ((300,), 700), ((70, 130), 1500), ((9, 200, 33), 1500),
+                     ((64, 128), 1500), ((16, 64, 8), 900), ((512,), 700), ((64, 9), 700)):
         D = len(knots)
         meshes, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=5 + D)
         theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()

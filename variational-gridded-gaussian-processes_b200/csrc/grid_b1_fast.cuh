@@ -119,16 +119,12 @@ __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_constant__ FpPass P) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    __shared__ double red[32];
-    int ti = 0;
-    while (ti + 1 < P.ntasks && (int)blockIdx.x >= P.t[ti + 1].tile0) ++ti;
-    const FpTask& tk = P.t[ti];
-    const int tile = (int)blockIdx.x - tk.tile0;
-    if (tile >= tk.ntiles) return;
-    if (tk.kind == FP_QROW) { fp_qrow<T>(P, tk, tile); return; }
+// SIMPLE: every slot of the tile is a live element -- n fills its window exactly (n == npad: 64, 128, 256, 512) and the tile
+// holds all its fibres -- and the per-stage address step fits 32 bits.  Validity is then `slot < 512` and the address an
+// arithmetic progression, which removes most of the integer work that dominated the big passes (ncu, round 2, 3-D backward
+// pass: 37 M warp instructions of which 13 % were float64 arithmetic and over half index / predicate arithmetic).
+template <typename T, bool SIMPLE>
+__device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, const int tile, unsigned char* smraw, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = tk.n, d = tk.d, kind = tk.kind;
     double* pd = reinterpret_cast<double*>(smraw);
@@ -180,9 +176,10 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
     }
     const int xrow = f * FF_PITCH;
     const i64 nfib = tk.nfib;
+    const int da32 = (int)da;
 #define FF_SLOT(u) (s0 + (u) * ds)
-#define FF_OK(u) (FF_SLOT(u) < 512 && (FF_SLOT(u) & mask) < n && fid0 + (i64)((FF_SLOT(u) >> lg) * fstep) < nfib)
-#define FF_GA(u) (a0 + (u) * da - (i64)((FF_SLOT(u) >> lg) * gap))
+#define FF_OK(u) (FF_SLOT(u) < 512 && (SIMPLE || ((FF_SLOT(u) & mask) < n && fid0 + (i64)((FF_SLOT(u) >> lg) * fstep) < nfib)))
+#define FF_GA(u) (SIMPLE ? a0 + (i64)((u) * da32) : a0 + (u) * da - (i64)((FF_SLOT(u) >> lg) * gap))
 #define FF_SO(u) (xrow + ff_p(FF_SLOT(u)))
     // R / DL tasks (pk == 0, strided in the factor): column k = fib0 + f, rows i0 + u di
     const int i0 = s0, di = ds;
@@ -396,6 +393,31 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
 #undef FF_OK
 #undef FF_GA
 #undef FF_SO
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_constant__ FpPass P) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double red[32];
+    int ti = 0;
+    while (ti + 1 < P.ntasks && (int)blockIdx.x >= P.t[ti + 1].tile0) ++ti;
+    const FpTask& tk = P.t[ti];
+    const int tile = (int)blockIdx.x - tk.tile0;
+    if (tile >= tk.ntiles) return;
+    if (tk.kind == FP_QROW) { fp_qrow<T>(P, tk, tile); return; }
+    // uniform over the CTA
+    const int kind = tk.kind;
+    bool simple = false;
+    if (kind == FP_PROD || kind == FP_ALPHA || kind == FP_DM || kind == FP_GA || kind == FP_GAONLY) {
+        const int nsrc = (kind == FP_GA) ? FF_F / 2 : FF_F;
+        const int npad = 512 >> tk.pk;
+        const i64 per_tile = (i64)nsrc << tk.pk;
+        const i64 step = (tk.inner == 1) ? (i64)(FP_THREADS >> (kind == FP_GA ? 2 : 3))
+                                         : (i64)(FP_THREADS >> ((kind == FP_GA ? 2 : 3) + tk.pk)) * tk.inner;
+        simple = tk.n == npad && (i64)(tile + 1) * per_tile <= tk.nfib && step * 16 < ((i64)1 << 31);
+    }
+    if (simple) ff_pass_body<T, true>(P, tk, tile, smraw, red);
+    else ff_pass_body<T, false>(P, tk, tile, smraw, red);
 }
 
 // Deterministic mode: sum the per-CTA partials of the pass that just ran, tiles in order, into the accumulators the atomics
