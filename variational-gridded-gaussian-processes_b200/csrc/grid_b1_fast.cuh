@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
 }
 
 // Deterministic mode: sum the per-CTA partials of the pass that just ran, tiles in order, into the accumulators the atomics
-// would have hit.  grid (D): CTA d walks the tasks of dimension d in task order (two tasks of a pass may feed the same band).
+// would have hit.  grid (D, FP_DET_YB): CTA (d, y) walks the tasks of dimension d in task order (two tasks of a pass may feed
+// the same band); a band element is owned by exactly one thread of one CTA, the scalar sums by CTA (d, 0).
+constexpr int FP_DET_YB = 6;        // 6 x 256 threads = one thread per band element at n = 512
 __global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ FpPass P) {
     const int d = blockIdx.x;
     for (int ti = 0; ti < P.ntasks; ++ti) {
@@ -430,13 +432,22 @@ __global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ F
         const int n = tk.n, kind = tk.kind;
         const double* base = P.det + (i64)tk.tile0 * FP_DET_SLOT;
         if (kind == FP_GA || kind == FP_GAONLY || kind == FP_DL) {
-            for (int e = threadIdx.x; e < 3 * n; e += 256) {
+            for (int e = blockIdx.y * 256 + threadIdx.x; e < 3 * n; e += 256 * FP_DET_YB) {
                 const int k = e / n, i = e - k * n;
                 if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
+                const double* src = base + FP_DET_BAND + k * 512 + i;
                 double v = 0.0;
-                for (int t = 0; t < tk.ntiles; ++t) v += base[(i64)t * FP_DET_SLOT + FP_DET_BAND + k * 512 + i];
+                int t = 0;
+                for (; t + 4 <= tk.ntiles; t += 4) {        // four loads in flight, added in tile order
+                    const double a0 = src[(i64)t * FP_DET_SLOT], a1 = src[(i64)(t + 1) * FP_DET_SLOT];
+                    const double a2 = src[(i64)(t + 2) * FP_DET_SLOT], a3 = src[(i64)(t + 3) * FP_DET_SLOT];
+                    v += a0; v += a1; v += a2; v += a3;
+                }
+                for (; t < tk.ntiles; ++t) v += src[(i64)t * FP_DET_SLOT];
                 P.acc[d][e] += v;
             }
+        } else if (blockIdx.y != 0) {
+            continue;
         } else if (kind == FP_ALPHA) {
             if (threadIdx.x == 0) {
                 double v = 0.0;
@@ -451,7 +462,6 @@ __global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ F
                 P.sc[(threadIdx.x == 0 ? SC_TR : SC_LOGDETS) + d] += v;
             }
         }
-        __syncthreads();
     }
 }
 

@@ -709,15 +709,29 @@ __global__ void __launch_bounds__(256) k_det_band(const BinGeom<D> geo, const De
     }
 }
 
-// last step, one CTA: the band block from the hyperplane sums (same destinations as the adds of bin_lane_flush), the scalar
-// term (double, slots in order), the sum y^2 of the observations outside the mesh, and the reset of the task counter
+// scalar term: CTA b sums the records of a fixed contiguous range of slots (thread t takes slots t, t + 256, ... of the range;
+// fixed-shape tree) -> E[b]; the ranges and the order in which k_det_final adds E[0 .. DET_EBLOCKS) depend on nslots only
+constexpr int DET_EBLOCKS = 128;
 template <typename T, int D>
-__global__ void __launch_bounds__(256) k_det_final(const BinGeom<D> geo, const T* __restrict__ S, const T* __restrict__ rec,
-                                                   const uint32_t* __restrict__ run_cell, i64 nslots, T* __restrict__ gband,
-                                                   double* __restrict__ gs, const unsigned char* __restrict__ buf,
-                                                   unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(256) k_det_escal(const T* __restrict__ rec, const uint32_t* __restrict__ run_cell, i64 nslots,
+                                                   double* __restrict__ E) {
     constexpr int R = BinRec<D>::v;
     __shared__ double sh[1][256];
+    const i64 chunk = (nslots + DET_EBLOCKS - 1) / DET_EBLOCKS;
+    const i64 lo = (i64)blockIdx.x * chunk, hi = lo + chunk < nslots ? lo + chunk : nslots;
+    double e[1] = {0.0};
+    for (i64 i = lo + threadIdx.x; i < hi; i += 256)
+        if (run_cell[i] != BIN_EMPTY) e[0] += (double)rec[i * R + R - 1];
+    det_block_sum<double, 1>(e, sh);
+    if (threadIdx.x == 0) E[blockIdx.x] = e[0];
+}
+
+// last step, one CTA: the band block from the hyperplane sums (same destinations as the adds of bin_lane_flush), the scalar
+// term from the partial sums of k_det_escal, the sum y^2 of the observations outside the mesh, and the reset of the task counter
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_det_final(const BinGeom<D> geo, const T* __restrict__ S, const double* __restrict__ E,
+                                                   T* __restrict__ gband, double* __restrict__ gs,
+                                                   const unsigned char* __restrict__ buf, unsigned int* __restrict__ counter) {
     int hoff = 0;
     for (int d = 0; d < D; ++d) {
         const int n = geo.K[d], nc = n - 1;
@@ -733,12 +747,10 @@ __global__ void __launch_bounds__(256) k_det_final(const BinGeom<D> geo, const T
         }
         hoff += nc;
     }
-    double e[1] = {0.0};
-    for (i64 i = threadIdx.x; i < nslots; i += 256)
-        if (run_cell[i] != BIN_EMPTY) e[0] += (double)rec[i * R + R - 1];
-    det_block_sum<double, 1>(e, sh);
     if (threadIdx.x == 0) {
-        gs[0] = e[0] + *reinterpret_cast<const double*>(buf);
+        double e = 0.0;
+        for (int b = 0; b < DET_EBLOCKS; ++b) e += E[b];
+        gs[0] = e + *reinterpret_cast<const double*>(buf);
         *counter = 0u;
     }
 }

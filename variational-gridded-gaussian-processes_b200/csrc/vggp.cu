@@ -680,7 +680,7 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
         else k_fibre_pass_fast<double><<<tiles, FP_THREADS, smem_fast, st>>>(P);
         VGGP_LAUNCH_CHECK();
         if (P.det) {
-            k_fp_det_reduce<<<P.D, 256, 0, st>>>(P);
+            k_fp_det_reduce<<<dim3(P.D, FP_DET_YB), 256, 0, st>>>(P);
             VGGP_LAUNCH_CHECK();
         }
         return 0;
@@ -1280,7 +1280,7 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t o_rec = 0, o_k0 = al(o_rec + sizeof(T) * (size_t)nslots * R), o_k1 = al(o_k0 + 4 * (size_t)nslots),
                  o_i0 = al(o_k1 + 4 * (size_t)nslots), o_i1 = al(o_i0 + 4 * (size_t)nslots), o_cf = al(o_i1 + 4 * (size_t)nslots),
-                 o_ce = al(o_cf + 4 * (size_t)ncells), o_S = al(o_ce + 4 * (size_t)ncells), o_tmp = al(o_S + sizeof(T) * 6 * (size_t)nplanes),
+                 o_ce = al(o_cf + 4 * (size_t)ncells), o_S = al(o_ce + 4 * (size_t)ncells), o_E = al(o_S + sizeof(T) * 6 * (size_t)nplanes), o_tmp = al(o_E + sizeof(double) * DET_EBLOCKS),
                  total_bytes = al(o_tmp + temp_bytes);
     if (int rc = det_reserve(&p->det_buf, &p->det_bytes, total_bytes, st)) return rc;
     unsigned char* base = reinterpret_cast<unsigned char*>(p->det_buf);
@@ -1289,6 +1289,7 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
              *i0 = reinterpret_cast<uint32_t*>(base + o_i0), *i1 = reinterpret_cast<uint32_t*>(base + o_i1),
              *cf = reinterpret_cast<uint32_t*>(base + o_cf), *ce = reinterpret_cast<uint32_t*>(base + o_ce);
     T* S = reinterpret_cast<T*>(base + o_S);
+    double* E = reinterpret_cast<double*>(base + o_E);
     if (p->bin_blocks_per_sm[0] == 0) {
         int nb = 0;
         VGGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_obs_b1_binned<T, D>, BIN_THREADS, 0));
@@ -1339,7 +1340,9 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
     VGGP_LAUNCH_CHECK();
     k_det_band<T, D><<<(unsigned)nplanes, 256, 0, st>>>(a.geo, ix, rec, S);
     VGGP_LAUNCH_CHECK();
-    k_det_final<T, D><<<1, 256, 0, st>>>(a.geo, S, rec, run_cell, nslots, a.gband, a.gs, a.buf, a.counter);
+    k_det_escal<T, D><<<DET_EBLOCKS, 256, 0, st>>>(rec, run_cell, nslots, E);
+    VGGP_LAUNCH_CHECK();
+    k_det_final<T, D><<<1, 256, 0, st>>>(a.geo, S, E, a.gband, a.gs, a.buf, a.counter);
     VGGP_LAUNCH_CHECK();
     return 0;
 }
