@@ -29,6 +29,7 @@ __device__ __forceinline__ int ff_p(int i) { return i + (i >> 4); }
 
 // one warp, one fibre (see fp_fibre): X holds x_i on entry and y_i = (P x)_i on exit; pd / rl / rup are padded with the
 // identity (0, 1, 1) past n and rup[p(i)] = ru[i - 1] (0 for i = 0)
+template <bool FULLWIN = false>
 __device__ __forceinline__ void ff_fibre(const double* __restrict__ pd, const double* __restrict__ rl,
                                          const double* __restrict__ rup, double* __restrict__ X, int lane, int n, int mask) {
     const int p0 = lane * FF_LS;
@@ -70,7 +71,7 @@ __device__ __forceinline__ void ff_fibre(const double* __restrict__ pd, const do
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const double r = rl[p0 + j];
-        if (((i0 + j) & mask) < n) X[p0 + j] = sv[j] + l + uu[j];
+        if (FULLWIN || ((i0 + j) & mask) < n) X[p0 + j] = sv[j] + l + uu[j];
         l = fma(r, l, r * sv[j]);
     }
 }
@@ -123,7 +124,7 @@ __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const
 // holds all its fibres -- and the per-stage address step fits 32 bits.  Validity is then `slot < 512` and the address an
 // arithmetic progression, which removes most of the integer work that dominated the big passes (ncu, round 2, 3-D backward
 // pass: 37 M warp instructions of which 13 % were float64 arithmetic and over half index / predicate arithmetic).
-template <typename T, bool SIMPLE>
+template <typename T, bool SIMPLE, int NU>
 __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, const int tile, unsigned char* smraw, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = tk.n, d = tk.d, kind = tk.kind;
@@ -177,10 +178,12 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
     const int xrow = f * FF_PITCH;
     const i64 nfib = tk.nfib;
     const int da32 = (int)da;
+    const int so0 = xrow + ff_p(s0), dso = ds + (ds >> 4);      // SIMPLE: ds is a multiple of 16, so the padded position is affine in u
 #define FF_SLOT(u) (s0 + (u) * ds)
-#define FF_OK(u) (FF_SLOT(u) < 512 && (SIMPLE || ((FF_SLOT(u) & mask) < n && fid0 + (i64)((FF_SLOT(u) >> lg) * fstep) < nfib)))
+#define FF_IN(u) (SIMPLE ? ((u) < NU) : (FF_SLOT(u) < 512))
+#define FF_OK(u) (SIMPLE ? ((u) < NU) : (FF_SLOT(u) < 512 && (FF_SLOT(u) & mask) < n && fid0 + (i64)((FF_SLOT(u) >> lg) * fstep) < nfib))
 #define FF_GA(u) (SIMPLE ? a0 + (i64)((u) * da32) : a0 + (u) * da - (i64)((FF_SLOT(u) >> lg) * gap))
-#define FF_SO(u) (xrow + ff_p(FF_SLOT(u)))
+#define FF_SO(u) (SIMPLE ? so0 + (u) * dso : xrow + ff_p(FF_SLOT(u)))
     // R / DL tasks (pk == 0, strided in the factor): column k = fib0 + f, rows i0 + u di
     const int i0 = s0, di = ds;
     const bool live = fib0 + f < nfib;
@@ -242,7 +245,7 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
 #pragma unroll
             for (int u8 = 0; u8 < 8; ++u8) {
                 const int u = h * 8 + u8;
-                if (FF_SLOT(u) < 512) {                // all 512 slots are written: zeros past n and for absent fibres
+                if (FF_IN(u)) {                        // all 512 slots are written: zeros past n and for absent fibres
                     const double gg = cg * gv[u8], hh = gg - 0.5 * mv[u8];
                     if (both) {
                         X[FF_SO(u)] = gg;
@@ -264,7 +267,7 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
         }
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (FF_SLOT(u) < 512) Cx[FF_SO(u)] = v[u];
+            if (FF_IN(u)) Cx[FF_SO(u)] = v[u];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = tid + u * FP_THREADS;
@@ -273,7 +276,7 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
     } else {
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (FF_SLOT(u) < 512) X[FF_SO(u)] = v[u];
+            if (FF_IN(u)) X[FF_SO(u)] = v[u];
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -302,7 +305,7 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
         __syncthreads();
     }
     // ---- recurrences: one warp per fibre
-    ff_fibre(pd, rl, rup, X + warp * FF_PITCH, lane, n, mask);
+    ff_fibre<SIMPLE>(pd, rl, rup, X + warp * FF_PITCH, lane, n, mask);
     __syncthreads();
     // ---- epilogues
     switch (kind) {
@@ -390,6 +393,7 @@ __device__ __forceinline__ void ff_pass_body(const FpPass& P, const FpTask& tk, 
         default: break;
     }
 #undef FF_SLOT
+#undef FF_IN
 #undef FF_OK
 #undef FF_GA
 #undef FF_SO
@@ -414,10 +418,14 @@ __global__ void __launch_bounds__(FP_THREADS, 2) k_fibre_pass_fast(const __grid_
         const i64 per_tile = (i64)nsrc << tk.pk;
         const i64 step = (tk.inner == 1) ? (i64)(FP_THREADS >> (kind == FP_GA ? 2 : 3))
                                          : (i64)(FP_THREADS >> ((kind == FP_GA ? 2 : 3) + tk.pk)) * tk.inner;
-        simple = tk.n == npad && (i64)(tile + 1) * per_tile <= tk.nfib && step * 16 < ((i64)1 << 31);
+        const int ds = (tk.inner == 1) ? (FP_THREADS >> (kind == FP_GA ? 2 : 3)) : (FP_THREADS >> ((kind == FP_GA ? 2 : 3) + tk.pk));
+        simple = tk.n == npad && (i64)(tile + 1) * per_tile <= tk.nfib && step * 16 < ((i64)1 << 31) && (ds & 15) == 0 &&
+                 (kind != FP_GA || tk.inner == 1);
     }
-    if (simple) ff_pass_body<T, true>(P, tk, tile, smraw, red);
-    else ff_pass_body<T, false>(P, tk, tile, smraw, red);
+    // live elements per thread: 512 / ds = 8 for the GA kind (4 source rows, contiguous), 16 otherwise
+    if (simple && kind == FP_GA) ff_pass_body<T, true, 8>(P, tk, tile, smraw, red);
+    else if (simple) ff_pass_body<T, true, 16>(P, tk, tile, smraw, red);
+    else ff_pass_body<T, false, 16>(P, tk, tile, smraw, red);
 }
 
 // Deterministic mode: sum the per-CTA partials of the pass that just ran, tiles in order, into the accumulators the atomics
