@@ -94,6 +94,12 @@ int vggp_plan_create(vggp_plan** out, int family, int D, const int* n_knots,
                      const float* const* knots_host, int obs_dtype, int device);
 int vggp_plan_destroy(vggp_plan* plan);
 
+/* Device memory behind a plan: `plan_bytes` = everything vggp_plan_create allocated (factors, work
+ * tensors, tables: the callee never allocates in a step), `gbuf_bytes` = the caller-owned gradient buffer a step needs
+ * (= vggp_gbuf_layout total), `scratch_bytes` = what the opt-in paths have grown so far (plain-array staging of
+ * vggp_obs_fwd_bwd / vggp_elbo_host, deterministic mode, B0 scan tables).  Any output pointer may be null. */
+int vggp_workspace_bytes(const vggp_plan* plan, int64_t* plan_bytes, int64_t* gbuf_bytes, int64_t* scratch_bytes);
+
 /* M_d (inducing variables per dimension) and M = prod M_d. */
 int vggp_plan_dims(const vggp_plan* plan, int* D, int* m_per_dim /*[D]*/, int64_t* M);
 

@@ -641,3 +641,25 @@ def test_deterministic_mode_matches_oracle_under_emulation(emu, knots, N, dtype,
             assert relerr(u, torch.from_numpy(np.asarray(v, dtype=np.float64))) < tol * 10
     finally:
         plan.close()
+
+
+def test_workspace_bytes_under_emulation(emu):
+    """vggp_workspace_bytes (include/vggp.h): the plan-owned memory is fixed at creation, the gradient
+    buffer size equals vggp_gbuf_layout's, and the scratch figure grows when an opt-in path (here the plain-array entry point)
+    stages observations."""
+    lib, L = emu
+    meshes, X, y, l, s2, noise, m, Ls = make_problem((9, 7), 300, seed=3)
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, [t.numpy() for t in meshes], np.float32)
+    try:
+        a, b, c = emul_lib.C.c_int64(), emul_lib.C.c_int64(), emul_lib.C.c_int64()
+        plan.check(lib.vggp_workspace_bytes(plan.h, emul_lib.C.byref(a), emul_lib.C.byref(b), emul_lib.C.byref(c)))
+        assert a.value > 8 * plan.M and b.value == plan.gbuf_bytes and c.value == 0
+        theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+        xs = [np.ascontiguousarray(X[:, d].numpy().astype(np.float32)) for d in range(2)]
+        plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(), xs, y.numpy().astype(np.float32))
+        a2, c2 = emul_lib.C.c_int64(), emul_lib.C.c_int64()
+        plan.check(lib.vggp_workspace_bytes(plan.h, emul_lib.C.byref(a2), None, emul_lib.C.byref(c2)))
+        assert a2.value == a.value and c2.value >= 300 * 4 * 3
+        assert lib.vggp_workspace_bytes(None, None, None, None) == -1
+    finally:
+        plan.close()

@@ -51,6 +51,7 @@ SIGNATURES = {
     "vggp_obs_fwd_bwd_binned": (C.c_int, [_vp, C.POINTER(BinnedDesc), _dp, _dp, _vp]),
     "vggp_set_binned_stream": (C.c_int, [C.c_int]),
     "vggp_set_deterministic": (C.c_int, [_vp, C.c_int]),
+    "vggp_workspace_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vggp_grid_backward": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _vp]),
     "vggp_read_info": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),
     "vggp_info_async": (C.c_int, [_vp, _vp, _vp]),

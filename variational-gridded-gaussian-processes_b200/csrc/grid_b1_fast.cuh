@@ -110,14 +110,14 @@ __device__ __forceinline__ void ff_band_dots(const double* __restrict__ Y, const
     }
     if (!packed) return;
     __syncthreads();
-    for (int e = threadIdx.x; e < 3 * n; e += FP_THREADS) {
-        const int k = e / n, i = e - k * n;
-        double v = 0.0;
-        for (int w = 0; w < 512; w += mask + 1) v += scr[k * 512 + w + i];
-        if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
-        if (det) det[FP_DET_BAND + k * 512 + i] = v;
-        else atomicAdd(acc + k * n + i, v);
-    }
+    for (int k = 0; k < 3; ++k)
+        for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+            if ((k == 0 && i == 0) || (k == 2 && i + 1 >= n)) continue;
+            double v = 0.0;
+            for (int w = 0; w < 512; w += mask + 1) v += scr[k * 512 + w + i];
+            if (det) det[FP_DET_BAND + k * 512 + i] = v;
+            else atomicAdd(acc + k * n + i, v);
+        }
 }
 
 // SIMPLE: every slot of the tile is a live element -- n fills its window exactly (n == npad: 64, 128, 256, 512) and the tile

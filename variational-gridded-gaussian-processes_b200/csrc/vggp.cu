@@ -129,6 +129,7 @@ struct vggp_plan {
     cudaStream_t last_stream = nullptr;                  // stream of the last grid forward (on-demand workspace fills)
     // deterministic mode (vggp_set_deterministic): run records + sort scratch of the per-observation kernel, per-CTA partials
     // of the fibre passes; both grown on demand (the first deterministic step must not run inside a stream capture)
+    size_t alloc_bytes = 0;                // device memory taken at plan creation (vggp_workspace_bytes)
     int det = 0;
     void* det_buf = nullptr; size_t det_bytes = 0;
     double* det_fp = nullptr; size_t det_fp_elems = 0;
@@ -163,6 +164,7 @@ int dev_alloc(vggp_plan* p, T** out, i64 count) {
     VGGP_CUDA(cudaMalloc(&ptr, (size_t)count * sizeof(T)));
     VGGP_CUDA(cudaMemset(ptr, 0, (size_t)count * sizeof(T)));
     p->allocs.push_back(ptr);
+    p->alloc_bytes += (size_t)count * sizeof(T);
     *out = reinterpret_cast<T*>(ptr);
     return 0;
 }
@@ -1865,6 +1867,21 @@ int vggp_set_gemm_mode(int use_mma) {
 
 int vggp_set_binned_stream(int mode) {
     g_bin_stream = mode ? 1 : 0;
+    return 0;
+}
+
+int vggp_workspace_bytes(const vggp_plan* p, int64_t* plan_bytes, int64_t* gbuf_bytes, int64_t* scratch_bytes) {
+    if (!p) return fail(VGGP_E_ARG, "null plan");
+    i64 n_elems, soff, nsc, total;
+    vggp_gbuf_layout(p, &n_elems, &soff, &nsc, &total);
+    if (plan_bytes) *plan_bytes = (int64_t)p->alloc_bytes;
+    if (gbuf_bytes) *gbuf_bytes = total;
+    if (scratch_bytes) {
+        const size_t tsz = p->obs_dtype == VGGP_F32 ? 4 : 8;
+        size_t sc = p->det_bytes + p->det_fp_elems * sizeof(double) + (size_t)p->pk_cap * tsz * (p->D + 1) + (size_t)p->b0s_raw_bytes;
+        if (p->st_x) sc += (size_t)p->st_n * tsz * (p->D + 1) + sizeof(double) * (2 * (size_t)p->M + 2 * (size_t)p->Lsize) + (size_t)total;
+        *scratch_bytes = (int64_t)sc;
+    }
     return 0;
 }
 

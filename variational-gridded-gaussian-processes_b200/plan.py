@@ -294,6 +294,12 @@ class GridPlan:
                 gs.outs = self.grid_backward(theta, m, L, ell_scale)
         return gs
 
+    def workspace_bytes(self) -> dict:
+        """Device memory behind the plan (vggp_workspace_bytes): plan-owned, the caller-owned gradient buffer, opt-in scratch."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.vggp_workspace_bytes(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {"plan": int(a.value), "gbuf": int(b.value), "scratch": int(c.value)}
+
     def set_deterministic(self, on: bool = True):
         """Bitwise run-to-run reproducible steps (vggp_set_deterministic): B1 family, binned layout, M_d <= 512."""
         _lib.check(self.lib.vggp_set_deterministic(self.handle, 1 if on else 0))
