@@ -457,3 +457,37 @@ def test_gridded_part_dense_matrices_asvgp(host, monkeypatch):
     assert relerr(q1.mean, Kvu1 @ torch.linalg.solve(Sig1, Kuf1 @ y1) / n1) < 1e-7
     cov1 = m1._Kvv() - Kvu1 @ torch.linalg.solve(Kuu1, Kvu1.T) + Kvu1 @ torch.linalg.solve(Sig1, Kvu1.T)
     assert relerr(q1.covariance_matrix, cov1) < 1e-6
+
+
+def test_model_level_deterministic_mode_over_the_emulator(host, monkeypatch):
+    """GriddedVariationalGP.set_deterministic (vggp_set_deterministic): same ELBO and raw-parameter gradients as the atomics path
+    to rounding, identical bits from two evaluations, and a clear error for a family the mode does not cover."""
+    gmod = _patched_models(host, monkeypatch)
+    gks = importlib.import_module(PKG + ".models.sparse.gridded_kronecker_structure")
+    monkeypatch.setenv("VGGP_OBS_LAYOUT", "binned")
+    g = torch.Generator().manual_seed(1)
+    N = 500
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64)
+    y = torch.sin(5 * X[:, 0]) + torch.cos(7 * X[:, 1]) + 0.05 * torch.randn(N, generator=g, dtype=torch.float64)
+    model = gks.GriddedMatern12ASVGP(X, y, 6, 1, (0, 1), (0, 1)).to(torch.float64)
+    with torch.no_grad():
+        model.variational_mean.normal_(0, 0.1)
+
+    def value_and_grads():
+        for q in model.parameters():
+            q.grad = None
+        e = model._elbo()
+        (-e).backward()
+        return [e.detach().clone()] + [q.grad.detach().clone() for q in model.parameters()]
+
+    plain = value_and_grads()
+    model.set_deterministic(True)
+    a, b = value_and_grads(), value_and_grads()
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    for u, v in zip(a, plain):
+        assert torch.allclose(u, v, rtol=1e-9, atol=1e-12)
+    model.set_deterministic(False)
+    other = gks.Matern12GriddedGP(X, y, 7, (0, 1), (0, 1)).to(torch.float64)
+    with pytest.raises(RuntimeError):
+        other.set_deterministic(True)

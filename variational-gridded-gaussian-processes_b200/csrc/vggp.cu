@@ -672,8 +672,9 @@ int fp_launch(vggp_plan* p, FpPass& P, cudaStream_t st) {
     if (p->det) {
         if (!fast) return fail(VGGP_E_UNSUPPORTED, "deterministic mode needs the fast fibre engine (M_d <= 512)");
         void* buf = p->det_fp; size_t have = p->det_fp_elems * sizeof(double);
-        if (int rc = det_reserve(&buf, &have, (size_t)tiles * FP_DET_SLOT * sizeof(double), st)) { p->det_fp = nullptr; p->det_fp_elems = 0; return rc; }
-        p->det_fp = reinterpret_cast<double*>(buf); p->det_fp_elems = have / sizeof(double);
+        const int rc = det_reserve(&buf, &have, (size_t)tiles * FP_DET_SLOT * sizeof(double), st);
+        p->det_fp = reinterpret_cast<double*>(buf); p->det_fp_elems = have / sizeof(double);      // whatever det_reserve left behind
+        if (rc) return rc;
         P.det = p->det_fp;
     }
     if (fast) {

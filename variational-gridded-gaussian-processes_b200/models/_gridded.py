@@ -141,6 +141,11 @@ class GriddedVariationalGP(nn.Module):
                 f"the per-dimension factor K_{flag} = Kuu along dimension {flag} is not positive definite at the current "
                 "hyper-parameters (Cholesky / pivot recurrence failed); the ELBO of that step is invalid")
 
+    def set_deterministic(self, on: bool = True) -> None:
+        """Bitwise run-to-run reproducible `_elbo()` values and gradients (vggp_set_deterministic; B1 family over the default
+        binned layout, full batch).  The reference is deterministic only because it is single-threaded CPU code."""
+        self._ensure_plan().set_deterministic(on)
+
     def check_factorisation(self) -> None:
         """Synchronise and raise torch.linalg.LinAlgError if the last `_elbo()` hit a non-positive-definite factor."""
         self._raise_if_failed(wait=True)
