@@ -116,6 +116,7 @@ unsigned long long yields();
 
 inline void __syncthreads() { cuda_emul::sync_block(); }
 inline void __syncwarp(unsigned int = 0xffffffffu) { cuda_emul::sync_warp(); }
+inline void __threadfence() { cuda_emul::yield(); }      // memory is sequentially consistent here; a fence is a scheduling point
 
 template <typename T>
 inline T __shfl_sync(unsigned int, T v, int src) {

@@ -663,3 +663,45 @@ def test_workspace_bytes_under_emulation(emu):
         assert lib.vggp_workspace_bytes(None, None, None, None) == -1
     finally:
         plan.close()
+
+
+def test_splitk_fixup_mode_product_under_emulation(emu):
+    """A group with fewer tiles than SMs is cut along k; the partial tiles meet in a workspace and the last CTA of a tile adds
+    them in split order (gemm.cuh gemm_fixup) -- no destination clear, no float64 atomics.  vggp_mode_product on a 140-knot
+    dimension (3 x 3 tiles, k = 139 -> two splits) against numpy, twice (the tile counters return to zero), into a destination
+    full of NaNs (nothing may be accumulated into it), and the dense-path step with both forms of the split."""
+    lib, L = emu
+    meshes = [np.linspace(0, 1, 140, dtype=np.float32), np.linspace(0, 1, 9, dtype=np.float32)]
+    plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, meshes, np.float64)
+    try:
+        n0, n1 = plan.m_per_dim
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((n0, n0))
+        src = rng.standard_normal((n0, n1))
+        for _ in range(2):
+            dst = np.full((n0, n1), np.nan)
+            plan.check(lib.vggp_mode_product(plan.h, 0, emul_lib.ptr(A), emul_lib.ptr(src), emul_lib.ptr(dst), None))
+            ref = A @ src if np.allclose(dst, A @ src, rtol=1e-12, atol=1e-12) else A.T @ src
+            assert np.allclose(dst, ref, rtol=1e-12, atol=1e-12)
+    finally:
+        plan.close()
+    knots, N = (140, 7), 600
+    meshes_t, X, y, l, s2, noise, m, Ls = make_problem(knots, N, seed=21, family=O.B0_GRIDDED)
+    l = torch.tensor([0.03, 0.3], dtype=torch.float64)      # l / delta small enough for the float32-rounded Toeplitz row to stay PD
+    elbo_ref, g_ref = oracle_value_and_grads(O.B0_GRIDDED, meshes_t, X, y, l, s2, noise, m, Ls, scale=1.2)
+    res = []
+    for fix in (1, 0):
+        lib.vggp_debug_splitk_fixup(fix)
+        try:
+            plan = emul_lib.EmuPlan(lib, L, L.B0_GRIDDED, [t.numpy() for t in meshes_t], np.float64)
+            theta = torch.cat([l, s2, noise.reshape(1)]).numpy().copy()
+            xs = [np.ascontiguousarray(X[:, d].numpy()) for d in range(2)]
+            res.append(plan.step(theta, m.numpy().copy(), torch.cat([Lx.reshape(-1) for Lx in Ls]).numpy().copy(),
+                                 xs, y.numpy().copy(), 1.2))
+            if fix:
+                check_against_oracle(plan, *res[-1], elbo_ref, g_ref, N, 1e-7)
+            plan.close()
+        finally:
+            lib.vggp_debug_splitk_fixup(1)
+    for a, b in zip(res[0], res[1]):
+        assert relerr(a, torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-9

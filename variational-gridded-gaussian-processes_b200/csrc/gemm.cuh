@@ -29,6 +29,11 @@ struct GemmDesc {
     int a_kcontig, b_ncontig, a_vec2, b_vec2;
     int zstart;          // first blockIdx.z of this problem (filled by gemm_finalize_group)
     int tiles_m, tiles_n;
+    // k-split without atomics (automatic splits): every CTA parks its 64 x 64 partial in `ws`, the last one to arrive at a tile
+    // (counter `cnt`, left at zero again) adds the partials in split order and stores alpha * sum + beta * C.  No destination
+    // clear, no float64 atomics, and the result does not depend on the arrival order.  Null: the atomic form above.
+    double* ws;          // [batch][tiles_m][tiles_n][splitk][16][256]
+    int* cnt;            // [batch][tiles_m][tiles_n]
 };
 
 constexpr int GBM = 64, GBN = 64, GBK = 16;
@@ -55,6 +60,40 @@ __device__ __forceinline__ void gemm_store(const GemmDesc& d, double* __restrict
     }
 }
 
+// Fix-up of a k-split tile (see GemmDesc::ws): v[16] = this thread's accumulators in a fixed enumeration.  Returns false for
+// every CTA but the last one of the tile, which leaves with v = sum over the splits in split order.
+__device__ __forceinline__ bool gemm_fixup(const GemmDesc& d, int b, int tile_m, int tile_n, int split, double (&v)[16]) {
+    __shared__ int last;
+    const int tid = threadIdx.x;
+    const i64 tile_lin = ((i64)b * d.tiles_m + tile_m) * d.tiles_n + tile_n;
+    double* base = d.ws + tile_lin * d.splitk * 4096;
+    double* slot = base + (i64)split * 4096;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) slot[i * 256 + tid] = v[i];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(d.cnt + tile_lin, 1) == d.splitk - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0;
+    for (int sp = 0; sp < d.splitk; ++sp) {
+        const volatile double* q = base + (i64)sp * 4096;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += q[i * 256 + tid];
+    }
+    if (tid == 0) d.cnt[tile_lin] = 0;
+    return true;
+}
+__device__ __forceinline__ void gemm_store_plain(const GemmDesc& d, double* __restrict__ Cb, int row, int col, double v) {
+    if (row >= d.m || col >= d.n) return;
+    double* p = Cb + (i64)row * d.rsC + (i64)col * d.csC;
+    double r = d.alpha * v;
+    if (d.beta != 0.0) r += d.beta * (*p);
+    *p = r;
+}
+
 template <bool MMA>
 __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As)[GBK + 4], double (*Bs)[GBN + 4]) {
     const int tid = threadIdx.x;
@@ -70,11 +109,11 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
         const int kchunk = ((d.k + d.splitk - 1) / d.splitk + GBK - 1) / GBK * GBK;
         kbeg = split * kchunk;
         kend = min(d.k, kbeg + kchunk);
-        if (kbeg >= kend) return;
+        if (kbeg >= kend) { if (!d.ws) return; kbeg = kend; }     // fix-up form: every split of a tile must arrive
     }
     if (d.tri_b == 1) kbeg = max(kbeg, n0 / GBK * GBK);          // triangular operand: skip the all-zero k range
     if (d.tri_b == 2) kend = min(kend, n0 + GBN);
-    if (kbeg >= kend && d.splitk > 1) return;
+    if (kbeg >= kend && d.splitk > 1) { if (!d.ws) return; kbeg = kend; }
     const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
     const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
     double* __restrict__ Cb = d.C + (i64)b * d.bsC;
@@ -149,6 +188,21 @@ __device__ __forceinline__ void gemm_body(const GemmDesc& d, int zz, double (*As
         __syncthreads();
     }
 
+    if (d.ws && d.splitk > 1) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if constexpr (MMA) v[i] = acc[i >> 2][(i >> 1) & 1][i & 1];
+            else v[i] = acc[i >> 2][i & 3][0];
+        }
+        if (!gemm_fixup(d, b, tile_m, tile_n, split, v)) return;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (MMA) gemm_store_plain(d, Cb, m0 + wm + (i >> 2) * 8 + g, n0 + wn + ((i >> 1) & 1) * 8 + t * 2 + (i & 1), v[i]);
+            else gemm_store_plain(d, Cb, m0 + ty * 4 + (i >> 2), n0 + tx * 4 + (i & 3), v[i]);
+        }
+        return;
+    }
     if constexpr (MMA) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -311,11 +365,11 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         const int kchunk = ((d.k + d.splitk - 1) / d.splitk + GBK - 1) / GBK * GBK;
         kbeg = split * kchunk;
         kend = min(d.k, kbeg + kchunk);
-        if (kbeg >= kend) return;
+        if (kbeg >= kend) { if (!d.ws) return; kbeg = kend; }     // fix-up form: every split of a tile must arrive
     }
     if (d.tri_b == 1) kbeg = max(kbeg, n0 / GBK * GBK);          // triangular operand: skip the all-zero k range
     if (d.tri_b == 2) kend = min(kend, n0 + GBN);
-    if (kbeg >= kend && d.splitk > 1) return;
+    if (kbeg >= kend && d.splitk > 1) { if (!d.ws) return; kbeg = kend; }
     const double* __restrict__ Ab = d.A + (i64)b * d.bsA;
     const double* __restrict__ Bb = d.B + (i64)b * d.bsB;
     double* __restrict__ Cb = d.C + (i64)b * d.bsC;
@@ -402,6 +456,16 @@ __device__ __forceinline__ void gemm_fast_body(const GemmDesc& d, int zz, double
         }
     }
     cp_async_wait<0>();
+    if (d.ws && d.splitk > 1) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = acc[i >> 2][(i >> 1) & 1][i & 1];
+        if (!gemm_fixup(d, b, tile_m, tile_n, split, v)) return;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            gemm_store_plain(d, Cb, m0 + wm + (i >> 2) * 8 + g, n0 + wn + ((i >> 1) & 1) * 8 + t * 2 + (i & 1), v[i]);
+        return;
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -461,6 +525,8 @@ inline void gemm_desc_defaults(GemmDesc& d) {
     d.beta = 0.0;
     d.batch = 1;
     d.splitk = 1;
+    d.ws = nullptr;
+    d.cnt = nullptr;
 }
 
 // Fill the derived fields of a group of descriptors (zstart, tile counts, coalescing hints).

@@ -130,6 +130,8 @@ struct vggp_plan {
     // deterministic mode (vggp_set_deterministic): run records + sort scratch of the per-observation kernel, per-CTA partials
     // of the fibre passes; both grown on demand (the first deterministic step must not run inside a stream capture)
     size_t alloc_bytes = 0;                // device memory taken at plan creation (vggp_workspace_bytes)
+    void* one_ws = nullptr; size_t one_ws_bytes = 0;      // fix-up workspace of ad-hoc k-split products (vggp_mode_product)
+    double* phase_ws = nullptr; int* phase_cnt = nullptr; // fix-up workspace shared by the scheduled GEMM groups (make_phase)
     int det = 0;
     void* det_buf = nullptr; size_t det_bytes = 0;
     double* det_fp = nullptr; size_t det_fp_elems = 0;
@@ -173,26 +175,28 @@ int dev_alloc(vggp_plan* p, T** out, i64 count) {
 // is cut along k so that about two CTAs land on every SM: partial sums go through float64 atomics into a destination that
 // already holds beta * C (beta = 1: nothing to do; beta = 0: zero-filled by a cudaMemset2DAsync queued before the launch).
 int g_auto_splitk = 1;
-void auto_splitk(std::vector<GemmDesc>& descs, std::vector<ZeroJob>& zero) {
+int g_splitk_fixup = 1;       // 1: automatic splits use the workspace fix-up (no destination clear, no atomics); 0: the atomic form
+// returns the split factor applied to every descriptor of the group (1: none).  `zero`: destinations the atomic form must clear.
+int auto_splitk(std::vector<GemmDesc>& descs, std::vector<ZeroJob>& zero, bool fixup) {
     zero.clear();
-    if (!g_auto_splitk) return;
+    if (!g_auto_splitk) return 1;
     i64 ctas = 0;
     int kmin = 1 << 30;
     for (const GemmDesc& d : descs) {
         const i64 tm = (d.m + GBM - 1) / GBM, tn = (d.n + GBN - 1) / GBN;
         ctas += (d.lower_only ? (tm * (tm + 1)) / 2 : tm * tn) * std::max(1, d.batch) * std::max(1, d.splitk);
         kmin = std::min(kmin, d.tri_b ? d.k / 2 : d.k);
-        if (d.splitk > 1 || d.kinner != 0) return;
-        if (!(d.beta == 0.0 || d.beta == 1.0)) return;
-        if (d.beta == 0.0 && !(d.csC == 1 || d.rsC == 1)) return;
+        if (d.splitk > 1 || d.kinner != 0) return 1;
+        if (!fixup && !(d.beta == 0.0 || d.beta == 1.0)) return 1;
+        if (!fixup && d.beta == 0.0 && !(d.csC == 1 || d.rsC == 1)) return 1;
     }
-    if (ctas <= 0 || ctas >= 148) return;
+    if (ctas <= 0 || ctas >= 148) return 1;
     int sk = (int)std::min<i64>(4, (2 * 148) / ctas);
     while (sk > 1 && kmin / sk < 4 * GBK) --sk;
-    if (sk <= 1) return;
+    if (sk <= 1) return 1;
     for (GemmDesc& d : descs) {
         d.splitk = sk;
-        if (d.beta != 0.0) continue;
+        if (fixup || d.beta != 0.0) continue;
         for (int b = 0; b < std::max(1, d.batch); ++b) {
             ZeroJob z;
             z.ptr = d.C + (i64)b * d.bsC;
@@ -201,14 +205,44 @@ void auto_splitk(std::vector<GemmDesc>& descs, std::vector<ZeroJob>& zero) {
             zero.push_back(z);
         }
     }
+    return sk;
+}
+// workspace of the fix-up form for one descriptor: partial tiles (doubles) and tile counters
+inline void splitk_ws_size(const GemmDesc& d, i64* ws_elems, i64* n_cnt) {
+    const i64 tiles = (i64)((d.m + GBM - 1) / GBM) * ((d.n + GBN - 1) / GBN) * std::max(1, d.batch);
+    *ws_elems = tiles * d.splitk * 4096;
+    *n_cnt = tiles;
 }
 
 int make_phase(vggp_plan* p, std::vector<GemmDesc>& descs, Phase& ph) {
     ph.ndesc = (int)descs.size();
     if (ph.ndesc == 0) return 0;
-    auto_splitk(descs, ph.zero);
+    const bool fixup = g_splitk_fixup != 0;
+    const int sk = auto_splitk(descs, ph.zero, fixup);
+    int rc;
+    if (sk > 1 && fixup) {
+        // One workspace for every phase of the plan: launches are stream-ordered and a launch consumes its partials before it
+        // ends; an automatically split group has fewer than 148 computed tiles and at most 2 x 148 computed partial tiles
+        // (auto_splitk); the workspace is indexed by the full tile grid, at most twice that for lower-triangular outputs.  The
+        // counters start at zero (dev_alloc) and return to zero after every launch.
+        constexpr i64 WS_TILES = 4 * 148 + 16, WS_CNT = 2 * 148 + 8;
+        if (!p->phase_ws) {
+            if ((rc = dev_alloc(p, &p->phase_ws, WS_TILES * 4096))) return rc;
+            if ((rc = dev_alloc(p, &p->phase_cnt, WS_CNT))) return rc;
+        }
+        i64 woff = 0, coff = 0;
+        for (GemmDesc& d : descs) {
+            i64 we, nc;
+            splitk_ws_size(d, &we, &nc);
+            if (woff + we > WS_TILES * 4096 || coff + nc > WS_CNT) return fail(VGGP_E_NOMEM, "k-split workspace too small for this group");
+            d.ws = p->phase_ws + woff;
+            d.cnt = p->phase_cnt + coff;
+            woff += we;
+            coff += nc;
+        }
+    }
     ph.dims = gemm_finalize_group(descs.data(), ph.ndesc);
-    int rc = dev_alloc(p, &ph.d_descs, ph.ndesc);
+    rc = dev_alloc(p, &ph.d_descs, ph.ndesc);
     if (rc) return rc;
     VGGP_CUDA(cudaMemcpy(ph.d_descs, descs.data(), sizeof(GemmDesc) * ph.ndesc, cudaMemcpyHostToDevice));
     return 0;
@@ -229,11 +263,29 @@ int launch_phase(const Phase& ph, cudaStream_t st) {
     return 0;
 }
 
-int launch_one(GemmDesc d, int use_mma, cudaStream_t st) {
+int det_reserve(void** buf, size_t* have, size_t want, cudaStream_t st);
+// `p` (may be null): the plan whose grow-only scratch holds the fix-up workspace of an automatic k-split; without a plan the
+// split uses the atomic form.
+int launch_one(GemmDesc d, int use_mma, cudaStream_t st, vggp_plan* p = nullptr) {
     if (d.m <= 0 || d.n <= 0) return 0;
     std::vector<GemmDesc> one(1, d);
     std::vector<ZeroJob> zero;
-    if (d.splitk <= 1) auto_splitk(one, zero);
+    const bool fixup = p != nullptr && g_splitk_fixup != 0;
+    if (d.splitk <= 1) {
+        const int sk = auto_splitk(one, zero, fixup);
+        if (sk > 1 && fixup) {
+            i64 we, nc;
+            splitk_ws_size(one[0], &we, &nc);
+            const size_t cnt_off = ((size_t)we * sizeof(double) + 255) / 256 * 256;
+            const size_t want = cnt_off + (size_t)nc * sizeof(int);
+            if (p->one_ws_bytes < want) {          // grown: the counters start at zero (and return to zero after every launch)
+                if (int rc = det_reserve(&p->one_ws, &p->one_ws_bytes, want, st)) return rc;
+                VGGP_CUDA(cudaMemsetAsync(p->one_ws, 0, p->one_ws_bytes, st));
+            }
+            one[0].ws = reinterpret_cast<double*>(p->one_ws);
+            one[0].cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(p->one_ws) + cnt_off);
+        }
+    }
     d = one[0];
     GemmGroupDims dims = gemm_finalize_group(&d, 1);
     for (const ZeroJob& z : zero) VGGP_CUDA(cudaMemset2DAsync(z.ptr, z.pitch, 0, z.width, z.height, st));
@@ -2086,6 +2138,7 @@ int vggp_plan_destroy(vggp_plan* p) {
     if (p->pk_y) cudaFree(p->pk_y);
     if (p->bin_perm) cudaFree(p->bin_perm);
     if (p->det_buf) cudaFree(p->det_buf);
+    if (p->one_ws) cudaFree(p->one_ws);
     if (p->det_fp) cudaFree(p->det_fp);
     for (auto& e : p->k1_ev) cudaEventDestroy(e);
     for (auto& e : p->k1_gev) if (e) cudaEventDestroy(e);
@@ -2473,6 +2526,9 @@ int vggp_debug_fp_stamps(long long* buf) { g_fp_dbg = buf; return 0; }
 int vggp_debug_b0s_seg(int on) { g_b0s_seg = on ? 1 : 0; return 0; }
 /* debugging aid: 0 = never cut a small GEMM group along k (plans created afterwards), 1 = default */
 int vggp_debug_auto_splitk(int on) { g_auto_splitk = on ? 1 : 0; return 0; }
+/* debugging aid: how an automatic k-split combines its partial sums in plans created afterwards: 1 (default) workspace fix-up by
+ * the last CTA of a tile (deterministic, no destination clear), 0 float64 atomics into a cleared destination */
+int vggp_debug_splitk_fixup(int on) { g_splitk_fixup = on ? 1 : 0; return 0; }
 /* debugging aid: observations per host-to-device chunk of vggp_elbo_host (default 2^23; tests use small values) */
 int vggp_debug_host_chunk(long long n) { g_host_chunk = n > 4 ? n : 4; return 0; }
 int vggp_debug_fp_fast(int on) { g_fp_fast = (on & 1); g_fp_pack = (on & 2) ? 0 : ((on & 4) ? 2 : 1); return 0; }
@@ -2781,7 +2837,7 @@ int vggp_gemm_f64(int use_mma, int batch, int m, int n, int k, double alpha, con
 int vggp_mode_product(vggp_plan* p, int dim, const double* A, const double* src, double* dst, void* stream) {
     DeviceGuard dev_guard(p ? p->device : -1);
     if (!p || !A || !src || !dst || dim < 0 || dim >= p->D) return fail(VGGP_E_ARG, "bad argument");
-    return launch_one(mode_desc(p, dim, A, src, dst), g_use_mma, (cudaStream_t)stream);
+    return launch_one(mode_desc(p, dim, A, src, dst), g_use_mma, (cudaStream_t)stream, p);
 }
 
 }  // extern "C"
