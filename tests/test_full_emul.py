@@ -705,3 +705,30 @@ def test_splitk_fixup_mode_product_under_emulation(emu):
             lib.vggp_debug_splitk_fixup(1)
     for a, b in zip(res[0], res[1]):
         assert relerr(a, torch.from_numpy(np.asarray(b, dtype=np.float64))) < 1e-9
+
+
+def test_deterministic_mode_edge_cases_under_emulation(emu):
+    """Deterministic mode on an empty shard and on a shard with every observation outside the mesh (no run at all): same
+    results as the plain-array path."""
+    lib, L = emu
+    meshes = [np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 7, dtype=np.float32)]
+    plan = emul_lib.EmuPlan(lib, L, L.B1_ASVGP, meshes, np.float64)
+    try:
+        rng = np.random.default_rng(0)
+        theta = np.array([0.3, 0.4, 1.0, 0.9, 0.05])
+        m = 0.1 * rng.standard_normal(63)
+        Lcat = np.concatenate([np.eye(n).reshape(-1) for n in (9, 7)])
+        empty = [np.zeros(0), np.zeros(0)]
+        xo = [np.full(50, 3.0), rng.random(50)]
+        yo = rng.standard_normal(50)
+        ref_e = plan.step(theta, m, Lcat, empty, np.zeros(0), 1.0)
+        ref_o = plan.step(theta, m, Lcat, xo, yo, 1.0)
+        b_e, b_o = plan.bin(empty, np.zeros(0)), plan.bin(xo, yo)
+        assert b_o[2].n_tasks == 0
+        plan.check(lib.vggp_set_deterministic(plan.h, 1))
+        for obs, ref in ((b_e, ref_e), (b_o, ref_o)):
+            got = plan.step(theta, m, Lcat, obs, None, 1.0)
+            for u, v in zip(got, ref):
+                assert np.allclose(u, v, rtol=1e-10, atol=1e-12)
+    finally:
+        plan.close()

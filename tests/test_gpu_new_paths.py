@@ -406,3 +406,25 @@ def test_deterministic_mode_refuses_other_families(vg, dev):
     plan = vg.GridPlan(vg.B0_GRIDDED, meshes, torch.float64, dev)
     with pytest.raises(RuntimeError):
         plan.set_deterministic(True)
+
+
+def test_deterministic_mode_empty_and_all_outside(vg, dev):
+    """Deterministic mode on an empty shard and on one whose observations all lie outside the mesh (no run, no record)."""
+    meshes = [torch.linspace(0, 1, 9), torch.linspace(0, 1, 7)]
+    plan = vg.GridPlan(vg.B1_ASVGP, meshes, torch.float64, dev)
+    g = torch.Generator().manual_seed(0)
+    theta = torch.tensor([0.3, 0.4, 1.0, 0.9, 0.05], dtype=torch.float64, device=dev)
+    m = (0.1 * torch.randn(63, generator=g, dtype=torch.float64)).to(dev)
+    L = torch.cat([torch.eye(n, dtype=torch.float64).reshape(-1) for n in (9, 7)]).to(dev)
+    empty = [torch.zeros(0, dtype=torch.float64, device=dev)] * 2
+    xo = [torch.full((50,), 3.0, dtype=torch.float64, device=dev), torch.rand(50, generator=g, dtype=torch.float64).to(dev)]
+    yo = torch.randn(50, generator=g, dtype=torch.float64).to(dev)
+    ref_e = [t.clone() for t in plan.step(theta, m, L, empty, torch.zeros(0, dtype=torch.float64, device=dev))]
+    ref_o = [t.clone() for t in plan.step(theta, m, L, xo, yo)]
+    b_e, b_o = plan.bin(empty, torch.zeros(0, dtype=torch.float64, device=dev)), plan.bin(xo, yo)
+    assert b_o.n_tasks == 0
+    plan.set_deterministic(True)
+    for obs, ref in ((b_e, ref_e), (b_o, ref_o)):
+        got = plan.step(theta, m, L, obs, None)
+        for a, b in zip(got, ref):
+            assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)

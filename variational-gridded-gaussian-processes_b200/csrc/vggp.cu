@@ -1383,18 +1383,23 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
     k_obs_b1_binned_det<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a, rec);
     k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
-    k_det_keys<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, run_start, nslots, k0, i0);
-    VGGP_LAUNCH_CHECK();
-    VGGP_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, (const uint32_t*)k0, k1, (const uint32_t*)i0, i1, (int)nslots, 0, 32, st));
-    VGGP_CUDA(cudaMemsetAsync(cf, 0, (o_S - o_cf), st));
-    k_det_mark<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, i1, nslots, cf, ce);
-    VGGP_LAUNCH_CHECK();
-    DetIndex ix;
-    ix.sorted_slot = i1; ix.cell_first = cf; ix.cell_end = ce;
-    k_det_alpha<T, D><<<ceil_div(p->M, 256), 256, 0, st>>>(a.geo, ix, rec, a.galpha, p->M);
-    VGGP_LAUNCH_CHECK();
-    k_det_band<T, D><<<(unsigned)nplanes, 256, 0, st>>>(a.geo, ix, rec, S);
-    VGGP_LAUNCH_CHECK();
+    if (nslots > 0) {
+        k_det_keys<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, run_start, nslots, k0, i0);
+        VGGP_LAUNCH_CHECK();
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, (const uint32_t*)k0, k1, (const uint32_t*)i0, i1, (int)nslots, 0, 32, st));
+        VGGP_CUDA(cudaMemsetAsync(cf, 0, (o_S - o_cf), st));
+        k_det_mark<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, i1, nslots, cf, ce);
+        VGGP_LAUNCH_CHECK();
+        DetIndex ix;
+        ix.sorted_slot = i1; ix.cell_first = cf; ix.cell_end = ce;
+        k_det_alpha<T, D><<<ceil_div(p->M, 256), 256, 0, st>>>(a.geo, ix, rec, a.galpha, p->M);
+        VGGP_LAUNCH_CHECK();
+        k_det_band<T, D><<<(unsigned)nplanes, 256, 0, st>>>(a.geo, ix, rec, S);
+        VGGP_LAUNCH_CHECK();
+    } else {
+        // every observation outside the mesh: no run, no record; the band block and d alpha stay zero (gbuf was cleared)
+        VGGP_CUDA(cudaMemsetAsync(S, 0, sizeof(T) * 6 * (size_t)nplanes, st));
+    }
     k_det_escal<T, D><<<DET_EBLOCKS, 256, 0, st>>>(rec, run_cell, nslots, E);
     VGGP_LAUNCH_CHECK();
     k_det_final<T, D><<<1, 256, 0, st>>>(a.geo, S, E, a.gband, a.gs, a.buf, a.counter);
