@@ -446,10 +446,12 @@ __global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ F
                 const double* src = base + FP_DET_BAND + k * 512 + i;
                 double v = 0.0;
                 int t = 0;
-                for (; t + 4 <= tk.ntiles; t += 4) {        // four loads in flight, added in tile order
-                    const double a0 = src[(i64)t * FP_DET_SLOT], a1 = src[(i64)(t + 1) * FP_DET_SLOT];
-                    const double a2 = src[(i64)(t + 2) * FP_DET_SLOT], a3 = src[(i64)(t + 3) * FP_DET_SLOT];
-                    v += a0; v += a1; v += a2; v += a3;
+                for (; t + 16 <= tk.ntiles; t += 16) {      // sixteen loads in flight, added in tile order
+                    double q[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) q[u] = src[(i64)(t + u) * FP_DET_SLOT];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v += q[u];
                 }
                 for (; t < tk.ntiles; ++t) v += src[(i64)t * FP_DET_SLOT];
                 P.acc[d][e] += v;
@@ -463,12 +465,22 @@ __global__ void __launch_bounds__(256) k_fp_det_reduce(const __grid_constant__ F
                 P.sc[SC_MALPHA] += v;
             }
         } else if (kind == FP_QROW) {
-            if (threadIdx.x < 2) {
-                const int off = threadIdx.x == 0 ? FP_DET_TR : FP_DET_LOGDET;
-                double v = 0.0;
-                for (int i = 0; i < n; ++i) v += base[(i64)(i / FP_WARPS) * FP_DET_SLOT + off + (i % FP_WARPS)];
-                P.sc[(threadIdx.x == 0 ? SC_TR : SC_LOGDETS) + d] += v;
+            // rows i = t, t + 256, ... per thread, then a fixed-shape tree: the order depends on n only
+            __shared__ double sh[2][256];
+            double tr = 0.0, ld = 0.0;
+            for (int i = threadIdx.x; i < n; i += 256) {
+                const double* q = base + (i64)(i / FP_WARPS) * FP_DET_SLOT + (i % FP_WARPS);
+                tr += q[FP_DET_TR];
+                ld += q[FP_DET_LOGDET];
             }
+            sh[0][threadIdx.x] = tr; sh[1][threadIdx.x] = ld;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) { P.sc[SC_TR + d] += sh[0][0]; P.sc[SC_LOGDETS + d] += sh[1][0]; }
+            __syncthreads();
         }
     }
 }

@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(256) k_band_reduce(T* __restrict__ rep, int n_
 // Floating-point atomics make the sums above depend on the order in which warps finish.  In deterministic mode a run does
 // not add anything: it writes its flush values as a RECORD (in the fixed order of the `add` calls of bin_lane_flush, then the
 // run's scalar term), and the reductions below sum the records in an order that depends only on the binned layout -- runs
-// sorted by their position in the cell-sorted stream -- so that two launches over the same buffer agree bit for bit whatever
+// sorted by cell, slot order inside a cell -- so that two launches over the same buffer agree bit for bit whatever
 // the grid size, the work stealing or the machine load.
 template <int D> struct BinRec { static constexpr int v = (1 << D) + 6 * D + 1; };
 
@@ -593,12 +593,14 @@ k_obs_b1_binned_det(const __grid_constant__ BinnedArgs<T, D> a, T* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0) a.gs[1] = a.n_real;
 }
 
-// sort keys of the run slots: position of the run in the cell-sorted stream; empty slots go to the end
-__global__ void __launch_bounds__(256) k_det_keys(const uint32_t* __restrict__ run_cell, const uint32_t* __restrict__ run_start,
+// sort keys of the run slots: the cell of the run (a stable sort keeps the slot order inside a cell: an order fixed by the
+// layout); empty slots get the key `ncells` and go to the end
+__global__ void __launch_bounds__(256) k_det_keys(const uint32_t* __restrict__ run_cell, uint32_t ncells,
                                                   i64 nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
-    keys[i] = run_cell[i] != BIN_EMPTY ? run_start[i] : 0xffffffffu;
+    const uint32_t c = run_cell[i];
+    keys[i] = c != BIN_EMPTY ? c : ncells;
     idx[i] = (uint32_t)i;
 }
 

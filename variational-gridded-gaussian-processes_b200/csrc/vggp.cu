@@ -1327,10 +1327,13 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
     i64 ncells = 1, nplanes = 0;
     for (int d = 0; d < D; ++d) { ncells *= p->K[d] - 1; nplanes += p->K[d] - 1; }
     if (nslots >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "deterministic mode: too many runs");
+    if (ncells >= ((i64)1 << 31)) return fail(VGGP_E_UNSUPPORTED, "deterministic mode: too many cells");
+    int key_bits = 1;
+    while (((i64)1 << key_bits) <= ncells) ++key_bits;          // keys 0 .. ncells (ncells = empty slot)
     size_t temp_bytes = 0;
     {
         const uint32_t* k = nullptr; uint32_t* ko = nullptr;
-        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, k, ko, k, ko, (int)nslots, 0, 32, st));
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, k, ko, k, ko, (int)nslots, 0, key_bits, st));
     }
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t o_rec = 0, o_k0 = al(o_rec + sizeof(T) * (size_t)nslots * R), o_k1 = al(o_k0 + 4 * (size_t)nslots),
@@ -1378,15 +1381,14 @@ int launch_obs_binned_det(vggp_plan* p, const vggp_binned_desc* desc, const void
     i64 blocks = (desc->n_tasks + BIN_WARPS - 1) / BIN_WARPS;
     blocks = std::max<i64>(1, std::min<i64>(blocks, (i64)p->sm_count * p->bin_blocks_per_sm[0]));
     const uint32_t* run_cell = reinterpret_cast<const uint32_t*>(a.buf + desc->off_run_cell);
-    const uint32_t* run_start = reinterpret_cast<const uint32_t*>(a.buf + desc->off_run_start);
     k1_mark(p, 0, st);
     k_obs_b1_binned_det<T, D><<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a, rec);
     k1_mark(p, 1, st);
     VGGP_LAUNCH_CHECK();
     if (nslots > 0) {
-        k_det_keys<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, run_start, nslots, k0, i0);
+        k_det_keys<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, (uint32_t)ncells, nslots, k0, i0);
         VGGP_LAUNCH_CHECK();
-        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, (const uint32_t*)k0, k1, (const uint32_t*)i0, i1, (int)nslots, 0, 32, st));
+        VGGP_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, (const uint32_t*)k0, k1, (const uint32_t*)i0, i1, (int)nslots, 0, key_bits, st));
         VGGP_CUDA(cudaMemsetAsync(cf, 0, (o_S - o_cf), st));
         k_det_mark<<<ceil_div(nslots, 256), 256, 0, st>>>(run_cell, i1, nslots, cf, ce);
         VGGP_LAUNCH_CHECK();
