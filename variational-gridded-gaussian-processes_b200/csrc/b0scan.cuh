@@ -698,6 +698,17 @@ __global__ void __launch_bounds__(256) k_b0s_gather(const __grid_constant__ B0sG
     }
 }
 
+// exp of a non-positive argument in the per-observation loop: float32 observations take the hardware exponential
+// (ex2.approx: ~ 2 ulp, far inside the 1e-3 tolerance of float32 configurations), float64 the library function
+__device__ __forceinline__ double b0s_exp(double x) { return exp(x); }
+__device__ __forceinline__ float b0s_exp(float x) {
+#ifdef VGGP_EMUL
+    return expf(x);
+#else
+    return __expf(x);
+#endif
+}
+
 template <typename T, int D>
 struct B0sObsArgs {
     B0sPointTables<T, D> tab;
@@ -719,11 +730,12 @@ __global__ void __launch_bounds__(B0S_THREADS, (sizeof(T) == 4 ? 4 : 2)) k_obs_b
     constexpr int NT = D == 1 ? 3 : 9;
     const int lane = threadIdx.x & 31;
     double accE = 0.0, accGl[D], accGs[D];
-    T l[D], s2[D];
+    T l[D], s2[D], rl[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         accGl[d] = 0.0; accGs[d] = 0.0;
         l[d] = (T)a.tab.theta[d];
+        rl[d] = (T)(1.0 / a.tab.theta[d]);      // one reciprocal per kernel instead of two divisions per observation and dimension
         s2[d] = (T)a.tab.theta[D + d];
     }
     const i64 EE = D == 1 ? (i64)a.tab.E[0] : (i64)a.tab.E[0] * a.tab.E[D - 1];
@@ -789,8 +801,8 @@ __global__ void __launch_bounds__(B0S_THREADS, (sizeof(T) == 4 ? 4 : 2)) k_obs_b
                 T f[D][3], df[D][3];
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const T zL = (xg[d][j] - tc[d]) / l[d], zR = (tc1[d] - xg[d][j]) / l[d];
-                    const T eL = hasL[d] ? exp(-zL) : (T)0, eR = hasR[d] ? exp(-zR) : (T)0;
+                    const T zL = (xg[d][j] - tc[d]) * rl[d], zR = (tc1[d] - xg[d][j]) * rl[d];
+                    const T eL = hasL[d] ? b0s_exp(-zL) : (T)0, eR = hasR[d] ? b0s_exp(-zR) : (T)0;
                     const bool real = hasL[d] && hasR[d];
                     f[d][0] = s2[d] * l[d] * eL;
                     f[d][2] = s2[d] * l[d] * eR;
